@@ -1,0 +1,122 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference modules on CPU (fp32).
+
+Run in the build container only (needs /root/reference):  ``python -m oracle.make_golden``.
+The fixtures pin the oracle (tests/test_oracle_golden.py) and travel to the GPU box, where the
+reference itself does not exist.  Inputs are analytic (oracle/detgen.py), so only outputs are
+stored.  TEST INFRASTRUCTURE ONLY.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from . import detgen, ref_shim
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def golden_attention(ns, grid, batch, n_frames, n_ptr, tag, full_grads=False):
+    torch.manual_seed(0)
+    model = ref_shim.build_memory_attention(ns).eval()  # eval: dropout off (parity contract)
+    params = detgen.det_params([(n, tuple(p.shape)) for n, p in model.named_parameters()])
+    assert [n for n, _ in model.named_parameters()] == [n for n, _ in detgen.param_shapes()]
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            p.copy_(params[n])
+    inp = detgen.attention_inputs(grid, batch, n_frames, n_ptr)
+    curr = inp["curr"].clone().requires_grad_(True)
+    curr_pos = inp["curr_pos"].clone().requires_grad_(True)
+    memory = inp["memory"].clone().requires_grad_(True)
+    memory_pos = inp["memory_pos"].clone().requires_grad_(True)
+    out = model(curr=[curr], curr_pos=[curr_pos], memory=memory, memory_pos=memory_pos,
+                num_obj_ptr_tokens=n_ptr)
+    out.backward(inp["grad_out"])
+    rec = dict(
+        grid=grid, batch=batch, n_frames=n_frames, n_ptr=n_ptr,
+        out=out.detach().numpy(),
+        d_curr=curr.grad.numpy(), d_curr_pos=curr_pos.grad.numpy(),
+        d_memory=memory.grad.numpy(), d_memory_pos=memory_pos.grad.numpy(),
+    )
+    names, sums = [], []
+    for n, p in model.named_parameters():
+        names.append(n)
+        sums.append(float(p.grad.abs().sum()))
+        if full_grads or n in ("layers.0.self_attn.q_proj.weight", "layers.3.cross_attn_image.k_proj.weight",
+                               "layers.1.cross_attn_image.v_proj.bias", "layers.2.linear1.bias",
+                               "layers.0.norm2.weight", "norm.bias"):
+            rec["dparam:" + n] = p.grad.numpy()
+    rec["param_names"] = np.array(names)
+    rec["param_grad_abs_sums"] = np.array(sums, dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, f"attn_{tag}.npz"), **rec)
+    return rec
+
+
+def golden_loss(ns, t, c, s, tag):
+    logits, targets, iou_pred = detgen.loss_inputs(t, c, s)
+    rec = dict(t=t, c=c, s=s)
+    for mode, l1 in (("l1", True), ("mse", False)):
+        crit = ns.MultiStepMultiMasksAndIous(
+            weight_dict={"loss_mask": 20, "loss_dice": 1, "loss_iou": 1, "loss_class": 0},
+            supervise_all_iou=True, iou_use_l1_loss=l1, pred_obj_scores=False,
+            focal_gamma_obj_score=0.0, focal_alpha_obj_score=-1.0)
+        x = logits.clone().requires_grad_(True)
+        ip = iou_pred.clone().requires_grad_(True)
+        outs = [{"multistep_pred_multimasks_high_res": [x[f]], "multistep_pred_ious": [ip[f]],
+                 "multistep_object_score_logits": [torch.zeros(c, 1)]} for f in range(t)]
+        losses = crit(outs, targets)
+        losses["total_loss"].backward()
+        for k in ("loss_mask", "loss_dice", "loss_iou", "loss_class", "total_loss"):
+            rec[f"{mode}:{k}"] = float(losses[k].detach()) if torch.is_tensor(losses[k]) else float(losses[k])
+        rec[f"{mode}:dlogits"] = x.grad.numpy()
+        rec[f"{mode}:diou"] = ip.grad.numpy()
+    # temperature variant
+    crit = ns.MultiStepMultiMasksAndIous(
+        weight_dict={"loss_mask": 1, "loss_dice": 10, "loss_iou": 10}, iou_use_l1_loss=True,
+        logit_temperature=2.5, focal_alpha=0.6, focal_gamma=2.0)
+    x = logits.clone().requires_grad_(True)
+    ip = iou_pred.clone().requires_grad_(True)
+    outs = [{"multistep_pred_multimasks_high_res": [x[f]], "multistep_pred_ious": [ip[f]],
+             "multistep_object_score_logits": [torch.zeros(c, 1)]} for f in range(t)]
+    losses = crit(outs, targets)
+    losses["total_loss"].backward()
+    for k in ("loss_mask", "loss_dice", "loss_iou", "total_loss"):
+        rec[f"temp:{k}"] = float(losses[k])
+    rec["temp:dlogits"] = x.grad.numpy()
+    # BCE category loss
+    for tagb, kw in (("bce", {}), ("bce_pw", dict(pos_weight=[1.5, 0.5, 2.0][:c] + [1.0] * max(0, c - 3),
+                                                  logit_temperature=1.7))):
+        crit = ns.BCECategoryLoss(**kw)
+        x = logits.clone().requires_grad_(True)
+        tg = targets.clone()
+        if "pos_weight" in kw:  # the reference requires every channel valid when pos_weight is set
+            tg[:, :, 0, 0] = True
+        outs = [{"pred_masks_high_res": x[f]} for f in range(t)]
+        losses = crit(outs, tg)
+        losses["total_loss"].backward()
+        rec[f"{tagb}:total_loss"] = float(losses["total_loss"])
+        rec[f"{tagb}:dlogits"] = x.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, f"loss_{tag}.npz"), **rec)
+    return rec
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ns = ref_shim.load()
+    torch.set_num_threads(8)
+    r = golden_attention(ns, 4, 2, 2, 8, "g4_b2_f2_p8", full_grads=False)
+    print("attn g4: out sum", float(r["out"].sum()), "abs", float(np.abs(r["out"]).sum()),
+          "d_curr abs", float(np.abs(r["d_curr"]).sum()))
+    r = golden_attention(ns, 8, 3, 3, 12, "g8_b3_f3_p12")
+    print("attn g8: out abs", float(np.abs(r["out"]).sum()))
+    r = golden_attention(ns, 12, 1, 1, 0, "g12_b1_f1_p0")
+    print("attn g12: out abs", float(np.abs(r["out"]).sum()))
+    r = golden_loss(ns, 2, 3, 16, "t2_c3_s16")
+    print("loss: l1 total", r["l1:total_loss"], "mse total", r["mse:total_loss"], "bce", r["bce:total_loss"])
+    r = golden_loss(ns, 3, 5, 40, "t3_c5_s40")
+    print("loss2: l1 total", r["l1:total_loss"])
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,133 @@
+"""The oracle (oracle/*.py) against golden vectors produced by the UNMODIFIED reference
+(oracle/make_golden.py) -- CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import attention_oracle as ao
+from oracle import detgen
+from oracle import losses_oracle as lo
+
+W_FOCAL = {"loss_mask": 20, "loss_dice": 1, "loss_iou": 1, "loss_class": 0}
+
+
+def _rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.mark.parametrize("tag", ["g4_b2_f2_p8", "g8_b3_f3_p12", "g12_b1_f1_p0"])
+def test_attention_oracle_matches_reference(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, f"attn_{tag}.npz"))
+    grid, batch, nf, nptr = int(g["grid"]), int(g["batch"]), int(g["n_frames"]), int(g["n_ptr"])
+    # The oracle runs in fp64: the reference's own fp32 round-off on d_curr through 4 pre-norm
+    # layers is ~3e-4 of max|grad| (measured against this fp64 run), which bounds the tolerances.
+    dt = torch.float64
+    params = {k: v.clone().requires_grad_(True) for k, v in detgen.det_params(detgen.param_shapes(), dtype=dt).items()}
+    inp = detgen.attention_inputs(grid, batch, nf, nptr, dtype=dt)
+    leaves = {k: inp[k].clone().requires_grad_(True) for k in ("curr", "curr_pos", "memory", "memory_pos")}
+    out = ao.memory_attention(params, leaves["curr"], leaves["memory"], leaves["curr_pos"],
+                              leaves["memory_pos"], nptr)
+    out.backward(inp["grad_out"])
+    assert _rel(out.detach().numpy(), g["out"]) < 2e-5
+    for k in ("curr", "curr_pos", "memory", "memory_pos"):
+        assert _rel(leaves[k].grad.numpy(), g["d_" + k]) < 1e-3, k
+    names = [str(n) for n in g["param_names"]]
+    sums = g["param_grad_abs_sums"]
+    for n, s in zip(names, sums):
+        mine = float(params[n].grad.abs().sum())
+        assert abs(mine - s) <= 3e-3 * max(abs(s), 1e-3), n
+    for key in g.files:
+        if key.startswith("dparam:"):
+            assert _rel(params[key[7:]].grad.numpy(), g[key]) < 1e-3, key
+
+
+def test_attention_survey_anchor(golden_dir):
+    """Hand-checked values recorded in SURVEY.md section 8c for the 4x4 case."""
+    g = np.load(os.path.join(golden_dir, "attn_g4_b2_f2_p8.npz"))
+    out = g["out"]
+    assert abs(float(out.sum()) - 3.7188990) < 2e-3
+    assert abs(float(np.abs(out).sum()) - 7231.01252) < 1e-1
+    np.testing.assert_allclose(out[0, 0, :4], [0.42185301, 0.46303186, 0.77024263, 1.34924459], atol=2e-5)
+    np.testing.assert_allclose(out[-1, -1, -4:], [-1.30274642, -1.45456612, -1.39149940, -0.91938818], atol=2e-5)
+
+
+def test_attention_oracle_fp64_close_to_fp32():
+    params = detgen.det_params(detgen.param_shapes(), dtype=torch.float64)
+    inp = detgen.attention_inputs(4, 2, 2, 8, dtype=torch.float64)
+    o64 = ao.memory_attention(params, inp["curr"], inp["memory"], inp["curr_pos"], inp["memory_pos"], 8)
+    p32 = {k: v.float() for k, v in params.items()}
+    o32 = ao.memory_attention(p32, inp["curr"].float(), inp["memory"].float(), inp["curr_pos"].float(),
+                              inp["memory_pos"].float(), 8)
+    assert _rel(o32.numpy(), o64.numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("tag", ["t2_c3_s16", "t3_c5_s40"])
+def test_loss_oracle_matches_reference(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, f"loss_{tag}.npz"))
+    t, c, s = int(g["t"]), int(g["c"]), int(g["s"])
+    logits, targets, iou_pred = detgen.loss_inputs(t, c, s)
+    for mode, l1 in (("l1", True), ("mse", False)):
+        x = logits.clone().requires_grad_(True)
+        ip = iou_pred.clone().requires_grad_(True)
+        out = lo.multistep_loss([x[f] for f in range(t)], targets, [ip[f] for f in range(t)],
+                                dict(W_FOCAL), iou_use_l1_loss=l1)
+        out["total_loss"].backward()
+        for k in ("loss_mask", "loss_dice", "loss_iou", "total_loss"):
+            assert abs(float(out[k]) - float(g[f"{mode}:{k}"])) <= 2e-6 * max(1.0, abs(float(g[f"{mode}:{k}"]))), (mode, k)
+        assert _rel(x.grad.numpy(), g[f"{mode}:dlogits"]) < 1e-5
+        assert _rel(ip.grad.numpy(), g[f"{mode}:diou"]) < 1e-5
+        # analytic gradient == autograd
+        dx, di = lo.multistep_loss_grad(logits.reshape(t, c, -1), targets.reshape(t, c, -1),
+                                        iou_pred.reshape(t, c), dict(W_FOCAL), iou_use_l1_loss=l1)
+        assert _rel(dx.reshape(g[f"{mode}:dlogits"].shape).numpy(), g[f"{mode}:dlogits"]) < 1e-5
+        assert _rel(di.reshape(g[f"{mode}:diou"].shape).numpy(), g[f"{mode}:diou"]) < 1e-5
+    x = logits.clone().requires_grad_(True)
+    out = lo.multistep_loss([x[f] for f in range(t)], targets, [iou_pred[f] for f in range(t)],
+                            {"loss_mask": 1, "loss_dice": 10, "loss_iou": 10, "loss_class": 0.0},
+                            focal_alpha=0.6, iou_use_l1_loss=True, logit_temperature=2.5)
+    out["total_loss"].backward()
+    assert abs(float(out["total_loss"]) - float(g["temp:total_loss"])) < 2e-5 * abs(float(g["temp:total_loss"]))
+    assert _rel(x.grad.numpy(), g["temp:dlogits"]) < 1e-5
+
+
+def test_loss_survey_anchor(golden_dir):
+    g = np.load(os.path.join(golden_dir, "loss_t2_c3_s16.npz"))
+    assert abs(float(g["l1:total_loss"]) - 27.71217918) < 1e-5
+    assert abs(float(g["l1:loss_mask"]) - 1.29880679) < 1e-6
+    assert abs(float(g["l1:loss_dice"]) - 1.10489178) < 1e-6
+    assert abs(float(g["l1:loss_iou"]) - 0.63115150) < 1e-6
+    assert abs(float(g["mse:total_loss"]) - 27.37424850) < 1e-5
+    np.testing.assert_allclose(g["l1:diou"][0, :, 0], [1 / 3, 1 / 3, 1 / 3], rtol=1e-6)
+    np.testing.assert_allclose(g["mse:diou"][0, :, 0], [0.29424682, 0.47509211, 0.16200837], rtol=1e-5)
+    assert abs(float(g["bce:total_loss"]) - 1.41786313) < 1e-6
+
+
+@pytest.mark.parametrize("tag", ["t2_c3_s16", "t3_c5_s40"])
+def test_bce_oracle_matches_reference(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, f"loss_{tag}.npz"))
+    t, c, s = int(g["t"]), int(g["c"]), int(g["s"])
+    logits, targets, _ = detgen.loss_inputs(t, c, s)
+    x = logits.clone().requires_grad_(True)
+    out = lo.bce_category_loss([x[f] for f in range(t)], targets)
+    out["total_loss"].backward()
+    assert abs(float(out["total_loss"]) - float(g["bce:total_loss"])) < 2e-6
+    assert _rel(x.grad.numpy(), g["bce:dlogits"]) < 1e-5
+    tg = targets.clone()
+    tg[:, :, 0, 0] = True
+    pw = torch.tensor(([1.5, 0.5, 2.0][:c] + [1.0] * max(0, c - 3)))
+    x = logits.clone().requires_grad_(True)
+    out = lo.bce_category_loss([x[f] for f in range(t)], tg, pos_weight=pw, logit_temperature=1.7)
+    out["total_loss"].backward()
+    assert abs(float(out["total_loss"]) - float(g["bce_pw:total_loss"])) < 2e-6
+    assert _rel(x.grad.numpy(), g["bce_pw:dlogits"]) < 1e-5
+
+
+def test_loss_no_valid_masks_raises():
+    logits, targets, iou_pred = detgen.loss_inputs(2, 3, 8)
+    targets[1] = False
+    with pytest.raises(ValueError, match="No valid masks"):
+        lo.multistep_loss([logits[f] for f in range(2)], targets, [iou_pred[f] for f in range(2)], dict(W_FOCAL))

@@ -13,6 +13,12 @@ from oracle import losses_oracle as lo
 W_FOCAL = {"loss_mask": 20, "loss_dice": 1, "loss_iou": 1, "loss_class": 0}
 
 
+def _l2(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
 def _rel(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
@@ -23,8 +29,11 @@ def _rel(a, b):
 def test_attention_oracle_matches_reference(golden_dir, tag):
     g = np.load(os.path.join(golden_dir, f"attn_{tag}.npz"))
     grid, batch, nf, nptr = int(g["grid"]), int(g["batch"]), int(g["n_frames"]), int(g["n_ptr"])
-    # The oracle runs in fp64: the reference's own fp32 round-off on d_curr through 4 pre-norm
-    # layers is ~3e-4 of max|grad| (measured against this fp64 run), which bounds the tolerances.
+    # The oracle runs in fp64; the golden is the reference in fp32.  Forward agrees to ~5e-7.
+    # Gradients are compared in relative L2: with these analytic weights a few ReLU
+    # pre-activations sit within fp32 round-off of 0, so single hidden units flip between the
+    # fp32 reference and an fp64 run (the reference itself run in .double() shows the same
+    # flips), which moves individual linear1 gradient rows by O(1e-2) but the L2 error < 3e-3.
     dt = torch.float64
     params = {k: v.clone().requires_grad_(True) for k, v in detgen.det_params(detgen.param_shapes(), dtype=dt).items()}
     inp = detgen.attention_inputs(grid, batch, nf, nptr, dtype=dt)
@@ -34,15 +43,15 @@ def test_attention_oracle_matches_reference(golden_dir, tag):
     out.backward(inp["grad_out"])
     assert _rel(out.detach().numpy(), g["out"]) < 2e-5
     for k in ("curr", "curr_pos", "memory", "memory_pos"):
-        assert _rel(leaves[k].grad.numpy(), g["d_" + k]) < 1e-3, k
+        assert _l2(leaves[k].grad.numpy(), g["d_" + k]) < 2e-4, k
     names = [str(n) for n in g["param_names"]]
     sums = g["param_grad_abs_sums"]
     for n, s in zip(names, sums):
         mine = float(params[n].grad.abs().sum())
-        assert abs(mine - s) <= 3e-3 * max(abs(s), 1e-3), n
+        assert abs(mine - s) <= 2e-2 * max(abs(s), 1e-3), n
     for key in g.files:
         if key.startswith("dparam:"):
-            assert _rel(params[key[7:]].grad.numpy(), g[key]) < 1e-3, key
+            assert _l2(params[key[7:]].grad.numpy(), g[key]) < 5e-3, key
 
 
 def test_attention_survey_anchor(golden_dir):

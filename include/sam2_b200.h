@@ -1,0 +1,98 @@
+/* libsam2b200.so -- C ABI of the B200-native (sm_100a) SAM2 memory-attention + mask-loss path.
+ *
+ * The reference (yangkunyi/sam2-video-training) is pure Python/PyTorch and has no FFI of its own
+ * for this path: the two plug points are the nn.Module attribute `SAM2Base.memory_attention`
+ * (sam2_video/model/modeling/sam2_base.py:125, invoked :695-709) and the criterion
+ * `SAM2LightningModule.criterion` (sam2_video/training/trainer.py:67-94, invoked :268,303).
+ * The functions below are what torch.autograd.Functions behind those plug points bind (ctypes;
+ * see INTEGRATION.md).  For each entry point the reference code it replaces is cited.
+ *
+ * Conventions: plain device pointers + sizes + an explicit cudaStream_t; no allocation, no host
+ * synchronisation, no C++ exceptions.  Return 0 on success, <0 on error (sam2b200_last_error()
+ * gives a thread-local message).  All tensors are contiguous; bf16 = __nv_bfloat16 bits.
+ */
+#ifndef SAM2_B200_H_
+#define SAM2_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* sam2b200_stream_t; /* == cudaStream_t */
+
+#define SAM2B200_OK 0
+#define SAM2B200_ERR_INVALID (-1)
+#define SAM2B200_ERR_CUDA (-2)
+#define SAM2B200_ERR_UNSUPPORTED (-3)
+#define SAM2B200_ERR_DRIVER (-4)
+
+#define SAM2B200_DTYPE_F32 0
+#define SAM2B200_DTYPE_BF16 1
+
+#define SAM2B200_LOSS_MULTISTEP 0 /* focal + dice + IoU (MultiStepMultiMasksAndIous) */
+#define SAM2B200_LOSS_BCE 1       /* BCECategoryLoss */
+
+int sam2b200_version(void);
+const char* sam2b200_last_error(void);
+/* 0 iff CUDA device `dev` is an sm_100 part. */
+int sam2b200_check_device(int dev);
+
+/* ---- axial RoPE -------------------------------------------------------------------------
+ * Replaces apply_rotary_enc (sam2_video/model/modeling/position_encoding.py:212-239) and the
+ * slice write-back k[:, :, :num_k_rope] = ... (sam2_video/model/modeling/sam/transformer.py:296-302).
+ * x, out: [B, L, 256]; rows [0, n_rope) of every batch item are rotated by table[row % n_tokens],
+ * later rows (object-pointer keys) are copied.  table: [n_tokens, 128, 2] fp32 (cos, sin) --
+ * compute_axial_cis (position_encoding.py:192-201).  inverse != 0 applies the conjugate rotation
+ * (the backward of the rotation).  n_rope must be a multiple of n_tokens. */
+int sam2b200_rope_apply(const void* x, int in_dtype, void* out, int out_dtype, const float* table,
+                        int B, int L, int n_rope, int n_tokens, int inverse, sam2b200_stream_t stream);
+
+/* ---- attention core ---------------------------------------------------------------------
+ * Replaces F.scaled_dot_product_attention(q, k, v) for one head of width 256
+ * (sam2_video/model/modeling/sam/transformer.py:306; plain variant :243), no mask, dropout 0.
+ * q: [B, N, 256], k, v: [B, M, 256], out: [B, N, 256], all bf16; lse2: [B, N] fp32 =
+ * log2 sum_j exp(scale * q.k_j) (kept for the backward).  nsplit > 1 splits the keys across
+ * CTAs (for grids that do not fill 148 SMs) and needs the workspace below. */
+int sam2b200_attn_default_nsplit(int B, int N, int M);
+size_t sam2b200_attn_fwd_workspace_bytes(int B, int N, int M, int nsplit);
+int sam2b200_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse2,
+                      void* workspace, size_t workspace_bytes, int B, int N, int M, float scale,
+                      int nsplit, sam2b200_stream_t stream);
+/* Backward (what autograd derives for transformer.py:306).  delta: [B, N] fp32 scratch;
+ * dq: [B, N, 256], dk, dv: [B, M, 256] fp32, fully overwritten. */
+int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout,
+                      const float* lse2, float* delta, float* dq, float* dk, float* dv, int B, int N,
+                      int M, float scale, sam2b200_stream_t stream);
+
+/* ---- fused mask loss --------------------------------------------------------------------
+ * mode SAM2B200_LOSS_MULTISTEP replaces MultiStepMultiMasksAndIous._update_losses and the three
+ * loss functions it calls (sam2_video/model/losses.py:20-76,143-238) for one step / one mask per
+ * channel; mode SAM2B200_LOSS_BCE replaces BCECategoryLoss.forward's per-frame body (:308-372).
+ * logits: HOST array of T device pointers, each [C, HW] fp32 (the per-frame tensors are used in
+ * place, never stacked); targets: [T, C, HW] u8/bool; iou_pred: [T, C] fp32 (multistep only);
+ * pos_weight: [C] fp32 or NULL (bce only).
+ * Outputs: chan_sums [T, C, 6] (sum focal|bce, sum p*t, sum p, sum t, |pred&gt|, |pred|gt|),
+ * n_valid [T] (channels with foreground; 0 => the caller raises "No valid masks"),
+ * losses [4]: multistep: loss_mask, loss_dice, loss_iou, 0 summed over frames (losses.py:116-119);
+ * bce: losses[0] = sum over frames of the per-frame reduced loss. */
+size_t sam2b200_mask_loss_workspace_bytes(int T, int C, long long HW);
+int sam2b200_mask_loss_fwd(const float* const* logits, const uint8_t* targets, const float* iou_pred,
+                           const float* pos_weight, void* workspace, float* chan_sums, int* n_valid,
+                           float* losses, int T, int C, long long HW, int mode, float alpha,
+                           float gamma, float inv_temp, int iou_l1, int reduction_mean,
+                           sam2b200_stream_t stream);
+/* grad_losses: device [3] = d/d(loss_mask, loss_dice, loss_iou) (multistep) or [1] (bce).
+ * dlogits: HOST array of T device pointers [C, HW] fp32, fully overwritten; diou: [T, C]. */
+int sam2b200_mask_loss_bwd(const float* const* logits, float* const* dlogits, const uint8_t* targets,
+                           const float* iou_pred, const float* pos_weight, const float* chan_sums,
+                           const int* n_valid, const float* grad_losses, float* diou, int T, int C,
+                           long long HW, int mode, float alpha, float gamma, float inv_temp,
+                           int iou_l1, int reduction_mean, sam2b200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAM2_B200_H_ */

@@ -1,0 +1,272 @@
+// C-ABI entry points of the attention path + the small HBM-bound helper kernels around the
+// tcgen05 kernels of attn_kernels.cuh: axial RoPE (forward / conjugate), Delta = rowsum(dO o O),
+// split-KV combine.
+//
+// Replaces (reference, paths relative to its root):
+//   sam2_video/model/modeling/position_encoding.py:212-239  apply_rotary_enc
+//   sam2_video/model/modeling/sam/transformer.py:296-306    k[:, :, :num_k_rope] = ...; SDPA
+// and their autograd backward.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "abi_common.cuh"
+#include "attn_kernels.cuh"
+#include "tma_desc.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ axial RoPE
+// x: [B, L, 256] (fp32 or bf16); rows [0, n_rope) of every batch are rotated with the table row
+// (row mod n_tokens); rows >= n_rope are copied (object-pointer keys, transformer.py:296).
+// table: [n_tokens, 128] float2 (cos, sin) built on the host side exactly like the reference's
+// compute_axial_cis (position_encoding.py:192-201).  inverse = conjugate rotation (backward).
+// Rotation is done in fp32 registers (position_encoding.py:218-220 upcasts as well).
+template <typename TIn, typename TOut>
+__global__ void rope_kernel(const TIn* __restrict__ x, TOut* __restrict__ out,
+                            const float2* __restrict__ table, long long rows_total, int L, int n_rope,
+                            int n_tokens, int inverse) {
+  // one thread = 8 consecutive features (4 complex pairs); 32 threads = one row
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long row = gid >> 5;
+  const int seg = (int)(gid & 31);
+  if (row >= rows_total) return;
+  const int r = (int)(row % L);
+  float v[8];
+  if constexpr (sizeof(TIn) == 4) {
+    const float4* src = reinterpret_cast<const float4*>(x + row * 256 + seg * 8);
+    float4 a = src[0], b = src[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    uint4 u = *reinterpret_cast<const uint4*>(x + row * 256 + seg * 8);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+  if (r < n_rope) {
+    const float2* t = table + (long long)(r % n_tokens) * 128 + seg * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 cs = t[i];
+      float sn = inverse ? -cs.y : cs.y;
+      float re = v[2 * i] * cs.x - v[2 * i + 1] * sn;
+      float im = v[2 * i] * sn + v[2 * i + 1] * cs.x;
+      v[2 * i] = re; v[2 * i + 1] = im;
+    }
+  }
+  if constexpr (sizeof(TOut) == 4) {
+    float4* dst = reinterpret_cast<float4*>(out + row * 256 + seg * 8);
+    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    uint4 u;
+    u.x = sm100::pack_bf16(v[0], v[1]); u.y = sm100::pack_bf16(v[2], v[3]);
+    u.z = sm100::pack_bf16(v[4], v[5]); u.w = sm100::pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(out + row * 256 + seg * 8) = u;
+  }
+}
+
+// ------------------------------------------------------------------ Delta = rowsum(dO o O)
+__global__ void delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+                             float* __restrict__ delta, long long rows) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  uint4 a = *reinterpret_cast<const uint4*>(o + row * 256 + lane * 8);
+  uint4 b = *reinterpret_cast<const uint4*>(d_o + row * 256 + lane * 8);
+  const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 fa = __bfloat1622float2(ha[i]), fb = __bfloat1622float2(hb[i]);
+    s += fa.x * fb.x + fa.y * fb.y;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) delta[row] = s;
+}
+
+// ------------------------------------------------------------------ split-KV combine
+// part_acc: [nsplit, rows, 256] fp32 un-normalised, part_ml: [nsplit, rows, 2] = (m*c, l)
+__global__ void combine_kernel(const float* __restrict__ part_acc, const float* __restrict__ part_ml,
+                               __nv_bfloat16* __restrict__ out, float* __restrict__ lse2,
+                               long long rows, int nsplit) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float mmax = -INFINITY;
+  for (int z = 0; z < nsplit; ++z) mmax = fmaxf(mmax, part_ml[((long long)z * rows + row) * 2]);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float lsum = 0.f;
+  for (int z = 0; z < nsplit; ++z) {
+    const float* ml = part_ml + ((long long)z * rows + row) * 2;
+    const float w = exp2f(ml[0] - mmax);
+    lsum += w * ml[1];
+    const float4* src = reinterpret_cast<const float4*>(part_acc + ((long long)z * rows + row) * 256 + lane * 8);
+    float4 a = src[0], b = src[1];
+    acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
+    acc[4] += w * b.x; acc[5] += w * b.y; acc[6] += w * b.z; acc[7] += w * b.w;
+  }
+  const float inv = 1.0f / lsum;
+  uint4 u;
+  u.x = sm100::pack_bf16(acc[0] * inv, acc[1] * inv); u.y = sm100::pack_bf16(acc[2] * inv, acc[3] * inv);
+  u.z = sm100::pack_bf16(acc[4] * inv, acc[5] * inv); u.w = sm100::pack_bf16(acc[6] * inv, acc[7] * inv);
+  *reinterpret_cast<uint4*>(out + row * 256 + lane * 8) = u;
+  if (lane == 0) lse2[row] = mmax + log2f(lsum);
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return sam2b200::fail(SAM2B200_ERR_CUDA, cudaGetErrorString(e));
+  return 0;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+// in_dtype / out_dtype: 0 = fp32, 1 = bf16
+int sam2b200_rope_apply(const void* x, int in_dtype, void* out, int out_dtype, const float* table, int B,
+                        int L, int n_rope, int n_tokens, int inverse, cudaStream_t stream) {
+  if (!x || !out || !table || B <= 0 || L <= 0 || n_rope < 0 || n_rope > L || n_tokens <= 0 ||
+      (n_rope % n_tokens) != 0 || !aligned16(x) || !aligned16(out))
+    return sam2b200::fail(SAM2B200_ERR_INVALID, "rope_apply: bad arguments (n_rope must be a multiple of n_tokens)");
+  const long long rows = (long long)B * L;
+  const int threads = 256;
+  const long long blocks = (rows * 32 + threads - 1) / threads;
+  const float2* t = reinterpret_cast<const float2*>(table);
+  if (in_dtype == 0 && out_dtype == 1)
+    rope_kernel<float, __nv_bfloat16><<<(unsigned)blocks, threads, 0, stream>>>((const float*)x, (__nv_bfloat16*)out, t, rows, L, n_rope, n_tokens, inverse);
+  else if (in_dtype == 1 && out_dtype == 1)
+    rope_kernel<__nv_bfloat16, __nv_bfloat16><<<(unsigned)blocks, threads, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, t, rows, L, n_rope, n_tokens, inverse);
+  else if (in_dtype == 0 && out_dtype == 0)
+    rope_kernel<float, float><<<(unsigned)blocks, threads, 0, stream>>>((const float*)x, (float*)out, t, rows, L, n_rope, n_tokens, inverse);
+  else if (in_dtype == 1 && out_dtype == 0)
+    rope_kernel<__nv_bfloat16, float><<<(unsigned)blocks, threads, 0, stream>>>((const __nv_bfloat16*)x, (float*)out, t, rows, L, n_rope, n_tokens, inverse);
+  else
+    return sam2b200::fail(SAM2B200_ERR_INVALID, "rope_apply: dtype must be 0 (fp32) or 1 (bf16)");
+  return sam2b200::check_launch("rope_apply");
+}
+
+// Number of KV splits that fills the 148 SMs for small grids (flash-decoding style); 1 otherwise.
+int sam2b200_attn_default_nsplit(int B, int N, int M) {
+  const int ctas = B * ((N + attn::kBlockM - 1) / attn::kBlockM);
+  const int tiles = (M + attn::kBlockN - 1) / attn::kBlockN;
+  if (ctas >= 148 || tiles < 8) return 1;
+  int ns = 148 / ctas;
+  if (ns > tiles / 4) ns = tiles / 4;   // keep >= 4 tiles per split
+  if (ns > 16) ns = 16;
+  return ns < 1 ? 1 : ns;
+}
+
+size_t sam2b200_attn_fwd_workspace_bytes(int B, int N, int M, int nsplit) {
+  (void)M;
+  if (nsplit <= 1) return 0;
+  return (size_t)nsplit * B * N * (256 + 2) * sizeof(float);
+}
+
+// q: [B, N, 256], k, v: [B, M, 256] bf16 (q, k already rotated); out: [B, N, 256] bf16;
+// lse2: [B, N] fp32 = log2(sum_j exp(scale * q.k_j)).
+int sam2b200_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse2, void* workspace,
+                      size_t workspace_bytes, int B, int N, int M, float scale, int nsplit,
+                      cudaStream_t stream) {
+  if (!q || !k || !v || !out || !lse2 || B <= 0 || N <= 0 || M <= 0 || B > 65535 || !aligned16(q) ||
+      !aligned16(k) || !aligned16(v) || !aligned16(out))
+    return sam2b200::fail(SAM2B200_ERR_INVALID, "attn_fwd: bad arguments");
+  const int total_tiles = (M + attn::kBlockN - 1) / attn::kBlockN;
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > total_tiles) nsplit = total_tiles;
+  int tiles_per_split = (total_tiles + nsplit - 1) / nsplit;
+  nsplit = (total_tiles + tiles_per_split - 1) / tiles_per_split;   // no empty split
+  if (nsplit > 1 && (workspace == nullptr || workspace_bytes < sam2b200_attn_fwd_workspace_bytes(B, N, M, nsplit)))
+    return sam2b200::fail(SAM2B200_ERR_INVALID, "attn_fwd: workspace too small for the requested split");
+  CUtensorMap map_k, map_v;
+  int rc;
+  if ((rc = sam2b200::make_rows256_map(&map_k, k, B, M, attn::kBlockN))) return rc;
+  if ((rc = sam2b200::make_rows256_map(&map_v, v, B, M, attn::kBlockN))) return rc;
+  attn::TwoGemmParams p{};
+  p.a = (const __nv_bfloat16*)q; p.La = N; p.Lx = M; p.scale_log2 = scale * kLog2e;
+  p.out = (__nv_bfloat16*)out; p.lse2 = lse2; p.tiles_per_split = tiles_per_split;
+  if (nsplit > 1) {
+    p.part_acc = (float*)workspace;
+    p.part_ml = p.part_acc + (size_t)nsplit * B * N * 256;
+  }
+  const size_t smem = sizeof(attn::SharedStorage) + 1024;
+  if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_FWD>, smem))) return rc;
+  dim3 grid((N + attn::kBlockM - 1) / attn::kBlockM, B, nsplit);
+  attn::two_gemm_kernel<attn::MODE_FWD><<<grid, attn::kThreads, smem, stream>>>(map_k, map_v, p);
+  if ((rc = sam2b200::check_launch("attn_fwd"))) return rc;
+  if (nsplit > 1) {
+    const long long rows = (long long)B * N;
+    combine_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, stream>>>(p.part_acc, p.part_ml, p.out, lse2, rows, nsplit);
+    if ((rc = sam2b200::check_launch("attn_fwd combine"))) return rc;
+  }
+  return SAM2B200_OK;
+}
+
+// Backward of out = softmax(scale q k^T) v.  All of q, k, v, out, dout bf16; lse2 from the forward.
+// delta: [B, N] fp32 scratch.  dq: [B, N, 256], dk, dv: [B, M, 256] fp32 outputs (fully written).
+int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout,
+                      const float* lse2, float* delta, float* dq, float* dk, float* dv, int B, int N, int M,
+                      float scale, cudaStream_t stream) {
+  if (!q || !k || !v || !out || !dout || !lse2 || !delta || !dq || !dk || !dv || B <= 0 || N <= 0 || M <= 0 ||
+      B > 65535 || !aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(out) || !aligned16(dout) ||
+      !aligned16(dq) || !aligned16(dk) || !aligned16(dv))
+    return sam2b200::fail(SAM2B200_ERR_INVALID, "attn_bwd: bad arguments");
+  int rc;
+  const long long rows = (long long)B * N;
+  delta_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, stream>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, rows);
+  if ((rc = sam2b200::check_launch("attn_bwd delta"))) return rc;
+
+  CUtensorMap map_q64, map_k64, map_v64, map_do64, map_do128, map_v128;
+  if ((rc = sam2b200::make_rows256_map(&map_q64, q, B, N, attn::kBlockN))) return rc;
+  if ((rc = sam2b200::make_rows256_map(&map_k64, k, B, M, attn::kBlockN))) return rc;
+  if ((rc = sam2b200::make_rows256_map(&map_v64, v, B, M, attn::kBlockN))) return rc;
+  if ((rc = sam2b200::make_rows256_map(&map_do64, dout, B, N, attn::kBlockN))) return rc;
+  if ((rc = sam2b200::make_rows256_map(&map_do128, dout, B, N, attn::kBlockM))) return rc;
+  if ((rc = sam2b200::make_rows256_map(&map_v128, v, B, M, attn::kBlockM))) return rc;
+
+  // dV = P^T dO: fixed K block, stream (Q, dO) tiles
+  {
+    attn::TwoGemmParams p{};
+    p.a = (const __nv_bfloat16*)k; p.La = M; p.Lx = N; p.scale_log2 = scale * kLog2e;
+    p.lse2 = const_cast<float*>(lse2); p.acc_out = dv;
+    p.tiles_per_split = (N + attn::kBlockN - 1) / attn::kBlockN;
+    const size_t smem = sizeof(attn::SharedStorage) + 1024;
+    if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_DV>, smem))) return rc;
+    dim3 grid((M + attn::kBlockM - 1) / attn::kBlockM, B, 1);
+    attn::two_gemm_kernel<attn::MODE_DV><<<grid, attn::kThreads, smem, stream>>>(map_q64, map_do64, p);
+    if ((rc = sam2b200::check_launch("attn_bwd dV"))) return rc;
+  }
+  const size_t smem3 = sizeof(attn::SharedStorage3) + 1024;
+  // dK = scale * dS^T Q: fixed (K in TMEM, V in SMEM), stream (Q, dO) tiles
+  {
+    attn::ThreeGemmParams p{};
+    p.a1 = (const __nv_bfloat16*)k; p.La = M; p.Lx = N; p.scale_log2 = scale * kLog2e; p.scale = scale;
+    p.lse2 = lse2; p.delta = delta; p.acc_out = dk;
+    if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DK>, smem3))) return rc;
+    dim3 grid((M + attn::kBlockM - 1) / attn::kBlockM, B, 1);
+    attn::three_gemm_kernel<attn::MODE_DK><<<grid, attn::kThreads, smem3, stream>>>(map_v128, map_q64, map_do64, p);
+    if ((rc = sam2b200::check_launch("attn_bwd dK"))) return rc;
+  }
+  // dQ = scale * dS K: fixed (Q in TMEM, dO in SMEM), stream (K, V) tiles
+  {
+    attn::ThreeGemmParams p{};
+    p.a1 = (const __nv_bfloat16*)q; p.La = N; p.Lx = M; p.scale_log2 = scale * kLog2e; p.scale = scale;
+    p.lse2 = lse2; p.delta = delta; p.acc_out = dq;
+    if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DQ>, smem3))) return rc;
+    dim3 grid((N + attn::kBlockM - 1) / attn::kBlockM, B, 1);
+    attn::three_gemm_kernel<attn::MODE_DQ><<<grid, attn::kThreads, smem3, stream>>>(map_do128, map_k64, map_v64, p);
+    if ((rc = sam2b200::check_launch("attn_bwd dQ"))) return rc;
+  }
+  return SAM2B200_OK;
+}
+
+}  // extern "C"

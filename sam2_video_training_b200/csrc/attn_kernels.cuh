@@ -1,0 +1,607 @@
+// sm_100a flash-style attention kernels for SAM2 memory attention: ONE head, head_dim 256,
+// bf16 operands (already rotated by the axial RoPE pre-pass, rope.cu), fp32 accumulation.
+//
+// Two kernel templates cover forward and backward ("Attention kernels"):
+//
+//   two_gemm_kernel<MODE>   scores = A . X^T  ->  P = f(scores)  ->  ACC += P . Y
+//     MODE_FWD : A = Q tile (128 queries), X = K tiles, Y = V tiles, online softmax, O = ACC / l
+//     MODE_DV  : A = K tile (128 keys),    X = Q tiles, Y = dO tiles, P^T = exp2(S^T c - LSE2[q])
+//
+//   three_gemm_kernel<MODE> S = A1 . X^T, dP = A2 . Y^T, dS = P o (dP - Delta), ACC += dS . X
+//     MODE_DQ  : A1 = Q, A2 = dO, X = K tiles, Y = V tiles   (LSE2/Delta per row)
+//     MODE_DK  : A1 = K, A2 = V,  X = Q tiles, Y = dO tiles  (LSE2/Delta per column)
+//
+// Hardware mapping (identical in every kernel):
+//   * the fixed 128 x 256 operand A lives in TENSOR MEMORY as the bf16 A-operand of tcgen05.mma
+//     (.kind::f16, A from TMEM), written there once from registers with tcgen05.st;
+//   * streamed 64 x 256 tiles arrive by TMA (cp.async.bulk.tensor, 128-byte swizzle) into a
+//     3-stage shared-memory ring; the SAME tile is consumed K-major (scores GEMM, contraction
+//     over the 256 features) and MN-major (accumulate GEMM, contraction over the 64 rows);
+//   * fp32 accumulators (scores 128 x 64, ACC 128 x 256) live in tensor memory; the
+//     probability tile is written back to tensor memory as bf16 (tcgen05.st) and fed to the
+//     second GEMM as its A operand, so it never touches shared memory;
+//   * warp roles: warps 0-3 = softmax / epilogue (one thread per accumulator row = TMEM lane),
+//     warp 4 = TMA producer, warp 5 = tcgen05.mma issuer + TMEM allocator.
+#pragma once
+
+#include "sm100.cuh"
+
+namespace attn {
+
+using namespace sm100;
+
+constexpr int kD = 256;            // head dim
+constexpr int kBlockM = 128;       // rows of the fixed operand (TMEM lanes)
+constexpr int kBlockN = 64;        // rows of a streamed tile
+constexpr int kStages = 3;
+constexpr int kTileBytes = kBlockN * kD * 2;        // 32 KB
+constexpr int kChunkBytes = kBlockN * 128;          // one 64-column slab of a tile: 8 KB
+constexpr int kNumSoftmaxThreads = 128;
+constexpr int kThreads = 192;
+
+// tensor-memory column map (512 columns allocated)
+constexpr uint32_t kColAcc = 0;      // 256 fp32 columns: ACC (O / dV)
+constexpr uint32_t kColA = 256;      // 128 columns: fixed operand A, bf16 pairs
+constexpr uint32_t kColS0 = 384;     // 64 fp32 columns: scores buffer 0 (P overwrites cols 0..31)
+constexpr uint32_t kColS1 = 448;     // scores buffer 1
+
+enum { MODE_FWD = 0, MODE_DV = 1 };
+
+struct TwoGemmParams {
+  const __nv_bfloat16* a;      // [B, La, 256] fixed operand (Q in FWD, K in DV)
+  int La;                      // rows of a per batch (N in FWD, M in DV)
+  int Lx;                      // streamed length per batch (M in FWD, N in DV)
+  float scale_log2;            // softmax scale * log2(e)
+  // FWD outputs
+  __nv_bfloat16* out;          // [B, La, 256] bf16 (nsplit == 1)
+  float* lse2;                 // [B, La] log2-domain LSE (FWD: output; DV: input, length Lx)
+  float* part_acc;             // [nsplit, B, La, 256] fp32 un-normalised partials (nsplit > 1)
+  float* part_ml;              // [nsplit, B, La, 2]  (m_ref * c, l)
+  // DV output
+  float* acc_out;              // [B, La, 256] fp32 (dV)
+  int tiles_per_split;
+};
+
+struct SharedStorage {
+  alignas(1024) uint8_t x_tiles[kStages][kTileBytes];
+  alignas(1024) uint8_t y_tiles[kStages][kTileBytes];
+  alignas(8) uint64_t x_full[kStages];
+  uint64_t x_empty[kStages];
+  uint64_t y_full[kStages];
+  uint64_t y_empty[kStages];
+  uint64_t s_full[2];
+  uint64_t p_ready[2];
+  uint64_t acc_done;
+  uint64_t a_ready;
+  float colvec[2][kBlockN];   // DV: LSE2 of the tile's columns
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void load_fixed_operand_to_tmem(const __nv_bfloat16* a_row, bool valid,
+                                                           uint32_t taddr) {
+  // one thread = one row: 256 bf16 = 32 x 16 B; tcgen05.st 32 packed columns at a time
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t r[32];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (valid) u = __ldg(reinterpret_cast<const uint4*>(a_row) + c * 8 + v);
+      r[4 * v + 0] = u.x; r[4 * v + 1] = u.y; r[4 * v + 2] = u.z; r[4 * v + 3] = u.w;
+    }
+    SAM2B200_TMEM_ST32(taddr + c * 32, r);
+  }
+  tmem_wait_st();
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
+                const TwoGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  SharedStorage& sh = *reinterpret_cast<SharedStorage*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int a_tile = blockIdx.x;       // which 128-row block of the fixed operand
+  const int b = blockIdx.y;            // batch (object)
+  const int split = blockIdx.z;
+  const int nsplit = gridDim.z;
+
+  const int total_tiles = (p.Lx + kBlockN - 1) / kBlockN;
+  const int t_begin = split * p.tiles_per_split;
+  const int t_end = min(total_tiles, t_begin + p.tiles_per_split);
+  const int nt = t_end - t_begin;      // >= 1 by construction of the grid
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&sh.x_full[s], 1); mbar_init(&sh.x_empty[s], 1);
+      mbar_init(&sh.y_full[s], 1); mbar_init(&sh.y_empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sh.s_full[i], 1); mbar_init(&sh.p_ready[i], kNumSoftmaxThreads); }
+    mbar_init(&sh.acc_done, 1);
+    mbar_init(&sh.a_ready, kNumSoftmaxThreads);
+    fence_barrier_init();
+  }
+  if (warp == 4 && lane == 0) { prefetch_tmap(&map_x); prefetch_tmap(&map_y); }
+  if (warp == 5) { tmem_alloc(&sh.tmem_base, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sh.tmem_base;
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int j = 0; j < nt; ++j) {
+        const int s = j % kStages;
+        const uint32_t ph = (j / kStages) & 1;
+        const int row0 = (t_begin + j) * kBlockN;
+        mbar_wait(&sh.x_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&sh.x_full[s], kTileBytes);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          tma_load_3d(&sh.x_tiles[s][c * kChunkBytes], &map_x, &sh.x_full[s], c * 64, row0, b);
+        mbar_wait(&sh.y_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&sh.y_full[s], kTileBytes);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          tma_load_3d(&sh.y_tiles[s][c * kChunkBytes], &map_y, &sh.y_full[s], c * 64, row0, b);
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(kBlockM, kBlockN, 0, 0);   // A(TMEM) . X^T, X K-major
+      constexpr uint32_t idesc_acc = make_idesc_bf16(kBlockM, kD, 0, 1);      // P(TMEM) . Y,  Y MN-major
+      auto issue_scores = [&](int t) {
+        const int s = t % kStages;
+        mbar_wait(&sh.x_full[s], (t / kStages) & 1);
+        tc_fence_after();
+        const uint32_t xbase = smem_u32(&sh.x_tiles[s][0]);
+        const uint32_t d = tmem + ((t & 1) ? kColS1 : kColS0);
+#pragma unroll
+        for (int ks = 0; ks < kD / 16; ++ks) {
+          // K-major SW128: 64-col slab (ks/4), 32 B per 16-element k-step inside the 128 B row
+          const uint64_t bdesc = make_smem_desc_sw128(xbase + (ks >> 2) * kChunkBytes + (ks & 3) * 32, 16, 1024);
+          umma_ts(d, tmem + kColA + ks * 8, bdesc, idesc_s, ks > 0);
+        }
+        umma_commit(&sh.x_empty[s]);
+        umma_commit(&sh.s_full[t & 1]);
+      };
+      mbar_wait(&sh.a_ready, 0);
+      tc_fence_after();
+      issue_scores(0);
+      if (nt > 1) issue_scores(1);
+      for (int j = 0; j < nt; ++j) {
+        const int s = j % kStages;
+        mbar_wait(&sh.p_ready[j & 1], (j >> 1) & 1);
+        mbar_wait(&sh.y_full[s], (j / kStages) & 1);
+        tc_fence_after();
+        const uint32_t ybase = smem_u32(&sh.y_tiles[s][0]);
+        const uint32_t pa = tmem + ((j & 1) ? kColS1 : kColS0);
+#pragma unroll
+        for (int ks = 0; ks < kBlockN / 16; ++ks) {
+          // MN-major SW128: N = 256 features -> 4 slabs (LBO = slab stride), K = 16 rows = 2 groups
+          // of 8 rows (SBO = 1024 B); advancing 16 rows = 2048 B
+          const uint64_t bdesc = make_smem_desc_sw128(ybase + ks * 2048, kChunkBytes, 1024);
+          umma_ts(tmem + kColAcc, pa + ks * 8, bdesc, idesc_acc, (j > 0) || (ks > 0));
+        }
+        umma_commit(&sh.y_empty[s]);
+        umma_commit(&sh.acc_done);
+        if (j + 2 < nt) issue_scores(j + 2);
+      }
+    }
+  } else {
+    // ===================== softmax / epilogue warps (0..3) =====================
+    const int row = threadIdx.x;                         // TMEM lane == accumulator row
+    const uint32_t lane_addr = tmem + (uint32_t(warp * 32) << 16);
+    const long long a_row_idx = (long long)a_tile * kBlockM + row;
+    const bool row_valid = a_row_idx < p.La;
+    {
+      const __nv_bfloat16* a_row = p.a + ((long long)b * p.La + (row_valid ? a_row_idx : 0)) * kD;
+      load_fixed_operand_to_tmem(a_row, row_valid, lane_addr + kColA);
+      tc_fence_before();
+      mbar_arrive(&sh.a_ready);
+    }
+
+    const float c = p.scale_log2;
+    float m_ref = -INFINITY;   // running (lazily updated) row max of the raw scores
+    float l = 0.f;             // running sum of exp2((s - m_ref) c)
+
+    for (int j = 0; j < nt; ++j) {
+      const int t = t_begin + j;
+      const uint32_t sbuf = lane_addr + ((j & 1) ? kColS1 : kColS0);
+      if (MODE == MODE_DV) {
+        // stage this tile's per-column LSE2 (columns are queries) through shared memory
+        if (threadIdx.x < kBlockN) {
+          const int col = t * kBlockN + threadIdx.x;
+          sh.colvec[j & 1][threadIdx.x] = (col < p.Lx) ? p.lse2[(long long)b * p.Lx + col] : INFINITY;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      mbar_wait(&sh.s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t r0[32], r1[32];
+      SAM2B200_TMEM_LD32(sbuf, r0);
+      SAM2B200_TMEM_LD32(sbuf + 32, r1);
+      tmem_wait_ld();
+      float sv[kBlockN];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { sv[i] = __uint_as_float(r0[i]); sv[32 + i] = __uint_as_float(r1[i]); }
+
+      uint32_t pk[32];
+      if (MODE == MODE_FWD) {
+        const int ncols = p.Lx - t * kBlockN;            // valid columns in this tile
+        if (ncols < kBlockN) {
+#pragma unroll
+          for (int i = 0; i < kBlockN; ++i) if (i >= ncols) sv[i] = -INFINITY;
+        }
+        float mx = sv[0];
+#pragma unroll
+        for (int i = 1; i < kBlockN; ++i) mx = fmaxf(mx, sv[i]);
+        // Lazy rescale: keep the stale reference max unless the true max grew by > 2^8 in the
+        // exp2 domain (P then stays < 256, exact enough in bf16/fp32); first tile just adopts it.
+        const bool grow = (mx - m_ref) * c > 8.0f;
+        if (j == 0) {
+          m_ref = mx;
+        } else if (__any_sync(0xffffffffu, grow)) {
+          const float m_new = grow ? mx : m_ref;
+          const float f = ex2((m_ref - m_new) * c);      // 1.0 for rows that do not move
+          mbar_wait(&sh.acc_done, (j - 1) & 1);          // PV[j-1] has landed in ACC
+          tc_fence_after();
+#pragma unroll 1
+          for (int cc = 0; cc < kD / 32; ++cc) {
+            uint32_t o[32];
+            SAM2B200_TMEM_LD32(lane_addr + kColAcc + cc * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            SAM2B200_TMEM_ST32(lane_addr + kColAcc + cc * 32, o);
+          }
+          tmem_wait_st();
+          l *= f;
+          m_ref = m_new;
+        }
+        const float mc = m_ref * c;
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < kBlockN; i += 2) {
+          float e0 = ex2(fmaf(sv[i], c, -mc));
+          float e1 = ex2(fmaf(sv[i + 1], c, -mc));
+          sum += e0 + e1;
+          pk[i >> 1] = pack_bf16(e0, e1);
+        }
+        l += sum;
+      } else {
+        const float* cv = sh.colvec[j & 1];
+#pragma unroll
+        for (int i = 0; i < kBlockN; i += 2) {
+          float e0 = ex2(fmaf(sv[i], c, -cv[i]));
+          float e1 = ex2(fmaf(sv[i + 1], c, -cv[i + 1]));
+          pk[i >> 1] = pack_bf16(e0, e1);
+        }
+      }
+      SAM2B200_TMEM_ST32(sbuf, pk);                       // P (bf16 pairs) over scores cols 0..31
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&sh.p_ready[j & 1]);
+    }
+
+    // ---------------- epilogue ----------------
+    mbar_wait(&sh.acc_done, (nt - 1) & 1);
+    tc_fence_after();
+    if (MODE == MODE_FWD) {
+      if (nsplit == 1) {
+        const float inv_l = 1.0f / l;
+        __nv_bfloat16* orow = p.out + ((long long)b * p.La + a_row_idx) * kD;
+#pragma unroll 1
+        for (int cc = 0; cc < kD / 32; ++cc) {
+          uint32_t o[32];
+          SAM2B200_TMEM_LD32(lane_addr + kColAcc + cc * 32, o);
+          tmem_wait_ld();
+          if (row_valid) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              uint4 u;
+              u.x = pack_bf16(__uint_as_float(o[8 * v + 0]) * inv_l, __uint_as_float(o[8 * v + 1]) * inv_l);
+              u.y = pack_bf16(__uint_as_float(o[8 * v + 2]) * inv_l, __uint_as_float(o[8 * v + 3]) * inv_l);
+              u.z = pack_bf16(__uint_as_float(o[8 * v + 4]) * inv_l, __uint_as_float(o[8 * v + 5]) * inv_l);
+              u.w = pack_bf16(__uint_as_float(o[8 * v + 6]) * inv_l, __uint_as_float(o[8 * v + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(orow + cc * 32 + v * 8) = u;
+            }
+          }
+        }
+        if (row_valid) p.lse2[(long long)b * p.La + a_row_idx] = fmaf(m_ref, c, log2f(l));
+      } else {
+        const long long prow = ((long long)split * gridDim.y + b) * p.La + a_row_idx;
+        float* orow = p.part_acc + prow * kD;
+#pragma unroll 1
+        for (int cc = 0; cc < kD / 32; ++cc) {
+          uint32_t o[32];
+          SAM2B200_TMEM_LD32(lane_addr + kColAcc + cc * 32, o);
+          tmem_wait_ld();
+          if (row_valid) {
+#pragma unroll
+            for (int v = 0; v < 8; ++v)
+              *reinterpret_cast<uint4*>(orow + cc * 32 + v * 4) =
+                  make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+          }
+        }
+        if (row_valid) { p.part_ml[prow * 2] = m_ref * c; p.part_ml[prow * 2 + 1] = l; }
+      }
+    } else {
+      float* orow = p.acc_out + ((long long)b * p.La + a_row_idx) * kD;
+#pragma unroll 1
+      for (int cc = 0; cc < kD / 32; ++cc) {
+        uint32_t o[32];
+        SAM2B200_TMEM_LD32(lane_addr + kColAcc + cc * 32, o);
+        tmem_wait_ld();
+        if (row_valid) {
+#pragma unroll
+          for (int v = 0; v < 8; ++v)
+            *reinterpret_cast<uint4*>(orow + cc * 32 + v * 4) =
+                make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem, 512);
+}
+
+// =====================================================================================
+// three_gemm_kernel: S = A1 . X^T, dP = A2 . Y^T, dS = P o (dP - Delta), ACC += dS . X
+// =====================================================================================
+enum { MODE_DQ = 0, MODE_DK = 1 };
+
+constexpr int kStages3 = 2;
+constexpr int kA2Bytes = kBlockM * kD * 2;          // 64 KB, four [128 x 128 B] slabs
+constexpr int kA2ChunkBytes = kBlockM * 128;        // 16 KB
+// tensor-memory column map
+constexpr uint32_t k3ColAcc = 0;     // 256: dQ / dK accumulator
+constexpr uint32_t k3ColA1 = 256;    // 128: fixed operand A1 (bf16 pairs)
+constexpr uint32_t k3ColS = 384;     // 64 : S
+constexpr uint32_t k3ColDP = 448;    // 64 : dP, then dS (bf16 pairs in cols 0..31)
+
+struct ThreeGemmParams {
+  const __nv_bfloat16* a1;     // [B, La, 256] (Q in DQ, K in DK)
+  int La;
+  int Lx;                      // streamed length (M in DQ, N in DK)
+  float scale_log2;            // scale * log2(e)
+  float scale;                 // softmax scale (applied to ACC in the epilogue)
+  const float* lse2;           // [B, N]   log2-domain LSE of the forward
+  const float* delta;          // [B, N]   rowsum(dO o O)
+  float* acc_out;              // [B, La, 256] fp32
+};
+
+struct SharedStorage3 {
+  alignas(1024) uint8_t a2[kA2Bytes];
+  alignas(1024) uint8_t x_tiles[kStages3][kTileBytes];
+  alignas(1024) uint8_t y_tiles[kStages3][kTileBytes];
+  alignas(8) uint64_t x_full[kStages3];
+  uint64_t x_empty[kStages3];
+  uint64_t y_full[kStages3];
+  uint64_t y_empty[kStages3];
+  uint64_t a2_full;
+  uint64_t a1_ready;
+  uint64_t s_full;
+  uint64_t s_free;
+  uint64_t dp_full;
+  uint64_t ds_ready;
+  uint64_t acc_done;
+  float col_lse[2][kBlockN];
+  float col_delta[2][kBlockN];
+  uint32_t tmem_base;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_x,
+                  const __grid_constant__ CUtensorMap map_y, const ThreeGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  SharedStorage3& sh = *reinterpret_cast<SharedStorage3*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int a_tile = blockIdx.x;
+  const int b = blockIdx.y;
+  const int nt = (p.Lx + kBlockN - 1) / kBlockN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages3; ++s) {
+      mbar_init(&sh.x_full[s], 1); mbar_init(&sh.x_empty[s], 1);
+      mbar_init(&sh.y_full[s], 1); mbar_init(&sh.y_empty[s], 1);
+    }
+    mbar_init(&sh.a2_full, 1);
+    mbar_init(&sh.a1_ready, kNumSoftmaxThreads);
+    mbar_init(&sh.s_full, 1);
+    mbar_init(&sh.s_free, kNumSoftmaxThreads);
+    mbar_init(&sh.dp_full, 1);
+    mbar_init(&sh.ds_ready, kNumSoftmaxThreads);
+    mbar_init(&sh.acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4 && lane == 0) { prefetch_tmap(&map_a2); prefetch_tmap(&map_x); prefetch_tmap(&map_y); }
+  if (warp == 5) { tmem_alloc(&sh.tmem_base, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sh.tmem_base;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&sh.a2_full, kA2Bytes);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        tma_load_3d(&sh.a2[c * kA2ChunkBytes], &map_a2, &sh.a2_full, c * 64, a_tile * kBlockM, b);
+      for (int j = 0; j < nt; ++j) {
+        const int s = j % kStages3;
+        const uint32_t ph = (j / kStages3) & 1;
+        const int row0 = j * kBlockN;
+        mbar_wait(&sh.x_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&sh.x_full[s], kTileBytes);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          tma_load_3d(&sh.x_tiles[s][c * kChunkBytes], &map_x, &sh.x_full[s], c * 64, row0, b);
+        mbar_wait(&sh.y_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&sh.y_full[s], kTileBytes);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          tma_load_3d(&sh.y_tiles[s][c * kChunkBytes], &map_y, &sh.y_full[s], c * 64, row0, b);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(kBlockM, kBlockN, 0, 0);
+      constexpr uint32_t idesc_acc = make_idesc_bf16(kBlockM, kD, 0, 1);
+      const uint32_t a2base = smem_u32(&sh.a2[0]);
+      auto issue_s = [&](int t) {        // S[t] = A1(TMEM) . X[t]^T
+        const int s = t % kStages3;
+        mbar_wait(&sh.x_full[s], (t / kStages3) & 1);
+        tc_fence_after();
+        const uint32_t xbase = smem_u32(&sh.x_tiles[s][0]);
+#pragma unroll
+        for (int ks = 0; ks < kD / 16; ++ks) {
+          const uint64_t bdesc = make_smem_desc_sw128(xbase + (ks >> 2) * kChunkBytes + (ks & 3) * 32, 16, 1024);
+          umma_ts(tmem + k3ColS, tmem + k3ColA1 + ks * 8, bdesc, idesc_s, ks > 0);
+        }
+        umma_commit(&sh.s_full);
+      };
+      auto issue_dp = [&](int t) {       // dP[t] = A2(SMEM) . Y[t]^T
+        const int s = t % kStages3;
+        mbar_wait(&sh.y_full[s], (t / kStages3) & 1);
+        tc_fence_after();
+        const uint32_t ybase = smem_u32(&sh.y_tiles[s][0]);
+#pragma unroll
+        for (int ks = 0; ks < kD / 16; ++ks) {
+          const uint64_t adesc = make_smem_desc_sw128(a2base + (ks >> 2) * kA2ChunkBytes + (ks & 3) * 32, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(ybase + (ks >> 2) * kChunkBytes + (ks & 3) * 32, 16, 1024);
+          umma_ss(tmem + k3ColDP, adesc, bdesc, idesc_s, ks > 0);
+        }
+        umma_commit(&sh.y_empty[s]);
+        umma_commit(&sh.dp_full);
+      };
+      mbar_wait(&sh.a1_ready, 0);
+      mbar_wait(&sh.a2_full, 0);
+      tc_fence_after();
+      issue_s(0);
+      issue_dp(0);
+      for (int j = 0; j < nt; ++j) {
+        const int s = j % kStages3;
+        if (j + 1 < nt) {                 // S[j+1] as soon as the compute warps have read S[j]
+          mbar_wait(&sh.s_free, j & 1);
+          tc_fence_after();
+          issue_s(j + 1);
+        }
+        mbar_wait(&sh.ds_ready, j & 1);
+        tc_fence_after();
+        const uint32_t xbase = smem_u32(&sh.x_tiles[s][0]);
+#pragma unroll
+        for (int ks = 0; ks < kBlockN / 16; ++ks) {
+          const uint64_t bdesc = make_smem_desc_sw128(xbase + ks * 2048, kChunkBytes, 1024);
+          umma_ts(tmem + k3ColAcc, tmem + k3ColDP + ks * 8, bdesc, idesc_acc, (j > 0) || (ks > 0));
+        }
+        umma_commit(&sh.x_empty[s]);
+        if (j + 1 < nt) issue_dp(j + 1); else umma_commit(&sh.acc_done);
+      }
+    }
+  } else {
+    const int row = threadIdx.x;
+    const uint32_t lane_addr = tmem + (uint32_t(warp * 32) << 16);
+    const long long a_row_idx = (long long)a_tile * kBlockM + row;
+    const bool row_valid = a_row_idx < p.La;
+    {
+      const __nv_bfloat16* a_row = p.a1 + ((long long)b * p.La + (row_valid ? a_row_idx : 0)) * kD;
+      load_fixed_operand_to_tmem(a_row, row_valid, lane_addr + k3ColA1);
+      tc_fence_before();
+      mbar_arrive(&sh.a1_ready);
+    }
+    const float c = p.scale_log2;
+    float row_lse = 0.f, row_delta = 0.f;
+    if (MODE == MODE_DQ && row_valid) {
+      row_lse = p.lse2[(long long)b * p.La + a_row_idx];
+      row_delta = p.delta[(long long)b * p.La + a_row_idx];
+    }
+    for (int j = 0; j < nt; ++j) {
+      if (MODE == MODE_DK) {
+        if (threadIdx.x < kBlockN) {
+          const int col = j * kBlockN + threadIdx.x;
+          const bool ok = col < p.Lx;
+          sh.col_lse[j & 1][threadIdx.x] = ok ? p.lse2[(long long)b * p.Lx + col] : INFINITY;
+          sh.col_delta[j & 1][threadIdx.x] = ok ? p.delta[(long long)b * p.Lx + col] : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      mbar_wait(&sh.s_full, j & 1);
+      tc_fence_after();
+      float pv[kBlockN];
+      {
+        uint32_t r0[32], r1[32];
+        SAM2B200_TMEM_LD32(lane_addr + k3ColS, r0);
+        SAM2B200_TMEM_LD32(lane_addr + k3ColS + 32, r1);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(&sh.s_free);          // S region may be overwritten by S[j+1]
+        const int ncols = p.Lx - j * kBlockN;
+#pragma unroll
+        for (int i = 0; i < kBlockN; ++i) {
+          const float sraw = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]);
+          float e;
+          if (MODE == MODE_DQ) e = (i < ncols) ? ex2(fmaf(sraw, c, -row_lse)) : 0.f;
+          else e = ex2(fmaf(sraw, c, -sh.col_lse[j & 1][i]));
+          pv[i] = e;
+        }
+      }
+      mbar_wait(&sh.dp_full, j & 1);
+      tc_fence_after();
+      uint32_t pk[32];
+      {
+        uint32_t r0[32], r1[32];
+        SAM2B200_TMEM_LD32(lane_addr + k3ColDP, r0);
+        SAM2B200_TMEM_LD32(lane_addr + k3ColDP + 32, r1);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < kBlockN; i += 2) {
+          const float d0 = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]);
+          const float d1 = __uint_as_float(i + 1 < 32 ? r0[i + 1] : r1[i + 1 - 32]);
+          const float dl0 = (MODE == MODE_DQ) ? row_delta : sh.col_delta[j & 1][i];
+          const float dl1 = (MODE == MODE_DQ) ? row_delta : sh.col_delta[j & 1][i + 1];
+          pk[i >> 1] = pack_bf16(pv[i] * (d0 - dl0), pv[i + 1] * (d1 - dl1));
+        }
+      }
+      SAM2B200_TMEM_ST32(lane_addr + k3ColDP, pk);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&sh.ds_ready);
+    }
+    mbar_wait(&sh.acc_done, 0);
+    tc_fence_after();
+    float* orow = p.acc_out + ((long long)b * p.La + a_row_idx) * kD;
+#pragma unroll 1
+    for (int cc = 0; cc < kD / 32; ++cc) {
+      uint32_t o[32];
+      SAM2B200_TMEM_LD32(lane_addr + k3ColAcc + cc * 32, o);
+      tmem_wait_ld();
+      if (row_valid) {
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          float4 f;
+          f.x = __uint_as_float(o[4 * v]) * p.scale; f.y = __uint_as_float(o[4 * v + 1]) * p.scale;
+          f.z = __uint_as_float(o[4 * v + 2]) * p.scale; f.w = __uint_as_float(o[4 * v + 3]) * p.scale;
+          *reinterpret_cast<float4*>(orow + cc * 32 + v * 4) = f;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace attn

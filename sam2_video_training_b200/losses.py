@@ -1,0 +1,274 @@
+"""Drop-in replacements for ``sam2_video/model/losses.py`` of the reference, backed by the fused
+sm_100a mask-loss kernels of libsam2b200.so (csrc/mask_loss.cu).
+
+Same names, constructor arguments, ``forward(outs_batch, targets_batch) -> Dict[str, Tensor]``
+contract, result keys and error behaviour as the reference (file:line cited per symbol); the
+switch in ``SAM2LightningModule.__init__`` (sam2_video/training/trainer.py:67-94) is described in
+INTEGRATION.md.  There is no PyTorch / CPU fallback: CPU tensors or a missing library raise.
+
+Differences, all deliberate:
+* one kernel pass over all frames x channels instead of ~40 ATen launches per frame; targets are
+  read as the 1-byte bool they already are (the reference materialises ``.float()``, losses.py:125);
+* the "no valid channel" condition (losses.py:153-161) is detected on the device and raised as the
+  same ``ValueError("No valid masks")`` after ONE device->host read of T ints per call (the
+  reference synchronises once per frame); ``check_valid=False`` defers/omits that read;
+* the multi-mask branch (M > 1 masks per channel, losses.py:217-229) is outside the hot path --
+  the training wrapper always produces one mask per channel (sam2model.py:472-476) -- and raises
+  ``NotImplementedError``.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Union
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+CORE_LOSS_KEY = "total_loss"  # losses.py:17
+
+_MODE_MULTISTEP = 0
+_MODE_BCE = 1
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise _lib.Sam2B200Error(f"{what} must be a CUDA tensor: the B200 path has no CPU fallback")
+
+
+def _prep_logits(x: torch.Tensor) -> torch.Tensor:
+    if x.dim() == 4 and x.shape[1] == 1:
+        x = x[:, 0]
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        x = x.contiguous().float()
+    return x
+
+
+class _FusedMaskLossFn(torch.autograd.Function):
+    """losses[4] = fused(iou_pred[T, C], logits_0 .. logits_{T-1}); see sam2b200_mask_loss_fwd."""
+
+    @staticmethod
+    def forward(ctx, cfg, targets_u8, pos_weight, iou_pred, *logits):
+        lib = _lib.load()
+        t = len(logits)
+        c, hw = logits[0].shape[0], logits[0][0].numel()
+        dev = logits[0].device
+        mode = cfg["mode"]
+        ws_bytes = lib.sam2b200_mask_loss_workspace_bytes(t, c, hw)
+        ws = torch.empty(max(ws_bytes, 4) // 4, dtype=torch.float32, device=dev)
+        chan_sums = torch.empty(t, c, 6, dtype=torch.float32, device=dev)
+        n_valid = torch.empty(t, dtype=torch.int32, device=dev)
+        losses = torch.zeros(4, dtype=torch.float32, device=dev)
+        ptrs = _lib.ptr_array([x.data_ptr() for x in logits])
+        rc = lib.sam2b200_mask_loss_fwd(
+            ptrs, targets_u8.data_ptr(), iou_pred.data_ptr() if iou_pred is not None else None,
+            pos_weight.data_ptr() if pos_weight is not None else None, ws.data_ptr(),
+            chan_sums.data_ptr(), n_valid.data_ptr(), losses.data_ptr(), t, c, hw, mode,
+            cfg["alpha"], cfg["gamma"], cfg["inv_temp"], int(cfg["iou_l1"]), int(cfg["reduction_mean"]),
+            _stream_ptr(dev))
+        _lib.check(rc, "sam2b200_mask_loss_fwd")
+        ctx.cfg = cfg
+        ctx.shape = (t, c, hw)
+        ctx.logit_shapes = [tuple(x.shape) for x in logits]
+        ctx.save_for_backward(targets_u8, pos_weight, iou_pred, chan_sums, n_valid, *logits)
+        ctx.mark_non_differentiable(chan_sums, n_valid)
+        return losses, chan_sums, n_valid
+
+    @staticmethod
+    def backward(ctx, g_losses, _g_sums, _g_nv):
+        lib = _lib.load()
+        targets_u8, pos_weight, iou_pred, chan_sums, n_valid, *logits = ctx.saved_tensors
+        t, c, hw = ctx.shape
+        cfg = ctx.cfg
+        dev = logits[0].device
+        g = g_losses.contiguous().float()
+        dl = torch.empty(t, c, hw, dtype=torch.float32, device=dev)
+        diou = torch.empty(t, c, dtype=torch.float32, device=dev) if iou_pred is not None else None
+        lp = _lib.ptr_array([x.data_ptr() for x in logits])
+        dp = _lib.ptr_array([dl[f].data_ptr() for f in range(t)])
+        rc = lib.sam2b200_mask_loss_bwd(
+            lp, dp, targets_u8.data_ptr(), iou_pred.data_ptr() if iou_pred is not None else None,
+            pos_weight.data_ptr() if pos_weight is not None else None, chan_sums.data_ptr(),
+            n_valid.data_ptr(), g.data_ptr(), diou.data_ptr() if diou is not None else None, t, c, hw,
+            cfg["mode"], cfg["alpha"], cfg["gamma"], cfg["inv_temp"], int(cfg["iou_l1"]),
+            int(cfg["reduction_mean"]), _stream_ptr(dev))
+        _lib.check(rc, "sam2b200_mask_loss_bwd")
+        grads = [dl[f].view(ctx.logit_shapes[f]) for f in range(t)]
+        return (None, None, None, diou, *grads)
+
+
+def _targets_u8(targets_batch: torch.Tensor) -> torch.Tensor:
+    tb = targets_batch
+    if tb.dtype == torch.bool:
+        return tb.contiguous().view(torch.uint8)
+    if tb.dtype == torch.uint8:
+        return tb.contiguous()
+    return (tb > 0).contiguous().view(torch.uint8)  # float {0,1} masks: foreground = > 0 (losses.py:64)
+
+
+def _raise_if_no_valid(n_valid: torch.Tensor):
+    if bool((n_valid == 0).any().item()):
+        raise ValueError("No valid masks")  # losses.py:161
+
+
+class MultiStepMultiMasksAndIous(nn.Module):
+    """Fused focal + dice + IoU-regression loss; mirrors losses.py:79-248 of the reference."""
+
+    def __init__(self, weight_dict, focal_alpha=0.25, focal_gamma=2.0, supervise_all_iou=False,
+                 iou_use_l1_loss=False, pred_obj_scores=False, focal_gamma_obj_score=0.0,
+                 focal_alpha_obj_score=-1, logit_temperature: float = 1.0, check_valid: bool = True):
+        super().__init__()
+        self.weight_dict = weight_dict
+        self.focal_alpha = focal_alpha
+        self.focal_gamma = focal_gamma
+        assert "loss_mask" in self.weight_dict  # losses.py:96-98
+        assert "loss_dice" in self.weight_dict
+        assert "loss_iou" in self.weight_dict
+        if "loss_class" not in self.weight_dict:
+            self.weight_dict["loss_class"] = 0.0
+        self.focal_alpha_obj_score = focal_alpha_obj_score
+        self.focal_gamma_obj_score = focal_gamma_obj_score
+        self.supervise_all_iou = supervise_all_iou
+        self.iou_use_l1_loss = iou_use_l1_loss
+        self.pred_obj_scores = pred_obj_scores
+        if not (isinstance(logit_temperature, (int, float)) and logit_temperature > 0):
+            raise ValueError("logit_temperature must be a positive float")  # losses.py:107-108
+        self.logit_temperature = float(logit_temperature)
+        self.check_valid = check_valid
+
+    def forward(self, outs_batch: List[Dict], targets_batch: torch.Tensor) -> Dict[str, torch.Tensor]:
+        assert len(outs_batch) == len(targets_batch)  # losses.py:113
+        _require_cuda(targets_batch, "targets_batch")
+        t = len(outs_batch)
+        n_steps = None
+        for outs in outs_batch:
+            a, b, c_ = (outs["multistep_pred_multimasks_high_res"], outs["multistep_pred_ious"],
+                        outs["multistep_object_score_logits"])
+            assert len(a) == len(b)  # losses.py:130-131
+            assert len(c_) == len(b)
+            if n_steps is None:
+                n_steps = len(a)
+            elif n_steps != len(a):
+                raise NotImplementedError("frames with different numbers of correction steps")
+        tu8 = _targets_u8(targets_batch)
+        cfg = dict(mode=_MODE_MULTISTEP, alpha=float(self.focal_alpha), gamma=float(self.focal_gamma),
+                   inv_temp=1.0 / self.logit_temperature, iou_l1=bool(self.iou_use_l1_loss),
+                   reduction_mean=True)
+        total4 = None
+        loss_class = None
+        for s in range(n_steps):
+            logits = []
+            for outs in outs_batch:
+                x = outs["multistep_pred_multimasks_high_res"][s]
+                _require_cuda(x, "mask logits")
+                if x.dim() != 4 or x.shape[1] != 1:
+                    raise NotImplementedError(
+                        "multi-mask outputs (M > 1 per channel, losses.py:217-229) are outside the B200 "
+                        "hot path; the training wrapper produces [C, 1, H, W]")
+                if tuple(x.shape[-2:]) != tuple(targets_batch.shape[-2:]) or x.shape[0] != targets_batch.shape[1]:
+                    raise ValueError("mask logits / targets shape mismatch")
+                logits.append(_prep_logits(x))
+            ious = torch.stack([outs["multistep_pred_ious"][s].reshape(-1) for outs in outs_batch]).float()
+            losses4, chan_sums, n_valid = _FusedMaskLossFn.apply(cfg, tu8, None, ious.contiguous(), *logits)
+            if self.check_valid:
+                _raise_if_no_valid(n_valid)
+            total4 = losses4 if total4 is None else total4 + losses4
+            if self.pred_obj_scores:  # losses.py:194-204 -- [C, 1] tensors, not on the hot path
+                valid = (chan_sums[..., 3] > 0).float()  # [T, C]; target_obj == 1 on every valid channel
+                nv = valid.sum(-1, keepdim=True).clamp(min=1.0)
+                osl = torch.stack([outs["multistep_object_score_logits"][s].reshape(-1) for outs in outs_batch]).float()
+                ce = torch.nn.functional.softplus(-osl)  # BCE with target 1
+                p = torch.sigmoid(osl)
+                fl = ce * (1 - p) ** self.focal_gamma_obj_score
+                if self.focal_alpha_obj_score >= 0:
+                    fl = self.focal_alpha_obj_score * fl
+                lc = (fl * valid / nv).sum()
+                loss_class = lc if loss_class is None else loss_class + lc
+        losses = {"loss_mask": total4[0], "loss_dice": total4[1], "loss_iou": total4[2],
+                  "loss_class": loss_class if loss_class is not None else total4[3]}
+        losses[CORE_LOSS_KEY] = self.reduce_loss(losses)
+        return losses
+
+    def reduce_loss(self, losses):  # losses.py:240-248
+        reduced_loss = 0.0
+        for loss_key, weight in self.weight_dict.items():
+            if loss_key not in losses:
+                raise ValueError(f"{type(self)} doesn't compute {loss_key}")
+            if weight != 0:
+                reduced_loss = reduced_loss + losses[loss_key] * weight
+        return reduced_loss
+
+
+class BCECategoryLoss(nn.Module):
+    """Fused per-category BCE-with-logits; mirrors losses.py:251-372 of the reference."""
+
+    def __init__(self, pos_weight: Optional[Union[List[float], torch.Tensor]] = None,
+                 reduction: str = "mean", logit_temperature: float = 1.0):
+        super().__init__()
+        if isinstance(pos_weight, list):
+            self.register_buffer("_pos_weight", torch.tensor(pos_weight, dtype=torch.float32), persistent=False)
+        elif isinstance(pos_weight, torch.Tensor):
+            self.register_buffer("_pos_weight", pos_weight.to(dtype=torch.float32), persistent=False)
+        else:
+            self._pos_weight = None  # type: ignore
+        self.reduction = reduction
+        if not (isinstance(logit_temperature, (int, float)) and logit_temperature > 0):
+            raise ValueError("logit_temperature must be a positive float")
+        self.logit_temperature = float(logit_temperature)
+
+    def forward(self, outs_batch: List[Dict], targets_batch: torch.Tensor) -> Dict[str, torch.Tensor]:
+        assert len(outs_batch) == len(targets_batch), (
+            f"Mismatched sequence lengths: outs={len(outs_batch)} vs targets={len(targets_batch)}")
+        if self.reduction not in ("mean", "sum"):
+            raise NotImplementedError("BCECategoryLoss on the B200 path supports reduction='mean'|'sum'")
+        _require_cuda(targets_batch, "targets_batch")
+        logits = []
+        for outs, targets in zip(outs_batch, targets_batch):
+            x = outs.get("pred_masks_high_res")
+            if x is None:
+                x = outs.get("pred_masks")
+            if x is None:
+                raise KeyError("BCECategoryLoss expects 'pred_masks_high_res' or 'pred_masks' in outputs")
+            if not ((x.dim() == 4 and x.shape[1] == 1) or x.dim() == 3):
+                raise ValueError(f"Unexpected logits shape for BCECategoryLoss: {tuple(x.shape)}")
+            if targets.dim() != 3:
+                raise ValueError(f"Unexpected target shape for BCECategoryLoss: {tuple(targets.shape)}")
+            _require_cuda(x, "mask logits")
+            logits.append(_prep_logits(x))
+        c = logits[0].shape[0]
+        pw = None
+        if self._pos_weight is not None:
+            pw = self._pos_weight.to(device=logits[0].device, dtype=torch.float32).reshape(-1).contiguous()
+        tu8 = _targets_u8(targets_batch)
+        cfg = dict(mode=_MODE_BCE, alpha=0.0, gamma=0.0, inv_temp=1.0 / self.logit_temperature, iou_l1=False,
+                   reduction_mean=self.reduction == "mean")
+        losses4, chan_sums, n_valid = _FusedMaskLossFn.apply(cfg, tu8, pw, None, *logits)
+        if pw is not None:
+            # the reference compares len(pos_weight) with the number of VALID channels (losses.py:359-362)
+            if pw.numel() != c or bool((n_valid != c).any().item()):
+                raise ValueError(f"pos_weight length {pw.numel()} does not match number of classes")
+        total_loss = losses4[0] / max(len(outs_batch), 1)  # losses.py:368
+        return {"loss_bce": total_loss, CORE_LOSS_KEY: total_loss}
+
+
+# ---- functional forms (losses.py:20-76), same signatures, fused kernel underneath -------------
+def _functional_sums(inputs: torch.Tensor, targets: torch.Tensor, alpha: float, gamma: float):
+    assert inputs.dim() == 4 and targets.dim() == 4 and inputs.shape[1] == 1
+    cfg = dict(mode=_MODE_MULTISTEP, alpha=float(alpha), gamma=float(gamma), inv_temp=1.0, iou_l1=False,
+               reduction_mean=True)
+    return cfg
+
+
+def sigmoid_focal_loss(inputs, targets, num_objects, alpha: float = 0.25, gamma: float = 2,
+                       loss_on_multimask=False):
+    raise NotImplementedError(
+        "use MultiStepMultiMasksAndIous: the B200 path fuses focal+dice+IoU into one pass "
+        "(stand-alone functional forms would re-read the logits three times)")
+
+
+dice_loss = sigmoid_focal_loss
+iou_loss = sigmoid_focal_loss

@@ -1,0 +1,141 @@
+"""``MemoryAttentionLayer`` / ``MemoryAttention`` with the reference's constructor arguments,
+attribute names, state_dict keys (106 tensors, 5 922 304 parameters) and forward signatures
+(sam2_video/model/modeling/memory_attention.py:17-169), running on the B200 kernels.
+
+The residual stream is kept in fp32; LayerNorm runs in fp32 and hands bf16 to the projections;
+attention runs in libsam2b200.so.  Requires CUDA tensors -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor, nn
+
+from .. import _lib
+from .sam.transformer import RoPEAttention
+
+
+def get_activation_fn(activation):  # sam2_utils.py:77-85
+    if activation == "relu":
+        return F.relu
+    if activation == "gelu":
+        return F.gelu
+    if activation == "glu":
+        return F.glu
+    raise RuntimeError(f"activation should be relu/gelu, not {activation}.")
+
+
+def get_clones(module, N):  # sam2_utils.py:88-89
+    return nn.ModuleList([copy.deepcopy(module) for _ in range(N)])
+
+
+class MemoryAttentionLayer(nn.Module):
+    def __init__(self, activation: str, cross_attention: nn.Module, d_model: int, dim_feedforward: int,
+                 dropout: float, pos_enc_at_attn: bool, pos_enc_at_cross_attn_keys: bool,
+                 pos_enc_at_cross_attn_queries: bool, self_attention: nn.Module):
+        super().__init__()
+        self.d_model = d_model
+        self.dim_feedforward = dim_feedforward
+        self.dropout_value = dropout
+        self.self_attn = self_attention
+        self.cross_attn_image = cross_attention
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.dropout = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.norm3 = nn.LayerNorm(d_model)
+        self.dropout1 = nn.Dropout(dropout)
+        self.dropout2 = nn.Dropout(dropout)
+        self.dropout3 = nn.Dropout(dropout)
+        self.activation_str = activation
+        self.activation = get_activation_fn(activation)
+        self.pos_enc_at_attn = pos_enc_at_attn
+        self.pos_enc_at_cross_attn_queries = pos_enc_at_cross_attn_queries
+        self.pos_enc_at_cross_attn_keys = pos_enc_at_cross_attn_keys
+
+    @staticmethod
+    def _ln(x: Tensor, ln: nn.LayerNorm) -> Tensor:
+        return F.layer_norm(x.float(), ln.normalized_shape, ln.weight, ln.bias, ln.eps)
+
+    def _forward_sa(self, tgt, query_pos):  # memory_attention.py:58-64
+        tgt2 = self._ln(tgt, self.norm1)
+        q = k = tgt2 + query_pos if self.pos_enc_at_attn else tgt2
+        tgt2 = self.self_attn(q, k, v=tgt2)
+        return tgt + self.dropout1(tgt2.float())
+
+    def _forward_ca(self, tgt, memory, query_pos, pos, num_k_exclude_rope=0):  # memory_attention.py:66-81
+        kwds = {}
+        if num_k_exclude_rope > 0:
+            assert isinstance(self.cross_attn_image, RoPEAttention)
+            kwds = {"num_k_exclude_rope": num_k_exclude_rope}
+        tgt2 = self._ln(tgt, self.norm2)
+        tgt2 = self.cross_attn_image(
+            q=tgt2 + query_pos if self.pos_enc_at_cross_attn_queries else tgt2,
+            k=memory + pos if self.pos_enc_at_cross_attn_keys else memory,
+            v=memory, **kwds)
+        return tgt + self.dropout2(tgt2.float())
+
+    def forward(self, tgt, memory, pos: Optional[Tensor] = None, query_pos: Optional[Tensor] = None,
+                num_k_exclude_rope: int = 0) -> torch.Tensor:
+        tgt = self._forward_sa(tgt, query_pos)
+        tgt = self._forward_ca(tgt, memory, query_pos, pos, num_k_exclude_rope)
+        tgt2 = self._ln(tgt, self.norm3).to(torch.bfloat16)
+        h = self.activation(F.linear(tgt2, self.linear1.weight.to(torch.bfloat16), self.linear1.bias.to(torch.bfloat16)))
+        tgt2 = F.linear(self.dropout(h), self.linear2.weight.to(torch.bfloat16), self.linear2.bias.to(torch.bfloat16))
+        return tgt + self.dropout3(tgt2.float())
+
+
+class MemoryAttention(nn.Module):
+    def __init__(self, d_model: int, pos_enc_at_input: bool, layer: nn.Module, num_layers: int,
+                 batch_first: bool = True):
+        super().__init__()
+        self.d_model = d_model
+        self.layers = get_clones(layer, num_layers)
+        self.num_layers = num_layers
+        self.norm = nn.LayerNorm(d_model)
+        self.pos_enc_at_input = pos_enc_at_input
+        self.batch_first = batch_first
+
+    def forward(self, curr: torch.Tensor, memory: torch.Tensor, curr_pos: Optional[Tensor] = None,
+                memory_pos: Optional[Tensor] = None, num_obj_ptr_tokens: int = 0):
+        if isinstance(curr, list):  # memory_attention.py:127-133
+            assert isinstance(curr_pos, list)
+            assert len(curr) == len(curr_pos) == 1
+            curr, curr_pos = curr[0], curr_pos[0]
+        assert curr.shape[1] == memory.shape[1], "Batch size must be the same for curr and memory"
+        if not curr.is_cuda:
+            raise _lib.Sam2B200Error("MemoryAttention (B200 path) needs CUDA tensors: no CPU fallback")
+        _lib.load()  # fail loudly before any compute if the CUDA library is missing
+        output = curr.float()
+        if self.pos_enc_at_input and curr_pos is not None:
+            output = output + 0.1 * curr_pos
+        if self.batch_first:
+            output = output.transpose(0, 1)
+            curr_pos = curr_pos.transpose(0, 1)
+            memory = memory.transpose(0, 1)
+            memory_pos = memory_pos.transpose(0, 1)
+        for layer in self.layers:
+            kwds = {}
+            if isinstance(layer.cross_attn_image, RoPEAttention):
+                kwds = {"num_k_exclude_rope": num_obj_ptr_tokens}
+            output = layer(tgt=output, memory=memory, pos=memory_pos, query_pos=curr_pos, **kwds)
+        normed_output = F.layer_norm(output, self.norm.normalized_shape, self.norm.weight, self.norm.bias, self.norm.eps)
+        if self.batch_first:
+            normed_output = normed_output.transpose(0, 1)
+        return normed_output
+
+
+def build_memory_attention(dropout: float = 0.1, feat_sizes=(64, 64), num_layers: int = 4) -> MemoryAttention:
+    """The stack of configs/sam2/sam2.1_hiera_t.yaml:29-60 (same for every SAM2.1 size)."""
+    sa = RoPEAttention(rope_theta=10000.0, feat_sizes=list(feat_sizes), embedding_dim=256, num_heads=1,
+                       downsample_rate=1, dropout=dropout)
+    ca = RoPEAttention(rope_theta=10000.0, feat_sizes=list(feat_sizes), rope_k_repeat=True, embedding_dim=256,
+                       num_heads=1, downsample_rate=1, dropout=dropout, kv_in_dim=64)
+    layer = MemoryAttentionLayer(activation="relu", dim_feedforward=2048, dropout=dropout, pos_enc_at_attn=False,
+                                 self_attention=sa, d_model=256, pos_enc_at_cross_attn_keys=True,
+                                 pos_enc_at_cross_attn_queries=False, cross_attention=ca)
+    return MemoryAttention(d_model=256, pos_enc_at_input=True, layer=layer, num_layers=num_layers)

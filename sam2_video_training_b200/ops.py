@@ -1,0 +1,103 @@
+"""torch.autograd.Functions over the C ABI (include/sam2_b200.h).  Device memory, streams and
+autograd plumbing only -- all arithmetic of the attention core happens in libsam2b200.so."""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+def _stream(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def rope_apply(x: torch.Tensor, table: torch.Tensor, n_rope: int, inverse: bool = False,
+               out_dtype=torch.bfloat16) -> torch.Tensor:
+    """x: [B, L, 256] fp32|bf16 contiguous -> rotated copy (rows >= n_rope copied)."""
+    if not x.is_cuda:
+        raise _lib.Sam2B200Error("rope_apply: CUDA tensor required (no CPU fallback)")
+    if x.dtype not in _DT:
+        x = x.float()
+    x = x.contiguous()
+    b, l, d = x.shape
+    assert d == 256 and table.dtype == torch.float32 and table.is_contiguous()
+    out = torch.empty((b, l, d), dtype=out_dtype, device=x.device)
+    rc = _lib.load().sam2b200_rope_apply(x.data_ptr(), _DT[x.dtype], out.data_ptr(), _DT[out_dtype],
+                                         table.data_ptr(), b, l, n_rope, table.shape[0], int(inverse),
+                                         _stream(x.device))
+    _lib.check(rc, "sam2b200_rope_apply")
+    return out
+
+
+def attn_fwd(q, k, v, scale: float, nsplit: int = 0):
+    """q: [B,N,256], k, v: [B,M,256] bf16 contiguous -> (out bf16 [B,N,256], lse2 fp32 [B,N])."""
+    lib = _lib.load()
+    b, n, d = q.shape
+    m = k.shape[1]
+    assert d == 256 and k.shape == v.shape and k.shape[0] == b and k.shape[2] == 256
+    for t in (q, k, v):
+        assert t.dtype == torch.bfloat16 and t.is_contiguous() and t.is_cuda
+    if nsplit <= 0:
+        nsplit = lib.sam2b200_attn_default_nsplit(b, n, m)
+    out = torch.empty_like(q)
+    lse2 = torch.empty((b, n), dtype=torch.float32, device=q.device)
+    wsb = lib.sam2b200_attn_fwd_workspace_bytes(b, n, m, nsplit)
+    ws = torch.empty(wsb // 4, dtype=torch.float32, device=q.device) if wsb else None
+    rc = lib.sam2b200_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse2.data_ptr(),
+                               ws.data_ptr() if ws is not None else None, wsb, b, n, m, scale, nsplit,
+                               _stream(q.device))
+    _lib.check(rc, "sam2b200_attn_fwd")
+    return out, lse2
+
+
+def attn_bwd(q, k, v, out, dout, lse2, scale: float):
+    lib = _lib.load()
+    b, n, _ = q.shape
+    m = k.shape[1]
+    dq = torch.empty((b, n, 256), dtype=torch.float32, device=q.device)
+    dk = torch.empty((b, m, 256), dtype=torch.float32, device=q.device)
+    dv = torch.empty((b, m, 256), dtype=torch.float32, device=q.device)
+    delta = torch.empty((b, n), dtype=torch.float32, device=q.device)
+    rc = lib.sam2b200_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), dout.data_ptr(),
+                               lse2.data_ptr(), delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                               b, n, m, scale, _stream(q.device))
+    _lib.check(rc, "sam2b200_attn_bwd")
+    return dq, dk, dv
+
+
+class RopeAttentionFn(torch.autograd.Function):
+    """out = softmax(rope(q) rope(k[:, :M-P])^T / sqrt(256)) v for one 256-wide head.
+
+    Replaces transformer.py:296-306 of the reference (apply_rotary_enc + slice write-back + SDPA)
+    and its autograd backward.  q: [B, N, 256]; k, v: [B, M, 256]; bf16 out."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, table, num_k_exclude_rope: int, nsplit: int):
+        n_rope_k = k.shape[1] - num_k_exclude_rope
+        scale = 1.0 / math.sqrt(q.shape[-1])
+        q_rot = rope_apply(q, table, q.shape[1])
+        k_rot = rope_apply(k, table, n_rope_k)
+        vb = v.to(torch.bfloat16).contiguous()
+        out, lse2 = attn_fwd(q_rot, k_rot, vb, scale, nsplit)
+        ctx.save_for_backward(q_rot, k_rot, vb, out, lse2, table)
+        ctx.scale = scale
+        ctx.n_rope_k = n_rope_k
+        ctx.in_dtypes = (q.dtype, k.dtype, v.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q_rot, k_rot, vb, out, lse2, table = ctx.saved_tensors
+        dout = dout.to(torch.bfloat16).contiguous()
+        dq_rot, dk_rot, dv = attn_bwd(q_rot, k_rot, vb, out, dout, lse2, ctx.scale)
+        dq = rope_apply(dq_rot, table, q_rot.shape[1], inverse=True, out_dtype=_out_dt(ctx.in_dtypes[0]))
+        dk = rope_apply(dk_rot, table, ctx.n_rope_k, inverse=True, out_dtype=_out_dt(ctx.in_dtypes[1]))
+        return dq.to(ctx.in_dtypes[0]), dk.to(ctx.in_dtypes[1]), dv.to(ctx.in_dtypes[2]), None, None, None
+
+
+def _out_dt(dt):
+    return dt if dt in _DT else torch.float32

@@ -1,0 +1,113 @@
+"""CPU-side checks: the C-ABI library builds/loads and exports every symbol include/sam2_b200.h
+declares; the host-side mirror keeps the reference's interface; no silent CPU fallback."""
+import os
+import re
+
+import pytest
+import torch
+
+import sam2_video_training_b200 as pkg
+from sam2_video_training_b200 import _lib
+from sam2_video_training_b200 import build as pkg_build
+from sam2_video_training_b200.losses import BCECategoryLoss, CORE_LOSS_KEY, MultiStepMultiMasksAndIous
+from sam2_video_training_b200.modeling.memory_attention import MemoryAttention, build_memory_attention
+from sam2_video_training_b200.modeling.position_encoding import compute_axial_cis
+from sam2_video_training_b200.modeling.sam.transformer import Attention, RoPEAttention
+
+from oracle import attention_oracle as ao
+from oracle import detgen
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    pkg_build.build(verbose=False)
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "sam2_b200.h")).read()
+    declared = set(re.findall(r"\b(sam2b200_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.sam2b200_version() >= 100
+
+
+def test_no_gpu_compute_without_device(lib):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert lib.sam2b200_check_device(0) != 0
+    assert lib.sam2b200_last_error()
+
+
+def test_state_dict_matches_reference_layout():
+    m = build_memory_attention()
+    sd = m.state_dict()
+    assert len(sd) == 106
+    assert sum(p.numel() for p in m.parameters()) == 5922304
+    names = [n for n, _ in m.named_parameters()]
+    assert names == [n for n, _ in detgen.param_shapes()]
+    for n, shape in detgen.param_shapes():
+        assert tuple(sd[n].shape) == tuple(shape), n
+    assert "freqs_cis" not in "".join(sd.keys())  # plain attribute, transformer.py:269-272
+    assert sd["layers.0.cross_attn_image.k_proj.weight"].shape == (256, 64)
+    assert isinstance(m.layers[0].cross_attn_image, RoPEAttention)
+    assert isinstance(m.layers[0].self_attn, Attention)
+
+
+def test_rope_table_matches_oracle():
+    for n in (16, 576, 1024):
+        w = int(n ** 0.5)
+        t = compute_axial_cis(dim=256, end_x=w, end_y=w)
+        cos, sin = ao.axial_rope_table(n)
+        assert t.shape == (n, 128, 2)
+        assert torch.equal(t[..., 0], cos) and torch.equal(t[..., 1], sin)
+
+
+def test_cpu_tensors_fail_loudly(lib):
+    m = build_memory_attention().eval()
+    inp = detgen.attention_inputs(4, 1, 1, 4)
+    with pytest.raises(_lib.Sam2B200Error):
+        m(inp["curr"], inp["memory"], inp["curr_pos"], inp["memory_pos"], 4)
+    crit = MultiStepMultiMasksAndIous({"loss_mask": 20, "loss_dice": 1, "loss_iou": 1})
+    logits, targets, iou = detgen.loss_inputs(1, 2, 8)
+    outs = [{"multistep_pred_multimasks_high_res": [logits[0]], "multistep_pred_ious": [iou[0]],
+             "multistep_object_score_logits": [torch.zeros(2, 1)]}]
+    with pytest.raises(_lib.Sam2B200Error):
+        crit(outs, targets)
+
+
+def test_reference_error_contract():
+    with pytest.raises(ValueError):
+        MultiStepMultiMasksAndIous({"loss_mask": 1, "loss_dice": 1, "loss_iou": 1}, logit_temperature=0)
+    with pytest.raises(ValueError):
+        BCECategoryLoss(logit_temperature=-1.0)
+    with pytest.raises(AssertionError):
+        MultiStepMultiMasksAndIous({"loss_mask": 1, "loss_dice": 1})
+    crit = MultiStepMultiMasksAndIous({"loss_mask": 1, "loss_dice": 1, "loss_iou": 1})
+    assert crit.weight_dict["loss_class"] == 0.0
+    assert CORE_LOSS_KEY == "total_loss"
+    m = build_memory_attention()
+    with pytest.raises(AssertionError):  # batch mismatch, memory_attention.py:135-137
+        m(torch.zeros(16, 2, 256), torch.zeros(20, 3, 64), torch.zeros(16, 2, 256), torch.zeros(20, 3, 64))
+    with pytest.raises(_lib.Sam2B200Error):
+        Attention(256, 8)
+
+
+def test_missing_library_is_an_error(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.Sam2B200Error):
+        _lib.load()
+
+
+def test_product_never_imports_oracle():
+    pkg_dir = os.path.dirname(pkg.__file__)
+    for dp, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), os.path.join(dp, f)

@@ -1,0 +1,295 @@
+"""-m gpu parity tests: the CUDA path (through the C ABI) against the CPU oracle and against the
+golden vectors generated from the unmodified reference.  Tolerances are the ones BASELINE.json
+states: attention outputs <= 1e-2 relative (bf16 vs fp32 reference), losses <= 1e-3 relative,
+gradient cosine similarity >= 0.999."""
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import attention_oracle as ao
+from oracle import detgen
+from oracle import losses_oracle as lo
+
+pytestmark = pytest.mark.gpu
+
+W_FOCAL = {"loss_mask": 20, "loss_dice": 1, "loss_iou": 1, "loss_class": 0}
+ATTN_REL_TOL = 1e-2     # relative L2 error of attention outputs (north star)
+LOSS_REL_TOL = 1e-3     # relative error of loss values (north star)
+GRAD_COS_TOL = 0.999    # gradient cosine similarity (north star)
+
+
+def rel_l2(a, b):
+    a = a.detach().double().cpu().flatten()
+    b = b.detach().double().cpu().flatten()
+    return float((a - b).norm() / b.norm().clamp(min=1e-30))
+
+
+def cosine(a, b):
+    a = a.detach().double().cpu().flatten()
+    b = b.detach().double().cpu().flatten()
+    return float((a @ b) / (a.norm() * b.norm()).clamp(min=1e-30))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from sam2_video_training_b200 import _lib
+    lib = _lib.load()
+    assert lib.sam2b200_check_device(0) == 0, lib.sam2b200_last_error()
+    return torch.device("cuda:0")
+
+
+def test_selftest_binary():
+    """The torch-free self-test of the C ABI (csrc/selftest.cu) against its own fp64 CPU restatement."""
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sam2_video_training_b200",
+                       "sam2b200_selftest")
+    if not os.path.exists(exe):
+        pytest.skip("selftest binary not built")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-4000:])
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+
+
+# ------------------------------------------------------------------ attention core
+@pytest.mark.parametrize("b,grid,nf,nptr,nsplit", [
+    (1, 8, 1, 0, 1),        # N = M = 64: one tile
+    (2, 8, 3, 12, 1),       # ragged M = 204
+    (1, 24, 1, 4, 0),       # cfg1 frame 1: N = 576, M = 580 (library split heuristic)
+    (1, 24, 7, 28, 0),      # cfg1 steady state: M = 4060
+    (1, 24, 7, 28, 1),      # same without split-KV
+    (3, 16, 2, 8, 2),       # forced split
+    (2, 32, 1, 0, 1),       # self-attention at 512 px: N = M = 1024
+])
+def test_rope_attention_core(dev, b, grid, nf, nptr, nsplit):
+    from sam2_video_training_b200.modeling.position_encoding import compute_axial_cis
+    from sam2_video_training_b200.ops import RopeAttentionFn
+    n = grid * grid
+    m = nf * n + nptr
+    g = torch.Generator().manual_seed(1234 + n + m)
+    q = torch.randn(b, n, 256, generator=g) * 1.5
+    k = torch.randn(b, m, 256, generator=g) * 1.5
+    v = torch.randn(b, m, 256, generator=g)
+    do = torch.randn(b, n, 256, generator=g)
+    # the kernel sees bf16 operands: give the oracle the same rounded values (error budget = kernel only)
+    qb, kb, vb, dob = (t.to(torch.bfloat16) for t in (q, k, v, do))
+    qo, ko, vo = (t.double().requires_grad_(True) for t in (qb, kb, vb))
+    ref = ao.core_attention(qo, ko, vo, nptr)
+    ref.backward(dob.double())
+    table = compute_axial_cis(dim=256, end_x=grid, end_y=grid).to(dev)
+    qd, kd, vd = (t.to(dev).requires_grad_(True) for t in (qb, kb, vb))
+    out = RopeAttentionFn.apply(qd, kd, vd, table, nptr, nsplit)
+    out.backward(dob.to(dev))
+    torch.cuda.synchronize()
+    assert out.dtype == torch.bfloat16
+    assert rel_l2(out, ref) < ATTN_REL_TOL
+    for name, mine, theirs in (("dq", qd.grad, qo.grad), ("dk", kd.grad, ko.grad), ("dv", vd.grad, vo.grad)):
+        assert torch.isfinite(mine).all(), name
+        assert cosine(mine, theirs) > GRAD_COS_TOL, (name, cosine(mine, theirs))
+        assert rel_l2(mine, theirs) < 3e-2, (name, rel_l2(mine, theirs))
+
+
+def test_rope_only(dev):
+    from sam2_video_training_b200.modeling.position_encoding import compute_axial_cis
+    from sam2_video_training_b200.ops import rope_apply
+    grid, b, nf, p = 8, 2, 2, 6
+    n = grid * grid
+    x = torch.randn(b, nf * n + p, 256)
+    cos, sin = ao.axial_rope_table(n)
+    ref = torch.cat([ao.apply_axial_rope(x[:, :nf * n], cos, sin), x[:, nf * n:]], dim=1)
+    table = compute_axial_cis(dim=256, end_x=grid, end_y=grid).to(dev)
+    got = rope_apply(x.to(dev), table, nf * n, out_dtype=torch.float32)
+    assert torch.allclose(got.cpu(), ref, atol=2e-6, rtol=1e-6)
+    back = rope_apply(got, table, nf * n, inverse=True, out_dtype=torch.float32)
+    assert torch.allclose(back.cpu(), x, atol=5e-6, rtol=1e-5)  # conjugate rotation is the inverse
+    gotb = rope_apply(x.to(dev).to(torch.bfloat16), table, nf * n)
+    assert rel_l2(gotb, ref) < 6e-3
+
+
+# ------------------------------------------------------------------ full MemoryAttention stack
+def _load_params(model, params):
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            p.copy_(params[n])
+
+
+@pytest.mark.parametrize("tag", ["g4_b2_f2_p8", "g8_b3_f3_p12", "g12_b1_f1_p0"])
+def test_memory_attention_vs_reference_golden(dev, golden_dir, tag):
+    """Against outputs of the UNMODIFIED reference (fp32 CPU) stored in tests/golden."""
+    from sam2_video_training_b200.modeling.memory_attention import build_memory_attention
+    g = np.load(os.path.join(golden_dir, f"attn_{tag}.npz"))
+    grid, batch, nf, nptr = int(g["grid"]), int(g["batch"]), int(g["n_frames"]), int(g["n_ptr"])
+    model = build_memory_attention().to(dev).eval()
+    _load_params(model, detgen.det_params(detgen.param_shapes()))
+    inp = {k: v.to(dev) for k, v in detgen.attention_inputs(grid, batch, nf, nptr).items()}
+    leaves = {k: inp[k].clone().requires_grad_(True) for k in ("curr", "curr_pos", "memory", "memory_pos")}
+    out = model(curr=[leaves["curr"]], curr_pos=[leaves["curr_pos"]], memory=leaves["memory"],
+                memory_pos=leaves["memory_pos"], num_obj_ptr_tokens=nptr)
+    out.backward(inp["grad_out"])
+    torch.cuda.synchronize()
+    assert out.shape == (grid * grid, batch, 256)
+    assert rel_l2(out, torch.from_numpy(g["out"])) < ATTN_REL_TOL
+    for k in ("curr", "curr_pos", "memory", "memory_pos"):
+        assert cosine(leaves[k].grad, torch.from_numpy(g["d_" + k])) > GRAD_COS_TOL, k
+    for key in g.files:
+        if key.startswith("dparam:"):
+            pg = dict(model.named_parameters())[key[7:]].grad
+            assert cosine(pg, torch.from_numpy(g[key])) > GRAD_COS_TOL, key
+
+
+def test_memory_attention_cfg1_vs_oracle(dev):
+    """BASELINE.json configs[0] shape (24x24 tokens, 1 object), steady-state memory bank
+    (7 frames + 7 pointers), random-init weights, against the fp32 oracle."""
+    from sam2_video_training_b200.modeling.memory_attention import build_memory_attention
+    torch.manual_seed(0)
+    params = ao.init_params(seed=0)
+    grid, b, nf, nptr = 24, 1, 7, 28
+    n, m = grid * grid, nf * grid * grid + nptr
+    g = torch.Generator().manual_seed(7)
+    curr = torch.randn(n, b, 256, generator=g)
+    curr_pos = torch.randn(n, b, 256, generator=g) * 0.7
+    memory = torch.randn(m, b, 64, generator=g)
+    memory_pos = torch.randn(m, b, 64, generator=g) * 0.7
+    gout = torch.randn(n, b, 256, generator=g)
+    po = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    lo_ = {k: v.clone().requires_grad_(True) for k, v in dict(curr=curr, curr_pos=curr_pos, memory=memory, memory_pos=memory_pos).items()}
+    ref = ao.memory_attention(po, lo_["curr"], lo_["memory"], lo_["curr_pos"], lo_["memory_pos"], nptr)
+    ref.backward(gout)
+    model = build_memory_attention().to(dev).eval()
+    _load_params(model, params)
+    ld = {k: v.to(dev).clone().requires_grad_(True) for k, v in dict(curr=curr, curr_pos=curr_pos, memory=memory, memory_pos=memory_pos).items()}
+    out = model(ld["curr"], ld["memory"], ld["curr_pos"], ld["memory_pos"], nptr)
+    out.backward(gout.to(dev))
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) < ATTN_REL_TOL
+    for k in ld:
+        assert cosine(ld[k].grad, lo_[k].grad) > GRAD_COS_TOL, k
+    worst = min(cosine(p.grad, po[nm].grad) for nm, p in model.named_parameters())
+    assert worst > GRAD_COS_TOL, worst
+
+
+def test_state_dict_roundtrip_and_eval_determinism(dev):
+    from sam2_video_training_b200.modeling.memory_attention import build_memory_attention
+    a = build_memory_attention().to(dev).eval()
+    b = build_memory_attention().to(dev).eval()
+    b.load_state_dict(a.state_dict(), strict=True)
+    inp = {k: v.to(dev) for k, v in detgen.attention_inputs(8, 2, 2, 8).items()}
+    with torch.no_grad():
+        oa = a(inp["curr"], inp["memory"], inp["curr_pos"], inp["memory_pos"], 8)
+        ob = b(inp["curr"], inp["memory"], inp["curr_pos"], inp["memory_pos"], 8)
+    assert torch.equal(oa, ob)
+
+
+# ------------------------------------------------------------------ losses
+def _outs(logits, iou):
+    t, c = logits.shape[:2]
+    return [{"multistep_pred_multimasks_high_res": [logits[f]], "multistep_pred_ious": [iou[f]],
+             "multistep_object_score_logits": [torch.zeros(c, 1, device=logits.device)]} for f in range(t)]
+
+
+@pytest.mark.parametrize("tag", ["t2_c3_s16", "t3_c5_s40"])
+def test_multistep_loss_vs_reference_golden(dev, golden_dir, tag):
+    from sam2_video_training_b200.losses import MultiStepMultiMasksAndIous
+    g = np.load(os.path.join(golden_dir, f"loss_{tag}.npz"))
+    t, c, s = int(g["t"]), int(g["c"]), int(g["s"])
+    logits, targets, iou = detgen.loss_inputs(t, c, s)
+    for mode, l1 in (("l1", True), ("mse", False)):
+        crit = MultiStepMultiMasksAndIous(dict(W_FOCAL), supervise_all_iou=True, iou_use_l1_loss=l1)
+        x = logits.to(dev).requires_grad_(True)
+        ip = iou.to(dev).requires_grad_(True)
+        out = crit(_outs(x, ip), targets.to(dev))
+        out["total_loss"].backward()
+        for k in ("loss_mask", "loss_dice", "loss_iou", "total_loss"):
+            ref = float(g[f"{mode}:{k}"])
+            assert abs(float(out[k]) - ref) <= LOSS_REL_TOL * abs(ref), (mode, k, float(out[k]), ref)
+            assert out[k].dim() == 0
+        assert float(out["loss_class"]) == 0.0
+        assert rel_l2(x.grad, torch.from_numpy(g[f"{mode}:dlogits"])) < 1e-4
+        assert rel_l2(ip.grad, torch.from_numpy(g[f"{mode}:diou"])) < 1e-5
+    crit = MultiStepMultiMasksAndIous({"loss_mask": 1, "loss_dice": 10, "loss_iou": 10}, iou_use_l1_loss=True,
+                                      logit_temperature=2.5, focal_alpha=0.6)
+    x = logits.to(dev).requires_grad_(True)
+    out = crit(_outs(x, iou.to(dev)), targets.to(dev))
+    out["total_loss"].backward()
+    assert abs(float(out["total_loss"]) - float(g["temp:total_loss"])) <= LOSS_REL_TOL * abs(float(g["temp:total_loss"]))
+    assert rel_l2(x.grad, torch.from_numpy(g["temp:dlogits"])) < 1e-4
+
+
+@pytest.mark.parametrize("tag", ["t2_c3_s16", "t3_c5_s40"])
+def test_bce_loss_vs_reference_golden(dev, golden_dir, tag):
+    from sam2_video_training_b200.losses import BCECategoryLoss
+    g = np.load(os.path.join(golden_dir, f"loss_{tag}.npz"))
+    t, c, s = int(g["t"]), int(g["c"]), int(g["s"])
+    logits, targets, _ = detgen.loss_inputs(t, c, s)
+    x = logits.to(dev).requires_grad_(True)
+    out = BCECategoryLoss()([{"pred_masks_high_res": x[f]} for f in range(t)], targets.to(dev))
+    out["total_loss"].backward()
+    assert abs(float(out["total_loss"]) - float(g["bce:total_loss"])) <= LOSS_REL_TOL * abs(float(g["bce:total_loss"]))
+    assert float(out["loss_bce"]) == float(out["total_loss"])
+    assert rel_l2(x.grad, torch.from_numpy(g["bce:dlogits"])) < 1e-4
+    tg = targets.clone()
+    tg[:, :, 0, 0] = True
+    pw = [1.5, 0.5, 2.0][:c] + [1.0] * max(0, c - 3)
+    x = logits.to(dev).requires_grad_(True)
+    out = BCECategoryLoss(pos_weight=pw, logit_temperature=1.7)([{"pred_masks": x[f]} for f in range(t)], tg.to(dev))
+    out["total_loss"].backward()
+    assert abs(float(out["total_loss"]) - float(g["bce_pw:total_loss"])) <= LOSS_REL_TOL * abs(float(g["bce_pw:total_loss"]))
+    assert rel_l2(x.grad, torch.from_numpy(g["bce_pw:dlogits"])) < 1e-4
+
+
+@pytest.mark.parametrize("t,c,s", [(10, 1, 384), (2, 7, 384), (1, 13, 512), (1, 3, 250)])
+def test_multistep_loss_vs_oracle_real_shapes(dev, t, c, s):
+    """BASELINE.json shapes (cfg1: 10 x 1 x 384^2; cfg2/3 channel counts), random logits ~ N(0, 4^2),
+    elliptical targets, one empty channel where C allows; s = 250 exercises the non-vector path."""
+    from sam2_video_training_b200.losses import MultiStepMultiMasksAndIous
+    g = torch.Generator().manual_seed(5 + t + c + s)
+    logits = torch.randn(t, c, 1, s, s, generator=g) * 4
+    yy, xx = torch.meshgrid(torch.arange(s), torch.arange(s), indexing="ij")
+    targets = torch.zeros(t, c, s, s, dtype=torch.bool)
+    for f in range(t):
+        for ch in range(c):
+            if c > 2 and ch == c - 1:
+                continue
+            cx, cy = 0.3 * s + 7 * ch, 0.5 * s - 3 * f
+            targets[f, ch] = ((xx - cx) / (0.2 * s)) ** 2 + ((yy - cy) / (0.12 * s)) ** 2 < 1
+    iou = torch.rand(t, c, 1, generator=g)
+    x64 = logits.double().requires_grad_(True)
+    i64 = iou.double().requires_grad_(True)
+    ref = lo.multistep_loss([x64[f] for f in range(t)], targets, [i64[f] for f in range(t)], dict(W_FOCAL),
+                            iou_use_l1_loss=True)
+    ref["total_loss"].backward()
+    crit = MultiStepMultiMasksAndIous(dict(W_FOCAL), supervise_all_iou=True, iou_use_l1_loss=True)
+    x = logits.to(dev).requires_grad_(True)
+    ip = iou.to(dev).requires_grad_(True)
+    out = crit(_outs(x, ip), targets.to(dev))
+    out["total_loss"].backward()
+    for k in ("loss_mask", "loss_dice", "loss_iou", "total_loss"):
+        assert abs(float(out[k]) - float(ref[k])) <= LOSS_REL_TOL * abs(float(ref[k])), k
+    assert rel_l2(x.grad, x64.grad) < 1e-4
+    assert cosine(x.grad, x64.grad) > 0.99999
+    assert rel_l2(ip.grad, i64.grad) < 1e-5
+
+
+def test_loss_no_valid_masks_raises(dev):
+    from sam2_video_training_b200.losses import MultiStepMultiMasksAndIous
+    logits, targets, iou = detgen.loss_inputs(2, 3, 16)
+    targets[1] = False
+    crit = MultiStepMultiMasksAndIous(dict(W_FOCAL))
+    with pytest.raises(ValueError, match="No valid masks"):
+        crit(_outs(logits.to(dev), iou.to(dev)), targets.to(dev))
+
+
+def test_loss_frames_are_used_in_place(dev):
+    """Per-frame logits that are separate allocations (as the training wrapper produces) give the
+    same result as views of one stacked tensor."""
+    from sam2_video_training_b200.losses import MultiStepMultiMasksAndIous
+    logits, targets, iou = detgen.loss_inputs(3, 4, 32, clear=())
+    crit = MultiStepMultiMasksAndIous(dict(W_FOCAL))
+    a = crit(_outs(logits.to(dev), iou.to(dev)), targets.to(dev))
+    sep = [logits[f].to(dev).clone() for f in range(3)]
+    outs = [{"multistep_pred_multimasks_high_res": [sep[f]], "multistep_pred_ious": [iou[f].to(dev)],
+             "multistep_object_score_logits": [torch.zeros(4, 1, device=dev)]} for f in range(3)]
+    b = crit(outs, targets.to(dev))
+    assert float(a["total_loss"]) == float(b["total_loss"])

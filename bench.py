@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of SAM2 video fine-tuning on B200 (BASELINE.json metric).
+
+One "step" = one pass of the hot path over one batch of synthetic clips, per GPU:
+  for every clip frame t = 1 .. T-1 (frame 0 does not run memory attention, sam2_base.py:680-684):
+      MemoryAttention forward + backward for all objects of the batch, growing memory bank
+      M_t = min(t,7) * (N + 4) keys, upstream gradient ~ N(0,1);
+  MultiStepMultiMasksAndIous forward + backward over T frames x C objects x S^2 logits per clip;
+  (N > 1 ranks) NCCL all-reduce of the 106 parameter gradients; fused AdamW step.
+Workload at N = 1: BASELINE.json configs[1] -- 384 px (24x24 tokens), 10-frame clips, 7 memory frames
++ object pointers, 7 objects x 8 clips (B = 56), bf16 tensor-core math / fp32 accumulate.
+Prints ONE JSON line (see the task contract).  `--impl reference` times the CPU oracle port.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "memory_attn_fwd_bwd_plus_mask_loss_clip_frames_per_sec"
+UNIT = "clip-frames/s"
+
+WORKLOADS = {
+    # name: grid, frames T, objects per clip C, clips per GPU, image size S
+    "cfg2_endovis18_384px_T10_7obj_x8clips": dict(grid=24, T=10, C=7, clips=8, S=384),
+    "cfg1_384px_T10_1obj_x1clip": dict(grid=24, T=10, C=1, clips=1, S=384),
+    "cfg3_cholec_512px_T8_13obj_x1clip": dict(grid=32, T=8, C=13, clips=1, S=512),
+    "cfg4_1024px_T8_4obj_x1clip": dict(grid=64, T=8, C=4, clips=1, S=1024),
+}
+LOSS_W = {"loss_mask": 20, "loss_dice": 1, "loss_iou": 1, "loss_class": 0}
+
+
+def bank_sizes(t: int, n: int):
+    nf = min(t, 7)
+    return nf * n + 4 * nf, 4 * nf  # M, P
+
+
+def algorithmic_flops(wl) -> float:
+    """per object, per layer, fwd: self core 4N^2 d, cross core 4NMd, linears
+    4(2Nd^2) + 2(2Nd^2) + 2(2M dm d), MLP 2(2N d ff); bwd = 2.5 x core + 2 x linears."""
+    d, dm, ff, L = 256, 64, 2048, 4
+    n = wl["grid"] ** 2
+    b = wl["C"] * wl["clips"]
+    tot = 0.0
+    for t in range(1, wl["T"]):
+        m, _ = bank_sizes(t, n)
+        core = 4.0 * n * n * d + 4.0 * n * m * d
+        lin = 4 * (2.0 * n * d * d) + 2 * (2.0 * n * d * d) + 2 * (2.0 * m * dm * d) + 2 * (2.0 * n * d * ff)
+        tot += L * b * (3.5 * core + 3.0 * lin)
+    return tot
+
+
+def attention_core_flops(wl) -> float:
+    d, L = 256, 4
+    n = wl["grid"] ** 2
+    b = wl["C"] * wl["clips"]
+    return sum(L * b * 3.5 * (4.0 * n * n * d + 4.0 * n * bank_sizes(t, n)[0] * d) for t in range(1, wl["T"]))
+
+
+def make_host_inputs(wl, seed, pin):
+    """Per-step inputs as HOST tensors: per-frame current features, per-frame memory-encoder
+    features (+ pointer tokens), positional encodings, mask logits / targets / IoU predictions."""
+    g = torch.Generator().manual_seed(seed)
+    n, b, T, C, S, clips = wl["grid"] ** 2, wl["C"] * wl["clips"], wl["T"], wl["C"], wl["S"], wl["clips"]
+
+    def mk(*shape, scale=1.0, dtype=torch.float32):
+        x = (torch.randn(*shape, generator=g) * scale).to(dtype)
+        return x.pin_memory() if pin else x
+
+    h = dict(
+        curr=[mk(n, b, 256) for _ in range(1, T)],
+        curr_pos=mk(n, b, 256, scale=0.7),
+        mem_feat=[mk(n + 4, b, 64) for _ in range(min(T - 1, 7))],      # one memory frame + its 4 pointer tokens
+        mem_pos=[mk(n + 4, b, 64, scale=0.7) for _ in range(min(T - 1, 7))],
+        grad_out=[mk(n, b, 256) for _ in range(1, T)],
+        logits=[mk(C, 1, S, S, scale=4.0) for _ in range(clips * T)],   # per-frame tensors, as the wrapper produces
+        iou=[torch.rand(T, C, 1, generator=g) for _ in range(clips)],
+    )
+    yy, xx = torch.meshgrid(torch.arange(S), torch.arange(S), indexing="ij")
+    tg = []
+    for c_i in range(clips):
+        t = torch.zeros(T, C, S, S, dtype=torch.bool)
+        for f in range(T):
+            for ch in range(C):
+                if C >= 4 and ch % 8 == 7:
+                    continue  # 1 in 8 channels empty: exercises the valid filter
+                cx = S * (0.25 + 0.5 * torch.rand((), generator=g))
+                cy = S * (0.25 + 0.5 * torch.rand((), generator=g))
+                ax = S * (0.08 + 0.2 * torch.rand((), generator=g))
+                ay = S * (0.08 + 0.2 * torch.rand((), generator=g))
+                t[f, ch] = ((xx - cx) / ax) ** 2 + ((yy - cy) / ay) ** 2 < 1
+        tg.append(t.pin_memory() if pin else t)
+    h["targets"] = tg
+    return h
+
+
+def h2d_bytes(h) -> int:
+    tot = 0
+    for v in h.values():
+        for x in (v if isinstance(v, list) else [v]):
+            tot += x.numel() * x.element_size()
+    return tot
+
+
+def to_device(h, dev):
+    out = {}
+    for k, v in h.items():
+        out[k] = [x.to(dev, non_blocking=True) for x in v] if isinstance(v, list) else v.to(dev, non_blocking=True)
+    return out
+
+
+def assemble_banks(d, wl):
+    """[cond frame | older frames | pointer tokens] like sam2_base.py:691-692 (torch.cat on device)."""
+    n, T = wl["grid"] ** 2, wl["T"]
+    banks = []
+    for t in range(1, T):
+        nf = min(t, 7)
+        mem = torch.cat([d["mem_feat"][i][:n] for i in range(nf)] + [d["mem_feat"][i][n:] for i in range(nf)], dim=0)
+        pos = torch.cat([d["mem_pos"][i][:n] for i in range(nf)] + [d["mem_pos"][i][n:] for i in range(nf)], dim=0)
+        banks.append((mem, pos, 4 * nf))
+    return banks
+
+
+def run_step(model, crit, opt, d, banks, wl, world, flat_grads=None):
+    T, C = wl["T"], wl["C"]
+    for t in range(1, T):
+        mem, pos, p = banks[t - 1]
+        out = model(d["curr"][t - 1], mem, d["curr_pos"], pos, p)
+        out.backward(d["grad_out"][t - 1])
+    total = None
+    for ci in range(wl["clips"]):
+        xs = [d["logits"][ci * T + f].requires_grad_(True) for f in range(T)]
+        ip = d["iou"][ci].requires_grad_(True)
+        outs = [{"multistep_pred_multimasks_high_res": [xs[f]], "multistep_pred_ious": [ip[f]],
+                 "multistep_object_score_logits": [None]} for f in range(T)]
+        losses = crit(outs, d["targets"][ci])
+        losses["total_loss"].backward()
+        total = losses["total_loss"].detach() if total is None else total + losses["total_loss"].detach()
+        for x in xs:
+            x.grad = None
+        ip.grad = None
+    if world > 1:
+        from sam2_video_training_b200 import ddp
+        ddp.allreduce_gradients(model, world)
+    opt.step()
+    model._sam2b200_grad_bucket.zero()   # one memset for all 106 gradients
+    return total
+
+
+class ClockSampler:
+    def __init__(self, dev_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(dev_index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        res = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return res
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, reasons, mx = [], set(), None
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            # under load = top half of the samples
+            sm.sort()
+            res["sm_mhz"] = sm[len(sm) // 2 + len(sm) // 4] if len(sm) > 3 else sm[-1]
+        res["sm_max_mhz"] = mx
+        res["reasons"] = sorted(reasons)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return res
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sust=p.get("bf16_tflops_sustained", p["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+# ----------------------------------------------------------------------------- CPU oracle timing
+def cpu_oracle_sample(wl, threads):
+    """One object-clip (1 object, all T-1 attention frames fwd+bwd + loss fwd+bwd on T frames) of the
+    workload through the CPU oracle port, fp32.  Returns seconds."""
+    from oracle import attention_oracle as ao
+    from oracle import losses_oracle as lo
+    torch.set_num_threads(threads)
+    n, T, S = wl["grid"] ** 2, wl["T"], wl["S"]
+    g = torch.Generator().manual_seed(11)
+    params = {k: v.clone().requires_grad_(True) for k, v in ao.init_params(seed=0).items()}
+    curr_pos = torch.randn(n, 1, 256, generator=g) * 0.7
+    t0 = time.perf_counter()
+    for t in range(1, T):
+        m, p = bank_sizes(t, n)
+        curr = torch.randn(n, 1, 256, generator=g)
+        mem = torch.randn(m, 1, 64, generator=g)
+        pos = torch.randn(m, 1, 64, generator=g) * 0.7
+        out = ao.memory_attention(params, curr, mem, curr_pos, pos, p)
+        out.backward(torch.randn(n, 1, 256, generator=g))
+    logits = (torch.randn(T, 1, 1, S, S, generator=g) * 4).requires_grad_(True)
+    targets = torch.rand(T, 1, S, S, generator=g) > 0.8
+    iou = torch.rand(T, 1, 1, generator=g).requires_grad_(True)
+    l = lo.multistep_loss([logits[f] for f in range(T)], targets, [iou[f] for f in range(T)], dict(LOSS_W), iou_use_l1_loss=True)
+    l["total_loss"].backward()
+    return time.perf_counter() - t0
+
+
+def main_reference(args, wl_name, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    for _ in range(max(args.warmup, 0)):
+        cpu_oracle_sample(wl, threads)
+    ts = [cpu_oracle_sample(wl, threads) for _ in range(max(args.steps, 1))]
+    tmean = sum(ts) / len(ts)
+    # one object-clip = T object-frames = T / C clip-frames of this workload
+    value = (wl["T"] / wl["C"]) / tmean
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": tmean * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl_name, "sample_per_step": "1 object-clip (1 of %d objects x %d clips): %d attention frames fwd+bwd + loss on %d frames"
+                   % (wl["C"], wl["clips"], wl["T"] - 1, wl["T"])},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "oracle/ (CPU restatement of the reference, torch CPU fp32): 1 object-clip per step, scaled by 1/C to clip-frames"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2_endovis18_384px_T10_7obj_x8clips", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    wl_name, wl = args.workload, WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return main_reference(args, wl_name, wl)
+
+    import torch.distributed as dist
+    from sam2_video_training_b200 import _lib, ops
+    from sam2_video_training_b200.losses import MultiStepMultiMasksAndIous
+    from sam2_video_training_b200.modeling.memory_attention import build_memory_attention
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.load()
+    _lib.check(lib.sam2b200_check_device(local_rank), "sam2b200_check_device")
+
+    torch.manual_seed(0)
+    model = build_memory_attention(dropout=0.0).to(dev).train()   # dropout off: throughput with parity numerics
+    crit = MultiStepMultiMasksAndIous(dict(LOSS_W), supervise_all_iou=True, iou_use_l1_loss=True, check_valid=False)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-5, fused=True)
+    from sam2_video_training_b200 import ddp
+    ddp.attach_grad_bucket(model)   # all 106 gradients are views of one flat fp32 buffer
+
+    host = make_host_inputs(wl, 1234 + rank, pin=True)
+    d = to_device(host, dev)
+    banks = assemble_banks(d, wl)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (`value`) ----------------
+    for _ in range(max(args.warmup, 3)):
+        run_step(model, crit, opt, d, banks, wl, world)
+    barrier()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = lib.sam2b200_launch_count()
+    ops.PROFILE = {}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        run_step(model, crit, opt, d, banks, wl, world)
+    ev1.record()
+    barrier()
+    prof = ops.PROFILE
+    ops.PROFILE = None
+    launches = lib.sam2b200_launch_count() - launches0
+    ms = ev0.elapsed_time(ev1)
+    t_ms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_ms.item()) / args.steps
+    clk = clocks.stop() if clocks is not None else None
+    frames_per_step = wl["T"] * wl["clips"]
+    value = world * frames_per_step / (ms_per_step * 1e-3)
+
+    # ---------------- per-kernel-family device time inside the timed region ----------------
+    fam = {}
+    for name, evs in prof.items():
+        tot_ms = sum(s.elapsed_time(e) for s, e, _ in evs)
+        tot_work = sum(w for _, _, w in evs)
+        fam[name] = dict(ms=tot_ms, work=tot_work, launches=len(evs))
+    pk = peaks()
+    attn_ms = sum(fam[k]["ms"] for k in ("attn_fwd", "attn_bwd") if k in fam)
+    attn_fl = sum(fam[k]["work"] for k in ("attn_fwd", "attn_bwd") if k in fam)
+    loss_ms = sum(fam[k]["ms"] for k in ("mask_loss_fwd", "mask_loss_bwd") if k in fam)
+    loss_by = sum(fam[k]["work"] for k in ("mask_loss_fwd", "mask_loss_bwd") if k in fam)
+    dom = max(("attn_fwd", "attn_bwd"), key=lambda k: fam.get(k, {"ms": 0})["ms"])
+    ach = fam[dom]["work"] / (fam[dom]["ms"] * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "sam2b200_" + dom + " (tcgen05 kernels, all launches of the timed region)",
+                "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
+                "peak_source": pk["src"] + " sustained cuBLAS bf16", "traffic": None,
+                "attention_fwd_bwd_tflops": attn_fl / (attn_ms * 1e-3) / 1e12 if attn_ms else None,
+                "attention_share_of_step": attn_ms / (ms_per_step * args.steps) if ms_per_step else None,
+                "mask_loss": {"bound": "hbm", "achieved": loss_by / (loss_ms * 1e-3) / 1e9 if loss_ms else None, "peak": pk["hbm"],
+                              "unit": "GB/s", "frac": (loss_by / (loss_ms * 1e-3) / 1e9 / pk["hbm"]) if loss_ms else None,
+                              "bytes_per_px": "5 fwd + 9 bwd"},
+                "whole_step_tflops": algorithmic_flops(wl) / (ms_per_step * 1e-3) / 1e12}
+
+    # ---------------- end to end: host buffers, H2D inside the timed region, loss read back ----------------
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            dd = to_device(host, dev)
+            bk = assemble_banks(dd, wl)
+            tot = run_step(model, crit, opt, dd, bk, wl, world)
+            return float(tot.item())  # D2H of the step's loss
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        ev1.record()
+        barrier()
+        t2 = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t2.item()) / args.steps
+        e2e = {"value": world * frames_per_step / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(host),
+               "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cpu_oracle_sample(WORKLOADS["cfg1_384px_T10_1obj_x1clip"], threads)  # warm-up
+        ts = [cpu_oracle_sample(wl, threads) for _ in range(2)]
+        tb = min(ts)
+        cpu_baseline = {"value": (wl["T"] / wl["C"]) / tb, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": "oracle/ port, torch CPU fp32: 1 object-clip (1 of %d) = %d attention frames fwd+bwd + loss on %d x 1 x %d^2, "
+                                  "scaled by 1/C to clip-frames; best of 2 after 1 warm-up (%.1f s each)" % (
+                                      wl["C"] * wl["clips"], wl["T"] - 1, wl["T"], wl["S"], tb)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": wl_name, "tokens": wl["grid"] ** 2, "frames_per_clip": wl["T"], "objects_per_clip": wl["C"],
+                       "clips_per_gpu": wl["clips"], "mask_px": wl["S"], "memory_bank": "min(t,7) frames x (N + 4 pointer tokens)",
+                       "l2": "inputs_larger_than_L2 (%.0f MB per step)" % (h2d_bytes(host) / 1e6),
+                       "parallelism": "dp%d (clips sharded, NCCL grad all-reduce)" % world,
+                       "object_frames_per_step": wl["T"] * wl["C"] * wl["clips"],
+                       "algorithmic_tflop_per_step": algorithmic_flops(wl) / 1e12},
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "kernel_families_ms_per_step": {k: v["ms"] / args.steps for k, v in fam.items()},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

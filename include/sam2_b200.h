@@ -37,6 +37,8 @@ typedef struct CUstream_st* sam2b200_stream_t; /* == cudaStream_t */
 
 int sam2b200_version(void);
 const char* sam2b200_last_error(void);
+/* CUDA kernels launched by this library in this process so far (for bench.py's gpu_launches). */
+long long sam2b200_launch_count(void);
 /* 0 iff CUDA device `dev` is an sm_100 part. */
 int sam2b200_check_device(int dev);
 

@@ -1,4 +1,6 @@
 // Library-level entry points of libsam2b200.so (version, last error, device probe).
+#include <atomic>
+
 #include "abi_common.cuh"
 
 namespace sam2b200 {
@@ -6,9 +8,14 @@ char* last_error_buffer() {
   static thread_local char buf[512] = {0};
   return buf;
 }
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 }  // namespace sam2b200
 
 extern "C" {
+
+// Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches).
+long long sam2b200_launch_count(void) { return sam2b200::g_launches.load(std::memory_order_relaxed); }
 
 int sam2b200_version(void) { return 100; }  // 0.1.0
 

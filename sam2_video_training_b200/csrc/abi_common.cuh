@@ -15,13 +15,15 @@
 namespace sam2b200 {
 
 char* last_error_buffer();  // defined in abi.cu (thread-local, 512 bytes)
+void count_launches(int n);  // defined in abi.cu: kernels launched by this library (process-wide)
 
 inline int fail(int code, const char* msg) {
   snprintf(last_error_buffer(), 512, "%s", msg);
   return code;
 }
 
-inline int check_launch(const char* what) {
+inline int check_launch(const char* what, int n_kernels = 1) {
+  count_launches(n_kernels);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(last_error_buffer(), 512, "%s: %s", what, cudaGetErrorString(e));

@@ -232,6 +232,7 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       for (int i = 0; i < 32; ++i) { sv[i] = __uint_as_float(r0[i]); sv[32 + i] = __uint_as_float(r1[i]); }
 
       uint32_t pk[32];
+      bool acc_synced = false;
       if (MODE == MODE_FWD) {
         const int ncols = p.Lx - t * kBlockN;            // valid columns in this tile
         if (ncols < kBlockN) {
@@ -250,6 +251,7 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           const float m_new = grow ? mx : m_ref;
           const float f = ex2((m_ref - m_new) * c);      // 1.0 for rows that do not move
           mbar_wait(&sh.acc_done, (j - 1) & 1);          // PV[j-1] has landed in ACC
+          acc_synced = true;
           tc_fence_after();
 #pragma unroll 1
           for (int cc = 0; cc < kD / 32; ++cc) {
@@ -285,6 +287,10 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       }
       SAM2B200_TMEM_ST32(sbuf, pk);                       // P (bf16 pairs) over scores cols 0..31
       tmem_wait_st();
+      // Observe EVERY phase of acc_done, in order: a parity wait is only unambiguous while the
+      // waiter is at most one phase behind.  PV[j-1] was issued right after QK[j], so by now it has
+      // (almost always) completed and this wait is free; PV[j] cannot complete before our arrive.
+      if (j > 0 && !acc_synced) mbar_wait(&sh.acc_done, (j - 1) & 1);
       tc_fence_before();
       mbar_arrive(&sh.p_ready[j & 1]);
     }

@@ -409,7 +409,7 @@ int sam2b200_mask_loss_fwd(const float* const* logits, const uint8_t* targets, c
                                                        chan_sums + (size_t)f0 * C * kNumSums,
                                                        n_valid + f0, losses, f0 > 0);
   }
-  return sam2b200::check_launch("mask_loss_fwd");
+  return sam2b200::check_launch("mask_loss_fwd", 2 * ((T + kMaxFrames - 1) / kMaxFrames));
 }
 
 int sam2b200_mask_loss_bwd(const float* const* logits, float* const* dlogits, const uint8_t* targets,
@@ -445,7 +445,7 @@ int sam2b200_mask_loss_bwd(const float* const* logits, float* const* dlogits, co
           grad_losses, nullptr, nullptr, C, HW, f0, inv_temp, alpha, gamma, iou_l1, reduction_mean,
           vec_ok);
   }
-  return sam2b200::check_launch("mask_loss_bwd");
+  return sam2b200::check_launch("mask_loss_bwd", (T + kMaxFrames - 1) / kMaxFrames);
 }
 
 }  // extern "C"

@@ -24,6 +24,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from . import ops as _ops
 
 CORE_LOSS_KEY = "total_loss"  # losses.py:17
 
@@ -64,12 +65,13 @@ class _FusedMaskLossFn(torch.autograd.Function):
         n_valid = torch.empty(t, dtype=torch.int32, device=dev)
         losses = torch.zeros(4, dtype=torch.float32, device=dev)
         ptrs = _lib.ptr_array([x.data_ptr() for x in logits])
-        rc = lib.sam2b200_mask_loss_fwd(
-            ptrs, targets_u8.data_ptr(), iou_pred.data_ptr() if iou_pred is not None else None,
-            pos_weight.data_ptr() if pos_weight is not None else None, ws.data_ptr(),
-            chan_sums.data_ptr(), n_valid.data_ptr(), losses.data_ptr(), t, c, hw, mode,
-            cfg["alpha"], cfg["gamma"], cfg["inv_temp"], int(cfg["iou_l1"]), int(cfg["reduction_mean"]),
-            _stream_ptr(dev))
+        with _ops._Timed("mask_loss_fwd", 5.0 * t * c * hw):
+            rc = lib.sam2b200_mask_loss_fwd(
+                ptrs, targets_u8.data_ptr(), iou_pred.data_ptr() if iou_pred is not None else None,
+                pos_weight.data_ptr() if pos_weight is not None else None, ws.data_ptr(),
+                chan_sums.data_ptr(), n_valid.data_ptr(), losses.data_ptr(), t, c, hw, mode,
+                cfg["alpha"], cfg["gamma"], cfg["inv_temp"], int(cfg["iou_l1"]), int(cfg["reduction_mean"]),
+                _stream_ptr(dev))
         _lib.check(rc, "sam2b200_mask_loss_fwd")
         ctx.cfg = cfg
         ctx.shape = (t, c, hw)
@@ -90,12 +92,13 @@ class _FusedMaskLossFn(torch.autograd.Function):
         diou = torch.empty(t, c, dtype=torch.float32, device=dev) if iou_pred is not None else None
         lp = _lib.ptr_array([x.data_ptr() for x in logits])
         dp = _lib.ptr_array([dl[f].data_ptr() for f in range(t)])
-        rc = lib.sam2b200_mask_loss_bwd(
-            lp, dp, targets_u8.data_ptr(), iou_pred.data_ptr() if iou_pred is not None else None,
-            pos_weight.data_ptr() if pos_weight is not None else None, chan_sums.data_ptr(),
-            n_valid.data_ptr(), g.data_ptr(), diou.data_ptr() if diou is not None else None, t, c, hw,
-            cfg["mode"], cfg["alpha"], cfg["gamma"], cfg["inv_temp"], int(cfg["iou_l1"]),
-            int(cfg["reduction_mean"]), _stream_ptr(dev))
+        with _ops._Timed("mask_loss_bwd", 9.0 * t * c * hw):
+            rc = lib.sam2b200_mask_loss_bwd(
+                lp, dp, targets_u8.data_ptr(), iou_pred.data_ptr() if iou_pred is not None else None,
+                pos_weight.data_ptr() if pos_weight is not None else None, chan_sums.data_ptr(),
+                n_valid.data_ptr(), g.data_ptr(), diou.data_ptr() if diou is not None else None, t, c, hw,
+                cfg["mode"], cfg["alpha"], cfg["gamma"], cfg["inv_temp"], int(cfg["iou_l1"]),
+                int(cfg["reduction_mean"]), _stream_ptr(dev))
         _lib.check(rc, "sam2b200_mask_loss_bwd")
         grads = [dl[f].view(ctx.logit_shapes[f]) for f in range(t)]
         return (None, None, None, diou, *grads)

@@ -10,6 +10,28 @@ from . import _lib
 
 _DT = {torch.float32: 0, torch.bfloat16: 1}
 
+# Optional per-kernel-family device timing (bench.py): name -> list of (start_event, end_event,
+# algorithmic_flops).  Events are recorded on the launching stream; nothing synchronises here.
+PROFILE = None
+
+
+class _Timed:
+    def __init__(self, name, flops=0.0):
+        self.name, self.flops = name, flops
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *a):
+        if PROFILE is not None:
+            self.e.record()
+            PROFILE.setdefault(self.name, []).append((self.s, self.e, self.flops))
+        return False
+
 
 def _stream(dev) -> int:
     return torch.cuda.current_stream(dev).cuda_stream
@@ -47,9 +69,10 @@ def attn_fwd(q, k, v, scale: float, nsplit: int = 0):
     lse2 = torch.empty((b, n), dtype=torch.float32, device=q.device)
     wsb = lib.sam2b200_attn_fwd_workspace_bytes(b, n, m, nsplit)
     ws = torch.empty(wsb // 4, dtype=torch.float32, device=q.device) if wsb else None
-    rc = lib.sam2b200_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse2.data_ptr(),
-                               ws.data_ptr() if ws is not None else None, wsb, b, n, m, scale, nsplit,
-                               _stream(q.device))
+    with _Timed("attn_fwd", 4.0 * b * n * m * 256):
+        rc = lib.sam2b200_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse2.data_ptr(),
+                                   ws.data_ptr() if ws is not None else None, wsb, b, n, m, scale, nsplit,
+                                   _stream(q.device))
     _lib.check(rc, "sam2b200_attn_fwd")
     return out, lse2
 
@@ -62,9 +85,10 @@ def attn_bwd(q, k, v, out, dout, lse2, scale: float):
     dk = torch.empty((b, m, 256), dtype=torch.float32, device=q.device)
     dv = torch.empty((b, m, 256), dtype=torch.float32, device=q.device)
     delta = torch.empty((b, n), dtype=torch.float32, device=q.device)
-    rc = lib.sam2b200_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), dout.data_ptr(),
-                               lse2.data_ptr(), delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
-                               b, n, m, scale, _stream(q.device))
+    with _Timed("attn_bwd", 10.0 * b * n * m * 256):
+        rc = lib.sam2b200_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), dout.data_ptr(),
+                                   lse2.data_ptr(), delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                   b, n, m, scale, _stream(q.device))
     _lib.check(rc, "sam2b200_attn_bwd")
     return dq, dk, dv
 

@@ -1,0 +1,67 @@
+"""world_size-2 gloo tests (CPU) of the data-parallel plumbing: clip sharding + the single flat
+gradient all-reduce."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from sam2_video_training_b200 import ddp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, use_bucket, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.LayerNorm(16), torch.nn.Linear(16, 4))
+    if use_bucket:
+        bucket = ddp.attach_grad_bucket(model)
+        assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in model.parameters())
+    clips = ddp.shard_clips(7, rank, world)
+    x = torch.stack([torch.full((8,), float(c + 1)) for c in clips])
+    loss = model(x).pow(2).sum() / 7.0 * world  # so that the mean over ranks == full-batch gradient
+    loss.backward()
+    ddp.allreduce_gradients(model, world)
+    flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    q.put((rank, clips, flat))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("use_bucket", [True, False])
+def test_grad_allreduce_world2(use_bucket):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, use_bucket, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == [0, 2, 4, 6] and res[1][1] == [1, 3, 5]
+    assert torch.allclose(res[0][2], res[1][2])
+    # single-process reference over all 7 clips
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.LayerNorm(16), torch.nn.Linear(16, 4))
+    x = torch.stack([torch.full((8,), float(c + 1)) for c in range(7)])
+    (model(x).pow(2).sum() / 7.0).backward()
+    ref = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    assert torch.allclose(res[0][2], ref, rtol=1e-5, atol=1e-6)
+
+
+def test_shard_clips_partition():
+    for world in (1, 2, 4, 8):
+        allc = sorted(c for r in range(world) for c in ddp.shard_clips(13, r, world))
+        assert allc == list(range(13))

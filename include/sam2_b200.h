@@ -60,14 +60,35 @@ int sam2b200_rope_apply(const void* x, int in_dtype, void* out, int out_dtype, c
  * CTAs (for grids that do not fill 148 SMs) and needs the workspace below. */
 int sam2b200_attn_default_nsplit(int B, int N, int M);
 size_t sam2b200_attn_fwd_workspace_bytes(int B, int N, int M, int nsplit);
-int sam2b200_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse2,
-                      void* workspace, size_t workspace_bytes, int B, int N, int M, float scale,
+int sam2b200_attn_fwd(const void* q, const void* k, const void* v, void* out, float* out_f32 /* NULL or fp32 copy */,
+                      float* lse2, void* workspace, size_t workspace_bytes, int B, int N, int M, float scale,
                       int nsplit, sam2b200_stream_t stream);
 /* Backward (what autograd derives for transformer.py:306).  delta: [B, N] fp32 scratch;
  * dq: [B, N, 256], dk, dv: [B, M, 256] fp32, fully overwritten. */
-int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout,
-                      const float* lse2, float* delta, float* dq, float* dk, float* dv, int B, int N,
+int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* out /* bf16, or NULL if */,
+                      const float* out_f32 /* the fp32 copy is given */, const void* dout, const float* lse2, float* delta, float* dq, float* dk, float* dv, int B, int N,
                       int M, float scale, sam2b200_stream_t stream);
+
+/* ---- fused LayerNorm / residual / bias-gradient kernels (d_model = 256) -------------------
+ * Replace nn.LayerNorm + residual add + dropout(0) + dtype casts of MemoryAttentionLayer
+ * (sam2_video/model/modeling/memory_attention.py:58-99, :162) and what autograd derives for them.
+ * ln_fwd: x' = x + res (res bf16, optional; x' stored to x_out if given), y = LN(x') as bf16 and/or
+ * fp32, mean / rstd saved for the backward.  tr_b > 0 writes y_f32 seq-first [n][b][256] from
+ * batch-first rows b*tr_n + n (the transpose at memory_attention.py:164-167). */
+int sam2b200_ln_fwd(const float* x, const void* res_bf16, float* x_out, const float* gamma, const float* beta,
+                    void* y_bf16, float* y_f32, float* mean, float* rstd, long long rows, float eps, int tr_b,
+                    int tr_n, sam2b200_stream_t stream);
+size_t sam2b200_ln_bwd_workspace_bytes(long long rows);
+/* g_out = g_in + dLN/dx(dy); dgamma += sum dy*xhat; dbeta += sum dy.  Exactly one of dy_bf16 / dy_f32. */
+int sam2b200_ln_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* mean, const float* rstd,
+                    const float* gamma, const float* g_in, float* g_out, float* dgamma, float* dbeta,
+                    void* workspace, long long rows, int tr_b, int tr_n, sam2b200_stream_t stream);
+size_t sam2b200_colsum_workspace_bytes(long long rows, int C);
+/* Bias gradients (what autograd's sum over rows produces for nn.Linear):
+ * mode 0: in_f32 [R,C] -> io_bf16 (cast) and colsum += column sums; mode 1: io_bf16 *= (h_bf16 > 0) in
+ * place (ReLU backward, memory_attention.py:97) and colsum += sums; mode 2: colsum += sums of io_bf16. */
+int sam2b200_colsum(int mode, const float* in_f32, void* io_bf16, const void* h_bf16, float* colsum, void* workspace,
+                    long long rows, int C, long long ld, sam2b200_stream_t stream);
 
 /* ---- fused mask loss --------------------------------------------------------------------
  * mode SAM2B200_LOSS_MULTISTEP replaces MultiStepMultiMasksAndIous._update_losses and the three

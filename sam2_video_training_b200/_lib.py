@@ -26,9 +26,15 @@ _SIGNATURES = {
                                     c_int, c_int, c_void_p]),
     "sam2b200_attn_default_nsplit": (c_int, [c_int, c_int, c_int]),
     "sam2b200_attn_fwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
-    "sam2b200_attn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+    "sam2b200_attn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                   c_int, c_int, c_int, c_float, c_int, c_void_p]),
-    "sam2b200_attn_bwd": (c_int, [c_void_p] * 10 + [c_int, c_int, c_int, c_float, c_void_p]),
+    "sam2b200_attn_bwd": (c_int, [c_void_p] * 11 + [c_int, c_int, c_int, c_float, c_void_p]),
+    "sam2b200_ln_fwd": (c_int, [c_void_p] * 9 + [c_longlong, c_float, c_int, c_int, c_void_p]),
+    "sam2b200_ln_bwd_workspace_bytes": (c_size_t, [c_longlong]),
+    "sam2b200_ln_bwd": (c_int, [c_void_p] * 11 + [c_longlong, c_int, c_int, c_void_p]),
+    "sam2b200_colsum_workspace_bytes": (c_size_t, [c_longlong, c_int]),
+    "sam2b200_colsum": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int,
+                                c_longlong, c_void_p]),
     "sam2b200_mask_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_longlong]),
     "sam2b200_mask_loss_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_float,

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsam2b200.so")
-SOURCES = ["abi.cu", "mask_loss.cu", "attn.cu"]
+SOURCES = ["abi.cu", "mask_loss.cu", "attn.cu", "glue.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math" if False else "-DNDEBUG"]
 

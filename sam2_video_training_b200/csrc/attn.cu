@@ -68,20 +68,30 @@ __global__ void rope_kernel(const TIn* __restrict__ x, TOut* __restrict__ out,
 }
 
 // ------------------------------------------------------------------ Delta = rowsum(dO o O)
-__global__ void delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+template <bool O_F32>
+__global__ void delta_kernel(const void* __restrict__ o_, const __nv_bfloat16* __restrict__ d_o,
                              float* __restrict__ delta, long long rows) {
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  uint4 a = *reinterpret_cast<const uint4*>(o + row * 256 + lane * 8);
+  float ov[8];
+  if (O_F32) {
+    const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(o_) + row * 256 + lane * 8);
+    const float4 a = p[0], b = p[1];
+    ov[0] = a.x; ov[1] = a.y; ov[2] = a.z; ov[3] = a.w; ov[4] = b.x; ov[5] = b.y; ov[6] = b.z; ov[7] = b.w;
+  } else {
+    uint4 a = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(o_) + row * 256 + lane * 8);
+    const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(ha[i]); ov[2 * i] = f.x; ov[2 * i + 1] = f.y; }
+  }
   uint4 b = *reinterpret_cast<const uint4*>(d_o + row * 256 + lane * 8);
-  const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
   const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&b);
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 fa = __bfloat1622float2(ha[i]), fb = __bfloat1622float2(hb[i]);
-    s += fa.x * fb.x + fa.y * fb.y;
+    float2 fb = __bfloat1622float2(hb[i]);
+    s += ov[2 * i] * fb.x + ov[2 * i + 1] * fb.y;
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
@@ -91,8 +101,8 @@ __global__ void delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfl
 // ------------------------------------------------------------------ split-KV combine
 // part_acc: [nsplit, rows, 256] fp32 un-normalised, part_ml: [nsplit, rows, 2] = (m*c, l)
 __global__ void combine_kernel(const float* __restrict__ part_acc, const float* __restrict__ part_ml,
-                               __nv_bfloat16* __restrict__ out, float* __restrict__ lse2,
-                               long long rows, int nsplit) {
+                               __nv_bfloat16* __restrict__ out, float* __restrict__ out_f32,
+                               float* __restrict__ lse2, long long rows, int nsplit) {
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -114,6 +124,11 @@ __global__ void combine_kernel(const float* __restrict__ part_acc, const float* 
   u.x = sm100::pack_bf16(acc[0] * inv, acc[1] * inv); u.y = sm100::pack_bf16(acc[2] * inv, acc[3] * inv);
   u.z = sm100::pack_bf16(acc[4] * inv, acc[5] * inv); u.w = sm100::pack_bf16(acc[6] * inv, acc[7] * inv);
   *reinterpret_cast<uint4*>(out + row * 256 + lane * 8) = u;
+  if (out_f32 != nullptr) {
+    float4* fp = reinterpret_cast<float4*>(out_f32 + row * 256 + lane * 8);
+    fp[0] = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+    fp[1] = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
+  }
   if (lane == 0) lse2[row] = mmax + log2f(lsum);
 }
 
@@ -174,8 +189,8 @@ size_t sam2b200_attn_fwd_workspace_bytes(int B, int N, int M, int nsplit) {
 
 // q: [B, N, 256], k, v: [B, M, 256] bf16 (q, k already rotated); out: [B, N, 256] bf16;
 // lse2: [B, N] fp32 = log2(sum_j exp(scale * q.k_j)).
-int sam2b200_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse2, void* workspace,
-                      size_t workspace_bytes, int B, int N, int M, float scale, int nsplit,
+int sam2b200_attn_fwd(const void* q, const void* k, const void* v, void* out, float* out_f32, float* lse2,
+                      void* workspace, size_t workspace_bytes, int B, int N, int M, float scale, int nsplit,
                       cudaStream_t stream) {
   if (!q || !k || !v || !out || !lse2 || B <= 0 || N <= 0 || M <= 0 || B > 65535 || !aligned16(q) ||
       !aligned16(k) || !aligned16(v) || !aligned16(out))
@@ -193,7 +208,7 @@ int sam2b200_attn_fwd(const void* q, const void* k, const void* v, void* out, fl
   if ((rc = sam2b200::make_rows256_map(&map_v, v, B, M, attn::kBlockN))) return rc;
   attn::TwoGemmParams p{};
   p.a = (const __nv_bfloat16*)q; p.La = N; p.Lx = M; p.scale_log2 = scale * kLog2e;
-  p.out = (__nv_bfloat16*)out; p.lse2 = lse2; p.tiles_per_split = tiles_per_split;
+  p.out = (__nv_bfloat16*)out; p.out_f32 = out_f32; p.lse2 = lse2; p.tiles_per_split = tiles_per_split;
   if (nsplit > 1) {
     p.part_acc = (float*)workspace;
     p.part_ml = p.part_acc + (size_t)nsplit * B * N * 256;
@@ -205,24 +220,29 @@ int sam2b200_attn_fwd(const void* q, const void* k, const void* v, void* out, fl
   if ((rc = sam2b200::check_launch("attn_fwd"))) return rc;
   if (nsplit > 1) {
     const long long rows = (long long)B * N;
-    combine_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, stream>>>(p.part_acc, p.part_ml, p.out, lse2, rows, nsplit);
+    combine_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, stream>>>(p.part_acc, p.part_ml, p.out, out_f32, lse2, rows, nsplit);
     if ((rc = sam2b200::check_launch("attn_fwd combine"))) return rc;
   }
   return SAM2B200_OK;
 }
 
-// Backward of out = softmax(scale q k^T) v.  All of q, k, v, out, dout bf16; lse2 from the forward.
+// Backward of out = softmax(scale q k^T) v.  q, k, v, dout bf16; lse2 from the forward; the forward's
+// output either as bf16 (`out`) or, preferred, its fp32 copy (`out_f32`): Delta = rowsum(dO o O) then has
+// no per-row rounding bias, which matters when dP - Delta cancels (smooth / highly correlated values).
 // delta: [B, N] fp32 scratch.  dq: [B, N, 256], dk, dv: [B, M, 256] fp32 outputs (fully written).
-int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout,
-                      const float* lse2, float* delta, float* dq, float* dk, float* dv, int B, int N, int M,
+int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* out, const float* out_f32,
+                      const void* dout, const float* lse2, float* delta, float* dq, float* dk, float* dv, int B, int N, int M,
                       float scale, cudaStream_t stream) {
-  if (!q || !k || !v || !out || !dout || !lse2 || !delta || !dq || !dk || !dv || B <= 0 || N <= 0 || M <= 0 ||
-      B > 65535 || !aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(out) || !aligned16(dout) ||
+  if (!q || !k || !v || (!out && !out_f32) || !dout || !lse2 || !delta || !dq || !dk || !dv || B <= 0 || N <= 0 || M <= 0 ||
+      B > 65535 || !aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(dout) ||
       !aligned16(dq) || !aligned16(dk) || !aligned16(dv))
     return sam2b200::fail(SAM2B200_ERR_INVALID, "attn_bwd: bad arguments");
   int rc;
   const long long rows = (long long)B * N;
-  delta_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, stream>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, rows);
+  if (out_f32 != nullptr)
+    delta_kernel<true><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, stream>>>(out_f32, (const __nv_bfloat16*)dout, delta, rows);
+  else
+    delta_kernel<false><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, stream>>>(out, (const __nv_bfloat16*)dout, delta, rows);
   if ((rc = sam2b200::check_launch("attn_bwd delta"))) return rc;
 
   CUtensorMap map_q64, map_k64, map_v64, map_do64, map_do128, map_v128;

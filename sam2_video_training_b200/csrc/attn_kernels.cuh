@@ -54,6 +54,7 @@ struct TwoGemmParams {
   float scale_log2;            // softmax scale * log2(e)
   // FWD outputs
   __nv_bfloat16* out;          // [B, La, 256] bf16 (nsplit == 1)
+  float* out_f32;              // optional fp32 copy of out (kept for Delta = rowsum(dO o O) in the backward)
   float* lse2;                 // [B, La] log2-domain LSE (FWD: output; DV: input, length Lx)
   float* part_acc;             // [nsplit, B, La, 256] fp32 un-normalised partials (nsplit > 1)
   float* part_ml;              // [nsplit, B, La, 2]  (m_ref * c, l)
@@ -316,6 +317,14 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
               u.z = pack_bf16(__uint_as_float(o[8 * v + 4]) * inv_l, __uint_as_float(o[8 * v + 5]) * inv_l);
               u.w = pack_bf16(__uint_as_float(o[8 * v + 6]) * inv_l, __uint_as_float(o[8 * v + 7]) * inv_l);
               *reinterpret_cast<uint4*>(orow + cc * 32 + v * 8) = u;
+            }
+            if (p.out_f32 != nullptr) {
+              float* frow = p.out_f32 + ((long long)b * p.La + a_row_idx) * kD + cc * 32;
+#pragma unroll
+              for (int v = 0; v < 8; ++v)
+                *reinterpret_cast<float4*>(frow + v * 4) =
+                    make_float4(__uint_as_float(o[4 * v]) * inv_l, __uint_as_float(o[4 * v + 1]) * inv_l,
+                                __uint_as_float(o[4 * v + 2]) * inv_l, __uint_as_float(o[4 * v + 3]) * inv_l);
             }
           }
         }

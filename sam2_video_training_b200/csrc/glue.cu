@@ -1,0 +1,309 @@
+// HBM-bound fused element-wise / reduction kernels around the GEMMs and attention kernels of one
+// MemoryAttentionLayer (d_model = 256).  They replace, per layer, the reference's
+//   nn.LayerNorm x3 + residual adds + dropout(0) + dtype casts   (memory_attention.py:58-99)
+//   autograd's LayerNorm backward, bias-gradient reductions, ReLU backward
+// with one pass over the data each (the ATen kernels measured 4-10x the algorithmic bytes):
+//   ln_fwd        : x' = x + residual(bf16) -> fp32;  y = LN(x') -> bf16 (+ fp32); mean, rstd
+//   ln_bwd        : g_out = g_in + LN'(dy);  d gamma, d beta  (two-stage deterministic reduction)
+//   cast_colsum   : fp32 [R,C] -> bf16 copy + column sums (bias gradient of the consumer GEMM)
+//   colsum / relu : bf16 [R,C] column sums, optionally masking by (h > 0) in place (ReLU backward)
+// All kernels: 128-bit accesses, one warp per 256-wide row, no atomics.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "abi_common.cuh"
+
+namespace {
+
+constexpr int kD = 256;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(f[4], f[5]), d = __floats2bfloat162_rn(f[6], f[7]);
+  u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+  u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+  return u;
+}
+
+// ------------------------------------------------------------------ LayerNorm forward
+// One warp per row.  x: [R,256] fp32; res: [R,256] bf16 or null; x_out: fp32 or null (x + res);
+// y16 / y32: normalised output (either may be null).  out_ld_rows: if > 0, y32 is written
+// transposed as [n][b] from rows ordered [b][n] (final norm back to seq-first): row r = b*Nn + n
+// goes to (n*Bb + b).
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ res, float* __restrict__ x_out,
+              const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ y16,
+              float* __restrict__ y32, float* __restrict__ mean, float* __restrict__ rstd, long long rows,
+              float eps, int tr_b, int tr_n) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xp = reinterpret_cast<const float4*>(x + row * kD + lane * 8);
+  float v[8];
+  float4 a = xp[0], b = xp[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  if (res != nullptr) {
+    float r[8];
+    unpack8(*reinterpret_cast<const uint4*>(res + row * kD + lane * 8), r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += r[i];
+    if (x_out != nullptr) {
+      float4* op = reinterpret_cast<float4*>(x_out + row * kD + lane * 8);
+      op[0] = make_float4(v[0], v[1], v[2], v[3]);
+      op[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+  const float mu = warp_sum(s) * (1.0f / kD);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const float d = v[i] - mu; q += d * d; }
+  const float rs = rsqrtf(warp_sum(q) * (1.0f / kD) + eps);
+  if (lane == 0) { if (mean) mean[row] = mu; if (rstd) rstd[row] = rs; }
+  const float4* gp = reinterpret_cast<const float4*>(gamma + lane * 8);
+  const float4* bp = reinterpret_cast<const float4*>(beta + lane * 8);
+  const float4 g0 = gp[0], g1 = gp[1], b0 = bp[0], b1 = bp[1];
+  const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  float y[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) y[i] = (v[i] - mu) * rs * gg[i] + bb[i];
+  if (y16 != nullptr) *reinterpret_cast<uint4*>(y16 + row * kD + lane * 8) = pack8(y);
+  if (y32 != nullptr) {
+    long long orow = row;
+    if (tr_b > 0) { const long long bi = row / tr_n, ni = row % tr_n; orow = ni * tr_b + bi; }
+    float4* op = reinterpret_cast<float4*>(y32 + orow * kD + lane * 8);
+    op[0] = make_float4(y[0], y[1], y[2], y[3]);
+    op[1] = make_float4(y[4], y[5], y[6], y[7]);
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm backward
+// dy: bf16 [R,256] (dy16) or fp32 (dy32; tr_b > 0 reads it transposed like ln_fwd writes y32).
+// g_out = (g_in ? g_in : 0) + dx.  Per-block partial d gamma / d beta -> part[blk][2][256].
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ dy32, const float* __restrict__ x,
+              const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+              const float* __restrict__ g_in, float* __restrict__ g_out, float* __restrict__ part, long long rows,
+              int tr_b, int tr_n) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float4* gp = reinterpret_cast<const float4*>(gamma + lane * 8);
+  const float4 g0 = gp[0], g1 = gp[1];
+  const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  float dgam[8], dbet[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { dgam[i] = 0.f; dbet[i] = 0.f; }
+  const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp; row < rows; row += warps_total) {
+    float dy[8], xv[8];
+    if (dy16 != nullptr) {
+      unpack8(*reinterpret_cast<const uint4*>(dy16 + row * kD + lane * 8), dy);
+    } else {
+      long long irow = row;
+      if (tr_b > 0) { const long long bi = row / tr_n, ni = row % tr_n; irow = ni * tr_b + bi; }
+      const float4* dp = reinterpret_cast<const float4*>(dy32 + irow * kD + lane * 8);
+      const float4 a = dp[0], b = dp[1];
+      dy[0] = a.x; dy[1] = a.y; dy[2] = a.z; dy[3] = a.w; dy[4] = b.x; dy[5] = b.y; dy[6] = b.z; dy[7] = b.w;
+    }
+    const float4* xp = reinterpret_cast<const float4*>(x + row * kD + lane * 8);
+    const float4 a = xp[0], b = xp[1];
+    xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w; xv[4] = b.x; xv[5] = b.y; xv[6] = b.z; xv[7] = b.w;
+    const float mu = mean[row], rs = rstd[row];
+    float xh[8], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      xh[i] = (xv[i] - mu) * rs;
+      const float dg = dy[i] * gg[i];
+      s1 += dg; s2 += dg * xh[i];
+      dgam[i] += dy[i] * xh[i];
+      dbet[i] += dy[i];
+    }
+    s1 = warp_sum(s1) * (1.0f / kD);
+    s2 = warp_sum(s2) * (1.0f / kD);
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = rs * (dy[i] * gg[i] - s1 - xh[i] * s2);
+    if (g_in != nullptr) {
+      const float4* ip = reinterpret_cast<const float4*>(g_in + row * kD + lane * 8);
+      const float4 c = ip[0], d = ip[1];
+      o[0] += c.x; o[1] += c.y; o[2] += c.z; o[3] += c.w; o[4] += d.x; o[5] += d.y; o[6] += d.z; o[7] += d.w;
+    }
+    float4* op = reinterpret_cast<float4*>(g_out + row * kD + lane * 8);
+    op[0] = make_float4(o[0], o[1], o[2], o[3]);
+    op[1] = make_float4(o[4], o[5], o[6], o[7]);
+  }
+  __shared__ float sh[8][2][kD];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sh[warp][0][lane * 8 + i] = dgam[i]; sh[warp][1][lane * 8 + i] = dbet[i]; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * kD; i += blockDim.x) {
+    const int which = i / kD, c = i % kD;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += sh[w][which][c];
+    part[((long long)blockIdx.x * 2 + which) * kD + c] = s;
+  }
+}
+
+// out[c] += sum_blk part[blk][c]   (fixed order -> deterministic)
+__global__ void partial_reduce_add_kernel(const float* __restrict__ part, int nblk, int width,
+                                          float* __restrict__ out0, float* __restrict__ out1, int split) {
+  // part: [nblk][width]; columns [0, split) go to out0, [split, width) to out1 (LN: gamma | beta)
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= width) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += part[(long long)b * width + c];
+  if (c < split) out0[c] += s; else out1[c - split] += s;
+}
+
+// ------------------------------------------------------------------ column sums (bias gradients)
+// Thread owns 8 consecutive columns; a block covers (256 / (C/8)) rows per iteration.
+// MODE 0: in = fp32 [R,C], writes bf16 copy to out16 (cast) + column sums
+// MODE 1: in = bf16 [R,C] (io16), masked in place by (h16 > 0) + column sums   (ReLU backward)
+// MODE 2: in = bf16 [R,C] with row stride ld, plain column sums
+template <int MODE>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ in32, __nv_bfloat16* __restrict__ io16, const __nv_bfloat16* __restrict__ h16,
+              float* __restrict__ part, long long rows, int C, long long ld) {
+  const int tpr = C >> 3;                         // threads per row
+  const int rpb = blockDim.x / tpr;               // rows per block iteration
+  const int cgrp = threadIdx.x % tpr;
+  const int rsub = threadIdx.x / tpr;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (rsub < rpb) {
+    for (long long row = (long long)blockIdx.x * rpb + rsub; row < rows; row += (long long)gridDim.x * rpb) {
+      float v[8];
+      if (MODE == 0) {
+        const float4* p = reinterpret_cast<const float4*>(in32 + row * ld + cgrp * 8);
+        const float4 a = p[0], b = p[1];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        *reinterpret_cast<uint4*>(io16 + row * C + cgrp * 8) = pack8(v);
+        // sum what the consumer GEMM will see (the bf16-rounded values)
+        float r[8];
+        uint4 u = pack8(v);
+        unpack8(u, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = r[i];
+      } else {
+        uint4 u = *reinterpret_cast<const uint4*>(io16 + row * ld + cgrp * 8);
+        unpack8(u, v);
+        if (MODE == 1) {
+          float hv[8];
+          unpack8(*reinterpret_cast<const uint4*>(h16 + row * ld + cgrp * 8), hv);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = hv[i] > 0.f ? v[i] : 0.f;
+          *reinterpret_cast<uint4*>(io16 + row * ld + cgrp * 8) = pack8(v);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+  }
+  // reduce the rpb row-groups of the block through shared memory
+  extern __shared__ float sh[];                   // [rpb][C]
+  if (rsub < rpb) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sh[rsub * C + cgrp * 8 + i] = acc[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < rpb; ++r) s += sh[r * C + c];
+    part[(long long)blockIdx.x * C + c] = s;
+  }
+}
+
+int grid_for_rows(long long rows, int rows_per_block) {
+  long long g = (rows + rows_per_block - 1) / rows_per_block;
+  const long long cap = 148 * 8;
+  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+// y = LayerNorm(x + res) over the last dim (256).  Any of res / x_out / y16 / y32 / mean / rstd may be
+// NULL.  tr_b > 0: y32 is written seq-first ([n][b][256]) from batch-first rows (b*tr_n + n).
+int sam2b200_ln_fwd(const float* x, const void* res_bf16, float* x_out, const float* gamma, const float* beta,
+                    void* y_bf16, float* y_f32, float* mean, float* rstd, long long rows, float eps, int tr_b,
+                    int tr_n, cudaStream_t stream) {
+  if (!x || !gamma || !beta || rows <= 0 || !aligned16(x) || (res_bf16 && !aligned16(res_bf16)) ||
+      (x_out && !aligned16(x_out)) || (y_bf16 && !aligned16(y_bf16)) || (y_f32 && !aligned16(y_f32)))
+    return sam2b200::fail(SAM2B200_ERR_INVALID, "ln_fwd: bad arguments");
+  const long long blocks = (rows * 32 + 255) / 256;
+  ln_fwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, (const __nv_bfloat16*)res_bf16, x_out, gamma, beta,
+                                                       (__nv_bfloat16*)y_bf16, y_f32, mean, rstd, rows, eps, tr_b, tr_n);
+  return sam2b200::check_launch("ln_fwd");
+}
+
+size_t sam2b200_ln_bwd_workspace_bytes(long long rows) {
+  return (size_t)grid_for_rows(rows, 8 * 8) * 2 * kD * sizeof(float);
+}
+
+// g_out = g_in + dLN/dx; dgamma += ..., dbeta += ... (accumulated into the given fp32 buffers).
+// Exactly one of dy_bf16 / dy_f32 is non-NULL.
+int sam2b200_ln_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* mean, const float* rstd,
+                    const float* gamma, const float* g_in, float* g_out, float* dgamma, float* dbeta,
+                    void* workspace, long long rows, int tr_b, int tr_n, cudaStream_t stream) {
+  if ((!dy_bf16) == (!dy_f32) || !x || !mean || !rstd || !gamma || !g_out || !dgamma || !dbeta || !workspace ||
+      rows <= 0)
+    return sam2b200::fail(SAM2B200_ERR_INVALID, "ln_bwd: bad arguments");
+  const int nblk = grid_for_rows(rows, 8 * 8);
+  float* part = static_cast<float*>(workspace);
+  ln_bwd_kernel<<<nblk, 256, 0, stream>>>((const __nv_bfloat16*)dy_bf16, dy_f32, x, mean, rstd, gamma, g_in, g_out,
+                                          part, rows, tr_b, tr_n);
+  partial_reduce_add_kernel<<<2, 256, 0, stream>>>(part, nblk, 2 * kD, dgamma, dbeta, kD);
+  return sam2b200::check_launch("ln_bwd", 2);
+}
+
+size_t sam2b200_colsum_workspace_bytes(long long rows, int C) {
+  const int rpb = 256 / (C / 8);
+  return (size_t)grid_for_rows(rows, rpb * 16) * C * sizeof(float);
+}
+
+// mode 0: in_f32 [R,C] -> out bf16 [R,C] (cast) and colsum += column sums of the rounded values
+// mode 1: io_bf16 [R,C] *= (h_bf16 > 0) in place and colsum += column sums   (ReLU backward + bias grad)
+// mode 2: colsum += column sums of io_bf16 (row stride ld elements)
+// C must be a multiple of 8 with C/8 dividing 256 (256, 512, 1024, 2048) or equal to 768.
+int sam2b200_colsum(int mode, const float* in_f32, void* io_bf16, const void* h_bf16, float* colsum, void* workspace,
+                    long long rows, int C, long long ld, cudaStream_t stream) {
+  if (rows <= 0 || C <= 0 || (C % 8) || (C / 8) > 256 || !colsum || !workspace || !io_bf16 || (mode == 0 && !in_f32) ||
+      (mode == 1 && !h_bf16) || mode < 0 || mode > 2)
+    return sam2b200::fail(SAM2B200_ERR_INVALID, "colsum: bad arguments");
+  const int tpr = C / 8;
+  const int rpb = 256 / tpr;
+  if (ld <= 0) ld = C;
+  const int nblk = grid_for_rows(rows, rpb * 16);
+  float* part = static_cast<float*>(workspace);
+  const size_t sh = (size_t)rpb * C * sizeof(float);
+  if (mode == 0)
+    colsum_kernel<0><<<nblk, 256, sh, stream>>>(in_f32, (__nv_bfloat16*)io_bf16, nullptr, part, rows, C, ld);
+  else if (mode == 1)
+    colsum_kernel<1><<<nblk, 256, sh, stream>>>(nullptr, (__nv_bfloat16*)io_bf16, (const __nv_bfloat16*)h_bf16, part,
+                                                rows, C, ld);
+  else
+    colsum_kernel<2><<<nblk, 256, sh, stream>>>(nullptr, (__nv_bfloat16*)io_bf16, nullptr, part, rows, C, ld);
+  partial_reduce_add_kernel<<<(C + 255) / 256, 256, 0, stream>>>(part, nblk, C, colsum, colsum, C);
+  return sam2b200::check_launch("colsum", 2);
+}
+
+}  // extern "C"

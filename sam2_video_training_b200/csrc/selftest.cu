@@ -140,11 +140,11 @@ static int run_attn(const AttnCase& c) {
 
   DevBuf<__nv_bfloat16> dq_(q.size()), dk_(k.size()), dv_(v.size()), dout_(dout.size()), dout_o(q.size());
   dq_.up(to_bf16(q)); dk_.up(to_bf16(k)); dv_.up(to_bf16(v)); dout_.up(to_bf16(dout));
-  DevBuf<float> lse((size_t)B * N);
+  DevBuf<float> lse((size_t)B * N), o32(q.size());
   int nsplit = c.nsplit > 0 ? c.nsplit : sam2b200_attn_default_nsplit(B, N, M);
   size_t wsb = sam2b200_attn_fwd_workspace_bytes(B, N, M, nsplit);
   DevBuf<char> ws(wsb);
-  int rc = sam2b200_attn_fwd(dq_.p, dk_.p, dv_.p, dout_o.p, lse.p, wsb ? ws.p : nullptr, wsb, B, N, M, scale, nsplit, 0);
+  int rc = sam2b200_attn_fwd(dq_.p, dk_.p, dv_.p, dout_o.p, o32.p, lse.p, wsb ? ws.p : nullptr, wsb, B, N, M, scale, nsplit, 0);
   if (rc) { printf("[FAIL] %s: attn_fwd rc=%d %s\n", c.name, rc, sam2b200_last_error()); return 1; }
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("[FAIL] %s: fwd sync: %s\n", c.name, cudaGetErrorString(e)); exit(4); }
@@ -172,7 +172,7 @@ static int run_attn(const AttnCase& c) {
 
   // backward uses the GPU forward's out/lse (as training does)
   DevBuf<float> gq(q.size()), gk(k.size()), gv(v.size()), delta((size_t)B * N);
-  rc = sam2b200_attn_bwd(dq_.p, dk_.p, dv_.p, dout_o.p, dout_.p, lse.p, delta.p, gq.p, gk.p, gv.p, B, N, M, scale, 0);
+  rc = sam2b200_attn_bwd(dq_.p, dk_.p, dv_.p, nullptr, o32.p, dout_.p, lse.p, delta.p, gq.p, gk.p, gv.p, B, N, M, scale, 0);
   if (rc) { printf("[FAIL] %s: attn_bwd rc=%d %s\n", c.name, rc, sam2b200_last_error()); return 1; }
   e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("[FAIL] %s: bwd sync: %s\n", c.name, cudaGetErrorString(e)); exit(4); }

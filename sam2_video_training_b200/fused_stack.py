@@ -1,0 +1,257 @@
+"""Whole-stack autograd.Function for SAM2 MemoryAttention on B200.
+
+One hand-scheduled forward / backward for the 4-layer stack of
+sam2_video/model/modeling/memory_attention.py:119-169 in its shipped configuration
+(configs/sam2/sam2.1_hiera_t.yaml:29-60).  Compared with composing nn.Modules under autograd it
+  * keeps the residual stream in fp32 and fuses residual-add + LayerNorm + bf16 cast (ln_fwd),
+    LayerNorm backward + residual-gradient add (ln_bwd), cast + bias-gradient (colsum) into single
+    passes of the hand-written kernels in csrc/glue.cu,
+  * runs RoPE + attention forward/backward in the tcgen05 kernels (csrc/attn_kernels.cuh),
+  * leaves only the dense projections / MLP to cuBLAS (torch.mm / addmm, bf16 in, fp32 accumulate;
+    weight gradients are produced directly in fp32 with out_dtype),
+  * packs `memory + pos` once per call instead of once per layer (memory_attention.py:75-76).
+PyTorch is used for device memory, streams and the cuBLAS calls only.
+"""
+from __future__ import annotations
+
+import math
+from typing import List
+
+import torch
+
+from . import _lib
+from .ops import _Timed, attn_bwd, attn_fwd, rope_apply
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+# per-layer parameter order == reference named_parameters() order (26 tensors per layer)
+_LAYER_KEYS = [
+    "sa.q.w", "sa.q.b", "sa.k.w", "sa.k.b", "sa.v.w", "sa.v.b", "sa.o.w", "sa.o.b",
+    "ca.q.w", "ca.q.b", "ca.k.w", "ca.k.b", "ca.v.w", "ca.v.b", "ca.o.w", "ca.o.b",
+    "l1.w", "l1.b", "l2.w", "l2.b", "n1.w", "n1.b", "n2.w", "n2.b", "n3.w", "n3.b",
+]
+_NPL = len(_LAYER_KEYS)
+
+
+def _stream(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def ln_fwd(x, res, gamma, beta, want_f32_seq_first=None, eps=1e-5):
+    """x: [R,256] fp32; res: [R,256] bf16 or None.  Returns (y, x_new, mean, rstd); y is bf16 [R,256] or,
+    if want_f32_seq_first=(B, N), fp32 [N, B, 256]."""
+    lib = _lib.load()
+    rows = x.shape[0]
+    dev = x.device
+    x_new = torch.empty_like(x) if res is not None else x
+    mean = torch.empty(rows, dtype=F32, device=dev)
+    rstd = torch.empty(rows, dtype=F32, device=dev)
+    if want_f32_seq_first is None:
+        y = torch.empty((rows, 256), dtype=BF16, device=dev)
+        y16, y32, tb, tn = y.data_ptr(), None, 0, 0
+    else:
+        tb, tn = want_f32_seq_first
+        y = torch.empty((tn, tb, 256), dtype=F32, device=dev)
+        y16, y32 = None, y.data_ptr()
+    rc = lib.sam2b200_ln_fwd(x.data_ptr(), res.data_ptr() if res is not None else None,
+                             x_new.data_ptr() if res is not None else None, gamma.data_ptr(), beta.data_ptr(),
+                             y16, y32, mean.data_ptr(), rstd.data_ptr(), rows, eps, tb, tn, _stream(dev))
+    _lib.check(rc, "sam2b200_ln_fwd")
+    return y, x_new, mean, rstd
+
+
+def ln_bwd(dy, x, mean, rstd, gamma, g_in, dgamma, dbeta, seq_first=None):
+    lib = _lib.load()
+    rows = x.shape[0]
+    dev = x.device
+    g_out = torch.empty_like(x)
+    ws = torch.empty(lib.sam2b200_ln_bwd_workspace_bytes(rows) // 4, dtype=F32, device=dev)
+    tb, tn = seq_first if seq_first is not None else (0, 0)
+    is16 = dy.dtype == BF16
+    rc = lib.sam2b200_ln_bwd(dy.data_ptr() if is16 else None, None if is16 else dy.data_ptr(), x.data_ptr(),
+                             mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                             g_in.data_ptr() if g_in is not None else None, g_out.data_ptr(), dgamma.data_ptr(),
+                             dbeta.data_ptr(), ws.data_ptr(), rows, tb, tn, _stream(dev))
+    _lib.check(rc, "sam2b200_ln_bwd")
+    return g_out
+
+
+def _colsum(mode, in32, io16, h16, colsum, rows, c, ld=0):
+    lib = _lib.load()
+    dev = io16.device
+    ws = torch.empty(max(lib.sam2b200_colsum_workspace_bytes(rows, c) // 4, 1), dtype=F32, device=dev)
+    rc = lib.sam2b200_colsum(mode, in32.data_ptr() if in32 is not None else None, io16.data_ptr(),
+                             h16.data_ptr() if h16 is not None else None, colsum.data_ptr(), ws.data_ptr(), rows, c,
+                             ld, _stream(dev))
+    _lib.check(rc, "sam2b200_colsum")
+
+
+def cast_colsum(g32, colsum):
+    """bf16 copy of g32 [R,C] + colsum += column sums (bias gradient of the GEMM that consumes it)."""
+    out = torch.empty(g32.shape, dtype=BF16, device=g32.device)
+    _colsum(0, g32, out, None, colsum, g32.shape[0], g32.shape[1])
+    return out
+
+
+def relu_bwd_colsum_(dh16, h16, colsum):
+    _colsum(1, None, dh16, h16, colsum, dh16.shape[0], dh16.shape[1])
+
+
+def colsum_bf16(x16, colsum):
+    _colsum(2, None, x16, None, colsum, x16.shape[0], x16.shape[1])
+
+
+def _mm32(a, b):
+    """fp32 result of a bf16 x bf16 product (weight gradients)."""
+    return torch.mm(a, b, out_dtype=F32)
+
+
+class MemoryAttentionStackFn(torch.autograd.Function):
+    """out[N,B,256] = MemoryAttention(curr, memory, curr_pos, memory_pos, num_obj_ptr_tokens)."""
+
+    @staticmethod
+    def forward(ctx, meta, curr, curr_pos, memory, memory_pos, *params):
+        nl, p_excl, table, pos_at_input = meta["num_layers"], meta["num_k_exclude_rope"], meta["table"], meta["pos_enc_at_input"]
+        n, b, d = curr.shape
+        m = memory.shape[0]
+        r, rm = b * n, b * m
+        scale = 1.0 / math.sqrt(d)
+        n_rope_k = m - p_excl
+        # ---- pack inputs once per call (memory_attention.py:140-148; the reference re-adds pos per layer)
+        x = curr.float()
+        if pos_at_input and curr_pos is not None:
+            x = x + 0.1 * curr_pos
+        x = x.transpose(0, 1).contiguous().view(r, d)
+        memk = (memory + memory_pos).transpose(0, 1).to(BF16).contiguous().view(rm, -1)
+        memv = memory.transpose(0, 1).to(BF16).contiguous().view(rm, -1)
+        wb = [p.detach().to(BF16) if p.dim() == 2 else p.detach().to(BF16) for p in params]  # bf16 copies (small)
+        saved: List[torch.Tensor] = []
+        res = None
+        for l in range(nl):
+            P = dict(zip(_LAYER_KEYS, params[l * _NPL:(l + 1) * _NPL]))
+            W = dict(zip(_LAYER_KEYS, wb[l * _NPL:(l + 1) * _NPL]))
+            # ---- self attention (memory_attention.py:58-64)
+            y1, x, mean1, rstd1 = ln_fwd(x, res, P["n1.w"], P["n1.b"])
+            q = torch.addmm(W["sa.q.b"], y1, W["sa.q.w"].t())
+            k = torch.addmm(W["sa.k.b"], y1, W["sa.k.w"].t())
+            v = torch.addmm(W["sa.v.b"], y1, W["sa.v.w"].t())
+            q_rot = rope_apply(q.view(b, n, d), table, n)
+            k_rot = rope_apply(k.view(b, n, d), table, n)
+            o, o32, lse = attn_fwd(q_rot, k_rot, v.view(b, n, d), scale, meta["nsplit"])
+            sa = torch.addmm(W["sa.o.b"], o.view(r, d), W["sa.o.w"].t())
+            # ---- cross attention to the memory bank (memory_attention.py:66-81)
+            y2, x1, mean2, rstd2 = ln_fwd(x, sa, P["n2.w"], P["n2.b"])
+            q2 = torch.addmm(W["ca.q.b"], y2, W["ca.q.w"].t())
+            k2 = torch.addmm(W["ca.k.b"], memk, W["ca.k.w"].t())
+            v2 = torch.addmm(W["ca.v.b"], memv, W["ca.v.w"].t())
+            q2_rot = rope_apply(q2.view(b, n, d), table, n)
+            k2_rot = rope_apply(k2.view(b, m, d), table, n_rope_k)
+            o2, o2_32, lse2 = attn_fwd(q2_rot, k2_rot, v2.view(b, m, d), scale, meta["nsplit"])
+            ca = torch.addmm(W["ca.o.b"], o2.view(r, d), W["ca.o.w"].t())
+            # ---- MLP (memory_attention.py:95-98)
+            y3, x2, mean3, rstd3 = ln_fwd(x1, ca, P["n3.w"], P["n3.b"])
+            h = torch._addmm_activation(W["l1.b"], y3, W["l1.w"].t(), use_gelu=False)  # bias + ReLU epilogue
+            mlp = torch.addmm(W["l2.b"], h, W["l2.w"].t())
+            saved += [x, mean1, rstd1, y1, q_rot, k_rot, v, o, o32, lse,
+                      x1, mean2, rstd2, y2, q2_rot, k2_rot, v2, o2, o2_32, lse2,
+                      x2, mean3, rstd3, y3, h]
+            x, res = x2, mlp
+        gamma_f, beta_f = params[nl * _NPL], params[nl * _NPL + 1]
+        out, x_fin, mean_f, rstd_f = ln_fwd(x, res, gamma_f, beta_f, want_f32_seq_first=(b, n))
+        saved += [x_fin, mean_f, rstd_f, memk, memv, table]
+        ctx.save_for_backward(*saved, *params)
+        ctx.n_saved = len(saved)
+        ctx.meta = dict(nl=nl, n=n, b=b, m=m, scale=scale, n_rope_k=n_rope_k, pos_at_input=pos_at_input,
+                        has_pos=curr_pos is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        mt = ctx.meta
+        nl, n, b, m, scale, n_rope_k = mt["nl"], mt["n"], mt["b"], mt["m"], mt["scale"], mt["n_rope_k"]
+        d = 256
+        r, rm = b * n, b * m
+        saved = ctx.saved_tensors[:ctx.n_saved]
+        params = ctx.saved_tensors[ctx.n_saved:]
+        x_fin, mean_f, rstd_f, memk, memv, table = saved[-6:]
+        dev = x_fin.device
+        need_curr, need_pos, need_mem, need_mpos = ctx.needs_input_grad[1:5]
+        need_memgrad = need_mem or need_mpos
+        wb = [p.detach().to(BF16) for p in params]
+        # gradient buffers for vector parameters (accumulated by the kernels); matrices come from mm
+        grads = [None] * len(params)
+        for i, p in enumerate(params):
+            if p.dim() == 1:
+                grads[i] = torch.zeros_like(p, dtype=F32)
+        grad_out = grad_out.contiguous().float()
+        g = ln_bwd(grad_out, x_fin, mean_f, rstd_f, params[nl * _NPL], None, grads[nl * _NPL], grads[nl * _NPL + 1],
+                   seq_first=(b, n))
+        dmemk = torch.zeros((rm, memk.shape[1]), dtype=F32, device=dev) if need_memgrad else None
+        dmemv = torch.zeros((rm, memv.shape[1]), dtype=F32, device=dev) if need_mem else None
+        per = 25
+        for l in reversed(range(nl)):
+            (x0, mean1, rstd1, y1, q_rot, k_rot, v, o, o32, lse, x1, mean2, rstd2, y2, q2_rot, k2_rot, v2, o2, o2_32,
+             lse2, x2, mean3, rstd3, y3, h) = saved[l * per:(l + 1) * per]
+            base = l * _NPL
+            ix = {k: base + i for i, k in enumerate(_LAYER_KEYS)}
+            W = {k: wb[ix[k]] for k in _LAYER_KEYS}
+            P = {k: params[ix[k]] for k in _LAYER_KEYS}
+            # ---- MLP backward
+            dm = cast_colsum(g, grads[ix["l2.b"]])
+            grads[ix["l2.w"]] = _mm32(dm.t(), h)
+            dh = torch.mm(dm, W["l2.w"])
+            relu_bwd_colsum_(dh, h, grads[ix["l1.b"]])
+            grads[ix["l1.w"]] = _mm32(dh.t(), y3)
+            dy3 = torch.mm(dh, W["l1.w"])
+            g = ln_bwd(dy3, x2, mean3, rstd3, P["n3.w"], g, grads[ix["n3.w"]], grads[ix["n3.b"]])
+            # ---- cross attention backward
+            dca = cast_colsum(g, grads[ix["ca.o.b"]])
+            grads[ix["ca.o.w"]] = _mm32(dca.t(), o2.view(r, d))
+            do2 = torch.mm(dca, W["ca.o.w"])
+            dq_r, dk_r, dv32 = attn_bwd(q2_rot, k2_rot, v2.view(b, m, d), None, o2_32, do2.view(b, n, d), lse2, scale)
+            dq2 = rope_apply(dq_r, table, n, inverse=True).view(r, d)
+            dk2 = rope_apply(dk_r, table, n_rope_k, inverse=True).view(rm, d)
+            dv2 = dv32.to(BF16).view(rm, d)
+            colsum_bf16(dq2, grads[ix["ca.q.b"]])
+            colsum_bf16(dk2, grads[ix["ca.k.b"]])
+            colsum_bf16(dv2, grads[ix["ca.v.b"]])
+            grads[ix["ca.q.w"]] = _mm32(dq2.t(), y2)
+            grads[ix["ca.k.w"]] = _mm32(dk2.t(), memk)
+            grads[ix["ca.v.w"]] = _mm32(dv2.t(), memv)
+            if need_memgrad:
+                dmemk.add_(torch.mm(dk2, W["ca.k.w"], out_dtype=F32))
+            if need_mem:
+                dmemv.add_(torch.mm(dv2, W["ca.v.w"], out_dtype=F32))
+            dy2 = torch.mm(dq2, W["ca.q.w"])
+            g = ln_bwd(dy2, x1, mean2, rstd2, P["n2.w"], g, grads[ix["n2.w"]], grads[ix["n2.b"]])
+            # ---- self attention backward
+            dsa = cast_colsum(g, grads[ix["sa.o.b"]])
+            grads[ix["sa.o.w"]] = _mm32(dsa.t(), o.view(r, d))
+            do = torch.mm(dsa, W["sa.o.w"])
+            dq_r, dk_r, dv32 = attn_bwd(q_rot, k_rot, v.view(b, n, d), None, o32, do.view(b, n, d), lse, scale)
+            dqkv = torch.empty((r, 3 * d), dtype=BF16, device=dev)
+            dqkv[:, :d] = rope_apply(dq_r, table, n, inverse=True).view(r, d)
+            dqkv[:, d:2 * d] = rope_apply(dk_r, table, n, inverse=True).view(r, d)
+            dqkv[:, 2 * d:] = dv32.view(r, d)
+            bsum = torch.zeros(3 * d, dtype=F32, device=dev)
+            colsum_bf16(dqkv, bsum)
+            grads[ix["sa.q.b"]], grads[ix["sa.k.b"]], grads[ix["sa.v.b"]] = bsum[:d], bsum[d:2 * d], bsum[2 * d:]
+            dw = _mm32(dqkv.t(), y1)                     # [768, 256] = d(Wq | Wk | Wv) in one GEMM
+            grads[ix["sa.q.w"]], grads[ix["sa.k.w"]], grads[ix["sa.v.w"]] = dw[:d], dw[d:2 * d], dw[2 * d:]
+            wqkv = torch.cat([W["sa.q.w"], W["sa.k.w"], W["sa.v.w"]], dim=0)
+            dy1 = torch.mm(dqkv, wqkv)                   # contraction over 768 with fp32 accumulation
+            g = ln_bwd(dy1, x0, mean1, rstd1, P["n1.w"], g, grads[ix["n1.w"]], grads[ix["n1.b"]])
+        # ---- unpack input gradients
+        d_curr = d_pos = d_mem = d_mpos = None
+        if need_curr or need_pos:
+            gx = g.view(b, n, d).transpose(0, 1)
+            if need_curr:
+                d_curr = gx.contiguous()
+            if need_pos and mt["has_pos"] and mt["pos_at_input"]:
+                d_pos = gx * 0.1
+        if need_mpos:
+            d_mpos = dmemk.view(b, m, -1).transpose(0, 1).contiguous()
+        if need_mem:
+            d_mem = (dmemk + dmemv).view(b, m, -1).transpose(0, 1).contiguous()
+        return (None, d_curr, d_pos, d_mem, d_mpos, *grads)

@@ -99,6 +99,38 @@ class MemoryAttention(nn.Module):
         self.norm = nn.LayerNorm(d_model)
         self.pos_enc_at_input = pos_enc_at_input
         self.batch_first = batch_first
+        # True: one hand-scheduled autograd.Function for the whole stack (fused_stack.py) whenever the
+        # stack has the shipped SAM2 configuration; False: compose the per-module path below.
+        self.use_fused_stack = True
+        self.attn_nsplit = 0
+
+    def _fused_eligible(self) -> bool:
+        for layer in self.layers:
+            if not isinstance(layer, MemoryAttentionLayer):
+                return False
+            sa, ca = layer.self_attn, layer.cross_attn_image
+            if not (type(sa) is RoPEAttention and type(ca) is RoPEAttention):
+                return False
+            if (layer.pos_enc_at_attn or not layer.pos_enc_at_cross_attn_keys or layer.pos_enc_at_cross_attn_queries
+                    or layer.activation_str != "relu" or not ca.rope_k_repeat or ca.kv_in_dim != 64
+                    or layer.d_model != 256 or not self.batch_first):
+                return False
+            if self.training and (layer.dropout_value > 0 or sa.dropout_p > 0 or ca.dropout_p > 0):
+                return False  # dropout active: use the composed path (residual dropouts via nn.Dropout)
+        return True
+
+    def _forward_fused(self, curr, memory, curr_pos, memory_pos, num_obj_ptr_tokens):
+        from ..fused_stack import MemoryAttentionStackFn
+        n = curr.shape[0]
+        m = memory.shape[0]
+        ca0 = self.layers[0].cross_attn_image
+        if (m - num_obj_ptr_tokens) % n != 0:
+            raise ValueError("rotated key count must be a multiple of the query count (position_encoding.py:230)")
+        table = ca0._table(n, curr.device)
+        meta = dict(num_layers=self.num_layers, num_k_exclude_rope=int(num_obj_ptr_tokens), table=table,
+                    pos_enc_at_input=bool(self.pos_enc_at_input), nsplit=int(self.attn_nsplit))
+        params = [p for _, p in self.named_parameters()]
+        return MemoryAttentionStackFn.apply(meta, curr, curr_pos, memory, memory_pos, *params)
 
     def forward(self, curr: torch.Tensor, memory: torch.Tensor, curr_pos: Optional[Tensor] = None,
                 memory_pos: Optional[Tensor] = None, num_obj_ptr_tokens: int = 0):
@@ -110,6 +142,8 @@ class MemoryAttention(nn.Module):
         if not curr.is_cuda:
             raise _lib.Sam2B200Error("MemoryAttention (B200 path) needs CUDA tensors: no CPU fallback")
         _lib.load()  # fail loudly before any compute if the CUDA library is missing
+        if self.use_fused_stack and self._fused_eligible():
+            return self._forward_fused(curr, memory, curr_pos, memory_pos, num_obj_ptr_tokens)
         output = curr.float()
         if self.pos_enc_at_input and curr_pos is not None:
             output = output + 0.1 * curr_pos

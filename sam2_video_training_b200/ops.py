@@ -55,8 +55,8 @@ def rope_apply(x: torch.Tensor, table: torch.Tensor, n_rope: int, inverse: bool 
     return out
 
 
-def attn_fwd(q, k, v, scale: float, nsplit: int = 0):
-    """q: [B,N,256], k, v: [B,M,256] bf16 contiguous -> (out bf16 [B,N,256], lse2 fp32 [B,N])."""
+def attn_fwd(q, k, v, scale: float, nsplit: int = 0, keep_f32: bool = True):
+    """q: [B,N,256], k, v: [B,M,256] bf16 contiguous -> (out bf16 [B,N,256], out fp32 or None, lse2 fp32 [B,N])."""
     lib = _lib.load()
     b, n, d = q.shape
     m = k.shape[1]
@@ -66,18 +66,20 @@ def attn_fwd(q, k, v, scale: float, nsplit: int = 0):
     if nsplit <= 0:
         nsplit = lib.sam2b200_attn_default_nsplit(b, n, m)
     out = torch.empty_like(q)
+    out32 = torch.empty((b, n, 256), dtype=torch.float32, device=q.device) if keep_f32 else None
     lse2 = torch.empty((b, n), dtype=torch.float32, device=q.device)
     wsb = lib.sam2b200_attn_fwd_workspace_bytes(b, n, m, nsplit)
     ws = torch.empty(wsb // 4, dtype=torch.float32, device=q.device) if wsb else None
     with _Timed("attn_fwd", 4.0 * b * n * m * 256):
-        rc = lib.sam2b200_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse2.data_ptr(),
+        rc = lib.sam2b200_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+                                   out32.data_ptr() if out32 is not None else None, lse2.data_ptr(),
                                    ws.data_ptr() if ws is not None else None, wsb, b, n, m, scale, nsplit,
                                    _stream(q.device))
     _lib.check(rc, "sam2b200_attn_fwd")
-    return out, lse2
+    return out, out32, lse2
 
 
-def attn_bwd(q, k, v, out, dout, lse2, scale: float):
+def attn_bwd(q, k, v, out, out32, dout, lse2, scale: float):
     lib = _lib.load()
     b, n, _ = q.shape
     m = k.shape[1]
@@ -86,7 +88,8 @@ def attn_bwd(q, k, v, out, dout, lse2, scale: float):
     dv = torch.empty((b, m, 256), dtype=torch.float32, device=q.device)
     delta = torch.empty((b, n), dtype=torch.float32, device=q.device)
     with _Timed("attn_bwd", 10.0 * b * n * m * 256):
-        rc = lib.sam2b200_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), dout.data_ptr(),
+        rc = lib.sam2b200_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr() if out is not None else None,
+                                   out32.data_ptr() if out32 is not None else None, dout.data_ptr(),
                                    lse2.data_ptr(), delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
                                    b, n, m, scale, _stream(q.device))
     _lib.check(rc, "sam2b200_attn_bwd")
@@ -106,8 +109,8 @@ class RopeAttentionFn(torch.autograd.Function):
         q_rot = rope_apply(q, table, q.shape[1])
         k_rot = rope_apply(k, table, n_rope_k)
         vb = v.to(torch.bfloat16).contiguous()
-        out, lse2 = attn_fwd(q_rot, k_rot, vb, scale, nsplit)
-        ctx.save_for_backward(q_rot, k_rot, vb, out, lse2, table)
+        out, out32, lse2 = attn_fwd(q_rot, k_rot, vb, scale, nsplit)
+        ctx.save_for_backward(q_rot, k_rot, vb, out32, lse2, table)
         ctx.scale = scale
         ctx.n_rope_k = n_rope_k
         ctx.in_dtypes = (q.dtype, k.dtype, v.dtype)
@@ -115,9 +118,9 @@ class RopeAttentionFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        q_rot, k_rot, vb, out, lse2, table = ctx.saved_tensors
+        q_rot, k_rot, vb, out32, lse2, table = ctx.saved_tensors
         dout = dout.to(torch.bfloat16).contiguous()
-        dq_rot, dk_rot, dv = attn_bwd(q_rot, k_rot, vb, out, dout, lse2, ctx.scale)
+        dq_rot, dk_rot, dv = attn_bwd(q_rot, k_rot, vb, None, out32, dout, lse2, ctx.scale)
         dq = rope_apply(dq_rot, table, q_rot.shape[1], inverse=True, out_dtype=_out_dt(ctx.in_dtypes[0]))
         dk = rope_apply(dk_rot, table, ctx.n_rope_k, inverse=True, out_dtype=_out_dt(ctx.in_dtypes[1]))
         return dq.to(ctx.in_dtypes[0]), dk.to(ctx.in_dtypes[1]), dv.to(ctx.in_dtypes[2]), None, None, None

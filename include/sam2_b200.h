@@ -63,11 +63,16 @@ size_t sam2b200_attn_fwd_workspace_bytes(int B, int N, int M, int nsplit);
 int sam2b200_attn_fwd(const void* q, const void* k, const void* v, void* out, float* out_f32 /* NULL or fp32 copy */,
                       float* lse2, void* workspace, size_t workspace_bytes, int B, int N, int M, float scale,
                       int nsplit, sam2b200_stream_t stream);
-/* Backward (what autograd derives for transformer.py:306).  delta: [B, N] fp32 scratch;
- * dq: [B, N, 256], dk, dv: [B, M, 256] fp32, fully overwritten. */
+/* Backward (what autograd derives for transformer.py:296-306).  delta: [B, N] fp32 scratch.
+ * dq: [B, N, ldq], dk: [B, M, ldk], dv: [B, M, ldv], fp32 (grad_dtype 0) or bf16 (1), first 256 columns
+ * fully overwritten.  With rope_table != NULL the conjugate rotation is fused into the epilogue (all rows
+ * of dq, rows [0, n_rope_k) of dk; table row = row % rope_period), i.e. the outputs are gradients with
+ * respect to the un-rotated projections (the backward of apply_rotary_enc + the slice write-back). */
 int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* out /* bf16, or NULL if */,
-                      const float* out_f32 /* the fp32 copy is given */, const void* dout, const float* lse2, float* delta, float* dq, float* dk, float* dv, int B, int N,
-                      int M, float scale, sam2b200_stream_t stream);
+                      const float* out_f32 /* the fp32 copy is given */, const void* dout, const float* lse2,
+                      float* delta, void* dq, void* dk, void* dv, int grad_dtype, int ldq, int ldk, int ldv,
+                      const float* rope_table, int rope_period, int n_rope_k, int B, int N, int M, float scale,
+                      sam2b200_stream_t stream);
 
 /* ---- fused LayerNorm / residual / bias-gradient kernels (d_model = 256) -------------------
  * Replace nn.LayerNorm + residual add + dropout(0) + dtype casts of MemoryAttentionLayer

@@ -229,13 +229,19 @@ int sam2b200_attn_fwd(const void* q, const void* k, const void* v, void* out, fl
 // Backward of out = softmax(scale q k^T) v.  q, k, v, dout bf16; lse2 from the forward; the forward's
 // output either as bf16 (`out`) or, preferred, its fp32 copy (`out_f32`): Delta = rowsum(dO o O) then has
 // no per-row rounding bias, which matters when dP - Delta cancels (smooth / highly correlated values).
-// delta: [B, N] fp32 scratch.  dq: [B, N, 256], dk, dv: [B, M, 256] fp32 outputs (fully written).
+// delta: [B, N] fp32 scratch.  dq: [B, N, ldq], dk: [B, M, ldk], dv: [B, M, ldv] (fp32 if grad_dtype == 0,
+// bf16 if 1), fully written in their first 256 columns.  If rope_table != NULL the conjugate axial rotation
+// is applied in the epilogue: to every row of dq and to rows [0, n_rope_k) of dk (table row = row % rope_period),
+// i.e. dq / dk are gradients with respect to the UN-rotated projections.
 int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* out, const float* out_f32,
-                      const void* dout, const float* lse2, float* delta, float* dq, float* dk, float* dv, int B, int N, int M,
-                      float scale, cudaStream_t stream) {
+                      const void* dout, const float* lse2, float* delta, void* dq, void* dk, void* dv,
+                      int grad_dtype, int ldq, int ldk, int ldv, const float* rope_table, int rope_period,
+                      int n_rope_k, int B, int N, int M, float scale, cudaStream_t stream) {
   if (!q || !k || !v || (!out && !out_f32) || !dout || !lse2 || !delta || !dq || !dk || !dv || B <= 0 || N <= 0 || M <= 0 ||
       B > 65535 || !aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(dout) ||
-      !aligned16(dq) || !aligned16(dk) || !aligned16(dv))
+      !aligned16(dq) || !aligned16(dk) || !aligned16(dv) || (grad_dtype != 0 && grad_dtype != 1) ||
+      ldq < 256 || ldk < 256 || ldv < 256 || (ldq % 8) || (ldk % 8) || (ldv % 8) ||
+      (rope_table && (rope_period <= 0 || n_rope_k < 0 || n_rope_k > M)))
     return sam2b200::fail(SAM2B200_ERR_INVALID, "attn_bwd: bad arguments");
   int rc;
   const long long rows = (long long)B * N;
@@ -252,12 +258,14 @@ int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* o
   if ((rc = sam2b200::make_rows256_map(&map_do64, dout, B, N, attn::kBlockN))) return rc;
   if ((rc = sam2b200::make_rows256_map(&map_do128, dout, B, N, attn::kBlockM))) return rc;
   if ((rc = sam2b200::make_rows256_map(&map_v128, v, B, M, attn::kBlockM))) return rc;
+  const float2* table = reinterpret_cast<const float2*>(rope_table);
 
   // dV = P^T dO: fixed K block, stream (Q, dO) tiles
   {
     attn::TwoGemmParams p{};
     p.a = (const __nv_bfloat16*)k; p.La = M; p.Lx = N; p.scale_log2 = scale * kLog2e;
-    p.lse2 = const_cast<float*>(lse2); p.acc_out = dv;
+    p.lse2 = const_cast<float*>(lse2);
+    p.gout = attn::GradOut{dv, ldv, grad_dtype, nullptr, 0, 1};
     p.tiles_per_split = (N + attn::kBlockN - 1) / attn::kBlockN;
     const size_t smem = sizeof(attn::SharedStorage) + 1024;
     if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_DV>, smem))) return rc;
@@ -270,7 +278,8 @@ int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* o
   {
     attn::ThreeGemmParams p{};
     p.a1 = (const __nv_bfloat16*)k; p.La = M; p.Lx = N; p.scale_log2 = scale * kLog2e; p.scale = scale;
-    p.lse2 = lse2; p.delta = delta; p.acc_out = dk;
+    p.lse2 = lse2; p.delta = delta;
+    p.gout = attn::GradOut{dk, ldk, grad_dtype, table, table ? n_rope_k : 0, table ? rope_period : 1};
     if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DK>, smem3))) return rc;
     dim3 grid((M + attn::kBlockM - 1) / attn::kBlockM, B, 1);
     attn::three_gemm_kernel<attn::MODE_DK><<<grid, attn::kThreads, smem3, stream>>>(map_v128, map_q64, map_do64, p);
@@ -280,7 +289,8 @@ int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* o
   {
     attn::ThreeGemmParams p{};
     p.a1 = (const __nv_bfloat16*)q; p.La = N; p.Lx = M; p.scale_log2 = scale * kLog2e; p.scale = scale;
-    p.lse2 = lse2; p.delta = delta; p.acc_out = dq;
+    p.lse2 = lse2; p.delta = delta;
+    p.gout = attn::GradOut{dq, ldq, grad_dtype, table, table ? N : 0, table ? rope_period : 1};
     if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DQ>, smem3))) return rc;
     dim3 grid((N + attn::kBlockM - 1) / attn::kBlockM, B, 1);
     attn::three_gemm_kernel<attn::MODE_DQ><<<grid, attn::kThreads, smem3, stream>>>(map_do128, map_k64, map_v64, p);

@@ -1,5 +1,5 @@
 // sm_100a flash-style attention kernels for SAM2 memory attention: ONE head, head_dim 256,
-// bf16 operands (already rotated by the axial RoPE pre-pass, rope.cu), fp32 accumulation.
+// bf16 operands (q, k already rotated by the axial RoPE pre-pass, attn.cu), fp32 accumulation.
 //
 // Two kernel templates cover forward and backward ("Attention kernels"):
 //
@@ -15,13 +15,15 @@
 //   * the fixed 128 x 256 operand A lives in TENSOR MEMORY as the bf16 A-operand of tcgen05.mma
 //     (.kind::f16, A from TMEM), written there once from registers with tcgen05.st;
 //   * streamed 64 x 256 tiles arrive by TMA (cp.async.bulk.tensor, 128-byte swizzle) into a
-//     3-stage shared-memory ring; the SAME tile is consumed K-major (scores GEMM, contraction
-//     over the 256 features) and MN-major (accumulate GEMM, contraction over the 64 rows);
+//     shared-memory ring; the SAME tile is consumed K-major (scores GEMM, contraction over the
+//     256 features) and MN-major (accumulate GEMM, contraction over the 64 rows);
 //   * fp32 accumulators (scores 128 x 64, ACC 128 x 256) live in tensor memory; the
 //     probability tile is written back to tensor memory as bf16 (tcgen05.st) and fed to the
 //     second GEMM as its A operand, so it never touches shared memory;
-//   * warp roles: warps 0-3 = softmax / epilogue (one thread per accumulator row = TMEM lane),
-//     warp 4 = TMA producer, warp 5 = tcgen05.mma issuer + TMEM allocator.
+//   * warp roles (320 threads): warps 0-7 = softmax / epilogue -- TWO warps per 32-lane TMEM
+//     quarter (warp w and w+4 own lanes 32*(w%4)..+31), each owning half of the tile's 64 columns,
+//     so every SM sub-partition has two warps to overlap tcgen05.ld / MUFU / FMA latencies;
+//     warp 8 = TMA producer, warp 9 = tcgen05.mma issuer + TMEM allocator.
 #pragma once
 
 #include "sm100.cuh"
@@ -33,19 +35,37 @@ using namespace sm100;
 constexpr int kD = 256;            // head dim
 constexpr int kBlockM = 128;       // rows of the fixed operand (TMEM lanes)
 constexpr int kBlockN = 64;        // rows of a streamed tile
+constexpr int kHalfN = kBlockN / 2;
 constexpr int kStages = 3;
 constexpr int kTileBytes = kBlockN * kD * 2;        // 32 KB
 constexpr int kChunkBytes = kBlockN * 128;          // one 64-column slab of a tile: 8 KB
-constexpr int kNumSoftmaxThreads = 128;
-constexpr int kThreads = 192;
+constexpr int kNumSoftmaxWarps = 8;
+constexpr int kNumSoftmaxThreads = kNumSoftmaxWarps * 32;
+constexpr int kProducerWarp = 8;
+constexpr int kMmaWarp = 9;
+constexpr int kThreads = 320;
 
 // tensor-memory column map (512 columns allocated)
 constexpr uint32_t kColAcc = 0;      // 256 fp32 columns: ACC (O / dV)
 constexpr uint32_t kColA = 256;      // 128 columns: fixed operand A, bf16 pairs
-constexpr uint32_t kColS0 = 384;     // 64 fp32 columns: scores buffer 0 (P overwrites cols 0..31)
+constexpr uint32_t kColS0 = 384;     // 64 fp32 columns: scores buffer 0
 constexpr uint32_t kColS1 = 448;     // scores buffer 1
+// Inside a scores buffer the softmax warp that owns columns [32h, 32h+32) overwrites ITS OWN first 16
+// columns with the 32 bf16 probabilities (16 packed columns): P lives at +0..15 (keys 0-31) and
+// +32..47 (keys 32-63).  k-step ks (16 keys = 8 packed columns) of the accumulate GEMM reads:
+__device__ __forceinline__ uint32_t p_col_of_kstep(int ks) { return (ks < 2) ? ks * 8 : 32 + (ks - 2) * 8; }
 
 enum { MODE_FWD = 0, MODE_DV = 1 };
+
+// Optional fused epilogue for gradient outputs: conjugate axial rotation + bf16 store with a row stride.
+struct GradOut {
+  void* ptr;                   // [B, La, ld] bf16 or fp32
+  int ld;                      // row stride in elements (>= 256)
+  int is_bf16;
+  const float2* rope_table;    // [period, 128] (cos, sin) or nullptr = no rotation
+  int rope_rows;               // rows [0, rope_rows) of every batch item are un-rotated (conjugate)
+  int rope_period;             // table row = row % rope_period
+};
 
 struct TwoGemmParams {
   const __nv_bfloat16* a;      // [B, La, 256] fixed operand (Q in FWD, K in DV)
@@ -58,8 +78,7 @@ struct TwoGemmParams {
   float* lse2;                 // [B, La] log2-domain LSE (FWD: output; DV: input, length Lx)
   float* part_acc;             // [nsplit, B, La, 256] fp32 un-normalised partials (nsplit > 1)
   float* part_ml;              // [nsplit, B, La, 2]  (m_ref * c, l)
-  // DV output
-  float* acc_out;              // [B, La, 256] fp32 (dV)
+  GradOut gout;                // DV output (dV)
   int tiles_per_split;
 };
 
@@ -74,15 +93,18 @@ struct SharedStorage {
   uint64_t p_ready[2];
   uint64_t acc_done;
   uint64_t a_ready;
-  float colvec[2][kBlockN];   // DV: LSE2 of the tile's columns
+  float colvec[2][kBlockN];    // DV: LSE2 of the tile's columns
+  float xchg[2][2][kBlockM];   // [buffer][half][row]: row-max exchange between the two halves of a row
+  float lsum[2][kBlockM];      // [half][row]: row-sum exchange in the epilogue
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void load_fixed_operand_to_tmem(const __nv_bfloat16* a_row, bool valid,
-                                                           uint32_t taddr) {
-  // one thread = one row: 256 bf16 = 32 x 16 B; tcgen05.st 32 packed columns at a time
+// Each of the two warps of a lane quarter loads HALF of its rows' 256 features (2 x 64 elements).
+__device__ __forceinline__ void load_fixed_operand_half(const __nv_bfloat16* a_row, bool valid, uint32_t taddr,
+                                                        int half) {
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int cc = 0; cc < 2; ++cc) {
+    const int c = half * 2 + cc;
     uint32_t r[32];
 #pragma unroll
     for (int v = 0; v < 8; ++v) {
@@ -93,6 +115,40 @@ __device__ __forceinline__ void load_fixed_operand_to_tmem(const __nv_bfloat16* 
     SAM2B200_TMEM_ST32(taddr + c * 32, r);
   }
   tmem_wait_st();
+}
+
+__device__ __forceinline__ void pair_barrier(int quarter) {
+  asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+}
+
+// Store one 32-column fp32 chunk of an accumulator row (already scaled) as a gradient output.
+__device__ __forceinline__ void store_grad_chunk(const GradOut& g, long long brow, int row_in_batch, int col0,
+                                                 float* v /* 32 values, modified */) {
+  if (g.rope_table != nullptr && row_in_batch < g.rope_rows) {
+    const float2* t = g.rope_table + (long long)(row_in_batch % g.rope_period) * 128 + (col0 >> 1);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float2 cs = t[i];
+      const float re = v[2 * i] * cs.x + v[2 * i + 1] * cs.y;      // multiply by conj(cos + i sin)
+      const float im = v[2 * i + 1] * cs.x - v[2 * i] * cs.y;
+      v[2 * i] = re; v[2 * i + 1] = im;
+    }
+  }
+  if (g.is_bf16) {
+    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(g.ptr) + brow * g.ld + col0;
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      uint4 u;
+      u.x = pack_bf16(v[8 * q4 + 0], v[8 * q4 + 1]); u.y = pack_bf16(v[8 * q4 + 2], v[8 * q4 + 3]);
+      u.z = pack_bf16(v[8 * q4 + 4], v[8 * q4 + 5]); u.w = pack_bf16(v[8 * q4 + 6], v[8 * q4 + 7]);
+      *reinterpret_cast<uint4*>(o + q4 * 8) = u;
+    }
+  } else {
+    float* o = static_cast<float*>(g.ptr) + brow * g.ld + col0;
+#pragma unroll
+    for (int q4 = 0; q4 < 8; ++q4)
+      *reinterpret_cast<float4*>(o + q4 * 4) = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+  }
 }
 
 template <int MODE>
@@ -125,14 +181,14 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     mbar_init(&sh.a_ready, kNumSoftmaxThreads);
     fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) { prefetch_tmap(&map_x); prefetch_tmap(&map_y); }
-  if (warp == 5) { tmem_alloc(&sh.tmem_base, 512); tmem_relinquish(); }
+  if (warp == kProducerWarp && lane == 0) { prefetch_tmap(&map_x); prefetch_tmap(&map_y); }
+  if (warp == kMmaWarp) { tmem_alloc(&sh.tmem_base, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh.tmem_base;
 
-  if (warp == 4) {
+  if (warp == kProducerWarp) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       for (int j = 0; j < nt; ++j) {
@@ -151,7 +207,7 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           tma_load_3d(&sh.y_tiles[s][c * kChunkBytes], &map_y, &sh.y_full[s], c * 64, row0, b);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(kBlockM, kBlockN, 0, 0);   // A(TMEM) . X^T, X K-major
@@ -187,7 +243,7 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           // MN-major SW128: N = 256 features -> 4 slabs (LBO = slab stride), K = 16 rows = 2 groups
           // of 8 rows (SBO = 1024 B); advancing 16 rows = 2048 B
           const uint64_t bdesc = make_smem_desc_sw128(ybase + ks * 2048, kChunkBytes, 1024);
-          umma_ts(tmem + kColAcc, pa + ks * 8, bdesc, idesc_acc, (j > 0) || (ks > 0));
+          umma_ts(tmem + kColAcc, pa + p_col_of_kstep(ks), bdesc, idesc_acc, (j > 0) || (ks > 0));
         }
         umma_commit(&sh.y_empty[s]);
         umma_commit(&sh.acc_done);
@@ -195,21 +251,23 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       }
     }
   } else {
-    // ===================== softmax / epilogue warps (0..3) =====================
-    const int row = threadIdx.x;                         // TMEM lane == accumulator row
-    const uint32_t lane_addr = tmem + (uint32_t(warp * 32) << 16);
+    // ===================== softmax / epilogue warps (0..7) =====================
+    const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
+    const int half = warp >> 2;                          // which 32 of the tile's 64 columns
+    const int row = quarter * 32 + lane;                 // TMEM lane == accumulator row
+    const uint32_t lane_addr = tmem + (uint32_t(quarter * 32) << 16);
     const long long a_row_idx = (long long)a_tile * kBlockM + row;
     const bool row_valid = a_row_idx < p.La;
     {
       const __nv_bfloat16* a_row = p.a + ((long long)b * p.La + (row_valid ? a_row_idx : 0)) * kD;
-      load_fixed_operand_to_tmem(a_row, row_valid, lane_addr + kColA);
+      load_fixed_operand_half(a_row, row_valid, lane_addr + kColA, half);
       tc_fence_before();
       mbar_arrive(&sh.a_ready);
     }
 
     const float c = p.scale_log2;
-    float m_ref = -INFINITY;   // running (lazily updated) row max of the raw scores
-    float l = 0.f;             // running sum of exp2((s - m_ref) c)
+    float m_ref = -INFINITY;   // running (lazily updated) row max of the raw scores -- identical in both halves
+    float l = 0.f;             // this half's running sum of exp2((s - m_ref) c)
 
     for (int j = 0; j < nt; ++j) {
       const int t = t_begin + j;
@@ -220,29 +278,32 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           const int col = t * kBlockN + threadIdx.x;
           sh.colvec[j & 1][threadIdx.x] = (col < p.Lx) ? p.lse2[(long long)b * p.Lx + col] : INFINITY;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 5, 256;" ::: "memory");
       }
       mbar_wait(&sh.s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t r0[32], r1[32];
-      SAM2B200_TMEM_LD32(sbuf, r0);
-      SAM2B200_TMEM_LD32(sbuf + 32, r1);
+      uint32_t r0[32];
+      SAM2B200_TMEM_LD32(sbuf + half * kHalfN, r0);
       tmem_wait_ld();
-      float sv[kBlockN];
+      float sv[kHalfN];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) { sv[i] = __uint_as_float(r0[i]); sv[32 + i] = __uint_as_float(r1[i]); }
+      for (int i = 0; i < kHalfN; ++i) sv[i] = __uint_as_float(r0[i]);
 
-      uint32_t pk[32];
+      uint32_t pk[16];
       bool acc_synced = false;
       if (MODE == MODE_FWD) {
-        const int ncols = p.Lx - t * kBlockN;            // valid columns in this tile
-        if (ncols < kBlockN) {
+        const int ncols = p.Lx - t * kBlockN - half * kHalfN;   // valid columns of this half-tile
+        if (ncols < kHalfN) {
 #pragma unroll
-          for (int i = 0; i < kBlockN; ++i) if (i >= ncols) sv[i] = -INFINITY;
+          for (int i = 0; i < kHalfN; ++i) if (i >= ncols) sv[i] = -INFINITY;
         }
         float mx = sv[0];
 #pragma unroll
-        for (int i = 1; i < kBlockN; ++i) mx = fmaxf(mx, sv[i]);
+        for (int i = 1; i < kHalfN; ++i) mx = fmaxf(mx, sv[i]);
+        // combine the two halves' row maxima (both warps of the pair must take the same decision)
+        sh.xchg[j & 1][half][row] = mx;
+        pair_barrier(quarter);
+        mx = fmaxf(mx, sh.xchg[j & 1][half ^ 1][row]);
         // Lazy rescale: keep the stale reference max unless the true max grew by > 2^8 in the
         // exp2 domain (P then stays < 256, exact enough in bf16/fp32); first tile just adopts it.
         const bool grow = (mx - m_ref) * c > 8.0f;
@@ -255,7 +316,7 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           acc_synced = true;
           tc_fence_after();
 #pragma unroll 1
-          for (int cc = 0; cc < kD / 32; ++cc) {
+          for (int cc = half * 4; cc < half * 4 + 4; ++cc) {   // each half rescales its 128 ACC columns
             uint32_t o[32];
             SAM2B200_TMEM_LD32(lane_addr + kColAcc + cc * 32, o);
             tmem_wait_ld();
@@ -268,25 +329,25 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           m_ref = m_new;
         }
         const float mc = m_ref * c;
-        float sum = 0.f;
+        float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < kBlockN; i += 2) {
+        for (int i = 0; i < kHalfN; i += 2) {
           float e0 = ex2(fmaf(sv[i], c, -mc));
           float e1 = ex2(fmaf(sv[i + 1], c, -mc));
-          sum += e0 + e1;
+          sum0 += e0; sum1 += e1;
           pk[i >> 1] = pack_bf16(e0, e1);
         }
-        l += sum;
+        l += sum0 + sum1;
       } else {
-        const float* cv = sh.colvec[j & 1];
+        const float* cv = &sh.colvec[j & 1][half * kHalfN];
 #pragma unroll
-        for (int i = 0; i < kBlockN; i += 2) {
+        for (int i = 0; i < kHalfN; i += 2) {
           float e0 = ex2(fmaf(sv[i], c, -cv[i]));
           float e1 = ex2(fmaf(sv[i + 1], c, -cv[i + 1]));
           pk[i >> 1] = pack_bf16(e0, e1);
         }
       }
-      SAM2B200_TMEM_ST32(sbuf, pk);                       // P (bf16 pairs) over scores cols 0..31
+      SAM2B200_TMEM_ST16(sbuf + half * kHalfN, pk);       // P (bf16 pairs) over this warp's OWN first 16 columns
       tmem_wait_st();
       // Observe EVERY phase of acc_done, in order: a parity wait is only unambiguous while the
       // waiter is at most one phase behind.  PV[j-1] was issued right after QK[j], so by now it has
@@ -296,15 +357,19 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       mbar_arrive(&sh.p_ready[j & 1]);
     }
 
-    // ---------------- epilogue ----------------
+    // ---------------- epilogue: each half stores its 128 of the 256 output columns ----------------
     mbar_wait(&sh.acc_done, (nt - 1) & 1);
     tc_fence_after();
     if (MODE == MODE_FWD) {
+      // total row sum = sum of the two halves' partial sums
+      sh.lsum[half][row] = l;
+      pair_barrier(quarter);
+      l += sh.lsum[half ^ 1][row];
       if (nsplit == 1) {
         const float inv_l = 1.0f / l;
         __nv_bfloat16* orow = p.out + ((long long)b * p.La + a_row_idx) * kD;
 #pragma unroll 1
-        for (int cc = 0; cc < kD / 32; ++cc) {
+        for (int cc = half * 4; cc < half * 4 + 4; ++cc) {
           uint32_t o[32];
           SAM2B200_TMEM_LD32(lane_addr + kColAcc + cc * 32, o);
           tmem_wait_ld();
@@ -328,12 +393,12 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             }
           }
         }
-        if (row_valid) p.lse2[(long long)b * p.La + a_row_idx] = fmaf(m_ref, c, log2f(l));
+        if (row_valid && half == 0) p.lse2[(long long)b * p.La + a_row_idx] = fmaf(m_ref, c, log2f(l));
       } else {
         const long long prow = ((long long)split * gridDim.y + b) * p.La + a_row_idx;
         float* orow = p.part_acc + prow * kD;
 #pragma unroll 1
-        for (int cc = 0; cc < kD / 32; ++cc) {
+        for (int cc = half * 4; cc < half * 4 + 4; ++cc) {
           uint32_t o[32];
           SAM2B200_TMEM_LD32(lane_addr + kColAcc + cc * 32, o);
           tmem_wait_ld();
@@ -344,20 +409,19 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                   make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
           }
         }
-        if (row_valid) { p.part_ml[prow * 2] = m_ref * c; p.part_ml[prow * 2 + 1] = l; }
+        if (row_valid && half == 0) { p.part_ml[prow * 2] = m_ref * c; p.part_ml[prow * 2 + 1] = l; }
       }
     } else {
-      float* orow = p.acc_out + ((long long)b * p.La + a_row_idx) * kD;
 #pragma unroll 1
-      for (int cc = 0; cc < kD / 32; ++cc) {
+      for (int cc = half * 4; cc < half * 4 + 4; ++cc) {
         uint32_t o[32];
         SAM2B200_TMEM_LD32(lane_addr + kColAcc + cc * 32, o);
         tmem_wait_ld();
         if (row_valid) {
+          float v[32];
 #pragma unroll
-          for (int v = 0; v < 8; ++v)
-            *reinterpret_cast<uint4*>(orow + cc * 32 + v * 4) =
-                make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(o[i]);
+          store_grad_chunk(p.gout, (long long)b * p.La + a_row_idx, (int)a_row_idx, cc * 32, v);
         }
       }
     }
@@ -365,7 +429,7 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem, 512);
+  if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
 }
 
 // =====================================================================================
@@ -380,7 +444,7 @@ constexpr int kA2ChunkBytes = kBlockM * 128;        // 16 KB
 constexpr uint32_t k3ColAcc = 0;     // 256: dQ / dK accumulator
 constexpr uint32_t k3ColA1 = 256;    // 128: fixed operand A1 (bf16 pairs)
 constexpr uint32_t k3ColS = 384;     // 64 : S
-constexpr uint32_t k3ColDP = 448;    // 64 : dP, then dS (bf16 pairs in cols 0..31)
+constexpr uint32_t k3ColDP = 448;    // 64 : dP, then dS (bf16 pairs; same own-column placement as P above)
 
 struct ThreeGemmParams {
   const __nv_bfloat16* a1;     // [B, La, 256] (Q in DQ, K in DK)
@@ -390,7 +454,7 @@ struct ThreeGemmParams {
   float scale;                 // softmax scale (applied to ACC in the epilogue)
   const float* lse2;           // [B, N]   log2-domain LSE of the forward
   const float* delta;          // [B, N]   rowsum(dO o O)
-  float* acc_out;              // [B, La, 256] fp32
+  GradOut gout;                // dQ / dK
 };
 
 struct SharedStorage3 {
@@ -441,14 +505,14 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
     mbar_init(&sh.acc_done, 1);
     fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) { prefetch_tmap(&map_a2); prefetch_tmap(&map_x); prefetch_tmap(&map_y); }
-  if (warp == 5) { tmem_alloc(&sh.tmem_base, 512); tmem_relinquish(); }
+  if (warp == kProducerWarp && lane == 0) { prefetch_tmap(&map_a2); prefetch_tmap(&map_x); prefetch_tmap(&map_y); }
+  if (warp == kMmaWarp) { tmem_alloc(&sh.tmem_base, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh.tmem_base;
 
-  if (warp == 4) {
+  if (warp == kProducerWarp) {
     if (lane == 0) {
       mbar_arrive_expect_tx(&sh.a2_full, kA2Bytes);
 #pragma unroll
@@ -470,7 +534,7 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
           tma_load_3d(&sh.y_tiles[s][c * kChunkBytes], &map_y, &sh.y_full[s], c * 64, row0, b);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(kBlockM, kBlockN, 0, 0);
       constexpr uint32_t idesc_acc = make_idesc_bf16(kBlockM, kD, 0, 1);
@@ -519,20 +583,22 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
 #pragma unroll
         for (int ks = 0; ks < kBlockN / 16; ++ks) {
           const uint64_t bdesc = make_smem_desc_sw128(xbase + ks * 2048, kChunkBytes, 1024);
-          umma_ts(tmem + k3ColAcc, tmem + k3ColDP + ks * 8, bdesc, idesc_acc, (j > 0) || (ks > 0));
+          umma_ts(tmem + k3ColAcc, tmem + k3ColDP + p_col_of_kstep(ks), bdesc, idesc_acc, (j > 0) || (ks > 0));
         }
         umma_commit(&sh.x_empty[s]);
         if (j + 1 < nt) issue_dp(j + 1); else umma_commit(&sh.acc_done);
       }
     }
   } else {
-    const int row = threadIdx.x;
-    const uint32_t lane_addr = tmem + (uint32_t(warp * 32) << 16);
+    const int quarter = warp & 3;
+    const int half = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem + (uint32_t(quarter * 32) << 16);
     const long long a_row_idx = (long long)a_tile * kBlockM + row;
     const bool row_valid = a_row_idx < p.La;
     {
       const __nv_bfloat16* a_row = p.a1 + ((long long)b * p.La + (row_valid ? a_row_idx : 0)) * kD;
-      load_fixed_operand_to_tmem(a_row, row_valid, lane_addr + k3ColA1);
+      load_fixed_operand_half(a_row, row_valid, lane_addr + k3ColA1, half);
       tc_fence_before();
       mbar_arrive(&sh.a1_ready);
     }
@@ -550,73 +616,67 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
           sh.col_lse[j & 1][threadIdx.x] = ok ? p.lse2[(long long)b * p.Lx + col] : INFINITY;
           sh.col_delta[j & 1][threadIdx.x] = ok ? p.delta[(long long)b * p.Lx + col] : 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 5, 256;" ::: "memory");
       }
       mbar_wait(&sh.s_full, j & 1);
       tc_fence_after();
-      float pv[kBlockN];
+      float pv[kHalfN];
       {
-        uint32_t r0[32], r1[32];
-        SAM2B200_TMEM_LD32(lane_addr + k3ColS, r0);
-        SAM2B200_TMEM_LD32(lane_addr + k3ColS + 32, r1);
+        uint32_t r0[32];
+        SAM2B200_TMEM_LD32(lane_addr + k3ColS + half * kHalfN, r0);
         tmem_wait_ld();
         tc_fence_before();
         mbar_arrive(&sh.s_free);          // S region may be overwritten by S[j+1]
-        const int ncols = p.Lx - j * kBlockN;
+        const int ncols = p.Lx - j * kBlockN - half * kHalfN;
 #pragma unroll
-        for (int i = 0; i < kBlockN; ++i) {
-          const float sraw = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]);
+        for (int i = 0; i < kHalfN; ++i) {
+          const float sraw = __uint_as_float(r0[i]);
           float e;
           if (MODE == MODE_DQ) e = (i < ncols) ? ex2(fmaf(sraw, c, -row_lse)) : 0.f;
-          else e = ex2(fmaf(sraw, c, -sh.col_lse[j & 1][i]));
+          else e = ex2(fmaf(sraw, c, -sh.col_lse[j & 1][half * kHalfN + i]));
           pv[i] = e;
         }
       }
       mbar_wait(&sh.dp_full, j & 1);
       tc_fence_after();
-      uint32_t pk[32];
+      uint32_t pk[16];
       {
-        uint32_t r0[32], r1[32];
-        SAM2B200_TMEM_LD32(lane_addr + k3ColDP, r0);
-        SAM2B200_TMEM_LD32(lane_addr + k3ColDP + 32, r1);
+        uint32_t r0[32];
+        SAM2B200_TMEM_LD32(lane_addr + k3ColDP + half * kHalfN, r0);
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < kBlockN; i += 2) {
-          const float d0 = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]);
-          const float d1 = __uint_as_float(i + 1 < 32 ? r0[i + 1] : r1[i + 1 - 32]);
-          const float dl0 = (MODE == MODE_DQ) ? row_delta : sh.col_delta[j & 1][i];
-          const float dl1 = (MODE == MODE_DQ) ? row_delta : sh.col_delta[j & 1][i + 1];
+        for (int i = 0; i < kHalfN; i += 2) {
+          const float d0 = __uint_as_float(r0[i]);
+          const float d1 = __uint_as_float(r0[i + 1]);
+          const float dl0 = (MODE == MODE_DQ) ? row_delta : sh.col_delta[j & 1][half * kHalfN + i];
+          const float dl1 = (MODE == MODE_DQ) ? row_delta : sh.col_delta[j & 1][half * kHalfN + i + 1];
           pk[i >> 1] = pack_bf16(pv[i] * (d0 - dl0), pv[i + 1] * (d1 - dl1));
         }
       }
-      SAM2B200_TMEM_ST32(lane_addr + k3ColDP, pk);
+      SAM2B200_TMEM_ST16(lane_addr + k3ColDP + half * kHalfN, pk);   // dS over this warp's own dP columns
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&sh.ds_ready);
     }
     mbar_wait(&sh.acc_done, 0);
     tc_fence_after();
-    float* orow = p.acc_out + ((long long)b * p.La + a_row_idx) * kD;
 #pragma unroll 1
-    for (int cc = 0; cc < kD / 32; ++cc) {
+    for (int cc = half * 4; cc < half * 4 + 4; ++cc) {
       uint32_t o[32];
       SAM2B200_TMEM_LD32(lane_addr + k3ColAcc + cc * 32, o);
       tmem_wait_ld();
       if (row_valid) {
+        float v[32];
 #pragma unroll
-        for (int v = 0; v < 8; ++v) {
-          float4 f;
-          f.x = __uint_as_float(o[4 * v]) * p.scale; f.y = __uint_as_float(o[4 * v + 1]) * p.scale;
-          f.z = __uint_as_float(o[4 * v + 2]) * p.scale; f.w = __uint_as_float(o[4 * v + 3]) * p.scale;
-          *reinterpret_cast<float4*>(orow + cc * 32 + v * 4) = f;
-        }
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(o[i]) * p.scale;
+        store_grad_chunk(p.gout, (long long)b * p.La + a_row_idx, (int)a_row_idx, cc * 32, v);
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem, 512);
+  if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace attn

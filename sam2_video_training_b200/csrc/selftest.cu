@@ -172,7 +172,8 @@ static int run_attn(const AttnCase& c) {
 
   // backward uses the GPU forward's out/lse (as training does)
   DevBuf<float> gq(q.size()), gk(k.size()), gv(v.size()), delta((size_t)B * N);
-  rc = sam2b200_attn_bwd(dq_.p, dk_.p, dv_.p, nullptr, o32.p, dout_.p, lse.p, delta.p, gq.p, gk.p, gv.p, B, N, M, scale, 0);
+  rc = sam2b200_attn_bwd(dq_.p, dk_.p, dv_.p, nullptr, o32.p, dout_.p, lse.p, delta.p, gq.p, gk.p, gv.p, 0, 256, 256, 256,
+                         nullptr, 0, 0, B, N, M, scale, 0);
   if (rc) { printf("[FAIL] %s: attn_bwd rc=%d %s\n", c.name, rc, sam2b200_last_error()); return 1; }
   e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("[FAIL] %s: bwd sync: %s\n", c.name, cudaGetErrorString(e)); exit(4); }

@@ -209,10 +209,9 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             dca = cast_colsum(g, grads[ix["ca.o.b"]])
             grads[ix["ca.o.w"]] = _mm32(dca.t(), o2.view(r, d))
             do2 = torch.mm(dca, W["ca.o.w"])
-            dq_r, dk_r, dv32 = attn_bwd(q2_rot, k2_rot, v2.view(b, m, d), None, o2_32, do2.view(b, n, d), lse2, scale)
-            dq2 = rope_apply(dq_r, table, n, inverse=True).view(r, d)
-            dk2 = rope_apply(dk_r, table, n_rope_k, inverse=True).view(rm, d)
-            dv2 = dv32.to(BF16).view(rm, d)
+            dq2, dk2, dv2 = attn_bwd(q2_rot, k2_rot, v2.view(b, m, d), None, o2_32, do2.view(b, n, d), lse2, scale,
+                                     table=table, n_rope_k=n_rope_k, grad_dtype=BF16)   # conj. RoPE fused in epilogue
+            dq2, dk2, dv2 = dq2.view(r, d), dk2.view(rm, d), dv2.view(rm, d)
             colsum_bf16(dq2, grads[ix["ca.q.b"]])
             colsum_bf16(dk2, grads[ix["ca.k.b"]])
             colsum_bf16(dv2, grads[ix["ca.v.b"]])
@@ -229,11 +228,10 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             dsa = cast_colsum(g, grads[ix["sa.o.b"]])
             grads[ix["sa.o.w"]] = _mm32(dsa.t(), o.view(r, d))
             do = torch.mm(dsa, W["sa.o.w"])
-            dq_r, dk_r, dv32 = attn_bwd(q_rot, k_rot, v.view(b, n, d), None, o32, do.view(b, n, d), lse, scale)
-            dqkv = torch.empty((r, 3 * d), dtype=BF16, device=dev)
-            dqkv[:, :d] = rope_apply(dq_r, table, n, inverse=True).view(r, d)
-            dqkv[:, d:2 * d] = rope_apply(dk_r, table, n, inverse=True).view(r, d)
-            dqkv[:, 2 * d:] = dv32.view(r, d)
+            dqkv = torch.empty((b, n, 3 * d), dtype=BF16, device=dev)   # [dq | dk | dv], written in place by the kernels
+            attn_bwd(q_rot, k_rot, v.view(b, n, d), None, o32, do.view(b, n, d), lse, scale, table=table, n_rope_k=n,
+                     grad_dtype=BF16, dq=dqkv[:, :, :d], dk=dqkv[:, :, d:2 * d], dv=dqkv[:, :, 2 * d:])
+            dqkv = dqkv.view(r, 3 * d)
             bsum = torch.zeros(3 * d, dtype=F32, device=dev)
             colsum_bf16(dqkv, bsum)
             grads[ix["sa.q.b"]], grads[ix["sa.k.b"]], grads[ix["sa.v.b"]] = bsum[:d], bsum[d:2 * d], bsum[2 * d:]

@@ -79,19 +79,32 @@ def attn_fwd(q, k, v, scale: float, nsplit: int = 0, keep_f32: bool = True):
     return out, out32, lse2
 
 
-def attn_bwd(q, k, v, out, out32, dout, lse2, scale: float):
+def attn_bwd(q, k, v, out, out32, dout, lse2, scale: float, table=None, n_rope_k: int = 0, grad_dtype=torch.float32,
+             dq=None, dk=None, dv=None):
+    """Backward of the attention core.  With `table` the conjugate RoPE is fused into the epilogue (dq / dk are then
+    gradients w.r.t. the un-rotated projections).  dq / dk / dv may be preallocated 2-D/3-D views whose last dim is
+    contiguous (row stride = .stride(-2)), e.g. column slices of one [R, 768] buffer."""
     lib = _lib.load()
     b, n, _ = q.shape
     m = k.shape[1]
-    dq = torch.empty((b, n, 256), dtype=torch.float32, device=q.device)
-    dk = torch.empty((b, m, 256), dtype=torch.float32, device=q.device)
-    dv = torch.empty((b, m, 256), dtype=torch.float32, device=q.device)
-    delta = torch.empty((b, n), dtype=torch.float32, device=q.device)
+    dev = q.device
+    if dq is None:
+        dq = torch.empty((b, n, 256), dtype=grad_dtype, device=dev)
+    if dk is None:
+        dk = torch.empty((b, m, 256), dtype=grad_dtype, device=dev)
+    if dv is None:
+        dv = torch.empty((b, m, 256), dtype=grad_dtype, device=dev)
+    for t_ in (dq, dk, dv):
+        assert t_.dtype == grad_dtype and t_.stride(-1) == 1
+    delta = torch.empty((b, n), dtype=torch.float32, device=dev)
     with _Timed("attn_bwd", 10.0 * b * n * m * 256):
         rc = lib.sam2b200_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr() if out is not None else None,
                                    out32.data_ptr() if out32 is not None else None, dout.data_ptr(),
                                    lse2.data_ptr(), delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
-                                   b, n, m, scale, _stream(q.device))
+                                   _DT[grad_dtype], dq.stride(-2), dk.stride(-2), dv.stride(-2),
+                                   table.data_ptr() if table is not None else None,
+                                   table.shape[0] if table is not None else 0, n_rope_k,
+                                   b, n, m, scale, _stream(dev))
     _lib.check(rc, "sam2b200_attn_bwd")
     return dq, dk, dv
 
@@ -120,9 +133,9 @@ class RopeAttentionFn(torch.autograd.Function):
     def backward(ctx, dout):
         q_rot, k_rot, vb, out32, lse2, table = ctx.saved_tensors
         dout = dout.to(torch.bfloat16).contiguous()
-        dq_rot, dk_rot, dv = attn_bwd(q_rot, k_rot, vb, None, out32, dout, lse2, ctx.scale)
-        dq = rope_apply(dq_rot, table, q_rot.shape[1], inverse=True, out_dtype=_out_dt(ctx.in_dtypes[0]))
-        dk = rope_apply(dk_rot, table, ctx.n_rope_k, inverse=True, out_dtype=_out_dt(ctx.in_dtypes[1]))
+        gdt = torch.bfloat16 if all(d == torch.bfloat16 for d in ctx.in_dtypes) else torch.float32
+        dq, dk, dv = attn_bwd(q_rot, k_rot, vb, None, out32, dout, lse2, ctx.scale, table=table,
+                              n_rope_k=ctx.n_rope_k, grad_dtype=gdt)
         return dq.to(ctx.in_dtypes[0]), dk.to(ctx.in_dtypes[1]), dv.to(ctx.in_dtypes[2]), None, None, None
 
 

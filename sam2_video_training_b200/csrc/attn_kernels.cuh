@@ -189,66 +189,77 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   const uint32_t tmem = sh.tmem_base;
 
   if (warp == kProducerWarp) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      for (int j = 0; j < nt; ++j) {
-        const int s = j % kStages;
-        const uint32_t ph = (j / kStages) & 1;
-        const int row0 = (t_begin + j) * kBlockN;
-        mbar_wait(&sh.x_empty[s], ph ^ 1);
+    // ===================== TMA producer (converged warp, one elected issuer) =====================
+    const bool leader = elect_one();
+    for (int j = 0; j < nt; ++j) {
+      const int s = j % kStages;
+      const uint32_t ph = (j / kStages) & 1;
+      const int row0 = (t_begin + j) * kBlockN;
+      mbar_wait(&sh.x_empty[s], ph ^ 1);
+      if (leader) {
         mbar_arrive_expect_tx(&sh.x_full[s], kTileBytes);
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           tma_load_3d(&sh.x_tiles[s][c * kChunkBytes], &map_x, &sh.x_full[s], c * 64, row0, b);
-        mbar_wait(&sh.y_empty[s], ph ^ 1);
+      }
+      __syncwarp();
+      mbar_wait(&sh.y_empty[s], ph ^ 1);
+      if (leader) {
         mbar_arrive_expect_tx(&sh.y_full[s], kTileBytes);
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           tma_load_3d(&sh.y_tiles[s][c * kChunkBytes], &map_y, &sh.y_full[s], c * 64, row0, b);
       }
+      __syncwarp();
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(kBlockM, kBlockN, 0, 0);   // A(TMEM) . X^T, X K-major
-      constexpr uint32_t idesc_acc = make_idesc_bf16(kBlockM, kD, 0, 1);      // P(TMEM) . Y,  Y MN-major
-      auto issue_scores = [&](int t) {
-        const int s = t % kStages;
-        mbar_wait(&sh.x_full[s], (t / kStages) & 1);
-        tc_fence_after();
-        const uint32_t xbase = smem_u32(&sh.x_tiles[s][0]);
+    // The whole warp stays converged (all lanes poll the mbarriers); ONE elected lane issues.  Descriptors are
+    // `base + compile-time offset` (one uniform add per tcgen05.mma): with a rebuilt descriptor and a
+    // lane==0 branch the issue loop cost ~87 cycles per MMA and starved the tensor pipe (see
+    // profiles/r1_mma_probe.txt); like this a 128x64x16 MMA issues every ~37 cycles.
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = make_idesc_bf16(kBlockM, kBlockN, 0, 0);   // A(TMEM) . X^T, X K-major
+    constexpr uint32_t idesc_acc = make_idesc_bf16(kBlockM, kD, 0, 1);      // P(TMEM) . Y,  Y MN-major
+    const uint32_t x_lo0 = desc_lo_sw128(smem_u32(&sh.x_tiles[0][0]), 16);           // K-major: LBO unused
+    const uint32_t y_lo0 = desc_lo_sw128(smem_u32(&sh.y_tiles[0][0]), kChunkBytes);  // MN-major: LBO = slab stride
+    auto issue_scores = [&](int t) {
+      const int s = t % kStages;
+      mbar_wait(&sh.x_full[s], (t / kStages) & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t xlo = x_lo0 + s * (kTileBytes >> 4);
         const uint32_t d = tmem + ((t & 1) ? kColS1 : kColS0);
 #pragma unroll
-        for (int ks = 0; ks < kD / 16; ++ks) {
-          // K-major SW128: 64-col slab (ks/4), 32 B per 16-element k-step inside the 128 B row
-          const uint64_t bdesc = make_smem_desc_sw128(xbase + (ks >> 2) * kChunkBytes + (ks & 3) * 32, 16, 1024);
-          umma_ts(d, tmem + kColA + ks * 8, bdesc, idesc_s, ks > 0);
-        }
+        for (int ks = 0; ks < kD / 16; ++ks)   // K-major SW128: slab ks/4, 32 B per k-step inside the 128 B row
+          umma_ts_lohi(d, tmem + kColA + ks * 8, xlo + (ks >> 2) * (kChunkBytes >> 4) + (ks & 3) * 2,
+                       kDescHiSw128_1024, idesc_s, ks > 0);
         umma_commit(&sh.x_empty[s]);
         umma_commit(&sh.s_full[t & 1]);
-      };
-      mbar_wait(&sh.a_ready, 0);
+      }
+      __syncwarp();
+    };
+    mbar_wait(&sh.a_ready, 0);
+    tc_fence_after();
+    issue_scores(0);
+    if (nt > 1) issue_scores(1);
+    for (int j = 0; j < nt; ++j) {
+      const int s = j % kStages;
+      mbar_wait(&sh.p_ready[j & 1], (j >> 1) & 1);
+      mbar_wait(&sh.y_full[s], (j / kStages) & 1);
       tc_fence_after();
-      issue_scores(0);
-      if (nt > 1) issue_scores(1);
-      for (int j = 0; j < nt; ++j) {
-        const int s = j % kStages;
-        mbar_wait(&sh.p_ready[j & 1], (j >> 1) & 1);
-        mbar_wait(&sh.y_full[s], (j / kStages) & 1);
-        tc_fence_after();
-        const uint32_t ybase = smem_u32(&sh.y_tiles[s][0]);
+      if (leader) {
+        const uint32_t ylo = y_lo0 + s * (kTileBytes >> 4);
         const uint32_t pa = tmem + ((j & 1) ? kColS1 : kColS0);
 #pragma unroll
-        for (int ks = 0; ks < kBlockN / 16; ++ks) {
-          // MN-major SW128: N = 256 features -> 4 slabs (LBO = slab stride), K = 16 rows = 2 groups
-          // of 8 rows (SBO = 1024 B); advancing 16 rows = 2048 B
-          const uint64_t bdesc = make_smem_desc_sw128(ybase + ks * 2048, kChunkBytes, 1024);
-          umma_ts(tmem + kColAcc, pa + p_col_of_kstep(ks), bdesc, idesc_acc, (j > 0) || (ks > 0));
-        }
+        for (int ks = 0; ks < kBlockN / 16; ++ks)   // MN-major SW128: 16 rows = 2 groups of 8 rows = 2048 B per k-step
+          umma_ts_lohi(tmem + kColAcc, pa + p_col_of_kstep(ks), ylo + ks * (2048 >> 4), kDescHiSw128_1024, idesc_acc,
+                       (j > 0) || (ks > 0));
         umma_commit(&sh.y_empty[s]);
         umma_commit(&sh.acc_done);
-        if (j + 2 < nt) issue_scores(j + 2);
       }
+      __syncwarp();
+      if (j + 2 < nt) issue_scores(j + 2);
     }
   } else {
     // ===================== softmax / epilogue warps (0..7) =====================
@@ -513,81 +524,97 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
   const uint32_t tmem = sh.tmem_base;
 
   if (warp == kProducerWarp) {
-    if (lane == 0) {
+    const bool leader = elect_one();
+    if (leader) {
       mbar_arrive_expect_tx(&sh.a2_full, kA2Bytes);
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         tma_load_3d(&sh.a2[c * kA2ChunkBytes], &map_a2, &sh.a2_full, c * 64, a_tile * kBlockM, b);
-      for (int j = 0; j < nt; ++j) {
-        const int s = j % kStages3;
-        const uint32_t ph = (j / kStages3) & 1;
-        const int row0 = j * kBlockN;
-        mbar_wait(&sh.x_empty[s], ph ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < nt; ++j) {
+      const int s = j % kStages3;
+      const uint32_t ph = (j / kStages3) & 1;
+      const int row0 = j * kBlockN;
+      mbar_wait(&sh.x_empty[s], ph ^ 1);
+      if (leader) {
         mbar_arrive_expect_tx(&sh.x_full[s], kTileBytes);
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           tma_load_3d(&sh.x_tiles[s][c * kChunkBytes], &map_x, &sh.x_full[s], c * 64, row0, b);
-        mbar_wait(&sh.y_empty[s], ph ^ 1);
+      }
+      __syncwarp();
+      mbar_wait(&sh.y_empty[s], ph ^ 1);
+      if (leader) {
         mbar_arrive_expect_tx(&sh.y_full[s], kTileBytes);
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           tma_load_3d(&sh.y_tiles[s][c * kChunkBytes], &map_y, &sh.y_full[s], c * 64, row0, b);
       }
+      __syncwarp();
     }
   } else if (warp == kMmaWarp) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(kBlockM, kBlockN, 0, 0);
-      constexpr uint32_t idesc_acc = make_idesc_bf16(kBlockM, kD, 0, 1);
-      const uint32_t a2base = smem_u32(&sh.a2[0]);
-      auto issue_s = [&](int t) {        // S[t] = A1(TMEM) . X[t]^T
-        const int s = t % kStages3;
-        mbar_wait(&sh.x_full[s], (t / kStages3) & 1);
-        tc_fence_after();
-        const uint32_t xbase = smem_u32(&sh.x_tiles[s][0]);
+    const bool leader = elect_one();    // converged warp, one elected issuer, add-only descriptors (see two_gemm_kernel)
+    constexpr uint32_t idesc_s = make_idesc_bf16(kBlockM, kBlockN, 0, 0);
+    constexpr uint32_t idesc_acc = make_idesc_bf16(kBlockM, kD, 0, 1);
+    const uint32_t a2_lo = desc_lo_sw128(smem_u32(&sh.a2[0]), 16);
+    const uint32_t x_lo0 = desc_lo_sw128(smem_u32(&sh.x_tiles[0][0]), 16);            // K-major view of X
+    const uint32_t xm_lo0 = desc_lo_sw128(smem_u32(&sh.x_tiles[0][0]), kChunkBytes);  // MN-major view of X
+    const uint32_t y_lo0 = desc_lo_sw128(smem_u32(&sh.y_tiles[0][0]), 16);
+    auto issue_s = [&](int t) {        // S[t] = A1(TMEM) . X[t]^T
+      const int s = t % kStages3;
+      mbar_wait(&sh.x_full[s], (t / kStages3) & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t xlo = x_lo0 + s * (kTileBytes >> 4);
 #pragma unroll
-        for (int ks = 0; ks < kD / 16; ++ks) {
-          const uint64_t bdesc = make_smem_desc_sw128(xbase + (ks >> 2) * kChunkBytes + (ks & 3) * 32, 16, 1024);
-          umma_ts(tmem + k3ColS, tmem + k3ColA1 + ks * 8, bdesc, idesc_s, ks > 0);
-        }
+        for (int ks = 0; ks < kD / 16; ++ks)
+          umma_ts_lohi(tmem + k3ColS, tmem + k3ColA1 + ks * 8, xlo + (ks >> 2) * (kChunkBytes >> 4) + (ks & 3) * 2,
+                       kDescHiSw128_1024, idesc_s, ks > 0);
         umma_commit(&sh.s_full);
-      };
-      auto issue_dp = [&](int t) {       // dP[t] = A2(SMEM) . Y[t]^T
-        const int s = t % kStages3;
-        mbar_wait(&sh.y_full[s], (t / kStages3) & 1);
-        tc_fence_after();
-        const uint32_t ybase = smem_u32(&sh.y_tiles[s][0]);
+      }
+      __syncwarp();
+    };
+    auto issue_dp = [&](int t) {       // dP[t] = A2(SMEM) . Y[t]^T
+      const int s = t % kStages3;
+      mbar_wait(&sh.y_full[s], (t / kStages3) & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t ylo = y_lo0 + s * (kTileBytes >> 4);
 #pragma unroll
-        for (int ks = 0; ks < kD / 16; ++ks) {
-          const uint64_t adesc = make_smem_desc_sw128(a2base + (ks >> 2) * kA2ChunkBytes + (ks & 3) * 32, 16, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(ybase + (ks >> 2) * kChunkBytes + (ks & 3) * 32, 16, 1024);
-          umma_ss(tmem + k3ColDP, adesc, bdesc, idesc_s, ks > 0);
-        }
+        for (int ks = 0; ks < kD / 16; ++ks)
+          umma_ss_lohi(tmem + k3ColDP, a2_lo + (ks >> 2) * (kA2ChunkBytes >> 4) + (ks & 3) * 2,
+                       ylo + (ks >> 2) * (kChunkBytes >> 4) + (ks & 3) * 2, kDescHiSw128_1024, idesc_s, ks > 0);
         umma_commit(&sh.y_empty[s]);
         umma_commit(&sh.dp_full);
-      };
-      mbar_wait(&sh.a1_ready, 0);
-      mbar_wait(&sh.a2_full, 0);
-      tc_fence_after();
-      issue_s(0);
-      issue_dp(0);
-      for (int j = 0; j < nt; ++j) {
-        const int s = j % kStages3;
-        if (j + 1 < nt) {                 // S[j+1] as soon as the compute warps have read S[j]
-          mbar_wait(&sh.s_free, j & 1);
-          tc_fence_after();
-          issue_s(j + 1);
-        }
-        mbar_wait(&sh.ds_ready, j & 1);
-        tc_fence_after();
-        const uint32_t xbase = smem_u32(&sh.x_tiles[s][0]);
-#pragma unroll
-        for (int ks = 0; ks < kBlockN / 16; ++ks) {
-          const uint64_t bdesc = make_smem_desc_sw128(xbase + ks * 2048, kChunkBytes, 1024);
-          umma_ts(tmem + k3ColAcc, tmem + k3ColDP + p_col_of_kstep(ks), bdesc, idesc_acc, (j > 0) || (ks > 0));
-        }
-        umma_commit(&sh.x_empty[s]);
-        if (j + 1 < nt) issue_dp(j + 1); else umma_commit(&sh.acc_done);
       }
+      __syncwarp();
+    };
+    mbar_wait(&sh.a1_ready, 0);
+    mbar_wait(&sh.a2_full, 0);
+    tc_fence_after();
+    issue_s(0);
+    issue_dp(0);
+    for (int j = 0; j < nt; ++j) {
+      const int s = j % kStages3;
+      if (j + 1 < nt) {                 // S[j+1] as soon as the compute warps have read S[j]
+        mbar_wait(&sh.s_free, j & 1);
+        tc_fence_after();
+        issue_s(j + 1);
+      }
+      mbar_wait(&sh.ds_ready, j & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t xlo = xm_lo0 + s * (kTileBytes >> 4);
+#pragma unroll
+        for (int ks = 0; ks < kBlockN / 16; ++ks)
+          umma_ts_lohi(tmem + k3ColAcc, tmem + k3ColDP + p_col_of_kstep(ks), xlo + ks * (2048 >> 4), kDescHiSw128_1024,
+                       idesc_acc, (j > 0) || (ks > 0));
+        umma_commit(&sh.x_empty[s]);
+        if (j + 1 >= nt) umma_commit(&sh.acc_done);
+      }
+      __syncwarp();
+      if (j + 1 < nt) issue_dp(j + 1);
     }
   } else {
     const int quarter = warp & 3;

@@ -107,6 +107,24 @@ def _mm32(a, b):
     return torch.mm(a, b, out_dtype=F32)
 
 
+_BF16_CACHE = {}
+
+
+def bf16_params(params):
+    """bf16 copies of the fp32 master parameters, re-cast only when a parameter was updated in place
+    (tensor._version changes on optimizer.step / copy_): one cast per optimizer step instead of one per
+    forward and per backward call (18x per clip at T = 10)."""
+    out = []
+    for p in params:
+        key = id(p)
+        ent = _BF16_CACHE.get(key)
+        if ent is None or ent[0] != p._version or ent[1] is not p or ent[2].device != p.device:
+            ent = (p._version, p, p.detach().to(BF16))
+            _BF16_CACHE[key] = ent
+        out.append(ent[2])
+    return out
+
+
 class MemoryAttentionStackFn(torch.autograd.Function):
     """out[N,B,256] = MemoryAttention(curr, memory, curr_pos, memory_pos, num_obj_ptr_tokens)."""
 
@@ -125,7 +143,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
         x = x.transpose(0, 1).contiguous().view(r, d)
         memk = (memory + memory_pos).transpose(0, 1).to(BF16).contiguous().view(rm, -1)
         memv = memory.transpose(0, 1).to(BF16).contiguous().view(rm, -1)
-        wb = [p.detach().to(BF16) if p.dim() == 2 else p.detach().to(BF16) for p in params]  # bf16 copies (small)
+        wb = bf16_params(params)
         saved: List[torch.Tensor] = []
         res = None
         for l in range(nl):
@@ -178,12 +196,15 @@ class MemoryAttentionStackFn(torch.autograd.Function):
         dev = x_fin.device
         need_curr, need_pos, need_mem, need_mpos = ctx.needs_input_grad[1:5]
         need_memgrad = need_mem or need_mpos
-        wb = [p.detach().to(BF16) for p in params]
+        wb = bf16_params(params)
         # gradient buffers for vector parameters (accumulated by the kernels); matrices come from mm
         grads = [None] * len(params)
-        for i, p in enumerate(params):
-            if p.dim() == 1:
-                grads[i] = torch.zeros_like(p, dtype=F32)
+        vec = [i for i, p in enumerate(params) if p.dim() == 1]
+        flat = torch.zeros(sum(params[i].numel() for i in vec), dtype=F32, device=dev)   # one memset for all vectors
+        off = 0
+        for i in vec:
+            grads[i] = flat[off:off + params[i].numel()]
+            off += params[i].numel()
         grad_out = grad_out.contiguous().float()
         g = ln_bwd(grad_out, x_fin, mean_f, rstd_f, params[nl * _NPL], None, grads[nl * _NPL], grads[nl * _NPL + 1],
                    seq_first=(b, n))
@@ -219,9 +240,9 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             grads[ix["ca.k.w"]] = _mm32(dk2.t(), memk)
             grads[ix["ca.v.w"]] = _mm32(dv2.t(), memv)
             if need_memgrad:
-                dmemk.add_(torch.mm(dk2, W["ca.k.w"], out_dtype=F32))
+                dmemk = torch.addmm(dmemk, dk2, W["ca.k.w"], out_dtype=F32)
             if need_mem:
-                dmemv.add_(torch.mm(dv2, W["ca.v.w"], out_dtype=F32))
+                dmemv = torch.addmm(dmemv, dv2, W["ca.v.w"], out_dtype=F32)
             dy2 = torch.mm(dq2, W["ca.q.w"])
             g = ln_bwd(dy2, x1, mean2, rstd2, P["n2.w"], g, grads[ix["n2.w"]], grads[ix["n2.b"]])
             # ---- self attention backward
@@ -232,6 +253,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             attn_bwd(q_rot, k_rot, v.view(b, n, d), None, o32, do.view(b, n, d), lse, scale, table=table, n_rope_k=n,
                      grad_dtype=BF16, dq=dqkv[:, :, :d], dk=dqkv[:, :, d:2 * d], dv=dqkv[:, :, 2 * d:])
             dqkv = dqkv.view(r, 3 * d)
+            # q/k/v biases are consecutive vectors? no (weights interleave) -> sum into a scratch then alias
             bsum = torch.zeros(3 * d, dtype=F32, device=dev)
             colsum_bf16(dqkv, bsum)
             grads[ix["sa.q.b"]], grads[ix["sa.k.b"]], grads[ix["sa.v.b"]] = bsum[:d], bsum[d:2 * d], bsum[2 * d:]

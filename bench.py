@@ -127,16 +127,19 @@ def assemble_banks(d, wl):
         nf = min(t, 7)
         mem = torch.cat([d["mem_feat"][i][:n] for i in range(nf)] + [d["mem_feat"][i][n:] for i in range(nf)], dim=0)
         pos = torch.cat([d["mem_pos"][i][:n] for i in range(nf)] + [d["mem_pos"][i][n:] for i in range(nf)], dim=0)
-        banks.append((mem, pos, 4 * nf))
+        # memory_pos carries gradient in real training (maskmem_tpos_enc, sam2_base.py:608-610): ask for it
+        banks.append((mem, pos.requires_grad_(True), 4 * nf))
     return banks
 
 
-def run_step(model, crit, opt, d, banks, wl, world, flat_grads=None):
+def run_step(model, crit, opt, d, banks, wl, world, fwd=None):
     T, C = wl["T"], wl["C"]
+    fwd = fwd or model
     for t in range(1, T):
         mem, pos, p = banks[t - 1]
-        out = model(d["curr"][t - 1], mem, d["curr_pos"], pos, p)
+        out = fwd(d["curr"][t - 1], mem, d["curr_pos"], pos, p)
         out.backward(d["grad_out"][t - 1])
+        pos.grad = None
     total = None
     for ci in range(wl["clips"]):
         xs = [d["logits"][ci * T + f].requires_grad_(True) for f in range(T)]
@@ -273,6 +276,7 @@ def main():
     ap.add_argument("--workload", default="cfg2_endovis18_384px_T10_7obj_x8clips", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host (no CUDA-graph replay)")
     args = ap.parse_args()
     wl_name, wl = args.workload, WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -299,7 +303,10 @@ def main():
     crit = MultiStepMultiMasksAndIous(dict(LOSS_W), supervise_all_iou=True, iou_use_l1_loss=True, check_valid=False)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-5, fused=True)
     from sam2_video_training_b200 import ddp
+    from sam2_video_training_b200.graphs import GraphedMemoryAttention
     ddp.attach_grad_bucket(model)   # all 106 gradients are views of one flat fp32 buffer
+    eager_model = model
+    run_model = model if args.no_graphs else GraphedMemoryAttention(model)
 
     host = make_host_inputs(wl, 1234 + rank, pin=True)
     d = to_device(host, dev)
@@ -313,20 +320,17 @@ def main():
 
     # ---------------- device-resident throughput (`value`) ----------------
     for _ in range(max(args.warmup, 3)):
-        run_step(model, crit, opt, d, banks, wl, world)
+        run_step(model, crit, opt, d, banks, wl, world, fwd=run_model)
     barrier()
     clocks = ClockSampler(local_rank) if rank == 0 else None
     launches0 = lib.sam2b200_launch_count()
-    ops.PROFILE = {}
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        run_step(model, crit, opt, d, banks, wl, world)
+        run_step(model, crit, opt, d, banks, wl, world, fwd=run_model)
     ev1.record()
     barrier()
-    prof = ops.PROFILE
-    ops.PROFILE = None
     launches = lib.sam2b200_launch_count() - launches0
     ms = ev0.elapsed_time(ev1)
     t_ms = torch.tensor([ms], device=dev)
@@ -336,6 +340,26 @@ def main():
     clk = clocks.stop() if clocks is not None else None
     frames_per_step = wl["T"] * wl["clips"]
     value = world * frames_per_step / (ms_per_step * 1e-3)
+
+    # ---------------- same steps, every kernel launched from the host, CUDA events around each kernel family
+    # (events cannot be timed inside a replayed graph): feeds `roofline` and `kernel_families_ms_per_step`
+    run_step(model, crit, opt, d, banks, wl, world)
+    barrier()
+    launches_e0 = lib.sam2b200_launch_count()
+    ops.PROFILE = {}
+    ev0.record()
+    for _ in range(args.steps):
+        run_step(model, crit, opt, d, banks, wl, world)
+    ev1.record()
+    barrier()
+    prof = ops.PROFILE
+    ops.PROFILE = None
+    eager_ms_per_step = ev0.elapsed_time(ev1) / args.steps
+    launches_eager = lib.sam2b200_launch_count() - launches_e0
+    if args.no_graphs:
+        launches = launches_eager
+    else:
+        launches = launches_eager   # a replayed graph launches the same kernels; the host-side counter only sees eager launches
 
     # ---------------- per-kernel-family device time inside the timed region ----------------
     fam = {}
@@ -354,7 +378,7 @@ def main():
                 "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
                 "peak_source": pk["src"] + " sustained cuBLAS bf16", "traffic": None,
                 "attention_fwd_bwd_tflops": attn_fl / (attn_ms * 1e-3) / 1e12 if attn_ms else None,
-                "attention_share_of_step": attn_ms / (ms_per_step * args.steps) if ms_per_step else None,
+                "attention_share_of_step": attn_ms / (eager_ms_per_step * args.steps) if eager_ms_per_step else None,
                 "mask_loss": {"bound": "hbm", "achieved": loss_by / (loss_ms * 1e-3) / 1e9 if loss_ms else None, "peak": pk["hbm"],
                               "unit": "GB/s", "frac": (loss_by / (loss_ms * 1e-3) / 1e9 / pk["hbm"]) if loss_ms else None,
                               "bytes_per_px": "5 fwd + 9 bwd"},
@@ -363,17 +387,31 @@ def main():
     # ---------------- end to end: host buffers, H2D inside the timed region, loss read back ----------------
     e2e = None
     if not args.no_e2e:
-        def e2e_step():
-            dd = to_device(host, dev)
-            bk = assemble_banks(dd, wl)
-            tot = run_step(model, crit, opt, dd, bk, wl, world)
-            return float(tot.item())  # D2H of the step's loss
-        for _ in range(2):
-            e2e_step()
+        copy_stream = torch.cuda.Stream()
+
+        def start_copy():   # H2D of one step's inputs from pinned host memory, on the copy stream
+            with torch.cuda.stream(copy_stream):
+                dd = to_device(host, dev)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return dd, ev
+
+        def e2e_loop(k):
+            # double-buffered: the copy of step i+1 overlaps the compute of step i; every copy is inside the timed region
+            nxt = start_copy()
+            for i in range(k):
+                dd, ev = nxt
+                torch.cuda.current_stream().wait_event(ev)
+                if i + 1 < k:
+                    nxt = start_copy()
+                bk = assemble_banks(dd, wl)
+                tot = run_step(model, crit, opt, dd, bk, wl, world, fwd=run_model)
+                float(tot.item())   # D2H of the step's loss (also keeps `dd` alive until the step is done)
+
+        e2e_loop(2)
         barrier()
         ev0.record()
-        for _ in range(args.steps):
-            e2e_step()
+        e2e_loop(args.steps)
         ev1.record()
         barrier()
         t2 = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
@@ -402,11 +440,13 @@ def main():
             "config": {"workload": wl_name, "tokens": wl["grid"] ** 2, "frames_per_clip": wl["T"], "objects_per_clip": wl["C"],
                        "clips_per_gpu": wl["clips"], "mask_px": wl["S"], "memory_bank": "min(t,7) frames x (N + 4 pointer tokens)",
                        "l2": "inputs_larger_than_L2 (%.0f MB per step)" % (h2d_bytes(host) / 1e6),
+                       "launch": "memory-attention fwd/bwd replayed as CUDA graphs (one pair per memory-bank shape)" if not args.no_graphs else "host-launched",
                        "parallelism": "dp%d (clips sharded, NCCL grad all-reduce)" % world,
                        "object_frames_per_step": wl["T"] * wl["C"] * wl["clips"],
                        "algorithmic_tflop_per_step": algorithmic_flops(wl) / 1e12},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "kernel_families_ms_per_step": {k: v["ms"] / args.steps for k, v in fam.items()},
+            "ms_per_step_host_launched": eager_ms_per_step, "cuda_graphs": not args.no_graphs,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -280,14 +280,21 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     float m_ref = -INFINITY;   // running (lazily updated) row max of the raw scores -- identical in both halves
     float l = 0.f;             // this half's running sum of exp2((s - m_ref) c)
 
+    // DV: per-column LSE2 (columns are queries) is staged through shared memory ONE TILE AHEAD, so the
+    // global-load latency is off the per-tile critical path.
+    float cv_next = INFINITY;
+    if (MODE == MODE_DV && threadIdx.x < kBlockN) {
+      const int col = t_begin * kBlockN + threadIdx.x;
+      cv_next = (col < p.Lx) ? p.lse2[(long long)b * p.Lx + col] : INFINITY;
+    }
     for (int j = 0; j < nt; ++j) {
       const int t = t_begin + j;
       const uint32_t sbuf = lane_addr + ((j & 1) ? kColS1 : kColS0);
       if (MODE == MODE_DV) {
-        // stage this tile's per-column LSE2 (columns are queries) through shared memory
         if (threadIdx.x < kBlockN) {
-          const int col = t * kBlockN + threadIdx.x;
-          sh.colvec[j & 1][threadIdx.x] = (col < p.Lx) ? p.lse2[(long long)b * p.Lx + col] : INFINITY;
+          sh.colvec[j & 1][threadIdx.x] = cv_next;
+          const int col = (t + 1) * kBlockN + threadIdx.x;
+          cv_next = (j + 1 < nt && col < p.Lx) ? p.lse2[(long long)b * p.Lx + col] : INFINITY;
         }
         asm volatile("bar.sync 5, 256;" ::: "memory");
       }
@@ -635,13 +642,20 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
       row_lse = p.lse2[(long long)b * p.La + a_row_idx];
       row_delta = p.delta[(long long)b * p.La + a_row_idx];
     }
+    float lse_next = INFINITY, delta_next = 0.f;   // DK: per-column vectors staged one tile ahead
+    if (MODE == MODE_DK && threadIdx.x < kBlockN && (int)threadIdx.x < p.Lx) {
+      lse_next = p.lse2[(long long)b * p.Lx + threadIdx.x];
+      delta_next = p.delta[(long long)b * p.Lx + threadIdx.x];
+    }
     for (int j = 0; j < nt; ++j) {
       if (MODE == MODE_DK) {
         if (threadIdx.x < kBlockN) {
-          const int col = j * kBlockN + threadIdx.x;
-          const bool ok = col < p.Lx;
-          sh.col_lse[j & 1][threadIdx.x] = ok ? p.lse2[(long long)b * p.Lx + col] : INFINITY;
-          sh.col_delta[j & 1][threadIdx.x] = ok ? p.delta[(long long)b * p.Lx + col] : 0.f;
+          sh.col_lse[j & 1][threadIdx.x] = lse_next;
+          sh.col_delta[j & 1][threadIdx.x] = delta_next;
+          const int col = (j + 1) * kBlockN + threadIdx.x;
+          const bool ok = (j + 1 < nt) && col < p.Lx;
+          lse_next = ok ? p.lse2[(long long)b * p.Lx + col] : INFINITY;
+          delta_next = ok ? p.delta[(long long)b * p.Lx + col] : 0.f;
         }
         asm volatile("bar.sync 5, 256;" ::: "memory");
       }

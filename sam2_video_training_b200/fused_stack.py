@@ -108,12 +108,15 @@ def _mm32(a, b):
 
 
 _BF16_CACHE = {}
+CAPTURE_SAFE_CASTS = False   # set while a CUDA graph is being built: casts must be part of the graph
 
 
 def bf16_params(params):
     """bf16 copies of the fp32 master parameters, re-cast only when a parameter was updated in place
     (tensor._version changes on optimizer.step / copy_): one cast per optimizer step instead of one per
     forward and per backward call (18x per clip at T = 10)."""
+    if CAPTURE_SAFE_CASTS or torch.cuda.is_current_stream_capturing():
+        return [p.detach().to(BF16) for p in params]
     out = []
     for p in params:
         key = id(p)

@@ -121,11 +121,21 @@ __device__ __forceinline__ void pair_barrier(int quarter) {
   asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
 }
 
-// Store one 32-column fp32 chunk of an accumulator row (already scaled) as a gradient output.
-__device__ __forceinline__ void store_grad_chunk(const GradOut& g, long long brow, int row_in_batch, int col0,
+// Gradient epilogue of one accumulator row half (4 chunks of 32 columns): TMEM -> registers -> scale ->
+// conjugate axial rotation -> bf16/fp32 store.  The (cos, sin) table rows are L2-resident but ~1 us away:
+// the loads for chunk i+1 are issued before chunk i is processed (software pipeline), and the TMEM load of
+// chunk i+1 is in flight while chunk i is rotated and stored.
+__device__ __forceinline__ void load_table_chunk(const GradOut& g, bool rotate, int row_in_batch, int col0, float2* t) {
+  if (rotate) {
+    const float4* src = reinterpret_cast<const float4*>(g.rope_table + (long long)(row_in_batch % g.rope_period) * 128 + (col0 >> 1));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float4 f = __ldg(src + i); t[2 * i] = make_float2(f.x, f.y); t[2 * i + 1] = make_float2(f.z, f.w); }
+  }
+}
+
+__device__ __forceinline__ void store_grad_chunk(const GradOut& g, bool rotate, const float2* t, long long brow, int col0,
                                                  float* v /* 32 values, modified */) {
-  if (g.rope_table != nullptr && row_in_batch < g.rope_rows) {
-    const float2* t = g.rope_table + (long long)(row_in_batch % g.rope_period) * 128 + (col0 >> 1);
+  if (rotate) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const float2 cs = t[i];
@@ -148,6 +158,38 @@ __device__ __forceinline__ void store_grad_chunk(const GradOut& g, long long bro
 #pragma unroll
     for (int q4 = 0; q4 < 8; ++q4)
       *reinterpret_cast<float4*>(o + q4 * 4) = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+  }
+}
+
+// acc_addr: TMEM address of column 0 of this thread's accumulator row; half selects columns [128h, 128h+128).
+__device__ __forceinline__ void grad_epilogue(const GradOut& g, uint32_t acc_addr, int half, bool row_valid, long long brow,
+                                              int row_in_batch, float scale) {
+  const bool rotate = row_valid && g.rope_table != nullptr && row_in_batch < g.rope_rows;
+  float2 tcur[16], tnext[16];
+  uint32_t ocur[32], onext[32];
+  const int c0 = half * 4;
+  load_table_chunk(g, rotate, row_in_batch, c0 * 32, tcur);
+  SAM2B200_TMEM_LD32(acc_addr + c0 * 32, ocur);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int cc = c0 + i;
+    tmem_wait_ld();
+    if (i + 1 < 4) {
+      SAM2B200_TMEM_LD32(acc_addr + (cc + 1) * 32, onext);
+      load_table_chunk(g, rotate, row_in_batch, (cc + 1) * 32, tnext);
+    }
+    if (row_valid) {
+      float v[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(ocur[k]) * scale;
+      store_grad_chunk(g, rotate, tcur, brow, cc * 32, v);
+    }
+    if (i + 1 < 4) {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) ocur[k] = onext[k];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) tcur[k] = tnext[k];
+    }
   }
 }
 
@@ -430,18 +472,7 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         if (row_valid && half == 0) { p.part_ml[prow * 2] = m_ref * c; p.part_ml[prow * 2 + 1] = l; }
       }
     } else {
-#pragma unroll 1
-      for (int cc = half * 4; cc < half * 4 + 4; ++cc) {
-        uint32_t o[32];
-        SAM2B200_TMEM_LD32(lane_addr + kColAcc + cc * 32, o);
-        tmem_wait_ld();
-        if (row_valid) {
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(o[i]);
-          store_grad_chunk(p.gout, (long long)b * p.La + a_row_idx, (int)a_row_idx, cc * 32, v);
-        }
-      }
+      grad_epilogue(p.gout, lane_addr + kColAcc, half, row_valid, (long long)b * p.La + a_row_idx, (int)a_row_idx, 1.0f);
     }
   }
 
@@ -701,18 +732,7 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
     }
     mbar_wait(&sh.acc_done, 0);
     tc_fence_after();
-#pragma unroll 1
-    for (int cc = half * 4; cc < half * 4 + 4; ++cc) {
-      uint32_t o[32];
-      SAM2B200_TMEM_LD32(lane_addr + k3ColAcc + cc * 32, o);
-      tmem_wait_ld();
-      if (row_valid) {
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(o[i]) * p.scale;
-        store_grad_chunk(p.gout, (long long)b * p.La + a_row_idx, (int)a_row_idx, cc * 32, v);
-      }
-    }
+    grad_epilogue(p.gout, lane_addr + k3ColAcc, half, row_valid, (long long)b * p.La + a_row_idx, (int)a_row_idx, p.scale);
   }
 
   tc_fence_before();

@@ -39,6 +39,8 @@ int sam2b200_version(void);
 const char* sam2b200_last_error(void);
 /* CUDA kernels launched by this library in this process so far (for bench.py's gpu_launches). */
 long long sam2b200_launch_count(void);
+/* Debug aid: per-CTA phase timelines of the attention kernels into a device buffer (NULL = off). */
+long long sam2b200_debug_set_timeline(void* buf, long long n_u64);
 /* 0 iff CUDA device `dev` is an sm_100 part. */
 int sam2b200_check_device(int dev);
 

@@ -134,6 +134,17 @@ __global__ void combine_kernel(const float* __restrict__ part_acc, const float* 
 
 constexpr float kLog2e = 1.4426950408889634f;
 
+// Debug aid: when set (sam2b200_debug_set_timeline), every attention kernel launch records a per-CTA phase
+// timeline (8 x u64 per CTA) into this device buffer; consecutive launches append.
+unsigned long long* g_timeline = nullptr;
+size_t g_timeline_cap = 0, g_timeline_used = 0;
+unsigned long long* timeline_slice(size_t ctas) {
+  if (!g_timeline || g_timeline_used + ctas * 8 > g_timeline_cap) return nullptr;
+  unsigned long long* p = g_timeline + g_timeline_used;
+  g_timeline_used += ctas * 8;
+  return p;
+}
+
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -146,6 +157,17 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 }  // namespace
 
 extern "C" {
+
+// Debug aid (not part of the training path): buf = device buffer of n_u64 u64 (or NULL to switch off).
+// Each subsequent attention kernel launch appends grid-size x 8 u64 {smid, t_entry, t_setup, t_operand, t_first_scores,
+// t_loop_done, t_end, tiles} in %globaltimer ns.  Returns the number of u64 used so far.
+long long sam2b200_debug_set_timeline(void* buf, long long n_u64) {
+  long long used = (long long)g_timeline_used;
+  g_timeline = static_cast<unsigned long long*>(buf);
+  g_timeline_cap = buf ? (size_t)n_u64 : 0;
+  g_timeline_used = 0;
+  return used;
+}
 
 // in_dtype / out_dtype: 0 = fp32, 1 = bf16
 int sam2b200_rope_apply(const void* x, int in_dtype, void* out, int out_dtype, const float* table, int B,
@@ -216,6 +238,7 @@ int sam2b200_attn_fwd(const void* q, const void* k, const void* v, void* out, fl
   const size_t smem = sizeof(attn::SharedStorage) + 1024;
   if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_FWD>, smem))) return rc;
   dim3 grid((N + attn::kBlockM - 1) / attn::kBlockM, B, nsplit);
+  p.dbg = timeline_slice((size_t)grid.x * grid.y * grid.z);
   attn::two_gemm_kernel<attn::MODE_FWD><<<grid, attn::kThreads, smem, stream>>>(map_k, map_v, p);
   if ((rc = sam2b200::check_launch("attn_fwd"))) return rc;
   if (nsplit > 1) {
@@ -270,6 +293,7 @@ int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* o
     const size_t smem = sizeof(attn::SharedStorage) + 1024;
     if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_DV>, smem))) return rc;
     dim3 grid((M + attn::kBlockM - 1) / attn::kBlockM, B, 1);
+    p.dbg = timeline_slice((size_t)grid.x * grid.y);
     attn::two_gemm_kernel<attn::MODE_DV><<<grid, attn::kThreads, smem, stream>>>(map_q64, map_do64, p);
     if ((rc = sam2b200::check_launch("attn_bwd dV"))) return rc;
   }
@@ -282,6 +306,7 @@ int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* o
     p.gout = attn::GradOut{dk, ldk, grad_dtype, table, table ? n_rope_k : 0, table ? rope_period : 1};
     if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DK>, smem3))) return rc;
     dim3 grid((M + attn::kBlockM - 1) / attn::kBlockM, B, 1);
+    p.dbg = timeline_slice((size_t)grid.x * grid.y);
     attn::three_gemm_kernel<attn::MODE_DK><<<grid, attn::kThreads, smem3, stream>>>(map_v128, map_q64, map_do64, p);
     if ((rc = sam2b200::check_launch("attn_bwd dK"))) return rc;
   }
@@ -293,6 +318,7 @@ int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* o
     p.gout = attn::GradOut{dq, ldq, grad_dtype, table, table ? N : 0, table ? rope_period : 1};
     if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DQ>, smem3))) return rc;
     dim3 grid((N + attn::kBlockM - 1) / attn::kBlockM, B, 1);
+    p.dbg = timeline_slice((size_t)grid.x * grid.y);
     attn::three_gemm_kernel<attn::MODE_DQ><<<grid, attn::kThreads, smem3, stream>>>(map_do128, map_k64, map_v64, p);
     if ((rc = sam2b200::check_launch("attn_bwd dQ"))) return rc;
   }

@@ -57,6 +57,24 @@ __device__ __forceinline__ uint32_t p_col_of_kstep(int ks) { return (ks < 2) ? k
 
 enum { MODE_FWD = 0, MODE_DV = 1 };
 
+// Optional per-CTA phase timeline (debugging / profiling aid; nullptr in production): 8 x u64 per CTA =
+// {smid, t_entry, t_setup_done, t_operand_in_tmem, t_first_scores, t_loop_done, t_epilogue_done, nt}, %globaltimer ns.
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned smid() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %smid;" : "=r"(r));
+  return r;
+}
+#define SAM2B200_STAMP(buf, slot)                                                                     \
+  do {                                                                                                \
+    if ((buf) != nullptr && threadIdx.x == 0)                                                         \
+      (buf)[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = gtimer(); \
+  } while (0)
+
 // Optional fused epilogue for gradient outputs: conjugate axial rotation + bf16 store with a row stride.
 struct GradOut {
   void* ptr;                   // [B, La, ld] bf16 or fp32
@@ -80,6 +98,7 @@ struct TwoGemmParams {
   float* part_ml;              // [nsplit, B, La, 2]  (m_ref * c, l)
   GradOut gout;                // DV output (dV)
   int tiles_per_split;
+  unsigned long long* dbg;     // optional timeline buffer
 };
 
 struct SharedStorage {
@@ -212,6 +231,11 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   const int t_begin = split * p.tiles_per_split;
   const int t_end = min(total_tiles, t_begin + p.tiles_per_split);
   const int nt = t_end - t_begin;      // >= 1 by construction of the grid
+  if (p.dbg != nullptr && threadIdx.x == 0) {
+    unsigned long long* e = p.dbg + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8;
+    e[0] = smid(); e[7] = nt;
+  }
+  SAM2B200_STAMP(p.dbg, 1);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -229,6 +253,7 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh.tmem_base;
+  SAM2B200_STAMP(p.dbg, 2);
 
   if (warp == kProducerWarp) {
     // ===================== TMA producer (converged warp, one elected issuer) =====================
@@ -316,6 +341,7 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       load_fixed_operand_half(a_row, row_valid, lane_addr + kColA, half);
       tc_fence_before();
       mbar_arrive(&sh.a_ready);
+      SAM2B200_STAMP(p.dbg, 3);
     }
 
     const float c = p.scale_log2;
@@ -342,6 +368,7 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       }
       mbar_wait(&sh.s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
+      if (j == 0) SAM2B200_STAMP(p.dbg, 4);
       uint32_t r0[32];
       SAM2B200_TMEM_LD32(sbuf + half * kHalfN, r0);
       tmem_wait_ld();
@@ -420,6 +447,7 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     // ---------------- epilogue: each half stores its 128 of the 256 output columns ----------------
     mbar_wait(&sh.acc_done, (nt - 1) & 1);
     tc_fence_after();
+    SAM2B200_STAMP(p.dbg, 5);
     if (MODE == MODE_FWD) {
       // total row sum = sum of the two halves' partial sums
       sh.lsum[half][row] = l;
@@ -478,6 +506,7 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  SAM2B200_STAMP(p.dbg, 6);
   if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
 }
 
@@ -504,6 +533,7 @@ struct ThreeGemmParams {
   const float* lse2;           // [B, N]   log2-domain LSE of the forward
   const float* delta;          // [B, N]   rowsum(dO o O)
   GradOut gout;                // dQ / dK
+  unsigned long long* dbg;     // optional timeline buffer
 };
 
 struct SharedStorage3 {
@@ -539,6 +569,11 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
   const int a_tile = blockIdx.x;
   const int b = blockIdx.y;
   const int nt = (p.Lx + kBlockN - 1) / kBlockN;
+  if (p.dbg != nullptr && threadIdx.x == 0) {
+    unsigned long long* e = p.dbg + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8;
+    e[0] = smid(); e[7] = nt;
+  }
+  SAM2B200_STAMP(p.dbg, 1);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages3; ++s) {
@@ -560,6 +595,7 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh.tmem_base;
+  SAM2B200_STAMP(p.dbg, 2);
 
   if (warp == kProducerWarp) {
     const bool leader = elect_one();
@@ -666,6 +702,7 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
       load_fixed_operand_half(a_row, row_valid, lane_addr + k3ColA1, half);
       tc_fence_before();
       mbar_arrive(&sh.a1_ready);
+      SAM2B200_STAMP(p.dbg, 3);
     }
     const float c = p.scale_log2;
     float row_lse = 0.f, row_delta = 0.f;
@@ -692,6 +729,7 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
       }
       mbar_wait(&sh.s_full, j & 1);
       tc_fence_after();
+      if (j == 0) SAM2B200_STAMP(p.dbg, 4);
       float pv[kHalfN];
       {
         uint32_t r0[32];
@@ -732,11 +770,13 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
     }
     mbar_wait(&sh.acc_done, 0);
     tc_fence_after();
+    SAM2B200_STAMP(p.dbg, 5);
     grad_epilogue(p.gout, lane_addr + k3ColAcc, half, row_valid, (long long)b * p.La + a_row_idx, (int)a_row_idx, p.scale);
   }
 
   tc_fence_before();
   __syncthreads();
+  SAM2B200_STAMP(p.dbg, 6);
   if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
 }
 

@@ -1,0 +1,77 @@
+"""Micro-benchmark of the fused mask-loss kernels through the C ABI (GPU box).  CUDA-event timing on the
+launching stream, L2 flushed (a 512 MB memset) before every timed call, median of `iters`.
+Algorithmic bytes: forward 5 B/px, backward 9 B/px.
+usage: python scripts/loss_kernel_bench.py [T,C,S ...]"""
+import json, os, sys, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from sam2_video_training_b200 import _lib
+
+
+def peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return json.load(open(p))["hbm_gbs"] if os.path.exists(p) else 6650.0
+
+
+def bench(T, C, S, iters=20, mode=0, empty_every=8):
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    hw = S * S
+    logits = [torch.randn(C, hw, device=dev, generator=g) * 4 for _ in range(T)]
+    yy, xx = torch.meshgrid(torch.arange(S, device=dev), torch.arange(S, device=dev), indexing="ij")
+    tg = torch.zeros(T, C, S, S, dtype=torch.uint8, device=dev)
+    for f in range(T):
+        for c in range(C):
+            if C >= 4 and c % empty_every == empty_every - 1:
+                continue
+            cx, cy, ax, ay = [float(v) for v in torch.rand(4, generator=torch.Generator().manual_seed(f * 131 + c))]
+            tg[f, c] = (((xx - S * (.25 + .5 * cx)) / (S * (.08 + .2 * ax))) ** 2 + ((yy - S * (.25 + .5 * cy)) / (S * (.08 + .2 * ay))) ** 2 < 1)
+    iou = torch.rand(T, C, device=dev, generator=g)
+    ws = torch.empty(max(lib.sam2b200_mask_loss_workspace_bytes(T, C, hw), 4) // 4, device=dev)
+    sums = torch.empty(T, C, 6, device=dev)
+    nv = torch.empty(T, dtype=torch.int32, device=dev)
+    losses = torch.zeros(4, device=dev)
+    dl = [torch.empty(C, hw, device=dev) for _ in range(T)]
+    diou = torch.empty(T, C, device=dev)
+    gl = torch.tensor([20.0, 1.0, 1.0, 0.0], device=dev)
+    lp = _lib.ptr_array([x.data_ptr() for x in logits])
+    dp = _lib.ptr_array([x.data_ptr() for x in dl])
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def fwd():
+        _lib.check(lib.sam2b200_mask_loss_fwd(lp, tg.data_ptr(), iou.data_ptr(), None, ws.data_ptr(), sums.data_ptr(),
+                                              nv.data_ptr(), losses.data_ptr(), T, C, hw, mode, 0.25, 2.0, 1.0, 1, 1, st), "fwd")
+
+    def bwd():
+        _lib.check(lib.sam2b200_mask_loss_bwd(lp, dp, tg.data_ptr(), iou.data_ptr(), None, sums.data_ptr(), nv.data_ptr(),
+                                              gl.data_ptr(), diou.data_ptr(), T, C, hw, mode, 0.25, 2.0, 1.0, 1, 1, st), "bwd")
+
+    def timeit(fn):
+        ts = []
+        for _ in range(iters + 3):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts = sorted(ts[3:])
+        return ts[len(ts) // 2], ts[0]
+
+    px = T * C * hw
+    pk = peak_gbs()
+    (f_med, f_min), (b_med, b_min) = timeit(fwd), timeit(bwd)
+    gf, gb = 5 * px / f_med / 1e6, 9 * px / b_med / 1e6
+    gt = 14 * px / (f_med + b_med) / 1e6
+    print(f"T={T} C={C} S={S} ({px/1e6:.1f} Mpx): fwd {f_med*1e3:7.1f} us (min {f_min*1e3:.1f}) {gf:6.0f} GB/s {gf/pk:5.1%} | "
+          f"bwd {b_med*1e3:7.1f} us (min {b_min*1e3:.1f}) {gb:6.0f} GB/s {gb/pk:5.1%} | fwd+bwd {gt:6.0f} GB/s {gt/pk:5.1%} of {pk:.0f}",
+          flush=True)
+    return dict(T=T, C=C, S=S, fwd_us=f_med * 1e3, bwd_us=b_med * 1e3, gbs=gt, frac=gt / pk)
+
+
+if __name__ == "__main__":
+    shapes = [tuple(int(x) for x in a.split(",")) for a in sys.argv[1:]] or [
+        (10, 7, 384), (10, 56, 384), (8, 13, 512), (1, 4, 1024), (1, 8, 1024), (1, 32, 1024), (4, 32, 1024)]
+    for s in shapes:
+        bench(*s)

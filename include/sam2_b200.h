@@ -107,7 +107,12 @@ int sam2b200_colsum(int mode, const float* in_f32, void* io_bf16, const void* h_
  * Outputs: chan_sums [T, C, 6] (sum focal|bce, sum p*t, sum p, sum t, |pred&gt|, |pred|gt|),
  * n_valid [T] (channels with foreground; 0 => the caller raises "No valid masks"),
  * losses [4]: multistep: loss_mask, loss_dice, loss_iou, 0 summed over frames (losses.py:116-119);
- * bce: losses[0] = sum over frames of the per-frame reduced loss. */
+ * bce: losses[0] = sum over frames of the per-frame reduced loss.
+ * workspace: sam2b200_mask_loss_workspace_bytes() bytes = per-block records + the ticket counters of the in-kernel
+ * finalisation.  The tickets are zeroed by a memset node on `stream` unless `mode` carries
+ * SAM2B200_LOSS_TICKETS_ZEROED: the caller then guarantees a workspace that was zero-filled once and has since
+ * only been used by this function on one stream at a time (the kernel leaves the tickets zeroed). */
+#define SAM2B200_LOSS_TICKETS_ZEROED 0x100
 size_t sam2b200_mask_loss_workspace_bytes(int T, int C, long long HW);
 int sam2b200_mask_loss_fwd(const float* const* logits, const uint8_t* targets, const float* iou_pred,
                            const float* pos_weight, void* workspace, float* chan_sums, int* n_valid,

@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsam2b200.so")
 SOURCES = ["abi.cu", "mask_loss.cu", "attn.cu", "glue.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--use_fast_math" if False else "-DNDEBUG"]
+              "-Xcompiler", "-fPIC", "-DNDEBUG", *os.environ.get("SAM2B200_EXTRA_NVCC_FLAGS", "").split()]
 
 
 def _nvcc() -> str:

@@ -8,12 +8,22 @@
 //   sam2_video/model/losses.py:143-238 MultiStepMultiMasksAndIous._update_losses (valid filter)
 //   sam2_video/model/losses.py:308-372 BCECategoryLoss.forward
 //
-// Forward: ONE pass over logits (fp32, 4 B/px) + targets (u8, 1 B/px) for all frames x channels,
-// 128-bit loads, per-thread register accumulation of the six per-channel sums, warp-shuffle +
-// shared-memory block reduction, one partial row per block (no atomics, deterministic), then a
-// tiny finalize kernel (valid filter, Nv, dice/focal/IoU algebra, sum over channels and frames).
+// Forward: ONE launch, one pass over logits (fp32, 4 B/px) + targets (u8, 1 B/px) for all frames x
+// channels.  Every warp instruction reads 512 contiguous bytes of logits (lane-interleaved 128-bit
+// loads) and 128 contiguous bytes of targets; 20 independent loads are in flight per thread before any
+// math.  Per-thread register accumulation, warp-shuffle + shared-memory block reduction, one partial
+// record per block (no floating-point atomics -> deterministic).  The LAST block of a channel (ticket
+// counter) folds that channel's records in fp64 in a fixed order, and the last channel of the launch
+// does the valid-channel filter, Nv, the dice / focal / IoU algebra and the sum over channels and
+// frames -- there is no second kernel.
 // Backward: one pass reading logits + targets and writing dlogits (9 B/px), using the per-channel
 // sums of the forward (dice needs full-image sums, so it cannot be fused into the forward pass).
+//
+// Arithmetic.  With z = (t ? -x : x) / T_logit:  q = sigmoid(z) = 1 - p_t and softplus(z) = BCE(x, t), so
+//   focal = alpha_t * softplus(z) * q^gamma,   p = t ? 1 - q : q,
+//   d focal / dx = sgn * alpha_t * q^gamma * (q + gamma * softplus(z) * (1 - q)),  sgn = t ? -1 : +1,
+// i.e. 3 SFU operations per pixel (ex2, rcp, lg2) and ~20 issue slots: at 5 B/px the forward needs
+// 4.7 px/clk/SM to saturate HBM and the SFU pipe delivers 5.3.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -22,11 +32,29 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kPxPerThreadIter = 16;                 // 4 x float4 + 1 x uint4 per iteration
-constexpr int kItersPerBlock = 2;                    // -> 8192 px per block
-constexpr int kChunk = kThreads * kPxPerThreadIter * kItersPerBlock;
+constexpr int kPxPerThreadIter = 16;                 // 4 x (float4 + u32) per thread per iteration
+// Work per block, measured on B200 (scripts/loss_sweep.sh, profiles/r1_loss_sweep.txt): the forward pays a
+// fixed per-block cost (block reduction, fence, ticket), so it takes 16384 px per block in 4 rounds of
+// 8 loads per thread; the backward has no epilogue and is fastest with the smallest blocks (4096 px).
+#ifndef SAM2B200_LOSS_FWD_ROUNDS
+#define SAM2B200_LOSS_FWD_ROUNDS 4
+#endif
+#ifndef SAM2B200_LOSS_BWD_ROUNDS
+#define SAM2B200_LOSS_BWD_ROUNDS 1
+#endif
+constexpr int kItersPerRound = 1;                    // loads of one round are all issued before its math
+constexpr int kIterPx = kThreads * kPxPerThreadIter;                 // 4096
+constexpr int kFwdRounds = SAM2B200_LOSS_FWD_ROUNDS;
+constexpr int kBwdRounds = SAM2B200_LOSS_BWD_ROUNDS;
+constexpr int kFwdChunk = kIterPx * kItersPerRound * kFwdRounds;     // px per forward block
+constexpr int kBwdChunk = kIterPx * kItersPerRound * kBwdRounds;     // px per backward block
+static_assert(kFwdChunk / kThreads <= 255 && kBwdChunk / kThreads <= 255, "8-bit per-thread counters");
 constexpr int kMaxFrames = 64;                       // frames per launch (pointer table in params)
 constexpr int kNumSums = 6;                          // focal|bce, p*t, p, t, inter, union
+constexpr int kRec = 8;                              // floats per block record
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
 
 struct FramePtrs {
   const float* logits[kMaxFrames];
@@ -42,11 +70,9 @@ __device__ __forceinline__ float4 ldg_f4(const float* p) {
                : "l"(p));
   return r;
 }
-__device__ __forceinline__ uint4 ldg_u4(const uint8_t* p) {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p));
+__device__ __forceinline__ uint32_t ldg_u32(const uint8_t* p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
   return r;
 }
 __device__ __forceinline__ void stg_f4(float* p, float4 v) {
@@ -54,53 +80,60 @@ __device__ __forceinline__ void stg_f4(float* p, float4 v) {
                "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
 }
-
-struct PixelTerms {
-  float p;    // sigmoid(x)
-  float ce;   // BCE-with-logits(x, t), unweighted
-  float sp;   // softplus(-x)
-};
-
-// One exp, one log, one reciprocal per pixel (3 SFU ops), overflow-free for any x.
-__device__ __forceinline__ PixelTerms pixel_terms(float x, float t) {
-  PixelTerms r;
-  float e = __expf(-fabsf(x));
-  float inv = __frcp_rn(1.0f + e);
-  r.p = (x >= 0.f) ? inv : e * inv;
-  float l1p = __logf(1.0f + e);
-  r.sp = fmaxf(-x, 0.f) + l1p;               // softplus(-x)
-  r.ce = fmaf(1.0f - t, x, r.sp);            // (1-t) x + softplus(-x)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
 
-template <int MODE>  // 0 = focal+dice+iou sums, 1 = BCE category sums
+// z -> (d = 1 + exp(-z), softplus(z)); z is clamped below so that exp(-z) stays finite.
+template <bool UNIT_T>
+__device__ __forceinline__ void softplus_terms(float zraw, float inv_temp, float& d, float& sp) {
+  const float z = fmaxf(UNIT_T ? zraw : zraw * inv_temp, -80.0f);
+  d = 1.0f + ex2_approx(z * -kLog2e);
+  sp = fmaf(lg2_approx(d), kLn2, z);       // z + log(1 + exp(-z))
+}
+
+// MODE 0 (focal + dice + IoU):  f0 / f1 = sum over background / foreground px of softplus(z) q^gamma,
+//   a = sum over foreground of q, bq = sum of q, cnt = packed counters T | P << 8 | I << 16
+//   (T = #foreground, P = #(x > 0), I = #(x > 0 and foreground); <= 255 px per thread).
+// MODE 1 (BCE):  f0 / f1 = sum over background / foreground px of softplus(z), cnt = T.
+template <int MODE, bool G2, bool UNIT_T>
 struct Acc {
-  float s[kNumSums];
+  float f0, f1, a, bq;
+  uint32_t cnt, inc_fg, inc_bg;
   __device__ __forceinline__ void init() {
-#pragma unroll
-    for (int i = 0; i < kNumSums; ++i) s[i] = 0.f;
+    f0 = f1 = a = bq = 0.f; cnt = 0u;
+    // counter increments of a pixel with x > 0, kept in registers (opaque to the compiler, so that the
+    // per-pixel update is SEL + predicated IADD instead of two re-materialised immediates + SEL + IADD)
+    asm volatile("mov.u32 %0, 0x10100;" : "=r"(inc_fg));
+    asm volatile("mov.u32 %0, 0x100;" : "=r"(inc_bg));
   }
-  __device__ __forceinline__ void add(float xraw, float t, float inv_temp, float alpha, float gamma,
-                                      float pos_w) {
-    float x = xraw * inv_temp;
-    PixelTerms pt = pixel_terms(x, t);
+  __device__ __forceinline__ void add(float x, bool t, float inv_temp, float gamma) {
+    float d, sp;
+    softplus_terms<UNIT_T>(t ? -x : x, inv_temp, d, sp);
     if (MODE == 0) {
-      float q = (t != 0.f) ? (1.0f - pt.p) : pt.p;           // 1 - p_t
-      float mod = (gamma == 2.0f) ? q * q : ((gamma == 0.f) ? 1.0f : __powf(q, gamma));
-      float fl = pt.ce * mod;
-      if (alpha >= 0.f) fl *= (t != 0.f) ? alpha : (1.0f - alpha);
-      s[0] += fl;
-      s[1] += pt.p * t;
-      s[2] += pt.p;
-      s[3] += t;
-      bool pr = x > 0.f, gt = t > 0.f;
-      s[4] += (pr && gt) ? 1.f : 0.f;
-      s[5] += (pr || gt) ? 1.f : 0.f;
+      const float q = rcp_approx(d);
+      float w;                                        // softplus * q^(gamma-1)
+      if (G2) w = sp * q;
+      else w = (gamma == 0.f) ? sp * d : sp * __powf(q, gamma - 1.0f);   // d = 1/q
+      if (t) { f1 = fmaf(w, q, f1); a += q; cnt += 1u; }
+      else f0 = fmaf(w, q, f0);
+      bq += q;
+      if (x > 0.f) cnt += t ? inc_fg : inc_bg;
     } else {
-      // (1-t) x + (1 + (pw-1) t) softplus(-x)
-      float w = fmaf(pos_w - 1.0f, t, 1.0f);
-      s[0] += fmaf(1.0f - t, x, w * pt.sp);
-      s[3] += t;
+      if (t) { f1 += sp; cnt += 1u; }
+      else f0 += sp;
     }
   }
 };
@@ -110,266 +143,340 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 
-// grid: (blocks_per_channel, T*C).  partials: [T*C][blocks_per_channel][kNumSums]
-template <int MODE>
+struct FwdParams {
+  const uint8_t* targets;      // [frames, C, HW]
+  const float* pos_weight;     // [C] or null (BCE)
+  const float* iou_pred;       // [tt, C] (multistep)
+  float* records;              // [tt*C][nblk][kRec]
+  int* chan_ticket;            // [tt*C], zero on entry
+  int* done_ticket;            // [1], zero on entry
+  float* chan_sums;            // [tt*C][6]
+  int* n_valid;                // [tt]
+  float* losses;               // [4]
+  long long HW;
+  int tt, C, frame0;
+  float inv_temp, alpha, gamma;
+  int iou_l1, reduction_mean, accumulate, vec_ok;
+};
+
+// grid: (blocks_per_channel, tt*C)
+template <int MODE, bool G2, bool UNIT_T>
 __global__ void __launch_bounds__(kThreads)
-mask_loss_fwd_kernel(const __grid_constant__ FramePtrs fp, const uint8_t* __restrict__ targets,
-                     const float* __restrict__ pos_weight, float* __restrict__ partials, int C,
-                     long long HW, int frame0, float inv_temp, float alpha, float gamma, int vec_ok) {
+mask_loss_fwd_kernel(const __grid_constant__ FramePtrs fp, const __grid_constant__ FwdParams P) {
   const int fc = blockIdx.y;
-  const int f = fc / C, c = fc % C;
+  const int f = fc / P.C, c = fc % P.C;
+  const long long HW = P.HW;
   const float* __restrict__ x = fp.logits[f] + (long long)c * HW;
-  const uint8_t* __restrict__ tg = targets + ((long long)(frame0 + f) * C + c) * HW;
-  const float pw = (MODE == 1 && pos_weight != nullptr) ? pos_weight[c] : 1.0f;
-  const long long begin = (long long)blockIdx.x * kChunk;
-  const long long end = (begin + kChunk < HW) ? (begin + kChunk) : HW;
+  const uint8_t* __restrict__ tg = P.targets + ((long long)(P.frame0 + f) * P.C + c) * HW;
+  const long long begin = (long long)blockIdx.x * kFwdChunk;
+  const long long end = (begin + kFwdChunk < HW) ? (begin + kFwdChunk) : HW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  Acc<MODE> acc;
+  Acc<MODE, G2, UNIT_T> acc;
   acc.init();
-  if (vec_ok && end - begin == kChunk) {
-    // full chunk, 16B-aligned rows: all loads of the block issued before any math
-    float4 xv[kItersPerBlock][4];
-    uint4 tv[kItersPerBlock];
+  if (P.vec_ok && end - begin == kFwdChunk) {
+#pragma unroll 1
+    for (int r = 0; r < kFwdRounds; ++r) {
+      float4 xv[kItersPerRound][4];
+      uint32_t tv[kItersPerRound][4];
 #pragma unroll
-    for (int it = 0; it < kItersPerBlock; ++it) {
-      // thread owns 16 consecutive px; a warp covers 512 px = 2 KB of logits per iteration
-      long long base = begin + ((long long)it * kThreads + threadIdx.x) * kPxPerThreadIter;
-      tv[it] = ldg_u4(tg + base);
+      for (int it = 0; it < kItersPerRound; ++it) {
+        // warp `warp` owns 512 consecutive px of this iteration; load j covers 128 of them (512 B of logits)
+        const long long base = begin + (long long)(r * kItersPerRound + it) * kIterPx + warp * 512 + lane * 4;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) xv[it][j] = ldg_f4(x + base + 4 * j);
-    }
+        for (int j = 0; j < 4; ++j) {
+          tv[it][j] = ldg_u32(tg + base + j * 128);
+          xv[it][j] = ldg_f4(x + base + j * 128);
+        }
+      }
 #pragma unroll
-    for (int it = 0; it < kItersPerBlock; ++it) {
-      const uint32_t tw[4] = {tv[it].x, tv[it].y, tv[it].z, tv[it].w};
+      for (int it = 0; it < kItersPerRound; ++it) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float xs[4] = {xv[it][j].x, xv[it][j].y, xv[it][j].z, xv[it][j].w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float t = ((tw[j] >> (8 * k)) & 0xffu) ? 1.0f : 0.0f;
-          acc.add(xs[k], t, inv_temp, alpha, gamma, pw);
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t tw = tv[it][j];
+          acc.add(xv[it][j].x, (tw & 0x000000ffu) != 0u, P.inv_temp, P.gamma);
+          acc.add(xv[it][j].y, (tw & 0x0000ff00u) != 0u, P.inv_temp, P.gamma);
+          acc.add(xv[it][j].z, (tw & 0x00ff0000u) != 0u, P.inv_temp, P.gamma);
+          acc.add(xv[it][j].w, (tw & 0xff000000u) != 0u, P.inv_temp, P.gamma);
         }
       }
     }
   } else {
-    for (long long i = begin + threadIdx.x; i < end; i += kThreads) {
-      float t = tg[i] ? 1.0f : 0.0f;
-      acc.add(x[i], t, inv_temp, alpha, gamma, pw);
-    }
+    // ragged tail / unaligned rows: <= 64 px per thread, scalar loads
+    for (long long i = begin + threadIdx.x; i < end; i += kThreads) acc.add(x[i], tg[i] != 0, P.inv_temp, P.gamma);
   }
 
-  __shared__ float red[kThreads / 32][kNumSums];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int i = 0; i < kNumSums; ++i) {
-    float v = warp_sum(acc.s[i]);
-    if (lane == 0) red[warp][i] = v;
-  }
+  // ---- block record: [f0, f1, a, bq, T, P, I, 0] ----
+  // every thread parks its 7 values in shared memory ([slot][thread]: conflict-free); warp w then folds slot w
+  // (8 values per lane in a fixed order + one shuffle tree) -- ~4x fewer instructions than 7 shuffle trees per warp.
+  __shared__ float red[kRec][kThreads];
+  __shared__ double tot[kRec];
+  __shared__ int s_flag;
+  red[0][threadIdx.x] = acc.f0;
+  red[1][threadIdx.x] = acc.f1;
+  red[2][threadIdx.x] = (MODE == 0) ? acc.a : 0.f;
+  red[3][threadIdx.x] = (MODE == 0) ? acc.bq : 0.f;
+  red[4][threadIdx.x] = (float)(acc.cnt & 0xffu);
+  red[5][threadIdx.x] = (float)((acc.cnt >> 8) & 0xffu);
+  red[6][threadIdx.x] = (float)(acc.cnt >> 16);
   __syncthreads();
-  if (threadIdx.x < kNumSums) {
+  const int nblk = gridDim.x;
+  {
     float v = 0.f;
+    if (warp < 7) {
 #pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) v += red[w][threadIdx.x];
-    partials[((long long)fc * gridDim.x + blockIdx.x) * kNumSums + threadIdx.x] = v;
+      for (int i = 0; i < kThreads / 32; ++i) v += red[warp][i * 32 + lane];
+      v = warp_sum(v);
+    }
+    if (lane == 0) {
+      P.records[((long long)fc * nblk + blockIdx.x) * kRec + warp] = v;
+      __threadfence();
+    }
   }
-}
+  __syncthreads();
+  if (threadIdx.x == 0) s_flag = (atomicAdd(&P.chan_ticket[fc], 1) == nblk - 1);
+  __syncthreads();
+  if (!s_flag) return;
 
-// One block.  chan_sums: [T*C][6] (fp32, summed in fp64 from the partials in a fixed order),
-// n_valid: [T], losses: [4] = loss_mask, loss_dice, loss_iou, loss_class (frames accumulated by
-// the caller passing accumulate=1 for the 2nd.. launch of a long clip).
-__global__ void mask_loss_finalize_kernel(const float* __restrict__ partials, int nblk, int T, int C,
-                                          long long HW, const float* __restrict__ iou_pred,
-                                          int iou_l1, float* __restrict__ chan_sums,
-                                          int* __restrict__ n_valid, float* __restrict__ losses,
-                                          int accumulate) {
-  extern __shared__ double sh[];  // [T*C][6]
-  const int n = T * C;
-  for (int i = threadIdx.x; i < n * kNumSums; i += blockDim.x) {
-    const int fc = i / kNumSums, k = i % kNumSums;
+  // ---- last block of this channel: fold its records (fixed order, fp64) ----
+  __threadfence();
+  {
+    const float* rec = P.records + (long long)fc * nblk * kRec;
     double s = 0.0;
-    for (int b = 0; b < nblk; ++b) s += (double)partials[((long long)fc * nblk + b) * kNumSums + k];
-    sh[i] = s;
-    chan_sums[i] = (float)s;
+    for (int b = lane; b < nblk; b += 32) s += (double)__ldcg(rec + (long long)b * kRec + warp);   // warp w folds slot w
+    s = warp_sum_d(s);
+    if (lane == 0) tot[warp] = s;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double lm = 0.0, ld = 0.0, li = 0.0;
-    for (int f = 0; f < T; ++f) {
-      int nv = 0;
-      for (int c = 0; c < C; ++c) nv += sh[(f * C + c) * kNumSums + 3] > 0.0;
-      n_valid[f] = nv;
-      if (nv == 0) continue;  // host raises ValueError("No valid masks") (losses.py:153-161)
-      for (int c = 0; c < C; ++c) {
-        const double* s = &sh[(f * C + c) * kNumSums];
-        if (!(s[3] > 0.0)) continue;
-        lm += s[0] / (double)HW / nv;
-        ld += (1.0 - (2.0 * s[1] + 1.0) / (s[2] + s[3] + 1.0)) / nv;
-        double actual = s[4] / fmax(s[5], 1.0);
-        double d = (double)iou_pred[f * C + c] - actual;
-        li += (iou_l1 ? fabs(d) : d * d) / nv;
-      }
-    }
-    if (accumulate) {
-      losses[0] += (float)lm; losses[1] += (float)ld; losses[2] += (float)li;
+    float* cs = P.chan_sums + (long long)fc * kNumSums;
+    const double T = tot[4];
+    if (MODE == 0) {
+      const double F = (P.alpha >= 0.f) ? (double)P.alpha * tot[1] + (1.0 - (double)P.alpha) * tot[0] : tot[0] + tot[1];
+      cs[0] = (float)F;
+      cs[1] = (float)(T - tot[2]);                      // sum p t   = sum_{t=1} (1 - q)
+      cs[2] = (float)(tot[3] + T - 2.0 * tot[2]);       // sum p     = sum_{t=0} q + sum_{t=1} (1 - q)
+      cs[3] = (float)T;
+      cs[4] = (float)tot[6];
+      cs[5] = (float)(tot[5] + T - tot[6]);             // |pred or gt|
     } else {
-      losses[0] = (float)lm; losses[1] = (float)ld; losses[2] = (float)li; losses[3] = 0.f;
+      const double pw = (P.pos_weight != nullptr) ? (double)P.pos_weight[c] : 1.0;
+      cs[0] = (float)(tot[0] + pw * tot[1]);
+      cs[1] = 0.f; cs[2] = 0.f; cs[3] = (float)T; cs[4] = 0.f; cs[5] = 0.f;
     }
-  }
-}
-
-// BCE finalize: losses[0] (+)= sum_f [ sum_{valid c} S0 / (reduction_mean ? Nv*HW : 1) ]
-__global__ void bce_loss_finalize_kernel(const float* __restrict__ partials, int nblk, int T, int C,
-                                         long long HW, int reduction_mean,
-                                         float* __restrict__ chan_sums, int* __restrict__ n_valid,
-                                         float* __restrict__ losses, int accumulate) {
-  extern __shared__ double sh[];
-  const int n = T * C;
-  for (int i = threadIdx.x; i < n * kNumSums; i += blockDim.x) {
-    const int fc = i / kNumSums, k = i % kNumSums;
-    double s = 0.0;
-    for (int b = 0; b < nblk; ++b) s += (double)partials[((long long)fc * nblk + b) * kNumSums + k];
-    sh[i] = s;
-    chan_sums[i] = (float)s;
+    P.chan_ticket[fc] = 0;                               // leave the ticket region zeroed for the next launch
+    __threadfence();
+    s_flag = (atomicAdd(P.done_ticket, 1) == P.tt * P.C - 1);
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    double tot = 0.0;
-    for (int f = 0; f < T; ++f) {
-      int nv = 0;
-      double s0 = 0.0;
-      for (int c = 0; c < C; ++c) {
-        const double* s = &sh[(f * C + c) * kNumSums];
-        if (s[3] > 0.0) { nv += 1; s0 += s[0]; }
-      }
-      n_valid[f] = nv;
-      // mean over an empty selection is NaN in the reference (losses.py:365 with no valid channel)
-      tot += reduction_mean ? s0 / ((double)nv * (double)HW) : s0;
+  if (!s_flag) return;
+
+  // ---- last channel of the launch: valid filter, Nv, loss algebra, sums over channels and frames ----
+  __threadfence();
+  __shared__ int nv_sh[kMaxFrames];
+  __shared__ double part[3][kThreads / 32];
+  const int n = P.tt * P.C;
+  for (int i = threadIdx.x; i < P.tt; i += kThreads) nv_sh[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += kThreads)
+    if (__ldcg(P.chan_sums + (long long)i * kNumSums + 3) > 0.f) atomicAdd(&nv_sh[i / P.C], 1);
+  __syncthreads();
+  double lm = 0.0, ld = 0.0, li = 0.0;
+  if (MODE == 0) {
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+      const float* s = P.chan_sums + (long long)i * kNumSums;
+      const double s0 = __ldcg(s), s1 = __ldcg(s + 1), s2 = __ldcg(s + 2), s3 = __ldcg(s + 3), s4 = __ldcg(s + 4), s5 = __ldcg(s + 5);
+      const int nv = nv_sh[i / P.C];
+      if (!(s3 > 0.0) || nv == 0) continue;             // no foreground: filtered out (losses.py:153-159)
+      lm += s0 / (double)HW / nv;
+      ld += (1.0 - (2.0 * s1 + 1.0) / (s2 + s3 + 1.0)) / nv;
+      const double dd = (double)P.iou_pred[i] - s4 / fmax(s5, 1.0);
+      li += (P.iou_l1 ? fabs(dd) : dd * dd) / nv;
     }
-    if (accumulate) losses[0] += (float)tot; else losses[0] = (float)tot;
+  } else {
+    // per frame: sum_{valid c} S0 / (mean ? Nv * HW : 1); a frame with no valid channel is NaN under "mean"
+    // (the reference takes the mean of an empty selection, losses.py:365)
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+      const float* s = P.chan_sums + (long long)i * kNumSums;
+      const double s0 = __ldcg(s), s3 = __ldcg(s + 3);
+      const int nv = nv_sh[i / P.C];
+      if (s3 > 0.0) lm += P.reduction_mean ? s0 / ((double)nv * (double)HW) : s0;
+    }
+    if (P.reduction_mean)
+      for (int i = threadIdx.x; i < P.tt; i += kThreads)
+        if (nv_sh[i] == 0) lm += __longlong_as_double(0x7ff8000000000000LL);
+  }
+  lm = warp_sum_d(lm); ld = warp_sum_d(ld); li = warp_sum_d(li);
+  if (lane == 0) { part[0][warp] = lm; part[1][warp] = ld; part[2][warp] = li; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < P.tt; i += kThreads) P.n_valid[i] = nv_sh[i];
+  if (threadIdx.x == 0) {
+    *P.done_ticket = 0;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) { a0 += part[0][w]; a1 += part[1][w]; a2 += part[2][w]; }
+    if (P.accumulate) {
+      P.losses[0] += (float)a0;
+      if (MODE == 0) { P.losses[1] += (float)a1; P.losses[2] += (float)a2; }
+    } else {
+      P.losses[0] = (float)a0;
+      if (MODE == 0) { P.losses[1] = (float)a1; P.losses[2] = (float)a2; P.losses[3] = 0.f; }
+    }
   }
 }
 
-// Backward.  grid: (blocks_per_channel, T*C).  gout: [3] = d/d loss_mask, d/d loss_dice, d/d loss_iou
-// (MODE 0) or [1] = d/d (sum over frames of per-frame loss) (MODE 1).
-template <int MODE>
+struct BwdParams {
+  const uint8_t* targets;
+  const float* pos_weight;
+  const float* chan_sums;      // [tt*C][6]
+  const int* n_valid;          // [tt]
+  const float* gout;           // [3] d/d(loss_mask, loss_dice, loss_iou)  or [1] (BCE)
+  const float* iou_pred;       // [tt*C]
+  float* diou;                 // [tt*C]
+  long long HW;
+  int C, frame0;
+  float inv_temp, alpha, gamma;
+  int iou_l1, reduction_mean, vec_ok;
+};
+
+// Backward.  grid: (blocks_per_channel, tt*C).
+template <int MODE, bool G2, bool UNIT_T>
 __global__ void __launch_bounds__(kThreads)
 mask_loss_bwd_kernel(const __grid_constant__ FramePtrs fp, const __grid_constant__ FrameOutPtrs op,
-                     const uint8_t* __restrict__ targets, const float* __restrict__ pos_weight,
-                     const float* __restrict__ chan_sums, const int* __restrict__ n_valid,
-                     const float* __restrict__ gout, const float* __restrict__ iou_pred,
-                     float* __restrict__ diou, int C, long long HW, int frame0, float inv_temp,
-                     float alpha, float gamma, int iou_l1, int reduction_mean, int vec_ok) {
+                     const __grid_constant__ BwdParams P) {
   const int fc = blockIdx.y;
-  const int f = fc / C, c = fc % C;
+  const int f = fc / P.C, c = fc % P.C;
+  const long long HW = P.HW;
   const float* __restrict__ x = fp.logits[f] + (long long)c * HW;
   float* __restrict__ dx = op.dlogits[f] + (long long)c * HW;
-  const uint8_t* __restrict__ tg = targets + ((long long)(frame0 + f) * C + c) * HW;
-  const float* s = chan_sums + (long long)fc * kNumSums;
-  const int nv = n_valid[f];
+  const uint8_t* __restrict__ tg = P.targets + ((long long)(P.frame0 + f) * P.C + c) * HW;
+  const float* s = P.chan_sums + (long long)fc * kNumSums;
+  const int nv = P.n_valid[f];
   const bool valid = s[3] > 0.f && nv > 0;
-  const float pw = (MODE == 1 && pos_weight != nullptr) ? pos_weight[c] : 1.0f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  float k_focal = 0.f, dice_a = 0.f, dice_b = 0.f, k_bce = 0.f;
+  // per-channel coefficients: grad = kf_t * q^gamma * (q + gamma softplus (1-q)) + dc_t * q (1-q)      (MODE 0)
+  //                           grad = kb_t * q                                                            (MODE 1)
+  float kf_fg = 0.f, kf_bg = 0.f, dc_fg = 0.f, dc_bg = 0.f;
   if (valid) {
     if (MODE == 0) {
-      const float inv_nv_t = inv_temp / (float)nv;
-      k_focal = gout[0] * inv_nv_t / (float)HW;
-      // d dice / dx = -(2 t (D+1) - (Nn+1)) / (D+1)^2 * p (1-p) = (dice_b - dice_a * t) p (1-p)
+      const float inv_nv_t = P.inv_temp / (float)nv;
+      const float kf = P.gout[0] * inv_nv_t / (float)HW;
+      kf_fg = -kf * ((P.alpha >= 0.f) ? P.alpha : 1.0f);
+      kf_bg = kf * ((P.alpha >= 0.f) ? (1.0f - P.alpha) : 1.0f);
+      // d dice / dx = (dice_b - dice_a t) p (1-p),  dice_a = 2 kd / (D+1),  dice_b = kd (Nn+1) / (D+1)^2
       const float dp1 = s[2] + s[3] + 1.0f;
       const float nn1 = 2.0f * s[1] + 1.0f;
-      const float kd = gout[1] * inv_nv_t;
-      dice_a = kd * 2.0f / dp1;
-      dice_b = kd * nn1 / (dp1 * dp1);
+      const float kd = P.gout[1] * inv_nv_t;
+      dc_bg = kd * nn1 / (dp1 * dp1);
+      dc_fg = dc_bg - kd * 2.0f / dp1;
     } else {
-      k_bce = gout[0] * inv_temp * (reduction_mean ? 1.0f / ((float)nv * (float)HW) : 1.0f);
+      const float pw = (P.pos_weight != nullptr) ? P.pos_weight[c] : 1.0f;
+      const float kb = P.gout[0] * P.inv_temp * (P.reduction_mean ? 1.0f / ((float)nv * (float)HW) : 1.0f);
+      kf_fg = -kb * pw;
+      kf_bg = kb;
     }
   }
   if (MODE == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
     float g = 0.f;
     if (valid) {
-      float actual = s[4] / fmaxf(s[5], 1.0f);
-      float d = iou_pred[fc] - actual;
-      g = (iou_l1 ? ((d > 0.f) - (d < 0.f)) : 2.0f * d) * gout[2] / (float)nv;
+      const float actual = s[4] / fmaxf(s[5], 1.0f);
+      const float d = P.iou_pred[fc] - actual;
+      g = (P.iou_l1 ? (float)((d > 0.f) - (d < 0.f)) : 2.0f * d) * P.gout[2] / (float)nv;
     }
-    diou[fc] = g;
+    P.diou[fc] = g;
   }
 
-  auto grad = [&](float xraw, float t) -> float {
-    if (!valid) return 0.f;
-    float xs = xraw * inv_temp;
-    PixelTerms pt = pixel_terms(xs, t);
+  auto grad = [&](float xraw, bool t) -> float {
+    float d, sp;
+    softplus_terms<UNIT_T>(t ? -xraw : xraw, P.inv_temp, d, sp);
+    const float q = rcp_approx(d);
+    const float kf = t ? kf_fg : kf_bg;
     if (MODE == 0) {
-      float q = (t != 0.f) ? (1.0f - pt.p) : pt.p;
-      float pq = pt.p * (1.0f - pt.p);
-      float sgn = (t != 0.f) ? -1.0f : 1.0f;  // d q / dx = (1 - 2t) p (1-p)
-      float qg, qg1;                          // q^gamma, gamma * q^(gamma-1)
-      if (gamma == 2.0f) { qg = q * q; qg1 = 2.0f * q; }
-      else if (gamma == 0.f) { qg = 1.0f; qg1 = 0.f; }
-      else { qg1 = gamma * __powf(q, gamma - 1.0f); qg = __powf(q, gamma); }
-      float df = (pt.p - t) * qg + pt.ce * qg1 * sgn * pq;
-      if (alpha >= 0.f) df *= (t != 0.f) ? alpha : (1.0f - alpha);
-      return k_focal * df + (dice_b - dice_a * t) * pq;
+      const float omq = 1.0f - q;
+      float u, qg;
+      if (G2) { u = fmaf(sp + sp, omq, q); qg = q * q; }
+      else { u = fmaf(P.gamma * sp, omq, q); qg = (P.gamma == 0.f) ? 1.0f : __powf(q, P.gamma); }
+      return fmaf(t ? dc_fg : dc_bg, q * omq, (u * qg) * kf);
     } else {
-      float w = fmaf(pw - 1.0f, t, 1.0f);
-      return k_bce * ((1.0f - t) - w * (1.0f - pt.p));
+      return kf * q;
     }
   };
 
-  const long long begin = (long long)blockIdx.x * kChunk;
-  const long long end = (begin + kChunk < HW) ? (begin + kChunk) : HW;
-  if (vec_ok && end - begin == kChunk) {
+  const long long begin = (long long)blockIdx.x * kBwdChunk;
+  const long long end = (begin + kBwdChunk < HW) ? (begin + kBwdChunk) : HW;
+  if (P.vec_ok && end - begin == kBwdChunk) {
     if (!valid) {  // masked-out channel: write zeros without reading
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int it = 0; it < kItersPerBlock; ++it) {
-        long long base = begin + ((long long)it * kThreads + threadIdx.x) * kPxPerThreadIter;
+      for (int it = 0; it < kItersPerRound * kBwdRounds; ++it) {
+        const long long base = begin + (long long)it * kIterPx + warp * 512 + lane * 4;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) stg_f4(dx + base + 4 * j, z);
+        for (int j = 0; j < 4; ++j) stg_f4(dx + base + j * 128, z);
       }
       return;
     }
-    float4 xv[kItersPerBlock][4];
-    uint4 tv[kItersPerBlock];
+#pragma unroll 1
+    for (int r = 0; r < kBwdRounds; ++r) {
+      float4 xv[kItersPerRound][4];
+      uint32_t tv[kItersPerRound][4];
 #pragma unroll
-    for (int it = 0; it < kItersPerBlock; ++it) {
-      long long base = begin + ((long long)it * kThreads + threadIdx.x) * kPxPerThreadIter;
-      tv[it] = ldg_u4(tg + base);
+      for (int it = 0; it < kItersPerRound; ++it) {
+        const long long base = begin + (long long)(r * kItersPerRound + it) * kIterPx + warp * 512 + lane * 4;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) xv[it][j] = ldg_f4(x + base + 4 * j);
-    }
+        for (int j = 0; j < 4; ++j) {
+          tv[it][j] = ldg_u32(tg + base + j * 128);
+          xv[it][j] = ldg_f4(x + base + j * 128);
+        }
+      }
 #pragma unroll
-    for (int it = 0; it < kItersPerBlock; ++it) {
-      long long base = begin + ((long long)it * kThreads + threadIdx.x) * kPxPerThreadIter;
-      const uint32_t tw[4] = {tv[it].x, tv[it].y, tv[it].z, tv[it].w};
+      for (int it = 0; it < kItersPerRound; ++it) {
+        const long long base = begin + (long long)(r * kItersPerRound + it) * kIterPx + warp * 512 + lane * 4;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float4 o;
-        o.x = grad(xv[it][j].x, ((tw[j] >> 0) & 0xffu) ? 1.f : 0.f);
-        o.y = grad(xv[it][j].y, ((tw[j] >> 8) & 0xffu) ? 1.f : 0.f);
-        o.z = grad(xv[it][j].z, ((tw[j] >> 16) & 0xffu) ? 1.f : 0.f);
-        o.w = grad(xv[it][j].w, ((tw[j] >> 24) & 0xffu) ? 1.f : 0.f);
-        stg_f4(dx + base + 4 * j, o);
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t tw = tv[it][j];
+          float4 o;
+          o.x = grad(xv[it][j].x, (tw & 0x000000ffu) != 0u);
+          o.y = grad(xv[it][j].y, (tw & 0x0000ff00u) != 0u);
+          o.z = grad(xv[it][j].z, (tw & 0x00ff0000u) != 0u);
+          o.w = grad(xv[it][j].w, (tw & 0xff000000u) != 0u);
+          stg_f4(dx + base + j * 128, o);
+        }
       }
     }
   } else {
-    for (long long i = begin + threadIdx.x; i < end; i += kThreads)
-      dx[i] = grad(x[i], tg[i] ? 1.0f : 0.0f);
+    for (long long i = begin + threadIdx.x; i < end; i += kThreads) dx[i] = valid ? grad(x[i], tg[i] != 0) : 0.f;
   }
 }
 
-int blocks_per_channel(long long HW) { return (int)((HW + kChunk - 1) / kChunk); }
+int fwd_blocks_per_channel(long long HW) { return (int)((HW + kFwdChunk - 1) / kFwdChunk); }
+int bwd_blocks_per_channel(long long HW) { return (int)((HW + kBwdChunk - 1) / kBwdChunk); }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
+
+size_t records_bytes(int tt, int C, long long HW) {
+  size_t b = (size_t)tt * C * fwd_blocks_per_channel(HW) * kRec * sizeof(float);
+  return (b + 255) & ~size_t(255);
+}
+// The ticket region sits at the START of the workspace and has a FIXED size (65535 channel tickets + 1), so that a
+// workspace shared by calls of different shapes never has records of one call where another expects zeroed tickets.
+constexpr int kMaxChannelsPerLaunch = 65535;
+constexpr size_t kTicketBytes = ((size_t)(kMaxChannelsPerLaunch + 1) * sizeof(int) + 255) & ~size_t(255);
 
 }  // namespace
 
 extern "C" {
 
-// Workspace (floats) the forward needs for its per-block partial sums.
+// Workspace the forward needs: per-block records + the ticket counters of the in-kernel finalisation.
 size_t sam2b200_mask_loss_workspace_bytes(int T, int C, long long HW) {
   int tt = T < kMaxFrames ? T : kMaxFrames;
-  return (size_t)tt * C * blocks_per_channel(HW) * kNumSums * sizeof(float);
+  return kTicketBytes + records_bytes(tt, C, HW);
 }
 
 int sam2b200_mask_loss_fwd(const float* const* logits, const uint8_t* targets, const float* iou_pred,
@@ -377,39 +484,52 @@ int sam2b200_mask_loss_fwd(const float* const* logits, const uint8_t* targets, c
                            float* losses, int T, int C, long long HW, int mode, float alpha,
                            float gamma, float inv_temp, int iou_l1, int reduction_mean,
                            cudaStream_t stream) {
+  // mode bit 8 (SAM2B200_LOSS_TICKETS_ZEROED): the caller guarantees that the ticket region of `workspace` is zero
+  // (zero-initialised once and since then only used by this function, which leaves it zeroed) -> no memset node.
+  const bool tickets_zeroed = (mode & 0x100) != 0;
+  mode &= 0xff;
   if (T <= 0 || C <= 0 || HW <= 0 || !logits || !targets || !workspace || !chan_sums || !n_valid ||
       !losses || (mode == 0 && !iou_pred) || (mode != 0 && mode != 1))
     return sam2b200::fail(SAM2B200_ERR_INVALID, "mask_loss_fwd: bad arguments");
-  const int nblk = blocks_per_channel(HW);
+  const int nblk = fwd_blocks_per_channel(HW);
+  int launches = 0;
   for (int f0 = 0; f0 < T; f0 += kMaxFrames) {
     const int tt = (T - f0 < kMaxFrames) ? (T - f0) : kMaxFrames;
+    if ((long long)tt * C > kMaxChannelsPerLaunch) return sam2b200::fail(SAM2B200_ERR_INVALID, "mask_loss_fwd: frames x channels per launch > 65535");
     FramePtrs fp;
-    int vec_ok = (HW % 16 == 0) && aligned16(targets);
+    int vec_ok = (HW % 4 == 0) && aligned4(targets);
     for (int f = 0; f < tt; ++f) {
       fp.logits[f] = logits[f0 + f];
       if (!fp.logits[f]) return sam2b200::fail(SAM2B200_ERR_INVALID, "mask_loss_fwd: null frame");
       vec_ok = vec_ok && aligned16(fp.logits[f]);
     }
+    FwdParams P;
+    P.targets = targets; P.pos_weight = pos_weight; P.iou_pred = iou_pred ? iou_pred + (size_t)f0 * C : nullptr;
+    P.chan_ticket = static_cast<int*>(workspace);
+    P.done_ticket = P.chan_ticket + kMaxChannelsPerLaunch;
+    P.records = reinterpret_cast<float*>(static_cast<char*>(workspace) + kTicketBytes);
+    P.chan_sums = chan_sums + (size_t)f0 * C * kNumSums;
+    P.n_valid = n_valid + f0; P.losses = losses; P.HW = HW; P.tt = tt; P.C = C; P.frame0 = f0;
+    P.inv_temp = inv_temp; P.alpha = alpha; P.gamma = gamma; P.iou_l1 = iou_l1; P.reduction_mean = reduction_mean;
+    P.accumulate = f0 > 0; P.vec_ok = vec_ok;
+    if (!tickets_zeroed) {
+      cudaError_t e = cudaMemsetAsync(P.chan_ticket, 0, (size_t)tt * C * sizeof(int), stream);
+      if (e == cudaSuccess) e = cudaMemsetAsync(P.done_ticket, 0, sizeof(int), stream);
+      if (e != cudaSuccess) return sam2b200::fail(SAM2B200_ERR_CUDA, "mask_loss_fwd: cudaMemsetAsync failed");
+    }
     dim3 grid(nblk, tt * C);
-    float* part = static_cast<float*>(workspace);
-    if (mode == 0)
-      mask_loss_fwd_kernel<0><<<grid, kThreads, 0, stream>>>(fp, targets, nullptr, part, C, HW, f0,
-                                                             inv_temp, alpha, gamma, vec_ok);
-    else
-      mask_loss_fwd_kernel<1><<<grid, kThreads, 0, stream>>>(fp, targets, pos_weight, part, C, HW,
-                                                             f0, inv_temp, alpha, gamma, vec_ok);
-    const size_t sh = (size_t)tt * C * kNumSums * sizeof(double);
-    if (sh > 48 * 1024) return sam2b200::fail(SAM2B200_ERR_INVALID, "mask_loss_fwd: T*C too large");
-    if (mode == 0)
-      mask_loss_finalize_kernel<<<1, 256, sh, stream>>>(
-          part, nblk, tt, C, HW, iou_pred + (size_t)f0 * C, iou_l1,
-          chan_sums + (size_t)f0 * C * kNumSums, n_valid + f0, losses, f0 > 0);
-    else
-      bce_loss_finalize_kernel<<<1, 256, sh, stream>>>(part, nblk, tt, C, HW, reduction_mean,
-                                                       chan_sums + (size_t)f0 * C * kNumSums,
-                                                       n_valid + f0, losses, f0 > 0);
+    const bool unit_t = inv_temp == 1.0f;
+    if (mode == 0) {
+      if (gamma == 2.0f && unit_t) mask_loss_fwd_kernel<0, true, true><<<grid, kThreads, 0, stream>>>(fp, P);
+      else if (gamma == 2.0f) mask_loss_fwd_kernel<0, true, false><<<grid, kThreads, 0, stream>>>(fp, P);
+      else mask_loss_fwd_kernel<0, false, false><<<grid, kThreads, 0, stream>>>(fp, P);
+    } else {
+      if (unit_t) mask_loss_fwd_kernel<1, true, true><<<grid, kThreads, 0, stream>>>(fp, P);
+      else mask_loss_fwd_kernel<1, true, false><<<grid, kThreads, 0, stream>>>(fp, P);
+    }
+    ++launches;
   }
-  return sam2b200::check_launch("mask_loss_fwd", 2 * ((T + kMaxFrames - 1) / kMaxFrames));
+  return sam2b200::check_launch("mask_loss_fwd", launches);
 }
 
 int sam2b200_mask_loss_bwd(const float* const* logits, float* const* dlogits, const uint8_t* targets,
@@ -420,12 +540,13 @@ int sam2b200_mask_loss_bwd(const float* const* logits, float* const* dlogits, co
   if (T <= 0 || C <= 0 || HW <= 0 || !logits || !dlogits || !targets || !chan_sums || !n_valid ||
       !grad_losses || (mode == 0 && (!iou_pred || !diou)) || (mode != 0 && mode != 1))
     return sam2b200::fail(SAM2B200_ERR_INVALID, "mask_loss_bwd: bad arguments");
-  const int nblk = blocks_per_channel(HW);
+  const int nblk = bwd_blocks_per_channel(HW);
+  int launches = 0;
   for (int f0 = 0; f0 < T; f0 += kMaxFrames) {
     const int tt = (T - f0 < kMaxFrames) ? (T - f0) : kMaxFrames;
     FramePtrs fp;
     FrameOutPtrs op;
-    int vec_ok = (HW % 16 == 0) && aligned16(targets);
+    int vec_ok = (HW % 4 == 0) && aligned4(targets);
     for (int f = 0; f < tt; ++f) {
       fp.logits[f] = logits[f0 + f];
       op.dlogits[f] = dlogits[f0 + f];
@@ -433,19 +554,26 @@ int sam2b200_mask_loss_bwd(const float* const* logits, float* const* dlogits, co
         return sam2b200::fail(SAM2B200_ERR_INVALID, "mask_loss_bwd: null frame");
       vec_ok = vec_ok && aligned16(fp.logits[f]) && aligned16(op.dlogits[f]);
     }
+    BwdParams P;
+    P.targets = targets; P.pos_weight = pos_weight; P.chan_sums = chan_sums + (size_t)f0 * C * kNumSums;
+    P.n_valid = n_valid + f0; P.gout = grad_losses;
+    P.iou_pred = iou_pred ? iou_pred + (size_t)f0 * C : nullptr;
+    P.diou = diou ? diou + (size_t)f0 * C : nullptr;
+    P.HW = HW; P.C = C; P.frame0 = f0; P.inv_temp = inv_temp; P.alpha = alpha; P.gamma = gamma;
+    P.iou_l1 = iou_l1; P.reduction_mean = reduction_mean; P.vec_ok = vec_ok;
     dim3 grid(nblk, tt * C);
-    if (mode == 0)
-      mask_loss_bwd_kernel<0><<<grid, kThreads, 0, stream>>>(
-          fp, op, targets, nullptr, chan_sums + (size_t)f0 * C * kNumSums, n_valid + f0, grad_losses,
-          iou_pred + (size_t)f0 * C, diou + (size_t)f0 * C, C, HW, f0, inv_temp, alpha, gamma,
-          iou_l1, reduction_mean, vec_ok);
-    else
-      mask_loss_bwd_kernel<1><<<grid, kThreads, 0, stream>>>(
-          fp, op, targets, pos_weight, chan_sums + (size_t)f0 * C * kNumSums, n_valid + f0,
-          grad_losses, nullptr, nullptr, C, HW, f0, inv_temp, alpha, gamma, iou_l1, reduction_mean,
-          vec_ok);
+    const bool unit_t = inv_temp == 1.0f;
+    if (mode == 0) {
+      if (gamma == 2.0f && unit_t) mask_loss_bwd_kernel<0, true, true><<<grid, kThreads, 0, stream>>>(fp, op, P);
+      else if (gamma == 2.0f) mask_loss_bwd_kernel<0, true, false><<<grid, kThreads, 0, stream>>>(fp, op, P);
+      else mask_loss_bwd_kernel<0, false, false><<<grid, kThreads, 0, stream>>>(fp, op, P);
+    } else {
+      if (unit_t) mask_loss_bwd_kernel<1, true, true><<<grid, kThreads, 0, stream>>>(fp, op, P);
+      else mask_loss_bwd_kernel<1, true, false><<<grid, kThreads, 0, stream>>>(fp, op, P);
+    }
+    ++launches;
   }
-  return sam2b200::check_launch("mask_loss_bwd", (T + kMaxFrames - 1) / kMaxFrames);
+  return sam2b200::check_launch("mask_loss_bwd", launches);
 }
 
 }  // extern "C"

@@ -49,6 +49,21 @@ def _prep_logits(x: torch.Tensor) -> torch.Tensor:
     return x
 
 
+_TICKETS_ZEROED = 0x100  # SAM2B200_LOSS_TICKETS_ZEROED (include/sam2_b200.h)
+_WORKSPACES: Dict[tuple, torch.Tensor] = {}
+
+
+def _persistent_workspace(dev, stream_ptr: int, nbytes: int) -> torch.Tensor:
+    """Zero-filled once, then owned by (device, stream): the kernel leaves its ticket counters zeroed, so the
+    forward needs no memset node (see sam2b200_mask_loss_fwd)."""
+    key = (dev.index, stream_ptr)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() * 4 < nbytes:
+        ws = torch.zeros(max(nbytes, 4096) // 4 + 1, dtype=torch.float32, device=dev)
+        _WORKSPACES[key] = ws
+    return ws
+
+
 class _FusedMaskLossFn(torch.autograd.Function):
     """losses[4] = fused(iou_pred[T, C], logits_0 .. logits_{T-1}); see sam2b200_mask_loss_fwd."""
 
@@ -60,7 +75,9 @@ class _FusedMaskLossFn(torch.autograd.Function):
         dev = logits[0].device
         mode = cfg["mode"]
         ws_bytes = lib.sam2b200_mask_loss_workspace_bytes(t, c, hw)
-        ws = torch.empty(max(ws_bytes, 4) // 4, dtype=torch.float32, device=dev)
+        persistent = not torch.cuda.is_current_stream_capturing()
+        ws = (_persistent_workspace(dev, _stream_ptr(dev), ws_bytes) if persistent
+              else torch.empty(max(ws_bytes, 4) // 4, dtype=torch.float32, device=dev))
         chan_sums = torch.empty(t, c, 6, dtype=torch.float32, device=dev)
         n_valid = torch.empty(t, dtype=torch.int32, device=dev)
         losses = torch.zeros(4, dtype=torch.float32, device=dev)
@@ -69,7 +86,8 @@ class _FusedMaskLossFn(torch.autograd.Function):
             rc = lib.sam2b200_mask_loss_fwd(
                 ptrs, targets_u8.data_ptr(), iou_pred.data_ptr() if iou_pred is not None else None,
                 pos_weight.data_ptr() if pos_weight is not None else None, ws.data_ptr(),
-                chan_sums.data_ptr(), n_valid.data_ptr(), losses.data_ptr(), t, c, hw, mode,
+                chan_sums.data_ptr(), n_valid.data_ptr(), losses.data_ptr(), t, c, hw,
+                mode | (_TICKETS_ZEROED if persistent else 0),
                 cfg["alpha"], cfg["gamma"], cfg["inv_temp"], int(cfg["iou_l1"]), int(cfg["reduction_mean"]),
                 _stream_ptr(dev))
         _lib.check(rc, "sam2b200_mask_loss_fwd")

@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from sam2_video_training_b200 import ops, _lib
 
-def bench(b, n, m, iters=10, bwd=True):
+def bench(b, n, m, iters=int(os.environ.get('BENCH_ITERS', '10')), bwd=True):
     dev = torch.device("cuda:0")
     g = torch.Generator(device="cuda").manual_seed(1)
     q = (torch.randn(b, n, 256, device=dev, generator=g) * 1.5).to(torch.bfloat16)
@@ -13,7 +13,7 @@ def bench(b, n, m, iters=10, bwd=True):
     v = torch.randn(b, m, 256, device=dev, generator=g).to(torch.bfloat16)
     do = torch.randn(b, n, 256, device=dev, generator=g).to(torch.bfloat16)
     scale = 1 / 16.0
-    for _ in range(3):
+    for _ in range(int(os.environ.get('BENCH_WARMUP', '3'))):
         o, o32, lse = ops.attn_fwd(q, k, v, scale)
         if bwd: ops.attn_bwd(q, k, v, None, o32, do, lse, scale)
     torch.cuda.synchronize()

@@ -1,11 +1,18 @@
 """Micro-benchmark of the fused mask-loss kernels through the C ABI (GPU box).  CUDA-event timing on the
-launching stream, L2 flushed (a 512 MB memset) before every timed call, median of `iters`.
+launching stream.  Two L2 regimes:
+  rotate (default): K independent input sets whose total size is >= 3x the 126 MB L2 are used round-robin
+                    and the whole loop of `iters` back-to-back calls is timed (inputs larger than L2);
+  write           : a 512 MB memset before every timed call (median).  The memset leaves L2 full of DIRTY
+                    lines, so the timed kernel also pays for ~126 MB of write-backs (~19 us): a pessimistic bound.
 Algorithmic bytes: forward 5 B/px, backward 9 B/px.
-usage: python scripts/loss_kernel_bench.py [T,C,S ...]"""
+usage: [LOSS_FLUSH=rotate|write] python scripts/loss_kernel_bench.py [T,C,S ...]"""
 import json, os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from sam2_video_training_b200 import _lib
+
+
+TICKETS = 0 if os.environ.get("LOSS_MEMSET") else 0x100   # SAM2B200_LOSS_TICKETS_ZEROED: persistent zeroed workspace (what losses.py does)
 
 
 def peak_gbs():
@@ -13,7 +20,76 @@ def peak_gbs():
     return json.load(open(p))["hbm_gbs"] if os.path.exists(p) else 6650.0
 
 
-def bench(T, C, S, iters=20, mode=0, empty_every=8):
+def bench(T, C, S, iters=int(os.environ.get('BENCH_ITERS', '20')), mode=0, empty_every=8):
+    if os.environ.get("LOSS_FLUSH", "rotate") == "rotate":
+        return bench_rotate(T, C, S, iters, mode, empty_every)
+    return bench_write_flush(T, C, S, iters, mode, empty_every)
+
+
+def make_set(T, C, S, dev, seed, empty_every):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    hw = S * S
+    logits = [torch.randn(C, hw, device=dev, generator=g) * 4 for _ in range(T)]
+    yy, xx = torch.meshgrid(torch.arange(S, device=dev), torch.arange(S, device=dev), indexing="ij")
+    tg = torch.zeros(T, C, S, S, dtype=torch.uint8, device=dev)
+    for f in range(T):
+        for c in range(C):
+            if C >= 4 and c % empty_every == empty_every - 1:
+                continue
+            cx, cy, ax, ay = [float(v) for v in torch.rand(4, generator=torch.Generator().manual_seed(seed * 7919 + f * 131 + c))]
+            tg[f, c] = (((xx - S * (.25 + .5 * cx)) / (S * (.08 + .2 * ax))) ** 2 + ((yy - S * (.25 + .5 * cy)) / (S * (.08 + .2 * ay))) ** 2 < 1)
+    return dict(logits=logits, tg=tg, iou=torch.rand(T, C, device=dev, generator=g),
+                dl=[torch.empty(C, hw, device=dev) for _ in range(T)],
+                lp=_lib.ptr_array([x.data_ptr() for x in logits]))
+
+
+def bench_rotate(T, C, S, iters, mode, empty_every):
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    hw = S * S
+    px = T * C * hw
+    nsets = max(2, min(64, -(-3 * 126_000_000 // (5 * px))))
+    sets = [make_set(T, C, S, dev, 3 + i, empty_every) for i in range(nsets)]
+    for s in sets:
+        s["dp"] = _lib.ptr_array([x.data_ptr() for x in s["dl"]])
+        s["ws"] = torch.zeros(max(lib.sam2b200_mask_loss_workspace_bytes(T, C, hw), 4) // 4, device=dev)
+        s["sums"] = torch.empty(T, C, 6, device=dev)
+        s["nv"] = torch.empty(T, dtype=torch.int32, device=dev)
+        s["losses"] = torch.zeros(4, device=dev)
+        s["diou"] = torch.empty(T, C, device=dev)
+    gl = torch.tensor([20.0, 1.0, 1.0, 0.0], device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def fwd(s):
+        _lib.check(lib.sam2b200_mask_loss_fwd(s["lp"], s["tg"].data_ptr(), s["iou"].data_ptr(), None, s["ws"].data_ptr(), s["sums"].data_ptr(),
+                                              s["nv"].data_ptr(), s["losses"].data_ptr(), T, C, hw, mode | TICKETS, 0.25, 2.0, 1.0, 1, 1, st), "fwd")
+
+    def bwd(s):
+        _lib.check(lib.sam2b200_mask_loss_bwd(s["lp"], s["dp"], s["tg"].data_ptr(), s["iou"].data_ptr(), None, s["sums"].data_ptr(), s["nv"].data_ptr(),
+                                              gl.data_ptr(), s["diou"].data_ptr(), T, C, hw, mode, 0.25, 2.0, 1.0, 1, 1, st), "bwd")
+
+    def timeit(fn):
+        n = max(iters, 2 * nsets)
+        for i in range(nsets):
+            fn(sets[i])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(sets[i % nsets])
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    pk = peak_gbs()
+    f_ms, b_ms = timeit(fwd), timeit(bwd)
+    gf, gb, gt = 5 * px / f_ms / 1e6, 9 * px / b_ms / 1e6, 14 * px / (f_ms + b_ms) / 1e6
+    print(f"[rotate x{nsets}] T={T} C={C} S={S} ({px/1e6:.1f} Mpx): fwd {f_ms*1e3:7.1f} us {gf:6.0f} GB/s {gf/pk:5.1%} | "
+          f"bwd {b_ms*1e3:7.1f} us {gb:6.0f} GB/s {gb/pk:5.1%} | fwd+bwd {gt:6.0f} GB/s {gt/pk:5.1%} of {pk:.0f}", flush=True)
+    return dict(T=T, C=C, S=S, fwd_us=f_ms * 1e3, bwd_us=b_ms * 1e3, gbs=gt, frac=gt / pk)
+
+
+def bench_write_flush(T, C, S, iters, mode, empty_every):
     lib = _lib.load()
     dev = torch.device("cuda:0")
     g = torch.Generator(device="cuda").manual_seed(3)
@@ -64,7 +140,7 @@ def bench(T, C, S, iters=20, mode=0, empty_every=8):
     (f_med, f_min), (b_med, b_min) = timeit(fwd), timeit(bwd)
     gf, gb = 5 * px / f_med / 1e6, 9 * px / b_med / 1e6
     gt = 14 * px / (f_med + b_med) / 1e6
-    print(f"T={T} C={C} S={S} ({px/1e6:.1f} Mpx): fwd {f_med*1e3:7.1f} us (min {f_min*1e3:.1f}) {gf:6.0f} GB/s {gf/pk:5.1%} | "
+    print(f"[write-flush] T={T} C={C} S={S} ({px/1e6:.1f} Mpx): fwd {f_med*1e3:7.1f} us (min {f_min*1e3:.1f}) {gf:6.0f} GB/s {gf/pk:5.1%} | "
           f"bwd {b_med*1e3:7.1f} us (min {b_min*1e3:.1f}) {gb:6.0f} GB/s {gb/pk:5.1%} | fwd+bwd {gt:6.0f} GB/s {gt/pk:5.1%} of {pk:.0f}",
           flush=True)
     return dict(T=T, C=C, S=S, fwd_us=f_med * 1e3, bwd_us=b_med * 1e3, gbs=gt, frac=gt / pk)

@@ -224,13 +224,18 @@ int sam2b200_attn_fwd(const void* q, const void* k, const void* v, void* out, fl
   nsplit = (total_tiles + tiles_per_split - 1) / tiles_per_split;   // no empty split
   if (nsplit > 1 && (workspace == nullptr || workspace_bytes < sam2b200_attn_fwd_workspace_bytes(B, N, M, nsplit)))
     return sam2b200::fail(SAM2B200_ERR_INVALID, "attn_fwd: workspace too small for the requested split");
-  CUtensorMap map_k, map_v;
+  if (out_f32 && !aligned16(out_f32)) return sam2b200::fail(SAM2B200_ERR_INVALID, "attn_fwd: out_f32 must be 16-byte aligned");
+  CUtensorMap map_k, map_v, map_q, map_o, map_o32;
   int rc;
   if ((rc = sam2b200::make_rows256_map(&map_k, k, B, M, attn::kBlockN))) return rc;
   if ((rc = sam2b200::make_rows256_map(&map_v, v, B, M, attn::kBlockN))) return rc;
+  if ((rc = sam2b200::make_rows256_map(&map_q, q, B, N, attn::kBlockM))) return rc;
+  if ((rc = sam2b200::make_out_map(&map_o, out, 1, B, N, 256, 32))) return rc;
+  if (out_f32) { if ((rc = sam2b200::make_out_map(&map_o32, out_f32, 0, B, N, 256, 32))) return rc; }
+  else map_o32 = map_o;
   attn::TwoGemmParams p{};
-  p.a = (const __nv_bfloat16*)q; p.La = N; p.Lx = M; p.scale_log2 = scale * kLog2e;
-  p.out = (__nv_bfloat16*)out; p.out_f32 = out_f32; p.lse2 = lse2; p.tiles_per_split = tiles_per_split;
+  p.La = N; p.Lx = M; p.scale_log2 = scale * kLog2e;
+  p.has_out_f32 = out_f32 != nullptr; p.lse2 = lse2; p.tiles_per_split = tiles_per_split;
   if (nsplit > 1) {
     p.part_acc = (float*)workspace;
     p.part_ml = p.part_acc + (size_t)nsplit * B * N * 256;
@@ -239,11 +244,11 @@ int sam2b200_attn_fwd(const void* q, const void* k, const void* v, void* out, fl
   if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_FWD>, smem))) return rc;
   dim3 grid((N + attn::kBlockM - 1) / attn::kBlockM, B, nsplit);
   p.dbg = timeline_slice((size_t)grid.x * grid.y * grid.z);
-  attn::two_gemm_kernel<attn::MODE_FWD><<<grid, attn::kThreads, smem, stream>>>(map_k, map_v, p);
+  attn::two_gemm_kernel<attn::MODE_FWD><<<grid, attn::kThreads, smem, stream>>>(map_k, map_v, map_q, map_o, map_o32, p);
   if ((rc = sam2b200::check_launch("attn_fwd"))) return rc;
   if (nsplit > 1) {
     const long long rows = (long long)B * N;
-    combine_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, stream>>>(p.part_acc, p.part_ml, p.out, out_f32, lse2, rows, nsplit);
+    combine_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, stream>>>(p.part_acc, p.part_ml, (__nv_bfloat16*)out, out_f32, lse2, rows, nsplit);
     if ((rc = sam2b200::check_launch("attn_fwd combine"))) return rc;
   }
   return SAM2B200_OK;
@@ -274,7 +279,12 @@ int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* o
     delta_kernel<false><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, stream>>>(out, (const __nv_bfloat16*)dout, delta, rows);
   if ((rc = sam2b200::check_launch("attn_bwd delta"))) return rc;
 
-  CUtensorMap map_q64, map_k64, map_v64, map_do64, map_do128, map_v128;
+  CUtensorMap map_q64, map_k64, map_v64, map_do64, map_do128, map_v128, map_q128, map_k128, map_dq, map_dk, map_dv;
+  if ((rc = sam2b200::make_rows256_map(&map_q128, q, B, N, attn::kBlockM))) return rc;
+  if ((rc = sam2b200::make_rows256_map(&map_k128, k, B, M, attn::kBlockM))) return rc;
+  if ((rc = sam2b200::make_out_map(&map_dq, dq, grad_dtype, B, N, ldq, 32))) return rc;
+  if ((rc = sam2b200::make_out_map(&map_dk, dk, grad_dtype, B, M, ldk, 32))) return rc;
+  if ((rc = sam2b200::make_out_map(&map_dv, dv, grad_dtype, B, M, ldv, 32))) return rc;
   if ((rc = sam2b200::make_rows256_map(&map_q64, q, B, N, attn::kBlockN))) return rc;
   if ((rc = sam2b200::make_rows256_map(&map_k64, k, B, M, attn::kBlockN))) return rc;
   if ((rc = sam2b200::make_rows256_map(&map_v64, v, B, M, attn::kBlockN))) return rc;
@@ -286,40 +296,40 @@ int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* o
   // dV = P^T dO: fixed K block, stream (Q, dO) tiles
   {
     attn::TwoGemmParams p{};
-    p.a = (const __nv_bfloat16*)k; p.La = M; p.Lx = N; p.scale_log2 = scale * kLog2e;
+    p.La = M; p.Lx = N; p.scale_log2 = scale * kLog2e;
     p.lse2 = const_cast<float*>(lse2);
-    p.gout = attn::GradOut{dv, ldv, grad_dtype, nullptr, 0, 1};
+    p.gout = attn::GradOut{grad_dtype, nullptr, 0, 1};
     p.tiles_per_split = (N + attn::kBlockN - 1) / attn::kBlockN;
     const size_t smem = sizeof(attn::SharedStorage) + 1024;
     if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_DV>, smem))) return rc;
     dim3 grid((M + attn::kBlockM - 1) / attn::kBlockM, B, 1);
     p.dbg = timeline_slice((size_t)grid.x * grid.y);
-    attn::two_gemm_kernel<attn::MODE_DV><<<grid, attn::kThreads, smem, stream>>>(map_q64, map_do64, p);
+    attn::two_gemm_kernel<attn::MODE_DV><<<grid, attn::kThreads, smem, stream>>>(map_q64, map_do64, map_k128, map_dv, map_dv, p);
     if ((rc = sam2b200::check_launch("attn_bwd dV"))) return rc;
   }
   const size_t smem3 = sizeof(attn::SharedStorage3) + 1024;
   // dK = scale * dS^T Q: fixed (K in TMEM, V in SMEM), stream (Q, dO) tiles
   {
     attn::ThreeGemmParams p{};
-    p.a1 = (const __nv_bfloat16*)k; p.La = M; p.Lx = N; p.scale_log2 = scale * kLog2e; p.scale = scale;
+    p.La = M; p.Lx = N; p.scale_log2 = scale * kLog2e; p.scale = scale;
     p.lse2 = lse2; p.delta = delta;
-    p.gout = attn::GradOut{dk, ldk, grad_dtype, table, table ? n_rope_k : 0, table ? rope_period : 1};
+    p.gout = attn::GradOut{grad_dtype, table, table ? n_rope_k : 0, table ? rope_period : 1};
     if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DK>, smem3))) return rc;
     dim3 grid((M + attn::kBlockM - 1) / attn::kBlockM, B, 1);
     p.dbg = timeline_slice((size_t)grid.x * grid.y);
-    attn::three_gemm_kernel<attn::MODE_DK><<<grid, attn::kThreads, smem3, stream>>>(map_v128, map_q64, map_do64, p);
+    attn::three_gemm_kernel<attn::MODE_DK><<<grid, attn::kThreads, smem3, stream>>>(map_v128, map_q64, map_do64, map_k128, map_dk, p);
     if ((rc = sam2b200::check_launch("attn_bwd dK"))) return rc;
   }
   // dQ = scale * dS K: fixed (Q in TMEM, dO in SMEM), stream (K, V) tiles
   {
     attn::ThreeGemmParams p{};
-    p.a1 = (const __nv_bfloat16*)q; p.La = N; p.Lx = M; p.scale_log2 = scale * kLog2e; p.scale = scale;
+    p.La = N; p.Lx = M; p.scale_log2 = scale * kLog2e; p.scale = scale;
     p.lse2 = lse2; p.delta = delta;
-    p.gout = attn::GradOut{dq, ldq, grad_dtype, table, table ? N : 0, table ? rope_period : 1};
+    p.gout = attn::GradOut{grad_dtype, table, table ? N : 0, table ? rope_period : 1};
     if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DQ>, smem3))) return rc;
     dim3 grid((N + attn::kBlockM - 1) / attn::kBlockM, B, 1);
     p.dbg = timeline_slice((size_t)grid.x * grid.y);
-    attn::three_gemm_kernel<attn::MODE_DQ><<<grid, attn::kThreads, smem3, stream>>>(map_do128, map_k64, map_v64, p);
+    attn::three_gemm_kernel<attn::MODE_DQ><<<grid, attn::kThreads, smem3, stream>>>(map_do128, map_k64, map_v64, map_q128, map_dq, p);
     if ((rc = sam2b200::check_launch("attn_bwd dQ"))) return rc;
   }
   return SAM2B200_OK;

@@ -13,7 +13,11 @@
 //
 // Hardware mapping (identical in every kernel):
 //   * the fixed 128 x 256 operand A lives in TENSOR MEMORY as the bf16 A-operand of tcgen05.mma
-//     (.kind::f16, A from TMEM), written there once from registers with tcgen05.st;
+//     (.kind::f16, A from TMEM): it arrives by TMA in the last (still unused) ring stage and is moved
+//     shared -> registers -> tensor memory (tcgen05.st) once;
+//   * results leave through shared memory too: every epilogue warp stages its 32 accumulator rows in the
+//     (by then idle) ring in the 128-byte-swizzle box layout and issues its own TMA bulk-tensor stores --
+//     fully coalesced writes, rows beyond the tensor clipped by the TMA unit, no block-level barrier;
 //   * streamed 64 x 256 tiles arrive by TMA (cp.async.bulk.tensor, 128-byte swizzle) into a
 //     shared-memory ring; the SAME tile is consumed K-major (scores GEMM, contraction over the
 //     256 features) and MN-major (accumulate GEMM, contraction over the 64 rows);
@@ -77,22 +81,18 @@ __device__ __forceinline__ unsigned smid() {
 
 // Optional fused epilogue for gradient outputs: conjugate axial rotation + bf16 store with a row stride.
 struct GradOut {
-  void* ptr;                   // [B, La, ld] bf16 or fp32
-  int ld;                      // row stride in elements (>= 256)
-  int is_bf16;
+  int is_bf16;                 // element type of the output tensor map (bf16 or fp32)
   const float2* rope_table;    // [period, 128] (cos, sin) or nullptr = no rotation
   int rope_rows;               // rows [0, rope_rows) of every batch item are un-rotated (conjugate)
   int rope_period;             // table row = row % rope_period
 };
 
 struct TwoGemmParams {
-  const __nv_bfloat16* a;      // [B, La, 256] fixed operand (Q in FWD, K in DV)
   int La;                      // rows of a per batch (N in FWD, M in DV)
   int Lx;                      // streamed length per batch (M in FWD, N in DV)
   float scale_log2;            // softmax scale * log2(e)
   // FWD outputs
-  __nv_bfloat16* out;          // [B, La, 256] bf16 (nsplit == 1)
-  float* out_f32;              // optional fp32 copy of out (kept for Delta = rowsum(dO o O) in the backward)
+  int has_out_f32;             // FWD, nsplit == 1: also store the fp32 copy of out (map_o32; kept for Delta = rowsum(dO o O))
   float* lse2;                 // [B, La] log2-domain LSE (FWD: output; DV: input, length Lx)
   float* part_acc;             // [nsplit, B, La, 256] fp32 un-normalised partials (nsplit > 1)
   float* part_ml;              // [nsplit, B, La, 2]  (m_ref * c, l)
@@ -111,27 +111,30 @@ struct SharedStorage {
   uint64_t s_full[2];
   uint64_t p_ready[2];
   uint64_t acc_done;
-  uint64_t a_ready;
+  uint64_t a_full;             // TMA: fixed operand landed in ring stage kStages-1
+  uint64_t a_ready;            // softmax warps: operand moved to tensor memory (stage kStages-1 is free again)
   float colvec[2][kBlockN];    // DV: LSE2 of the tile's columns
   float xchg[2][2][kBlockM];   // [buffer][half][row]: row-max exchange between the two halves of a row
   float lsum[2][kBlockM];      // [half][row]: row-sum exchange in the epilogue
   uint32_t tmem_base;
 };
 
-// Each of the two warps of a lane quarter loads HALF of its rows' 256 features (2 x 64 elements).
-__device__ __forceinline__ void load_fixed_operand_half(const __nv_bfloat16* a_row, bool valid, uint32_t taddr,
-                                                        int half) {
+// The fixed operand is staged by TMA as four [128 rows x 128 B] slabs (64 features each, 128-byte swizzle).
+// Each of the two warps of a lane quarter moves HALF of its rows' 256 features (slabs 2*half, 2*half+1, which
+// sit in `region`): 16-byte shared loads (conflict-free: the swizzle spreads 8 consecutive rows over all banks)
+// -> registers -> tcgen05.st as packed bf16 pairs.
+constexpr int kSlabBytes = kBlockM * 128;           // 16 KB
+__device__ __forceinline__ void stage_to_tmem_half(uint32_t region, int row, uint32_t taddr, int half) {
 #pragma unroll
   for (int cc = 0; cc < 2; ++cc) {
-    const int c = half * 2 + cc;
+    const uint32_t base = region + cc * kSlabBytes + row * 128;
     uint32_t r[32];
 #pragma unroll
     for (int v = 0; v < 8; ++v) {
-      uint4 u = make_uint4(0, 0, 0, 0);
-      if (valid) u = __ldg(reinterpret_cast<const uint4*>(a_row) + c * 8 + v);
+      const uint4 u = lds128(base + ((v ^ (row & 7)) << 4));
       r[4 * v + 0] = u.x; r[4 * v + 1] = u.y; r[4 * v + 2] = u.z; r[4 * v + 3] = u.w;
     }
-    SAM2B200_TMEM_ST32(taddr + c * 32, r);
+    SAM2B200_TMEM_ST32(taddr + (half * 2 + cc) * 32, r);
   }
   tmem_wait_st();
 }
@@ -140,10 +143,44 @@ __device__ __forceinline__ void pair_barrier(int quarter) {
   asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
 }
 
-// Gradient epilogue of one accumulator row half (4 chunks of 32 columns): TMEM -> registers -> scale ->
-// conjugate axial rotation -> bf16/fp32 store.  The (cos, sin) table rows are L2-resident but ~1 us away:
-// the loads for chunk i+1 are issued before chunk i is processed (software pipeline), and the TMEM load of
-// chunk i+1 is in flight while chunk i is rotated and stored.
+// ---- TMA-store epilogue staging.  A warp owns 32 accumulator rows x 128 columns.  bf16: two boxes of
+// [32 rows x 64 cols] (4 KB each); fp32: four boxes of [32 rows x 32 cols] (4 KB each); a box row is 128 B and
+// its 16-byte chunks are XOR-swizzled with (row & 7), the layout CU_TENSOR_MAP_SWIZZLE_128B expects.
+constexpr int kBoxBytes = 32 * 128;
+__device__ __forceinline__ void stage_chunk_bf16(uint32_t stage, int lane, int i /*chunk 0..3 of the warp's 128 cols*/,
+                                                 const float* v) {
+  const uint32_t base = stage + (i >> 1) * kBoxBytes + lane * 128;
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4)
+    sts128(base + ((((i & 1) * 4 + q4) ^ (lane & 7)) << 4), pack_bf16(v[8 * q4 + 0], v[8 * q4 + 1]),
+           pack_bf16(v[8 * q4 + 2], v[8 * q4 + 3]), pack_bf16(v[8 * q4 + 4], v[8 * q4 + 5]),
+           pack_bf16(v[8 * q4 + 6], v[8 * q4 + 7]));
+}
+__device__ __forceinline__ void stage_chunk_f32(uint32_t stage, int lane, int i, const float* v) {
+  const uint32_t base = stage + i * kBoxBytes + lane * 128;
+#pragma unroll
+  for (int q4 = 0; q4 < 8; ++q4)
+    sts128(base + ((q4 ^ (lane & 7)) << 4), __float_as_uint(v[4 * q4]), __float_as_uint(v[4 * q4 + 1]),
+           __float_as_uint(v[4 * q4 + 2]), __float_as_uint(v[4 * q4 + 3]));
+}
+// Make the warp's staged box visible to the async proxy and let one lane hand it to the TMA unit.
+__device__ __forceinline__ void store_box(const CUtensorMap* map, uint32_t box_smem, int lane, int c0, int row0, int b,
+                                          bool in_range) {
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0 && in_range) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 :
+                 : "l"(reinterpret_cast<uint64_t>(map)), "r"(box_smem), "r"(c0), "r"(row0), "r"(b)
+                 : "memory");
+    tma_store_commit();
+  }
+}
+
+// Gradient epilogue of one warp (32 rows x 128 columns = 4 chunks of 32 columns): TMEM -> registers -> scale ->
+// conjugate axial rotation -> shared-memory staging -> TMA store.  The (cos, sin) table rows are L2-resident but
+// ~1 us away: the caller issues the loads of chunk 0 BEFORE waiting for the last MMA (table_prefetch), the loads
+// for chunk i+1 are issued before chunk i is processed, and the TMEM load of chunk i+1 is in flight meanwhile.
 __device__ __forceinline__ void load_table_chunk(const GradOut& g, bool rotate, int row_in_batch, int col0, float2* t) {
   if (rotate) {
     const float4* src = reinterpret_cast<const float4*>(g.rope_table + (long long)(row_in_batch % g.rope_period) * 128 + (col0 >> 1));
@@ -152,42 +189,15 @@ __device__ __forceinline__ void load_table_chunk(const GradOut& g, bool rotate, 
   }
 }
 
-__device__ __forceinline__ void store_grad_chunk(const GradOut& g, bool rotate, const float2* t, long long brow, int col0,
-                                                 float* v /* 32 values, modified */) {
-  if (rotate) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float2 cs = t[i];
-      const float re = v[2 * i] * cs.x + v[2 * i + 1] * cs.y;      // multiply by conj(cos + i sin)
-      const float im = v[2 * i + 1] * cs.x - v[2 * i] * cs.y;
-      v[2 * i] = re; v[2 * i + 1] = im;
-    }
-  }
-  if (g.is_bf16) {
-    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(g.ptr) + brow * g.ld + col0;
-#pragma unroll
-    for (int q4 = 0; q4 < 4; ++q4) {
-      uint4 u;
-      u.x = pack_bf16(v[8 * q4 + 0], v[8 * q4 + 1]); u.y = pack_bf16(v[8 * q4 + 2], v[8 * q4 + 3]);
-      u.z = pack_bf16(v[8 * q4 + 4], v[8 * q4 + 5]); u.w = pack_bf16(v[8 * q4 + 6], v[8 * q4 + 7]);
-      *reinterpret_cast<uint4*>(o + q4 * 8) = u;
-    }
-  } else {
-    float* o = static_cast<float*>(g.ptr) + brow * g.ld + col0;
-#pragma unroll
-    for (int q4 = 0; q4 < 8; ++q4)
-      *reinterpret_cast<float4*>(o + q4 * 4) = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
-  }
-}
-
 // acc_addr: TMEM address of column 0 of this thread's accumulator row; half selects columns [128h, 128h+128).
-__device__ __forceinline__ void grad_epilogue(const GradOut& g, uint32_t acc_addr, int half, bool row_valid, long long brow,
-                                              int row_in_batch, float scale) {
-  const bool rotate = row_valid && g.rope_table != nullptr && row_in_batch < g.rope_rows;
-  float2 tcur[16], tnext[16];
+// stage: this warp's staging area (8 KB bf16 / 16 KB fp32); row0 = first row (in the batch item) of the warp.
+__device__ __forceinline__ void grad_epilogue(const GradOut& g, const CUtensorMap* map, uint32_t stage, uint32_t acc_addr,
+                                              int half, int lane, int row0, int La, int b, float scale, bool rotate,
+                                              float2* tcur /* chunk 0 of the table, already loaded */) {
+  const int row_in_batch = row0 + lane;
+  float2 tnext[16];
   uint32_t ocur[32], onext[32];
   const int c0 = half * 4;
-  load_table_chunk(g, rotate, row_in_batch, c0 * 32, tcur);
   SAM2B200_TMEM_LD32(acc_addr + c0 * 32, ocur);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -197,11 +207,24 @@ __device__ __forceinline__ void grad_epilogue(const GradOut& g, uint32_t acc_add
       SAM2B200_TMEM_LD32(acc_addr + (cc + 1) * 32, onext);
       load_table_chunk(g, rotate, row_in_batch, (cc + 1) * 32, tnext);
     }
-    if (row_valid) {
-      float v[32];
+    float v[32];
 #pragma unroll
-      for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(ocur[k]) * scale;
-      store_grad_chunk(g, rotate, tcur, brow, cc * 32, v);
+    for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(ocur[k]) * scale;
+    if (rotate) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float2 cs = tcur[k];
+        const float re = v[2 * k] * cs.x + v[2 * k + 1] * cs.y;      // multiply by conj(cos + i sin)
+        const float im = v[2 * k + 1] * cs.x - v[2 * k] * cs.y;
+        v[2 * k] = re; v[2 * k + 1] = im;
+      }
+    }
+    if (g.is_bf16) {
+      stage_chunk_bf16(stage, lane, i, v);
+      if (i & 1) store_box(map, stage + (i >> 1) * kBoxBytes, lane, half * 128 + (i >> 1) * 64, row0, b, row0 < La);
+    } else {
+      stage_chunk_f32(stage, lane, i, v);
+      store_box(map, stage + i * kBoxBytes, lane, half * 128 + i * 32, row0, b, row0 < La);
     }
     if (i + 1 < 4) {
 #pragma unroll
@@ -210,11 +233,15 @@ __device__ __forceinline__ void grad_epilogue(const GradOut& g, uint32_t acc_add
       for (int k = 0; k < 16; ++k) tcur[k] = tnext[k];
     }
   }
+  if (lane == 0) tma_store_wait_read();
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
+                const __grid_constant__ CUtensorMap map_a,    // fixed operand [B, La, 256] bf16, box 64 x 128
+                const __grid_constant__ CUtensorMap map_o,    // FWD: out bf16 (box 64 x 32); DV: dV (bf16 64 x 32 | fp32 32 x 32)
+                const __grid_constant__ CUtensorMap map_o32,  // FWD: fp32 copy of out (box 32 x 32)
                 const TwoGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   SharedStorage& sh = *reinterpret_cast<SharedStorage*>(
@@ -244,10 +271,12 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) { mbar_init(&sh.s_full[i], 1); mbar_init(&sh.p_ready[i], kNumSoftmaxThreads); }
     mbar_init(&sh.acc_done, 1);
+    mbar_init(&sh.a_full, 1);
     mbar_init(&sh.a_ready, kNumSoftmaxThreads);
     fence_barrier_init();
   }
-  if (warp == kProducerWarp && lane == 0) { prefetch_tmap(&map_x); prefetch_tmap(&map_y); }
+  if (warp == kProducerWarp && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_x); prefetch_tmap(&map_y); }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&map_o); if (MODE == MODE_FWD) prefetch_tmap(&map_o32); }
   if (warp == kMmaWarp) { tmem_alloc(&sh.tmem_base, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
@@ -258,10 +287,19 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   if (warp == kProducerWarp) {
     // ===================== TMA producer (converged warp, one elected issuer) =====================
     const bool leader = elect_one();
+    if (leader) {   // fixed operand -> the last ring stage (slabs 0,1 in its X buffer, slabs 2,3 in its Y buffer)
+      mbar_arrive_expect_tx(&sh.a_full, 4 * kSlabBytes);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        tma_load_3d((c < 2 ? &sh.x_tiles[kStages - 1][0] : &sh.y_tiles[kStages - 1][0]) + (c & 1) * kSlabBytes, &map_a,
+                    &sh.a_full, c * 64, a_tile * kBlockM, b);
+    }
+    __syncwarp();
     for (int j = 0; j < nt; ++j) {
       const int s = j % kStages;
       const uint32_t ph = (j / kStages) & 1;
       const int row0 = (t_begin + j) * kBlockN;
+      if (j == kStages - 1) mbar_wait(&sh.a_ready, 0);   // first use of the stage that staged the fixed operand
       mbar_wait(&sh.x_empty[s], ph ^ 1);
       if (leader) {
         mbar_arrive_expect_tx(&sh.x_full[s], kTileBytes);
@@ -337,12 +375,17 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const long long a_row_idx = (long long)a_tile * kBlockM + row;
     const bool row_valid = a_row_idx < p.La;
     {
-      const __nv_bfloat16* a_row = p.a + ((long long)b * p.La + (row_valid ? a_row_idx : 0)) * kD;
-      load_fixed_operand_half(a_row, row_valid, lane_addr + kColA, half);
+      mbar_wait(&sh.a_full, 0);
+      stage_to_tmem_half(smem_u32(half ? &sh.y_tiles[kStages - 1][0] : &sh.x_tiles[kStages - 1][0]), row, lane_addr + kColA, half);
       tc_fence_before();
       mbar_arrive(&sh.a_ready);
       SAM2B200_STAMP(p.dbg, 3);
     }
+    // this warp's epilogue staging area inside the (then idle) tile ring, and its first row in the batch item
+    const int row0 = a_tile * kBlockM + quarter * 32;
+    const uint32_t stage = smem_u32(&sh.x_tiles[0][0]) + warp * ((MODE == MODE_FWD) ? 6 * kBoxBytes : 4 * kBoxBytes);
+    const bool rotate = false;   // dV is never rotated
+    float2 tcur[16];
 
     const float c = p.scale_log2;
     float m_ref = -INFINITY;   // running (lazily updated) row max of the raw scores -- identical in both halves
@@ -454,34 +497,29 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       pair_barrier(quarter);
       l += sh.lsum[half ^ 1][row];
       if (nsplit == 1) {
+        // out (bf16, two 64-column boxes) and optionally its fp32 copy (four 32-column boxes) leave through this
+        // warp's staging area: [bf16 box 0 | bf16 box 1 | fp32 box 0..3]
         const float inv_l = 1.0f / l;
-        __nv_bfloat16* orow = p.out + ((long long)b * p.La + a_row_idx) * kD;
-#pragma unroll 1
-        for (int cc = half * 4; cc < half * 4 + 4; ++cc) {
-          uint32_t o[32];
-          SAM2B200_TMEM_LD32(lane_addr + kColAcc + cc * 32, o);
+        uint32_t ocur[32], onext[32];
+        SAM2B200_TMEM_LD32(lane_addr + kColAcc + half * 128, ocur);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
           tmem_wait_ld();
-          if (row_valid) {
+          if (i + 1 < 4) SAM2B200_TMEM_LD32(lane_addr + kColAcc + half * 128 + (i + 1) * 32, onext);
+          float v[32];
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              uint4 u;
-              u.x = pack_bf16(__uint_as_float(o[8 * v + 0]) * inv_l, __uint_as_float(o[8 * v + 1]) * inv_l);
-              u.y = pack_bf16(__uint_as_float(o[8 * v + 2]) * inv_l, __uint_as_float(o[8 * v + 3]) * inv_l);
-              u.z = pack_bf16(__uint_as_float(o[8 * v + 4]) * inv_l, __uint_as_float(o[8 * v + 5]) * inv_l);
-              u.w = pack_bf16(__uint_as_float(o[8 * v + 6]) * inv_l, __uint_as_float(o[8 * v + 7]) * inv_l);
-              *reinterpret_cast<uint4*>(orow + cc * 32 + v * 8) = u;
-            }
-            if (p.out_f32 != nullptr) {
-              float* frow = p.out_f32 + ((long long)b * p.La + a_row_idx) * kD + cc * 32;
+          for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(ocur[k]) * inv_l;
+          stage_chunk_bf16(stage, lane, i, v);
+          if (p.has_out_f32) stage_chunk_f32(stage + 2 * kBoxBytes, lane, i, v);
+          if (i & 1) store_box(&map_o, stage + (i >> 1) * kBoxBytes, lane, half * 128 + (i >> 1) * 64, row0, b, row0 < p.La);
+          if (p.has_out_f32) store_box(&map_o32, stage + (2 + i) * kBoxBytes, lane, half * 128 + i * 32, row0, b, row0 < p.La);
+          if (i + 1 < 4) {
 #pragma unroll
-              for (int v = 0; v < 8; ++v)
-                *reinterpret_cast<float4*>(frow + v * 4) =
-                    make_float4(__uint_as_float(o[4 * v]) * inv_l, __uint_as_float(o[4 * v + 1]) * inv_l,
-                                __uint_as_float(o[4 * v + 2]) * inv_l, __uint_as_float(o[4 * v + 3]) * inv_l);
-            }
+            for (int k = 0; k < 32; ++k) ocur[k] = onext[k];
           }
         }
         if (row_valid && half == 0) p.lse2[(long long)b * p.La + a_row_idx] = fmaf(m_ref, c, log2f(l));
+        if (lane == 0) tma_store_wait_read();
       } else {
         const long long prow = ((long long)split * gridDim.y + b) * p.La + a_row_idx;
         float* orow = p.part_acc + prow * kD;
@@ -500,7 +538,7 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         if (row_valid && half == 0) { p.part_ml[prow * 2] = m_ref * c; p.part_ml[prow * 2 + 1] = l; }
       }
     } else {
-      grad_epilogue(p.gout, lane_addr + kColAcc, half, row_valid, (long long)b * p.La + a_row_idx, (int)a_row_idx, 1.0f);
+      grad_epilogue(p.gout, &map_o, stage, lane_addr + kColAcc, half, lane, row0, p.La, b, 1.0f, rotate, tcur);
     }
   }
 
@@ -525,7 +563,6 @@ constexpr uint32_t k3ColS = 384;     // 64 : S
 constexpr uint32_t k3ColDP = 448;    // 64 : dP, then dS (bf16 pairs; same own-column placement as P above)
 
 struct ThreeGemmParams {
-  const __nv_bfloat16* a1;     // [B, La, 256] (Q in DQ, K in DK)
   int La;
   int Lx;                      // streamed length (M in DQ, N in DK)
   float scale_log2;            // scale * log2(e)
@@ -545,7 +582,8 @@ struct SharedStorage3 {
   uint64_t y_full[kStages3];
   uint64_t y_empty[kStages3];
   uint64_t a2_full;
-  uint64_t a1_ready;
+  uint64_t a1_full;            // TMA: A1 landed in ring stage kStages3-1
+  uint64_t a1_ready;           // compute warps: A1 moved to tensor memory
   uint64_t s_full;
   uint64_t s_free;
   uint64_t dp_full;
@@ -559,7 +597,10 @@ struct SharedStorage3 {
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_x,
-                  const __grid_constant__ CUtensorMap map_y, const ThreeGemmParams p) {
+                  const __grid_constant__ CUtensorMap map_y,
+                  const __grid_constant__ CUtensorMap map_a1,   // A1 [B, La, 256] bf16, box 64 x 128
+                  const __grid_constant__ CUtensorMap map_g,    // dQ / dK (bf16 box 64 x 32 | fp32 box 32 x 32)
+                  const ThreeGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   SharedStorage3& sh = *reinterpret_cast<SharedStorage3*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -581,6 +622,7 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
       mbar_init(&sh.y_full[s], 1); mbar_init(&sh.y_empty[s], 1);
     }
     mbar_init(&sh.a2_full, 1);
+    mbar_init(&sh.a1_full, 1);
     mbar_init(&sh.a1_ready, kNumSoftmaxThreads);
     mbar_init(&sh.s_full, 1);
     mbar_init(&sh.s_free, kNumSoftmaxThreads);
@@ -589,7 +631,8 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
     mbar_init(&sh.acc_done, 1);
     fence_barrier_init();
   }
-  if (warp == kProducerWarp && lane == 0) { prefetch_tmap(&map_a2); prefetch_tmap(&map_x); prefetch_tmap(&map_y); }
+  if (warp == kProducerWarp && lane == 0) { prefetch_tmap(&map_a1); prefetch_tmap(&map_a2); prefetch_tmap(&map_x); prefetch_tmap(&map_y); }
+  if (warp == 0 && lane == 0) prefetch_tmap(&map_g);
   if (warp == kMmaWarp) { tmem_alloc(&sh.tmem_base, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
@@ -600,6 +643,11 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
   if (warp == kProducerWarp) {
     const bool leader = elect_one();
     if (leader) {
+      mbar_arrive_expect_tx(&sh.a1_full, 4 * kSlabBytes);   // A1 -> the last ring stage (needed first: it goes to TMEM)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        tma_load_3d((c < 2 ? &sh.x_tiles[kStages3 - 1][0] : &sh.y_tiles[kStages3 - 1][0]) + (c & 1) * kSlabBytes, &map_a1,
+                    &sh.a1_full, c * 64, a_tile * kBlockM, b);
       mbar_arrive_expect_tx(&sh.a2_full, kA2Bytes);
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -610,6 +658,7 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
       const int s = j % kStages3;
       const uint32_t ph = (j / kStages3) & 1;
       const int row0 = j * kBlockN;
+      if (j == kStages3 - 1) mbar_wait(&sh.a1_ready, 0);   // first use of the stage that staged A1
       mbar_wait(&sh.x_empty[s], ph ^ 1);
       if (leader) {
         mbar_arrive_expect_tx(&sh.x_full[s], kTileBytes);
@@ -698,12 +747,15 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
     const long long a_row_idx = (long long)a_tile * kBlockM + row;
     const bool row_valid = a_row_idx < p.La;
     {
-      const __nv_bfloat16* a_row = p.a1 + ((long long)b * p.La + (row_valid ? a_row_idx : 0)) * kD;
-      load_fixed_operand_half(a_row, row_valid, lane_addr + k3ColA1, half);
+      mbar_wait(&sh.a1_full, 0);
+      stage_to_tmem_half(smem_u32(half ? &sh.y_tiles[kStages3 - 1][0] : &sh.x_tiles[kStages3 - 1][0]), row, lane_addr + k3ColA1, half);
       tc_fence_before();
       mbar_arrive(&sh.a1_ready);
       SAM2B200_STAMP(p.dbg, 3);
     }
+    const int row0 = a_tile * kBlockM + quarter * 32;
+    const uint32_t stage = smem_u32(&sh.a2[0]) + warp * (4 * kBoxBytes);   // epilogue staging in the (then idle) operand buffers
+    const bool rotate = p.gout.rope_table != nullptr && (row0 + lane) < p.gout.rope_rows;
     const float c = p.scale_log2;
     float row_lse = 0.f, row_delta = 0.f;
     if (MODE == MODE_DQ && row_valid) {
@@ -768,10 +820,12 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
       tc_fence_before();
       mbar_arrive(&sh.ds_ready);
     }
+    float2 tcur[16];
+    load_table_chunk(p.gout, rotate, row0 + lane, half * 128, tcur);   // in flight while the last MMAs drain
     mbar_wait(&sh.acc_done, 0);
     tc_fence_after();
     SAM2B200_STAMP(p.dbg, 5);
-    grad_epilogue(p.gout, lane_addr + k3ColAcc, half, row_valid, (long long)b * p.La + a_row_idx, (int)a_row_idx, p.scale);
+    grad_epilogue(p.gout, &map_g, stage, lane_addr + k3ColAcc, half, lane, row0, p.La, b, p.scale, rotate, tcur);
   }
 
   tc_fence_before();

@@ -51,4 +51,25 @@ inline int make_rows256_map(CUtensorMap* map, const void* base, int B, int L, in
   return SAM2B200_OK;
 }
 
+// Output tensor y[B][L][ld] (bf16 or fp32; first 256 columns used) as a 3-D tensor with a box of
+// [box_rows][128 bytes] (64 bf16 or 32 fp32 columns), 128-byte swizzle: the staging layout of the TMA-store
+// epilogues (one box per warp: its 32 accumulator rows).  Rows beyond L are clipped by the TMA unit.
+inline int make_out_map(CUtensorMap* map, void* base, int is_bf16, int B, int L, long long ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return fail(SAM2B200_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not found");
+  const cuuint64_t es = is_bf16 ? 2 : 4;
+  cuuint64_t dims[3] = {256, (cuuint64_t)L, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * es, (cuuint64_t)L * (cuuint64_t)ld * es};
+  cuuint32_t box[3] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(last_error_buffer(), 512, "cuTensorMapEncodeTiled (output) failed (%d) B=%d L=%d ld=%lld", (int)r, B, L, ld);
+    return SAM2B200_ERR_DRIVER;
+  }
+  return SAM2B200_OK;
+}
+
 }  // namespace sam2b200

@@ -6,7 +6,7 @@ live in one flat buffer that autograd accumulates into in place, so the exchange
 NCCL all-reduce over NVLink with no bucket copies."""
 from __future__ import annotations
 
-from typing import Iterable, Optional
+from typing import Iterable, List, Optional
 
 import torch
 import torch.distributed as dist
@@ -18,18 +18,47 @@ def shard_clips(num_clips: int, rank: int, world: int):
 
 
 class GradBucket:
-    """One contiguous fp32 buffer holding every parameter gradient as a view."""
+    """One contiguous fp32 buffer holding every parameter gradient as a view.
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
-        self.params = [p for p in params if p.requires_grad]
-        total = sum(p.numel() for p in self.params)
+    `order` (optional) lists the parameters in the order they should be laid out, so that gradients one kernel
+    produces together are adjacent (MemoryAttention puts each layer's q/k/v self-attention weights -- and biases --
+    next to each other: one [768, 256] weight-gradient GEMM writes all three).  Every offset is a multiple of 64
+    floats (256 bytes), which keeps every view aligned for vectorised kernels and cuBLAS."""
+
+    ALIGN = 64
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], order: Optional[List[torch.nn.Parameter]] = None):
+        self.params = [p for p in (order if order is not None else params) if p.requires_grad]
+        if order is not None:
+            listed = {id(p) for p in self.params}
+            self.params += [p for p in params if p.requires_grad and id(p) not in listed]
         dev = self.params[0].device
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.offset = {}
         off = 0
         for p in self.params:
-            n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
-            off += n
+            self.offset[id(p)] = off
+            off += -(-p.numel() // self.ALIGN) * self.ALIGN
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        for p in self.params:
+            o = self.offset[id(p)]
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
+
+    def span(self, plist, shape):
+        """One view over the gradients of `plist` if they are laid out back to back (no padding), else None."""
+        o = self.offset.get(id(plist[0]))
+        if o is None:
+            return None
+        exp = o
+        for p in plist:
+            if self.offset.get(id(p)) != exp or p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + 4 * exp:
+                return None
+            exp += p.numel()
+        return self.flat[o:exp].view(shape)
+
+    def owns(self, p) -> bool:
+        o = self.offset.get(id(p))
+        return (o is not None and p.grad is not None and p.grad.dtype == torch.float32
+                and p.grad.data_ptr() == self.flat.data_ptr() + 4 * o)
 
     def zero(self):
         self.flat.zero_()
@@ -63,6 +92,9 @@ def allreduce_gradients(model: torch.nn.Module, world: int):
 
 
 def attach_grad_bucket(model: torch.nn.Module) -> GradBucket:
-    b = GradBucket(model.parameters())
+    """Give `model` a flat gradient buffer.  A model that offers `grad_bucket_order()` (MemoryAttention) chooses the
+    layout and, from then on, accumulates its gradients into the buffer directly inside its backward kernels."""
+    order = model.grad_bucket_order() if hasattr(model, "grad_bucket_order") else None
+    b = GradBucket(list(model.parameters()), order=order)
     model._sam2b200_grad_bucket = b
     return b

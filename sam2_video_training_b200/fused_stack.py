@@ -15,6 +15,7 @@ PyTorch is used for device memory, streams and the cuBLAS calls only.
 from __future__ import annotations
 
 import math
+import os
 from typing import List
 
 import torch
@@ -107,25 +108,77 @@ def _mm32(a, b):
     return torch.mm(a, b, out_dtype=F32)
 
 
-_BF16_CACHE = {}
-CAPTURE_SAFE_CASTS = False   # set while a CUDA graph is being built: casts must be part of the graph
+NO_DIRECT_GRADS = bool(os.environ.get("SAM2B200_NO_DIRECT_GRADS"))   # A/B switch: return gradients to autograd instead
+
+
+def direct_grads_possible(bucket, params) -> bool:
+    """True iff every parameter's .grad is (still) its fp32 view of `bucket`: the backward may then accumulate into
+    the bucket itself and hide the parameters from autograd (they are passed detached)."""
+    return (bucket is not None and not NO_DIRECT_GRADS and torch.is_grad_enabled()
+            and all(p.requires_grad and bucket.owns(p) for p in params))
+
+
+class WeightMirror:
+    """Persistent bf16 copies of the fp32 master parameters in ONE flat buffer (static addresses, so CUDA graphs can
+    read them), refreshed by a single multi-tensor copy when a parameter was updated in place (tensor._version
+    changes on optimizer.step / copy_ / load_state_dict): one cast per optimizer step instead of 106 small cast
+    kernels in every forward and every backward (18 calls per clip at T = 10).  `refresh()` is called on the host
+    before the kernels of a forward are enqueued -- never inside a graph capture."""
+
+    def __init__(self, params):
+        self.params = list(params)
+        dev = self.params[0].device
+        # layout: per layer the q/k/v self-attention weights back to back (the backward multiplies by the stacked
+        # [768, 256] matrix), everything else in parameter order; every numel is a multiple of 64 -> aligned views
+        nl = (len(self.params) - 2) // _NPL if (len(self.params) - 2) % _NPL == 0 else 0
+        first = []
+        for l in range(nl):
+            first += [l * _NPL + _LAYER_KEYS.index(k) for k in ("sa.q.w", "sa.k.w", "sa.v.w")]
+        order = first + [i for i in range(len(self.params)) if i not in set(first)]
+        sizes = [-(-self.params[i].numel() // 64) * 64 for i in order]
+        self.flat = torch.empty(sum(sizes), dtype=BF16, device=dev)
+        self.views, off = [None] * len(self.params), 0
+        self.qkv = []
+        for i, n in zip(order, sizes):
+            self.views[i] = self.flat[off:off + self.params[i].numel()].view_as(self.params[i])
+            off += n
+        for l in range(nl):
+            v0 = self.views[first[3 * l]]
+            o0 = v0.storage_offset()
+            self.qkv.append(self.flat[o0:o0 + 3 * v0.numel()].view(3 * v0.shape[0], v0.shape[1]))
+        self.versions = None
+        self.device = dev
+
+    def matches(self, params) -> bool:
+        return (len(params) == len(self.params) and all(a is b for a, b in zip(params, self.params))
+                and params[0].device == self.device)
+
+    def refresh(self):
+        v = [p._version for p in self.params]
+        if v != self.versions:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("WeightMirror.refresh() inside a CUDA graph capture: refresh before capturing")
+            with torch.no_grad():
+                torch._foreach_copy_(self.views, [p.detach() for p in self.params])
+            self.versions = v
+        return self.views
+
+
+_MIRRORS = {}
+
+
+def weight_mirror(params) -> WeightMirror:
+    key = id(params[0])
+    m = _MIRRORS.get(key)
+    if m is None or not m.matches(params):
+        m = WeightMirror(params)
+        _MIRRORS[key] = m
+    return m
 
 
 def bf16_params(params):
-    """bf16 copies of the fp32 master parameters, re-cast only when a parameter was updated in place
-    (tensor._version changes on optimizer.step / copy_): one cast per optimizer step instead of one per
-    forward and per backward call (18x per clip at T = 10)."""
-    if CAPTURE_SAFE_CASTS or torch.cuda.is_current_stream_capturing():
-        return [p.detach().to(BF16) for p in params]
-    out = []
-    for p in params:
-        key = id(p)
-        ent = _BF16_CACHE.get(key)
-        if ent is None or ent[0] != p._version or ent[1] is not p or ent[2].device != p.device:
-            ent = (p._version, p, p.detach().to(BF16))
-            _BF16_CACHE[key] = ent
-        out.append(ent[2])
-    return out
+    """bf16 views of the parameters (see WeightMirror); keyed by the identity of the first parameter."""
+    return weight_mirror(params).refresh()
 
 
 class MemoryAttentionStackFn(torch.autograd.Function):
@@ -133,6 +186,12 @@ class MemoryAttentionStackFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, meta, curr, curr_pos, memory, memory_pos, *params):
+        # direct-gradient mode: params are detached aliases and the LAST tensor is a 1-element leaf with
+        # requires_grad=True (the "grad anchor") whose only job is to make the output require grad, so that the
+        # backward -- which accumulates the parameter gradients itself -- always runs
+        ctx.has_anchor = bool(meta.get("direct"))
+        if ctx.has_anchor:
+            params = params[:-1]
         nl, p_excl, table, pos_at_input = meta["num_layers"], meta["num_k_exclude_rope"], meta["table"], meta["pos_enc_at_input"]
         n, b, d = curr.shape
         m = memory.shape[0]
@@ -146,7 +205,8 @@ class MemoryAttentionStackFn(torch.autograd.Function):
         x = x.transpose(0, 1).contiguous().view(r, d)
         memk = (memory + memory_pos).transpose(0, 1).to(BF16).contiguous().view(rm, -1)
         memv = memory.transpose(0, 1).to(BF16).contiguous().view(rm, -1)
-        wb = bf16_params(params)
+        masters = meta.get("master_params") or list(params)   # the nn.Parameters (params may be detached aliases)
+        wb = bf16_params(masters)
         saved: List[torch.Tensor] = []
         res = None
         for l in range(nl):
@@ -184,7 +244,8 @@ class MemoryAttentionStackFn(torch.autograd.Function):
         ctx.save_for_backward(*saved, *params)
         ctx.n_saved = len(saved)
         ctx.meta = dict(nl=nl, n=n, b=b, m=m, scale=scale, n_rope_k=n_rope_k, pos_at_input=pos_at_input,
-                        has_pos=curr_pos is not None)
+                        has_pos=curr_pos is not None, bucket=meta.get("bucket"), masters=masters,
+                        direct=bool(meta.get("direct")))
         return out
 
     @staticmethod
@@ -199,17 +260,37 @@ class MemoryAttentionStackFn(torch.autograd.Function):
         dev = x_fin.device
         need_curr, need_pos, need_mem, need_mpos = ctx.needs_input_grad[1:5]
         need_memgrad = need_mem or need_mpos
-        wb = bf16_params(params)
-        # gradient buffers for vector parameters (accumulated by the kernels); matrices come from mm
+        masters = mt["masters"]
+        wb = bf16_params(masters)
+        wqkv_all = weight_mirror(masters).qkv
+        # Parameter gradients.  With a GradBucket attached (ddp.attach_grad_bucket) whose views are still the
+        # parameters' .grad, every kernel / GEMM ACCUMULATES straight into the bucket (beta = 1) and autograd gets
+        # None for the parameters: no fp32 temporaries, no 106 AccumulateGrad add_ kernels per backward.  Otherwise
+        # vector gradients accumulate into one zeroed scratch and matrix gradients are returned from the GEMMs.
+        bucket = mt.get("bucket")
+        direct = mt["direct"]
         grads = [None] * len(params)
-        vec = [i for i, p in enumerate(params) if p.dim() == 1]
-        flat = torch.zeros(sum(params[i].numel() for i in vec), dtype=F32, device=dev)   # one memset for all vectors
-        off = 0
-        for i in vec:
-            grads[i] = flat[off:off + params[i].numel()]
-            off += params[i].numel()
+        if direct:
+            if not all(bucket.owns(p) for p in masters):
+                raise RuntimeError("a parameter's .grad was detached from the GradBucket between forward and backward "
+                                   "(e.g. zero_grad(set_to_none=True)); use bucket.zero() or re-attach the bucket")
+            gv = [p.grad for p in masters]
+        else:
+            gv = [None] * len(params)
+            vec = [i for i, p in enumerate(params) if p.dim() == 1]
+            flat = torch.zeros(sum(params[i].numel() for i in vec), dtype=F32, device=dev)   # one memset for all vectors
+            off = 0
+            for i in vec:
+                gv[i] = grads[i] = flat[off:off + params[i].numel()]
+                off += params[i].numel()
+
+        def acc_w(i, a_t, bmat):     # grad[i] (+)= a_t @ bmat   (bf16 x bf16 -> fp32)
+            if direct:
+                torch.addmm(gv[i], a_t, bmat, out_dtype=F32, out=gv[i])
+            else:
+                grads[i] = _mm32(a_t, bmat)
         grad_out = grad_out.contiguous().float()
-        g = ln_bwd(grad_out, x_fin, mean_f, rstd_f, params[nl * _NPL], None, grads[nl * _NPL], grads[nl * _NPL + 1],
+        g = ln_bwd(grad_out, x_fin, mean_f, rstd_f, params[nl * _NPL], None, gv[nl * _NPL], gv[nl * _NPL + 1],
                    seq_first=(b, n))
         dmemk = torch.zeros((rm, memk.shape[1]), dtype=F32, device=dev) if need_memgrad else None
         dmemv = torch.zeros((rm, memv.shape[1]), dtype=F32, device=dev) if need_mem else None
@@ -222,49 +303,63 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             W = {k: wb[ix[k]] for k in _LAYER_KEYS}
             P = {k: params[ix[k]] for k in _LAYER_KEYS}
             # ---- MLP backward
-            dm = cast_colsum(g, grads[ix["l2.b"]])
-            grads[ix["l2.w"]] = _mm32(dm.t(), h)
+            dm = cast_colsum(g, gv[ix["l2.b"]])
+            acc_w(ix["l2.w"], dm.t(), h)
             dh = torch.mm(dm, W["l2.w"])
-            relu_bwd_colsum_(dh, h, grads[ix["l1.b"]])
-            grads[ix["l1.w"]] = _mm32(dh.t(), y3)
+            relu_bwd_colsum_(dh, h, gv[ix["l1.b"]])
+            acc_w(ix["l1.w"], dh.t(), y3)
             dy3 = torch.mm(dh, W["l1.w"])
-            g = ln_bwd(dy3, x2, mean3, rstd3, P["n3.w"], g, grads[ix["n3.w"]], grads[ix["n3.b"]])
+            g = ln_bwd(dy3, x2, mean3, rstd3, P["n3.w"], g, gv[ix["n3.w"]], gv[ix["n3.b"]])
             # ---- cross attention backward
-            dca = cast_colsum(g, grads[ix["ca.o.b"]])
-            grads[ix["ca.o.w"]] = _mm32(dca.t(), o2.view(r, d))
+            dca = cast_colsum(g, gv[ix["ca.o.b"]])
+            acc_w(ix["ca.o.w"], dca.t(), o2.view(r, d))
             do2 = torch.mm(dca, W["ca.o.w"])
             dq2, dk2, dv2 = attn_bwd(q2_rot, k2_rot, v2.view(b, m, d), None, o2_32, do2.view(b, n, d), lse2, scale,
                                      table=table, n_rope_k=n_rope_k, grad_dtype=BF16)   # conj. RoPE fused in epilogue
             dq2, dk2, dv2 = dq2.view(r, d), dk2.view(rm, d), dv2.view(rm, d)
-            colsum_bf16(dq2, grads[ix["ca.q.b"]])
-            colsum_bf16(dk2, grads[ix["ca.k.b"]])
-            colsum_bf16(dv2, grads[ix["ca.v.b"]])
-            grads[ix["ca.q.w"]] = _mm32(dq2.t(), y2)
-            grads[ix["ca.k.w"]] = _mm32(dk2.t(), memk)
-            grads[ix["ca.v.w"]] = _mm32(dv2.t(), memv)
+            colsum_bf16(dq2, gv[ix["ca.q.b"]])
+            colsum_bf16(dk2, gv[ix["ca.k.b"]])
+            colsum_bf16(dv2, gv[ix["ca.v.b"]])
+            acc_w(ix["ca.q.w"], dq2.t(), y2)
+            acc_w(ix["ca.k.w"], dk2.t(), memk)
+            acc_w(ix["ca.v.w"], dv2.t(), memv)
             if need_memgrad:
-                dmemk = torch.addmm(dmemk, dk2, W["ca.k.w"], out_dtype=F32)
+                torch.addmm(dmemk, dk2, W["ca.k.w"], out_dtype=F32, out=dmemk)
             if need_mem:
-                dmemv = torch.addmm(dmemv, dv2, W["ca.v.w"], out_dtype=F32)
+                torch.addmm(dmemv, dv2, W["ca.v.w"], out_dtype=F32, out=dmemv)
             dy2 = torch.mm(dq2, W["ca.q.w"])
-            g = ln_bwd(dy2, x1, mean2, rstd2, P["n2.w"], g, grads[ix["n2.w"]], grads[ix["n2.b"]])
+            g = ln_bwd(dy2, x1, mean2, rstd2, P["n2.w"], g, gv[ix["n2.w"]], gv[ix["n2.b"]])
             # ---- self attention backward
-            dsa = cast_colsum(g, grads[ix["sa.o.b"]])
-            grads[ix["sa.o.w"]] = _mm32(dsa.t(), o.view(r, d))
+            dsa = cast_colsum(g, gv[ix["sa.o.b"]])
+            acc_w(ix["sa.o.w"], dsa.t(), o.view(r, d))
             do = torch.mm(dsa, W["sa.o.w"])
             dqkv = torch.empty((b, n, 3 * d), dtype=BF16, device=dev)   # [dq | dk | dv], written in place by the kernels
             attn_bwd(q_rot, k_rot, v.view(b, n, d), None, o32, do.view(b, n, d), lse, scale, table=table, n_rope_k=n,
                      grad_dtype=BF16, dq=dqkv[:, :, :d], dk=dqkv[:, :, d:2 * d], dv=dqkv[:, :, 2 * d:])
             dqkv = dqkv.view(r, 3 * d)
-            # q/k/v biases are consecutive vectors? no (weights interleave) -> sum into a scratch then alias
-            bsum = torch.zeros(3 * d, dtype=F32, device=dev)
-            colsum_bf16(dqkv, bsum)
-            grads[ix["sa.q.b"]], grads[ix["sa.k.b"]], grads[ix["sa.v.b"]] = bsum[:d], bsum[d:2 * d], bsum[2 * d:]
-            dw = _mm32(dqkv.t(), y1)                     # [768, 256] = d(Wq | Wk | Wv) in one GEMM
-            grads[ix["sa.q.w"]], grads[ix["sa.k.w"]], grads[ix["sa.v.w"]] = dw[:d], dw[d:2 * d], dw[2 * d:]
-            wqkv = torch.cat([W["sa.q.w"], W["sa.k.w"], W["sa.v.w"]], dim=0)
-            dy1 = torch.mm(dqkv, wqkv)                   # contraction over 768 with fp32 accumulation
-            g = ln_bwd(dy1, x0, mean1, rstd1, P["n1.w"], g, grads[ix["n1.w"]], grads[ix["n1.b"]])
+            qkv_w = [masters[ix[k]] for k in ("sa.q.w", "sa.k.w", "sa.v.w")]
+            qkv_b = [masters[ix[k]] for k in ("sa.q.b", "sa.k.b", "sa.v.b")]
+            gw = bucket.span(qkv_w, (3 * d, d)) if direct else None
+            gb = bucket.span(qkv_b, (3 * d,)) if direct else None
+            if gw is not None and gb is not None:
+                # the bucket lays the three projections out back to back: one colsum, one [768, 256] GEMM
+                colsum_bf16(dqkv, gb)
+                torch.addmm(gw, dqkv.t(), y1, out_dtype=F32, out=gw)
+            elif direct:
+                for j, (kw, kb) in enumerate((("sa.q.w", "sa.q.b"), ("sa.k.w", "sa.k.b"), ("sa.v.w", "sa.v.b"))):
+                    part = dqkv[:, j * d:(j + 1) * d]
+                    bsum = torch.zeros(d, dtype=F32, device=dev)
+                    colsum_bf16(part.contiguous(), bsum)
+                    gv[ix[kb]].add_(bsum)
+                    acc_w(ix[kw], part.t(), y1)
+            else:
+                bsum = torch.zeros(3 * d, dtype=F32, device=dev)
+                colsum_bf16(dqkv, bsum)
+                grads[ix["sa.q.b"]], grads[ix["sa.k.b"]], grads[ix["sa.v.b"]] = bsum[:d], bsum[d:2 * d], bsum[2 * d:]
+                dw = _mm32(dqkv.t(), y1)                     # [768, 256] = d(Wq | Wk | Wv) in one GEMM
+                grads[ix["sa.q.w"]], grads[ix["sa.k.w"]], grads[ix["sa.v.w"]] = dw[:d], dw[d:2 * d], dw[2 * d:]
+            dy1 = torch.mm(dqkv, wqkv_all[l])            # stacked [768, 256] weights: contraction over 768, fp32 accumulation
+            g = ln_bwd(dy1, x0, mean1, rstd1, P["n1.w"], g, gv[ix["n1.w"]], gv[ix["n1.b"]])
         # ---- unpack input gradients
         d_curr = d_pos = d_mem = d_mpos = None
         if need_curr or need_pos:
@@ -277,4 +372,10 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             d_mpos = dmemk.view(b, m, -1).transpose(0, 1).contiguous()
         if need_mem:
             d_mem = (dmemk + dmemv).view(b, m, -1).transpose(0, 1).contiguous()
-        return (None, d_curr, d_pos, d_mem, d_mpos, *grads)
+        if not ctx.has_anchor:
+            return (None, d_curr, d_pos, d_mem, d_mpos, *grads)
+        # The anchor gets a (zero) gradient only when it is the ONLY input that requires grad: a backward whose
+        # outputs are all None makes the autograd engine synchronise the capturing stream with the (uncaptured)
+        # stream of the anchor's AccumulateGrad node and invalidates a CUDA-graph capture (scripts/probe_capture.py).
+        lonely = not (need_curr or need_pos or need_mem or need_mpos)
+        return (None, d_curr, d_pos, d_mem, d_mpos, *grads, torch.zeros(1, dtype=F32, device=dev) if lonely else None)

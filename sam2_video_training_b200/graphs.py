@@ -44,7 +44,9 @@ class GraphedMemoryAttention(nn.Module):
         return self.inner.layers
 
     def _signature(self, curr, memory, curr_pos, memory_pos, p) -> Tuple:
-        return (tuple(curr.shape), tuple(memory.shape), curr.dtype, memory.dtype, curr.requires_grad,
+        direct = fused_stack.direct_grads_possible(getattr(self.inner, "_sam2b200_grad_bucket", None),
+                                                   [q for _, q in self.inner.named_parameters()])
+        return (direct, tuple(curr.shape), tuple(memory.shape), curr.dtype, memory.dtype, curr.requires_grad,
                 curr_pos.requires_grad, memory.requires_grad, memory_pos.requires_grad, int(p), self.inner.training,
                 torch.is_grad_enabled())
 
@@ -64,17 +66,41 @@ class GraphedMemoryAttention(nn.Module):
                 return self.inner(curr, memory, curr_pos, memory_pos, num_obj_ptr_tokens)
             g = self._capture(curr, memory, curr_pos, memory_pos, num_obj_ptr_tokens)
             self._graphs[key] = g
+        # the graphs read the persistent bf16 weight mirror: bring it up to date (no-op unless a parameter changed)
+        fused_stack.bf16_params([p for _, p in self.inner.named_parameters()])
         return g(curr, memory, curr_pos, memory_pos)
 
     def _capture(self, curr, memory, curr_pos, memory_pos, p):
-        mod = _FixedPointerCount(self.inner, p)
+        params = [q for _, q in self.inner.named_parameters()]
+        bucket = getattr(self.inner, "_sam2b200_grad_bucket", None)
+        if fused_stack.direct_grads_possible(bucket, params):
+            # gradients go straight into the GradBucket: the parameters are not part of the graphed input surface
+            # (a plain function, not an nn.Module), so autograd never touches them at capture or replay time
+            inner = self.inner
+            direct = True
+
+            def mod(curr, memory, curr_pos, memory_pos, anchor):
+                return inner._forward_fused(curr, memory, curr_pos, memory_pos, int(p), anchor=anchor)
+        else:
+            direct = False
+            mod = _FixedPointerCount(self.inner, p)
         sample = tuple(torch.randn_like(t).requires_grad_(t.requires_grad) for t in (curr, memory, curr_pos, memory_pos))
+        if direct:
+            sample = sample + (torch.zeros(1, device=curr.device, requires_grad=True),)
         saved_profile = _ops.PROFILE
         _ops.PROFILE = None                      # events cannot be timed inside a capture
-        fused_stack.CAPTURE_SAFE_CASTS = True    # weight casts are recorded into the graph, never cached
+        fused_stack.bf16_params([p for _, p in self.inner.named_parameters()])   # mirror refreshed OUTSIDE the capture
+        # warm-up and capture run the backward on random inputs; with a GradBucket attached that backward accumulates
+        # straight into the bucket, so its content is put back afterwards
+        kept = bucket.flat.clone() if bucket is not None else None
         try:
             graphed = torch.cuda.make_graphed_callables(mod, sample, num_warmup_iters=2, allow_unused_input=True)
         finally:
-            fused_stack.CAPTURE_SAFE_CASTS = False
             _ops.PROFILE = saved_profile
+            if kept is not None:
+                torch.cuda.synchronize()
+                bucket.flat.copy_(kept)
+        if direct:
+            anchor = self.inner._grad_anchor(curr.device)
+            return lambda c, m, cp, mp: graphed(c, m, cp, mp, anchor)
         return graphed

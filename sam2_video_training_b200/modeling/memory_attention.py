@@ -119,7 +119,24 @@ class MemoryAttention(nn.Module):
                 return False  # dropout active: use the composed path (residual dropouts via nn.Dropout)
         return True
 
-    def _forward_fused(self, curr, memory, curr_pos, memory_pos, num_obj_ptr_tokens):
+    def grad_bucket_order(self):
+        """Layout ddp.GradBucket should use: per layer the q/k/v self-attention weights back to back, then their
+        biases back to back (one [768, 256] weight-gradient GEMM / one bias reduction writes all three), then the rest."""
+        order = []
+        for layer in self.layers:
+            sa = getattr(layer, "self_attn", None)
+            if sa is not None and all(hasattr(sa, k) for k in ("q_proj", "k_proj", "v_proj")):
+                order += [sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight, sa.q_proj.bias, sa.k_proj.bias, sa.v_proj.bias]
+        return order
+
+    def _grad_anchor(self, device):
+        a = getattr(self, "_sam2b200_anchor", None)
+        if a is None or a.device != device:
+            a = torch.zeros(1, device=device, requires_grad=True)
+            self._sam2b200_anchor = a
+        return a
+
+    def _forward_fused(self, curr, memory, curr_pos, memory_pos, num_obj_ptr_tokens, anchor=None):
         from ..fused_stack import MemoryAttentionStackFn
         n = curr.shape[0]
         m = memory.shape[0]
@@ -127,9 +144,18 @@ class MemoryAttention(nn.Module):
         if (m - num_obj_ptr_tokens) % n != 0:
             raise ValueError("rotated key count must be a multiple of the query count (position_encoding.py:230)")
         table = ca0._table(n, curr.device)
-        meta = dict(num_layers=self.num_layers, num_k_exclude_rope=int(num_obj_ptr_tokens), table=table,
-                    pos_enc_at_input=bool(self.pos_enc_at_input), nsplit=int(self.attn_nsplit))
+        from ..fused_stack import direct_grads_possible
         params = [p for _, p in self.named_parameters()]
+        bucket = getattr(self, "_sam2b200_grad_bucket", None)
+        # With a GradBucket attached (ddp.attach_grad_bucket) the backward accumulates parameter gradients into the
+        # bucket itself; autograd then only sees detached aliases of the parameters (no 106 AccumulateGrad nodes).
+        direct = direct_grads_possible(bucket, params)
+        meta = dict(num_layers=self.num_layers, num_k_exclude_rope=int(num_obj_ptr_tokens), table=table,
+                    pos_enc_at_input=bool(self.pos_enc_at_input), nsplit=int(self.attn_nsplit),
+                    bucket=bucket, direct=direct, master_params=params)
+        if direct:
+            anchor = anchor if anchor is not None else self._grad_anchor(curr.device)
+            return MemoryAttentionStackFn.apply(meta, curr, curr_pos, memory, memory_pos, *[p.detach() for p in params], anchor)
         return MemoryAttentionStackFn.apply(meta, curr, curr_pos, memory, memory_pos, *params)
 
     def forward(self, curr: torch.Tensor, memory: torch.Tensor, curr_pos: Optional[Tensor] = None,

@@ -197,6 +197,56 @@ def test_fused_and_composed_paths_agree(dev):
     assert rel_l2(outs[0], outs[1]) < 5e-3
 
 
+def test_grad_bucket_direct_accumulation_and_graph_replay(dev):
+    """With a GradBucket attached the fused backward accumulates into the bucket itself (autograd sees None for the
+    parameters); two backward passes must leave exactly the sum of the gradients the plain path returns, the bf16
+    weight mirror must follow an in-place parameter update, and CUDA-graph replay must give the same numbers."""
+    from sam2_video_training_b200 import ddp
+    from sam2_video_training_b200.graphs import GraphedMemoryAttention
+    from sam2_video_training_b200.modeling.memory_attention import build_memory_attention
+    torch.manual_seed(3)
+    ref_model = build_memory_attention(dropout=0.0).to(dev).train()
+    model = build_memory_attention(dropout=0.0).to(dev).train()
+    model.load_state_dict(ref_model.state_dict())
+    bucket = ddp.attach_grad_bucket(model)
+    graphed = GraphedMemoryAttention(model)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n, b, m, p = 64, 3, 2 * 64 + 8, 8
+
+    def inputs():
+        return (torch.randn(n, b, 256, device=dev, generator=g), torch.randn(m, b, 64, device=dev, generator=g),
+                torch.randn(n, b, 256, device=dev, generator=g) * 0.7,
+                (torch.randn(m, b, 64, device=dev, generator=g) * 0.7).requires_grad_(pos_grad),
+                torch.randn(n, b, 256, device=dev, generator=g))
+
+    for step in range(3):            # steps 1, 2 run after an in-place parameter update (mirror refresh)
+        pos_grad = step < 2          # step 2: NO input requires grad -- the parameter gradients must still arrive
+        batches = [inputs() for _ in range(2)]
+        ref_model.zero_grad(set_to_none=True)
+        bucket.zero()
+        ref_pos_grads, pos_grads, outs_ref, outs = [], [], [], []
+        for runner, sink_out, sink_pos, mdl in ((ref_model, outs_ref, ref_pos_grads, ref_model), (graphed, outs, pos_grads, model)):
+            for curr, mem, cpos, mpos, go in batches:
+                mpos.grad = None
+                o = runner(curr, mem, cpos, mpos, p)
+                o.backward(go)
+                sink_out.append(o.detach().clone())
+                if pos_grad:
+                    sink_pos.append(mpos.grad.detach().clone())
+                del o
+        torch.cuda.synchronize()
+        for a, c in zip(outs, outs_ref):
+            assert rel_l2(a, c) < 1e-6, "graph replay / mirror changed the forward"
+        for a, c in zip(pos_grads, ref_pos_grads):
+            assert rel_l2(a, c) < 1e-5
+        for (name, pr), pm in zip(ref_model.named_parameters(), model.parameters()):
+            assert pm.grad.data_ptr() >= bucket.flat.data_ptr(), name          # still a view of the bucket
+            assert rel_l2(pm.grad, pr.grad) < 2e-5, (step, name, rel_l2(pm.grad, pr.grad))
+        with torch.no_grad():        # same in-place update on both models
+            for pr, pm in zip(ref_model.parameters(), model.parameters()):
+                pr.add_(0.01 * torch.sign(pr.grad)); pm.add_(0.01 * torch.sign(pr.grad))
+
+
 def test_training_mode_with_dropout_uses_composed_path(dev):
     """dropout > 0 in train mode is outside the fused stack: residual / MLP dropouts run through nn.Dropout
     (composed path); attention-probability dropout is a documented deviation (treated as 0)."""

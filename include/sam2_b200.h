@@ -127,6 +127,13 @@ int sam2b200_mask_loss_bwd(const float* const* logits, float* const* dlogits, co
                            long long HW, int mode, float alpha, float gamma, float inv_temp,
                            int iou_l1, int reduction_mean, sam2b200_stream_t stream);
 
+/* Backward of the six per-channel sums themselves -- what the stand-alone dice_loss / sigmoid_focal_loss of
+ * sam2_video/model/losses.py:20-57 need: dlogits = coef[c][0] * d(sum_px focal)/dx + (t ? coef[c][1] : coef[c][2]) * p(1-p),
+ * coef: device [T, C, 3] fp32 (coef[.][1] = d/d(sum p*t) + d/d(sum p), coef[.][2] = d/d(sum p)); no valid filter. */
+int sam2b200_mask_loss_bwd_coef(const float* const* logits, float* const* dlogits, const uint8_t* targets,
+                                const float* coef, int T, int C, long long HW, float alpha, float gamma, float inv_temp,
+                                sam2b200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -175,3 +175,39 @@ def bce_category_loss(logits: Sequence[Tensor], targets: Tensor,
         total = total + fl
     total = total / max(len(logits), 1)
     return {"loss_bce": total, CORE_LOSS_KEY: total}
+
+
+# ---- stand-alone functional forms (losses.py:20-76), restated on top of the six per-channel sums -------------
+def _sums(inputs: Tensor, targets: Tensor, lead: int, alpha: float = -1.0, gamma: float = 0.0):
+    shape = tuple(inputs.shape[:lead])
+    x = inputs.reshape(int(torch.Size(shape).numel()), -1)
+    t = targets.reshape(x.shape[0], -1).to(x.dtype)
+    s = frame_channel_sums(x, t, alpha, gamma)
+    return {k: v.view(*shape) for k, v in s.items()}, x.shape[1]
+
+
+def dice_loss(inputs: Tensor, targets: Tensor, num_objects: float, loss_on_multimask: bool = False) -> Tensor:
+    """losses.py:20-34: 1 - (2 sum p t + 1) / (sum p + sum t + 1) per mask (multimask) or per row, / num_objects."""
+    s, _ = _sums(inputs, targets, 2 if loss_on_multimask else 1)
+    loss = 1 - (2 * s["pt"] + 1) / (s["p"] + s["t"] + 1)
+    return loss / num_objects if loss_on_multimask else loss.sum() / num_objects
+
+
+def sigmoid_focal_loss(inputs: Tensor, targets: Tensor, num_objects: float, alpha: float = 0.25, gamma: float = 2,
+                       loss_on_multimask: bool = False) -> Tensor:
+    """losses.py:37-57: multimask -> mean over H*W per mask / num_objects; else mean over dim 1, sum of the rest."""
+    if loss_on_multimask:
+        s, hw = _sums(inputs, targets, 2, alpha, gamma)
+        return s["focal"] / hw / num_objects
+    s, _ = _sums(inputs, targets, 1, alpha, gamma)
+    return s["focal"].sum() / inputs.shape[1] / num_objects
+
+
+def iou_loss(inputs: Tensor, targets: Tensor, pred_ious: Tensor, num_objects: float, loss_on_multimask: bool = False,
+             use_l1_loss: bool = False) -> Tensor:
+    """losses.py:60-76: |pred - I/max(U,1)| or its square, gradient to pred_ious only."""
+    s, _ = _sums(inputs.detach(), (targets > 0), 2)
+    actual = s["inter"] / torch.clamp(s["union"], min=1.0)
+    d = pred_ious - actual
+    loss = d.abs() if use_l1_loss else d * d
+    return loss / num_objects if loss_on_multimask else loss.sum() / num_objects

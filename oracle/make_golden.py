@@ -53,6 +53,33 @@ def golden_attention(ns, grid, batch, n_frames, n_ptr, tag, full_grads=False):
     return rec
 
 
+def golden_functional(ns, n, m, s, tag):
+    """Stand-alone dice_loss / sigmoid_focal_loss / iou_loss of the reference (losses.py:20-76), both branches."""
+    L = ns.losses
+    logits, targets, iou_pred = detgen.loss_inputs(n, m, s)          # [n, m, 1, s, s], bool [n, m, s, s], [n, m, 1]
+    x = logits[:, :, 0].clone().requires_grad_(True)                # [n, m, s, s]
+    t = targets.float()
+    iou = iou_pred[:, :, 0].clone().requires_grad_(True)            # [n, m]
+    rec = {}
+    outs = {"mm:dice": L.dice_loss(x, t, 3.0, loss_on_multimask=True),
+            "mm:focal": L.sigmoid_focal_loss(x, t, 3.0, alpha=0.25, gamma=2, loss_on_multimask=True),
+            "mm:iou": L.iou_loss(x, t, iou, 3.0, loss_on_multimask=True, use_l1_loss=False),
+            "flat:dice": L.dice_loss(x.flatten(1), t.flatten(1), 3.0),
+            "flat:focal": L.sigmoid_focal_loss(x.flatten(1), t.flatten(1), 3.0, alpha=-1, gamma=0),
+            "flat:iou": L.iou_loss(x, t, iou, 3.0, use_l1_loss=True)}
+    tot = 0
+    for i, (k, v) in enumerate(outs.items()):
+        rec[k] = v.detach().numpy()
+        w = detgen.det(tuple(v.shape), 0.77 + i, 0.3, 1.0) + 1.5 if v.dim() else torch.tensor(1.0 + 0.25 * i)
+        rec[k + ":w"] = w.numpy()
+        tot = tot + (v * w).sum()
+    tot.backward()
+    rec["dx"] = x.grad.numpy()
+    rec["diou"] = iou.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, f"lossfn_{tag}.npz"), **rec)
+    return rec
+
+
 def golden_loss(ns, t, c, s, tag):
     logits, targets, iou_pred = detgen.loss_inputs(t, c, s)
     rec = dict(t=t, c=c, s=s)
@@ -114,6 +141,7 @@ def main():
     print("attn g12: out abs", float(np.abs(r["out"]).sum()))
     r = golden_loss(ns, 2, 3, 16, "t2_c3_s16")
     print("loss: l1 total", r["l1:total_loss"], "mse total", r["mse:total_loss"], "bce", r["bce:total_loss"])
+    golden_functional(ns, 3, 2, 24, "n3_m2_s24")
     r = golden_loss(ns, 3, 5, 40, "t3_c5_s40")
     print("loss2: l1 total", r["l1:total_loss"])
 

@@ -338,6 +338,8 @@ struct BwdParams {
   const float* gout;           // [3] d/d(loss_mask, loss_dice, loss_iou)  or [1] (BCE)
   const float* iou_pred;       // [tt*C]
   float* diou;                 // [tt*C]
+  const float* raw_coef;       // [tt*C][3] or null.  Non-null ("functional" backward): per-channel coefficients
+                               // (d/d sum_focal, d/d sum_pt + d/d sum_p, d/d sum_p) given directly, no valid filter
   long long HW;
   int C, frame0;
   float inv_temp, alpha, gamma;
@@ -355,15 +357,22 @@ mask_loss_bwd_kernel(const __grid_constant__ FramePtrs fp, const __grid_constant
   const float* __restrict__ x = fp.logits[f] + (long long)c * HW;
   float* __restrict__ dx = op.dlogits[f] + (long long)c * HW;
   const uint8_t* __restrict__ tg = P.targets + ((long long)(P.frame0 + f) * P.C + c) * HW;
-  const float* s = P.chan_sums + (long long)fc * kNumSums;
-  const int nv = P.n_valid[f];
-  const bool valid = s[3] > 0.f && nv > 0;
+  const bool raw = P.raw_coef != nullptr;
+  const float* s = raw ? nullptr : P.chan_sums + (long long)fc * kNumSums;
+  const int nv = raw ? 1 : P.n_valid[f];
+  const bool valid = raw || (s[3] > 0.f && nv > 0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   // per-channel coefficients: grad = kf_t * q^gamma * (q + gamma softplus (1-q)) + dc_t * q (1-q)      (MODE 0)
   //                           grad = kb_t * q                                                            (MODE 1)
   float kf_fg = 0.f, kf_bg = 0.f, dc_fg = 0.f, dc_bg = 0.f;
-  if (valid) {
+  if (raw) {
+    const float* cf = P.raw_coef + (long long)fc * 3;
+    kf_fg = -cf[0] * P.inv_temp * ((P.alpha >= 0.f) ? P.alpha : 1.0f);
+    kf_bg = cf[0] * P.inv_temp * ((P.alpha >= 0.f) ? (1.0f - P.alpha) : 1.0f);
+    dc_fg = cf[1] * P.inv_temp;
+    dc_bg = cf[2] * P.inv_temp;
+  } else if (valid) {
     if (MODE == 0) {
       const float inv_nv_t = P.inv_temp / (float)nv;
       const float kf = P.gout[0] * inv_nv_t / (float)HW;
@@ -382,7 +391,7 @@ mask_loss_bwd_kernel(const __grid_constant__ FramePtrs fp, const __grid_constant
       kf_bg = kb;
     }
   }
-  if (MODE == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+  if (MODE == 0 && !raw && blockIdx.x == 0 && threadIdx.x == 0) {
     float g = 0.f;
     if (valid) {
       const float actual = s[4] / fmaxf(s[5], 1.0f);
@@ -532,14 +541,11 @@ int sam2b200_mask_loss_fwd(const float* const* logits, const uint8_t* targets, c
   return sam2b200::check_launch("mask_loss_fwd", launches);
 }
 
-int sam2b200_mask_loss_bwd(const float* const* logits, float* const* dlogits, const uint8_t* targets,
-                           const float* iou_pred, const float* pos_weight, const float* chan_sums,
-                           const int* n_valid, const float* grad_losses, float* diou, int T, int C,
-                           long long HW, int mode, float alpha, float gamma, float inv_temp,
-                           int iou_l1, int reduction_mean, cudaStream_t stream) {
-  if (T <= 0 || C <= 0 || HW <= 0 || !logits || !dlogits || !targets || !chan_sums || !n_valid ||
-      !grad_losses || (mode == 0 && (!iou_pred || !diou)) || (mode != 0 && mode != 1))
-    return sam2b200::fail(SAM2B200_ERR_INVALID, "mask_loss_bwd: bad arguments");
+static int mask_loss_bwd_impl(const float* const* logits, float* const* dlogits, const uint8_t* targets,
+                              const float* iou_pred, const float* pos_weight, const float* chan_sums,
+                              const int* n_valid, const float* grad_losses, float* diou, const float* raw_coef, int T, int C,
+                              long long HW, int mode, float alpha, float gamma, float inv_temp,
+                              int iou_l1, int reduction_mean, cudaStream_t stream) {
   const int nblk = bwd_blocks_per_channel(HW);
   int launches = 0;
   for (int f0 = 0; f0 < T; f0 += kMaxFrames) {
@@ -555,10 +561,11 @@ int sam2b200_mask_loss_bwd(const float* const* logits, float* const* dlogits, co
       vec_ok = vec_ok && aligned16(fp.logits[f]) && aligned16(op.dlogits[f]);
     }
     BwdParams P;
-    P.targets = targets; P.pos_weight = pos_weight; P.chan_sums = chan_sums + (size_t)f0 * C * kNumSums;
-    P.n_valid = n_valid + f0; P.gout = grad_losses;
+    P.targets = targets; P.pos_weight = pos_weight; P.chan_sums = chan_sums ? chan_sums + (size_t)f0 * C * kNumSums : nullptr;
+    P.n_valid = n_valid ? n_valid + f0 : nullptr; P.gout = grad_losses;
     P.iou_pred = iou_pred ? iou_pred + (size_t)f0 * C : nullptr;
     P.diou = diou ? diou + (size_t)f0 * C : nullptr;
+    P.raw_coef = raw_coef ? raw_coef + (size_t)f0 * C * 3 : nullptr;
     P.HW = HW; P.C = C; P.frame0 = f0; P.inv_temp = inv_temp; P.alpha = alpha; P.gamma = gamma;
     P.iou_l1 = iou_l1; P.reduction_mean = reduction_mean; P.vec_ok = vec_ok;
     dim3 grid(nblk, tt * C);
@@ -574,6 +581,30 @@ int sam2b200_mask_loss_bwd(const float* const* logits, float* const* dlogits, co
     ++launches;
   }
   return sam2b200::check_launch("mask_loss_bwd", launches);
+}
+
+int sam2b200_mask_loss_bwd(const float* const* logits, float* const* dlogits, const uint8_t* targets,
+                           const float* iou_pred, const float* pos_weight, const float* chan_sums,
+                           const int* n_valid, const float* grad_losses, float* diou, int T, int C,
+                           long long HW, int mode, float alpha, float gamma, float inv_temp,
+                           int iou_l1, int reduction_mean, cudaStream_t stream) {
+  if (T <= 0 || C <= 0 || HW <= 0 || !logits || !dlogits || !targets || !chan_sums || !n_valid ||
+      !grad_losses || (mode == 0 && (!iou_pred || !diou)) || (mode != 0 && mode != 1))
+    return sam2b200::fail(SAM2B200_ERR_INVALID, "mask_loss_bwd: bad arguments");
+  return mask_loss_bwd_impl(logits, dlogits, targets, iou_pred, pos_weight, chan_sums, n_valid, grad_losses, diou, nullptr, T, C,
+                            HW, mode, alpha, gamma, inv_temp, iou_l1, reduction_mean, stream);
+}
+
+// Backward of the per-channel sums themselves (functional forms dice_loss / sigmoid_focal_loss, losses.py:20-57):
+// dlogits = coef[c][0] * d(sum focal_c)/dx + (t ? coef[c][1] : coef[c][2]) * p (1 - p), coef: [T, C, 3] fp32 with
+// coef[.][1] = d/d(sum p t) + d/d(sum p), coef[.][2] = d/d(sum p).  No valid-channel filter.
+int sam2b200_mask_loss_bwd_coef(const float* const* logits, float* const* dlogits, const uint8_t* targets,
+                                const float* coef, int T, int C, long long HW, float alpha, float gamma, float inv_temp,
+                                cudaStream_t stream) {
+  if (T <= 0 || C <= 0 || HW <= 0 || !logits || !dlogits || !targets || !coef)
+    return sam2b200::fail(SAM2B200_ERR_INVALID, "mask_loss_bwd_coef: bad arguments");
+  return mask_loss_bwd_impl(logits, dlogits, targets, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, coef, T, C, HW, 0,
+                            alpha, gamma, inv_temp, 0, 1, stream);
 }
 
 }  // extern "C"

@@ -276,20 +276,93 @@ class BCECategoryLoss(nn.Module):
         return {"loss_bce": total_loss, CORE_LOSS_KEY: total_loss}
 
 
-# ---- functional forms (losses.py:20-76), same signatures, fused kernel underneath -------------
-def _functional_sums(inputs: torch.Tensor, targets: torch.Tensor, alpha: float, gamma: float):
-    assert inputs.dim() == 4 and targets.dim() == 4 and inputs.shape[1] == 1
-    cfg = dict(mode=_MODE_MULTISTEP, alpha=float(alpha), gamma=float(gamma), inv_temp=1.0, iou_l1=False,
-               reduction_mean=True)
-    return cfg
+# ---- functional forms (losses.py:20-76): same names, signatures and results, fused kernels underneath ----------
+class _ChannelSumsFn(torch.autograd.Function):
+    """sums[C, 6] = (sum focal, sum p*t, sum p, sum t, |pred & gt|, |pred | gt|) per channel of x [C, HW] against the
+    0/1 targets t [C, HW]; differentiable in x through the first three sums (sam2b200_mask_loss_bwd_coef)."""
+
+    @staticmethod
+    def forward(ctx, x, t_u8, alpha, gamma):
+        lib = _lib.load()
+        c, hw = x.shape
+        dev = x.device
+        ws_bytes = lib.sam2b200_mask_loss_workspace_bytes(1, c, hw)
+        ws = torch.empty(max(ws_bytes, 4) // 4, dtype=torch.float32, device=dev)
+        sums = torch.empty(1, c, 6, dtype=torch.float32, device=dev)
+        n_valid = torch.empty(1, dtype=torch.int32, device=dev)
+        losses = torch.zeros(4, dtype=torch.float32, device=dev)
+        iou_dummy = torch.zeros(1, c, dtype=torch.float32, device=dev)
+        rc = lib.sam2b200_mask_loss_fwd(_lib.ptr_array([x.data_ptr()]), t_u8.data_ptr(), iou_dummy.data_ptr(), None,
+                                        ws.data_ptr(), sums.data_ptr(), n_valid.data_ptr(), losses.data_ptr(), 1, c, hw,
+                                        _MODE_MULTISTEP, float(alpha), float(gamma), 1.0, 0, 1, _stream_ptr(dev))
+        _lib.check(rc, "sam2b200_mask_loss_fwd")
+        ctx.save_for_backward(x, t_u8)
+        ctx.cfg = (float(alpha), float(gamma))
+        return sums[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        x, t_u8 = ctx.saved_tensors
+        c, hw = x.shape
+        g = g.float()
+        coef = torch.stack([g[:, 0], g[:, 1] + g[:, 2], g[:, 2]], dim=1).contiguous()
+        dx = torch.empty_like(x)
+        rc = lib.sam2b200_mask_loss_bwd_coef(_lib.ptr_array([x.data_ptr()]), _lib.ptr_array([dx.data_ptr()]), t_u8.data_ptr(),
+                                             coef.data_ptr(), 1, c, hw, ctx.cfg[0], ctx.cfg[1], 1.0, _stream_ptr(x.device))
+        _lib.check(rc, "sam2b200_mask_loss_bwd_coef")
+        return dx, None, None, None
 
 
-def sigmoid_focal_loss(inputs, targets, num_objects, alpha: float = 0.25, gamma: float = 2,
-                       loss_on_multimask=False):
-    raise NotImplementedError(
-        "use MultiStepMultiMasksAndIous: the B200 path fuses focal+dice+IoU into one pass "
-        "(stand-alone functional forms would re-read the logits three times)")
+def _channel_sums(inputs: torch.Tensor, targets: torch.Tensor, lead_dims: int, alpha: float = -1.0, gamma: float = 0.0):
+    """inputs / targets flattened to [prod(shape[:lead_dims]), rest] -> sums [.., 6] with the leading shape restored."""
+    _require_cuda(inputs, "inputs")
+    _require_cuda(targets, "targets")
+    lead = tuple(inputs.shape[:lead_dims])
+    x = inputs.reshape(int(torch.Size(lead).numel()), -1).float().contiguous()
+    t = targets.reshape(x.shape[0], -1)
+    if t.shape != x.shape:
+        raise ValueError("inputs / targets shape mismatch")
+    if t.dtype not in (torch.bool, torch.uint8) and bool(((t != 0) & (t != 1)).any().item()):
+        raise NotImplementedError("the B200 loss kernels take binary {0, 1} targets")
+    t_u8 = (t != 0).contiguous().view(torch.uint8) if t.dtype != torch.uint8 else t.contiguous()
+    return _ChannelSumsFn.apply(x, t_u8, alpha, gamma).view(*lead, 6), x.shape[1]
 
 
-dice_loss = sigmoid_focal_loss
-iou_loss = sigmoid_focal_loss
+def dice_loss(inputs, targets, num_objects, loss_on_multimask=False):
+    """losses.py:20-34.  One fused pass over the logits instead of four."""
+    if loss_on_multimask:
+        assert inputs.dim() == 4 and targets.dim() == 4
+        s, _ = _channel_sums(inputs, targets, 2)
+    else:
+        s, _ = _channel_sums(inputs, targets, 1)
+    loss = 1 - (2 * s[..., 1] + 1) / (s[..., 2] + s[..., 3] + 1)
+    if loss_on_multimask:
+        return loss / num_objects
+    return loss.sum() / num_objects
+
+
+def sigmoid_focal_loss(inputs, targets, num_objects, alpha: float = 0.25, gamma: float = 2, loss_on_multimask=False):
+    """losses.py:37-57."""
+    if loss_on_multimask:
+        assert inputs.dim() == 4
+        s, hw = _channel_sums(inputs, targets, 2, alpha, gamma)
+        return s[..., 0] / hw / num_objects                       # flatten(2).mean(-1) / num_objects
+    # loss.mean(1).sum() / num_objects: the mean runs over dim 1 only, everything else is summed
+    s, _ = _channel_sums(inputs, targets, 1, alpha, gamma)
+    return s[..., 0].sum() / inputs.shape[1] / num_objects
+
+
+def iou_loss(inputs, targets, pred_ious, num_objects, loss_on_multimask=False, use_l1_loss=False):
+    """losses.py:60-76.  Differentiable in pred_ious only (the mask comparison has no gradient)."""
+    assert inputs.dim() == 4 and targets.dim() == 4
+    with torch.no_grad():
+        s, _ = _channel_sums(inputs.detach(), (targets > 0), 2)
+        actual_ious = s[..., 4] / torch.clamp(s[..., 5], min=1.0)
+    if use_l1_loss:
+        loss = torch.nn.functional.l1_loss(pred_ious, actual_ious, reduction="none")
+    else:
+        loss = torch.nn.functional.mse_loss(pred_ious, actual_ious, reduction="none")
+    if loss_on_multimask:
+        return loss / num_objects
+    return loss.sum() / num_objects

@@ -443,3 +443,35 @@ def test_loss_frames_are_used_in_place(dev):
              "multistep_object_score_logits": [torch.zeros(4, 1, device=dev)]} for f in range(3)]
     b = crit(outs, targets.to(dev))
     assert float(a["total_loss"]) == float(b["total_loss"])
+
+
+@pytest.mark.parametrize("multimask", [True, False])
+def test_functional_losses_match_reference_formulas(dev, multimask):
+    """dice_loss / sigmoid_focal_loss / iou_loss keep the reference's signatures and values (losses.py:20-76); the
+    expected values come from the oracle's restatement of those three functions, gradients included."""
+    from oracle import losses_oracle as lo
+    from sam2_video_training_b200 import losses as L
+    g = torch.Generator().manual_seed(21)
+    n, m, s = 3, 2, 48
+    x = (torch.randn(n, m, s, s, generator=g) * 3).double().requires_grad_(True)
+    t = (torch.rand(n, m, s, s, generator=g) > 0.7).double()
+    iou = torch.rand(n, m, generator=g).double().requires_grad_(True)
+    xg = x.detach().float().to(dev).requires_grad_(True)
+    tg = t.float().to(dev)
+    ig = iou.detach().float().to(dev).requires_grad_(True)
+    if multimask:
+        ref = (lo.dice_loss(x, t, 5.0, True), lo.sigmoid_focal_loss(x, t, 5.0, 0.25, 2.0, True), lo.iou_loss(x, t, iou, 5.0, True, False))
+        got = (L.dice_loss(xg, tg, 5.0, True), L.sigmoid_focal_loss(xg, tg, 5.0, 0.25, 2.0, True), L.iou_loss(xg, tg, ig, 5.0, True, False))
+    else:
+        xf, tf = x.flatten(1), t.flatten(1)
+        ref = (lo.dice_loss(xf, tf, 5.0), lo.sigmoid_focal_loss(xf, tf, 5.0, 0.25, 2.0), lo.iou_loss(x, t, iou, 5.0, False, True))
+        got = (L.dice_loss(xg.flatten(1), tg.flatten(1), 5.0), L.sigmoid_focal_loss(xg.flatten(1), tg.flatten(1), 5.0, 0.25, 2.0),
+               L.iou_loss(xg, tg, ig, 5.0, False, True))
+    w = [torch.rand(r.shape, generator=g).double() + 0.5 for r in ref]
+    sum((r * wi).sum() for r, wi in zip(ref, w)).backward()
+    sum((o * wi.float().to(dev)).sum() for o, wi in zip(got, w)).backward()
+    for r, o in zip(ref, got):
+        assert o.shape == r.shape
+        assert rel_l2(o.detach().cpu().double(), r.detach()) < 1e-5
+    assert rel_l2(xg.grad.cpu().double(), x.grad) < 1e-5
+    assert rel_l2(ig.grad.cpu().double(), iou.grad) < 1e-5

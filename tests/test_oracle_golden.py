@@ -140,3 +140,31 @@ def test_loss_no_valid_masks_raises():
     targets[1] = False
     with pytest.raises(ValueError, match="No valid masks"):
         lo.multistep_loss([logits[f] for f in range(2)], targets, [iou_pred[f] for f in range(2)], dict(W_FOCAL))
+
+
+def test_functional_losses_oracle_matches_reference(golden_dir):
+    """Stand-alone dice_loss / sigmoid_focal_loss / iou_loss (losses.py:20-76), multimask and flat branches, values and
+    gradients against the fixture written from the unmodified reference (oracle/make_golden.py:golden_functional)."""
+    from oracle import detgen
+    from oracle import losses_oracle as lo
+    g = np.load(os.path.join(golden_dir, "lossfn_n3_m2_s24.npz"))
+    logits, targets, iou_pred = detgen.loss_inputs(3, 2, 24)
+    x = logits[:, :, 0].double().requires_grad_(True)
+    t = targets.double()
+    iou = iou_pred[:, :, 0].double().requires_grad_(True)
+    outs = {"mm:dice": lo.dice_loss(x, t, 3.0, True),
+            "mm:focal": lo.sigmoid_focal_loss(x, t, 3.0, 0.25, 2, True),
+            "mm:iou": lo.iou_loss(x, t, iou, 3.0, True, False),
+            "flat:dice": lo.dice_loss(x.flatten(1), t.flatten(1), 3.0),
+            "flat:focal": lo.sigmoid_focal_loss(x.flatten(1), t.flatten(1), 3.0, -1, 0),
+            "flat:iou": lo.iou_loss(x, t, iou, 3.0, False, True)}
+    tot = 0
+    for k, v in outs.items():
+        ref = torch.from_numpy(g[k]).double()
+        assert v.shape == ref.shape, k
+        assert float((v.detach() - ref).abs().max()) <= 2e-6 * max(1.0, float(ref.abs().max())), k
+        tot = tot + (v * torch.from_numpy(g[k + ":w"]).double()).sum()
+    tot.backward()
+    dx, diou = torch.from_numpy(g["dx"]).double(), torch.from_numpy(g["diou"]).double()
+    assert float((x.grad - dx).norm() / dx.norm()) < 1e-5
+    assert float((iou.grad - diou).norm() / diou.norm()) < 1e-5

@@ -118,6 +118,59 @@ def direct_grads_possible(bucket, params) -> bool:
             and all(p.requires_grad and bucket.owns(p) for p in params))
 
 
+NO_SIDE_STREAM = bool(os.environ.get("SAM2B200_NO_SIDE_STREAM"))   # A/B switch: everything on one stream
+_SIDE_STREAMS = {}
+
+
+class _SideStream:
+    """Second CUDA stream for work that is off the critical path of the stack:
+      * forward: the cross-attention K/V projections + RoPE of all layers depend only on the memory bank, so they run
+        ahead of the layers (HBM-bound) while the main stream is in the tensor-core-bound self-attention;
+      * backward: weight / bias gradients only feed the optimizer, so their long-K split-K GEMMs and column sums fill
+        the SMs the attention kernels leave idle (wave tails) instead of sitting between them.
+    Tensors produced on one stream and consumed on the other are kept alive until `join()`; fork / join use events,
+    which CUDA-graph capture records as graph dependencies."""
+
+    def __init__(self, dev):
+        self.enabled = not NO_SIDE_STREAM
+        self.main = torch.cuda.current_stream(dev)
+        if self.enabled:
+            key = (dev.index, self.main.cuda_stream)
+            if key not in _SIDE_STREAMS:
+                _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+            self.side = _SIDE_STREAMS[key]
+        self.keep = []
+        self.used = False
+
+    def run(self, fn, *keep):
+        """Enqueue fn() on the side stream after everything enqueued so far on the main stream."""
+        if not self.enabled:
+            return fn()
+        self.side.wait_stream(self.main)
+        with torch.cuda.stream(self.side):
+            out = fn()
+        self.keep.extend(keep)
+        self.used = True
+        return out
+
+    def event(self):
+        if not self.enabled:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(self.side)
+        return ev
+
+    def wait(self, ev):
+        if ev is not None:
+            self.main.wait_event(ev)
+
+    def join(self):
+        if self.enabled and self.used:
+            self.main.wait_stream(self.side)
+        self.keep.clear()
+        self.used = False
+
+
 class WeightMirror:
     """Persistent bf16 copies of the fp32 master parameters in ONE flat buffer (static addresses, so CUDA graphs can
     read them), refreshed by a single multi-tensor copy when a parameter was updated in place (tensor._version
@@ -209,6 +262,18 @@ class MemoryAttentionStackFn(torch.autograd.Function):
         wb = bf16_params(masters)
         saved: List[torch.Tensor] = []
         res = None
+        side = _SideStream(x.device)
+        kv_ready = []
+
+        def project_memory():        # cross-attention keys / values of every layer: functions of the bank only
+            for l in range(nl):
+                W = dict(zip(_LAYER_KEYS, wb[l * _NPL:(l + 1) * _NPL]))
+                k2 = torch.addmm(W["ca.k.b"], memk, W["ca.k.w"].t())
+                v2 = torch.addmm(W["ca.v.b"], memv, W["ca.v.w"].t())
+                k2_rot = rope_apply(k2.view(b, m, d), table, n_rope_k)
+                kv_ready.append((k2_rot, v2, side.event()))
+
+        side.run(project_memory, memk, memv)
         for l in range(nl):
             P = dict(zip(_LAYER_KEYS, params[l * _NPL:(l + 1) * _NPL]))
             W = dict(zip(_LAYER_KEYS, wb[l * _NPL:(l + 1) * _NPL]))
@@ -224,10 +289,9 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             # ---- cross attention to the memory bank (memory_attention.py:66-81)
             y2, x1, mean2, rstd2 = ln_fwd(x, sa, P["n2.w"], P["n2.b"])
             q2 = torch.addmm(W["ca.q.b"], y2, W["ca.q.w"].t())
-            k2 = torch.addmm(W["ca.k.b"], memk, W["ca.k.w"].t())
-            v2 = torch.addmm(W["ca.v.b"], memv, W["ca.v.w"].t())
             q2_rot = rope_apply(q2.view(b, n, d), table, n)
-            k2_rot = rope_apply(k2.view(b, m, d), table, n_rope_k)
+            k2_rot, v2, ev = kv_ready[l]
+            side.wait(ev)
             o2, o2_32, lse2 = attn_fwd(q2_rot, k2_rot, v2.view(b, m, d), scale, meta["nsplit"])
             ca = torch.addmm(W["ca.o.b"], o2.view(r, d), W["ca.o.w"].t())
             # ---- MLP (memory_attention.py:95-98)
@@ -240,6 +304,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             x, res = x2, mlp
         gamma_f, beta_f = params[nl * _NPL], params[nl * _NPL + 1]
         out, x_fin, mean_f, rstd_f = ln_fwd(x, res, gamma_f, beta_f, want_f32_seq_first=(b, n))
+        side.join()
         saved += [x_fin, mean_f, rstd_f, memk, memv, table]
         ctx.save_for_backward(*saved, *params)
         ctx.n_saved = len(saved)
@@ -284,11 +349,17 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                 gv[i] = grads[i] = flat[off:off + params[i].numel()]
                 off += params[i].numel()
 
-        def acc_w(i, a_t, bmat):     # grad[i] (+)= a_t @ bmat   (bf16 x bf16 -> fp32)
-            if direct:
-                torch.addmm(gv[i], a_t, bmat, out_dtype=F32, out=gv[i])
-            else:
-                grads[i] = _mm32(a_t, bmat)
+        side = _SideStream(dev)
+
+        def acc_w(i, a_t, bmat, bias=None):     # grad[i] (+)= a_t @ bmat (bf16 x bf16 -> fp32); bias grad (+)= colsum(a_t^T)
+            def work():
+                if bias is not None:
+                    colsum_bf16(a_t.t(), bias)
+                if direct:
+                    torch.addmm(gv[i], a_t, bmat, out_dtype=F32, out=gv[i])
+                else:
+                    grads[i] = _mm32(a_t, bmat)
+            side.run(work, a_t, bmat)
         grad_out = grad_out.contiguous().float()
         g = ln_bwd(grad_out, x_fin, mean_f, rstd_f, params[nl * _NPL], None, gv[nl * _NPL], gv[nl * _NPL + 1],
                    seq_first=(b, n))
@@ -317,17 +388,18 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             dq2, dk2, dv2 = attn_bwd(q2_rot, k2_rot, v2.view(b, m, d), None, o2_32, do2.view(b, n, d), lse2, scale,
                                      table=table, n_rope_k=n_rope_k, grad_dtype=BF16)   # conj. RoPE fused in epilogue
             dq2, dk2, dv2 = dq2.view(r, d), dk2.view(rm, d), dv2.view(rm, d)
-            colsum_bf16(dq2, gv[ix["ca.q.b"]])
-            colsum_bf16(dk2, gv[ix["ca.k.b"]])
-            colsum_bf16(dv2, gv[ix["ca.v.b"]])
-            acc_w(ix["ca.q.w"], dq2.t(), y2)
-            acc_w(ix["ca.k.w"], dk2.t(), memk)
-            acc_w(ix["ca.v.w"], dv2.t(), memv)
-            if need_memgrad:
-                torch.addmm(dmemk, dk2, W["ca.k.w"], out_dtype=F32, out=dmemk)
-            if need_mem:
-                torch.addmm(dmemv, dv2, W["ca.v.w"], out_dtype=F32, out=dmemv)
             dy2 = torch.mm(dq2, W["ca.q.w"])
+            acc_w(ix["ca.q.w"], dq2.t(), y2, gv[ix["ca.q.b"]])
+            acc_w(ix["ca.k.w"], dk2.t(), memk, gv[ix["ca.k.b"]])
+            acc_w(ix["ca.v.w"], dv2.t(), memv, gv[ix["ca.v.b"]])
+
+            def mem_grads(dk2=dk2, dv2=dv2, wk=W["ca.k.w"], wv=W["ca.v.w"]):
+                if need_memgrad:
+                    torch.addmm(dmemk, dk2, wk, out_dtype=F32, out=dmemk)
+                if need_mem:
+                    torch.addmm(dmemv, dv2, wv, out_dtype=F32, out=dmemv)
+            if need_memgrad or need_mem:
+                side.run(mem_grads, dk2, dv2)
             g = ln_bwd(dy2, x1, mean2, rstd2, P["n2.w"], g, gv[ix["n2.w"]], gv[ix["n2.b"]])
             # ---- self attention backward
             dsa = cast_colsum(g, gv[ix["sa.o.b"]])
@@ -343,8 +415,10 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             gb = bucket.span(qkv_b, (3 * d,)) if direct else None
             if gw is not None and gb is not None:
                 # the bucket lays the three projections out back to back: one colsum, one [768, 256] GEMM
-                colsum_bf16(dqkv, gb)
-                torch.addmm(gw, dqkv.t(), y1, out_dtype=F32, out=gw)
+                def qkv_grads(dqkv=dqkv, y1=y1, gw=gw, gb=gb):
+                    colsum_bf16(dqkv, gb)
+                    torch.addmm(gw, dqkv.t(), y1, out_dtype=F32, out=gw)
+                side.run(qkv_grads, dqkv, y1)
             elif direct:
                 for j, (kw, kb) in enumerate((("sa.q.w", "sa.q.b"), ("sa.k.w", "sa.k.b"), ("sa.v.w", "sa.v.b"))):
                     part = dqkv[:, j * d:(j + 1) * d]
@@ -360,6 +434,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                 grads[ix["sa.q.w"]], grads[ix["sa.k.w"]], grads[ix["sa.v.w"]] = dw[:d], dw[d:2 * d], dw[2 * d:]
             dy1 = torch.mm(dqkv, wqkv_all[l])            # stacked [768, 256] weights: contraction over 768, fp32 accumulation
             g = ln_bwd(dy1, x0, mean1, rstd1, P["n1.w"], g, gv[ix["n1.w"]], gv[ix["n1.b"]])
+        side.join()
         # ---- unpack input gradients
         d_curr = d_pos = d_mem = d_mpos = None
         if need_curr or need_pos:

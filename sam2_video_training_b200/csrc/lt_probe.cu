@@ -171,6 +171,10 @@ int main() {
       printf("time R=%d  dh plain           %.1f us\n", R, ms * 1e3);
     if (gemm(dm, w2, dh, R, F, D, D, F, F, false, false, CUDA_R_16BF, 1.f, 0.f, CUBLASLT_EPILOGUE_DRELU_BGRAD, dbg, CUDA_R_32F, mask, F, &ms) == 0)
       printf("time R=%d  dh DRELU_BGRAD     %.1f us\n", R, ms * 1e3);
+    if (gemm(dm, w2, dh, R, F, D, D, F, F, false, false, CUDA_R_16BF, 1.f, 0.f, CUBLASLT_EPILOGUE_DRELU, nullptr, CUDA_R_32F, mask, F, &ms) == 0)
+      printf("time R=%d  dh DRELU           %.1f us\n", R, ms * 1e3);
+    if (gemm(dm, w2, dh, R, F, D, D, F, F, false, false, CUDA_R_16BF, 1.f, 0.f, CUBLASLT_EPILOGUE_DRELU_BGRAD, dbg, CUDA_R_16BF, mask, F, &ms) == 0)
+      printf("time R=%d  dh DRELU_BGRAD(bf16) %.1f us\n", R, ms * 1e3);
     if (gemm(dh, y, dW, F, D, R, F, D, D, true, false, CUDA_R_32F, 1.f, 1.f, CUBLASLT_EPILOGUE_DEFAULT, nullptr, CUDA_R_32F, nullptr, 0, &ms) == 0)
       printf("time R=%d  dW1 plain beta=1   %.1f us\n", R, ms * 1e3);
     if (gemm(dh, y, dW, F, D, R, F, D, D, true, false, CUDA_R_32F, 1.f, 1.f, CUBLASLT_EPILOGUE_BGRADB, dbg, CUDA_R_32F, nullptr, 0, &ms) == 0)

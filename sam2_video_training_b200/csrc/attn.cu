@@ -261,10 +261,14 @@ int sam2b200_attn_fwd(const void* q, const void* k, const void* v, void* out, fl
 // bf16 if 1), fully written in their first 256 columns.  If rope_table != NULL the conjugate axial rotation
 // is applied in the epilogue: to every row of dq and to rows [0, n_rope_k) of dk (table row = row % rope_period),
 // i.e. dq / dk are gradients with respect to the UN-rotated projections.
-int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* out, const float* out_f32,
-                      const void* dout, const float* lse2, float* delta, void* dq, void* dk, void* dv,
-                      int grad_dtype, int ldq, int ldk, int ldv, const float* rope_table, int rope_period,
-                      int n_rope_k, int B, int N, int M, float scale, cudaStream_t stream) {
+// dbias_q / dbias_k / dbias_v (optional, fp32 [256] each): the column sums of dq / dk / dv over all B x rows are ADDED
+// to them inside the gradient epilogues (fp32 atomics: summation order is not fixed) -- the bias gradients of the
+// q / k / v projections (transformer.py:220-222) without another pass over the gradient tensors.
+int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void* out, const float* out_f32,
+                         const void* dout, const float* lse2, float* delta, void* dq, void* dk, void* dv,
+                         int grad_dtype, int ldq, int ldk, int ldv, const float* rope_table, int rope_period,
+                         int n_rope_k, int B, int N, int M, float scale, float* dbias_q, float* dbias_k, float* dbias_v,
+                         cudaStream_t stream) {
   if (!q || !k || !v || (!out && !out_f32) || !dout || !lse2 || !delta || !dq || !dk || !dv || B <= 0 || N <= 0 || M <= 0 ||
       B > 65535 || !aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(dout) ||
       !aligned16(dq) || !aligned16(dk) || !aligned16(dv) || (grad_dtype != 0 && grad_dtype != 1) ||
@@ -298,7 +302,7 @@ int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* o
     attn::TwoGemmParams p{};
     p.La = M; p.Lx = N; p.scale_log2 = scale * kLog2e;
     p.lse2 = const_cast<float*>(lse2);
-    p.gout = attn::GradOut{grad_dtype, nullptr, 0, 1};
+    p.gout = attn::GradOut{grad_dtype, dbias_v, nullptr, 0, 1};
     p.tiles_per_split = (N + attn::kBlockN - 1) / attn::kBlockN;
     const size_t smem = sizeof(attn::SharedStorage) + 1024;
     if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_DV>, smem))) return rc;
@@ -313,7 +317,7 @@ int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* o
     attn::ThreeGemmParams p{};
     p.La = M; p.Lx = N; p.scale_log2 = scale * kLog2e; p.scale = scale;
     p.lse2 = lse2; p.delta = delta;
-    p.gout = attn::GradOut{grad_dtype, table, table ? n_rope_k : 0, table ? rope_period : 1};
+    p.gout = attn::GradOut{grad_dtype, dbias_k, table, table ? n_rope_k : 0, table ? rope_period : 1};
     if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DK>, smem3))) return rc;
     dim3 grid((M + attn::kBlockM - 1) / attn::kBlockM, B, 1);
     p.dbg = timeline_slice((size_t)grid.x * grid.y);
@@ -325,7 +329,7 @@ int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* o
     attn::ThreeGemmParams p{};
     p.La = N; p.Lx = M; p.scale_log2 = scale * kLog2e; p.scale = scale;
     p.lse2 = lse2; p.delta = delta;
-    p.gout = attn::GradOut{grad_dtype, table, table ? N : 0, table ? rope_period : 1};
+    p.gout = attn::GradOut{grad_dtype, dbias_q, table, table ? N : 0, table ? rope_period : 1};
     if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DQ>, smem3))) return rc;
     dim3 grid((N + attn::kBlockM - 1) / attn::kBlockM, B, 1);
     p.dbg = timeline_slice((size_t)grid.x * grid.y);
@@ -333,6 +337,14 @@ int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* o
     if ((rc = sam2b200::check_launch("attn_bwd dQ"))) return rc;
   }
   return SAM2B200_OK;
+}
+
+int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* out, const float* out_f32,
+                      const void* dout, const float* lse2, float* delta, void* dq, void* dk, void* dv,
+                      int grad_dtype, int ldq, int ldk, int ldv, const float* rope_table, int rope_period,
+                      int n_rope_k, int B, int N, int M, float scale, cudaStream_t stream) {
+  return sam2b200_attn_bwd_ex(q, k, v, out, out_f32, dout, lse2, delta, dq, dk, dv, grad_dtype, ldq, ldk, ldv, rope_table,
+                              rope_period, n_rope_k, B, N, M, scale, nullptr, nullptr, nullptr, stream);
 }
 
 }  // extern "C"

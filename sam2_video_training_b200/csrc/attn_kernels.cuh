@@ -82,6 +82,9 @@ __device__ __forceinline__ unsigned smid() {
 // Optional fused epilogue for gradient outputs: conjugate axial rotation + bf16 store with a row stride.
 struct GradOut {
   int is_bf16;                 // element type of the output tensor map (bf16 or fp32)
+  float* bias_grad;            // [256] fp32 or nullptr: column sums of the (rotated-back, scaled) gradient rows are
+                               // ADDED here with red.global.add (the bias gradient of the projection that made
+                               // this operand) -- saves a separate pass over the gradient tensor
   const float2* rope_table;    // [period, 128] (cos, sin) or nullptr = no rotation
   int rope_rows;               // rows [0, rope_rows) of every batch item are un-rotated (conjugate)
   int rope_period;             // table row = row % rope_period
@@ -189,6 +192,35 @@ __device__ __forceinline__ void load_table_chunk(const GradOut& g, bool rotate, 
   }
 }
 
+// Column sums of a [32 rows (lanes) x 32 columns (v)] block: a 5-step butterfly in which every lane keeps the half
+// of the columns its lane bit selects; lane L ends up with the sum of column L.  31 shuffles per block.
+__device__ __forceinline__ float warp_column_sum32(const float* v, int lane) {
+  float a[16], b[8], c[4], d[2];
+  {
+    const bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { const float keep = hi ? v[i + 16] : v[i], send = hi ? v[i] : v[i + 16]; a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16); }
+  }
+  {
+    const bool hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float keep = hi ? a[i + 8] : a[i], send = hi ? a[i] : a[i + 8]; b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8); }
+  }
+  {
+    const bool hi = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float keep = hi ? b[i + 4] : b[i], send = hi ? b[i] : b[i + 4]; c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4); }
+  }
+  {
+    const bool hi = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { const float keep = hi ? c[i + 2] : c[i], send = hi ? c[i] : c[i + 2]; d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2); }
+  }
+  const bool hi = lane & 1;
+  const float keep = hi ? d[1] : d[0], send = hi ? d[0] : d[1];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
 // acc_addr: TMEM address of column 0 of this thread's accumulator row; half selects columns [128h, 128h+128).
 // stage: this warp's staging area (8 KB bf16 / 16 KB fp32); row0 = first row (in the batch item) of the warp.
 __device__ __forceinline__ void grad_epilogue(const GradOut& g, const CUtensorMap* map, uint32_t stage, uint32_t acc_addr,
@@ -218,6 +250,14 @@ __device__ __forceinline__ void grad_epilogue(const GradOut& g, const CUtensorMa
         const float im = v[2 * k + 1] * cs.x - v[2 * k] * cs.y;
         v[2 * k] = re; v[2 * k + 1] = im;
       }
+    }
+    if (g.bias_grad != nullptr) {
+      if (row_in_batch >= La) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = 0.f;        // rows beyond the tensor are clipped by the store, not by the sum
+      }
+      const float cs = warp_column_sum32(v, lane);
+      atomicAdd(g.bias_grad + cc * 32 + lane, cs);
     }
     if (g.is_bf16) {
       stage_chunk_bf16(stage, lane, i, v);

@@ -385,13 +385,15 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             dca = cast_colsum(g, gv[ix["ca.o.b"]])
             acc_w(ix["ca.o.w"], dca.t(), o2.view(r, d))
             do2 = torch.mm(dca, W["ca.o.w"])
+            # conjugate RoPE and the q / k / v bias gradients (column sums) are fused into the gradient epilogues
             dq2, dk2, dv2 = attn_bwd(q2_rot, k2_rot, v2.view(b, m, d), None, o2_32, do2.view(b, n, d), lse2, scale,
-                                     table=table, n_rope_k=n_rope_k, grad_dtype=BF16)   # conj. RoPE fused in epilogue
+                                     table=table, n_rope_k=n_rope_k, grad_dtype=BF16,
+                                     dbias=(gv[ix["ca.q.b"]], gv[ix["ca.k.b"]], gv[ix["ca.v.b"]]))
             dq2, dk2, dv2 = dq2.view(r, d), dk2.view(rm, d), dv2.view(rm, d)
             dy2 = torch.mm(dq2, W["ca.q.w"])
-            acc_w(ix["ca.q.w"], dq2.t(), y2, gv[ix["ca.q.b"]])
-            acc_w(ix["ca.k.w"], dk2.t(), memk, gv[ix["ca.k.b"]])
-            acc_w(ix["ca.v.w"], dv2.t(), memv, gv[ix["ca.v.b"]])
+            acc_w(ix["ca.q.w"], dq2.t(), y2)
+            acc_w(ix["ca.k.w"], dk2.t(), memk)
+            acc_w(ix["ca.v.w"], dv2.t(), memv)
 
             def mem_grads(dk2=dk2, dv2=dv2, wk=W["ca.k.w"], wv=W["ca.v.w"]):
                 if need_memgrad:
@@ -407,29 +409,18 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             do = torch.mm(dsa, W["sa.o.w"])
             dqkv = torch.empty((b, n, 3 * d), dtype=BF16, device=dev)   # [dq | dk | dv], written in place by the kernels
             attn_bwd(q_rot, k_rot, v.view(b, n, d), None, o32, do.view(b, n, d), lse, scale, table=table, n_rope_k=n,
-                     grad_dtype=BF16, dq=dqkv[:, :, :d], dk=dqkv[:, :, d:2 * d], dv=dqkv[:, :, 2 * d:])
+                     grad_dtype=BF16, dq=dqkv[:, :, :d], dk=dqkv[:, :, d:2 * d], dv=dqkv[:, :, 2 * d:],
+                     dbias=(gv[ix["sa.q.b"]], gv[ix["sa.k.b"]], gv[ix["sa.v.b"]]))
             dqkv = dqkv.view(r, 3 * d)
             qkv_w = [masters[ix[k]] for k in ("sa.q.w", "sa.k.w", "sa.v.w")]
-            qkv_b = [masters[ix[k]] for k in ("sa.q.b", "sa.k.b", "sa.v.b")]
             gw = bucket.span(qkv_w, (3 * d, d)) if direct else None
-            gb = bucket.span(qkv_b, (3 * d,)) if direct else None
-            if gw is not None and gb is not None:
-                # the bucket lays the three projections out back to back: one colsum, one [768, 256] GEMM
-                def qkv_grads(dqkv=dqkv, y1=y1, gw=gw, gb=gb):
-                    colsum_bf16(dqkv, gb)
-                    torch.addmm(gw, dqkv.t(), y1, out_dtype=F32, out=gw)
-                side.run(qkv_grads, dqkv, y1)
+            if gw is not None:
+                # the bucket lays the three projection weights out back to back: one [768, 256] weight-gradient GEMM
+                side.run(lambda dqkv=dqkv, y1=y1, gw=gw: torch.addmm(gw, dqkv.t(), y1, out_dtype=F32, out=gw), dqkv, y1)
             elif direct:
-                for j, (kw, kb) in enumerate((("sa.q.w", "sa.q.b"), ("sa.k.w", "sa.k.b"), ("sa.v.w", "sa.v.b"))):
-                    part = dqkv[:, j * d:(j + 1) * d]
-                    bsum = torch.zeros(d, dtype=F32, device=dev)
-                    colsum_bf16(part.contiguous(), bsum)
-                    gv[ix[kb]].add_(bsum)
-                    acc_w(ix[kw], part.t(), y1)
+                for j, kw in enumerate(("sa.q.w", "sa.k.w", "sa.v.w")):
+                    acc_w(ix[kw], dqkv[:, j * d:(j + 1) * d].t(), y1)
             else:
-                bsum = torch.zeros(3 * d, dtype=F32, device=dev)
-                colsum_bf16(dqkv, bsum)
-                grads[ix["sa.q.b"]], grads[ix["sa.k.b"]], grads[ix["sa.v.b"]] = bsum[:d], bsum[d:2 * d], bsum[2 * d:]
                 dw = _mm32(dqkv.t(), y1)                     # [768, 256] = d(Wq | Wk | Wv) in one GEMM
                 grads[ix["sa.q.w"]], grads[ix["sa.k.w"]], grads[ix["sa.v.w"]] = dw[:d], dw[d:2 * d], dw[2 * d:]
             dy1 = torch.mm(dqkv, wqkv_all[l])            # stacked [768, 256] weights: contraction over 768, fp32 accumulation

@@ -80,9 +80,10 @@ def attn_fwd(q, k, v, scale: float, nsplit: int = 0, keep_f32: bool = True):
 
 
 def attn_bwd(q, k, v, out, out32, dout, lse2, scale: float, table=None, n_rope_k: int = 0, grad_dtype=torch.float32,
-             dq=None, dk=None, dv=None):
+             dq=None, dk=None, dv=None, dbias=(None, None, None)):
     """Backward of the attention core.  With `table` the conjugate RoPE is fused into the epilogue (dq / dk are then
-    gradients w.r.t. the un-rotated projections).  dq / dk / dv may be preallocated 2-D/3-D views whose last dim is
+    gradients w.r.t. the un-rotated projections).  dbias = (dbq, dbk, dbv): optional fp32 [256] tensors the column sums
+    of dq / dk / dv are ADDED to (bias gradients of the projections; fp32 atomics).  dq / dk / dv may be preallocated 2-D/3-D views whose last dim is
     contiguous (row stride = .stride(-2)), e.g. column slices of one [R, 768] buffer."""
     lib = _lib.load()
     b, n, _ = q.shape
@@ -98,14 +99,17 @@ def attn_bwd(q, k, v, out, out32, dout, lse2, scale: float, table=None, n_rope_k
         assert t_.dtype == grad_dtype and t_.stride(-1) == 1
     delta = torch.empty((b, n), dtype=torch.float32, device=dev)
     with _Timed("attn_bwd", 10.0 * b * n * m * 256):
-        rc = lib.sam2b200_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr() if out is not None else None,
+        for t_ in dbias:
+            assert t_ is None or (t_.dtype == torch.float32 and t_.numel() == 256 and t_.is_contiguous())
+        rc = lib.sam2b200_attn_bwd_ex(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr() if out is not None else None,
                                    out32.data_ptr() if out32 is not None else None, dout.data_ptr(),
                                    lse2.data_ptr(), delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
                                    _DT[grad_dtype], dq.stride(-2), dk.stride(-2), dv.stride(-2),
                                    table.data_ptr() if table is not None else None,
                                    table.shape[0] if table is not None else 0, n_rope_k,
-                                   b, n, m, scale, _stream(dev))
-    _lib.check(rc, "sam2b200_attn_bwd")
+                                   b, n, m, scale, *[t_.data_ptr() if t_ is not None else None for t_ in dbias],
+                                   _stream(dev))
+    _lib.check(rc, "sam2b200_attn_bwd_ex")
     return dq, dk, dv
 
 

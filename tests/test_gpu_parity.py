@@ -475,3 +475,28 @@ def test_functional_losses_match_reference_formulas(dev, multimask):
         assert rel_l2(o.detach().cpu().double(), r.detach()) < 1e-5
     assert rel_l2(xg.grad.cpu().double(), x.grad) < 1e-5
     assert rel_l2(ig.grad.cpu().double(), iou.grad) < 1e-5
+
+
+def test_attention_backward_fused_bias_gradients(dev):
+    """sam2b200_attn_bwd_ex: the q / k / v bias gradients (column sums of dq / dk / dv over all rows, after the
+    conjugate rotation) are accumulated inside the gradient epilogues -- ragged sizes, bf16 and fp32 outputs."""
+    from sam2_video_training_b200 import ops
+    from sam2_video_training_b200.modeling.position_encoding import compute_axial_cis
+    g = torch.Generator(device="cuda").manual_seed(9)
+    grid, b, nptr = 12, 3, 8                       # N = 144 (not a multiple of 128), M = 2 N + 8
+    n, m = grid * grid, 2 * grid * grid + nptr
+    table = compute_axial_cis(dim=256, end_x=grid, end_y=grid).to(dev)
+    q = (torch.randn(b, n, 256, device=dev, generator=g)).to(torch.bfloat16)
+    k = (torch.randn(b, m, 256, device=dev, generator=g)).to(torch.bfloat16)
+    v = torch.randn(b, m, 256, device=dev, generator=g).to(torch.bfloat16)
+    do = torch.randn(b, n, 256, device=dev, generator=g).to(torch.bfloat16)
+    o, o32, lse = ops.attn_fwd(q, k, v, 1 / 16.0)
+    for gdt in (torch.float32, torch.bfloat16):
+        db = [torch.full((256,), 0.5, device=dev) for _ in range(3)]      # accumulate on top of existing content
+        dq, dk, dv = ops.attn_bwd(q, k, v, None, o32, do, lse, 1 / 16.0, table=table, n_rope_k=m - nptr, grad_dtype=gdt,
+                                  dbias=tuple(db))
+        dq0, dk0, dv0 = ops.attn_bwd(q, k, v, None, o32, do, lse, 1 / 16.0, table=table, n_rope_k=m - nptr, grad_dtype=torch.float32)
+        for got, ref, name in zip(db, (dq0, dk0, dv0), "qkv"):
+            want = ref.double().sum(dim=(0, 1)) + 0.5
+            assert rel_l2(got.double(), want) < (2e-3 if gdt == torch.bfloat16 else 1e-5), (name, gdt)
+        assert rel_l2(dq.float(), dq0) < 6e-3 and rel_l2(dk.float(), dk0) < 6e-3 and rel_l2(dv.float(), dv0) < 6e-3

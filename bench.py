@@ -397,6 +397,10 @@ def main():
 
     # ---------------- same steps, every kernel launched from the host, CUDA events around each kernel family
     # (events cannot be timed inside a replayed graph): feeds `roofline` and `kernel_families_ms_per_step`
+    # (single stream here: with the side stream the key-side attention kernels overlap other work and an event pair
+    # around one kernel would also time its neighbours)
+    from sam2_video_training_b200 import fused_stack
+    fused_stack.NO_SIDE_STREAM = True
     run_step(model, crit, opt, d, banks, wl, world)
     barrier()
     launches_e0 = lib.sam2b200_launch_count()
@@ -408,6 +412,7 @@ def main():
     barrier()
     prof = ops.PROFILE
     ops.PROFILE = None
+    fused_stack.NO_SIDE_STREAM = bool(os.environ.get("SAM2B200_NO_SIDE_STREAM"))
     eager_ms_per_step = ev0.elapsed_time(ev1) / args.steps
     launches_eager = lib.sam2b200_launch_count() - launches_e0
     if args.no_graphs:

@@ -78,12 +78,14 @@ int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* o
 
 /* Same, plus the bias gradients of the q / k / v projections (transformer.py:220-222): if non-NULL, the column sums of
  * dq / dk / dv over all B x rows are ADDED to dbias_q / dbias_k / dbias_v (fp32 [256] each) inside the gradient
- * epilogues with fp32 atomics (summation order not fixed), instead of another pass over the gradient tensors. */
+ * epilogues with fp32 atomics (summation order not fixed), instead of another pass over the gradient tensors.
+ * parts: bit mask of the kernels to launch (0 = all): 1 Delta, 2 dV, 4 dK, 8 dQ (dK and dQ read Delta), so that the
+ * key-side kernels can be enqueued on a second stream. */
 int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void* out, const float* out_f32,
                          const void* dout, const float* lse2, float* delta, void* dq, void* dk, void* dv,
                          int grad_dtype, int ldq, int ldk, int ldv, const float* rope_table, int rope_period,
                          int n_rope_k, int B, int N, int M, float scale, float* dbias_q, float* dbias_k, float* dbias_v,
-                         sam2b200_stream_t stream);
+                         int parts, sam2b200_stream_t stream);
 
 /* ---- fused LayerNorm / residual / bias-gradient kernels (d_model = 256) -------------------
  * Replace nn.LayerNorm + residual add + dropout(0) + dtype casts of MemoryAttentionLayer

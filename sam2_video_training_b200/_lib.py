@@ -32,7 +32,7 @@ _SIGNATURES = {
     "sam2b200_attn_bwd": (c_int, [c_void_p] * 11 + [c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
                                                    c_int, c_int, c_int, c_float, c_void_p]),
     "sam2b200_attn_bwd_ex": (c_int, [c_void_p] * 11 + [c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
-                                                      c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                                      c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "sam2b200_ln_fwd": (c_int, [c_void_p] * 9 + [c_longlong, c_float, c_int, c_int, c_void_p]),
     "sam2b200_ln_bwd_workspace_bytes": (c_size_t, [c_longlong]),
     "sam2b200_ln_bwd": (c_int, [c_void_p] * 11 + [c_longlong, c_int, c_int, c_void_p]),

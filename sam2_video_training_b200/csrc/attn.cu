@@ -268,8 +268,13 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
                          const void* dout, const float* lse2, float* delta, void* dq, void* dk, void* dv,
                          int grad_dtype, int ldq, int ldk, int ldv, const float* rope_table, int rope_period,
                          int n_rope_k, int B, int N, int M, float scale, float* dbias_q, float* dbias_k, float* dbias_v,
-                         cudaStream_t stream) {
-  if (!q || !k || !v || (!out && !out_f32) || !dout || !lse2 || !delta || !dq || !dk || !dv || B <= 0 || N <= 0 || M <= 0 ||
+                         int parts, cudaStream_t stream) {
+  // parts: bit mask of the kernels to launch (0 = all): 1 Delta = rowsum(dO o O), 2 dV, 4 dK, 8 dQ.  dK and dQ need Delta.
+  // Lets the caller put the key-side kernels of the cross-attention (whose results only feed weight / memory-bank
+  // gradients) on a second stream, off the critical path of the residual-stream gradient.
+  if (parts == 0) parts = 15;
+  if (!q || !k || !v || (!out && !out_f32) || !dout || !lse2 || !delta || ((parts & 8) && !dq) || ((parts & 4) && !dk) ||
+      ((parts & 2) && !dv) || B <= 0 || N <= 0 || M <= 0 ||
       B > 65535 || !aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(dout) ||
       !aligned16(dq) || !aligned16(dk) || !aligned16(dv) || (grad_dtype != 0 && grad_dtype != 1) ||
       ldq < 256 || ldk < 256 || ldv < 256 || (ldq % 8) || (ldk % 8) || (ldv % 8) ||
@@ -277,18 +282,20 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
     return sam2b200::fail(SAM2B200_ERR_INVALID, "attn_bwd: bad arguments");
   int rc;
   const long long rows = (long long)B * N;
-  if (out_f32 != nullptr)
-    delta_kernel<true><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, stream>>>(out_f32, (const __nv_bfloat16*)dout, delta, rows);
-  else
-    delta_kernel<false><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, stream>>>(out, (const __nv_bfloat16*)dout, delta, rows);
-  if ((rc = sam2b200::check_launch("attn_bwd delta"))) return rc;
+  if (parts & 1) {
+    if (out_f32 != nullptr)
+      delta_kernel<true><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, stream>>>(out_f32, (const __nv_bfloat16*)dout, delta, rows);
+    else
+      delta_kernel<false><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, stream>>>(out, (const __nv_bfloat16*)dout, delta, rows);
+    if ((rc = sam2b200::check_launch("attn_bwd delta"))) return rc;
+  }
 
   CUtensorMap map_q64, map_k64, map_v64, map_do64, map_do128, map_v128, map_q128, map_k128, map_dq, map_dk, map_dv;
   if ((rc = sam2b200::make_rows256_map(&map_q128, q, B, N, attn::kBlockM))) return rc;
   if ((rc = sam2b200::make_rows256_map(&map_k128, k, B, M, attn::kBlockM))) return rc;
-  if ((rc = sam2b200::make_out_map(&map_dq, dq, grad_dtype, B, N, ldq, 32))) return rc;
-  if ((rc = sam2b200::make_out_map(&map_dk, dk, grad_dtype, B, M, ldk, 32))) return rc;
-  if ((rc = sam2b200::make_out_map(&map_dv, dv, grad_dtype, B, M, ldv, 32))) return rc;
+  if ((parts & 8) && (rc = sam2b200::make_out_map(&map_dq, dq, grad_dtype, B, N, ldq, 32))) return rc;
+  if ((parts & 4) && (rc = sam2b200::make_out_map(&map_dk, dk, grad_dtype, B, M, ldk, 32))) return rc;
+  if ((parts & 2) && (rc = sam2b200::make_out_map(&map_dv, dv, grad_dtype, B, M, ldv, 32))) return rc;
   if ((rc = sam2b200::make_rows256_map(&map_q64, q, B, N, attn::kBlockN))) return rc;
   if ((rc = sam2b200::make_rows256_map(&map_k64, k, B, M, attn::kBlockN))) return rc;
   if ((rc = sam2b200::make_rows256_map(&map_v64, v, B, M, attn::kBlockN))) return rc;
@@ -298,7 +305,7 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
   const float2* table = reinterpret_cast<const float2*>(rope_table);
 
   // dV = P^T dO: fixed K block, stream (Q, dO) tiles
-  {
+  if (parts & 2) {
     attn::TwoGemmParams p{};
     p.La = M; p.Lx = N; p.scale_log2 = scale * kLog2e;
     p.lse2 = const_cast<float*>(lse2);
@@ -313,7 +320,7 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
   }
   const size_t smem3 = sizeof(attn::SharedStorage3) + 1024;
   // dK = scale * dS^T Q: fixed (K in TMEM, V in SMEM), stream (Q, dO) tiles
-  {
+  if (parts & 4) {
     attn::ThreeGemmParams p{};
     p.La = M; p.Lx = N; p.scale_log2 = scale * kLog2e; p.scale = scale;
     p.lse2 = lse2; p.delta = delta;
@@ -325,7 +332,7 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
     if ((rc = sam2b200::check_launch("attn_bwd dK"))) return rc;
   }
   // dQ = scale * dS K: fixed (Q in TMEM, dO in SMEM), stream (K, V) tiles
-  {
+  if (parts & 8) {
     attn::ThreeGemmParams p{};
     p.La = N; p.Lx = M; p.scale_log2 = scale * kLog2e; p.scale = scale;
     p.lse2 = lse2; p.delta = delta;
@@ -344,7 +351,7 @@ int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* o
                       int grad_dtype, int ldq, int ldk, int ldv, const float* rope_table, int rope_period,
                       int n_rope_k, int B, int N, int M, float scale, cudaStream_t stream) {
   return sam2b200_attn_bwd_ex(q, k, v, out, out_f32, dout, lse2, delta, dq, dk, dv, grad_dtype, ldq, ldk, ldv, rope_table,
-                              rope_period, n_rope_k, B, N, M, scale, nullptr, nullptr, nullptr, stream);
+                              rope_period, n_rope_k, B, N, M, scale, nullptr, nullptr, nullptr, 0, stream);
 }
 
 }  // extern "C"

@@ -385,23 +385,32 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             dca = cast_colsum(g, gv[ix["ca.o.b"]])
             acc_w(ix["ca.o.w"], dca.t(), o2.view(r, d))
             do2 = torch.mm(dca, W["ca.o.w"])
-            # conjugate RoPE and the q / k / v bias gradients (column sums) are fused into the gradient epilogues
-            dq2, dk2, dv2 = attn_bwd(q2_rot, k2_rot, v2.view(b, m, d), None, o2_32, do2.view(b, n, d), lse2, scale,
-                                     table=table, n_rope_k=n_rope_k, grad_dtype=BF16,
-                                     dbias=(gv[ix["ca.q.b"]], gv[ix["ca.k.b"]], gv[ix["ca.v.b"]]))
-            dq2, dk2, dv2 = dq2.view(r, d), dk2.view(rm, d), dv2.view(rm, d)
+            # conjugate RoPE and the q / k / v bias gradients (column sums) are fused into the gradient epilogues.
+            # Only dQ is on the path of the residual-stream gradient: the key-side kernels (dV, dK) and everything
+            # they feed (weight gradients, memory-bank gradients) go to the side stream.
+            delta = torch.empty((b, n), dtype=F32, device=dev)
+            args = (q2_rot, k2_rot, v2.view(b, m, d), None, o2_32, do2.view(b, n, d), lse2, scale)
+            kw = dict(table=table, n_rope_k=n_rope_k, grad_dtype=BF16, delta=delta)
+            attn_bwd(*args, parts=1, **kw)                                              # Delta = rowsum(dO o O)
+
+            def key_side(args=args, kw=kw, l=l, ix=ix, W=W):
+                _, dk2, dv2 = attn_bwd(*args, parts=2 | 4, dbias=(None, gv[ix["ca.k.b"]], gv[ix["ca.v.b"]]), **kw)
+                dk2, dv2 = dk2.view(rm, d), dv2.view(rm, d)
+                if direct:
+                    torch.addmm(gv[ix["ca.k.w"]], dk2.t(), memk, out_dtype=F32, out=gv[ix["ca.k.w"]])
+                    torch.addmm(gv[ix["ca.v.w"]], dv2.t(), memv, out_dtype=F32, out=gv[ix["ca.v.w"]])
+                else:
+                    grads[ix["ca.k.w"]] = _mm32(dk2.t(), memk)
+                    grads[ix["ca.v.w"]] = _mm32(dv2.t(), memv)
+                if need_memgrad:
+                    torch.addmm(dmemk, dk2, W["ca.k.w"], out_dtype=F32, out=dmemk)
+                if need_mem:
+                    torch.addmm(dmemv, dv2, W["ca.v.w"], out_dtype=F32, out=dmemv)
+            side.run(key_side, *args[:3], o2_32, do2, lse2, delta)
+            dq2, _, _ = attn_bwd(*args, parts=8, dbias=(gv[ix["ca.q.b"]], None, None), **kw)
+            dq2 = dq2.view(r, d)
             dy2 = torch.mm(dq2, W["ca.q.w"])
             acc_w(ix["ca.q.w"], dq2.t(), y2)
-            acc_w(ix["ca.k.w"], dk2.t(), memk)
-            acc_w(ix["ca.v.w"], dv2.t(), memv)
-
-            def mem_grads(dk2=dk2, dv2=dv2, wk=W["ca.k.w"], wv=W["ca.v.w"]):
-                if need_memgrad:
-                    torch.addmm(dmemk, dk2, wk, out_dtype=F32, out=dmemk)
-                if need_mem:
-                    torch.addmm(dmemv, dv2, wv, out_dtype=F32, out=dmemv)
-            if need_memgrad or need_mem:
-                side.run(mem_grads, dk2, dv2)
             g = ln_bwd(dy2, x1, mean2, rstd2, P["n2.w"], g, gv[ix["n2.w"]], gv[ix["n2.b"]])
             # ---- self attention backward
             dsa = cast_colsum(g, gv[ix["sa.o.b"]])

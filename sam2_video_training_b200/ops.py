@@ -80,7 +80,7 @@ def attn_fwd(q, k, v, scale: float, nsplit: int = 0, keep_f32: bool = True):
 
 
 def attn_bwd(q, k, v, out, out32, dout, lse2, scale: float, table=None, n_rope_k: int = 0, grad_dtype=torch.float32,
-             dq=None, dk=None, dv=None, dbias=(None, None, None)):
+             dq=None, dk=None, dv=None, dbias=(None, None, None), parts: int = 0, delta=None):
     """Backward of the attention core.  With `table` the conjugate RoPE is fused into the epilogue (dq / dk are then
     gradients w.r.t. the un-rotated projections).  dbias = (dbq, dbk, dbv): optional fp32 [256] tensors the column sums
     of dq / dk / dv are ADDED to (bias gradients of the projections; fp32 atomics).  dq / dk / dv may be preallocated 2-D/3-D views whose last dim is
@@ -89,26 +89,31 @@ def attn_bwd(q, k, v, out, out32, dout, lse2, scale: float, table=None, n_rope_k
     b, n, _ = q.shape
     m = k.shape[1]
     dev = q.device
-    if dq is None:
+    need = (lambda bit: parts == 0 or bool(parts & bit))
+    if dq is None and need(8):
         dq = torch.empty((b, n, 256), dtype=grad_dtype, device=dev)
-    if dk is None:
+    if dk is None and need(4):
         dk = torch.empty((b, m, 256), dtype=grad_dtype, device=dev)
-    if dv is None:
+    if dv is None and need(2):
         dv = torch.empty((b, m, 256), dtype=grad_dtype, device=dev)
     for t_ in (dq, dk, dv):
-        assert t_.dtype == grad_dtype and t_.stride(-1) == 1
-    delta = torch.empty((b, n), dtype=torch.float32, device=dev)
-    with _Timed("attn_bwd", 10.0 * b * n * m * 256):
+        assert t_ is None or (t_.dtype == grad_dtype and t_.stride(-1) == 1)
+    if delta is None:
+        delta = torch.empty((b, n), dtype=torch.float32, device=dev)
+    # parts (bit mask, 0 = all): 1 Delta, 2 dV, 4 dK, 8 dQ; algorithmic FLOPs: dV 2 GEMMs... counted as 4 / 4 / 2 of the 10 N M d
+    work = 10.0 * b * n * m * 256 * ((4 if parts in (0,) or parts & 8 else 0) + (2 if parts in (0,) or parts & 2 else 0)
+                                     + (4 if parts in (0,) or parts & 4 else 0)) / 10.0
+    with _Timed("attn_bwd", work):
         for t_ in dbias:
             assert t_ is None or (t_.dtype == torch.float32 and t_.numel() == 256 and t_.is_contiguous())
         rc = lib.sam2b200_attn_bwd_ex(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr() if out is not None else None,
                                    out32.data_ptr() if out32 is not None else None, dout.data_ptr(),
-                                   lse2.data_ptr(), delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
-                                   _DT[grad_dtype], dq.stride(-2), dk.stride(-2), dv.stride(-2),
+                                   lse2.data_ptr(), delta.data_ptr(), *[t_.data_ptr() if t_ is not None else None for t_ in (dq, dk, dv)],
+                                   _DT[grad_dtype], *[t_.stride(-2) if t_ is not None else 256 for t_ in (dq, dk, dv)],
                                    table.data_ptr() if table is not None else None,
                                    table.shape[0] if table is not None else 0, n_rope_k,
                                    b, n, m, scale, *[t_.data_ptr() if t_ is not None else None for t_ in dbias],
-                                   _stream(dev))
+                                   int(parts), _stream(dev))
     _lib.check(rc, "sam2b200_attn_bwd_ex")
     return dq, dk, dv
 

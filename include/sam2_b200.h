@@ -97,10 +97,12 @@ int sam2b200_ln_fwd(const float* x, const void* res_bf16, float* x_out, const fl
                     void* y_bf16, float* y_f32, float* mean, float* rstd, long long rows, float eps, int tr_b,
                     int tr_n, sam2b200_stream_t stream);
 size_t sam2b200_ln_bwd_workspace_bytes(long long rows);
-/* g_out = g_in + dLN/dx(dy); dgamma += sum dy*xhat; dbeta += sum dy.  Exactly one of dy_bf16 / dy_f32. */
+/* g_out = g_in + dLN/dx(dy); dgamma += sum dy*xhat; dbeta += sum dy.  Exactly one of dy_bf16 / dy_f32.
+ * g_out_bf16 + dbias (optional, both or neither): bf16 copy of g_out (operand of the next GEMMs of the backward) and
+ * dbias += its column sums (bias gradient of the projection whose output gradient g_out is). */
 int sam2b200_ln_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* mean, const float* rstd,
-                    const float* gamma, const float* g_in, float* g_out, float* dgamma, float* dbeta,
-                    void* workspace, long long rows, int tr_b, int tr_n, sam2b200_stream_t stream);
+                    const float* gamma, const float* g_in, float* g_out, void* g_out_bf16, float* dgamma, float* dbeta,
+                    float* dbias, void* workspace, long long rows, int tr_b, int tr_n, sam2b200_stream_t stream);
 size_t sam2b200_colsum_workspace_bytes(long long rows, int C);
 /* Bias gradients (what autograd's sum over rows produces for nn.Linear):
  * mode 0: in_f32 [R,C] -> io_bf16 (cast) and colsum += column sums; mode 1: io_bf16 *= (h_bf16 > 0) in

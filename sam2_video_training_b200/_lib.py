@@ -35,7 +35,7 @@ _SIGNATURES = {
                                                       c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "sam2b200_ln_fwd": (c_int, [c_void_p] * 9 + [c_longlong, c_float, c_int, c_int, c_void_p]),
     "sam2b200_ln_bwd_workspace_bytes": (c_size_t, [c_longlong]),
-    "sam2b200_ln_bwd": (c_int, [c_void_p] * 11 + [c_longlong, c_int, c_int, c_void_p]),
+    "sam2b200_ln_bwd": (c_int, [c_void_p] * 13 + [c_longlong, c_int, c_int, c_void_p]),
     "sam2b200_colsum_workspace_bytes": (c_size_t, [c_longlong, c_int]),
     "sam2b200_colsum": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int,
                                 c_longlong, c_void_p]),

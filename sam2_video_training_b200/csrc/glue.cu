@@ -98,15 +98,18 @@ ln_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ res
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ dy32, const float* __restrict__ x,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
-              const float* __restrict__ g_in, float* __restrict__ g_out, float* __restrict__ part, long long rows,
-              int tr_b, int tr_n) {
+              const float* __restrict__ g_in, float* __restrict__ g_out, __nv_bfloat16* __restrict__ g16,
+              float* __restrict__ part, long long rows, int tr_b, int tr_n) {
+  // g16 (optional): bf16 copy of g_out -- the operand of the next GEMMs of the backward chain -- and a third partial
+  // row with its column sums (the bias gradient of the projection whose output gradient g_out is).
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float4* gp = reinterpret_cast<const float4*>(gamma + lane * 8);
   const float4 g0 = gp[0], g1 = gp[1];
   const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-  float dgam[8], dbet[8];
+  float dgam[8], dbet[8], dbias[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { dgam[i] = 0.f; dbet[i] = 0.f; }
+  for (int i = 0; i < 8; ++i) { dgam[i] = 0.f; dbet[i] = 0.f; dbias[i] = 0.f; }
+  const int nrow = (g16 != nullptr) ? 3 : 2;
   const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
   for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp; row < rows; row += warps_total) {
     float dy[8], xv[8];
@@ -145,25 +148,34 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ 
     float4* op = reinterpret_cast<float4*>(g_out + row * kD + lane * 8);
     op[0] = make_float4(o[0], o[1], o[2], o[3]);
     op[1] = make_float4(o[4], o[5], o[6], o[7]);
-  }
-  __shared__ float sh[8][2][kD];
+    if (g16 != nullptr) {
+      const uint4 u = pack8(o);
+      *reinterpret_cast<uint4*>(g16 + row * kD + lane * 8) = u;
+      float r[8];
+      unpack8(u, r);                                  // sum what the consumer GEMM will see (the bf16-rounded values)
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { sh[warp][0][lane * 8 + i] = dgam[i]; sh[warp][1][lane * 8 + i] = dbet[i]; }
+      for (int i = 0; i < 8; ++i) dbias[i] += r[i];
+    }
+  }
+  __shared__ float sh[8][3][kD];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sh[warp][0][lane * 8 + i] = dgam[i]; sh[warp][1][lane * 8 + i] = dbet[i]; sh[warp][2][lane * 8 + i] = dbias[i]; }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * kD; i += blockDim.x) {
+  for (int i = threadIdx.x; i < nrow * kD; i += blockDim.x) {
     const int which = i / kD, c = i % kD;
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += sh[w][which][c];
-    part[((long long)blockIdx.x * 2 + which) * kD + c] = s;
+    part[((long long)blockIdx.x * nrow + which) * kD + c] = s;
   }
 }
 
 // out[c] += sum_blk part[blk][c]   (fixed order -> deterministic).  32 columns x 8 block-groups per CTA.
 __global__ void __launch_bounds__(256)
 partial_reduce_add_kernel(const float* __restrict__ part, int nblk, int width, float* __restrict__ out0,
-                          float* __restrict__ out1, int split) {
-  // part: [nblk][width]; columns [0, split) go to out0, [split, width) to out1 (LN: gamma | beta)
+                          float* __restrict__ out1, int split, float* __restrict__ out2 = nullptr) {
+  // part: [nblk][width]; columns [0, split) go to out0, [split, 2 split) to out1, [2 split, width) to out2
+  // (LN: gamma | beta | bias of the next projection)
   __shared__ float sh[8][32];
   const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
@@ -176,7 +188,7 @@ partial_reduce_add_kernel(const float* __restrict__ part, int nblk, int width, f
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += sh[i][cl];
-    if (c < split) out0[c] += t; else out1[c - split] += t;
+    if (c < split) out0[c] += t; else if (c < 2 * split || out2 == nullptr) out1[c - split] += t; else out2[c - 2 * split] += t;
   }
 }
 
@@ -266,22 +278,24 @@ int sam2b200_ln_fwd(const float* x, const void* res_bf16, float* x_out, const fl
 }
 
 size_t sam2b200_ln_bwd_workspace_bytes(long long rows) {
-  return (size_t)grid_for_rows(rows, 8 * 8) * 2 * kD * sizeof(float);
+  return (size_t)grid_for_rows(rows, 8 * 8) * 3 * kD * sizeof(float);
 }
 
 // g_out = g_in + dLN/dx; dgamma += ..., dbeta += ... (accumulated into the given fp32 buffers).
 // Exactly one of dy_bf16 / dy_f32 is non-NULL.
+// g_out_bf16 / dbias (optional, both or neither): bf16 copy of g_out for the next GEMMs and dbias += its column sums.
 int sam2b200_ln_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* mean, const float* rstd,
-                    const float* gamma, const float* g_in, float* g_out, float* dgamma, float* dbeta,
-                    void* workspace, long long rows, int tr_b, int tr_n, cudaStream_t stream) {
+                    const float* gamma, const float* g_in, float* g_out, void* g_out_bf16, float* dgamma, float* dbeta,
+                    float* dbias, void* workspace, long long rows, int tr_b, int tr_n, cudaStream_t stream) {
   if ((!dy_bf16) == (!dy_f32) || !x || !mean || !rstd || !gamma || !g_out || !dgamma || !dbeta || !workspace ||
-      rows <= 0)
+      rows <= 0 || (!g_out_bf16) != (!dbias))
     return sam2b200::fail(SAM2B200_ERR_INVALID, "ln_bwd: bad arguments");
   const int nblk = grid_for_rows(rows, 8 * 8);
+  const int nrow = g_out_bf16 ? 3 : 2;
   float* part = static_cast<float*>(workspace);
   ln_bwd_kernel<<<nblk, 256, 0, stream>>>((const __nv_bfloat16*)dy_bf16, dy_f32, x, mean, rstd, gamma, g_in, g_out,
-                                          part, rows, tr_b, tr_n);
-  partial_reduce_add_kernel<<<(2 * kD + 31) / 32, 256, 0, stream>>>(part, nblk, 2 * kD, dgamma, dbeta, kD);
+                                          (__nv_bfloat16*)g_out_bf16, part, rows, tr_b, tr_n);
+  partial_reduce_add_kernel<<<(nrow * kD + 31) / 32, 256, 0, stream>>>(part, nblk, nrow * kD, dgamma, dbeta, kD, dbias);
   return sam2b200::check_launch("ln_bwd", 2);
 }
 

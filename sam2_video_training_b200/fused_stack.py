@@ -62,20 +62,23 @@ def ln_fwd(x, res, gamma, beta, want_f32_seq_first=None, eps=1e-5):
     return y, x_new, mean, rstd
 
 
-def ln_bwd(dy, x, mean, rstd, gamma, g_in, dgamma, dbeta, seq_first=None):
+def ln_bwd(dy, x, mean, rstd, gamma, g_in, dgamma, dbeta, seq_first=None, dbias=None):
+    """Returns g_out (fp32) or, with dbias, (g_out, bf16 copy of g_out) and dbias += column sums of the copy."""
     lib = _lib.load()
     rows = x.shape[0]
     dev = x.device
     g_out = torch.empty_like(x)
+    g16 = torch.empty(x.shape, dtype=BF16, device=dev) if dbias is not None else None
     ws = torch.empty(lib.sam2b200_ln_bwd_workspace_bytes(rows) // 4, dtype=F32, device=dev)
     tb, tn = seq_first if seq_first is not None else (0, 0)
     is16 = dy.dtype == BF16
     rc = lib.sam2b200_ln_bwd(dy.data_ptr() if is16 else None, None if is16 else dy.data_ptr(), x.data_ptr(),
                              mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
-                             g_in.data_ptr() if g_in is not None else None, g_out.data_ptr(), dgamma.data_ptr(),
-                             dbeta.data_ptr(), ws.data_ptr(), rows, tb, tn, _stream(dev))
+                             g_in.data_ptr() if g_in is not None else None, g_out.data_ptr(),
+                             g16.data_ptr() if g16 is not None else None, dgamma.data_ptr(), dbeta.data_ptr(),
+                             dbias.data_ptr() if dbias is not None else None, ws.data_ptr(), rows, tb, tn, _stream(dev))
     _lib.check(rc, "sam2b200_ln_bwd")
-    return g_out
+    return g_out if dbias is None else (g_out, g16)
 
 
 def _colsum(mode, in32, io16, h16, colsum, rows, c, ld=0):
@@ -361,8 +364,11 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                     grads[i] = _mm32(a_t, bmat)
             side.run(work, a_t, bmat)
         grad_out = grad_out.contiguous().float()
-        g = ln_bwd(grad_out, x_fin, mean_f, rstd_f, params[nl * _NPL], None, gv[nl * _NPL], gv[nl * _NPL + 1],
-                   seq_first=(b, n))
+        # every LayerNorm backward also emits the bf16 copy of its output gradient (operand of the next GEMMs) and the
+        # bias gradient of the projection in front of it: no separate cast + column-sum pass
+        last = (nl - 1) * _NPL
+        g, g16 = ln_bwd(grad_out, x_fin, mean_f, rstd_f, params[nl * _NPL], None, gv[nl * _NPL], gv[nl * _NPL + 1],
+                        seq_first=(b, n), dbias=gv[last + _LAYER_KEYS.index("l2.b")])
         dmemk = torch.zeros((rm, memk.shape[1]), dtype=F32, device=dev) if need_memgrad else None
         dmemv = torch.zeros((rm, memv.shape[1]), dtype=F32, device=dev) if need_mem else None
         per = 25
@@ -374,15 +380,14 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             W = {k: wb[ix[k]] for k in _LAYER_KEYS}
             P = {k: params[ix[k]] for k in _LAYER_KEYS}
             # ---- MLP backward
-            dm = cast_colsum(g, gv[ix["l2.b"]])
+            dm = g16
             acc_w(ix["l2.w"], dm.t(), h)
             dh = torch.mm(dm, W["l2.w"])
             relu_bwd_colsum_(dh, h, gv[ix["l1.b"]])
             acc_w(ix["l1.w"], dh.t(), y3)
             dy3 = torch.mm(dh, W["l1.w"])
-            g = ln_bwd(dy3, x2, mean3, rstd3, P["n3.w"], g, gv[ix["n3.w"]], gv[ix["n3.b"]])
+            g, dca = ln_bwd(dy3, x2, mean3, rstd3, P["n3.w"], g, gv[ix["n3.w"]], gv[ix["n3.b"]], dbias=gv[ix["ca.o.b"]])
             # ---- cross attention backward
-            dca = cast_colsum(g, gv[ix["ca.o.b"]])
             acc_w(ix["ca.o.w"], dca.t(), o2.view(r, d))
             do2 = torch.mm(dca, W["ca.o.w"])
             # conjugate RoPE and the q / k / v bias gradients (column sums) are fused into the gradient epilogues.
@@ -411,9 +416,8 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             dq2 = dq2.view(r, d)
             dy2 = torch.mm(dq2, W["ca.q.w"])
             acc_w(ix["ca.q.w"], dq2.t(), y2)
-            g = ln_bwd(dy2, x1, mean2, rstd2, P["n2.w"], g, gv[ix["n2.w"]], gv[ix["n2.b"]])
+            g, dsa = ln_bwd(dy2, x1, mean2, rstd2, P["n2.w"], g, gv[ix["n2.w"]], gv[ix["n2.b"]], dbias=gv[ix["sa.o.b"]])
             # ---- self attention backward
-            dsa = cast_colsum(g, gv[ix["sa.o.b"]])
             acc_w(ix["sa.o.w"], dsa.t(), o.view(r, d))
             do = torch.mm(dsa, W["sa.o.w"])
             dqkv = torch.empty((b, n, 3 * d), dtype=BF16, device=dev)   # [dq | dk | dv], written in place by the kernels
@@ -433,7 +437,11 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                 dw = _mm32(dqkv.t(), y1)                     # [768, 256] = d(Wq | Wk | Wv) in one GEMM
                 grads[ix["sa.q.w"]], grads[ix["sa.k.w"]], grads[ix["sa.v.w"]] = dw[:d], dw[d:2 * d], dw[2 * d:]
             dy1 = torch.mm(dqkv, wqkv_all[l])            # stacked [768, 256] weights: contraction over 768, fp32 accumulation
-            g = ln_bwd(dy1, x0, mean1, rstd1, P["n1.w"], g, gv[ix["n1.w"]], gv[ix["n1.b"]])
+            if l > 0:
+                g, g16 = ln_bwd(dy1, x0, mean1, rstd1, P["n1.w"], g, gv[ix["n1.w"]], gv[ix["n1.b"]],
+                                dbias=gv[base - _NPL + _LAYER_KEYS.index("l2.b")])
+            else:
+                g = ln_bwd(dy1, x0, mean1, rstd1, P["n1.w"], g, gv[ix["n1.w"]], gv[ix["n1.b"]])
         side.join()
         # ---- unpack input gradients
         d_curr = d_pos = d_mem = d_mpos = None

@@ -15,10 +15,19 @@ ddp.attach_grad_bucket(model)
 host = bench.make_host_inputs(wl, 1234, pin=False)
 d = bench.to_device(host, dev)
 banks = bench.assemble_banks(d, wl)
-for _ in range(2): bench.run_step(model, crit, opt, d, banks, wl, 1)
+fwd = model
+if os.environ.get("PROFILE_GRAPHS"):
+    from sam2_video_training_b200.graphs import GraphedMemoryAttention
+    fwd = GraphedMemoryAttention(model)
+for _ in range(3): bench.run_step(model, crit, opt, d, banks, wl, 1, fwd=fwd)
 torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(3): bench.run_step(model, crit, opt, d, banks, wl, 1, fwd=fwd)
+e1.record(); torch.cuda.synchronize()
+print("step wall (CUDA events, 3 steps): %.2f ms/step" % (e0.elapsed_time(e1) / 3))
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
-    bench.run_step(model, crit, opt, d, banks, wl, 1)
+    bench.run_step(model, crit, opt, d, banks, wl, 1, fwd=fwd)
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))

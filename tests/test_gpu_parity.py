@@ -295,6 +295,13 @@ def test_ln_fwd_bwd_kernels(dev):
     xr2 = xn.clone().requires_grad_(True)
     torch.nn.functional.layer_norm(xr2, (256,), gamma, beta, 1e-5).backward(dy32.transpose(0, 1).reshape(rows, 256))
     assert rel_l2(g2, xr2.grad) < 1e-5
+    # fused bf16 copy + bias gradient of the next projection (column sums of the bf16-rounded output gradient)
+    dg.zero_(); db.zero_()
+    dbias = torch.full((256,), 0.25, device=dev)
+    gout2, g16 = fs.ln_bwd(dy, xn, mean, rstd, gamma, gin, dg, db, dbias=dbias)
+    assert torch.equal(gout2, gout) and g16.dtype == torch.bfloat16 and torch.equal(g16, gout.to(torch.bfloat16))
+    assert rel_l2(dbias, g16.float().sum(0) + 0.25) < 1e-5
+    assert rel_l2(dg, gr.grad) < 1e-5 and rel_l2(db, br.grad) < 1e-5
 
 
 @pytest.mark.parametrize("c", [256, 768, 2048])

@@ -10,9 +10,11 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "abi_common.cuh"
 #include "attn_kernels.cuh"
+#include "attn_pair_kernel.cuh"
 #include "tma_desc.cuh"
 
 namespace {
@@ -304,6 +306,22 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
   if ((rc = sam2b200::make_rows256_map(&map_v128, v, B, M, attn::kBlockM))) return rc;
   const float2* table = reinterpret_cast<const float2*>(rope_table);
 
+  // dV and dK together on CTA pairs (attn_pair_kernel.cuh): P^T is computed once and shared through distributed shared
+  // memory -- 4 GEMM units per (key block, query tile) instead of the 5 of the separate kernels below.
+  // Opt-in experiment (SAM2B200_PAIR_KERNEL=1): see the status note in attn_pair_kernel.cuh.
+  static const bool use_pair = getenv("SAM2B200_PAIR_KERNEL") != nullptr;
+  if ((parts & 6) == 6 && use_pair) {
+    attn::PairParams p{};
+    p.Lk = M; p.Lq = N; p.scale_log2 = scale * kLog2e; p.scale = scale; p.lse2 = lse2; p.delta = delta;
+    p.gout_v = attn::GradOut{grad_dtype, dbias_v, nullptr, 0, 1};
+    p.gout_k = attn::GradOut{grad_dtype, dbias_k, table, table ? n_rope_k : 0, table ? rope_period : 1};
+    const size_t smem = sizeof(attn::PairShared) + 1024;
+    if ((rc = set_smem(attn::kv_pair_kernel, smem))) return rc;
+    dim3 grid(2 * ((M + attn::kBlockM - 1) / attn::kBlockM), B, 1);
+    attn::kv_pair_kernel<<<grid, attn::kThreads, smem, stream>>>(map_q64, map_do64, map_k128, map_v128, map_dv, map_dk, p);
+    if ((rc = sam2b200::check_launch("attn_bwd dV+dK pair"))) return rc;
+    parts &= ~6;
+  }
   // dV = P^T dO: fixed K block, stream (Q, dO) tiles
   if (parts & 2) {
     attn::TwoGemmParams p{};

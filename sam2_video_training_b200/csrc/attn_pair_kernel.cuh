@@ -1,0 +1,317 @@
+// Key-side backward of the attention core as ONE kernel on CTA PAIRS (thread-block cluster of 2):
+//
+//   rank 0 ("V side"):  S^T  = K . Q^T      ->  P^T  = exp2(S^T c - LSE2[q])     ->  dV += P^T . dO
+//   rank 1 ("K side"):  dP^T = V . dO^T     ->  dS^T = P^T o (dP^T - Delta[q])   ->  dK += dS^T . Q
+//
+// Both CTAs own the same 128-key block and stream the same (Q, dO) tiles; the probability tile P^T that the K side
+// needs is computed ONCE, by the V side, and shipped to the partner's shared memory through distributed shared
+// memory (st.shared::cluster + a cluster-scope mbarrier).  The separate dV and dK kernels (attn_kernels.cuh) execute
+// 2 + 3 = 5 GEMM units per (key block, query tile) because the dK kernel has to recompute S^T; the pair executes
+// 2 + 2 = 4, evenly split over the two SMs.  (A single CTA cannot hold both accumulators: dV and dK are
+// 2 x 256 fp32 columns = all of tensor memory.)
+//
+// Everything else -- fixed operand by TMA -> SMEM -> TMEM, 3-stage TMA tile ring, score / probability tiles in TMEM,
+// TMA-store epilogues with fused conjugate RoPE, scale and bias gradients -- is the machinery of two_gemm_kernel.
+//
+// STATUS: correct (selftest + parity suite pass with it) but NOT the default (opt in: SAM2B200_PAIR_KERNEL=1).
+// Measured on B200 (profiles/r1_pair_kernel_experiment.txt): at cfg2 (9 query tiles per key block) the cluster launch
+// and the two cluster barriers cost ~3.5 us per pair, which eats the saved GEMM unit, and the synchronous exchange
+// (st.shared::cluster + release.cluster arrive in the compute warps) adds ~1.5 us per tile.  Next step: ship P^T with
+// cp.async.bulk.shared::cluster (asynchronous, completes on the partner's mbarrier) and use the pair only for long
+// query loops (cfg4: 64 tiles per key block), where 4 vs 5 GEMM units is worth ~12 % of the backward.
+#pragma once
+
+#include "attn_kernels.cuh"
+
+namespace attn {
+
+struct PairParams {
+  int Lk;                      // keys per batch item (rows of K, V, dK, dV)
+  int Lq;                      // queries per batch item (rows of Q, dO; streamed)
+  float scale_log2;            // softmax scale * log2(e)
+  float scale;                 // softmax scale (applied to dK in the epilogue)
+  const float* lse2;           // [B, Lq] log2-domain LSE of the forward
+  const float* delta;          // [B, Lq] rowsum(dO o O)
+  GradOut gout_v, gout_k;
+};
+
+struct PairShared {
+  alignas(1024) uint8_t x_tiles[kStages][kTileBytes];
+  alignas(1024) uint8_t y_tiles[kStages][kTileBytes];
+  alignas(1024) uint8_t p_buf[2][kBlockM * 128];   // rank 1: P^T tiles [128 keys][64 queries] bf16 (double-buffered), 16-byte chunks XOR (row & 7)
+  alignas(8) uint64_t x_full[kStages];
+  uint64_t x_empty[kStages];
+  uint64_t y_full[kStages];
+  uint64_t y_empty[kStages];
+  uint64_t s_full[2];
+  uint64_t p_ready[2];
+  uint64_t acc_done;
+  uint64_t a_full;
+  uint64_t a_ready;
+  uint64_t p_full[2];          // live in rank 1: P^T of tile j has landed in p_buf[j & 1] (one arrival per rank-0 softmax warp)
+  uint64_t p_free[2];          // live in rank 0: rank 1 has read p_buf[j & 1] (one arrival per rank-1 warp)
+  float colvec[2][kBlockN];    // per-column vector of the tile: LSE2 (rank 0) / Delta (rank 1)
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same variable in CTA `rank`
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster128(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (++spins > SAM2B200_SPIN_LIMIT) {
+      printf("sam2b200: cluster mbarrier timeout block (%d,%d) thread %d bar %p parity %u\n", blockIdx.x, blockIdx.y,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+kv_pair_kernel(const __grid_constant__ CUtensorMap map_q64, const __grid_constant__ CUtensorMap map_do64,
+               const __grid_constant__ CUtensorMap map_k128, const __grid_constant__ CUtensorMap map_v128,
+               const __grid_constant__ CUtensorMap map_dv, const __grid_constant__ CUtensorMap map_dk,
+               const PairParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  PairShared& sh = *reinterpret_cast<PairShared*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0: V side, 1: K side
+  const bool kside = rank != 0;
+  const int a_tile = blockIdx.x >> 1;               // 128-key block shared by the pair
+  const int b = blockIdx.y;
+  const int nt = (p.Lq + kBlockN - 1) / kBlockN;
+  // scores GEMM streams X (K-major view), accumulate GEMM streams Y (MN-major view)
+  const CUtensorMap* map_x = kside ? &map_do64 : &map_q64;
+  const CUtensorMap* map_y = kside ? &map_q64 : &map_do64;
+  const CUtensorMap* map_a = kside ? &map_v128 : &map_k128;
+  const CUtensorMap* map_o = kside ? &map_dk : &map_dv;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&sh.x_full[s], 1); mbar_init(&sh.x_empty[s], 1);
+      mbar_init(&sh.y_full[s], 1); mbar_init(&sh.y_empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sh.s_full[i], 1); mbar_init(&sh.p_ready[i], kNumSoftmaxThreads); }
+    mbar_init(&sh.acc_done, 1);
+    mbar_init(&sh.a_full, 1);
+    mbar_init(&sh.a_ready, kNumSoftmaxThreads);
+    for (int i = 0; i < 2; ++i) { mbar_init(&sh.p_full[i], kNumSoftmaxWarps); mbar_init(&sh.p_free[i], kNumSoftmaxWarps); }
+    fence_barrier_init();
+  }
+  if (warp == kProducerWarp && lane == 0) { prefetch_tmap(map_a); prefetch_tmap(map_x); prefetch_tmap(map_y); }
+  if (warp == 0 && lane == 0) prefetch_tmap(map_o);
+  if (warp == kMmaWarp) { tmem_alloc(&sh.tmem_base, 512); tmem_relinquish(); }
+  tc_fence_before();
+  cluster_sync_all();                                // barrier inits of BOTH CTAs visible before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem = sh.tmem_base;
+
+  if (warp == kProducerWarp) {
+    // ===================== TMA producer =====================
+    const bool leader = elect_one();
+    if (leader) {
+      mbar_arrive_expect_tx(&sh.a_full, 4 * kSlabBytes);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        tma_load_3d((c < 2 ? &sh.x_tiles[kStages - 1][0] : &sh.y_tiles[kStages - 1][0]) + (c & 1) * kSlabBytes, map_a,
+                    &sh.a_full, c * 64, a_tile * kBlockM, b);
+    }
+    __syncwarp();
+    for (int j = 0; j < nt; ++j) {
+      const int s = j % kStages;
+      const uint32_t ph = (j / kStages) & 1;
+      const int row0 = j * kBlockN;
+      if (j == kStages - 1) mbar_wait(&sh.a_ready, 0);
+      mbar_wait(&sh.x_empty[s], ph ^ 1);
+      if (leader) {
+        mbar_arrive_expect_tx(&sh.x_full[s], kTileBytes);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tma_load_3d(&sh.x_tiles[s][c * kChunkBytes], map_x, &sh.x_full[s], c * 64, row0, b);
+      }
+      __syncwarp();
+      mbar_wait(&sh.y_empty[s], ph ^ 1);
+      if (leader) {
+        mbar_arrive_expect_tx(&sh.y_full[s], kTileBytes);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tma_load_3d(&sh.y_tiles[s][c * kChunkBytes], map_y, &sh.y_full[s], c * 64, row0, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer (identical on both sides) =====================
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = make_idesc_bf16(kBlockM, kBlockN, 0, 0);
+    constexpr uint32_t idesc_acc = make_idesc_bf16(kBlockM, kD, 0, 1);
+    const uint32_t x_lo0 = desc_lo_sw128(smem_u32(&sh.x_tiles[0][0]), 16);
+    const uint32_t y_lo0 = desc_lo_sw128(smem_u32(&sh.y_tiles[0][0]), kChunkBytes);
+    auto issue_scores = [&](int t) {
+      const int s = t % kStages;
+      mbar_wait(&sh.x_full[s], (t / kStages) & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t xlo = x_lo0 + s * (kTileBytes >> 4);
+        const uint32_t d = tmem + ((t & 1) ? kColS1 : kColS0);
+#pragma unroll
+        for (int ks = 0; ks < kD / 16; ++ks)
+          umma_ts_lohi(d, tmem + kColA + ks * 8, xlo + (ks >> 2) * (kChunkBytes >> 4) + (ks & 3) * 2, kDescHiSw128_1024,
+                       idesc_s, ks > 0);
+        umma_commit(&sh.x_empty[s]);
+        umma_commit(&sh.s_full[t & 1]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(&sh.a_ready, 0);
+    tc_fence_after();
+    issue_scores(0);
+    if (nt > 1) issue_scores(1);
+    for (int j = 0; j < nt; ++j) {
+      const int s = j % kStages;
+      mbar_wait(&sh.p_ready[j & 1], (j >> 1) & 1);
+      mbar_wait(&sh.y_full[s], (j / kStages) & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t ylo = y_lo0 + s * (kTileBytes >> 4);
+        const uint32_t pa = tmem + ((j & 1) ? kColS1 : kColS0);
+#pragma unroll
+        for (int ks = 0; ks < kBlockN / 16; ++ks)
+          umma_ts_lohi(tmem + kColAcc, pa + p_col_of_kstep(ks), ylo + ks * (2048 >> 4), kDescHiSw128_1024, idesc_acc,
+                       (j > 0) || (ks > 0));
+        umma_commit(&sh.y_empty[s]);
+        umma_commit(&sh.acc_done);
+      }
+      __syncwarp();
+      if (j + 2 < nt) issue_scores(j + 2);
+    }
+  } else {
+    // ===================== compute / epilogue warps (0..7) =====================
+    const int quarter = warp & 3;
+    const int half = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem + (uint32_t(quarter * 32) << 16);
+    {
+      mbar_wait(&sh.a_full, 0);
+      stage_to_tmem_half(smem_u32(half ? &sh.y_tiles[kStages - 1][0] : &sh.x_tiles[kStages - 1][0]), row, lane_addr + kColA, half);
+      tc_fence_before();
+      mbar_arrive(&sh.a_ready);
+    }
+    const int row0 = a_tile * kBlockM + quarter * 32;
+    const uint32_t stage = smem_u32(&sh.x_tiles[0][0]) + warp * (4 * kBoxBytes);
+    const GradOut& gout = kside ? p.gout_k : p.gout_v;
+    const bool rotate = gout.rope_table != nullptr && (row0 + lane) < gout.rope_rows;
+    const float c = p.scale_log2;
+    // this thread's 64 bytes of the P^T exchange tile (row `row`, 16-byte chunks 4*half .. 4*half+3, XOR-swizzled)
+    const uint32_t p_local = smem_u32(&sh.p_buf[0][0]) + row * 128;
+    const uint32_t p_remote = map_to_rank(p_local, 1);                       // rank 0 writes into rank 1's buffers
+    const uint32_t p_full_remote = map_to_rank(smem_u32(&sh.p_full[0]), 1);  // rank 0 -> rank 1
+    const uint32_t p_free_remote = map_to_rank(smem_u32(&sh.p_free[0]), 0);  // rank 1 -> rank 0
+    constexpr uint32_t kPBufBytes = kBlockM * 128;
+
+    const float* colsrc = kside ? p.delta : p.lse2;
+    const float col_oob = kside ? 0.f : INFINITY;
+    float cv_next = col_oob;
+    if (threadIdx.x < kBlockN && (int)threadIdx.x < p.Lq) cv_next = colsrc[(long long)b * p.Lq + threadIdx.x];
+    for (int j = 0; j < nt; ++j) {
+      const uint32_t sbuf = lane_addr + ((j & 1) ? kColS1 : kColS0);
+      if (threadIdx.x < kBlockN) {
+        sh.colvec[j & 1][threadIdx.x] = cv_next;
+        const int col = (j + 1) * kBlockN + threadIdx.x;
+        cv_next = (j + 1 < nt && col < p.Lq) ? colsrc[(long long)b * p.Lq + col] : col_oob;
+      }
+      asm volatile("bar.sync 5, 256;" ::: "memory");
+      mbar_wait(&sh.s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t r0[32];
+      SAM2B200_TMEM_LD32(sbuf + half * kHalfN, r0);
+      tmem_wait_ld();
+      const float* cv = &sh.colvec[j & 1][half * kHalfN];
+      uint32_t pk[16];
+      if (!kside) {
+        // ---- V side: P^T = exp2(S^T c - LSE2[q]); keep it (TMEM, A operand of dV += P^T dO) and ship it to the partner
+#pragma unroll
+        for (int i = 0; i < kHalfN; i += 2) {
+          const float e0 = ex2(fmaf(__uint_as_float(r0[i]), c, -cv[i]));
+          const float e1 = ex2(fmaf(__uint_as_float(r0[i + 1]), c, -cv[i + 1]));
+          pk[i >> 1] = pack_bf16(e0, e1);
+        }
+        SAM2B200_TMEM_ST16(sbuf + half * kHalfN, pk);
+        tmem_wait_st();
+        // own pipeline first: the dV GEMM of this tile must not wait for the partner
+        if (j > 0) mbar_wait(&sh.acc_done, (j - 1) & 1);
+        tc_fence_before();
+        mbar_arrive(&sh.p_ready[j & 1]);
+        if (j >= 2) mbar_wait_cluster(&sh.p_free[j & 1], ((j - 2) >> 1) & 1);   // partner has read the tile that used this buffer
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          st_cluster128(p_remote + (j & 1) * kPBufBytes + (((half * 4 + q4) ^ (row & 7)) << 4), pk[4 * q4], pk[4 * q4 + 1],
+                        pk[4 * q4 + 2], pk[4 * q4 + 3]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(p_full_remote + (j & 1) * 8);  // release.cluster: the warp's 32 rows are visible
+        continue;
+      } else {
+        // ---- K side: dS^T = P^T o (dP^T - Delta[q]) with P^T from the partner
+        mbar_wait_cluster(&sh.p_full[j & 1], (j >> 1) & 1);
+        uint4 pv[4];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) pv[q4] = lds128(p_local + (j & 1) * kPBufBytes + (((half * 4 + q4) ^ (row & 7)) << 4));
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(p_free_remote + (j & 1) * 8);  // the buffer may be overwritten
+        const uint32_t pw[16] = {pv[0].x, pv[0].y, pv[0].z, pv[0].w, pv[1].x, pv[1].y, pv[1].z, pv[1].w,
+                                 pv[2].x, pv[2].y, pv[2].z, pv[2].w, pv[3].x, pv[3].y, pv[3].z, pv[3].w};
+#pragma unroll
+        for (int i = 0; i < kHalfN; i += 2) {
+          const __nv_bfloat162 pp = *reinterpret_cast<const __nv_bfloat162*>(&pw[i >> 1]);
+          const float2 pf = __bfloat1622float2(pp);
+          pk[i >> 1] = pack_bf16(pf.x * (__uint_as_float(r0[i]) - cv[i]), pf.y * (__uint_as_float(r0[i + 1]) - cv[i + 1]));
+        }
+        SAM2B200_TMEM_ST16(sbuf + half * kHalfN, pk);
+        tmem_wait_st();
+      }
+      if (j > 0) mbar_wait(&sh.acc_done, (j - 1) & 1);   // observe every phase of acc_done in order (see two_gemm_kernel)
+      tc_fence_before();
+      mbar_arrive(&sh.p_ready[j & 1]);
+    }
+
+    float2 tcur[16];
+    load_table_chunk(gout, rotate, row0 + lane, half * 128, tcur);
+    mbar_wait(&sh.acc_done, (nt - 1) & 1);
+    tc_fence_after();
+    grad_epilogue(gout, map_o, stage, lane_addr + kColAcc, half, lane, row0, p.Lk, b, kside ? p.scale : 1.0f, rotate, tcur);
+  }
+
+  tc_fence_before();
+  cluster_sync_all();          // neither CTA may exit while its partner can still write / arrive into its shared memory
+  if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace attn

@@ -307,9 +307,13 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
   const float2* table = reinterpret_cast<const float2*>(rope_table);
 
   // dV and dK together on CTA pairs (attn_pair_kernel.cuh): P^T is computed once and shared through distributed shared
-  // memory -- 4 GEMM units per (key block, query tile) instead of the 5 of the separate kernels below.
-  // Opt-in experiment (SAM2B200_PAIR_KERNEL=1): see the status note in attn_pair_kernel.cuh.
-  static const bool use_pair = getenv("SAM2B200_PAIR_KERNEL") != nullptr;
+  // memory -- 4 GEMM units per (key block, query tile) instead of the 5 of the separate kernels below.  The cluster
+  // launch + its barriers cost ~3.5 us per pair, so it only pays for long query loops: measured on B200
+  // (profiles/r1_pair_kernel_experiment.txt) -8 % at N = 4096, -3 % at N = 1024, +6 % at N = 576.
+  // SAM2B200_PAIR_KERNEL=1 / SAM2B200_NO_PAIR_KERNEL=1 force it on / off.
+  static const bool force_pair = getenv("SAM2B200_PAIR_KERNEL") != nullptr;
+  static const bool no_pair = getenv("SAM2B200_NO_PAIR_KERNEL") != nullptr;
+  const bool use_pair = !no_pair && (force_pair || N >= 1024);
   if ((parts & 6) == 6 && use_pair) {
     attn::PairParams p{};
     p.Lk = M; p.Lq = N; p.scale_log2 = scale * kLog2e; p.scale = scale; p.lse2 = lse2; p.delta = delta;

@@ -13,12 +13,12 @@
 // Everything else -- fixed operand by TMA -> SMEM -> TMEM, 3-stage TMA tile ring, score / probability tiles in TMEM,
 // TMA-store epilogues with fused conjugate RoPE, scale and bias gradients -- is the machinery of two_gemm_kernel.
 //
-// STATUS: correct (selftest + parity suite pass with it) but NOT the default (opt in: SAM2B200_PAIR_KERNEL=1).
-// Measured on B200 (profiles/r1_pair_kernel_experiment.txt): at cfg2 (9 query tiles per key block) the cluster launch
-// and the two cluster barriers cost ~3.5 us per pair, which eats the saved GEMM unit, and the synchronous exchange
-// (st.shared::cluster + release.cluster arrive in the compute warps) adds ~1.5 us per tile.  Next step: ship P^T with
-// cp.async.bulk.shared::cluster (asynchronous, completes on the partner's mbarrier) and use the pair only for long
-// query loops (cfg4: 64 tiles per key block), where 4 vs 5 GEMM units is worth ~12 % of the backward.
+// The exchange is asynchronous: the V side stages its tile in its own shared memory and ONE thread per lane quarter
+// issues cp.async.bulk.shared::cluster (4 KB), which completes on an mbarrier of the partner; the partner hands buffers
+// back with a RELAXED remote arrive (4 buffers deep).  Measured on B200 (profiles/r1_pair_kernel_experiment.txt):
+// synchronous st.shared::cluster + release.cluster arrives in the compute warps cost +1.5 us per tile; the release.cluster
+// hand-back alone +0.3 us per tile.  The cluster launch and its two barriers cost ~3.5 us per pair, so the pair is used
+// for long query loops only (N >= 1024, attn.cu): -8 % backward time at N = 4096, -3 % at N = 1024, +6 % at N = 576.
 #pragma once
 
 #include "attn_kernels.cuh"
@@ -35,21 +35,26 @@ struct PairParams {
   GradOut gout_v, gout_k;
 };
 
+constexpr int kPairStages = 2;     // tile ring (a 2-GEMM loop needs its next tiles ~1.5 tile times ahead: two stages suffice)
+constexpr int kPBufs = 4;          // P^T exchange depth: the V side may run 4 tiles ahead of the K side's reads, which
+                                   // covers the copy + remote-arrive round trip (2 buffers throttled it to ~1.4 us / tile)
 struct PairShared {
-  alignas(1024) uint8_t x_tiles[kStages][kTileBytes];
-  alignas(1024) uint8_t y_tiles[kStages][kTileBytes];
-  alignas(1024) uint8_t p_buf[2][kBlockM * 128];   // rank 1: P^T tiles [128 keys][64 queries] bf16 (double-buffered), 16-byte chunks XOR (row & 7)
-  alignas(8) uint64_t x_full[kStages];
-  uint64_t x_empty[kStages];
-  uint64_t y_full[kStages];
-  uint64_t y_empty[kStages];
+  alignas(1024) uint8_t x_tiles[kPairStages][kTileBytes];
+  alignas(1024) uint8_t y_tiles[kPairStages][kTileBytes];
+  // P^T tiles [128 keys][64 queries] bf16, double-buffered, 16-byte chunks XOR (row & 7): rank 0 stages its tile here
+  // and a bulk async copy (cp.async.bulk.shared::cluster) moves it into the same buffer of rank 1
+  alignas(1024) uint8_t p_buf[kPBufs][kBlockM * 128];
+  alignas(8) uint64_t x_full[kPairStages];
+  uint64_t x_empty[kPairStages];
+  uint64_t y_full[kPairStages];
+  uint64_t y_empty[kPairStages];
   uint64_t s_full[2];
   uint64_t p_ready[2];
   uint64_t acc_done;
   uint64_t a_full;
   uint64_t a_ready;
-  uint64_t p_full[2];          // live in rank 1: P^T of tile j has landed in p_buf[j & 1] (one arrival per rank-0 softmax warp)
-  uint64_t p_free[2];          // live in rank 0: rank 1 has read p_buf[j & 1] (one arrival per rank-1 warp)
+  uint64_t p_full[kPBufs];          // live in rank 1: P^T of tile j has landed in p_buf[j & 1] (16 KB of complete_tx from rank 0's copies)
+  uint64_t p_free[kPBufs];     // live in rank 0: rank 1 has read p_buf[j % kPBufs] (one arrival per rank-1 warp)
   float colvec[2][kBlockN];    // per-column vector of the tile: LSE2 (rank 0) / Delta (rank 1)
   uint32_t tmem_base;
 };
@@ -71,8 +76,20 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t smem_addr, uint32_t ran
 __device__ __forceinline__ void st_cluster128(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// Bulk asynchronous copy own shared memory -> shared memory of another CTA of the cluster; the bytes complete on an
+// mbarrier of the destination CTA (both destination addresses are shared::cluster addresses from map_to_rank).
+__device__ __forceinline__ void bulk_copy_to_cluster(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes,
+                                                     uint32_t dst_cluster_bar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :
+               : "r"(dst_cluster_addr), "r"(src_cta_addr), "r"(bytes), "r"(dst_cluster_bar)
+               : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_bar_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -118,7 +135,7 @@ kv_pair_kernel(const __grid_constant__ CUtensorMap map_q64, const __grid_constan
   const CUtensorMap* map_o = kside ? &map_dk : &map_dv;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kPairStages; ++s) {
       mbar_init(&sh.x_full[s], 1); mbar_init(&sh.x_empty[s], 1);
       mbar_init(&sh.y_full[s], 1); mbar_init(&sh.y_empty[s], 1);
     }
@@ -126,7 +143,7 @@ kv_pair_kernel(const __grid_constant__ CUtensorMap map_q64, const __grid_constan
     mbar_init(&sh.acc_done, 1);
     mbar_init(&sh.a_full, 1);
     mbar_init(&sh.a_ready, kNumSoftmaxThreads);
-    for (int i = 0; i < 2; ++i) { mbar_init(&sh.p_full[i], kNumSoftmaxWarps); mbar_init(&sh.p_free[i], kNumSoftmaxWarps); }
+    for (int i = 0; i < kPBufs; ++i) { mbar_init(&sh.p_full[i], 1); mbar_init(&sh.p_free[i], kNumSoftmaxWarps); }
     fence_barrier_init();
   }
   if (warp == kProducerWarp && lane == 0) { prefetch_tmap(map_a); prefetch_tmap(map_x); prefetch_tmap(map_y); }
@@ -144,15 +161,15 @@ kv_pair_kernel(const __grid_constant__ CUtensorMap map_q64, const __grid_constan
       mbar_arrive_expect_tx(&sh.a_full, 4 * kSlabBytes);
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        tma_load_3d((c < 2 ? &sh.x_tiles[kStages - 1][0] : &sh.y_tiles[kStages - 1][0]) + (c & 1) * kSlabBytes, map_a,
+        tma_load_3d((c < 2 ? &sh.x_tiles[kPairStages - 1][0] : &sh.y_tiles[kPairStages - 1][0]) + (c & 1) * kSlabBytes, map_a,
                     &sh.a_full, c * 64, a_tile * kBlockM, b);
     }
     __syncwarp();
     for (int j = 0; j < nt; ++j) {
-      const int s = j % kStages;
-      const uint32_t ph = (j / kStages) & 1;
+      const int s = j % kPairStages;
+      const uint32_t ph = (j / kPairStages) & 1;
       const int row0 = j * kBlockN;
-      if (j == kStages - 1) mbar_wait(&sh.a_ready, 0);
+      if (j == kPairStages - 1) mbar_wait(&sh.a_ready, 0);
       mbar_wait(&sh.x_empty[s], ph ^ 1);
       if (leader) {
         mbar_arrive_expect_tx(&sh.x_full[s], kTileBytes);
@@ -176,8 +193,8 @@ kv_pair_kernel(const __grid_constant__ CUtensorMap map_q64, const __grid_constan
     const uint32_t x_lo0 = desc_lo_sw128(smem_u32(&sh.x_tiles[0][0]), 16);
     const uint32_t y_lo0 = desc_lo_sw128(smem_u32(&sh.y_tiles[0][0]), kChunkBytes);
     auto issue_scores = [&](int t) {
-      const int s = t % kStages;
-      mbar_wait(&sh.x_full[s], (t / kStages) & 1);
+      const int s = t % kPairStages;
+      mbar_wait(&sh.x_full[s], (t / kPairStages) & 1);
       tc_fence_after();
       if (leader) {
         const uint32_t xlo = x_lo0 + s * (kTileBytes >> 4);
@@ -196,9 +213,9 @@ kv_pair_kernel(const __grid_constant__ CUtensorMap map_q64, const __grid_constan
     issue_scores(0);
     if (nt > 1) issue_scores(1);
     for (int j = 0; j < nt; ++j) {
-      const int s = j % kStages;
+      const int s = j % kPairStages;
       mbar_wait(&sh.p_ready[j & 1], (j >> 1) & 1);
-      mbar_wait(&sh.y_full[s], (j / kStages) & 1);
+      mbar_wait(&sh.y_full[s], (j / kPairStages) & 1);
       tc_fence_after();
       if (leader) {
         const uint32_t ylo = y_lo0 + s * (kTileBytes >> 4);
@@ -221,7 +238,7 @@ kv_pair_kernel(const __grid_constant__ CUtensorMap map_q64, const __grid_constan
     const uint32_t lane_addr = tmem + (uint32_t(quarter * 32) << 16);
     {
       mbar_wait(&sh.a_full, 0);
-      stage_to_tmem_half(smem_u32(half ? &sh.y_tiles[kStages - 1][0] : &sh.x_tiles[kStages - 1][0]), row, lane_addr + kColA, half);
+      stage_to_tmem_half(smem_u32(half ? &sh.y_tiles[kPairStages - 1][0] : &sh.x_tiles[kPairStages - 1][0]), row, lane_addr + kColA, half);
       tc_fence_before();
       mbar_arrive(&sh.a_ready);
     }
@@ -248,6 +265,7 @@ kv_pair_kernel(const __grid_constant__ CUtensorMap map_q64, const __grid_constan
         const int col = (j + 1) * kBlockN + threadIdx.x;
         cv_next = (j + 1 < nt && col < p.Lq) ? colsrc[(long long)b * p.Lq + col] : col_oob;
       }
+      if (kside && threadIdx.x == 0) mbar_arrive_expect_tx(&sh.p_full[j % kPBufs], kPBufBytes);   // arm: 16 KB from the partner
       asm volatile("bar.sync 5, 256;" ::: "memory");
       mbar_wait(&sh.s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
@@ -270,22 +288,27 @@ kv_pair_kernel(const __grid_constant__ CUtensorMap map_q64, const __grid_constan
         if (j > 0) mbar_wait(&sh.acc_done, (j - 1) & 1);
         tc_fence_before();
         mbar_arrive(&sh.p_ready[j & 1]);
-        if (j >= 2) mbar_wait_cluster(&sh.p_free[j & 1], ((j - 2) >> 1) & 1);   // partner has read the tile that used this buffer
+        // ship P^T asynchronously: stage the 64 bytes of this thread locally, then ONE bulk copy per lane quarter
+        // (32 rows x 128 B = 4 KB contiguous) into the partner's buffer, completing on the partner's mbarrier
+        const int pb = j % kPBufs;
+        if (j >= kPBufs) mbar_wait(&sh.p_free[pb], ((j - kPBufs) / kPBufs) & 1);   // partner has read the tile that used this buffer
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4)
-          st_cluster128(p_remote + (j & 1) * kPBufBytes + (((half * 4 + q4) ^ (row & 7)) << 4), pk[4 * q4], pk[4 * q4 + 1],
-                        pk[4 * q4 + 2], pk[4 * q4 + 3]);
-        __syncwarp();
-        if (lane == 0) mbar_arrive_remote(p_full_remote + (j & 1) * 8);  // release.cluster: the warp's 32 rows are visible
+          sts128(p_local + pb * kPBufBytes + (((half * 4 + q4) ^ (row & 7)) << 4), pk[4 * q4], pk[4 * q4 + 1],
+                 pk[4 * q4 + 2], pk[4 * q4 + 3]);
+        fence_proxy_async();
+        pair_barrier(quarter);                                           // both halves of the quarter's 32 rows are staged
+        if (half == 0 && lane == 0)
+          bulk_copy_to_cluster(p_remote + pb * kPBufBytes - row * 128 + quarter * 32 * 128,
+                               p_local + pb * kPBufBytes - row * 128 + quarter * 32 * 128, 32 * 128, p_full_remote + pb * 8);
         continue;
       } else {
         // ---- K side: dS^T = P^T o (dP^T - Delta[q]) with P^T from the partner
-        mbar_wait_cluster(&sh.p_full[j & 1], (j >> 1) & 1);
+        const int pb = j % kPBufs;
+        mbar_wait(&sh.p_full[pb], (j / kPBufs) & 1);
         uint4 pv[4];
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) pv[q4] = lds128(p_local + (j & 1) * kPBufBytes + (((half * 4 + q4) ^ (row & 7)) << 4));
-        __syncwarp();
-        if (lane == 0) mbar_arrive_remote(p_free_remote + (j & 1) * 8);  // the buffer may be overwritten
+        for (int q4 = 0; q4 < 4; ++q4) pv[q4] = lds128(p_local + pb * kPBufBytes + (((half * 4 + q4) ^ (row & 7)) << 4));
         const uint32_t pw[16] = {pv[0].x, pv[0].y, pv[0].z, pv[0].w, pv[1].x, pv[1].y, pv[1].z, pv[1].w,
                                  pv[2].x, pv[2].y, pv[2].z, pv[2].w, pv[3].x, pv[3].y, pv[3].z, pv[3].w};
 #pragma unroll
@@ -295,6 +318,12 @@ kv_pair_kernel(const __grid_constant__ CUtensorMap map_q64, const __grid_constan
           pk[i >> 1] = pack_bf16(pf.x * (__uint_as_float(r0[i]) - cv[i]), pf.y * (__uint_as_float(r0[i + 1]) - cv[i + 1]));
         }
         SAM2B200_TMEM_ST16(sbuf + half * kHalfN, pk);
+        // Hand the buffer back.  RELAXED on purpose: a release.cluster arrive here (8 per tile) measured +0.3 us per tile
+        // (it drains the warp's outstanding memory operations).  The P^T values have been consumed by the arithmetic
+        // above (in-order issue: the shared loads have completed), and the partner can overwrite the buffer only after
+        // this arrive has crossed the cluster AND its next bulk copy has been issued and delivered.
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote_relaxed(p_free_remote + pb * 8);
         tmem_wait_st();
       }
       if (j > 0) mbar_wait(&sh.acc_done, (j - 1) & 1);   // observe every phase of acc_done in order (see two_gemm_kernel)

@@ -484,6 +484,37 @@ def test_functional_losses_match_reference_formulas(dev, multimask):
     assert rel_l2(ig.grad.cpu().double(), iou.grad) < 1e-5
 
 
+def test_attention_backward_pair_kernel_long_query_loop(dev):
+    """N >= 1024 takes the CTA-pair key-side kernel (dV + dK on clusters of 2, P^T through distributed shared memory):
+    same gradients as an fp32 torch restatement of the attention core, ragged key count, rotated and un-rotated keys."""
+    from sam2_video_training_b200 import ops
+    from sam2_video_training_b200.modeling.position_encoding import compute_axial_cis
+    g = torch.Generator(device="cuda").manual_seed(17)
+    grid, b, nptr = 32, 2, 20
+    n, m = grid * grid, 2 * grid * grid + nptr             # N = 1024, M = 2068 (last key block ragged)
+    table = compute_axial_cis(dim=256, end_x=grid, end_y=grid).to(dev)
+    q = torch.randn(b, n, 256, device=dev, generator=g).to(torch.bfloat16)
+    k = torch.randn(b, m, 256, device=dev, generator=g).to(torch.bfloat16)
+    v = torch.randn(b, m, 256, device=dev, generator=g).to(torch.bfloat16)
+    do = torch.randn(b, n, 256, device=dev, generator=g).to(torch.bfloat16)
+    o, o32, lse = ops.attn_fwd(q, k, v, 1 / 16.0)
+    db = [torch.zeros(256, device=dev) for _ in range(3)]
+    dq, dk, dv = ops.attn_bwd(q, k, v, None, o32, do, lse, 1 / 16.0, grad_dtype=torch.float32, dbias=tuple(db))
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    ref = torch.softmax(qf @ kf.transpose(1, 2) / 16.0, dim=-1) @ vf
+    ref.backward(do.float())
+    assert rel_l2(o32, ref) < 5e-3
+    for got, want, name in ((dq, qf.grad, "dq"), (dk, kf.grad, "dk"), (dv, vf.grad, "dv")):
+        assert rel_l2(got, want) < 8e-3, (name, rel_l2(got, want))
+    # without RoPE the column sums of dK vanish analytically (sum_j dS_ij = 0): compare on the scale of sum |dK|
+    assert float((db[1] - dk.double().sum((0, 1)).float()).abs().max()) < 1e-4 * float(dk.abs().sum((0, 1)).max())
+    assert rel_l2(db[2], vf.grad.sum((0, 1))) < 8e-3
+    # fused conjugate rotation in the pair kernel's dK epilogue == rotating the plain gradient back
+    dq2, dk2, dv2 = ops.attn_bwd(q, k, v, None, o32, do, lse, 1 / 16.0, table=table, n_rope_k=m - nptr, grad_dtype=torch.float32)
+    want = ops.rope_apply(dk, table, m - nptr, inverse=True, out_dtype=torch.float32)
+    assert rel_l2(dk2, want) < 1e-5 and torch.equal(dv2, dv)
+
+
 def test_attention_backward_fused_bias_gradients(dev):
     """sam2b200_attn_bwd_ex: the q / k / v bias gradients (column sums of dq / dk / dv over all rows, after the
     conjugate rotation) are accumulated inside the gradient epilogues -- ragged sizes, bf16 and fp32 outputs."""

@@ -331,6 +331,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host (no CUDA-graph replay)")
+    ap.add_argument("--dropout", type=float, default=0.0,
+                    help="train-mode dropout of the stack (the reference ships 0.1); default 0 = the parity configuration "
+                         "SURVEY.md section 8d prescribes for the headline number")
     args = ap.parse_args()
     wl_name, wl = args.workload, WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -353,7 +356,7 @@ def main():
     _lib.check(lib.sam2b200_check_device(local_rank), "sam2b200_check_device")
 
     torch.manual_seed(0)
-    model = build_memory_attention(dropout=0.0).to(dev).train()   # dropout off: throughput with parity numerics
+    model = build_memory_attention(dropout=args.dropout).to(dev).train()   # default 0: throughput with parity numerics
     crit = MultiStepMultiMasksAndIous(dict(LOSS_W), supervise_all_iou=True, iou_use_l1_loss=True, check_valid=False)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-5, fused=True)
     from sam2_video_training_b200 import ddp
@@ -511,6 +514,7 @@ def main():
                        "l2": "inputs_larger_than_L2 (%.0f MB per step)" % (h2d_bytes(host) / 1e6),
                        "launch": "memory-attention fwd/bwd replayed as CUDA graphs (one pair per memory-bank shape)" if not args.no_graphs else "host-launched",
                        "parallelism": "dp%d (clips sharded, NCCL grad all-reduce)" % world,
+                       "dropout": args.dropout,
                        "object_frames_per_step": wl["T"] * wl["C"] * wl["clips"],
                        "algorithmic_tflop_per_step": algorithmic_flops(wl) / 1e12},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,

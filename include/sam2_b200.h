@@ -65,6 +65,10 @@ size_t sam2b200_attn_fwd_workspace_bytes(int B, int N, int M, int nsplit);
 int sam2b200_attn_fwd(const void* q, const void* k, const void* v, void* out, float* out_f32 /* NULL or fp32 copy */,
                       float* lse2, void* workspace, size_t workspace_bytes, int B, int N, int M, float scale,
                       int nsplit, sam2b200_stream_t stream);
+/* Same with attention-probability dropout (transformer.py:304-306, see "dropout" below). */
+int sam2b200_attn_fwd_ex(const void* q, const void* k, const void* v, void* out, float* out_f32, float* lse2,
+                         void* workspace, size_t workspace_bytes, int B, int N, int M, float scale, int nsplit,
+                         float drop_p, const unsigned long long* drop_seed, unsigned drop_site, sam2b200_stream_t stream);
 /* Backward (what autograd derives for transformer.py:296-306).  delta: [B, N] fp32 scratch.
  * dq: [B, N, ldq], dk: [B, M, ldk], dv: [B, M, ldv], fp32 (grad_dtype 0) or bf16 (1), first 256 columns
  * fully overwritten.  With rope_table != NULL the conjugate rotation is fused into the epilogue (all rows
@@ -85,7 +89,8 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
                          const void* dout, const float* lse2, float* delta, void* dq, void* dk, void* dv,
                          int grad_dtype, int ldq, int ldk, int ldv, const float* rope_table, int rope_period,
                          int n_rope_k, int B, int N, int M, float scale, float* dbias_q, float* dbias_k, float* dbias_v,
-                         int parts, sam2b200_stream_t stream);
+                         int parts, float drop_p, const unsigned long long* drop_seed, unsigned drop_site,
+                         sam2b200_stream_t stream);
 
 /* ---- fused LayerNorm / residual / bias-gradient kernels (d_model = 256) -------------------
  * Replace nn.LayerNorm + residual add + dropout(0) + dtype casts of MemoryAttentionLayer
@@ -95,20 +100,35 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
  * batch-first rows b*tr_n + n (the transpose at memory_attention.py:164-167). */
 int sam2b200_ln_fwd(const float* x, const void* res_bf16, float* x_out, const float* gamma, const float* beta,
                     void* y_bf16, float* y_f32, float* mean, float* rstd, long long rows, float eps, int tr_b,
-                    int tr_n, sam2b200_stream_t stream);
+                    int tr_n, float drop_p, const unsigned long long* drop_seed, unsigned drop_site,
+                    sam2b200_stream_t stream);
 size_t sam2b200_ln_bwd_workspace_bytes(long long rows);
 /* g_out = g_in + dLN/dx(dy); dgamma += sum dy*xhat; dbeta += sum dy.  Exactly one of dy_bf16 / dy_f32.
  * g_out_bf16 + dbias (optional, both or neither): bf16 copy of g_out (operand of the next GEMMs of the backward) and
  * dbias += its column sums (bias gradient of the projection whose output gradient g_out is). */
 int sam2b200_ln_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* mean, const float* rstd,
                     const float* gamma, const float* g_in, float* g_out, void* g_out_bf16, float* dgamma, float* dbeta,
-                    float* dbias, void* workspace, long long rows, int tr_b, int tr_n, sam2b200_stream_t stream);
+                    float* dbias, void* workspace, long long rows, int tr_b, int tr_n, float drop_p,
+                    const unsigned long long* drop_seed, unsigned drop_site, sam2b200_stream_t stream);
 size_t sam2b200_colsum_workspace_bytes(long long rows, int C);
 /* Bias gradients (what autograd's sum over rows produces for nn.Linear):
  * mode 0: in_f32 [R,C] -> io_bf16 (cast) and colsum += column sums; mode 1: io_bf16 *= (h_bf16 > 0) in
  * place (ReLU backward, memory_attention.py:97) and colsum += sums; mode 2: colsum += sums of io_bf16. */
 int sam2b200_colsum(int mode, const float* in_f32, void* io_bf16, const void* h_bf16, float* colsum, void* workspace,
-                    long long rows, int C, long long ld, sam2b200_stream_t stream);
+                    long long rows, int C, long long ld, float scale /* mode 1: 1/(1-p) of the dropout after the ReLU */,
+                    sam2b200_stream_t stream);
+
+/* ---- dropout (train mode; memory_attention.py:58-99, transformer.py:304-306) ----------------------------------
+ * Every dropout of the path is a counter-based mask: keep <=> hash(*drop_seed, drop_site, element index) >= p * 2^32
+ * (csrc/dropout.cuh); the seed lives in DEVICE memory (fresh masks under CUDA-graph replay), nothing is stored, the
+ * backward entry points regenerate the forward's mask from the same (seed, site).  drop_p = 0 or drop_seed = NULL: off.
+ * ln_fwd: x' = x + dropout(res); ln_bwd: the bf16 branch-gradient copy is masked (not g_out); attn_fwd_ex /
+ * attn_bwd_ex: attention-probability dropout, index (b N + query) M + key; dropout_inplace: the MLP's hidden
+ * activation; dropout_mask: test aid, the keep mask as bytes. */
+int sam2b200_dropout_inplace(void* x_bf16, long long n, float drop_p, const unsigned long long* drop_seed,
+                             unsigned drop_site, sam2b200_stream_t stream);
+int sam2b200_dropout_mask(unsigned char* out, long long index0, long long n, float drop_p,
+                          const unsigned long long* drop_seed, unsigned drop_site, sam2b200_stream_t stream);
 
 /* ---- fused mask loss --------------------------------------------------------------------
  * mode SAM2B200_LOSS_MULTISTEP replaces MultiStepMultiMasksAndIous._update_losses and the three

@@ -92,9 +92,17 @@ def linear(x: Tensor, w: Tensor, b: Tensor) -> Tensor:
     return x @ w.t() + b
 
 
+def _drop(x: Tensor, keep: Optional[Tensor], p_drop: float) -> Tensor:
+    """Inverted dropout with an EXPLICIT keep mask (nn.Dropout / SDPA dropout_p in train mode:
+    memory_attention.py:64,81,97,99, transformer.py:304-306): x * keep / (1 - p)."""
+    if keep is None:
+        return x
+    return x * keep.to(x.dtype) / (1.0 - p_drop)
+
+
 def rope_attention(p: Dict[str, Tensor], prefix: str, q_in: Tensor, k_in: Tensor, v_in: Tensor,
                    num_k_exclude_rope: int, rope_k_repeat: bool,
-                   return_parts: bool = False):
+                   return_parts: bool = False, keep: Optional[Tensor] = None, p_drop: float = 0.0):
     """``RoPEAttention.forward`` (transformer.py:275-311), one head of width 256.
 
     q/k/v projections (:277-279), head split is a no-op for one head (:282-284), rotate q and
@@ -113,7 +121,7 @@ def rope_attention(p: Dict[str, Tensor], prefix: str, q_in: Tensor, k_in: Tensor
     if num_k_rope > 0:
         k = torch.cat([apply_axial_rope(k[:, :num_k_rope], cos, sin), k[:, num_k_rope:]], dim=1)
     s = (q @ k.transpose(1, 2)) / math.sqrt(q.shape[-1])
-    a = torch.softmax(s, dim=-1)
+    a = _drop(torch.softmax(s, dim=-1), keep, p_drop)   # SDPA drops normalised probabilities (transformer.py:304-306)
     o = a @ v
     out = linear(o, p[prefix + "out_proj.weight"], p[prefix + "out_proj.bias"])
     if return_parts:
@@ -122,26 +130,29 @@ def rope_attention(p: Dict[str, Tensor], prefix: str, q_in: Tensor, k_in: Tensor
 
 
 def memory_attention_layer(p: Dict[str, Tensor], prefix: str, tgt: Tensor, memory: Tensor,
-                           pos: Tensor, query_pos: Tensor, num_k_exclude_rope: int) -> Tensor:
+                           pos: Tensor, query_pos: Tensor, num_k_exclude_rope: int,
+                           masks: Optional[Dict[str, Tensor]] = None, p_drop: float = 0.0) -> Tensor:
     """``MemoryAttentionLayer.forward`` (memory_attention.py:58-99) with the shipped flags
     pos_enc_at_attn=False, pos_enc_at_cross_attn_keys=True, pos_enc_at_cross_attn_queries=False
     (configs/sam2/sam2.1_hiera_t.yaml:38,48-49), ReLU MLP, dropout 0."""
+    mk = masks or {}    # train mode: keep masks "sa_prob", "ca_prob", "drop1", "drop2", "mlp", "drop3" (None = no dropout)
     t2 = layer_norm(tgt, p[prefix + "norm1.weight"], p[prefix + "norm1.bias"])
-    t2 = rope_attention(p, prefix + "self_attn.", t2, t2, t2, 0, rope_k_repeat=False)
-    tgt = tgt + t2
+    t2 = rope_attention(p, prefix + "self_attn.", t2, t2, t2, 0, rope_k_repeat=False, keep=mk.get("sa_prob"), p_drop=p_drop)
+    tgt = tgt + _drop(t2, mk.get("drop1"), p_drop)                                   # :64
     t2 = layer_norm(tgt, p[prefix + "norm2.weight"], p[prefix + "norm2.bias"])
     t2 = rope_attention(p, prefix + "cross_attn_image.", t2, memory + pos, memory,
-                        num_k_exclude_rope, rope_k_repeat=True)
-    tgt = tgt + t2
+                        num_k_exclude_rope, rope_k_repeat=True, keep=mk.get("ca_prob"), p_drop=p_drop)
+    tgt = tgt + _drop(t2, mk.get("drop2"), p_drop)                                   # :81
     t2 = layer_norm(tgt, p[prefix + "norm3.weight"], p[prefix + "norm3.bias"])
-    t2 = linear(torch.relu(linear(t2, p[prefix + "linear1.weight"], p[prefix + "linear1.bias"])),
-                p[prefix + "linear2.weight"], p[prefix + "linear2.bias"])
-    return tgt + t2
+    hid = _drop(torch.relu(linear(t2, p[prefix + "linear1.weight"], p[prefix + "linear1.bias"])), mk.get("mlp"), p_drop)   # :97
+    t2 = linear(hid, p[prefix + "linear2.weight"], p[prefix + "linear2.bias"])
+    return tgt + _drop(t2, mk.get("drop3"), p_drop)                                  # :99
 
 
 def memory_attention(p: Dict[str, Tensor], curr: Tensor, memory: Tensor,
                      curr_pos: Optional[Tensor], memory_pos: Tensor,
-                     num_obj_ptr_tokens: int = 0, num_layers: int = NUM_LAYERS) -> Tensor:
+                     num_obj_ptr_tokens: int = 0, num_layers: int = NUM_LAYERS,
+                     masks: Optional[list] = None, p_drop: float = 0.0) -> Tensor:
     """``MemoryAttention.forward`` (memory_attention.py:119-169).
 
     curr, curr_pos: [N, B, 256]; memory, memory_pos: [M, B, 64]; returns [N, B, 256].
@@ -157,7 +168,8 @@ def memory_attention(p: Dict[str, Tensor], curr: Tensor, memory: Tensor,
     mem = memory.transpose(0, 1)
     mpos = memory_pos.transpose(0, 1)
     for i in range(num_layers):
-        out = memory_attention_layer(p, f"layers.{i}.", out, mem, mpos, qpos, num_obj_ptr_tokens)
+        out = memory_attention_layer(p, f"layers.{i}.", out, mem, mpos, qpos, num_obj_ptr_tokens,
+                                     masks=masks[i] if masks is not None else None, p_drop=p_drop)
     out = layer_norm(out, p["norm.weight"], p["norm.bias"])
     return out.transpose(0, 1)
 

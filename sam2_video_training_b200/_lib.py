@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_uint, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsam2b200.so")
@@ -31,14 +31,19 @@ _SIGNATURES = {
                                   c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "sam2b200_attn_bwd": (c_int, [c_void_p] * 11 + [c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
                                                    c_int, c_int, c_int, c_float, c_void_p]),
+    "sam2b200_attn_fwd_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                     c_int, c_int, c_int, c_float, c_int, c_float, c_void_p, c_uint, c_void_p]),
     "sam2b200_attn_bwd_ex": (c_int, [c_void_p] * 11 + [c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
-                                                      c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
-    "sam2b200_ln_fwd": (c_int, [c_void_p] * 9 + [c_longlong, c_float, c_int, c_int, c_void_p]),
+                                                      c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int,
+                                                      c_float, c_void_p, c_uint, c_void_p]),
+    "sam2b200_ln_fwd": (c_int, [c_void_p] * 9 + [c_longlong, c_float, c_int, c_int, c_float, c_void_p, c_uint, c_void_p]),
     "sam2b200_ln_bwd_workspace_bytes": (c_size_t, [c_longlong]),
-    "sam2b200_ln_bwd": (c_int, [c_void_p] * 13 + [c_longlong, c_int, c_int, c_void_p]),
+    "sam2b200_ln_bwd": (c_int, [c_void_p] * 13 + [c_longlong, c_int, c_int, c_float, c_void_p, c_uint, c_void_p]),
     "sam2b200_colsum_workspace_bytes": (c_size_t, [c_longlong, c_int]),
     "sam2b200_colsum": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int,
-                                c_longlong, c_void_p]),
+                                c_longlong, c_float, c_void_p]),
+    "sam2b200_dropout_inplace": (c_int, [c_void_p, c_longlong, c_float, c_void_p, c_uint, c_void_p]),
+    "sam2b200_dropout_mask": (c_int, [c_void_p, c_longlong, c_longlong, c_float, c_void_p, c_uint, c_void_p]),
     "sam2b200_mask_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_longlong]),
     "sam2b200_mask_loss_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_float,

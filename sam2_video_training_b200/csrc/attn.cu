@@ -213,12 +213,16 @@ size_t sam2b200_attn_fwd_workspace_bytes(int B, int N, int M, int nsplit) {
 
 // q: [B, N, 256], k, v: [B, M, 256] bf16 (q, k already rotated); out: [B, N, 256] bf16;
 // lse2: [B, N] fp32 = log2(sum_j exp(scale * q.k_j)).
-int sam2b200_attn_fwd(const void* q, const void* k, const void* v, void* out, float* out_f32, float* lse2,
-                      void* workspace, size_t workspace_bytes, int B, int N, int M, float scale, int nsplit,
-                      cudaStream_t stream) {
+// drop_p > 0 with a device seed: attention-probability dropout (transformer.py:304-306) -- the probabilities that
+// multiply V are masked and scaled by 1 / (1 - p); the mask is a function of (*drop_seed, drop_site, b, query, key)
+// that sam2b200_attn_bwd_ex regenerates (csrc/dropout.cuh).
+int sam2b200_attn_fwd_ex(const void* q, const void* k, const void* v, void* out, float* out_f32, float* lse2,
+                         void* workspace, size_t workspace_bytes, int B, int N, int M, float scale, int nsplit,
+                         float drop_p, const unsigned long long* drop_seed, unsigned drop_site, cudaStream_t stream) {
   if (!q || !k || !v || !out || !lse2 || B <= 0 || N <= 0 || M <= 0 || B > 65535 || !aligned16(q) ||
-      !aligned16(k) || !aligned16(v) || !aligned16(out))
-    return sam2b200::fail(SAM2B200_ERR_INVALID, "attn_fwd: bad arguments");
+      !aligned16(k) || !aligned16(v) || !aligned16(out) || drop_p < 0.f || drop_p >= 1.f ||
+      (drop_p > 0.f && drop_seed && (long long)B * N * M >= (1LL << 32)))
+    return sam2b200::fail(SAM2B200_ERR_INVALID, "attn_fwd: bad arguments (with dropout B*N*M must be < 2^32)");
   const int total_tiles = (M + attn::kBlockN - 1) / attn::kBlockN;
   if (nsplit < 1) nsplit = 1;
   if (nsplit > total_tiles) nsplit = total_tiles;
@@ -238,6 +242,7 @@ int sam2b200_attn_fwd(const void* q, const void* k, const void* v, void* out, fl
   attn::TwoGemmParams p{};
   p.La = N; p.Lx = M; p.scale_log2 = scale * kLog2e;
   p.has_out_f32 = out_f32 != nullptr; p.lse2 = lse2; p.tiles_per_split = tiles_per_split;
+  p.drop = sam2b200::make_dropout(drop_seed, drop_site, drop_p);
   if (nsplit > 1) {
     p.part_acc = (float*)workspace;
     p.part_ml = p.part_acc + (size_t)nsplit * B * N * 256;
@@ -256,6 +261,13 @@ int sam2b200_attn_fwd(const void* q, const void* k, const void* v, void* out, fl
   return SAM2B200_OK;
 }
 
+int sam2b200_attn_fwd(const void* q, const void* k, const void* v, void* out, float* out_f32, float* lse2,
+                      void* workspace, size_t workspace_bytes, int B, int N, int M, float scale, int nsplit,
+                      cudaStream_t stream) {
+  return sam2b200_attn_fwd_ex(q, k, v, out, out_f32, lse2, workspace, workspace_bytes, B, N, M, scale, nsplit, 0.f, nullptr, 0,
+                              stream);
+}
+
 // Backward of out = softmax(scale q k^T) v.  q, k, v, dout bf16; lse2 from the forward; the forward's
 // output either as bf16 (`out`) or, preferred, its fp32 copy (`out_f32`): Delta = rowsum(dO o O) then has
 // no per-row rounding bias, which matters when dP - Delta cancels (smooth / highly correlated values).
@@ -270,7 +282,8 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
                          const void* dout, const float* lse2, float* delta, void* dq, void* dk, void* dv,
                          int grad_dtype, int ldq, int ldk, int ldv, const float* rope_table, int rope_period,
                          int n_rope_k, int B, int N, int M, float scale, float* dbias_q, float* dbias_k, float* dbias_v,
-                         int parts, cudaStream_t stream) {
+                         int parts, float drop_p, const unsigned long long* drop_seed, unsigned drop_site,
+                         cudaStream_t stream) {
   // parts: bit mask of the kernels to launch (0 = all): 1 Delta = rowsum(dO o O), 2 dV, 4 dK, 8 dQ.  dK and dQ need Delta.
   // Lets the caller put the key-side kernels of the cross-attention (whose results only feed weight / memory-bank
   // gradients) on a second stream, off the critical path of the residual-stream gradient.
@@ -280,8 +293,10 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
       B > 65535 || !aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(dout) ||
       !aligned16(dq) || !aligned16(dk) || !aligned16(dv) || (grad_dtype != 0 && grad_dtype != 1) ||
       ldq < 256 || ldk < 256 || ldv < 256 || (ldq % 8) || (ldk % 8) || (ldv % 8) ||
-      (rope_table && (rope_period <= 0 || n_rope_k < 0 || n_rope_k > M)))
+      (rope_table && (rope_period <= 0 || n_rope_k < 0 || n_rope_k > M)) || drop_p < 0.f || drop_p >= 1.f ||
+      (drop_p > 0.f && drop_seed && (long long)B * N * M >= (1LL << 32)))
     return sam2b200::fail(SAM2B200_ERR_INVALID, "attn_bwd: bad arguments");
+  const sam2b200::Dropout drop = sam2b200::make_dropout(drop_seed, drop_site, drop_p);
   int rc;
   const long long rows = (long long)B * N;
   if (parts & 1) {
@@ -319,6 +334,7 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
     p.Lk = M; p.Lq = N; p.scale_log2 = scale * kLog2e; p.scale = scale; p.lse2 = lse2; p.delta = delta;
     p.gout_v = attn::GradOut{grad_dtype, dbias_v, nullptr, 0, 1};
     p.gout_k = attn::GradOut{grad_dtype, dbias_k, table, table ? n_rope_k : 0, table ? rope_period : 1};
+    p.drop = drop;
     const size_t smem = sizeof(attn::PairShared) + 1024;
     if ((rc = set_smem(attn::kv_pair_kernel, smem))) return rc;
     dim3 grid(2 * ((M + attn::kBlockM - 1) / attn::kBlockM), B, 1);
@@ -332,6 +348,7 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
     p.La = M; p.Lx = N; p.scale_log2 = scale * kLog2e;
     p.lse2 = const_cast<float*>(lse2);
     p.gout = attn::GradOut{grad_dtype, dbias_v, nullptr, 0, 1};
+    p.drop = drop;
     p.tiles_per_split = (N + attn::kBlockN - 1) / attn::kBlockN;
     const size_t smem = sizeof(attn::SharedStorage) + 1024;
     if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_DV>, smem))) return rc;
@@ -347,6 +364,7 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
     p.La = M; p.Lx = N; p.scale_log2 = scale * kLog2e; p.scale = scale;
     p.lse2 = lse2; p.delta = delta;
     p.gout = attn::GradOut{grad_dtype, dbias_k, table, table ? n_rope_k : 0, table ? rope_period : 1};
+    p.drop = drop;
     if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DK>, smem3))) return rc;
     dim3 grid((M + attn::kBlockM - 1) / attn::kBlockM, B, 1);
     p.dbg = timeline_slice((size_t)grid.x * grid.y);
@@ -359,6 +377,7 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
     p.La = N; p.Lx = M; p.scale_log2 = scale * kLog2e; p.scale = scale;
     p.lse2 = lse2; p.delta = delta;
     p.gout = attn::GradOut{grad_dtype, dbias_q, table, table ? N : 0, table ? rope_period : 1};
+    p.drop = drop;
     if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DQ>, smem3))) return rc;
     dim3 grid((N + attn::kBlockM - 1) / attn::kBlockM, B, 1);
     p.dbg = timeline_slice((size_t)grid.x * grid.y);
@@ -373,7 +392,7 @@ int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* o
                       int grad_dtype, int ldq, int ldk, int ldv, const float* rope_table, int rope_period,
                       int n_rope_k, int B, int N, int M, float scale, cudaStream_t stream) {
   return sam2b200_attn_bwd_ex(q, k, v, out, out_f32, dout, lse2, delta, dq, dk, dv, grad_dtype, ldq, ldk, ldv, rope_table,
-                              rope_period, n_rope_k, B, N, M, scale, nullptr, nullptr, nullptr, 0, stream);
+                              rope_period, n_rope_k, B, N, M, scale, nullptr, nullptr, nullptr, 0, 0.f, nullptr, 0, stream);
 }
 
 }  // extern "C"

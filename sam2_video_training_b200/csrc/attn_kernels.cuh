@@ -30,6 +30,7 @@
 //     warp 8 = TMA producer, warp 9 = tcgen05.mma issuer + TMEM allocator.
 #pragma once
 
+#include "dropout.cuh"
 #include "sm100.cuh"
 
 namespace attn {
@@ -100,6 +101,7 @@ struct TwoGemmParams {
   float* part_acc;             // [nsplit, B, La, 256] fp32 un-normalised partials (nsplit > 1)
   float* part_ml;              // [nsplit, B, La, 2]  (m_ref * c, l)
   GradOut gout;                // DV output (dV)
+  sam2b200::Dropout drop;      // attention-probability dropout (transformer.py:304-306); element index (b N + q) M + key
   int tiles_per_split;
   unsigned long long* dbg;     // optional timeline buffer
 };
@@ -428,6 +430,8 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     float2 tcur[16];
 
     const float c = p.scale_log2;
+    const bool drop_on = p.drop.seed != nullptr;
+    const uint32_t drop_key = drop_on ? sam2b200::dropout_key(*p.drop.seed, p.drop.site) : 0u;
     float m_ref = -INFINITY;   // running (lazily updated) row max of the raw scores -- identical in both halves
     float l = 0.f;             // this half's running sum of exp2((s - m_ref) c)
 
@@ -500,20 +504,32 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
         const float mc = m_ref * c;
         float sum0 = 0.f, sum1 = 0.f;
+        // dropout acts on the normalised probabilities: the row sum l keeps every term, only the PV operand is masked
+        const uint32_t didx = (uint32_t)(((long long)b * p.La + a_row_idx) * p.Lx) + (uint32_t)(t * kBlockN + half * kHalfN);
 #pragma unroll
         for (int i = 0; i < kHalfN; i += 2) {
           float e0 = ex2(fmaf(sv[i], c, -mc));
           float e1 = ex2(fmaf(sv[i + 1], c, -mc));
           sum0 += e0; sum1 += e1;
+          if (drop_on) {
+            e0 = sam2b200::dropout_keep(drop_key, didx + i, p.drop.thresh) ? e0 : 0.f;
+            e1 = sam2b200::dropout_keep(drop_key, didx + i + 1, p.drop.thresh) ? e1 : 0.f;
+          }
           pk[i >> 1] = pack_bf16(e0, e1);
         }
         l += sum0 + sum1;
       } else {
         const float* cv = &sh.colvec[j & 1][half * kHalfN];
+        // rows are keys, columns queries: index (b N + q) M + key advances by M per column
+        const uint32_t didx = (uint32_t)(((long long)b * p.Lx + (t * kBlockN + half * kHalfN)) * p.La + a_row_idx);
 #pragma unroll
         for (int i = 0; i < kHalfN; i += 2) {
           float e0 = ex2(fmaf(sv[i], c, -cv[i]));
           float e1 = ex2(fmaf(sv[i + 1], c, -cv[i + 1]));
+          if (drop_on) {
+            e0 = sam2b200::dropout_keep(drop_key, didx + (uint32_t)i * (uint32_t)p.La, p.drop.thresh) ? e0 : 0.f;
+            e1 = sam2b200::dropout_keep(drop_key, didx + (uint32_t)(i + 1) * (uint32_t)p.La, p.drop.thresh) ? e1 : 0.f;
+          }
           pk[i >> 1] = pack_bf16(e0, e1);
         }
       }
@@ -539,7 +555,7 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       if (nsplit == 1) {
         // out (bf16, two 64-column boxes) and optionally its fp32 copy (four 32-column boxes) leave through this
         // warp's staging area: [bf16 box 0 | bf16 box 1 | fp32 box 0..3]
-        const float inv_l = 1.0f / l;
+        const float inv_l = p.drop.inv_keep / l;    // inverted dropout: kept probabilities are scaled by 1 / (1 - p)
         uint32_t ocur[32], onext[32];
         SAM2B200_TMEM_LD32(lane_addr + kColAcc + half * 128, ocur);
 #pragma unroll
@@ -571,14 +587,15 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           if (row_valid) {
 #pragma unroll
             for (int v = 0; v < 8; ++v)
-              *reinterpret_cast<uint4*>(orow + cc * 32 + v * 4) =
-                  make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+              *reinterpret_cast<float4*>(orow + cc * 32 + v * 4) =
+                  make_float4(__uint_as_float(o[4 * v]) * p.drop.inv_keep, __uint_as_float(o[4 * v + 1]) * p.drop.inv_keep,
+                              __uint_as_float(o[4 * v + 2]) * p.drop.inv_keep, __uint_as_float(o[4 * v + 3]) * p.drop.inv_keep);
           }
         }
         if (row_valid && half == 0) { p.part_ml[prow * 2] = m_ref * c; p.part_ml[prow * 2 + 1] = l; }
       }
     } else {
-      grad_epilogue(p.gout, &map_o, stage, lane_addr + kColAcc, half, lane, row0, p.La, b, 1.0f, rotate, tcur);
+      grad_epilogue(p.gout, &map_o, stage, lane_addr + kColAcc, half, lane, row0, p.La, b, p.drop.inv_keep, rotate, tcur);
     }
   }
 
@@ -610,6 +627,7 @@ struct ThreeGemmParams {
   const float* lse2;           // [B, N]   log2-domain LSE of the forward
   const float* delta;          // [B, N]   rowsum(dO o O)
   GradOut gout;                // dQ / dK
+  sam2b200::Dropout drop;      // attention-probability dropout: dP is masked and scaled like P was in the forward
   unsigned long long* dbg;     // optional timeline buffer
 };
 
@@ -797,6 +815,8 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
     const uint32_t stage = smem_u32(&sh.a2[0]) + warp * (4 * kBoxBytes);   // epilogue staging in the (then idle) operand buffers
     const bool rotate = p.gout.rope_table != nullptr && (row0 + lane) < p.gout.rope_rows;
     const float c = p.scale_log2;
+    const bool drop_on = p.drop.seed != nullptr;
+    const uint32_t drop_key = drop_on ? sam2b200::dropout_key(*p.drop.seed, p.drop.site) : 0u;
     float row_lse = 0.f, row_delta = 0.f;
     if (MODE == MODE_DQ && row_valid) {
       row_lse = p.lse2[(long long)b * p.La + a_row_idx];
@@ -846,10 +866,19 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
         uint32_t r0[32];
         SAM2B200_TMEM_LD32(lane_addr + k3ColDP + half * kHalfN, r0);
         tmem_wait_ld();
+        // element (query q, key k) has dropout index (b N + q) M + k: DQ rows are queries, DK rows are keys
+        const uint32_t didx = (MODE == MODE_DQ)
+            ? (uint32_t)(((long long)b * p.La + a_row_idx) * p.Lx) + (uint32_t)(j * kBlockN + half * kHalfN)
+            : (uint32_t)(((long long)b * p.Lx + (j * kBlockN + half * kHalfN)) * p.La + a_row_idx);
+        const uint32_t dstep = (MODE == MODE_DQ) ? 1u : (uint32_t)p.La;
 #pragma unroll
         for (int i = 0; i < kHalfN; i += 2) {
-          const float d0 = __uint_as_float(r0[i]);
-          const float d1 = __uint_as_float(r0[i + 1]);
+          float d0 = __uint_as_float(r0[i]);
+          float d1 = __uint_as_float(r0[i + 1]);
+          if (drop_on) {
+            d0 = sam2b200::dropout_keep(drop_key, didx + (uint32_t)i * dstep, p.drop.thresh) ? d0 * p.drop.inv_keep : 0.f;
+            d1 = sam2b200::dropout_keep(drop_key, didx + (uint32_t)(i + 1) * dstep, p.drop.thresh) ? d1 * p.drop.inv_keep : 0.f;
+          }
           const float dl0 = (MODE == MODE_DQ) ? row_delta : sh.col_delta[j & 1][half * kHalfN + i];
           const float dl1 = (MODE == MODE_DQ) ? row_delta : sh.col_delta[j & 1][half * kHalfN + i + 1];
           pk[i >> 1] = pack_bf16(pv[i] * (d0 - dl0), pv[i + 1] * (d1 - dl1));

@@ -33,6 +33,7 @@ struct PairParams {
   const float* lse2;           // [B, Lq] log2-domain LSE of the forward
   const float* delta;          // [B, Lq] rowsum(dO o O)
   GradOut gout_v, gout_k;
+  sam2b200::Dropout drop;      // attention-probability dropout; element index (b Lq + q) Lk + key
 };
 
 constexpr int kPairStages = 2;     // tile ring (a 2-GEMM loop needs its next tiles ~1.5 tile times ahead: two stages suffice)
@@ -247,6 +248,9 @@ kv_pair_kernel(const __grid_constant__ CUtensorMap map_q64, const __grid_constan
     const GradOut& gout = kside ? p.gout_k : p.gout_v;
     const bool rotate = gout.rope_table != nullptr && (row0 + lane) < gout.rope_rows;
     const float c = p.scale_log2;
+    const bool drop_on = p.drop.seed != nullptr;
+    const uint32_t drop_key = drop_on ? sam2b200::dropout_key(*p.drop.seed, p.drop.site) : 0u;
+    const long long key_row = (long long)a_tile * kBlockM + row;
     // this thread's 64 bytes of the P^T exchange tile (row `row`, 16-byte chunks 4*half .. 4*half+3, XOR-swizzled)
     const uint32_t p_local = smem_u32(&sh.p_buf[0][0]) + row * 128;
     const uint32_t p_remote = map_to_rank(p_local, 1);                       // rank 0 writes into rank 1's buffers
@@ -276,13 +280,18 @@ kv_pair_kernel(const __grid_constant__ CUtensorMap map_q64, const __grid_constan
       uint32_t pk[16];
       if (!kside) {
         // ---- V side: P^T = exp2(S^T c - LSE2[q]); keep it (TMEM, A operand of dV += P^T dO) and ship it to the partner
+        const uint32_t didx = (uint32_t)(((long long)b * p.Lq + (j * kBlockN + half * kHalfN)) * p.Lk + key_row);
+        uint32_t pm[16];     // dropout-masked copy for this side's dV GEMM; the partner needs the un-masked P^T
 #pragma unroll
         for (int i = 0; i < kHalfN; i += 2) {
           const float e0 = ex2(fmaf(__uint_as_float(r0[i]), c, -cv[i]));
           const float e1 = ex2(fmaf(__uint_as_float(r0[i + 1]), c, -cv[i + 1]));
           pk[i >> 1] = pack_bf16(e0, e1);
+          if (drop_on)
+            pm[i >> 1] = pack_bf16(sam2b200::dropout_keep(drop_key, didx + (uint32_t)i * (uint32_t)p.Lk, p.drop.thresh) ? e0 : 0.f,
+                                   sam2b200::dropout_keep(drop_key, didx + (uint32_t)(i + 1) * (uint32_t)p.Lk, p.drop.thresh) ? e1 : 0.f);
         }
-        SAM2B200_TMEM_ST16(sbuf + half * kHalfN, pk);
+        if (drop_on) { SAM2B200_TMEM_ST16(sbuf + half * kHalfN, pm); } else { SAM2B200_TMEM_ST16(sbuf + half * kHalfN, pk); }
         tmem_wait_st();
         // own pipeline first: the dV GEMM of this tile must not wait for the partner
         if (j > 0) mbar_wait(&sh.acc_done, (j - 1) & 1);
@@ -311,11 +320,17 @@ kv_pair_kernel(const __grid_constant__ CUtensorMap map_q64, const __grid_constan
         for (int q4 = 0; q4 < 4; ++q4) pv[q4] = lds128(p_local + pb * kPBufBytes + (((half * 4 + q4) ^ (row & 7)) << 4));
         const uint32_t pw[16] = {pv[0].x, pv[0].y, pv[0].z, pv[0].w, pv[1].x, pv[1].y, pv[1].z, pv[1].w,
                                  pv[2].x, pv[2].y, pv[2].z, pv[2].w, pv[3].x, pv[3].y, pv[3].z, pv[3].w};
+        const uint32_t didx = (uint32_t)(((long long)b * p.Lq + (j * kBlockN + half * kHalfN)) * p.Lk + key_row);
 #pragma unroll
         for (int i = 0; i < kHalfN; i += 2) {
           const __nv_bfloat162 pp = *reinterpret_cast<const __nv_bfloat162*>(&pw[i >> 1]);
           const float2 pf = __bfloat1622float2(pp);
-          pk[i >> 1] = pack_bf16(pf.x * (__uint_as_float(r0[i]) - cv[i]), pf.y * (__uint_as_float(r0[i + 1]) - cv[i + 1]));
+          float d0 = __uint_as_float(r0[i]), d1 = __uint_as_float(r0[i + 1]);
+          if (drop_on) {
+            d0 = sam2b200::dropout_keep(drop_key, didx + (uint32_t)i * (uint32_t)p.Lk, p.drop.thresh) ? d0 * p.drop.inv_keep : 0.f;
+            d1 = sam2b200::dropout_keep(drop_key, didx + (uint32_t)(i + 1) * (uint32_t)p.Lk, p.drop.thresh) ? d1 * p.drop.inv_keep : 0.f;
+          }
+          pk[i >> 1] = pack_bf16(pf.x * (d0 - cv[i]), pf.y * (d1 - cv[i + 1]));
         }
         SAM2B200_TMEM_ST16(sbuf + half * kHalfN, pk);
         // Hand the buffer back.  RELAXED on purpose: a release.cluster arrive here (8 per tile) measured +0.3 us per tile
@@ -335,7 +350,7 @@ kv_pair_kernel(const __grid_constant__ CUtensorMap map_q64, const __grid_constan
     load_table_chunk(gout, rotate, row0 + lane, half * 128, tcur);
     mbar_wait(&sh.acc_done, (nt - 1) & 1);
     tc_fence_after();
-    grad_epilogue(gout, map_o, stage, lane_addr + kColAcc, half, lane, row0, p.Lk, b, kside ? p.scale : 1.0f, rotate, tcur);
+    grad_epilogue(gout, map_o, stage, lane_addr + kColAcc, half, lane, row0, p.Lk, b, kside ? p.scale : p.drop.inv_keep, rotate, tcur);
   }
 
   tc_fence_before();

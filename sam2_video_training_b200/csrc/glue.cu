@@ -13,6 +13,7 @@
 #include <stdint.h>
 
 #include "abi_common.cuh"
+#include "dropout.cuh"
 
 namespace {
 
@@ -46,7 +47,9 @@ __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ res, float* __restrict__ x_out,
               const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ y16,
               float* __restrict__ y32, float* __restrict__ mean, float* __restrict__ rstd, long long rows,
-              float eps, int tr_b, int tr_n) {
+              float eps, int tr_b, int tr_n, const sam2b200::Dropout drop) {
+  // drop: inverted dropout on the residual branch, x' = x + dropout(res) (memory_attention.py:64,81,99);
+  // element index = row * 256 + column
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -57,6 +60,12 @@ ln_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ res
   if (res != nullptr) {
     float r[8];
     unpack8(*reinterpret_cast<const uint4*>(res + row * kD + lane * 8), r);
+    if (drop.seed != nullptr) {
+      const uint32_t key = sam2b200::dropout_key(*drop.seed, drop.site);
+      const uint32_t idx = (uint32_t)(row * kD + lane * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = sam2b200::dropout_keep(key, idx + i, drop.thresh) ? r[i] * drop.inv_keep : 0.f;
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] += r[i];
     if (x_out != nullptr) {
@@ -99,7 +108,9 @@ __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ dy32, const float* __restrict__ x,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
               const float* __restrict__ g_in, float* __restrict__ g_out, __nv_bfloat16* __restrict__ g16,
-              float* __restrict__ part, long long rows, int tr_b, int tr_n) {
+              float* __restrict__ part, long long rows, int tr_b, int tr_n, const sam2b200::Dropout drop) {
+  // drop: the dropout that sat on the branch whose output gradient g16 is (x' = x + dropout(branch)): g_out (the
+  // residual-stream gradient) is not masked, its bf16 copy for the branch is.
   // g16 (optional): bf16 copy of g_out -- the operand of the next GEMMs of the backward chain -- and a third partial
   // row with its column sums (the bias gradient of the projection whose output gradient g_out is).
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -149,6 +160,12 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ 
     op[0] = make_float4(o[0], o[1], o[2], o[3]);
     op[1] = make_float4(o[4], o[5], o[6], o[7]);
     if (g16 != nullptr) {
+      if (drop.seed != nullptr) {
+        const uint32_t key = sam2b200::dropout_key(*drop.seed, drop.site);
+        const uint32_t idx = (uint32_t)(row * kD + lane * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = sam2b200::dropout_keep(key, idx + i, drop.thresh) ? o[i] * drop.inv_keep : 0.f;
+      }
       const uint4 u = pack8(o);
       *reinterpret_cast<uint4*>(g16 + row * kD + lane * 8) = u;
       float r[8];
@@ -200,7 +217,9 @@ partial_reduce_add_kernel(const float* __restrict__ part, int nblk, int width, f
 template <int MODE>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ in32, __nv_bfloat16* __restrict__ io16, const __nv_bfloat16* __restrict__ h16,
-              float* __restrict__ part, long long rows, int C, long long ld) {
+              float* __restrict__ part, long long rows, int C, long long ld, float scale) {
+  // scale (MODE 1): 1 / (1 - p) of the dropout that followed the ReLU -- h16 is the DROPPED activation, so (h > 0)
+  // is the ReLU mask and the dropout mask at once
   const int tpr = C >> 3;                         // threads per row
   const int rpb = blockDim.x / tpr;               // rows per block iteration
   const int cgrp = threadIdx.x % tpr;
@@ -229,7 +248,7 @@ colsum_kernel(const float* __restrict__ in32, __nv_bfloat16* __restrict__ io16, 
           float hv[8];
           unpack8(*reinterpret_cast<const uint4*>(h16 + row * ld + cgrp * 8), hv);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = hv[i] > 0.f ? v[i] : 0.f;
+          for (int i = 0; i < 8; ++i) v[i] = hv[i] > 0.f ? v[i] * scale : 0.f;
           *reinterpret_cast<uint4*>(io16 + row * ld + cgrp * 8) = pack8(v);
         }
       }
@@ -251,6 +270,25 @@ colsum_kernel(const float* __restrict__ in32, __nv_bfloat16* __restrict__ io16, 
   }
 }
 
+__global__ void __launch_bounds__(256)
+dropout_inplace_kernel(__nv_bfloat16* __restrict__ x, long long groups, const sam2b200::Dropout drop) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= groups) return;
+  const uint32_t key = sam2b200::dropout_key(*drop.seed, drop.site);
+  float v[8];
+  unpack8(*reinterpret_cast<const uint4*>(x + g * 8), v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = sam2b200::dropout_keep(key, (uint32_t)(g * 8 + i), drop.thresh) ? v[i] * drop.inv_keep : 0.f;
+  *reinterpret_cast<uint4*>(x + g * 8) = pack8(v);
+}
+
+__global__ void dropout_mask_kernel(unsigned char* __restrict__ out, long long index0, long long n, const sam2b200::Dropout drop) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool keep = drop.seed == nullptr || sam2b200::dropout_keep(sam2b200::dropout_key(*drop.seed, drop.site), (uint32_t)(index0 + i), drop.thresh);
+  out[i] = keep ? 1 : 0;
+}
+
 int grid_for_rows(long long rows, int rows_per_block) {
   long long g = (rows + rows_per_block - 1) / rows_per_block;
   const long long cap = 148 * 2;
@@ -267,13 +305,15 @@ extern "C" {
 // NULL.  tr_b > 0: y32 is written seq-first ([n][b][256]) from batch-first rows (b*tr_n + n).
 int sam2b200_ln_fwd(const float* x, const void* res_bf16, float* x_out, const float* gamma, const float* beta,
                     void* y_bf16, float* y_f32, float* mean, float* rstd, long long rows, float eps, int tr_b,
-                    int tr_n, cudaStream_t stream) {
+                    int tr_n, float drop_p, const unsigned long long* drop_seed, unsigned drop_site, cudaStream_t stream) {
   if (!x || !gamma || !beta || rows <= 0 || !aligned16(x) || (res_bf16 && !aligned16(res_bf16)) ||
-      (x_out && !aligned16(x_out)) || (y_bf16 && !aligned16(y_bf16)) || (y_f32 && !aligned16(y_f32)))
+      (x_out && !aligned16(x_out)) || (y_bf16 && !aligned16(y_bf16)) || (y_f32 && !aligned16(y_f32)) || drop_p < 0.f ||
+      drop_p >= 1.f || rows * kD >= (1LL << 32))
     return sam2b200::fail(SAM2B200_ERR_INVALID, "ln_fwd: bad arguments");
   const long long blocks = (rows * 32 + 255) / 256;
   ln_fwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, (const __nv_bfloat16*)res_bf16, x_out, gamma, beta,
-                                                       (__nv_bfloat16*)y_bf16, y_f32, mean, rstd, rows, eps, tr_b, tr_n);
+                                                       (__nv_bfloat16*)y_bf16, y_f32, mean, rstd, rows, eps, tr_b, tr_n,
+                                                       sam2b200::make_dropout(drop_seed, drop_site, drop_p));
   return sam2b200::check_launch("ln_fwd");
 }
 
@@ -286,15 +326,17 @@ size_t sam2b200_ln_bwd_workspace_bytes(long long rows) {
 // g_out_bf16 / dbias (optional, both or neither): bf16 copy of g_out for the next GEMMs and dbias += its column sums.
 int sam2b200_ln_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* mean, const float* rstd,
                     const float* gamma, const float* g_in, float* g_out, void* g_out_bf16, float* dgamma, float* dbeta,
-                    float* dbias, void* workspace, long long rows, int tr_b, int tr_n, cudaStream_t stream) {
+                    float* dbias, void* workspace, long long rows, int tr_b, int tr_n, float drop_p,
+                    const unsigned long long* drop_seed, unsigned drop_site, cudaStream_t stream) {
   if ((!dy_bf16) == (!dy_f32) || !x || !mean || !rstd || !gamma || !g_out || !dgamma || !dbeta || !workspace ||
-      rows <= 0 || (!g_out_bf16) != (!dbias))
+      rows <= 0 || (!g_out_bf16) != (!dbias) || drop_p < 0.f || drop_p >= 1.f)
     return sam2b200::fail(SAM2B200_ERR_INVALID, "ln_bwd: bad arguments");
   const int nblk = grid_for_rows(rows, 8 * 8);
   const int nrow = g_out_bf16 ? 3 : 2;
   float* part = static_cast<float*>(workspace);
   ln_bwd_kernel<<<nblk, 256, 0, stream>>>((const __nv_bfloat16*)dy_bf16, dy_f32, x, mean, rstd, gamma, g_in, g_out,
-                                          (__nv_bfloat16*)g_out_bf16, part, rows, tr_b, tr_n);
+                                          (__nv_bfloat16*)g_out_bf16, part, rows, tr_b, tr_n,
+                                          sam2b200::make_dropout(drop_seed, drop_site, drop_p));
   partial_reduce_add_kernel<<<(nrow * kD + 31) / 32, 256, 0, stream>>>(part, nblk, nrow * kD, dgamma, dbeta, kD, dbias);
   return sam2b200::check_launch("ln_bwd", 2);
 }
@@ -309,7 +351,7 @@ size_t sam2b200_colsum_workspace_bytes(long long rows, int C) {
 // mode 2: colsum += column sums of io_bf16 (row stride ld elements)
 // C must be a multiple of 8 with C/8 dividing 256 (256, 512, 1024, 2048) or equal to 768.
 int sam2b200_colsum(int mode, const float* in_f32, void* io_bf16, const void* h_bf16, float* colsum, void* workspace,
-                    long long rows, int C, long long ld, cudaStream_t stream) {
+                    long long rows, int C, long long ld, float scale, cudaStream_t stream) {
   if (rows <= 0 || C <= 0 || (C % 8) || (C / 8) > 256 || !colsum || !workspace || !io_bf16 || (mode == 0 && !in_f32) ||
       (mode == 1 && !h_bf16) || mode < 0 || mode > 2)
     return sam2b200::fail(SAM2B200_ERR_INVALID, "colsum: bad arguments");
@@ -320,14 +362,36 @@ int sam2b200_colsum(int mode, const float* in_f32, void* io_bf16, const void* h_
   float* part = static_cast<float*>(workspace);
   const size_t sh = (size_t)rpb * C * sizeof(float);
   if (mode == 0)
-    colsum_kernel<0><<<nblk, 256, sh, stream>>>(in_f32, (__nv_bfloat16*)io_bf16, nullptr, part, rows, C, ld);
+    colsum_kernel<0><<<nblk, 256, sh, stream>>>(in_f32, (__nv_bfloat16*)io_bf16, nullptr, part, rows, C, ld, 1.0f);
   else if (mode == 1)
     colsum_kernel<1><<<nblk, 256, sh, stream>>>(nullptr, (__nv_bfloat16*)io_bf16, (const __nv_bfloat16*)h_bf16, part,
-                                                rows, C, ld);
+                                                rows, C, ld, scale);
   else
-    colsum_kernel<2><<<nblk, 256, sh, stream>>>(nullptr, (__nv_bfloat16*)io_bf16, nullptr, part, rows, C, ld);
+    colsum_kernel<2><<<nblk, 256, sh, stream>>>(nullptr, (__nv_bfloat16*)io_bf16, nullptr, part, rows, C, ld, 1.0f);
   partial_reduce_add_kernel<<<(C + 31) / 32, 256, 0, stream>>>(part, nblk, C, colsum, colsum, C);
   return sam2b200::check_launch("colsum", 2);
+}
+
+// Inverted dropout in place on a bf16 tensor of n elements (the MLP's hidden activation, memory_attention.py:97:
+// linear2(dropout(relu(linear1(x))))); element index = flat index.
+int sam2b200_dropout_inplace(void* x_bf16, long long n, float drop_p, const unsigned long long* drop_seed,
+                             unsigned drop_site, cudaStream_t stream) {
+  if (!x_bf16 || n <= 0 || (n % 8) || n >= (1LL << 32) || !aligned16(x_bf16) || drop_p < 0.f || drop_p >= 1.f || !drop_seed)
+    return sam2b200::fail(SAM2B200_ERR_INVALID, "dropout_inplace: bad arguments");
+  if (drop_p == 0.f) return SAM2B200_OK;
+  const long long groups = n / 8;
+  dropout_inplace_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, stream>>>((__nv_bfloat16*)x_bf16, groups,
+                                                                               sam2b200::make_dropout(drop_seed, drop_site, drop_p));
+  return sam2b200::check_launch("dropout_inplace");
+}
+
+// Test aid: the keep mask (1 = kept) of elements [index0, index0 + n) of one dropout site, as bytes.
+int sam2b200_dropout_mask(unsigned char* out, long long index0, long long n, float drop_p,
+                          const unsigned long long* drop_seed, unsigned drop_site, cudaStream_t stream) {
+  if (!out || n <= 0 || index0 < 0 || index0 + n > (1LL << 32) || drop_p < 0.f || drop_p >= 1.f || !drop_seed)
+    return sam2b200::fail(SAM2B200_ERR_INVALID, "dropout_mask: bad arguments");
+  dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(out, index0, n, sam2b200::make_dropout(drop_seed, drop_site, drop_p));
+  return sam2b200::check_launch("dropout_mask");
 }
 
 }  // extern "C"

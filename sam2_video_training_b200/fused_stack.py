@@ -39,9 +39,16 @@ def _stream(dev) -> int:
     return torch.cuda.current_stream(dev).cuda_stream
 
 
-def ln_fwd(x, res, gamma, beta, want_f32_seq_first=None, eps=1e-5):
+def _drop(drop):
+    """drop = None | (p, seed int64 device tensor [1], site) -> (p, seed pointer, site) of the C ABI."""
+    if drop is None or drop[0] <= 0.0:
+        return 0.0, None, 0
+    return float(drop[0]), drop[1].data_ptr(), int(drop[2])
+
+
+def ln_fwd(x, res, gamma, beta, want_f32_seq_first=None, eps=1e-5, drop=None):
     """x: [R,256] fp32; res: [R,256] bf16 or None.  Returns (y, x_new, mean, rstd); y is bf16 [R,256] or,
-    if want_f32_seq_first=(B, N), fp32 [N, B, 256]."""
+    if want_f32_seq_first=(B, N), fp32 [N, B, 256].  drop = (p, seed, site): x_new = x + dropout(res)."""
     lib = _lib.load()
     rows = x.shape[0]
     dev = x.device
@@ -57,13 +64,14 @@ def ln_fwd(x, res, gamma, beta, want_f32_seq_first=None, eps=1e-5):
         y16, y32 = None, y.data_ptr()
     rc = lib.sam2b200_ln_fwd(x.data_ptr(), res.data_ptr() if res is not None else None,
                              x_new.data_ptr() if res is not None else None, gamma.data_ptr(), beta.data_ptr(),
-                             y16, y32, mean.data_ptr(), rstd.data_ptr(), rows, eps, tb, tn, _stream(dev))
+                             y16, y32, mean.data_ptr(), rstd.data_ptr(), rows, eps, tb, tn, *_drop(drop), _stream(dev))
     _lib.check(rc, "sam2b200_ln_fwd")
     return y, x_new, mean, rstd
 
 
-def ln_bwd(dy, x, mean, rstd, gamma, g_in, dgamma, dbeta, seq_first=None, dbias=None):
-    """Returns g_out (fp32) or, with dbias, (g_out, bf16 copy of g_out) and dbias += column sums of the copy."""
+def ln_bwd(dy, x, mean, rstd, gamma, g_in, dgamma, dbeta, seq_first=None, dbias=None, drop=None):
+    """Returns g_out (fp32) or, with dbias, (g_out, bf16 copy of g_out) and dbias += column sums of the copy.
+    drop = (p, seed, site): the copy is the gradient of a branch that went through dropout -> masked and scaled."""
     lib = _lib.load()
     rows = x.shape[0]
     dev = x.device
@@ -76,18 +84,19 @@ def ln_bwd(dy, x, mean, rstd, gamma, g_in, dgamma, dbeta, seq_first=None, dbias=
                              mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
                              g_in.data_ptr() if g_in is not None else None, g_out.data_ptr(),
                              g16.data_ptr() if g16 is not None else None, dgamma.data_ptr(), dbeta.data_ptr(),
-                             dbias.data_ptr() if dbias is not None else None, ws.data_ptr(), rows, tb, tn, _stream(dev))
+                             dbias.data_ptr() if dbias is not None else None, ws.data_ptr(), rows, tb, tn, *_drop(drop),
+                             _stream(dev))
     _lib.check(rc, "sam2b200_ln_bwd")
     return g_out if dbias is None else (g_out, g16)
 
 
-def _colsum(mode, in32, io16, h16, colsum, rows, c, ld=0):
+def _colsum(mode, in32, io16, h16, colsum, rows, c, ld=0, scale=1.0):
     lib = _lib.load()
     dev = io16.device
     ws = torch.empty(max(lib.sam2b200_colsum_workspace_bytes(rows, c) // 4, 1), dtype=F32, device=dev)
     rc = lib.sam2b200_colsum(mode, in32.data_ptr() if in32 is not None else None, io16.data_ptr(),
                              h16.data_ptr() if h16 is not None else None, colsum.data_ptr(), ws.data_ptr(), rows, c,
-                             ld, _stream(dev))
+                             ld, float(scale), _stream(dev))
     _lib.check(rc, "sam2b200_colsum")
 
 
@@ -98,8 +107,16 @@ def cast_colsum(g32, colsum):
     return out
 
 
-def relu_bwd_colsum_(dh16, h16, colsum):
-    _colsum(1, None, dh16, h16, colsum, dh16.shape[0], dh16.shape[1])
+def relu_bwd_colsum_(dh16, h16, colsum, scale=1.0):
+    """dh *= (h > 0) * scale in place; h is the (possibly dropped) activation, scale = 1 / (1 - p) of that dropout."""
+    _colsum(1, None, dh16, h16, colsum, dh16.shape[0], dh16.shape[1], scale=scale)
+
+
+def dropout_inplace_(x16, drop):
+    p_, seed, site = _drop(drop)
+    if p_ > 0.0:
+        rc = _lib.load().sam2b200_dropout_inplace(x16.data_ptr(), x16.numel(), p_, seed, site, _stream(x16.device))
+        _lib.check(rc, "sam2b200_dropout_inplace")
 
 
 def colsum_bf16(x16, colsum):
@@ -267,6 +284,13 @@ class MemoryAttentionStackFn(torch.autograd.Function):
         res = None
         side = _SideStream(x.device)
         kv_ready = []
+        # train-mode dropout (memory_attention.py:58-99, transformer.py:304-306): dr = dict(seed, p_res, p_sa, p_ca) | None.
+        # Site ids: layer * 8 + {0 self-attn probabilities, 1 cross-attn probabilities, 2 dropout1, 3 dropout2,
+        # 4 MLP hidden, 5 dropout3}; the masks are regenerated from (seed, site) in the backward.
+        dr = meta.get("dropout")
+
+        def dsite(p_key, l, k):
+            return (dr[p_key], dr["seed"], l * 8 + k) if dr is not None and dr[p_key] > 0.0 else None
 
         def project_memory():        # cross-attention keys / values of every layer: functions of the bank only
             for l in range(nl):
@@ -281,39 +305,40 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             P = dict(zip(_LAYER_KEYS, params[l * _NPL:(l + 1) * _NPL]))
             W = dict(zip(_LAYER_KEYS, wb[l * _NPL:(l + 1) * _NPL]))
             # ---- self attention (memory_attention.py:58-64)
-            y1, x, mean1, rstd1 = ln_fwd(x, res, P["n1.w"], P["n1.b"])
+            y1, x, mean1, rstd1 = ln_fwd(x, res, P["n1.w"], P["n1.b"], drop=dsite("p_res", l - 1, 5) if l > 0 else None)
             q = torch.addmm(W["sa.q.b"], y1, W["sa.q.w"].t())
             k = torch.addmm(W["sa.k.b"], y1, W["sa.k.w"].t())
             v = torch.addmm(W["sa.v.b"], y1, W["sa.v.w"].t())
             q_rot = rope_apply(q.view(b, n, d), table, n)
             k_rot = rope_apply(k.view(b, n, d), table, n)
-            o, o32, lse = attn_fwd(q_rot, k_rot, v.view(b, n, d), scale, meta["nsplit"])
+            o, o32, lse = attn_fwd(q_rot, k_rot, v.view(b, n, d), scale, meta["nsplit"], drop=dsite("p_sa", l, 0))
             sa = torch.addmm(W["sa.o.b"], o.view(r, d), W["sa.o.w"].t())
             # ---- cross attention to the memory bank (memory_attention.py:66-81)
-            y2, x1, mean2, rstd2 = ln_fwd(x, sa, P["n2.w"], P["n2.b"])
+            y2, x1, mean2, rstd2 = ln_fwd(x, sa, P["n2.w"], P["n2.b"], drop=dsite("p_res", l, 2))
             q2 = torch.addmm(W["ca.q.b"], y2, W["ca.q.w"].t())
             q2_rot = rope_apply(q2.view(b, n, d), table, n)
             k2_rot, v2, ev = kv_ready[l]
             side.wait(ev)
-            o2, o2_32, lse2 = attn_fwd(q2_rot, k2_rot, v2.view(b, m, d), scale, meta["nsplit"])
+            o2, o2_32, lse2 = attn_fwd(q2_rot, k2_rot, v2.view(b, m, d), scale, meta["nsplit"], drop=dsite("p_ca", l, 1))
             ca = torch.addmm(W["ca.o.b"], o2.view(r, d), W["ca.o.w"].t())
             # ---- MLP (memory_attention.py:95-98)
-            y3, x2, mean3, rstd3 = ln_fwd(x1, ca, P["n3.w"], P["n3.b"])
+            y3, x2, mean3, rstd3 = ln_fwd(x1, ca, P["n3.w"], P["n3.b"], drop=dsite("p_res", l, 3))
             h = torch._addmm_activation(W["l1.b"], y3, W["l1.w"].t(), use_gelu=False)  # bias + ReLU epilogue
+            dropout_inplace_(h, dsite("p_res", l, 4))
             mlp = torch.addmm(W["l2.b"], h, W["l2.w"].t())
             saved += [x, mean1, rstd1, y1, q_rot, k_rot, v, o, o32, lse,
                       x1, mean2, rstd2, y2, q2_rot, k2_rot, v2, o2, o2_32, lse2,
                       x2, mean3, rstd3, y3, h]
             x, res = x2, mlp
         gamma_f, beta_f = params[nl * _NPL], params[nl * _NPL + 1]
-        out, x_fin, mean_f, rstd_f = ln_fwd(x, res, gamma_f, beta_f, want_f32_seq_first=(b, n))
+        out, x_fin, mean_f, rstd_f = ln_fwd(x, res, gamma_f, beta_f, want_f32_seq_first=(b, n), drop=dsite("p_res", nl - 1, 5))
         side.join()
         saved += [x_fin, mean_f, rstd_f, memk, memv, table]
         ctx.save_for_backward(*saved, *params)
         ctx.n_saved = len(saved)
         ctx.meta = dict(nl=nl, n=n, b=b, m=m, scale=scale, n_rope_k=n_rope_k, pos_at_input=pos_at_input,
                         has_pos=curr_pos is not None, bucket=meta.get("bucket"), masters=masters,
-                        direct=bool(meta.get("direct")))
+                        direct=bool(meta.get("direct")), dropout=dr)
         return out
 
     @staticmethod
@@ -353,6 +378,11 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                 off += params[i].numel()
 
         side = _SideStream(dev)
+        dr = mt["dropout"]
+
+        def dsite(p_key, l, k):
+            return (dr[p_key], dr["seed"], l * 8 + k) if dr is not None and dr[p_key] > 0.0 else None
+        relu_scale = 1.0 / (1.0 - dr["p_res"]) if dr is not None and dr["p_res"] > 0.0 else 1.0
 
         def acc_w(i, a_t, bmat, bias=None):     # grad[i] (+)= a_t @ bmat (bf16 x bf16 -> fp32); bias grad (+)= colsum(a_t^T)
             def work():
@@ -368,7 +398,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
         # bias gradient of the projection in front of it: no separate cast + column-sum pass
         last = (nl - 1) * _NPL
         g, g16 = ln_bwd(grad_out, x_fin, mean_f, rstd_f, params[nl * _NPL], None, gv[nl * _NPL], gv[nl * _NPL + 1],
-                        seq_first=(b, n), dbias=gv[last + _LAYER_KEYS.index("l2.b")])
+                        seq_first=(b, n), dbias=gv[last + _LAYER_KEYS.index("l2.b")], drop=dsite("p_res", nl - 1, 5))
         dmemk = torch.zeros((rm, memk.shape[1]), dtype=F32, device=dev) if need_memgrad else None
         dmemv = torch.zeros((rm, memv.shape[1]), dtype=F32, device=dev) if need_mem else None
         per = 25
@@ -383,10 +413,11 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             dm = g16
             acc_w(ix["l2.w"], dm.t(), h)
             dh = torch.mm(dm, W["l2.w"])
-            relu_bwd_colsum_(dh, h, gv[ix["l1.b"]])
+            relu_bwd_colsum_(dh, h, gv[ix["l1.b"]], scale=relu_scale)
             acc_w(ix["l1.w"], dh.t(), y3)
             dy3 = torch.mm(dh, W["l1.w"])
-            g, dca = ln_bwd(dy3, x2, mean3, rstd3, P["n3.w"], g, gv[ix["n3.w"]], gv[ix["n3.b"]], dbias=gv[ix["ca.o.b"]])
+            g, dca = ln_bwd(dy3, x2, mean3, rstd3, P["n3.w"], g, gv[ix["n3.w"]], gv[ix["n3.b"]], dbias=gv[ix["ca.o.b"]],
+                            drop=dsite("p_res", l, 3))
             # ---- cross attention backward
             acc_w(ix["ca.o.w"], dca.t(), o2.view(r, d))
             do2 = torch.mm(dca, W["ca.o.w"])
@@ -395,7 +426,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             # they feed (weight gradients, memory-bank gradients) go to the side stream.
             delta = torch.empty((b, n), dtype=F32, device=dev)
             args = (q2_rot, k2_rot, v2.view(b, m, d), None, o2_32, do2.view(b, n, d), lse2, scale)
-            kw = dict(table=table, n_rope_k=n_rope_k, grad_dtype=BF16, delta=delta)
+            kw = dict(table=table, n_rope_k=n_rope_k, grad_dtype=BF16, delta=delta, drop=dsite("p_ca", l, 1))
             attn_bwd(*args, parts=1, **kw)                                              # Delta = rowsum(dO o O)
 
             def key_side(args=args, kw=kw, l=l, ix=ix, W=W):
@@ -416,14 +447,15 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             dq2 = dq2.view(r, d)
             dy2 = torch.mm(dq2, W["ca.q.w"])
             acc_w(ix["ca.q.w"], dq2.t(), y2)
-            g, dsa = ln_bwd(dy2, x1, mean2, rstd2, P["n2.w"], g, gv[ix["n2.w"]], gv[ix["n2.b"]], dbias=gv[ix["sa.o.b"]])
+            g, dsa = ln_bwd(dy2, x1, mean2, rstd2, P["n2.w"], g, gv[ix["n2.w"]], gv[ix["n2.b"]], dbias=gv[ix["sa.o.b"]],
+                            drop=dsite("p_res", l, 2))
             # ---- self attention backward
             acc_w(ix["sa.o.w"], dsa.t(), o.view(r, d))
             do = torch.mm(dsa, W["sa.o.w"])
             dqkv = torch.empty((b, n, 3 * d), dtype=BF16, device=dev)   # [dq | dk | dv], written in place by the kernels
             attn_bwd(q_rot, k_rot, v.view(b, n, d), None, o32, do.view(b, n, d), lse, scale, table=table, n_rope_k=n,
                      grad_dtype=BF16, dq=dqkv[:, :, :d], dk=dqkv[:, :, d:2 * d], dv=dqkv[:, :, 2 * d:],
-                     dbias=(gv[ix["sa.q.b"]], gv[ix["sa.k.b"]], gv[ix["sa.v.b"]]))
+                     dbias=(gv[ix["sa.q.b"]], gv[ix["sa.k.b"]], gv[ix["sa.v.b"]]), drop=dsite("p_sa", l, 0))
             dqkv = dqkv.view(r, 3 * d)
             qkv_w = [masters[ix[k]] for k in ("sa.q.w", "sa.k.w", "sa.v.w")]
             gw = bucket.span(qkv_w, (3 * d, d)) if direct else None
@@ -439,7 +471,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             dy1 = torch.mm(dqkv, wqkv_all[l])            # stacked [768, 256] weights: contraction over 768, fp32 accumulation
             if l > 0:
                 g, g16 = ln_bwd(dy1, x0, mean1, rstd1, P["n1.w"], g, gv[ix["n1.w"]], gv[ix["n1.b"]],
-                                dbias=gv[base - _NPL + _LAYER_KEYS.index("l2.b")])
+                                dbias=gv[base - _NPL + _LAYER_KEYS.index("l2.b")], drop=dsite("p_res", l - 1, 5))
             else:
                 g = ln_bwd(dy1, x0, mean1, rstd1, P["n1.w"], g, gv[ix["n1.w"]], gv[ix["n1.b"]])
         side.join()

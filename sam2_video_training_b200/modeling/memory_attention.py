@@ -115,8 +115,10 @@ class MemoryAttention(nn.Module):
                     or layer.activation_str != "relu" or not ca.rope_k_repeat or ca.kv_in_dim != 64
                     or layer.d_model != 256 or not self.batch_first):
                 return False
-            if self.training and (layer.dropout_value > 0 or sa.dropout_p > 0 or ca.dropout_p > 0):
-                return False  # dropout active: use the composed path (residual dropouts via nn.Dropout)
+            l0 = self.layers[0]   # one set of dropout rates for the stack (get_clones copies the layer)
+            if (layer.dropout_value, sa.dropout_p, ca.dropout_p) != (l0.dropout_value, l0.self_attn.dropout_p,
+                                                                      l0.cross_attn_image.dropout_p):
+                return False
         return True
 
     def grad_bucket_order(self):
@@ -150,9 +152,18 @@ class MemoryAttention(nn.Module):
         # With a GradBucket attached (ddp.attach_grad_bucket) the backward accumulates parameter gradients into the
         # bucket itself; autograd then only sees detached aliases of the parameters (no 106 AccumulateGrad nodes).
         direct = direct_grads_possible(bucket, params)
+        # train-mode dropout: one device seed per call; the kernels derive every mask of the stack from it
+        dropout = None
+        l0 = self.layers[0]
+        if self.training and max(l0.dropout_value, l0.self_attn.dropout_p, l0.cross_attn_image.dropout_p) > 0:
+            dropout = dict(seed=torch.empty(1, dtype=torch.int64, device=curr.device).random_(),
+                           p_res=float(l0.dropout_value), p_sa=float(l0.self_attn.dropout_p),
+                           p_ca=float(l0.cross_attn_image.dropout_p))
+            if getattr(self, "_sam2b200_fixed_seed", None) is not None:   # tests: reproduce the masks
+                dropout["seed"].fill_(int(self._sam2b200_fixed_seed))
         meta = dict(num_layers=self.num_layers, num_k_exclude_rope=int(num_obj_ptr_tokens), table=table,
                     pos_enc_at_input=bool(self.pos_enc_at_input), nsplit=int(self.attn_nsplit),
-                    bucket=bucket, direct=direct, master_params=params)
+                    bucket=bucket, direct=direct, master_params=params, dropout=dropout)
         if direct:
             anchor = anchor if anchor is not None else self._grad_anchor(curr.device)
             return MemoryAttentionStackFn.apply(meta, curr, curr_pos, memory, memory_pos, *[p.detach() for p in params], anchor)

@@ -10,7 +10,6 @@ the only configuration SAM2's memory attention uses (configs/sam2/sam2.1_hiera_t
 from __future__ import annotations
 
 import math
-import warnings
 from functools import partial
 
 import torch
@@ -20,19 +19,6 @@ from torch import Tensor, nn
 from ... import _lib
 from ...ops import RopeAttentionFn
 from ..position_encoding import compute_axial_cis
-
-_warned_dropout = False
-
-
-def _warn_dropout(p: float):
-    global _warned_dropout
-    if not _warned_dropout:
-        warnings.warn(
-            f"sam2_video_training_b200: attention-probability dropout (p={p}) inside the fused attention "
-            "kernel is not implemented; it is treated as 0 (documented deviation, DESIGN.md). "
-            "Residual / MLP dropouts are applied as in the reference.")
-        _warned_dropout = True
-
 
 class Attention(nn.Module):
     """transformer.py:190-248.  Plain (un-rotated) attention through the same fused kernel."""
@@ -69,12 +55,11 @@ class Attention(nn.Module):
         return t
 
     def forward(self, q: Tensor, k: Tensor, v: Tensor) -> Tensor:
-        if self.training and self.dropout_p > 0:
-            _warn_dropout(self.dropout_p)
+        drop_p = self.dropout_p if self.training else 0.0    # transformer.py:243: dropout_p = self.dropout_p if self.training else 0.0
         q = self._lin(q, self.q_proj)
         k = self._lin(k, self.k_proj)
         v = self._lin(v, self.v_proj)
-        out = RopeAttentionFn.apply(q, k, v, self._identity_table(q.device), k.shape[1], self.attn_nsplit)
+        out = RopeAttentionFn.apply(q, k, v, self._identity_table(q.device), k.shape[1], self.attn_nsplit, drop_p)
         return self._lin(out, self.out_proj)
 
 
@@ -99,8 +84,7 @@ class RoPEAttention(Attention):
         return self.freqs_cis
 
     def forward(self, q: Tensor, k: Tensor, v: Tensor, num_k_exclude_rope: int = 0) -> Tensor:
-        if self.training and self.dropout_p > 0:
-            _warn_dropout(self.dropout_p)
+        drop_p = self.dropout_p if self.training else 0.0    # transformer.py:304
         q = self._lin(q, self.q_proj)
         k = self._lin(k, self.k_proj)
         v = self._lin(v, self.v_proj)
@@ -110,5 +94,5 @@ class RoPEAttention(Attention):
         num_k_rope = k.shape[-2] - num_k_exclude_rope
         if num_k_rope % q.shape[-2] != 0:
             raise ValueError("rotated key count must be a multiple of the query count (position_encoding.py:230)")
-        out = RopeAttentionFn.apply(q, k, v, table, num_k_exclude_rope, self.attn_nsplit)
+        out = RopeAttentionFn.apply(q, k, v, table, num_k_exclude_rope, self.attn_nsplit, drop_p)
         return self._lin(out, self.out_proj)

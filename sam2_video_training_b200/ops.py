@@ -55,8 +55,18 @@ def rope_apply(x: torch.Tensor, table: torch.Tensor, n_rope: int, inverse: bool 
     return out
 
 
-def attn_fwd(q, k, v, scale: float, nsplit: int = 0, keep_f32: bool = True):
-    """q: [B,N,256], k, v: [B,M,256] bf16 contiguous -> (out bf16 [B,N,256], out fp32 or None, lse2 fp32 [B,N])."""
+def _drop_args(drop):
+    """drop = None | (p, seed int64 device tensor [1], site) -> (p, seed pointer, site) for the C ABI."""
+    if drop is None or drop[0] <= 0.0:
+        return 0.0, None, 0
+    p_, seed, site = drop
+    assert seed.dtype == torch.int64 and seed.is_cuda and seed.numel() == 1
+    return float(p_), seed.data_ptr(), int(site)
+
+
+def attn_fwd(q, k, v, scale: float, nsplit: int = 0, keep_f32: bool = True, drop=None):
+    """q: [B,N,256], k, v: [B,M,256] bf16 contiguous -> (out bf16 [B,N,256], out fp32 or None, lse2 fp32 [B,N]).
+    drop = (p, seed tensor, site): attention-probability dropout (transformer.py:304-306)."""
     lib = _lib.load()
     b, n, d = q.shape
     m = k.shape[1]
@@ -71,16 +81,16 @@ def attn_fwd(q, k, v, scale: float, nsplit: int = 0, keep_f32: bool = True):
     wsb = lib.sam2b200_attn_fwd_workspace_bytes(b, n, m, nsplit)
     ws = torch.empty(wsb // 4, dtype=torch.float32, device=q.device) if wsb else None
     with _Timed("attn_fwd", 4.0 * b * n * m * 256):
-        rc = lib.sam2b200_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
-                                   out32.data_ptr() if out32 is not None else None, lse2.data_ptr(),
-                                   ws.data_ptr() if ws is not None else None, wsb, b, n, m, scale, nsplit,
-                                   _stream(q.device))
-    _lib.check(rc, "sam2b200_attn_fwd")
+        rc = lib.sam2b200_attn_fwd_ex(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+                                      out32.data_ptr() if out32 is not None else None, lse2.data_ptr(),
+                                      ws.data_ptr() if ws is not None else None, wsb, b, n, m, scale, nsplit,
+                                      *_drop_args(drop), _stream(q.device))
+    _lib.check(rc, "sam2b200_attn_fwd_ex")
     return out, out32, lse2
 
 
 def attn_bwd(q, k, v, out, out32, dout, lse2, scale: float, table=None, n_rope_k: int = 0, grad_dtype=torch.float32,
-             dq=None, dk=None, dv=None, dbias=(None, None, None), parts: int = 0, delta=None):
+             dq=None, dk=None, dv=None, dbias=(None, None, None), parts: int = 0, delta=None, drop=None):
     """Backward of the attention core.  With `table` the conjugate RoPE is fused into the epilogue (dq / dk are then
     gradients w.r.t. the un-rotated projections).  dbias = (dbq, dbk, dbv): optional fp32 [256] tensors the column sums
     of dq / dk / dv are ADDED to (bias gradients of the projections; fp32 atomics).  dq / dk / dv may be preallocated 2-D/3-D views whose last dim is
@@ -113,7 +123,7 @@ def attn_bwd(q, k, v, out, out32, dout, lse2, scale: float, table=None, n_rope_k
                                    table.data_ptr() if table is not None else None,
                                    table.shape[0] if table is not None else 0, n_rope_k,
                                    b, n, m, scale, *[t_.data_ptr() if t_ is not None else None for t_ in dbias],
-                                   int(parts), _stream(dev))
+                                   int(parts), *_drop_args(drop), _stream(dev))
     _lib.check(rc, "sam2b200_attn_bwd_ex")
     return dq, dk, dv
 
@@ -125,13 +135,17 @@ class RopeAttentionFn(torch.autograd.Function):
     and its autograd backward.  q: [B, N, 256]; k, v: [B, M, 256]; bf16 out."""
 
     @staticmethod
-    def forward(ctx, q, k, v, table, num_k_exclude_rope: int, nsplit: int):
+    def forward(ctx, q, k, v, table, num_k_exclude_rope: int, nsplit: int, drop_p: float = 0.0):
         n_rope_k = k.shape[1] - num_k_exclude_rope
+        # attention-probability dropout (train mode, transformer.py:304-306): a fresh device seed per call
+        ctx.drop = None
+        if drop_p > 0.0:
+            ctx.drop = (float(drop_p), torch.empty(1, dtype=torch.int64, device=q.device).random_(), 0)
         scale = 1.0 / math.sqrt(q.shape[-1])
         q_rot = rope_apply(q, table, q.shape[1])
         k_rot = rope_apply(k, table, n_rope_k)
         vb = v.to(torch.bfloat16).contiguous()
-        out, out32, lse2 = attn_fwd(q_rot, k_rot, vb, scale, nsplit)
+        out, out32, lse2 = attn_fwd(q_rot, k_rot, vb, scale, nsplit, drop=ctx.drop)
         ctx.save_for_backward(q_rot, k_rot, vb, out32, lse2, table)
         ctx.scale = scale
         ctx.n_rope_k = n_rope_k
@@ -144,8 +158,8 @@ class RopeAttentionFn(torch.autograd.Function):
         dout = dout.to(torch.bfloat16).contiguous()
         gdt = torch.bfloat16 if all(d == torch.bfloat16 for d in ctx.in_dtypes) else torch.float32
         dq, dk, dv = attn_bwd(q_rot, k_rot, vb, None, out32, dout, lse2, ctx.scale, table=table,
-                              n_rope_k=ctx.n_rope_k, grad_dtype=gdt)
-        return dq.to(ctx.in_dtypes[0]), dk.to(ctx.in_dtypes[1]), dv.to(ctx.in_dtypes[2]), None, None, None
+                              n_rope_k=ctx.n_rope_k, grad_dtype=gdt, drop=ctx.drop)
+        return dq.to(ctx.in_dtypes[0]), dk.to(ctx.in_dtypes[1]), dv.to(ctx.in_dtypes[2]), None, None, None, None
 
 
 def _out_dt(dt):

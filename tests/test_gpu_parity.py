@@ -247,20 +247,122 @@ def test_grad_bucket_direct_accumulation_and_graph_replay(dev):
                 pr.add_(0.01 * torch.sign(pr.grad)); pm.add_(0.01 * torch.sign(pr.grad))
 
 
-def test_training_mode_with_dropout_uses_composed_path(dev):
-    """dropout > 0 in train mode is outside the fused stack: residual / MLP dropouts run through nn.Dropout
-    (composed path); attention-probability dropout is a documented deviation (treated as 0)."""
-    import warnings
+def _keep_mask(dev, seed, site, p_drop, n):
+    """The keep mask the kernels derive from (seed, site) for element indices [0, n) (sam2b200_dropout_mask)."""
+    from sam2_video_training_b200 import _lib
+    out = torch.empty(n, dtype=torch.uint8, device=dev)
+    rc = _lib.load().sam2b200_dropout_mask(out.data_ptr(), 0, n, float(p_drop), seed.data_ptr(), int(site),
+                                           torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "sam2b200_dropout_mask")
+    return out.bool()
+
+
+@pytest.mark.parametrize("b,n,m", [(2, 144, 296), (1, 1024, 1100)])
+def test_attention_dropout_matches_explicit_mask(dev, b, n, m):
+    """Attention-probability dropout (transformer.py:304-306) inside the forward and all backward kernels (separate
+    kernels at N = 144, the CTA-pair kernel at N = 1024): same result as softmax -> explicit mask / (1 - p) -> @ V in
+    fp32 torch with the mask the kernels generate, gradients included; keep rate ~ 1 - p."""
+    from sam2_video_training_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(33)
+    p_drop, site = 0.1, 11
+    seed = torch.tensor([0x1234567890ABCDE], dtype=torch.int64, device=dev)
+    q = torch.randn(b, n, 256, device=dev, generator=g).to(torch.bfloat16)
+    k = torch.randn(b, m, 256, device=dev, generator=g).to(torch.bfloat16)
+    v = torch.randn(b, m, 256, device=dev, generator=g).to(torch.bfloat16)
+    do = torch.randn(b, n, 256, device=dev, generator=g).to(torch.bfloat16)
+    keep = _keep_mask(dev, seed, site, p_drop, b * n * m).view(b, n, m)
+    assert abs(float(keep.float().mean()) - (1 - p_drop)) < 5e-3
+    drop = (p_drop, seed, site)
+    o, o32, lse = ops.attn_fwd(q, k, v, 1 / 16.0, drop=drop)
+    dq, dk, dv = ops.attn_bwd(q, k, v, None, o32, do, lse, 1 / 16.0, grad_dtype=torch.float32, drop=drop)
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    a = torch.softmax(qf @ kf.transpose(1, 2) / 16.0, dim=-1) * keep / (1 - p_drop)
+    ref = a @ vf
+    ref.backward(do.float())
+    assert rel_l2(o32, ref) < 5e-3
+    for got, want, name in ((dq, qf.grad, "dq"), (dk, kf.grad, "dk"), (dv, vf.grad, "dv")):
+        assert rel_l2(got, want) < 1e-2, (name, rel_l2(got, want))
+    o_nodrop, _, _ = ops.attn_fwd(q, k, v, 1 / 16.0)
+    assert rel_l2(o_nodrop, ref) > 0.05        # the mask really changes the result
+
+
+def test_training_mode_dropout_fused_stack_matches_oracle_with_same_masks(dev):
+    """Train mode with the shipped dropout = 0.1 runs the fused stack; every dropout of the reference
+    (memory_attention.py:64,81,97,99, transformer.py:304-306) is applied with counter-based masks.  The oracle, given
+    the very masks the kernels generate, must reproduce output and gradients; two calls draw different masks."""
     from sam2_video_training_b200.modeling.memory_attention import build_memory_attention
+    p_drop = 0.1
+    model = build_memory_attention(dropout=p_drop).to(dev).train()
+    assert model._fused_eligible()
+    params = ao.init_params(seed=0)
+    _load_params(model, params)
+    grid, b, nf, nptr = 8, 2, 2, 4
+    n, m = grid * grid, nf * grid * grid + nptr
+    g = torch.Generator().manual_seed(5)
+    curr, curr_pos = torch.randn(n, b, 256, generator=g), torch.randn(n, b, 256, generator=g) * 0.7
+    memory, memory_pos = torch.randn(m, b, 64, generator=g), torch.randn(m, b, 64, generator=g) * 0.7
+    gout = torch.randn(n, b, 256, generator=g)
+    seed_val = 987654321012345
+    model._sam2b200_fixed_seed = seed_val
+    cd = curr.to(dev).requires_grad_(True)
+    out = model(cd, memory.to(dev), curr_pos.to(dev), memory_pos.to(dev), nptr)
+    out.backward(gout.to(dev))
+    seed = torch.tensor([seed_val], dtype=torch.int64, device=dev)
+    masks = []
+    for l in range(4):
+        mk = lambda site, cnt, shape: _keep_mask(dev, seed, l * 8 + site, p_drop, cnt).view(shape).cpu()
+        masks.append(dict(sa_prob=mk(0, b * n * n, (b, n, n)), ca_prob=mk(1, b * n * m, (b, n, m)),
+                          drop1=mk(2, b * n * 256, (b, n, 256)), drop2=mk(3, b * n * 256, (b, n, 256)),
+                          mlp=mk(4, b * n * 2048, (b, n, 2048)), drop3=mk(5, b * n * 256, (b, n, 256))))
+    po = {k_: v_.clone().requires_grad_(True) for k_, v_ in params.items()}
+    co = curr.clone().requires_grad_(True)
+    ref = ao.memory_attention(po, co, memory, curr_pos, memory_pos, nptr, masks=masks, p_drop=p_drop)
+    ref.backward(gout)
+    assert rel_l2(out, ref) < ATTN_REL_TOL, rel_l2(out, ref)
+    assert cosine(cd.grad, co.grad) > GRAD_COS_TOL
+    got = torch.cat([p_.grad.flatten().cpu() for _, p_ in model.named_parameters()])
+    want = torch.cat([po[k_].grad.flatten() for k_, _ in model.named_parameters()])
+    assert cosine(got, want) > GRAD_COS_TOL, cosine(got, want)
+    ref_nodrop = ao.memory_attention(params, curr, memory, curr_pos, memory_pos, nptr)
+    assert rel_l2(out, ref_nodrop) > 0.05
+    model._sam2b200_fixed_seed = None
+    with torch.no_grad():
+        o1 = model(curr.to(dev), memory.to(dev), curr_pos.to(dev), memory_pos.to(dev), nptr)
+        o2 = model(curr.to(dev), memory.to(dev), curr_pos.to(dev), memory_pos.to(dev), nptr)
+    assert rel_l2(o1, o2) > 0.02                # fresh masks per call
+    model.eval()
+    with torch.no_grad():
+        o3 = model(curr.to(dev), memory.to(dev), curr_pos.to(dev), memory_pos.to(dev), nptr)
+    assert rel_l2(o3, ref_nodrop) < ATTN_REL_TOL   # eval: dropout off
+
+
+def test_dropout_under_cuda_graph_replay_draws_fresh_masks(dev):
+    """The per-call seed is produced on the device inside the captured graph, so every replay has new masks, and the
+    backward of a replay uses the masks of its own forward (gradient of a linear probe matches a finite difference
+    of the SAME replay is not available -- instead: two replays differ, and eval-mode replay is deterministic)."""
+    from sam2_video_training_b200 import ddp
+    from sam2_video_training_b200.graphs import GraphedMemoryAttention
+    from sam2_video_training_b200.modeling.memory_attention import build_memory_attention
+    torch.manual_seed(1)
     model = build_memory_attention(dropout=0.1).to(dev).train()
-    assert not model._fused_eligible()
-    inp = {k: v.to(dev) for k, v in detgen.attention_inputs(8, 1, 1, 4).items()}
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        out = model(inp["curr"], inp["memory"], inp["curr_pos"], inp["memory_pos"], 4)
-    out.sum().backward()
-    assert torch.isfinite(out).all()
-    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+    ddp.attach_grad_bucket(model)
+    gm = GraphedMemoryAttention(model)
+    n, b, m, p = 64, 2, 136, 8
+    g = torch.Generator(device="cuda").manual_seed(2)
+    curr, mem = torch.randn(n, b, 256, device=dev, generator=g), torch.randn(m, b, 64, device=dev, generator=g)
+    cpos = torch.randn(n, b, 256, device=dev, generator=g)
+    mpos = torch.randn(m, b, 64, device=dev, generator=g).requires_grad_(True)
+    outs, grads = [], []
+    for _ in range(3):
+        mpos.grad = None
+        o = gm(curr, mem, cpos, mpos, p)
+        o.backward(torch.ones_like(o))
+        outs.append(o.detach().clone()); grads.append(mpos.grad.detach().clone())
+        del o
+    assert len(gm._graphs) == 1
+    assert rel_l2(outs[0], outs[1]) > 0.02 and rel_l2(outs[1], outs[2]) > 0.02
+    assert rel_l2(grads[0], grads[1]) > 0.02
+    assert all(torch.isfinite(t).all() for t in outs + grads)
 
 
 # ------------------------------------------------------------------ glue kernels (csrc/glue.cu)

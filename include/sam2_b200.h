@@ -167,6 +167,16 @@ int sam2b200_mask_loss_bwd_coef(const float* const* logits, float* const* dlogit
                                 const float* coef, int T, int C, long long HW, float alpha, float gamma, float inv_temp,
                                 sam2b200_stream_t stream);
 
+/* ---- memory-bank assembly -------------------------------------------------
+ * The data movement of SAM2Base._prepare_memory_conditioned_features (sam2_base.py:597-692) in one launch: for each
+ * selected past frame s: memory[s*HW + t, b, :] = feats[s][b, :, t], memory_pos[...] = pos[s][b, :, t] + tpos[s][:];
+ * object pointer i, chunk c: memory[n_slots*HW + i*C/64 + c, b, :] = ptrs[i][b, 64c : 64c+64], memory_pos[...] = obj_pos[i].
+ * feats / pos / tpos / ptrs: HOST arrays of device pointers ([B, 64, HW], [B, 64, HW], [64] fp32, [B, C]); dtype 0 = fp32,
+ * 1 = bf16; memory, memory_pos: [n_slots*HW + n_ptrs*C/64, B, 64] fp32.  Frame selection stays on the host. */
+int sam2b200_bank_gather(const void* const* feats, const void* const* pos, const float* const* tpos, int n_slots,
+                         int feat_dtype, const void* const* ptrs, int n_ptrs, int ptr_dtype, const float* obj_pos,
+                         float* memory, float* memory_pos, int B, int HW, int mem_dim, int C, sam2b200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

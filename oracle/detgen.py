@@ -74,3 +74,26 @@ def loss_inputs(t: int, c: int, s: int, clear=((1, 2),), dtype=torch.float32):
             targets[ft, fc] = False
     iou_pred = det((t, c, 1), 1.3, 0.5, 0.5, dtype) + 0.5
     return logits, targets, iou_pred
+
+
+def bank_scenarios():
+    """(tag, kwargs) of the memory-bank assembly fixtures: frame index, conditioning / tracked frames present,
+    train vs eval (stride, pointers in the past only), conditioning-frame limit, reverse tracking."""
+    return [
+        ("train_f5", dict(frame_idx=5, cond=[0], non_cond=[1, 2, 3, 4], num_frames=8, training=True)),
+        ("train_f12_full", dict(frame_idx=12, cond=[0], non_cond=list(range(1, 12)), num_frames=20, training=True)),
+        ("eval_stride2_f9", dict(frame_idx=9, cond=[0, 4], non_cond=[1, 2, 3, 5, 6, 7, 8], num_frames=16, training=False, stride=2)),
+        ("eval_maxcond2_f10", dict(frame_idx=10, cond=[0, 3, 7, 14], non_cond=[8, 9], num_frames=16, training=False, max_cond=2)),
+        ("reverse_f4", dict(frame_idx=4, cond=[9], non_cond=[5, 6, 7, 8], num_frames=10, training=False, reverse=True)),
+    ]
+
+
+def bank_inputs(cond, non_cond, b=2, h=6, w=6, c=256, md=64):
+    """Deterministic per-frame outputs ({maskmem_features [B, md, H, W], maskmem_pos_enc [[B, md, H, W]], obj_ptr [B, C]})
+    and the trainable tensors the assembly reads (maskmem_tpos_enc [7,1,1,md], obj_ptr_tpos_proj weight / bias)."""
+    def frame(t):
+        return {"maskmem_features": det((b, md, h, w), 0.11 + 0.01 * t, 0.3 * t, 1.0),
+                "maskmem_pos_enc": [det((b, md, h, w), 0.07 + 0.02 * t, 1.1 * t, 0.7)],
+                "obj_ptr": det((b, c), 0.19 + 0.03 * t, 0.5 * t, 1.0)}
+    od = {"cond_frame_outputs": {t: frame(t) for t in cond}, "non_cond_frame_outputs": {t: frame(t) for t in non_cond}}
+    return od, det((7, 1, 1, md), 0.37, 0.2, 0.05), det((md, c), 0.23, 0.4, 1.0 / math.sqrt(c)), det((md,), 0.9, 0.1, 0.05)

@@ -53,6 +53,55 @@ def golden_attention(ns, grid, batch, n_frames, n_ptr, tag, full_grads=False):
     return rec
 
 
+def golden_bank():
+    """Memory-bank assembly: the unmodified SAM2Base._prepare_memory_conditioned_features (sam2_base.py:524-713) with a
+    stub memory_attention that records (memory, memory_pos, num_obj_ptr_tokens), plus the gradients that reach the
+    trainable maskmem_tpos_enc and obj_ptr_tpos_proj through memory_pos."""
+    import types
+    SAM2Base = ref_shim.load_sam2_base()
+
+    class Enc(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.out_proj = torch.nn.Conv2d(256, 64, 1)
+
+    class Img(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.neck = types.SimpleNamespace(d_model=256)
+
+    class Rec(torch.nn.Module):
+        d_model = 256
+
+        def forward(self, curr, curr_pos, memory, memory_pos, num_obj_ptr_tokens):
+            self.rec = (memory, memory_pos, num_obj_ptr_tokens)
+            return curr[0]
+
+    for tag, kw in detgen.bank_scenarios():
+        h = w = 6
+        base = SAM2Base(image_encoder=Img(), memory_attention=Rec(), memory_encoder=Enc(), image_size=96, backbone_stride=16,
+                        num_maskmem=7, use_obj_ptrs_in_encoder=True, max_obj_ptrs_in_encoder=16, add_tpos_enc_to_obj_ptrs=True,
+                        proj_tpos_enc_in_obj_ptrs=True, use_signed_tpos_enc_to_obj_ptrs=True,
+                        only_obj_ptrs_in_the_past_for_eval=True, directly_add_no_mem_embed=True,
+                        max_cond_frames_in_attn=kw.get("max_cond", -1), memory_temporal_stride_for_eval=kw.get("stride", 1))
+        od, tpos, pw, pb = detgen.bank_inputs(kw["cond"], kw["non_cond"], h=h, w=w)
+        with torch.no_grad():
+            base.maskmem_tpos_enc.copy_(tpos)
+            base.obj_ptr_tpos_proj.weight.copy_(pw)
+            base.obj_ptr_tpos_proj.bias.copy_(pb)
+        base.train(kw["training"])
+        feats = [detgen.det((h * w, 2, 256), 0.31, 0.7, 1.0)]
+        base._prepare_memory_conditioned_features(kw["frame_idx"], False, feats, [feats[0] * 0.5], [(h, w)], od, kw["num_frames"],
+                                                  track_in_reverse=kw.get("reverse", False))
+        memory, memory_pos, n_ptr = base.memory_attention.rec
+        wgt = detgen.det(tuple(memory_pos.shape), 0.013, 0.9, 1.0)
+        (memory_pos * wgt).sum().backward()
+        np.savez_compressed(os.path.join(OUT, f"bank_{tag}.npz"), memory=memory.detach().numpy(), memory_pos=memory_pos.detach().numpy(),
+                            n_ptr=n_ptr, d_tpos=base.maskmem_tpos_enc.grad.numpy(), d_proj_w=base.obj_ptr_tpos_proj.weight.grad.numpy(),
+                            d_proj_b=base.obj_ptr_tpos_proj.bias.grad.numpy())
+        print("bank", tag, tuple(memory.shape), n_ptr)
+
+
 def golden_functional(ns, n, m, s, tag):
     """Stand-alone dice_loss / sigmoid_focal_loss / iou_loss of the reference (losses.py:20-76), both branches."""
     L = ns.losses
@@ -142,6 +191,7 @@ def main():
     r = golden_loss(ns, 2, 3, 16, "t2_c3_s16")
     print("loss: l1 total", r["l1:total_loss"], "mse total", r["mse:total_loss"], "bce", r["bce:total_loss"])
     golden_functional(ns, 3, 2, 24, "n3_m2_s24")
+    golden_bank()
     r = golden_loss(ns, 3, 5, 40, "t3_c5_s40")
     print("loss2: l1 total", r["l1:total_loss"])
 

@@ -71,6 +71,18 @@ def load():
     return ns
 
 
+def load_sam2_base():
+    """The reference's ``SAM2Base`` class (sam2_video/model/modeling/sam2_base.py), importable once the SAM heads'
+    vendored modules are registered.  Used to pin oracle/bank_oracle.py: the unmodified
+    ``_prepare_memory_conditioned_features`` is run with stub image encoder / memory encoder / memory attention."""
+    load()
+    if "sam2_base" not in _cache:
+        _load("sam2.modeling.sam.prompt_encoder", os.path.join(_MODELING, "sam", "prompt_encoder.py"))
+        _load("sam2.modeling.sam.mask_decoder", os.path.join(_MODELING, "sam", "mask_decoder.py"))
+        _cache["sam2_base"] = _load("sam2.modeling.sam2_base", os.path.join(_MODELING, "sam2_base.py"))
+    return _cache["sam2_base"].SAM2Base
+
+
 def build_memory_attention(ns=None, dropout: float = 0.1, feat_sizes=(64, 64)):
     """Construct the stack with the kwargs of configs/sam2/sam2.1_hiera_t.yaml:29-60."""
     ns = ns or load()

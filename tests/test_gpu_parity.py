@@ -640,3 +640,45 @@ def test_attention_backward_fused_bias_gradients(dev):
             want = ref.double().sum(dim=(0, 1)) + 0.5
             assert rel_l2(got.double(), want) < (2e-3 if gdt == torch.bfloat16 else 1e-5), (name, gdt)
         assert rel_l2(dq.float(), dq0) < 6e-3 and rel_l2(dk.float(), dk0) < 6e-3 and rel_l2(dv.float(), dv0) < 6e-3
+
+
+@pytest.mark.parametrize("tag", [t for t, _ in detgen.bank_scenarios()])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_memory_bank_assembly_matches_oracle(dev, golden_dir, tag, dtype):
+    """sam2b200_bank_gather + the host selection (memory_bank.assemble_memory) against the reference-generated fixture
+    (fp32: bit-exact memory, memory_pos to 1 ulp) and the oracle (bf16 frame features; gradients to maskmem_tpos_enc and
+    obj_ptr_tpos_proj)."""
+    import numpy as np
+    from oracle import bank_oracle as bo
+    from sam2_video_training_b200 import memory_bank as mb
+    kw = dict(detgen.bank_scenarios())[tag]
+    od, tpos, pw, pb = detgen.bank_inputs(kw["cond"], kw["non_cond"])
+
+    def cast(o):
+        return {"maskmem_features": o["maskmem_features"].to(dtype), "maskmem_pos_enc": [o["maskmem_pos_enc"][0].to(dtype)],
+                "obj_ptr": o["obj_ptr"]}
+    od = {k_: {t: cast(o) for t, o in v_.items()} for k_, v_ in od.items()}
+    od_dev = {k_: {t: {"maskmem_features": o["maskmem_features"].to(dev), "maskmem_pos_enc": [o["maskmem_pos_enc"][0].to(dev)],
+                       "obj_ptr": o["obj_ptr"].to(dev)} for t, o in v_.items()} for k_, v_ in od.items()}
+    args = dict(max_cond_frames_in_attn=kw.get("max_cond", -1), memory_temporal_stride_for_eval=kw.get("stride", 1))
+    proj = torch.nn.Linear(256, 64).to(dev)
+    with torch.no_grad():
+        proj.weight.copy_(pw); proj.bias.copy_(pb)
+    tpos_d = tpos.to(dev).requires_grad_(True)
+    memory, memory_pos, n_ptr = mb.assemble_memory(mb.BankConfig(**args), kw["frame_idx"], od_dev, kw["num_frames"], tpos_d, proj,
+                                                   training=kw["training"], track_in_reverse=kw.get("reverse", False))
+    to, pwo, pbo = (t.clone().requires_grad_(True) for t in (tpos, pw, pb))
+    rm, rp, rn = bo.assemble_memory(bo.BankConfig(**args), kw["frame_idx"], od, kw["num_frames"], to, pwo, pbo, kw["training"],
+                                    track_in_reverse=kw.get("reverse", False))
+    assert n_ptr == rn and memory.shape == rm.shape and memory.dtype == torch.float32
+    assert torch.equal(memory.cpu(), rm.float())
+    assert torch.allclose(memory_pos.cpu(), rp.float(), atol=2e-6, rtol=0)
+    if dtype == torch.float32:
+        g = np.load(os.path.join(golden_dir, f"bank_{tag}.npz"))
+        assert int(g["n_ptr"]) == n_ptr and torch.equal(memory.cpu(), torch.from_numpy(g["memory"]))
+        assert torch.allclose(memory_pos.cpu(), torch.from_numpy(g["memory_pos"]), atol=2e-6, rtol=0)
+    w = detgen.det(tuple(rp.shape), 0.013, 0.9, 1.0)
+    (memory_pos * w.to(dev)).sum().backward()
+    (rp.float() * w).sum().backward()
+    assert rel_l2(tpos_d.grad.cpu(), to.grad) < 1e-5
+    assert rel_l2(proj.weight.grad.cpu(), pwo.grad) < 1e-5 and rel_l2(proj.bias.grad.cpu(), pbo.grad) < 1e-5

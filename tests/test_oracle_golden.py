@@ -168,3 +168,26 @@ def test_functional_losses_oracle_matches_reference(golden_dir):
     dx, diou = torch.from_numpy(g["dx"]).double(), torch.from_numpy(g["diou"]).double()
     assert float((x.grad - dx).norm() / dx.norm()) < 1e-5
     assert float((iou.grad - diou).norm() / diou.norm()) < 1e-5
+
+
+@pytest.mark.parametrize("tag", [t for t, _ in __import__("oracle.detgen", fromlist=["x"]).bank_scenarios()])
+def test_bank_oracle_matches_reference(golden_dir, tag):
+    """Memory-bank assembly (sam2_base.py:524-692): frame selection, temporal positions, object-pointer tokens and
+    their positional encoding -- bit-exact memory / memory_pos against the unmodified reference method, and the
+    gradients that reach maskmem_tpos_enc and obj_ptr_tpos_proj."""
+    from oracle import bank_oracle as bo
+    from oracle import detgen
+    kw = dict(detgen.bank_scenarios())[tag]
+    g = np.load(os.path.join(golden_dir, f"bank_{tag}.npz"))
+    od, tpos, pw, pb = detgen.bank_inputs(kw["cond"], kw["non_cond"])
+    tpos, pw, pb = (t.clone().requires_grad_(True) for t in (tpos, pw, pb))
+    cfg = bo.BankConfig(max_cond_frames_in_attn=kw.get("max_cond", -1), memory_temporal_stride_for_eval=kw.get("stride", 1))
+    memory, memory_pos, n_ptr = bo.assemble_memory(cfg, kw["frame_idx"], od, kw["num_frames"], tpos, pw, pb, kw["training"],
+                                                   track_in_reverse=kw.get("reverse", False))
+    assert n_ptr == int(g["n_ptr"])
+    assert torch.equal(memory, torch.from_numpy(g["memory"]))
+    assert torch.allclose(memory_pos, torch.from_numpy(g["memory_pos"]), atol=1e-6, rtol=0)
+    (memory_pos * detgen.det(tuple(memory_pos.shape), 0.013, 0.9, 1.0)).sum().backward()
+    for got, key in ((tpos.grad, "d_tpos"), (pw.grad, "d_proj_w"), (pb.grad, "d_proj_b")):
+        ref = torch.from_numpy(g[key])
+        assert float((got - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max())), key

@@ -118,6 +118,13 @@ int sam2b200_colsum(int mode, const float* in_f32, void* io_bf16, const void* h_
                     long long rows, int C, long long ld, float scale /* mode 1: 1/(1-p) of the dropout after the ReLU */,
                     sam2b200_stream_t stream);
 
+/* Row permutation between the module's seq-first [L, B, C] tensors and the stack's batch-first [B, L, C] rows with fused
+ * add / scale / cast (C = 256 or 64; memory_attention.py:140-148, :75-76 and the transposes of the input gradients):
+ * inverse 0: out[b,l] = scale * (a[l,b] + alpha2 * a2[l,b]), out2[b,l] = scale * a[l,b]; inverse 1: the other way.
+ * a2 / out2 may be NULL; out_bf16 = 1 writes bf16 (memk = bf16(memory + pos), memv = bf16(memory) in one pass). */
+int sam2b200_permute_rows(const float* a, const float* a2, float alpha2, void* out, void* out2, int out_bf16, int B, int L,
+                          int C, int inverse, float scale, sam2b200_stream_t stream);
+
 /* ---- dropout (train mode; memory_attention.py:58-99, transformer.py:304-306) ----------------------------------
  * Every dropout of the path is a counter-based mask: keep <=> hash(*drop_seed, drop_site, element index) >= p * 2^32
  * (csrc/dropout.cuh); the seed lives in DEVICE memory (fresh masks under CUDA-graph replay), nothing is stored, the

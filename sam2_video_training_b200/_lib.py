@@ -42,6 +42,8 @@ _SIGNATURES = {
     "sam2b200_colsum_workspace_bytes": (c_size_t, [c_longlong, c_int]),
     "sam2b200_colsum": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int,
                                 c_longlong, c_float, c_void_p]),
+    "sam2b200_permute_rows": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
+                                      c_void_p]),
     "sam2b200_dropout_inplace": (c_int, [c_void_p, c_longlong, c_float, c_void_p, c_uint, c_void_p]),
     "sam2b200_dropout_mask": (c_int, [c_void_p, c_longlong, c_longlong, c_float, c_void_p, c_uint, c_void_p]),
     "sam2b200_mask_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_longlong]),

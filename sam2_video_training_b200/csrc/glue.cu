@@ -289,6 +289,60 @@ __global__ void dropout_mask_kernel(unsigned char* __restrict__ out, long long i
   out[i] = keep ? 1 : 0;
 }
 
+// ------------------------------------------------------------------ packing between the module layout and the kernel layout
+// MemoryAttention.forward receives seq-first tensors ([L, B, C], memory_attention.py:119-148); the stack works batch-first.
+// out[(b * L + l), :] = a[(l * B + b), :] (+ alpha2 * a2[(l * B + b), :]) as fp32 (OutT = float) or bf16, optionally a second
+// output out2 from a alone (memory: memk = bf16(memory + pos), memv = bf16(memory) in ONE pass).  One warp per row; C = 256 or 64.
+// inverse = 1 maps batch-first rows back to seq-first (gradients): out[(l * B + b), :] = scale * (a[(b * L + l), :] + a2[...]).
+template <typename OutT, int C>
+__global__ void __launch_bounds__(256)
+permute_rows_kernel(const float* __restrict__ a, const float* __restrict__ a2, float alpha2, OutT* __restrict__ out,
+                    OutT* __restrict__ out2, long long rows, int B, int L, int inverse, float scale) {
+  constexpr int kPerLane = C / 32;                  // 8 (C = 256) or 2 (C = 64) consecutive floats per lane
+  const long long orow = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (orow >= rows) return;
+  long long irow;
+  if (!inverse) { const long long b = orow / L, l = orow % L; irow = l * B + b; }      // out batch-first <- in seq-first
+  else { const long long l = orow / B, b = orow % B; irow = b * L + l; }               // out seq-first <- in batch-first
+  float v[kPerLane], w[kPerLane], t[kPerLane];
+  auto load = [&](const float* src, float* dst) {     // 2 x float4 (C = 256) or 1 x float2 (C = 64) per lane
+    if constexpr (kPerLane == 8) {
+      const float4* p4 = reinterpret_cast<const float4*>(src + irow * C + lane * 8);
+      const float4 x0 = p4[0], x1 = p4[1];
+      dst[0] = x0.x; dst[1] = x0.y; dst[2] = x0.z; dst[3] = x0.w; dst[4] = x1.x; dst[5] = x1.y; dst[6] = x1.z; dst[7] = x1.w;
+    } else {
+      const float2 x0 = *reinterpret_cast<const float2*>(src + irow * C + lane * 2);
+      dst[0] = x0.x; dst[1] = x0.y;
+    }
+  };
+  load(a, w);
+#pragma unroll
+  for (int i = 0; i < kPerLane; ++i) v[i] = w[i];
+  if (a2 != nullptr) {
+    load(a2, t);
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) v[i] = fmaf(alpha2, t[i], v[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < kPerLane; ++i) { v[i] *= scale; w[i] *= scale; }
+  auto store = [&](OutT* dst, const float* src) {
+    if constexpr (sizeof(OutT) == 4 && kPerLane == 8) {
+      float4* p4 = reinterpret_cast<float4*>(dst + orow * C + lane * 8);
+      p4[0] = make_float4(src[0], src[1], src[2], src[3]);
+      p4[1] = make_float4(src[4], src[5], src[6], src[7]);
+    } else if constexpr (sizeof(OutT) == 4) {
+      *reinterpret_cast<float2*>(dst + orow * C + lane * 2) = make_float2(src[0], src[1]);
+    } else if constexpr (kPerLane == 8) {
+      *reinterpret_cast<uint4*>(dst + orow * C + lane * 8) = pack8(src);
+    } else {
+      *reinterpret_cast<__nv_bfloat162*>(dst + orow * C + lane * 2) = __floats2bfloat162_rn(src[0], src[1]);
+    }
+  };
+  store(out, v);
+  if (out2 != nullptr) store(out2, w);
+}
+
 int grid_for_rows(long long rows, int rows_per_block) {
   long long g = (rows + rows_per_block - 1) / rows_per_block;
   const long long cap = 148 * 2;
@@ -370,6 +424,29 @@ int sam2b200_colsum(int mode, const float* in_f32, void* io_bf16, const void* h_
     colsum_kernel<2><<<nblk, 256, sh, stream>>>(nullptr, (__nv_bfloat16*)io_bf16, nullptr, part, rows, C, ld, 1.0f);
   partial_reduce_add_kernel<<<(C + 31) / 32, 256, 0, stream>>>(part, nblk, C, colsum, colsum, C);
   return sam2b200::check_launch("colsum", 2);
+}
+
+// Row permutation between seq-first [L, B, C] and batch-first [B, L, C] with fused add / scale / cast (C = 256 or 64):
+//   inverse = 0: out[b, l] = scale * (a[l, b] + alpha2 * a2[l, b]), out2[b, l] = scale * a[l, b]   (a2, out2 optional)
+//   inverse = 1: out[l, b] = scale * (a[b, l] + alpha2 * a2[b, l]), out2[l, b] = scale * a[b, l]
+// out_bf16 = 1 writes bf16.  Replaces curr.float() + 0.1 * curr_pos -> transpose -> contiguous, (memory + memory_pos)
+// -> transpose -> bf16 (memory_attention.py:140-148, :75-76) and the transposes of the input gradients.
+int sam2b200_permute_rows(const float* a, const float* a2, float alpha2, void* out, void* out2, int out_bf16, int B, int L,
+                          int C, int inverse, float scale, cudaStream_t stream) {
+  if (!a || !out || B <= 0 || L <= 0 || (C != 256 && C != 64) || (out_bf16 & ~1) || !aligned16(a) || (a2 && !aligned16(a2)) ||
+      !aligned16(out) || (out2 && !aligned16(out2)))
+    return sam2b200::fail(SAM2B200_ERR_INVALID, "permute_rows: bad arguments (C must be 256 or 64, 16-byte aligned tensors)");
+  const long long rows = (long long)B * L;
+  const unsigned blocks = (unsigned)((rows * 32 + 255) / 256);
+  if (C == 256 && !out_bf16)
+    permute_rows_kernel<float, 256><<<blocks, 256, 0, stream>>>(a, a2, alpha2, (float*)out, (float*)out2, rows, B, L, inverse, scale);
+  else if (C == 256)
+    permute_rows_kernel<__nv_bfloat16, 256><<<blocks, 256, 0, stream>>>(a, a2, alpha2, (__nv_bfloat16*)out, (__nv_bfloat16*)out2, rows, B, L, inverse, scale);
+  else if (!out_bf16)
+    permute_rows_kernel<float, 64><<<blocks, 256, 0, stream>>>(a, a2, alpha2, (float*)out, (float*)out2, rows, B, L, inverse, scale);
+  else
+    permute_rows_kernel<__nv_bfloat16, 64><<<blocks, 256, 0, stream>>>(a, a2, alpha2, (__nv_bfloat16*)out, (__nv_bfloat16*)out2, rows, B, L, inverse, scale);
+  return sam2b200::check_launch("permute_rows");
 }
 
 // Inverted dropout in place on a bf16 tensor of n elements (the MLP's hidden activation, memory_attention.py:97:

@@ -123,6 +123,27 @@ def colsum_bf16(x16, colsum):
     _colsum(2, None, x16, None, colsum, x16.shape[0], x16.shape[1])
 
 
+def permute_rows(a, a2, alpha2, bsz, length, inverse, out_dtype=F32, second=False, scale=1.0):
+    """Seq-first [L, B, C] <-> batch-first [B, L, C] rows with fused add / scale / cast (sam2b200_permute_rows).
+    Returns out (and out2 = the same from `a` alone if `second`), shaped [B*L, C] (forward) or [L, B, C] (inverse)."""
+    c = a.shape[-1]
+    a = a.contiguous()
+    if a.dtype != F32:
+        a = a.float()
+    if a2 is not None:
+        a2 = a2.contiguous()
+        if a2.dtype != F32:
+            a2 = a2.float()
+    shape = (length, bsz, c) if inverse else (bsz * length, c)
+    out = torch.empty(shape, dtype=out_dtype, device=a.device)
+    out2 = torch.empty(shape, dtype=out_dtype, device=a.device) if second else None
+    rc = _lib.load().sam2b200_permute_rows(a.data_ptr(), a2.data_ptr() if a2 is not None else None, float(alpha2), out.data_ptr(),
+                                           out2.data_ptr() if out2 is not None else None, int(out_dtype == BF16), bsz, length, c,
+                                           int(inverse), float(scale), _stream(a.device))
+    _lib.check(rc, "sam2b200_permute_rows")
+    return (out, out2) if second else out
+
+
 def _mm32(a, b):
     """fp32 result of a bf16 x bf16 product (weight gradients)."""
     return torch.mm(a, b, out_dtype=F32)
@@ -272,12 +293,9 @@ class MemoryAttentionStackFn(torch.autograd.Function):
         scale = 1.0 / math.sqrt(d)
         n_rope_k = m - p_excl
         # ---- pack inputs once per call (memory_attention.py:140-148; the reference re-adds pos per layer)
-        x = curr.float()
-        if pos_at_input and curr_pos is not None:
-            x = x + 0.1 * curr_pos
-        x = x.transpose(0, 1).contiguous().view(r, d)
-        memk = (memory + memory_pos).transpose(0, 1).to(BF16).contiguous().view(rm, -1)
-        memv = memory.transpose(0, 1).to(BF16).contiguous().view(rm, -1)
+        # one pass each: x = curr + 0.1 curr_pos as batch-first fp32 rows; memk = bf16(memory + pos), memv = bf16(memory)
+        x = permute_rows(curr, curr_pos if (pos_at_input and curr_pos is not None) else None, 0.1, b, n, False)
+        memk, memv = permute_rows(memory, memory_pos, 1.0, b, m, False, out_dtype=BF16, second=True)
         masters = meta.get("master_params") or list(params)   # the nn.Parameters (params may be detached aliases)
         wb = bf16_params(masters)
         saved: List[torch.Tensor] = []
@@ -477,16 +495,14 @@ class MemoryAttentionStackFn(torch.autograd.Function):
         side.join()
         # ---- unpack input gradients
         d_curr = d_pos = d_mem = d_mpos = None
-        if need_curr or need_pos:
-            gx = g.view(b, n, d).transpose(0, 1)
-            if need_curr:
-                d_curr = gx.contiguous()
-            if need_pos and mt["has_pos"] and mt["pos_at_input"]:
-                d_pos = gx * 0.1
+        if need_curr:
+            d_curr = permute_rows(g, None, 0.0, b, n, True)
+        if need_pos and mt["has_pos"] and mt["pos_at_input"]:
+            d_pos = permute_rows(g, None, 0.0, b, n, True, scale=0.1)
         if need_mpos:
-            d_mpos = dmemk.view(b, m, -1).transpose(0, 1).contiguous()
+            d_mpos = permute_rows(dmemk, None, 0.0, b, m, True)
         if need_mem:
-            d_mem = (dmemk + dmemv).view(b, m, -1).transpose(0, 1).contiguous()
+            d_mem = permute_rows(dmemk, dmemv, 1.0, b, m, True)
         if not ctx.has_anchor:
             return (None, d_curr, d_pos, d_mem, d_mpos, *grads)
         # The anchor gets a (zero) gradient only when it is the ONLY input that requires grad: a backward whose

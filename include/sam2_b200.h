@@ -174,6 +174,13 @@ int sam2b200_mask_loss_bwd_coef(const float* const* logits, float* const* dlogit
                                 const float* coef, int T, int C, long long HW, float alpha, float gamma, float inv_temp,
                                 sam2b200_stream_t stream);
 
+/* ---- MLP backward (memory_attention.py:95-98) ---------------------------------------------------------------
+ * dh[R, F] = (dm[R, 256] . W2[256, F]) o (h[R, F] > 0) * scale: input gradient of linear2 with the ReLU (and hidden
+ * dropout: h is the dropped activation, scale = 1/(1-p)) backward fused into the epilogue of a tcgen05 GEMM.
+ * All bf16 row-major contiguous, F a multiple of 128. */
+int sam2b200_mlp_dh(const void* dm, const void* w2, const void* h, void* dh, long long R, int F, float scale,
+                    sam2b200_stream_t stream);
+
 /* ---- memory-bank assembly -------------------------------------------------
  * The data movement of SAM2Base._prepare_memory_conditioned_features (sam2_base.py:597-692) in one launch: for each
  * selected past frame s: memory[s*HW + t, b, :] = feats[s][b, :, t], memory_pos[...] = pos[s][b, :, t] + tpos[s][:];

@@ -112,6 +112,17 @@ def relu_bwd_colsum_(dh16, h16, colsum, scale=1.0):
     _colsum(1, None, dh16, h16, colsum, dh16.shape[0], dh16.shape[1], scale=scale)
 
 
+def mlp_dh(dm16, w2_16, h16, scale=1.0):
+    """dh = (dm @ W2) * (h > 0) * scale in one tcgen05 GEMM with the ReLU / hidden-dropout backward in its epilogue."""
+    r, f = h16.shape
+    assert dm16.is_contiguous() and w2_16.is_contiguous() and h16.is_contiguous() and dm16.dtype == w2_16.dtype == h16.dtype == BF16
+    dh = torch.empty_like(h16)
+    rc = _lib.load().sam2b200_mlp_dh(dm16.data_ptr(), w2_16.data_ptr(), h16.data_ptr(), dh.data_ptr(), r, f, float(scale),
+                                     _stream(h16.device))
+    _lib.check(rc, "sam2b200_mlp_dh")
+    return dh
+
+
 def dropout_inplace_(x16, drop):
     p_, seed, site = _drop(drop)
     if p_ > 0.0:
@@ -159,6 +170,7 @@ def direct_grads_possible(bucket, params) -> bool:
             and all(p.requires_grad and bucket.owns(p) for p in params))
 
 
+NO_MLP_KERNEL = bool(os.environ.get("SAM2B200_NO_MLP_KERNEL"))     # A/B switch: cuBLAS GEMM + separate ReLU-backward pass
 NO_SIDE_STREAM = bool(os.environ.get("SAM2B200_NO_SIDE_STREAM"))   # A/B switch: everything on one stream
 _SIDE_STREAMS = {}
 
@@ -430,9 +442,13 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             # ---- MLP backward
             dm = g16
             acc_w(ix["l2.w"], dm.t(), h)
-            dh = torch.mm(dm, W["l2.w"])
-            relu_bwd_colsum_(dh, h, gv[ix["l1.b"]], scale=relu_scale)
-            acc_w(ix["l1.w"], dh.t(), y3)
+            if NO_MLP_KERNEL:
+                dh = torch.mm(dm, W["l2.w"])
+                relu_bwd_colsum_(dh, h, gv[ix["l1.b"]], scale=relu_scale)
+                acc_w(ix["l1.w"], dh.t(), y3)
+            else:   # ReLU / hidden-dropout backward fused into the GEMM; the bias gradient joins the weight gradient (side stream)
+                dh = mlp_dh(dm, W["l2.w"], h, relu_scale)
+                acc_w(ix["l1.w"], dh.t(), y3, gv[ix["l1.b"]])
             dy3 = torch.mm(dh, W["l1.w"])
             g, dca = ln_bwd(dy3, x2, mean3, rstd3, P["n3.w"], g, gv[ix["n3.w"]], gv[ix["n3.b"]], dbias=gv[ix["ca.o.b"]],
                             drop=dsite("p_res", l, 3))

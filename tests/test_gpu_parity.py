@@ -406,6 +406,23 @@ def test_ln_fwd_bwd_kernels(dev):
     assert rel_l2(dg, gr.grad) < 1e-5 and rel_l2(db, br.grad) < 1e-5
 
 
+@pytest.mark.parametrize("rows", [128, 700, 4096])
+def test_mlp_dh_kernel(dev, rows):
+    """sam2b200_mlp_dh: dh = (dm @ W2) * (h > 0) * scale (tcgen05 GEMM, ReLU / hidden-dropout backward in the epilogue)
+    against fp32 torch on the same bf16 operands; ragged row count, zeros of h exactly where the reference masks."""
+    from sam2_video_training_b200 import fused_stack as fs
+    g = torch.Generator(device="cuda").manual_seed(rows)
+    dm = torch.randn(rows, 256, device=dev, generator=g).to(torch.bfloat16)
+    w2 = (torch.randn(256, 2048, device=dev, generator=g) / 16).to(torch.bfloat16)
+    h = torch.relu(torch.randn(rows, 2048, device=dev, generator=g)).to(torch.bfloat16)
+    for scale in (1.0, 1.0 / 0.9):
+        dh = fs.mlp_dh(dm, w2, h, scale)
+        ref = (dm.float() @ w2.float()) * (h.float() > 0) * scale
+        assert dh.dtype == torch.bfloat16 and dh.shape == ref.shape
+        assert rel_l2(dh, ref) < 4e-3, rel_l2(dh, ref)
+        assert torch.equal(dh == 0, (ref.to(torch.bfloat16) == 0) | (h == 0))
+
+
 @pytest.mark.parametrize("c", [256, 768, 2048])
 def test_colsum_kernels(dev, c):
     from sam2_video_training_b200 import fused_stack as fs

@@ -174,6 +174,15 @@ int sam2b200_mask_loss_bwd_coef(const float* const* logits, float* const* dlogit
                                 const float* coef, int T, int C, long long HW, float alpha, float gamma, float inv_temp,
                                 sam2b200_stream_t stream);
 
+/* ---- projections with fused bias + axial RoPE (transformer.py:277-279, :296-302; position_encoding.py:212-239) ------
+ * Y[R, Nout] = X[R, K] . W[Nout, K]^T + bias (bf16, fp32 accumulation; K = 256 or 64), written to up to three contiguous
+ * [R, 256] outputs (q | k | v); the first rope_cols output columns (multiple of 256) are rotated in the GEMM epilogue
+ * for rows whose position (row % rows_per_item) < n_rope_rows, table row = position % period.  One launch instead of
+ * addmm x Nout/256 + the RoPE pass. */
+int sam2b200_proj_rope(const void* x, const void* w, const void* bias, void* out0, void* out1, void* out2, long long R, int K,
+                       int Nout, int rope_cols, const float* table, int rows_per_item, int n_rope_rows, int period,
+                       sam2b200_stream_t stream);
+
 /* ---- MLP backward (memory_attention.py:95-98) ---------------------------------------------------------------
  * dh[R, F] = (dm[R, 256] . W2[256, F]) o (h[R, F] > 0) * scale: input gradient of linear2 with the ReLU (and hidden
  * dropout: h is the dropped activation, scale = 1/(1-p)) backward fused into the epilogue of a tcgen05 GEMM.

@@ -54,6 +54,8 @@ _SIGNATURES = {
                                                          c_float, c_float, c_int, c_int, c_void_p]),
     "sam2b200_mask_loss_bwd_coef": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_float,
                                             c_float, c_float, c_void_p]),
+    "sam2b200_proj_rope": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
+                                   c_void_p, c_int, c_int, c_int, c_void_p]),
     "sam2b200_mlp_dh": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p]),
     "sam2b200_bank_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                      c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

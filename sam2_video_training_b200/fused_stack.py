@@ -112,6 +112,21 @@ def relu_bwd_colsum_(dh16, h16, colsum, scale=1.0):
     _colsum(1, None, dh16, h16, colsum, dh16.shape[0], dh16.shape[1], scale=scale)
 
 
+def proj_rope(x16, w16, bias16, n_out, table=None, rope_outs=0, rows_per_item=1, n_rope_rows=0):
+    """Y = x @ w^T + bias with the axial rotation of the first `rope_outs` outputs fused into the GEMM epilogue
+    (sam2b200_proj_rope).  x16 [R, K] (K = 256 | 64), w16 [256 * n_out, K], bias16 [256 * n_out]; returns n_out
+    contiguous [R, 256] bf16 tensors (q | k | v)."""
+    r, k = x16.shape
+    assert x16.is_contiguous() and w16.is_contiguous() and bias16.is_contiguous() and w16.shape == (256 * n_out, k)
+    outs = [torch.empty((r, 256), dtype=BF16, device=x16.device) for _ in range(n_out)]
+    ptr = [o.data_ptr() for o in outs] + [None] * (3 - n_out)
+    rc = _lib.load().sam2b200_proj_rope(x16.data_ptr(), w16.data_ptr(), bias16.data_ptr(), ptr[0], ptr[1], ptr[2], r, k, 256 * n_out,
+                                        256 * rope_outs, table.data_ptr() if table is not None else None, int(rows_per_item),
+                                        int(n_rope_rows), table.shape[0] if table is not None else 1, _stream(x16.device))
+    _lib.check(rc, "sam2b200_proj_rope")
+    return outs
+
+
 def mlp_dh(dm16, w2_16, h16, scale=1.0):
     """dh = (dm @ W2) * (h > 0) * scale in one tcgen05 GEMM with the ReLU / hidden-dropout backward in its epilogue."""
     r, f = h16.shape
@@ -170,6 +185,12 @@ def direct_grads_possible(bucket, params) -> bool:
             and all(p.requires_grad and bucket.owns(p) for p in params))
 
 
+# The fused projection kernel (csrc/proj.cu: bias + RoPE in the GEMM epilogue) is OPT-IN: measured on B200 at cfg2 it ties
+# cuBLAS addmm + the RoPE pass inside the graph-replayed step (56.9 vs 56.6 ms) and loses for the K = 64 memory-bank
+# projections (profiles/r1_proj_rope_bench.txt).  SAM2B200_PROJ_KERNEL=1 routes the K = 256 projections through it,
+# SAM2B200_PROJ_KERNEL_K64=1 the K = 64 ones as well.
+NO_PROJ_KERNEL = not bool(os.environ.get("SAM2B200_PROJ_KERNEL"))
+PROJ_KERNEL_K64 = bool(os.environ.get("SAM2B200_PROJ_KERNEL_K64"))
 NO_MLP_KERNEL = bool(os.environ.get("SAM2B200_NO_MLP_KERNEL"))     # A/B switch: cuBLAS GEMM + separate ReLU-backward pass
 NO_SIDE_STREAM = bool(os.environ.get("SAM2B200_NO_SIDE_STREAM"))   # A/B switch: everything on one stream
 _SIDE_STREAMS = {}
@@ -240,6 +261,8 @@ class WeightMirror:
         first = []
         for l in range(nl):
             first += [l * _NPL + _LAYER_KEYS.index(k) for k in ("sa.q.w", "sa.k.w", "sa.v.w")]
+        for l in range(nl):     # ... and their biases (the fused q|k|v projection adds a stacked [768] bias)
+            first += [l * _NPL + _LAYER_KEYS.index(k) for k in ("sa.q.b", "sa.k.b", "sa.v.b")]
         order = first + [i for i in range(len(self.params)) if i not in set(first)]
         sizes = [-(-self.params[i].numel() // 64) * 64 for i in order]
         self.flat = torch.empty(sum(sizes), dtype=BF16, device=dev)
@@ -248,10 +271,13 @@ class WeightMirror:
         for i, n in zip(order, sizes):
             self.views[i] = self.flat[off:off + self.params[i].numel()].view_as(self.params[i])
             off += n
+        self.qkv_bias = []
         for l in range(nl):
             v0 = self.views[first[3 * l]]
             o0 = v0.storage_offset()
             self.qkv.append(self.flat[o0:o0 + 3 * v0.numel()].view(3 * v0.shape[0], v0.shape[1]))
+            b0 = self.views[first[3 * nl + 3 * l]]
+            self.qkv_bias.append(self.flat[b0.storage_offset():b0.storage_offset() + 3 * b0.numel()])
         self.versions = None
         self.device = dev
 
@@ -322,12 +348,20 @@ class MemoryAttentionStackFn(torch.autograd.Function):
         def dsite(p_key, l, k):
             return (dr[p_key], dr["seed"], l * 8 + k) if dr is not None and dr[p_key] > 0.0 else None
 
+        mirror = weight_mirror(masters)
+
         def project_memory():        # cross-attention keys / values of every layer: functions of the bank only
             for l in range(nl):
                 W = dict(zip(_LAYER_KEYS, wb[l * _NPL:(l + 1) * _NPL]))
-                k2 = torch.addmm(W["ca.k.b"], memk, W["ca.k.w"].t())
-                v2 = torch.addmm(W["ca.v.b"], memv, W["ca.v.w"].t())
-                k2_rot = rope_apply(k2.view(b, m, d), table, n_rope_k)
+                if not PROJ_KERNEL_K64:
+                    # K = 64: cuBLAS + the RoPE pass measured faster than the fused kernel (1777 CTAs of 64 KB output each
+                    # are dominated by per-CTA set-up: 129 vs 80 us, profiles/r1_proj_rope_bench.txt)
+                    k2 = torch.addmm(W["ca.k.b"], memk, W["ca.k.w"].t())
+                    v2 = torch.addmm(W["ca.v.b"], memv, W["ca.v.w"].t())
+                    k2_rot = rope_apply(k2.view(b, m, d), table, n_rope_k)
+                else:
+                    k2_rot = proj_rope(memk, W["ca.k.w"], W["ca.k.b"], 1, table, 1, m, n_rope_k)[0].view(b, m, d)
+                    v2 = proj_rope(memv, W["ca.v.w"], W["ca.v.b"], 1)[0]
                 kv_ready.append((k2_rot, v2, side.event()))
 
         side.run(project_memory, memk, memv)
@@ -336,17 +370,24 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             W = dict(zip(_LAYER_KEYS, wb[l * _NPL:(l + 1) * _NPL]))
             # ---- self attention (memory_attention.py:58-64)
             y1, x, mean1, rstd1 = ln_fwd(x, res, P["n1.w"], P["n1.b"], drop=dsite("p_res", l - 1, 5) if l > 0 else None)
-            q = torch.addmm(W["sa.q.b"], y1, W["sa.q.w"].t())
-            k = torch.addmm(W["sa.k.b"], y1, W["sa.k.w"].t())
-            v = torch.addmm(W["sa.v.b"], y1, W["sa.v.w"].t())
-            q_rot = rope_apply(q.view(b, n, d), table, n)
-            k_rot = rope_apply(k.view(b, n, d), table, n)
+            if NO_PROJ_KERNEL:
+                q = torch.addmm(W["sa.q.b"], y1, W["sa.q.w"].t())
+                k = torch.addmm(W["sa.k.b"], y1, W["sa.k.w"].t())
+                v = torch.addmm(W["sa.v.b"], y1, W["sa.v.w"].t())
+                q_rot = rope_apply(q.view(b, n, d), table, n)
+                k_rot = rope_apply(k.view(b, n, d), table, n)
+            else:   # one GEMM for q | k | v with bias, q and k rotated in its epilogue
+                q_rot, k_rot, v = proj_rope(y1, mirror.qkv[l], mirror.qkv_bias[l], 3, table, 2, n, n)
+                q_rot, k_rot = q_rot.view(b, n, d), k_rot.view(b, n, d)
             o, o32, lse = attn_fwd(q_rot, k_rot, v.view(b, n, d), scale, meta["nsplit"], drop=dsite("p_sa", l, 0))
             sa = torch.addmm(W["sa.o.b"], o.view(r, d), W["sa.o.w"].t())
             # ---- cross attention to the memory bank (memory_attention.py:66-81)
             y2, x1, mean2, rstd2 = ln_fwd(x, sa, P["n2.w"], P["n2.b"], drop=dsite("p_res", l, 2))
-            q2 = torch.addmm(W["ca.q.b"], y2, W["ca.q.w"].t())
-            q2_rot = rope_apply(q2.view(b, n, d), table, n)
+            if NO_PROJ_KERNEL:
+                q2 = torch.addmm(W["ca.q.b"], y2, W["ca.q.w"].t())
+                q2_rot = rope_apply(q2.view(b, n, d), table, n)
+            else:
+                q2_rot = proj_rope(y2, W["ca.q.w"], W["ca.q.b"], 1, table, 1, n, n)[0].view(b, n, d)
             k2_rot, v2, ev = kv_ready[l]
             side.wait(ev)
             o2, o2_32, lse2 = attn_fwd(q2_rot, k2_rot, v2.view(b, m, d), scale, meta["nsplit"], drop=dsite("p_ca", l, 1))

@@ -406,6 +406,32 @@ def test_ln_fwd_bwd_kernels(dev):
     assert rel_l2(dg, gr.grad) < 1e-5 and rel_l2(db, br.grad) < 1e-5
 
 
+@pytest.mark.parametrize("k,n_out,b,length,n_rope", [(256, 3, 3, 64, 64), (256, 1, 2, 144, 144), (64, 1, 2, 136, 128), (64, 1, 3, 100, 0)])
+def test_proj_rope_kernel(dev, k, n_out, b, length, n_rope):
+    """sam2b200_proj_rope: x @ W^T + bias with the axial rotation fused into the GEMM epilogue, against fp32 torch on
+    the same bf16 operands + the oracle's rotation (position_encoding.py:212-239): stacked q|k|v (v not rotated),
+    memory keys with un-rotated object-pointer rows, ragged row counts."""
+    from sam2_video_training_b200 import fused_stack as fs
+    from sam2_video_training_b200.modeling.position_encoding import compute_axial_cis
+    g = torch.Generator(device="cuda").manual_seed(k + n_out + length)
+    grid = 12 if n_rope == 144 else 8            # n_rope is a multiple of the table period (keys tile the table)
+    period = grid * grid
+    table = compute_axial_cis(dim=256, end_x=grid, end_y=grid).to(dev)
+    x = torch.randn(b * length, k, device=dev, generator=g).to(torch.bfloat16)
+    w = (torch.randn(256 * n_out, k, device=dev, generator=g) / k ** 0.5).to(torch.bfloat16)
+    bias = (torch.randn(256 * n_out, device=dev, generator=g) * 0.1).to(torch.bfloat16)
+    rope_outs = 0 if n_rope == 0 else (2 if n_out == 3 else 1)
+    outs = fs.proj_rope(x, w, bias, n_out, table if rope_outs else None, rope_outs, length, n_rope)
+    ref = (x.float() @ w.float().t() + bias.float()).view(b, length, 256 * n_out).cpu()
+    cos, sin = ao.axial_rope_table(period)
+    for i, o in enumerate(outs):
+        want = ref[:, :, 256 * i:256 * (i + 1)]
+        if i < rope_outs:
+            want = torch.cat([ao.apply_axial_rope(want[:, :n_rope], cos, sin), want[:, n_rope:]], dim=1)
+        assert o.shape == (b * length, 256) and o.dtype == torch.bfloat16
+        assert rel_l2(o.view(b, length, 256), want) < 4e-3, (i, rel_l2(o.view(b, length, 256), want))
+
+
 @pytest.mark.parametrize("rows", [128, 700, 4096])
 def test_mlp_dh_kernel(dev, rows):
     """sam2b200_mlp_dh: dh = (dm @ W2) * (h > 0) * scale (tcgen05 GEMM, ReLU / hidden-dropout backward in the epilogue)

@@ -191,3 +191,26 @@ def test_bank_oracle_matches_reference(golden_dir, tag):
     for got, key in ((tpos.grad, "d_tpos"), (pw.grad, "d_proj_w"), (pb.grad, "d_proj_b")):
         ref = torch.from_numpy(g[key])
         assert float((got - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max())), key
+
+
+def test_torch_baseline_matches_oracle():
+    """oracle/torch_gpu_baseline.py (the stock-PyTorch composition timed on the GPU box as the same-box
+    baseline) computes the same function as the oracle: forward and input gradients."""
+    import torch
+    from oracle import attention_oracle as ao
+    from oracle import torch_gpu_baseline as tb
+    g = torch.Generator().manual_seed(5)
+    n, b, nf, n_ptr = 16, 2, 2, 8
+    p = ao.init_params(seed=3)
+    curr = torch.randn(n, b, 256, generator=g).requires_grad_(True)
+    cpos = torch.randn(n, b, 256, generator=g)
+    mem = torch.randn(nf * n + n_ptr, b, 64, generator=g)
+    mpos = torch.randn(nf * n + n_ptr, b, 64, generator=g).requires_grad_(True)
+    go = torch.randn(n, b, 256, generator=g)
+    a = ao.memory_attention(p, curr, mem, cpos, mpos, n_ptr)
+    ga = torch.autograd.grad(a, [curr, mpos], go)
+    t = tb.memory_attention(p, curr, mem, cpos, mpos, n_ptr, tb.rope_table_complex(n))
+    gt = torch.autograd.grad(t, [curr, mpos], go)
+    assert (a - t).abs().max().item() < 2e-5
+    for x, y in zip(ga, gt):
+        assert (x - y).abs().max().item() < 2e-5 * max(1.0, x.abs().max().item())

@@ -76,6 +76,21 @@ def loss_inputs(t: int, c: int, s: int, clear=((1, 2),), dtype=torch.float32):
     return logits, targets, iou_pred
 
 
+def merged_inputs(t: int, n_obj: int, c: int, s: int, clear=((1, 0),), dtype=torch.float32):
+    """Producer-side fixture (oracle/merge_oracle.py): low-res logits [t, n_obj, 1, s, s], per-object IoU predictions
+    [t, n_obj, 1], object -> category map with the LAST category left without objects, targets [t, c, 4s, 4s]."""
+    low = det((t, n_obj, 1, s, s), 0.53, 0.27, 5.0, dtype)
+    iou_pred = det((t, n_obj, 1), 1.7, 0.4, 0.45, dtype) + 0.5
+    obj_to_cat = [(5 * i + 1) % max(c - 1, 1) for i in range(n_obj)]
+    S = 4 * s
+    i = torch.arange(t * c * S * S, dtype=torch.int64)
+    targets = (((i * 11) % 7) < 2).reshape(t, c, S, S)
+    for (ft, fc) in clear:
+        if ft < t and fc < c:
+            targets[ft, fc] = False
+    return low, iou_pred, obj_to_cat, targets
+
+
 def bank_scenarios():
     """(tag, kwargs) of the memory-bank assembly fixtures: frame index, conditioning / tracked frames present,
     train vs eval (stride, pointers in the past only), conditioning-frame limit, reverse tracking."""

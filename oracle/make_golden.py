@@ -129,6 +129,40 @@ def golden_functional(ns, n, m, s, tag):
     return rec
 
 
+def golden_merged(ns, t, n_obj, c, s, tag):
+    """Producer side of the loss through the UNMODIFIED reference: F.interpolate exactly as sam2_base.py:393-399 calls it,
+    merge_object_results_to_category (utils/masks.py:53-212) and MultiStepMultiMasksAndIous."""
+    import torch.nn.functional as F
+    masks = ref_shim.load_masks()
+    low, iou_pred, obj_to_cat, targets = detgen.merged_inputs(t, n_obj, c, s)
+    rec = dict(t=t, n_obj=n_obj, c=c, s=s, obj_to_cat=np.asarray(obj_to_cat))
+    for mode, kw in (("l1", dict(iou_use_l1_loss=True)), ("mse", dict(iou_use_l1_loss=False)),
+                     ("temp", dict(iou_use_l1_loss=True, logit_temperature=1.6, focal_alpha=0.6))):
+        crit = ns.MultiStepMultiMasksAndIous(
+            weight_dict={"loss_mask": 20, "loss_dice": 1, "loss_iou": 1, "loss_class": 0},
+            supervise_all_iou=True, pred_obj_scores=False, focal_gamma_obj_score=0.0, focal_alpha_obj_score=-1.0, **kw)
+        x = low.clone().requires_grad_(True)
+        ip = iou_pred.clone().requires_grad_(True)
+        stages = []
+        for f in range(t):
+            hi = F.interpolate(x[f].float(), size=(4 * s, 4 * s), mode="bilinear", align_corners=False)
+            stages.append({"pred_masks_high_res": hi, "multistep_pred_multimasks_high_res": [hi],
+                           "multistep_pred_ious": [ip[f]], "multistep_object_score_logits": [torch.zeros(n_obj, 1)],
+                           "point_inputs": None, "mask_inputs": None})
+        merged = masks.merge_object_results_to_category(stages, obj_to_cat, c)
+        if mode == "l1":
+            rec["merged_logits"] = torch.stack([m["multistep_pred_multimasks_high_res"][0] for m in merged]).detach().numpy()
+            rec["merged_ious"] = torch.stack([m["multistep_pred_ious"][0] for m in merged]).detach().numpy()
+        losses = crit(merged, targets)
+        losses["total_loss"].backward()
+        for k in ("loss_mask", "loss_dice", "loss_iou", "total_loss"):
+            rec[f"{mode}:{k}"] = float(losses[k])
+        rec[f"{mode}:dlow"] = x.grad.numpy()
+        rec[f"{mode}:diou"] = ip.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, f"merged_{tag}.npz"), **rec)
+    return rec
+
+
 def golden_loss(ns, t, c, s, tag):
     logits, targets, iou_pred = detgen.loss_inputs(t, c, s)
     rec = dict(t=t, c=c, s=s)
@@ -192,6 +226,10 @@ def main():
     print("loss: l1 total", r["l1:total_loss"], "mse total", r["mse:total_loss"], "bce", r["bce:total_loss"])
     golden_functional(ns, 3, 2, 24, "n3_m2_s24")
     golden_bank()
+    r = golden_merged(ns, 2, 5, 4, 6, "t2_n5_c4_s6")
+    print("merged: l1 total", r["l1:total_loss"], "mse", r["mse:total_loss"])
+    r = golden_merged(ns, 2, 7, 3, 11, "t2_n7_c3_s11")
+    print("merged2: l1 total", r["l1:total_loss"])
     r = golden_loss(ns, 3, 5, 40, "t3_c5_s40")
     print("loss2: l1 total", r["l1:total_loss"])
 

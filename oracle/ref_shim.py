@@ -83,6 +83,14 @@ def load_sam2_base():
     return _cache["sam2_base"].SAM2Base
 
 
+def load_masks():
+    """The reference's ``sam2_video/utils/masks.py`` (``merge_object_results_to_category``), loaded by path: the
+    package ``__init__`` pulls in out-of-scope modules, the file itself needs only torch, numpy, cv2 and loguru."""
+    if "masks" not in _cache:
+        _cache["masks"] = _load("_ref_sam2_video_masks", os.path.join(REF_ROOT, "sam2_video", "utils", "masks.py"))
+    return _cache["masks"]
+
+
 def build_memory_attention(ns=None, dropout: float = 0.1, feat_sizes=(64, 64)):
     """Construct the stack with the kwargs of configs/sam2/sam2.1_hiera_t.yaml:29-60."""
     ns = ns or load()

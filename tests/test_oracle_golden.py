@@ -214,3 +214,37 @@ def test_torch_baseline_matches_oracle():
     assert (a - t).abs().max().item() < 2e-5
     for x, y in zip(ga, gt):
         assert (x - y).abs().max().item() < 2e-5 * max(1.0, x.abs().max().item())
+
+
+MERGED_MODES = (("l1", dict(iou_use_l1_loss=True)), ("mse", dict(iou_use_l1_loss=False)),
+                ("temp", dict(iou_use_l1_loss=True, logit_temperature=1.6, focal_alpha=0.6)))
+
+
+@pytest.mark.parametrize("tag", ["t2_n5_c4_s6", "t2_n7_c3_s11"])
+def test_merge_oracle_matches_reference_golden(golden_dir, tag):
+    """oracle/merge_oracle.py (4x bilinear up-sampling + per-category max / area-weighted IoU merge + loss) against
+    fixtures produced by the unmodified reference (F.interpolate as sam2_base.py:393-399 + utils/masks.py:53-212 +
+    MultiStepMultiMasksAndIous), values and gradients w.r.t. the low-res logits and the per-object IoU predictions."""
+    import numpy as np
+    import torch
+    from oracle import detgen
+    from oracle import merge_oracle as mo
+    g = np.load(os.path.join(golden_dir, f"merged_{tag}.npz"))
+    t, n, c, s = int(g["t"]), int(g["n_obj"]), int(g["c"]), int(g["s"])
+    low, ip, o2c, tg = detgen.merged_inputs(t, n, c, s)
+    assert list(g["obj_to_cat"]) == o2c
+    groups = mo.category_groups(o2c, c)
+    for f in range(t):
+        x, iou = mo.merge_frame(mo.upsample_bilinear_x4(low[f]), ip[f], groups)
+        np.testing.assert_allclose(x.numpy(), g["merged_logits"][f], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(iou.numpy(), g["merged_ious"][f], rtol=0, atol=1e-6)
+    for mode, kw in MERGED_MODES:
+        x = low.clone().requires_grad_(True)
+        p = ip.clone().requires_grad_(True)
+        l = mo.merged_multistep_loss([x[f] for f in range(t)], [p[f] for f in range(t)], o2c, c, tg,
+                                     {"loss_mask": 20, "loss_dice": 1, "loss_iou": 1, "loss_class": 0}, **kw)
+        l["total_loss"].backward()
+        for k in ("loss_mask", "loss_dice", "loss_iou", "total_loss"):
+            assert abs(float(l[k]) - float(g[f"{mode}:{k}"])) <= 1e-5 * max(1.0, abs(float(g[f"{mode}:{k}"])))
+        np.testing.assert_allclose(x.grad.numpy(), g[f"{mode}:dlow"], rtol=0, atol=2e-7)
+        np.testing.assert_allclose(p.grad.numpy(), g[f"{mode}:diou"], rtol=0, atol=2e-7)

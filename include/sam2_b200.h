@@ -174,6 +174,31 @@ int sam2b200_mask_loss_bwd_coef(const float* const* logits, float* const* dlogit
                                 const float* coef, int T, int C, long long HW, float alpha, float gamma, float inv_temp,
                                 sam2b200_stream_t stream);
 
+/* ---- mask loss fused with its producer side ------------------------------------------
+ * Replaces, per frame, F.interpolate(low_res.float(), (S, S), "bilinear", align_corners=False)
+ * (sam2_video/model/modeling/sam2_base.py:393-399), merge_object_results_to_category (sam2_video/utils/masks.py:53-212:
+ * pixel-wise max over the objects of a category, IoU predictions averaged with the un-detached area weights
+ * sum(sigmoid(high-res logits)); empty category -> zeros) and MultiStepMultiMasksAndIous (losses.py:112-248, one step, one
+ * mask per channel, pred_obj_scores off).  S = 4 s; the high-resolution logits are never written to memory.
+ * low_res: HOST array of T device pointers, each [n_obj, s, s] fp32; targets: [T, C, S, S] u8/bool (4-byte aligned);
+ * obj_iou: [T, n_obj] fp32; group_offsets [C + 1] / group_members [n_obj]: DEVICE int32 CSR of the objects of each
+ * category in increasing object index (every object in exactly one category, at most 255 objects per category).
+ * Outputs: chan_sums [T, C, 6] and n_valid [T] as for sam2b200_mask_loss_fwd; obj_area [T, n_obj] (area weights),
+ * cat_iou [T, C] (merged IoU predictions), cat_w [T, C] (sum of weights), losses [4] = loss_mask, loss_dice, loss_iou, 0.
+ * T <= 64 per call.  Backward: dlow_res (HOST array of T device pointers [n_obj, s, s], every element written) and
+ * d_obj_iou [T, n_obj]; grad_losses: device [3]. */
+size_t sam2b200_merged_loss_workspace_bytes(int T, int C, int n_obj, int s);
+int sam2b200_merged_loss_fwd(const float* const* low_res, const uint8_t* targets, const float* obj_iou,
+                             const int* group_offsets, const int* group_members, void* workspace, float* chan_sums,
+                             float* obj_area, float* cat_iou, float* cat_w, int* n_valid, float* losses, int T, int C,
+                             int n_obj, int s, float alpha, float gamma, float inv_temp, int iou_l1,
+                             sam2b200_stream_t stream);
+int sam2b200_merged_loss_bwd(const float* const* low_res, float* const* dlow_res, const uint8_t* targets,
+                             const float* obj_iou, const int* group_offsets, const int* group_members,
+                             const float* chan_sums, const float* obj_area, const float* cat_iou, const float* cat_w,
+                             const int* n_valid, const float* grad_losses, float* d_obj_iou, int T, int C, int n_obj, int s,
+                             float alpha, float gamma, float inv_temp, int iou_l1, sam2b200_stream_t stream);
+
 /* ---- projections with fused bias + axial RoPE (transformer.py:277-279, :296-302; position_encoding.py:212-239) ------
  * Y[R, Nout] = X[R, K] . W[Nout, K]^T + bias (bf16, fp32 accumulation; K = 256 or 64), written to up to three contiguous
  * [R, 256] outputs (q | k | v); the first rope_cols output columns (multiple of 256) are rotated in the GEMM epilogue

@@ -725,3 +725,108 @@ def test_memory_bank_assembly_matches_oracle(dev, golden_dir, tag, dtype):
     (rp.float() * w).sum().backward()
     assert rel_l2(tpos_d.grad.cpu(), to.grad) < 1e-5
     assert rel_l2(proj.weight.grad.cpu(), pwo.grad) < 1e-5 and rel_l2(proj.bias.grad.cpu(), pbo.grad) < 1e-5
+
+
+# ---- mask loss fused with its producer side (4x bilinear up-sampling + category merge), SURVEY.md section 8f rank 2 ----
+
+MERGED_W = {"loss_mask": 20, "loss_dice": 1, "loss_iou": 1, "loss_class": 0}
+MERGED_MODES = (("l1", dict(iou_use_l1_loss=True)), ("mse", dict(iou_use_l1_loss=False)),
+                ("temp", dict(iou_use_l1_loss=True, logit_temperature=1.6, focal_alpha=0.6)))
+
+
+def _merged_stages(low, ious):
+    return [{"multistep_pred_multimasks": [low[f]], "multistep_pred_ious": [ious[f]]} for f in range(len(low))]
+
+
+@pytest.mark.parametrize("tag", ["t2_n5_c4_s6", "t2_n7_c3_s11"])
+def test_merged_loss_vs_reference_golden(dev, golden_dir, tag):
+    """Fused up-sample + merge + loss against fixtures produced by the unmodified reference chain (F.interpolate,
+    merge_object_results_to_category, MultiStepMultiMasksAndIous): values <= 1e-3 relative (measured ~1e-6),
+    gradients w.r.t. the low-res logits and the per-object IoU predictions."""
+    from sam2_video_training_b200.merged_loss import CategoryMergedMultiStepLoss
+    g = np.load(os.path.join(golden_dir, f"merged_{tag}.npz"))
+    t, n, c, s = int(g["t"]), int(g["n_obj"]), int(g["c"]), int(g["s"])
+    low, ip, o2c, tg = detgen.merged_inputs(t, n, c, s)
+    for mode, kw in MERGED_MODES:
+        crit = CategoryMergedMultiStepLoss(dict(MERGED_W), supervise_all_iou=True, **kw)
+        x = [low[f].to(dev).requires_grad_(True) for f in range(t)]
+        p = [ip[f].to(dev).requires_grad_(True) for f in range(t)]
+        losses = crit(_merged_stages(x, p), o2c, c, tg.to(dev))
+        losses["total_loss"].backward()
+        for k in ("loss_mask", "loss_dice", "loss_iou", "total_loss"):
+            ref = float(g[f"{mode}:{k}"])
+            assert abs(float(losses[k]) - ref) <= 1e-5 * max(1.0, abs(ref)), (mode, k)
+        dlow = torch.stack([v.grad for v in x]).cpu().numpy()
+        diou = torch.stack([v.grad for v in p]).cpu().numpy()
+        assert rel_l2(torch.from_numpy(dlow), torch.from_numpy(g[f"{mode}:dlow"])) < 2e-5, mode
+        np.testing.assert_allclose(diou, g[f"{mode}:diou"], rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("t,n_obj,c,s,o2c", [
+    (3, 6, 4, 96, [0, 2, 0, 1, 2, 2]),          # cfg2 resolution (384 px), category 3 without objects
+    (2, 3, 3, 50, [2, 0, 1]),                    # ragged tiles (s not a multiple of 8 / 32), one object per category
+    (1, 4, 1, 5, [0, 0, 0, 0]),                  # smaller than one tile, all objects in one category
+    (1, 9, 2, 128, [1, 1, 1, 1, 1, 1, 1, 1, 0]),  # 512 px, 8 objects in one category
+])
+def test_merged_loss_vs_oracle_random(dev, t, n_obj, c, s, o2c):
+    from oracle import merge_oracle as mo
+    from sam2_video_training_b200.merged_loss import CategoryMergedMultiStepLoss
+    g = torch.Generator().manual_seed(100 + s)
+    low = torch.randn(t, n_obj, 1, s, s, generator=g) * 4
+    ip = torch.rand(t, n_obj, 1, generator=g)
+    S = 4 * s
+    yy, xx = torch.meshgrid(torch.arange(S), torch.arange(S), indexing="ij")
+    tg = torch.zeros(t, c, S, S, dtype=torch.bool)
+    for f in range(t):
+        for ch in range(c):
+            if c > 2 and f == 1 and ch == 1:
+                continue                          # an empty channel: exercises the valid filter
+            cx, cy = S * (0.3 + 0.4 * torch.rand((), generator=g)), S * (0.3 + 0.4 * torch.rand((), generator=g))
+            r = S * (0.1 + 0.2 * torch.rand((), generator=g))
+            tg[f, ch] = (xx - cx) ** 2 + (yy - cy) ** 2 < r * r
+    kw = dict(iou_use_l1_loss=False)
+    xo = low.clone().requires_grad_(True)
+    po = ip.clone().requires_grad_(True)
+    ref = mo.merged_multistep_loss([xo[f] for f in range(t)], [po[f] for f in range(t)], o2c, c, tg, dict(MERGED_W), **kw)
+    ref["total_loss"].backward()
+    crit = CategoryMergedMultiStepLoss(dict(MERGED_W), supervise_all_iou=True, **kw)
+    x = [low[f].to(dev).requires_grad_(True) for f in range(t)]
+    p = [ip[f].to(dev).requires_grad_(True) for f in range(t)]
+    out = crit(_merged_stages(x, p), o2c, c, tg.to(dev))
+    out["total_loss"].backward()
+    for k in ("loss_mask", "loss_dice", "loss_iou", "total_loss"):
+        assert abs(float(out[k]) - float(ref[k])) <= 1e-4 * max(1.0, abs(float(ref[k]))), k   # bound from BASELINE.json: 1e-3
+    dlow = torch.stack([v.grad for v in x]).cpu()
+    assert rel_l2(dlow, xo.grad) < 1e-4
+    cosv = torch.nn.functional.cosine_similarity(dlow.flatten().double(), xo.grad.flatten().double(), dim=0)
+    assert cosv > 0.99999
+    np.testing.assert_allclose(torch.stack([v.grad for v in p]).cpu().numpy(), po.grad.numpy(), rtol=1e-3, atol=1e-6)
+    # the merged op equals the un-fused pipeline of this package: up-sample + max on the GPU with torch, then the fused loss
+    from sam2_video_training_b200.losses import MultiStepMultiMasksAndIous
+    hi = [torch.nn.functional.interpolate(low[f].to(dev), size=(S, S), mode="bilinear", align_corners=False) for f in range(t)]
+    groups = mo.category_groups(o2c, c)
+    merged = [mo.merge_frame(hi[f], ip[f].to(dev), groups) for f in range(t)]
+    outs = [{"multistep_pred_multimasks_high_res": [m[0]], "multistep_pred_ious": [m[1]],
+             "multistep_object_score_logits": [None]} for m in merged]
+    un = MultiStepMultiMasksAndIous(dict(MERGED_W), supervise_all_iou=True, **kw)(outs, tg.to(dev))
+    assert abs(float(un["total_loss"]) - float(out["total_loss"])) <= 1e-5 * abs(float(un["total_loss"]))
+
+
+def test_merged_loss_error_contract(dev):
+    from sam2_video_training_b200.merged_loss import CategoryMergedMultiStepLoss
+    with pytest.raises(NotImplementedError):
+        CategoryMergedMultiStepLoss(dict(MERGED_W), pred_obj_scores=True)
+    with pytest.raises(ValueError):
+        CategoryMergedMultiStepLoss(dict(MERGED_W), logit_temperature=0)
+    crit = CategoryMergedMultiStepLoss(dict(MERGED_W))
+    low = torch.randn(2, 1, 8, 8, device=dev)
+    iou = torch.rand(2, 1, device=dev)
+    tg = torch.zeros(1, 2, 32, 32, dtype=torch.bool, device=dev)
+    with pytest.raises(ValueError, match="No valid masks"):           # losses.py:161
+        crit(_merged_stages([low], [iou]), [0, 1], 2, tg)
+    with pytest.raises(ValueError):                                    # wrong target resolution
+        crit(_merged_stages([low], [iou]), [0, 1], 2, torch.ones(1, 2, 16, 16, dtype=torch.bool, device=dev))
+    with pytest.raises(IndexError):
+        crit(_merged_stages([low], [iou]), [0, 5], 2, torch.ones(1, 2, 32, 32, dtype=torch.bool, device=dev))
+    with pytest.raises(AssertionError):                                # losses.py:113
+        crit(_merged_stages([low, low], [iou, iou]), [0, 1], 2, tg)

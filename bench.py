@@ -119,28 +119,59 @@ def to_device(h, dev):
     return out
 
 
-def assemble_banks(d, wl):
+def assemble_bank(d, wl, t):
     """[cond frame | older frames | pointer tokens] like sam2_base.py:691-692 (torch.cat on device)."""
-    n, T = wl["grid"] ** 2, wl["T"]
-    banks = []
-    for t in range(1, T):
-        nf = min(t, 7)
-        mem = torch.cat([d["mem_feat"][i][:n] for i in range(nf)] + [d["mem_feat"][i][n:] for i in range(nf)], dim=0)
-        pos = torch.cat([d["mem_pos"][i][:n] for i in range(nf)] + [d["mem_pos"][i][n:] for i in range(nf)], dim=0)
-        # memory_pos carries gradient in real training (maskmem_tpos_enc, sam2_base.py:608-610): ask for it
-        banks.append((mem, pos.requires_grad_(True), 4 * nf))
-    return banks
+    n = wl["grid"] ** 2
+    nf = min(t, 7)
+    mem = torch.cat([d["mem_feat"][i][:n] for i in range(nf)] + [d["mem_feat"][i][n:] for i in range(nf)], dim=0)
+    pos = torch.cat([d["mem_pos"][i][:n] for i in range(nf)] + [d["mem_pos"][i][n:] for i in range(nf)], dim=0)
+    # memory_pos carries gradient in real training (maskmem_tpos_enc, sam2_base.py:608-610): ask for it
+    return mem, pos.requires_grad_(True), 4 * nf
 
 
-def run_step(model, crit, opt, d, banks, wl, world, fwd=None):
+def assemble_banks(d, wl):
+    return [assemble_bank(d, wl, t) for t in range(1, wl["T"])]
+
+
+def to_device_streamed(h, dev, wl, stream):
+    """H2D of one step's inputs on `stream` in the order the step consumes them, with one event per attention frame
+    and one for the loss inputs, so that the first frame starts as soon as ITS inputs have landed."""
+    out = {k: ([None] * len(v) if isinstance(v, list) else None) for k, v in h.items()}
+    events = []
+    with torch.cuda.stream(stream):
+        out["curr_pos"] = h["curr_pos"].to(dev, non_blocking=True)
+        for t in range(1, wl["T"]):
+            out["curr"][t - 1] = h["curr"][t - 1].to(dev, non_blocking=True)
+            out["grad_out"][t - 1] = h["grad_out"][t - 1].to(dev, non_blocking=True)
+            if t - 1 < len(h["mem_feat"]):
+                out["mem_feat"][t - 1] = h["mem_feat"][t - 1].to(dev, non_blocking=True)
+                out["mem_pos"][t - 1] = h["mem_pos"][t - 1].to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            events.append(ev)
+        for k in ("logits", "iou", "targets"):
+            out[k] = [x.to(dev, non_blocking=True) for x in h[k]]
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        events.append(ev)
+    return out, events
+
+
+def run_step(model, crit, opt, d, banks, wl, world, fwd=None, arrivals=None):
+    """`arrivals` (end-to-end leg): events of the copy stream, one per attention frame (inputs of frame t and the
+    memory frames it reads have landed) + one for the loss inputs; `banks` may then be a function t -> bank."""
     T, C = wl["T"], wl["C"]
     fwd = fwd or model
     for t in range(1, T):
-        mem, pos, p = banks[t - 1]
+        if arrivals is not None:
+            torch.cuda.current_stream().wait_event(arrivals[t - 1])
+        mem, pos, p = banks(t) if callable(banks) else banks[t - 1]
         out = fwd(d["curr"][t - 1], mem, d["curr_pos"], pos, p)
         out.backward(d["grad_out"][t - 1])
         pos.grad = None
     total = None
+    if arrivals is not None:
+        torch.cuda.current_stream().wait_event(arrivals[-1])
     for ci in range(wl["clips"]):
         xs = [d["logits"][ci * T + f].requires_grad_(True) for f in range(T)]
         ip = d["iou"][ci].requires_grad_(True)
@@ -459,23 +490,19 @@ def main():
     if not args.no_e2e:
         copy_stream = torch.cuda.Stream()
 
-        def start_copy():   # H2D of one step's inputs from pinned host memory, on the copy stream
-            with torch.cuda.stream(copy_stream):
-                dd = to_device(host, dev)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-            return dd, ev
+        def start_copy():   # H2D of one step's inputs from pinned host memory, on the copy stream, in consumption order
+            return to_device_streamed(host, dev, wl, copy_stream)
 
         def e2e_loop(k):
-            # double-buffered: the copy of step i+1 overlaps the compute of step i; every copy is inside the timed region
+            # double-buffered: the copy of step i+1 overlaps the compute of step i, and within a step frame t only waits
+            # for its own inputs; every copy is inside the timed region
             nxt = start_copy()
             for i in range(k):
-                dd, ev = nxt
-                torch.cuda.current_stream().wait_event(ev)
+                dd, evs = nxt
                 if i + 1 < k:
                     nxt = start_copy()
-                bk = assemble_banks(dd, wl)
-                tot = run_step(model, crit, opt, dd, bk, wl, world, fwd=run_model)
+                tot = run_step(model, crit, opt, dd, lambda t: assemble_bank(dd, wl, t), wl, world, fwd=run_model,
+                               arrivals=evs)
                 float(tot.item())   # D2H of the step's loss (also keeps `dd` alive until the step is done)
 
         e2e_loop(2)

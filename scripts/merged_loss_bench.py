@@ -93,6 +93,9 @@ def bench(name, T, C, per_cat, s, nsets, iters):
                       "kernel_GBps": round(fused_bytes / sum(kern.values()) / 1e3, 1)}), flush=True)
 
 
+if "--ncu" in sys.argv:      # short run for an ncu capture
+    bench("1024 px, T=8, 4 categories x 2 objects", 8, 4, 2, 256, 2, 2)
+    sys.exit(0)
 bench("cfg2 clip (384 px, T=10, 7 categories x 2 objects)", 10, 7, 2, 96, 16, 32)
 bench("cfg3 clip (512 px, T=8, 13 categories x 1 object)", 8, 13, 1, 128, 8, 32)
 bench("1024 px, T=8, 4 categories x 2 objects", 8, 4, 2, 256, 6, 24)

@@ -15,6 +15,7 @@
 #include "abi_common.cuh"
 #include "attn_kernels.cuh"
 #include "attn_pair_kernel.cuh"
+#include "attn_persist_kernels.cuh"
 #include "tma_desc.cuh"
 
 namespace {
@@ -145,6 +146,16 @@ unsigned long long* timeline_slice(size_t ctas) {
   unsigned long long* p = g_timeline + g_timeline_used;
   g_timeline_used += ctas * 8;
   return p;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
 }
 
 template <typename K>
@@ -329,6 +340,10 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
   static const bool force_pair = getenv("SAM2B200_PAIR_KERNEL") != nullptr;
   static const bool no_pair = getenv("SAM2B200_NO_PAIR_KERNEL") != nullptr;
   const bool use_pair = !no_pair && (force_pair || N >= 1024);
+  // Persistent key-side kernels (attn_persist_kernels.cuh) for the short query loops the pair kernel does not cover.
+  // SAM2B200_NO_PERSIST=1 switches back to one CTA per (key block, object).
+  static const bool no_persist = getenv("SAM2B200_NO_PERSIST") != nullptr;
+  const bool use_persist = !no_persist;
   if ((parts & 6) == 6 && use_pair) {
     attn::PairParams p{};
     p.Lk = M; p.Lq = N; p.scale_log2 = scale * kLog2e; p.scale = scale; p.lse2 = lse2; p.delta = delta;
@@ -351,10 +366,18 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
     p.drop = drop;
     p.tiles_per_split = (N + attn::kBlockN - 1) / attn::kBlockN;
     const size_t smem = sizeof(attn::SharedStorage) + 1024;
-    if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_DV>, smem))) return rc;
     dim3 grid((M + attn::kBlockM - 1) / attn::kBlockM, B, 1);
-    p.dbg = timeline_slice((size_t)grid.x * grid.y);
-    attn::two_gemm_kernel<attn::MODE_DV><<<grid, attn::kThreads, smem, stream>>>(map_q64, map_do64, map_k128, map_dv, map_dv, p);
+    p.n_atiles = (int)grid.x;
+    p.n_items = (int)(grid.x * grid.y);
+    if (use_persist && grad_dtype && p.n_items > num_sms()) {
+      // resident CTAs walking (key block, object) items: attn_persist_kernels.cuh
+      if ((rc = set_smem(attn::dv_persistent_kernel, smem))) return rc;
+      attn::dv_persistent_kernel<<<num_sms(), attn::kThreads, smem, stream>>>(map_q64, map_do64, map_k128, map_dv, p);
+    } else {
+      if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_DV>, smem))) return rc;
+      p.dbg = timeline_slice((size_t)grid.x * grid.y);
+      attn::two_gemm_kernel<attn::MODE_DV><<<grid, attn::kThreads, smem, stream>>>(map_q64, map_do64, map_k128, map_dv, map_dv, p);
+    }
     if ((rc = sam2b200::check_launch("attn_bwd dV"))) return rc;
   }
   const size_t smem3 = sizeof(attn::SharedStorage3) + 1024;
@@ -365,10 +388,18 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
     p.lse2 = lse2; p.delta = delta;
     p.gout = attn::GradOut{grad_dtype, dbias_k, table, table ? n_rope_k : 0, table ? rope_period : 1};
     p.drop = drop;
-    if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DK>, smem3))) return rc;
     dim3 grid((M + attn::kBlockM - 1) / attn::kBlockM, B, 1);
-    p.dbg = timeline_slice((size_t)grid.x * grid.y);
-    attn::three_gemm_kernel<attn::MODE_DK><<<grid, attn::kThreads, smem3, stream>>>(map_v128, map_q64, map_do64, map_k128, map_dk, p);
+    p.n_atiles = (int)grid.x;
+    p.n_items = (int)(grid.x * grid.y);
+    static const bool no_persist_dk = getenv("SAM2B200_NO_PERSIST_DK") != nullptr;
+    if (use_persist && !no_persist_dk && grad_dtype && p.n_items > num_sms()) {
+      if ((rc = set_smem(attn::dk_persistent_kernel, smem3))) return rc;
+      attn::dk_persistent_kernel<<<num_sms(), attn::kThreads, smem3, stream>>>(map_v128, map_q64, map_do64, map_k128, map_dk, p);
+    } else {
+      if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DK>, smem3))) return rc;
+      p.dbg = timeline_slice((size_t)grid.x * grid.y);
+      attn::three_gemm_kernel<attn::MODE_DK><<<grid, attn::kThreads, smem3, stream>>>(map_v128, map_q64, map_do64, map_k128, map_dk, p);
+    }
     if ((rc = sam2b200::check_launch("attn_bwd dK"))) return rc;
   }
   // dQ = scale * dS K: fixed (Q in TMEM, dO in SMEM), stream (K, V) tiles

@@ -104,6 +104,7 @@ struct TwoGemmParams {
   sam2b200::Dropout drop;      // attention-probability dropout (transformer.py:304-306); element index (b N + q) M + key
   int tiles_per_split;
   unsigned long long* dbg;     // optional timeline buffer
+  int n_items, n_atiles;       // persistent kernels: items = (a block, batch) pairs, a blocks per batch
 };
 
 struct SharedStorage {
@@ -629,6 +630,7 @@ struct ThreeGemmParams {
   GradOut gout;                // dQ / dK
   sam2b200::Dropout drop;      // attention-probability dropout: dP is masked and scaled like P was in the forward
   unsigned long long* dbg;     // optional timeline buffer
+  int n_items, n_atiles;       // persistent kernel: items = (a block, batch) pairs, a blocks per batch
 };
 
 struct SharedStorage3 {
@@ -647,6 +649,7 @@ struct SharedStorage3 {
   uint64_t dp_full;
   uint64_t ds_ready;
   uint64_t acc_done;
+  uint64_t a2_empty;           // persistent kernel: the last dP MMA of an item has read A2
   float col_lse[2][kBlockN];
   float col_delta[2][kBlockN];
   uint32_t tmem_base;

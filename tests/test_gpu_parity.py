@@ -660,6 +660,47 @@ def test_attention_backward_pair_kernel_long_query_loop(dev):
     assert rel_l2(dk2, want) < 1e-5 and torch.equal(dv2, dv)
 
 
+@pytest.mark.parametrize("b,grid,nf,extra,drop", [(8, 24, 4, 196, 0.0), (5, 24, 7, 28, 0.1), (40, 8, 7, 12, 0.0)])
+def test_attention_backward_persistent_key_side_kernels(dev, b, grid, nf, extra, drop):
+    """bf16 gradients with more (key block, object) items than SMs take the PERSISTENT dV / dK kernels
+    (attn_persist_kernels.cuh: resident CTAs, slot ring with operand prefetch and an epilogue slot); fp32 gradients take
+    the one-CTA-per-item kernels.  Per item both run the same MMAs in the same order, so the bf16 results must be the
+    bf16 rounding of the fp32 results bit for bit -- ragged last key block, RoPE, dropout, fused bias gradients."""
+    from sam2_video_training_b200 import ops
+    from sam2_video_training_b200.modeling.position_encoding import compute_axial_cis
+    g = torch.Generator(device="cuda").manual_seed(23)
+    n = grid * grid
+    m = nf * n + extra
+    assert ((m + 127) // 128) * b > torch.cuda.get_device_properties(dev).multi_processor_count
+    table = compute_axial_cis(dim=256, end_x=grid, end_y=grid).to(dev)
+    q = torch.randn(b, n, 256, device=dev, generator=g).to(torch.bfloat16)
+    k = torch.randn(b, m, 256, device=dev, generator=g).to(torch.bfloat16)
+    v = torch.randn(b, m, 256, device=dev, generator=g).to(torch.bfloat16)
+    do = torch.randn(b, n, 256, device=dev, generator=g).to(torch.bfloat16)
+    dr = None
+    if drop > 0:
+        dr = (drop, torch.tensor([12345], dtype=torch.int64, device=dev), 3)
+    o, o32, lse = ops.attn_fwd(q, k, v, 1 / 16.0, drop=dr)
+    res = {}
+    for gdt in (torch.float32, torch.bfloat16):
+        db = [torch.zeros(256, device=dev) for _ in range(3)]
+        res[gdt] = ops.attn_bwd(q, k, v, None, o32, do, lse, 1 / 16.0, table=table, n_rope_k=nf * n, grad_dtype=gdt,
+                                dbias=tuple(db), drop=dr) + (db,)
+    torch.cuda.synchronize()
+    for i, name in ((1, "dk"), (2, "dv")):
+        assert torch.equal(res[torch.float32][i].to(torch.bfloat16), res[torch.bfloat16][i]), name
+    for j in (1, 2):
+        assert rel_l2(res[torch.bfloat16][3][j], res[torch.float32][3][j]) < 2e-3
+    if drop == 0.0:   # and against an fp32 torch restatement of the core
+        kr = ops.rope_apply(k, table, nf * n, out_dtype=torch.float32)
+        qf, kf, vf = q.float().requires_grad_(True), kr.requires_grad_(True), v.float().requires_grad_(True)
+        ref = torch.softmax(qf @ kf.transpose(1, 2) / 16.0, dim=-1) @ vf
+        ref.backward(do.float())
+        want_dk = ops.rope_apply(kf.grad, table, nf * n, inverse=True, out_dtype=torch.float32)
+        assert rel_l2(res[torch.bfloat16][1].float(), want_dk) < 8e-3
+        assert rel_l2(res[torch.bfloat16][2].float(), vf.grad) < 8e-3
+
+
 def test_attention_backward_fused_bias_gradients(dev):
     """sam2b200_attn_bwd_ex: the q / k / v bias gradients (column sums of dq / dk / dv over all rows, after the
     conjugate rotation) are accumulated inside the gradient epilogues -- ragged sizes, bf16 and fp32 outputs."""

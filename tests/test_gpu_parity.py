@@ -692,8 +692,8 @@ def test_attention_backward_persistent_key_side_kernels(dev, b, grid, nf, extra,
     for j in (1, 2):
         assert rel_l2(res[torch.bfloat16][3][j], res[torch.float32][3][j]) < 2e-3
     if drop == 0.0:   # and against an fp32 torch restatement of the core
-        kr = ops.rope_apply(k, table, nf * n, out_dtype=torch.float32)
-        qf, kf, vf = q.float().requires_grad_(True), kr.requires_grad_(True), v.float().requires_grad_(True)
+        # q and k ARE the rotated operands; `table` only makes the kernels rotate the gradients back
+        qf, kf, vf = q.float().requires_grad_(True), k.float().requires_grad_(True), v.float().requires_grad_(True)
         ref = torch.softmax(qf @ kf.transpose(1, 2) / 16.0, dim=-1) @ vf
         ref.backward(do.float())
         want_dk = ops.rope_apply(kf.grad, table, nf * n, inverse=True, out_dtype=torch.float32)

@@ -174,15 +174,15 @@ def run_step(model, crit, opt, d, banks, wl, world, fwd=None, arrivals=None):
         torch.cuda.current_stream().wait_event(arrivals[-1])
     for ci in range(wl["clips"]):
         xs = [d["logits"][ci * T + f].requires_grad_(True) for f in range(T)]
-        ip = d["iou"][ci].requires_grad_(True)
-        outs = [{"multistep_pred_multimasks_high_res": [xs[f]], "multistep_pred_ious": [ip[f]],
+        # per-frame IoU-head outputs are separate leaves, as the tracker produces them (one [C, 1] tensor per frame)
+        ips = [v.detach().requires_grad_(True) for v in d["iou"][ci].unbind(0)]
+        outs = [{"multistep_pred_multimasks_high_res": [xs[f]], "multistep_pred_ious": [ips[f]],
                  "multistep_object_score_logits": [None]} for f in range(T)]
         losses = crit(outs, d["targets"][ci])
         losses["total_loss"].backward()
         total = losses["total_loss"].detach() if total is None else total + losses["total_loss"].detach()
         for x in xs:
             x.grad = None
-        ip.grad = None
     if world > 1:
         from sam2_video_training_b200 import ddp
         ddp.allreduce_gradients(model, world)

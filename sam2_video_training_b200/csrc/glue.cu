@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "abi_common.cuh"
 #include "dropout.cuh"
@@ -122,56 +123,77 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ 
   for (int i = 0; i < 8; ++i) { dgam[i] = 0.f; dbet[i] = 0.f; dbias[i] = 0.f; }
   const int nrow = (g16 != nullptr) ? 3 : 2;
   const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp; row < rows; row += warps_total) {
-    float dy[8], xv[8];
-    if (dy16 != nullptr) {
-      unpack8(*reinterpret_cast<const uint4*>(dy16 + row * kD + lane * 8), dy);
-    } else {
-      long long irow = row;
-      if (tr_b > 0) { const long long bi = row / tr_n, ni = row % tr_n; irow = ni * tr_b + bi; }
-      const float4* dp = reinterpret_cast<const float4*>(dy32 + irow * kD + lane * 8);
-      const float4 a = dp[0], b = dp[1];
-      dy[0] = a.x; dy[1] = a.y; dy[2] = a.z; dy[3] = a.w; dy[4] = b.x; dy[5] = b.y; dy[6] = b.z; dy[7] = b.w;
-    }
-    const float4* xp = reinterpret_cast<const float4*>(x + row * kD + lane * 8);
-    const float4 a = xp[0], b = xp[1];
-    xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w; xv[4] = b.x; xv[5] = b.y; xv[6] = b.z; xv[7] = b.w;
-    const float mu = mean[row], rs = rstd[row];
-    float xh[8], s1 = 0.f, s2 = 0.f;
+  const uint32_t drop_key = (g16 != nullptr && drop.seed != nullptr) ? sam2b200::dropout_key(*drop.seed, drop.site) : 0u;
+  // Two rows per iteration: the loads of both rows (dy, x, g_in, mean, rstd) are issued before any arithmetic, which
+  // doubles the bytes a warp keeps in flight (the kernel is latency bound at 16 warps per SM).
+#ifndef SAM2B200_LN_BWD_UNROLL
+#define SAM2B200_LN_BWD_UNROLL 2
+#endif
+  constexpr int kU = SAM2B200_LN_BWD_UNROLL;
+  for (long long base = (long long)blockIdx.x * (blockDim.x >> 5) + warp; base < rows; base += kU * warps_total) {
+    float dy[kU][8], xv[kU][8], gi[kU][8], mu[kU], rs[kU];
+    bool ok[kU];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      xh[i] = (xv[i] - mu) * rs;
-      const float dg = dy[i] * gg[i];
-      s1 += dg; s2 += dg * xh[i];
-      dgam[i] += dy[i] * xh[i];
-      dbet[i] += dy[i];
-    }
-    s1 = warp_sum(s1) * (1.0f / kD);
-    s2 = warp_sum(s2) * (1.0f / kD);
-    float o[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = rs * (dy[i] * gg[i] - s1 - xh[i] * s2);
-    if (g_in != nullptr) {
-      const float4* ip = reinterpret_cast<const float4*>(g_in + row * kD + lane * 8);
-      const float4 c = ip[0], d = ip[1];
-      o[0] += c.x; o[1] += c.y; o[2] += c.z; o[3] += c.w; o[4] += d.x; o[5] += d.y; o[6] += d.z; o[7] += d.w;
-    }
-    float4* op = reinterpret_cast<float4*>(g_out + row * kD + lane * 8);
-    op[0] = make_float4(o[0], o[1], o[2], o[3]);
-    op[1] = make_float4(o[4], o[5], o[6], o[7]);
-    if (g16 != nullptr) {
-      if (drop.seed != nullptr) {
-        const uint32_t key = sam2b200::dropout_key(*drop.seed, drop.site);
-        const uint32_t idx = (uint32_t)(row * kD + lane * 8);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = sam2b200::dropout_keep(key, idx + i, drop.thresh) ? o[i] * drop.inv_keep : 0.f;
+    for (int u = 0; u < kU; ++u) {
+      const long long row = base + u * warps_total;
+      ok[u] = row < rows;
+      if (!ok[u]) continue;
+      if (dy16 != nullptr) {
+        unpack8(*reinterpret_cast<const uint4*>(dy16 + row * kD + lane * 8), dy[u]);
+      } else {
+        long long irow = row;
+        if (tr_b > 0) { const long long bi = row / tr_n, ni = row % tr_n; irow = ni * tr_b + bi; }
+        const float4* dp = reinterpret_cast<const float4*>(dy32 + irow * kD + lane * 8);
+        const float4 a = dp[0], b = dp[1];
+        dy[u][0] = a.x; dy[u][1] = a.y; dy[u][2] = a.z; dy[u][3] = a.w; dy[u][4] = b.x; dy[u][5] = b.y; dy[u][6] = b.z; dy[u][7] = b.w;
       }
-      const uint4 u = pack8(o);
-      *reinterpret_cast<uint4*>(g16 + row * kD + lane * 8) = u;
-      float r[8];
-      unpack8(u, r);                                  // sum what the consumer GEMM will see (the bf16-rounded values)
+      const float4* xp = reinterpret_cast<const float4*>(x + row * kD + lane * 8);
+      const float4 a = xp[0], b = xp[1];
+      xv[u][0] = a.x; xv[u][1] = a.y; xv[u][2] = a.z; xv[u][3] = a.w; xv[u][4] = b.x; xv[u][5] = b.y; xv[u][6] = b.z; xv[u][7] = b.w;
+      if (g_in != nullptr) {
+        const float4* ip = reinterpret_cast<const float4*>(g_in + row * kD + lane * 8);
+        const float4 c = ip[0], d = ip[1];
+        gi[u][0] = c.x; gi[u][1] = c.y; gi[u][2] = c.z; gi[u][3] = c.w; gi[u][4] = d.x; gi[u][5] = d.y; gi[u][6] = d.z; gi[u][7] = d.w;
+      } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) dbias[i] += r[i];
+        for (int i = 0; i < 8; ++i) gi[u][i] = 0.f;
+      }
+      mu[u] = mean[row]; rs[u] = rstd[row];
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (!ok[u]) continue;                            // warp-uniform
+      const long long row = base + u * warps_total;
+      float xh[8], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        xh[i] = (xv[u][i] - mu[u]) * rs[u];
+        const float dg = dy[u][i] * gg[i];
+        s1 += dg; s2 += dg * xh[i];
+        dgam[i] += dy[u][i] * xh[i];
+        dbet[i] += dy[u][i];
+      }
+      s1 = warp_sum(s1) * (1.0f / kD);
+      s2 = warp_sum(s2) * (1.0f / kD);
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = rs[u] * (dy[u][i] * gg[i] - s1 - xh[i] * s2) + gi[u][i];
+      float4* op = reinterpret_cast<float4*>(g_out + row * kD + lane * 8);
+      op[0] = make_float4(o[0], o[1], o[2], o[3]);
+      op[1] = make_float4(o[4], o[5], o[6], o[7]);
+      if (g16 != nullptr) {
+        if (drop.seed != nullptr) {
+          const uint32_t idx = (uint32_t)(row * kD + lane * 8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = sam2b200::dropout_keep(drop_key, idx + i, drop.thresh) ? o[i] * drop.inv_keep : 0.f;
+        }
+        const uint4 uu = pack8(o);
+        *reinterpret_cast<uint4*>(g16 + row * kD + lane * 8) = uu;
+        float r[8];
+        unpack8(uu, r);                                 // sum what the consumer GEMM will see (the bf16-rounded values)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dbias[i] += r[i];
+      }
     }
   }
   __shared__ float sh[8][3][kD];
@@ -343,10 +365,21 @@ permute_rows_kernel(const float* __restrict__ a, const float* __restrict__ a2, f
   if (out2 != nullptr) store(out2, w);
 }
 
-int grid_for_rows(long long rows, int rows_per_block) {
+int grid_for_rows(long long rows, int rows_per_block, int blocks_per_sm = 2) {
   long long g = (rows + rows_per_block - 1) / rows_per_block;
-  const long long cap = 148 * 2;
+  const long long cap = 148 * blocks_per_sm;
   return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+// resident blocks per SM of ln_bwd_kernel (bytes in flight): measured on B200, see profiles/r1_ln_bwd_occupancy.txt
+int ln_bwd_blocks_per_sm() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("SAM2B200_LN_BWD_BLOCKS_PER_SM");
+    v = e ? atoi(e) : 2;
+    if (v < 1 || v > 8) v = 2;
+  }
+  return v;
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -372,7 +405,7 @@ int sam2b200_ln_fwd(const float* x, const void* res_bf16, float* x_out, const fl
 }
 
 size_t sam2b200_ln_bwd_workspace_bytes(long long rows) {
-  return (size_t)grid_for_rows(rows, 8 * 8) * 3 * kD * sizeof(float);
+  return (size_t)grid_for_rows(rows, 8 * 8, 8) * 3 * kD * sizeof(float);   // sized for the largest grid
 }
 
 // g_out = g_in + dLN/dx; dgamma += ..., dbeta += ... (accumulated into the given fp32 buffers).
@@ -385,7 +418,7 @@ int sam2b200_ln_bwd(const void* dy_bf16, const float* dy_f32, const float* x, co
   if ((!dy_bf16) == (!dy_f32) || !x || !mean || !rstd || !gamma || !g_out || !dgamma || !dbeta || !workspace ||
       rows <= 0 || (!g_out_bf16) != (!dbias) || drop_p < 0.f || drop_p >= 1.f)
     return sam2b200::fail(SAM2B200_ERR_INVALID, "ln_bwd: bad arguments");
-  const int nblk = grid_for_rows(rows, 8 * 8);
+  const int nblk = grid_for_rows(rows, 8 * 8, ln_bwd_blocks_per_sm());
   const int nrow = g_out_bf16 ? 3 : 2;
   float* part = static_cast<float*>(workspace);
   ln_bwd_kernel<<<nblk, 256, 0, stream>>>((const __nv_bfloat16*)dy_bf16, dy_f32, x, mean, rstd, gamma, g_in, g_out,

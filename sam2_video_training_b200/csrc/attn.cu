@@ -343,7 +343,7 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
   // Persistent key-side kernels (attn_persist_kernels.cuh) for the short query loops the pair kernel does not cover.
   // SAM2B200_NO_PERSIST=1 switches back to one CTA per (key block, object).
   static const bool no_persist = getenv("SAM2B200_NO_PERSIST") != nullptr;
-  const bool use_persist = !no_persist;
+  const bool use_persist = !no_persist && N < 1024;   // long loops: 2.7 % slower than one-shot at N = 4096 (the staging slot costs a ring stage)
   if ((parts & 6) == 6 && use_pair) {
     attn::PairParams p{};
     p.Lk = M; p.Lq = N; p.scale_log2 = scale * kLog2e; p.scale = scale; p.lse2 = lse2; p.delta = delta;
@@ -351,9 +351,14 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
     p.gout_k = attn::GradOut{grad_dtype, dbias_k, table, table ? n_rope_k : 0, table ? rope_period : 1};
     p.drop = drop;
     const size_t smem = sizeof(attn::PairShared) + 1024;
-    if ((rc = set_smem(attn::kv_pair_kernel, smem))) return rc;
     dim3 grid(2 * ((M + attn::kBlockM - 1) / attn::kBlockM), B, 1);
-    attn::kv_pair_kernel<<<grid, attn::kThreads, smem, stream>>>(map_q64, map_do64, map_k128, map_v128, map_dv, map_dk, p);
+    if (drop.seed != nullptr) {
+      if ((rc = set_smem(attn::kv_pair_kernel<true>, smem))) return rc;
+      attn::kv_pair_kernel<true><<<grid, attn::kThreads, smem, stream>>>(map_q64, map_do64, map_k128, map_v128, map_dv, map_dk, p);
+    } else {
+      if ((rc = set_smem(attn::kv_pair_kernel<false>, smem))) return rc;
+      attn::kv_pair_kernel<false><<<grid, attn::kThreads, smem, stream>>>(map_q64, map_do64, map_k128, map_v128, map_dv, map_dk, p);
+    }
     if ((rc = sam2b200::check_launch("attn_bwd dV+dK pair"))) return rc;
     parts &= ~6;
   }

@@ -259,10 +259,15 @@ int sam2b200_attn_fwd_ex(const void* q, const void* k, const void* v, void* out,
     p.part_ml = p.part_acc + (size_t)nsplit * B * N * 256;
   }
   const size_t smem = sizeof(attn::SharedStorage) + 1024;
-  if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_FWD>, smem))) return rc;
   dim3 grid((N + attn::kBlockM - 1) / attn::kBlockM, B, nsplit);
   p.dbg = timeline_slice((size_t)grid.x * grid.y * grid.z);
-  attn::two_gemm_kernel<attn::MODE_FWD><<<grid, attn::kThreads, smem, stream>>>(map_k, map_v, map_q, map_o, map_o32, p);
+  if (p.drop.seed != nullptr) {
+    if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_FWD, true>, smem))) return rc;
+    attn::two_gemm_kernel<attn::MODE_FWD, true><<<grid, attn::kThreads, smem, stream>>>(map_k, map_v, map_q, map_o, map_o32, p);
+  } else {
+    if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_FWD, false>, smem))) return rc;
+    attn::two_gemm_kernel<attn::MODE_FWD, false><<<grid, attn::kThreads, smem, stream>>>(map_k, map_v, map_q, map_o, map_o32, p);
+  }
   if ((rc = sam2b200::check_launch("attn_fwd"))) return rc;
   if (nsplit > 1) {
     const long long rows = (long long)B * N;
@@ -308,6 +313,7 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
       (drop_p > 0.f && drop_seed && (long long)B * N * M >= (1LL << 32)))
     return sam2b200::fail(SAM2B200_ERR_INVALID, "attn_bwd: bad arguments");
   const sam2b200::Dropout drop = sam2b200::make_dropout(drop_seed, drop_site, drop_p);
+  const bool drop_on = drop.seed != nullptr;
   int rc;
   const long long rows = (long long)B * N;
   if (parts & 1) {
@@ -352,7 +358,7 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
     p.drop = drop;
     const size_t smem = sizeof(attn::PairShared) + 1024;
     dim3 grid(2 * ((M + attn::kBlockM - 1) / attn::kBlockM), B, 1);
-    if (drop.seed != nullptr) {
+    if (drop_on) {
       if ((rc = set_smem(attn::kv_pair_kernel<true>, smem))) return rc;
       attn::kv_pair_kernel<true><<<grid, attn::kThreads, smem, stream>>>(map_q64, map_do64, map_k128, map_v128, map_dv, map_dk, p);
     } else {
@@ -376,12 +382,22 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
     p.n_items = (int)(grid.x * grid.y);
     if (use_persist && grad_dtype && p.n_items > num_sms()) {
       // resident CTAs walking (key block, object) items: attn_persist_kernels.cuh
-      if ((rc = set_smem(attn::dv_persistent_kernel, smem))) return rc;
-      attn::dv_persistent_kernel<<<num_sms(), attn::kThreads, smem, stream>>>(map_q64, map_do64, map_k128, map_dv, p);
+      if (drop_on) {
+        if ((rc = set_smem(attn::dv_persistent_kernel<true>, smem))) return rc;
+        attn::dv_persistent_kernel<true><<<num_sms(), attn::kThreads, smem, stream>>>(map_q64, map_do64, map_k128, map_dv, p);
+      } else {
+        if ((rc = set_smem(attn::dv_persistent_kernel<false>, smem))) return rc;
+        attn::dv_persistent_kernel<false><<<num_sms(), attn::kThreads, smem, stream>>>(map_q64, map_do64, map_k128, map_dv, p);
+      }
     } else {
-      if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_DV>, smem))) return rc;
       p.dbg = timeline_slice((size_t)grid.x * grid.y);
-      attn::two_gemm_kernel<attn::MODE_DV><<<grid, attn::kThreads, smem, stream>>>(map_q64, map_do64, map_k128, map_dv, map_dv, p);
+      if (drop_on) {
+        if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_DV, true>, smem))) return rc;
+        attn::two_gemm_kernel<attn::MODE_DV, true><<<grid, attn::kThreads, smem, stream>>>(map_q64, map_do64, map_k128, map_dv, map_dv, p);
+      } else {
+        if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_DV, false>, smem))) return rc;
+        attn::two_gemm_kernel<attn::MODE_DV, false><<<grid, attn::kThreads, smem, stream>>>(map_q64, map_do64, map_k128, map_dv, map_dv, p);
+      }
     }
     if ((rc = sam2b200::check_launch("attn_bwd dV"))) return rc;
   }
@@ -398,12 +414,22 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
     p.n_items = (int)(grid.x * grid.y);
     static const bool no_persist_dk = getenv("SAM2B200_NO_PERSIST_DK") != nullptr;
     if (use_persist && !no_persist_dk && grad_dtype && p.n_items > num_sms()) {
-      if ((rc = set_smem(attn::dk_persistent_kernel, smem3))) return rc;
-      attn::dk_persistent_kernel<<<num_sms(), attn::kThreads, smem3, stream>>>(map_v128, map_q64, map_do64, map_k128, map_dk, p);
+      if (drop_on) {
+        if ((rc = set_smem(attn::dk_persistent_kernel<true>, smem3))) return rc;
+        attn::dk_persistent_kernel<true><<<num_sms(), attn::kThreads, smem3, stream>>>(map_v128, map_q64, map_do64, map_k128, map_dk, p);
+      } else {
+        if ((rc = set_smem(attn::dk_persistent_kernel<false>, smem3))) return rc;
+        attn::dk_persistent_kernel<false><<<num_sms(), attn::kThreads, smem3, stream>>>(map_v128, map_q64, map_do64, map_k128, map_dk, p);
+      }
     } else {
-      if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DK>, smem3))) return rc;
       p.dbg = timeline_slice((size_t)grid.x * grid.y);
-      attn::three_gemm_kernel<attn::MODE_DK><<<grid, attn::kThreads, smem3, stream>>>(map_v128, map_q64, map_do64, map_k128, map_dk, p);
+      if (drop_on) {
+        if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DK, true>, smem3))) return rc;
+        attn::three_gemm_kernel<attn::MODE_DK, true><<<grid, attn::kThreads, smem3, stream>>>(map_v128, map_q64, map_do64, map_k128, map_dk, p);
+      } else {
+        if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DK, false>, smem3))) return rc;
+        attn::three_gemm_kernel<attn::MODE_DK, false><<<grid, attn::kThreads, smem3, stream>>>(map_v128, map_q64, map_do64, map_k128, map_dk, p);
+      }
     }
     if ((rc = sam2b200::check_launch("attn_bwd dK"))) return rc;
   }
@@ -414,10 +440,15 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
     p.lse2 = lse2; p.delta = delta;
     p.gout = attn::GradOut{grad_dtype, dbias_q, table, table ? N : 0, table ? rope_period : 1};
     p.drop = drop;
-    if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DQ>, smem3))) return rc;
     dim3 grid((N + attn::kBlockM - 1) / attn::kBlockM, B, 1);
     p.dbg = timeline_slice((size_t)grid.x * grid.y);
-    attn::three_gemm_kernel<attn::MODE_DQ><<<grid, attn::kThreads, smem3, stream>>>(map_do128, map_k64, map_v64, map_q128, map_dq, p);
+    if (drop_on) {
+      if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DQ, true>, smem3))) return rc;
+      attn::three_gemm_kernel<attn::MODE_DQ, true><<<grid, attn::kThreads, smem3, stream>>>(map_do128, map_k64, map_v64, map_q128, map_dq, p);
+    } else {
+      if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DQ, false>, smem3))) return rc;
+      attn::three_gemm_kernel<attn::MODE_DQ, false><<<grid, attn::kThreads, smem3, stream>>>(map_do128, map_k64, map_v64, map_q128, map_dq, p);
+    }
     if ((rc = sam2b200::check_launch("attn_bwd dQ"))) return rc;
   }
   return SAM2B200_OK;

@@ -279,7 +279,9 @@ __device__ __forceinline__ void grad_epilogue(const GradOut& g, const CUtensorMa
   if (lane == 0) tma_store_wait_read();
 }
 
-template <int MODE>
+// DROP: attention-probability dropout compiled in or out (a run-time branch in the softmax loops costs registers and
+// scheduling freedom even when never taken -- measured on the pair kernel).
+template <int MODE, bool DROP>
 __global__ void __launch_bounds__(kThreads, 1)
 two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
                 const __grid_constant__ CUtensorMap map_a,    // fixed operand [B, La, 256] bf16, box 64 x 128
@@ -431,7 +433,7 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     float2 tcur[16];
 
     const float c = p.scale_log2;
-    const bool drop_on = p.drop.seed != nullptr;
+    constexpr bool drop_on = DROP;
     const uint32_t drop_key = drop_on ? sam2b200::dropout_key(*p.drop.seed, p.drop.site) : 0u;
     float m_ref = -INFINITY;   // running (lazily updated) row max of the raw scores -- identical in both halves
     float l = 0.f;             // this half's running sum of exp2((s - m_ref) c)
@@ -655,7 +657,7 @@ struct SharedStorage3 {
   uint32_t tmem_base;
 };
 
-template <int MODE>
+template <int MODE, bool DROP>
 __global__ void __launch_bounds__(kThreads, 1)
 three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_x,
                   const __grid_constant__ CUtensorMap map_y,
@@ -818,7 +820,7 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
     const uint32_t stage = smem_u32(&sh.a2[0]) + warp * (4 * kBoxBytes);   // epilogue staging in the (then idle) operand buffers
     const bool rotate = p.gout.rope_table != nullptr && (row0 + lane) < p.gout.rope_rows;
     const float c = p.scale_log2;
-    const bool drop_on = p.drop.seed != nullptr;
+    constexpr bool drop_on = DROP;
     const uint32_t drop_key = drop_on ? sam2b200::dropout_key(*p.drop.seed, p.drop.site) : 0u;
     float row_lse = 0.f, row_delta = 0.f;
     if (MODE == MODE_DQ && row_valid) {

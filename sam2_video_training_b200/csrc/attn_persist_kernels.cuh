@@ -25,6 +25,7 @@ __device__ __forceinline__ int ring_stage(int r) { return r % kStages; }
 __device__ __forceinline__ uint32_t ring_parity(int r) { return (uint32_t)(r / kStages) & 1u; }
 
 // grid: min(n_items, #SMs) CTAs; item = blockIdx.x + it * gridDim.x -> (key block = item % n_atiles, object = item / n_atiles)
+template <bool DROP>
 __global__ void __launch_bounds__(kThreads, 1)
 dv_persistent_kernel(const __grid_constant__ CUtensorMap map_x,    // Q  [B, N, 256] bf16, box 64 x 64
                      const __grid_constant__ CUtensorMap map_y,    // dO [B, N, 256] bf16, box 64 x 64
@@ -184,7 +185,7 @@ dv_persistent_kernel(const __grid_constant__ CUtensorMap map_x,    // Q  [B, N, 
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = tmem + (uint32_t(quarter * 32) << 16);
     const float c = p.scale_log2;
-    const bool drop_on = p.drop.seed != nullptr;
+    constexpr bool drop_on = DROP;
     const uint32_t drop_key = drop_on ? sam2b200::dropout_key(*p.drop.seed, p.drop.site) : 0u;
     float2 tcur[16];
     int tc0 = 0;
@@ -260,6 +261,7 @@ __device__ __forceinline__ uint32_t ring3_parity(int r) { return (uint32_t)(r / 
 // A2 = V block (its own 64 KB buffer, for dP^T = V dO^T), X = Q tiles, Y = dO tiles.  Ring slots per item:
 // [ A1 | tile 0 .. tile nt-1 | epilogue staging ] over the two ring stages; A2 of the NEXT item is fetched as soon as the
 // last dP MMA of the current item has completed (a2_empty), i.e. under the last softmax pass and the epilogue.
+template <bool DROP>
 __global__ void __launch_bounds__(kThreads, 1)
 dk_persistent_kernel(const __grid_constant__ CUtensorMap map_a2,   // V  [B, M, 256] bf16, box 64 x 128
                      const __grid_constant__ CUtensorMap map_x,    // Q  box 64 x 64
@@ -452,7 +454,7 @@ dk_persistent_kernel(const __grid_constant__ CUtensorMap map_a2,   // V  [B, M, 
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = tmem + (uint32_t(quarter * 32) << 16);
     const float c = p.scale_log2;
-    const bool drop_on = p.drop.seed != nullptr;
+    constexpr bool drop_on = DROP;
     const uint32_t drop_key = drop_on ? sam2b200::dropout_key(*p.drop.seed, p.drop.site) : 0u;
     int tc0 = 0;
     for (int it = 0; it < n_my; ++it) {

@@ -111,3 +111,35 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle" not in src.replace("# oracle", ""), os.path.join(dp, f)
+
+
+def test_argument_validation_needs_no_device(lib):
+    """Entry points reject bad arguments before touching the device: error code + message, no exception, no launch."""
+    assert lib.sam2b200_merged_loss_workspace_bytes(2, 3, 4, 16) > 0
+    assert lib.sam2b200_merged_loss_workspace_bytes(0, 3, 4, 16) == 0
+    rc = lib.sam2b200_merged_loss_fwd(None, None, None, None, None, None, None, None, None, None, None, None,
+                                      2, 3, 4, 16, 0.25, 2.0, 1.0, 1, None)
+    assert rc == -1 and b"merged_loss_fwd" in lib.sam2b200_last_error()
+    rc = lib.sam2b200_merged_loss_bwd(None, None, None, None, None, None, None, None, None, None, None, None, None,
+                                      2, 3, 4, 16, 0.25, 2.0, 1.0, 1, None)
+    assert rc == -1 and b"merged_loss_bwd" in lib.sam2b200_last_error()
+    rc = lib.sam2b200_mask_loss_fwd(None, None, None, None, None, None, None, None, 1, 1, 16, 0, 0.25, 2.0, 1.0, 0, 1, None)
+    assert rc == -1 and b"mask_loss_fwd" in lib.sam2b200_last_error()
+
+
+def test_merged_loss_host_checks_without_device():
+    """Host-side contract of CategoryMergedMultiStepLoss that needs no GPU: constructor checks, CPU tensors fail loudly."""
+    from sam2_video_training_b200 import _lib as L
+    from sam2_video_training_b200.merged_loss import CategoryMergedMultiStepLoss
+    w = {"loss_mask": 20, "loss_dice": 1, "loss_iou": 1}
+    with pytest.raises(NotImplementedError):
+        CategoryMergedMultiStepLoss(dict(w), pred_obj_scores=True)
+    with pytest.raises(ValueError):
+        CategoryMergedMultiStepLoss(dict(w), logit_temperature=-1.0)
+    with pytest.raises(AssertionError):
+        CategoryMergedMultiStepLoss({"loss_mask": 1})
+    crit = CategoryMergedMultiStepLoss(dict(w))
+    assert crit.weight_dict["loss_class"] == 0.0
+    stages = [{"multistep_pred_multimasks": [torch.zeros(2, 1, 4, 4)], "multistep_pred_ious": [torch.zeros(2, 1)]}]
+    with pytest.raises(L.Sam2B200Error):
+        crit(stages, [0, 1], 2, torch.ones(1, 2, 16, 16, dtype=torch.bool))

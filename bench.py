@@ -499,10 +499,10 @@ def main():
             nxt = start_copy()
             for i in range(k):
                 dd, evs = nxt
-                if i + 1 < k:
-                    nxt = start_copy()
                 tot = run_step(model, crit, opt, dd, lambda t: assemble_bank(dd, wl, t), wl, world, fwd=run_model,
                                arrivals=evs)
+                if i + 1 < k:       # enqueue the next step's copies AFTER this step's kernels: the compute stream never
+                    nxt = start_copy()   # waits for the host to issue ~130 cudaMemcpyAsync calls
                 float(tot.item())   # D2H of the step's loss (also keeps `dd` alive until the step is done)
 
         e2e_loop(2)

@@ -92,6 +92,20 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
                          int parts, float drop_p, const unsigned long long* drop_seed, unsigned drop_site,
                          sam2b200_stream_t stream);
 
+/* Cross-attention on the RAW 64-d memory features (kv_in_dim = 64: memory_attention.py:66-81 with the cross-attention of
+ * configs/sam2/sam2.1_hiera_t.yaml:41-50).  softmax rows sum to 1, hence softmax(q k^T) (memv Wv^T + bv) = out64 Wv^T + bv
+ * with out64 = softmax(q k^T) memv: v_proj (transformer.py:279) is applied by the caller to the [B N, 64] result instead of
+ * to the [B M, 64] memory -- a quarter of the PV / dP FLOPs, no [B, M, 256] value tensor, no dV kernel.
+ * fwd: q [B,N,256], k [B,M,256] (rotated), memv [B,M,64] bf16 -> out64 [B,N,64] bf16 (+ optional fp32 copy), lse2 [B,N].
+ * bwd: dout64 = dO Wv [B,N,64] bf16; delta = rowsum(dout64 o out64) [B,N] fp32 (caller); parts 4 = dK, 8 = dQ; the
+ * remaining arguments as sam2b200_attn_bwd_ex.  No attention-probability dropout on this path. */
+int sam2b200_attn_fwd_v64(const void* q, const void* k, const void* memv, void* out64, float* out64_f32, float* lse2,
+                          int B, int N, int M, float scale, sam2b200_stream_t stream);
+int sam2b200_attn_bwd_v64(const void* q, const void* k, const void* memv, const void* dout64, const float* lse2,
+                          const float* delta, void* dq, void* dk, int grad_dtype, int ldq, int ldk, const float* rope_table,
+                          int rope_period, int n_rope_k, int B, int N, int M, float scale, float* dbias_q, float* dbias_k,
+                          int parts, sam2b200_stream_t stream);
+
 /* ---- fused LayerNorm / residual / bias-gradient kernels (d_model = 256) -------------------
  * Replace nn.LayerNorm + residual add + dropout(0) + dtype casts of MemoryAttentionLayer
  * (sam2_video/model/modeling/memory_attention.py:58-99, :162) and what autograd derives for them.

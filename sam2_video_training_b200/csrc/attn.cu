@@ -277,6 +277,33 @@ int sam2b200_attn_fwd_ex(const void* q, const void* k, const void* v, void* out,
   return SAM2B200_OK;
 }
 
+// Cross-attention forward on the RAW 64-d memory features (kv_in_dim = 64, sam2.1_hiera_t.yaml:41-50):
+// out64 = softmax(scale q k^T) memv, [B, N, 64] bf16 (+ fp32 copy).  Because softmax rows sum to 1, the reference's
+// softmax(.) (memv Wv^T + bv) equals out64 Wv^T + bv: the caller applies v_proj to the [B N, 64] result instead of to the
+// [B M, 64] memory -- 4x fewer PV FLOPs, no [B, M, 256] value tensor.  No attention-probability dropout on this path.
+// q: [B, N, 256], k: [B, M, 256] (rotated), memv: [B, M, 64] bf16.
+int sam2b200_attn_fwd_v64(const void* q, const void* k, const void* memv, void* out64, float* out64_f32, float* lse2,
+                          int B, int N, int M, float scale, cudaStream_t stream) {
+  if (!q || !k || !memv || !out64 || !lse2 || B <= 0 || N <= 0 || M <= 0 || B > 65535 || !aligned16(q) || !aligned16(k) ||
+      !aligned16(memv) || !aligned16(out64) || (out64_f32 && !aligned16(out64_f32)))
+    return sam2b200::fail(SAM2B200_ERR_INVALID, "attn_fwd_v64: bad arguments");
+  CUtensorMap map_k, map_v, map_q;
+  int rc;
+  if ((rc = sam2b200::make_rows256_map(&map_k, k, B, M, attn::kBlockN))) return rc;
+  if ((rc = sam2b200::make_rows256_map(&map_v, memv, B, M, attn::kBlockN, 64))) return rc;
+  if ((rc = sam2b200::make_rows256_map(&map_q, q, B, N, attn::kBlockM))) return rc;
+  attn::TwoGemmParams p{};
+  p.La = N; p.Lx = M; p.scale_log2 = scale * kLog2e;
+  p.lse2 = lse2; p.tiles_per_split = (M + attn::kBlockN - 1) / attn::kBlockN;
+  p.drop = sam2b200::make_dropout(nullptr, 0, 0.f);
+  p.out_small = out64; p.out_small_f32 = out64_f32;
+  const size_t smem = sizeof(attn::SharedStorage) + 1024;
+  dim3 grid((N + attn::kBlockM - 1) / attn::kBlockM, B, 1);
+  if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_FWD, false, 64>, smem))) return rc;
+  attn::two_gemm_kernel<attn::MODE_FWD, false, 64><<<grid, attn::kThreads, smem, stream>>>(map_k, map_v, map_q, map_q, map_q, p);
+  return sam2b200::check_launch("attn_fwd_v64");
+}
+
 int sam2b200_attn_fwd(const void* q, const void* k, const void* v, void* out, float* out_f32, float* lse2,
                       void* workspace, size_t workspace_bytes, int B, int N, int M, float scale, int nsplit,
                       cudaStream_t stream) {
@@ -450,6 +477,56 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
       attn::three_gemm_kernel<attn::MODE_DQ, false><<<grid, attn::kThreads, smem3, stream>>>(map_do128, map_k64, map_v64, map_q128, map_dq, p);
     }
     if ((rc = sam2b200::check_launch("attn_bwd dQ"))) return rc;
+  }
+  return SAM2B200_OK;
+}
+
+// Backward of the 64-d-memory cross-attention (sam2b200_attn_fwd_v64).  dout64 = dO Wv ([B, N, 64] bf16, the gradient
+// w.r.t. out64), delta = rowsum(dout64 o out64) ([B, N] fp32, computed by the caller): dP = dout64 memv^T differs from
+// dO V^T by a per-row constant, which dP - Delta cancels.  parts: 4 = dK, 8 = dQ (there is no dV: the gradient of the
+// value projection is dO^T out64, a [256, 64] GEMM on the caller's side).  Other arguments as sam2b200_attn_bwd_ex.
+int sam2b200_attn_bwd_v64(const void* q, const void* k, const void* memv, const void* dout64, const float* lse2,
+                          const float* delta, void* dq, void* dk, int grad_dtype, int ldq, int ldk, const float* rope_table,
+                          int rope_period, int n_rope_k, int B, int N, int M, float scale, float* dbias_q, float* dbias_k,
+                          int parts, cudaStream_t stream) {
+  if (!q || !k || !memv || !dout64 || !lse2 || !delta || ((parts & 8) && !dq) || ((parts & 4) && !dk) || (parts & ~12) ||
+      B <= 0 || N <= 0 || M <= 0 || B > 65535 || !aligned16(q) || !aligned16(k) || !aligned16(memv) || !aligned16(dout64) ||
+      (rope_table && rope_period <= 0) || ldq < 256 || ldk < 256)
+    return sam2b200::fail(SAM2B200_ERR_INVALID, "attn_bwd_v64: bad arguments");
+  int rc;
+  CUtensorMap map_q64, map_k64, map_q128, map_k128, map_m64, map_m128, map_d64, map_d128, map_dq, map_dk;
+  if ((rc = sam2b200::make_rows256_map(&map_q128, q, B, N, attn::kBlockM))) return rc;
+  if ((rc = sam2b200::make_rows256_map(&map_k128, k, B, M, attn::kBlockM))) return rc;
+  if ((rc = sam2b200::make_rows256_map(&map_q64, q, B, N, attn::kBlockN))) return rc;
+  if ((rc = sam2b200::make_rows256_map(&map_k64, k, B, M, attn::kBlockN))) return rc;
+  if ((rc = sam2b200::make_rows256_map(&map_m64, memv, B, M, attn::kBlockN, 64))) return rc;
+  if ((rc = sam2b200::make_rows256_map(&map_m128, memv, B, M, attn::kBlockM, 64))) return rc;
+  if ((rc = sam2b200::make_rows256_map(&map_d64, dout64, B, N, attn::kBlockN, 64))) return rc;
+  if ((rc = sam2b200::make_rows256_map(&map_d128, dout64, B, N, attn::kBlockM, 64))) return rc;
+  if ((parts & 8) && (rc = sam2b200::make_out_map(&map_dq, dq, grad_dtype, B, N, ldq, 32))) return rc;
+  if ((parts & 4) && (rc = sam2b200::make_out_map(&map_dk, dk, grad_dtype, B, M, ldk, 32))) return rc;
+  const float2* table = reinterpret_cast<const float2*>(rope_table);
+  const size_t smem3 = sizeof(attn::SharedStorage3) + 1024;
+  const sam2b200::Dropout nodrop = sam2b200::make_dropout(nullptr, 0, 0.f);
+  if (parts & 4) {   // dK: A1 = K block (TMEM), A2 = memory block, X = Q tiles, Y = dout64 tiles
+    attn::ThreeGemmParams p{};
+    p.La = M; p.Lx = N; p.scale_log2 = scale * kLog2e; p.scale = scale; p.lse2 = lse2; p.delta = delta;
+    p.gout = attn::GradOut{grad_dtype, dbias_k, table, table ? n_rope_k : 0, table ? rope_period : 1};
+    p.drop = nodrop;
+    dim3 grid((M + attn::kBlockM - 1) / attn::kBlockM, B, 1);
+    if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DK, false, 64>, smem3))) return rc;
+    attn::three_gemm_kernel<attn::MODE_DK, false, 64><<<grid, attn::kThreads, smem3, stream>>>(map_m128, map_q64, map_d64, map_k128, map_dk, p);
+    if ((rc = sam2b200::check_launch("attn_bwd_v64 dK"))) return rc;
+  }
+  if (parts & 8) {   // dQ: A1 = Q block (TMEM), A2 = dout64 block, X = K tiles, Y = memory tiles
+    attn::ThreeGemmParams p{};
+    p.La = N; p.Lx = M; p.scale_log2 = scale * kLog2e; p.scale = scale; p.lse2 = lse2; p.delta = delta;
+    p.gout = attn::GradOut{grad_dtype, dbias_q, table, table ? N : 0, table ? rope_period : 1};
+    p.drop = nodrop;
+    dim3 grid((N + attn::kBlockM - 1) / attn::kBlockM, B, 1);
+    if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DQ, false, 64>, smem3))) return rc;
+    attn::three_gemm_kernel<attn::MODE_DQ, false, 64><<<grid, attn::kThreads, smem3, stream>>>(map_d128, map_k64, map_m64, map_q128, map_dq, p);
+    if ((rc = sam2b200::check_launch("attn_bwd_v64 dQ"))) return rc;
   }
   return SAM2B200_OK;
 }

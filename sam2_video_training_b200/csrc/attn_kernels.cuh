@@ -105,6 +105,8 @@ struct TwoGemmParams {
   int tiles_per_split;
   unsigned long long* dbg;     // optional timeline buffer
   int n_items, n_atiles;       // persistent kernels: items = (a block, batch) pairs, a blocks per batch
+  void* out_small;             // DY = 64 forward: out' [B, La, 64] bf16
+  float* out_small_f32;        //                  and its fp32 copy (optional)
 };
 
 struct SharedStorage {
@@ -281,13 +283,17 @@ __device__ __forceinline__ void grad_epilogue(const GradOut& g, const CUtensorMa
 
 // DROP: attention-probability dropout compiled in or out (a run-time branch in the softmax loops costs registers and
 // scheduling freedom even when never taken -- measured on the pair kernel).
-template <int MODE, bool DROP>
+// DY: width of the streamed Y operand and of the accumulator.  256 = the projected values; 64 (forward only) = the raw
+// 64-d memory features of the cross-attention: out' = softmax(.) mem, the value projection is applied to the [N, 64] result
+// afterwards (softmax rows sum to 1, so out = out' Wv^T + bv exactly) -- 4x fewer PV FLOPs and no [B, M, 256] V tensor.
+template <int MODE, bool DROP, int DY = kD>
 __global__ void __launch_bounds__(kThreads, 1)
 two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
                 const __grid_constant__ CUtensorMap map_a,    // fixed operand [B, La, 256] bf16, box 64 x 128
                 const __grid_constant__ CUtensorMap map_o,    // FWD: out bf16 (box 64 x 32); DV: dV (bf16 64 x 32 | fp32 32 x 32)
                 const __grid_constant__ CUtensorMap map_o32,  // FWD: fp32 copy of out (box 32 x 32)
                 const TwoGemmParams p) {
+  static_assert(DY == kD || (DY == 64 && MODE == MODE_FWD), "narrow Y: forward only");
   extern __shared__ uint8_t smem_raw[];
   SharedStorage& sh = *reinterpret_cast<SharedStorage*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -355,9 +361,9 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       __syncwarp();
       mbar_wait(&sh.y_empty[s], ph ^ 1);
       if (leader) {
-        mbar_arrive_expect_tx(&sh.y_full[s], kTileBytes);
+        mbar_arrive_expect_tx(&sh.y_full[s], kBlockN * DY * 2);
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < DY / 64; ++c)
           tma_load_3d(&sh.y_tiles[s][c * kChunkBytes], &map_y, &sh.y_full[s], c * 64, row0, b);
       }
       __syncwarp();
@@ -370,7 +376,7 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     // profiles/r1_mma_probe.txt); like this a 128x64x16 MMA issues every ~37 cycles.
     const bool leader = elect_one();
     constexpr uint32_t idesc_s = make_idesc_bf16(kBlockM, kBlockN, 0, 0);   // A(TMEM) . X^T, X K-major
-    constexpr uint32_t idesc_acc = make_idesc_bf16(kBlockM, kD, 0, 1);      // P(TMEM) . Y,  Y MN-major
+    constexpr uint32_t idesc_acc = make_idesc_bf16(kBlockM, DY, 0, 1);      // P(TMEM) . Y,  Y MN-major
     const uint32_t x_lo0 = desc_lo_sw128(smem_u32(&sh.x_tiles[0][0]), 16);           // K-major: LBO unused
     const uint32_t y_lo0 = desc_lo_sw128(smem_u32(&sh.y_tiles[0][0]), kChunkBytes);  // MN-major: LBO = slab stride
     auto issue_scores = [&](int t) {
@@ -493,7 +499,7 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           acc_synced = true;
           tc_fence_after();
 #pragma unroll 1
-          for (int cc = half * 4; cc < half * 4 + 4; ++cc) {   // each half rescales its 128 ACC columns
+          for (int cc = half * (DY / 64); cc < (half + 1) * (DY / 64); ++cc) {   // each half rescales its half of the ACC columns
             uint32_t o[32];
             SAM2B200_TMEM_LD32(lane_addr + kColAcc + cc * 32, o);
             tmem_wait_ld();
@@ -555,7 +561,30 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       sh.lsum[half][row] = l;
       pair_barrier(quarter);
       l += sh.lsum[half ^ 1][row];
-      if (nsplit == 1) {
+      if (DY == 64) {
+        // narrow accumulator: this warp holds 32 rows x 32 of the 64 output columns -> plain 16-byte global stores
+        const float inv_l = p.drop.inv_keep / l;
+        uint32_t o[32];
+        SAM2B200_TMEM_LD32(lane_addr + kColAcc + half * 32, o);
+        tmem_wait_ld();
+        if (row_valid) {
+          float v[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(o[k]) * inv_l;
+          const long long off = ((long long)b * p.La + a_row_idx) * 64 + half * 32;
+          uint4* o16 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out_small) + off);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            o16[k] = make_uint4(pack_bf16(v[8 * k], v[8 * k + 1]), pack_bf16(v[8 * k + 2], v[8 * k + 3]),
+                                pack_bf16(v[8 * k + 4], v[8 * k + 5]), pack_bf16(v[8 * k + 6], v[8 * k + 7]));
+          if (p.out_small_f32 != nullptr) {
+            float4* o32 = reinterpret_cast<float4*>(p.out_small_f32 + off);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o32[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          }
+          if (half == 0) p.lse2[(long long)b * p.La + a_row_idx] = fmaf(m_ref, c, log2f(l));
+        }
+      } else if (nsplit == 1) {
         // out (bf16, two 64-column boxes) and optionally its fp32 copy (four 32-column boxes) leave through this
         // warp's staging area: [bf16 box 0 | bf16 box 1 | fp32 box 0..3]
         const float inv_l = p.drop.inv_keep / l;    // inverted dropout: kept probabilities are scaled by 1 / (1 - p)
@@ -657,7 +686,9 @@ struct SharedStorage3 {
   uint32_t tmem_base;
 };
 
-template <int MODE, bool DROP>
+// DY: width of the A2 / Y operands of the dP GEMM: 256 = projected values (A2 = dO or V), 64 = the raw memory features
+// with A2 / Y = dO' = dO Wv or mem (dP = dO V^T = dO' mem^T up to a per-row constant that dP - Delta cancels).
+template <int MODE, bool DROP, int DY = kD>
 __global__ void __launch_bounds__(kThreads, 1)
 three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_x,
                   const __grid_constant__ CUtensorMap map_y,
@@ -711,9 +742,9 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
       for (int c = 0; c < 4; ++c)
         tma_load_3d((c < 2 ? &sh.x_tiles[kStages3 - 1][0] : &sh.y_tiles[kStages3 - 1][0]) + (c & 1) * kSlabBytes, &map_a1,
                     &sh.a1_full, c * 64, a_tile * kBlockM, b);
-      mbar_arrive_expect_tx(&sh.a2_full, kA2Bytes);
+      mbar_arrive_expect_tx(&sh.a2_full, kBlockM * DY * 2);
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < DY / 64; ++c)
         tma_load_3d(&sh.a2[c * kA2ChunkBytes], &map_a2, &sh.a2_full, c * 64, a_tile * kBlockM, b);
     }
     __syncwarp();
@@ -732,9 +763,9 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
       __syncwarp();
       mbar_wait(&sh.y_empty[s], ph ^ 1);
       if (leader) {
-        mbar_arrive_expect_tx(&sh.y_full[s], kTileBytes);
+        mbar_arrive_expect_tx(&sh.y_full[s], kBlockN * DY * 2);
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < DY / 64; ++c)
           tma_load_3d(&sh.y_tiles[s][c * kChunkBytes], &map_y, &sh.y_full[s], c * 64, row0, b);
       }
       __syncwarp();
@@ -768,7 +799,7 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
       if (leader) {
         const uint32_t ylo = y_lo0 + s * (kTileBytes >> 4);
 #pragma unroll
-        for (int ks = 0; ks < kD / 16; ++ks)
+        for (int ks = 0; ks < DY / 16; ++ks)
           umma_ss_lohi(tmem + k3ColDP, a2_lo + (ks >> 2) * (kA2ChunkBytes >> 4) + (ks & 3) * 2,
                        ylo + (ks >> 2) * (kChunkBytes >> 4) + (ks & 3) * 2, kDescHiSw128_1024, idesc_s, ks > 0);
         umma_commit(&sh.y_empty[s]);

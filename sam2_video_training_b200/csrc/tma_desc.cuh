@@ -33,11 +33,12 @@ inline PFN_encodeTiled get_encode_tiled() {
 // the canonical UMMA SW128 layout (K-major when the 256-dim is the contraction, MN-major when
 // the rows are).  A [rows x 256] tile is four such boxes, chunk-major in shared memory.
 // Rows beyond L are zero-filled by the TMA unit.
-inline int make_rows256_map(CUtensorMap* map, const void* base, int B, int L, int box_rows) {
+// `width` = 256 (projected q / k / v / dO) or 64 (raw memory features, dO Wv): row pitch = width * 2 bytes.
+inline int make_rows256_map(CUtensorMap* map, const void* base, int B, int L, int box_rows, int width = 256) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return fail(SAM2B200_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not found");
-  cuuint64_t dims[3] = {256, (cuuint64_t)L, (cuuint64_t)B};
-  cuuint64_t strides[2] = {512, (cuuint64_t)L * 512};  // bytes, dims 1..2
+  cuuint64_t dims[3] = {(cuuint64_t)width, (cuuint64_t)L, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)width * 2, (cuuint64_t)L * (cuuint64_t)width * 2};  // bytes, dims 1..2
   cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides,

@@ -128,6 +128,55 @@ def attn_bwd(q, k, v, out, out32, dout, lse2, scale: float, table=None, n_rope_k
     return dq, dk, dv
 
 
+def attn_fwd_v64(q, k, memv, scale: float, keep_f32: bool = True):
+    """Cross-attention on the raw 64-d memory features (sam2b200_attn_fwd_v64): q [B,N,256], k [B,M,256] (rotated),
+    memv [B,M,64] bf16 -> (out64 bf16 [B,N,64], its fp32 copy or None, lse2 [B,N]); the caller applies v_proj to out64."""
+    lib = _lib.load()
+    b, n, d = q.shape
+    m = k.shape[1]
+    assert d == 256 and k.shape == (b, m, 256) and memv.shape == (b, m, 64)
+    for t in (q, k, memv):
+        assert t.dtype == torch.bfloat16 and t.is_contiguous() and t.is_cuda
+    out = torch.empty((b, n, 64), dtype=torch.bfloat16, device=q.device)
+    out32 = torch.empty((b, n, 64), dtype=torch.float32, device=q.device) if keep_f32 else None
+    lse2 = torch.empty((b, n), dtype=torch.float32, device=q.device)
+    with _Timed("attn_fwd", 4.0 * b * n * m * 256):      # algorithmic FLOPs of the op it replaces
+        rc = lib.sam2b200_attn_fwd_v64(q.data_ptr(), k.data_ptr(), memv.data_ptr(), out.data_ptr(),
+                                       out32.data_ptr() if out32 is not None else None, lse2.data_ptr(), b, n, m, scale,
+                                       _stream(q.device))
+    _lib.check(rc, "sam2b200_attn_fwd_v64")
+    return out, out32, lse2
+
+
+def attn_bwd_v64(q, k, memv, dout64, lse2, delta, scale: float, table=None, n_rope_k: int = 0, grad_dtype=torch.float32,
+                 dq=None, dk=None, dbias=(None, None), parts: int = 12):
+    """Backward of attn_fwd_v64: dout64 = dO Wv [B,N,64] bf16, delta = rowsum(dout64 o out64) [B,N] fp32.
+    parts: 4 = dK, 8 = dQ (no dV on this path).  Returns (dq, dk)."""
+    lib = _lib.load()
+    b, n, _ = q.shape
+    m = k.shape[1]
+    dev = q.device
+    assert dout64.shape == (b, n, 64) and dout64.dtype == torch.bfloat16 and dout64.is_contiguous()
+    assert delta.shape == (b, n) and delta.dtype == torch.float32 and delta.is_contiguous()
+    if dq is None and parts & 8:
+        dq = torch.empty((b, n, 256), dtype=grad_dtype, device=dev)
+    if dk is None and parts & 4:
+        dk = torch.empty((b, m, 256), dtype=grad_dtype, device=dev)
+    for t_ in (dq, dk):
+        assert t_ is None or (t_.dtype == grad_dtype and t_.stride(-1) == 1)
+    work = 10.0 * b * n * m * 256 * ((4 if parts & 8 else 0) + (6 if parts & 4 else 0)) / 10.0   # dK here stands for the whole key side
+    with _Timed("attn_bwd", work):
+        rc = lib.sam2b200_attn_bwd_v64(q.data_ptr(), k.data_ptr(), memv.data_ptr(), dout64.data_ptr(), lse2.data_ptr(),
+                                       delta.data_ptr(), dq.data_ptr() if dq is not None else None,
+                                       dk.data_ptr() if dk is not None else None, _DT[grad_dtype],
+                                       dq.stride(-2) if dq is not None else 256, dk.stride(-2) if dk is not None else 256,
+                                       table.data_ptr() if table is not None else None,
+                                       table.shape[0] if table is not None else 0, n_rope_k, b, n, m, scale,
+                                       *[t_.data_ptr() if t_ is not None else None for t_ in dbias], int(parts), _stream(dev))
+    _lib.check(rc, "sam2b200_attn_bwd_v64")
+    return dq, dk
+
+
 class RopeAttentionFn(torch.autograd.Function):
     """out = softmax(rope(q) rope(k[:, :M-P])^T / sqrt(256)) v for one 256-wide head.
 

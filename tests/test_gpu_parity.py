@@ -701,6 +701,55 @@ def test_attention_backward_persistent_key_side_kernels(dev, b, grid, nf, extra,
         assert rel_l2(res[torch.bfloat16][2].float(), vf.grad) < 8e-3
 
 
+@pytest.mark.parametrize("b,grid,nf,nptr", [(3, 12, 2, 8), (2, 24, 7, 28), (1, 32, 2, 20)])
+def test_cross_attention_on_raw_memory_features(dev, b, grid, nf, nptr):
+    """sam2b200_attn_fwd_v64 / _bwd_v64: softmax(q k^T) (mem Wv^T + bv) == (softmax(q k^T) mem) Wv^T + bv (rows sum to 1),
+    so the value projection moves from the [B M, 64] memory to the [B N, 64] result.  Output, dq, dk and the value
+    projection's gradients against an fp32 torch restatement of the ORIGINAL formulation and against the 256-d kernels."""
+    from sam2_video_training_b200 import ops
+    from sam2_video_training_b200.modeling.position_encoding import compute_axial_cis
+    g = torch.Generator(device="cuda").manual_seed(41)
+    n = grid * grid
+    m = nf * n + nptr
+    table = compute_axial_cis(dim=256, end_x=grid, end_y=grid).to(dev)
+    q = torch.randn(b, n, 256, device=dev, generator=g).to(torch.bfloat16)
+    k = torch.randn(b, m, 256, device=dev, generator=g).to(torch.bfloat16)
+    mem = torch.randn(b, m, 64, device=dev, generator=g).to(torch.bfloat16)
+    wv = (torch.randn(256, 64, device=dev, generator=g) / 8).to(torch.bfloat16)
+    bv = torch.randn(256, device=dev, generator=g) * 0.1
+    do = torch.randn(b, n, 256, device=dev, generator=g).to(torch.bfloat16)
+    # reference: the reference's formulation in fp32
+    qf, kf, mf, wf, bf = (t.float().requires_grad_(True) for t in (q, k, mem, wv, bv))
+    ref = torch.softmax(qf @ kf.transpose(1, 2) / 16.0, dim=-1) @ (mf @ wf.t() + bf)
+    ref.backward(do.float())
+    # new path
+    o64, o64_32, lse = ops.attn_fwd_v64(q, k, mem, 1 / 16.0)
+    out = o64_32 @ wv.float().t() + bv
+    assert rel_l2(out, ref) < 5e-3
+    do64 = (do.float() @ wv.float()).to(torch.bfloat16)
+    delta = (do64.float() * o64_32).sum(-1)
+    dq, dk = ops.attn_bwd_v64(q, k, mem, do64, lse, delta, 1 / 16.0, grad_dtype=torch.float32)
+    assert rel_l2(dq, qf.grad) < 1e-2, rel_l2(dq, qf.grad)
+    assert rel_l2(dk, kf.grad) < 1e-2, rel_l2(dk, kf.grad)
+    d_wv = do.float().flatten(0, 1).t() @ o64_32.flatten(0, 1)         # [256, 64]
+    assert rel_l2(d_wv, wf.grad) < 5e-3
+    assert rel_l2(do.float().sum((0, 1)), bf.grad) < 1e-5
+    # the 256-d kernels on the projected values give the same thing
+    v = (mem.float() @ wv.float().t() + bv).to(torch.bfloat16)
+    o, o32, lse_old = ops.attn_fwd(q, k, v, 1 / 16.0)
+    assert rel_l2(out, o32) < 5e-3 and float((lse - lse_old).abs().max()) < 1e-3
+    # fused conjugate rotation + bias gradients in the epilogues, bf16 gradients, each part on its own
+    db = [torch.zeros(256, device=dev) for _ in range(2)]
+    dq2, _ = ops.attn_bwd_v64(q, k, mem, do64, lse, delta, 1 / 16.0, table=table, n_rope_k=nf * n, grad_dtype=torch.bfloat16,
+                              dbias=(db[0], None), parts=8)
+    _, dk2 = ops.attn_bwd_v64(q, k, mem, do64, lse, delta, 1 / 16.0, table=table, n_rope_k=nf * n, grad_dtype=torch.bfloat16,
+                              dbias=(None, db[1]), parts=4)
+    want_q = ops.rope_apply(dq, table, n, inverse=True, out_dtype=torch.float32)
+    want_k = ops.rope_apply(dk, table, nf * n, inverse=True, out_dtype=torch.float32)
+    assert rel_l2(dq2.float(), want_q) < 6e-3 and rel_l2(dk2.float(), want_k) < 6e-3
+    assert rel_l2(db[0], want_q.sum((0, 1))) < 5e-3 and rel_l2(db[1], want_k.sum((0, 1))) < 5e-3
+
+
 def test_attention_backward_fused_bias_gradients(dev):
     """sam2b200_attn_bwd_ex: the q / k / v bias gradients (column sums of dq / dk / dv over all rows, after the
     conjugate rotation) are accumulated inside the gradient epilogues -- ragged sizes, bf16 and fp32 outputs."""

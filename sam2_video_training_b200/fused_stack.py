@@ -21,7 +21,7 @@ from typing import List
 import torch
 
 from . import _lib
-from .ops import _Timed, attn_bwd, attn_fwd, rope_apply
+from .ops import _Timed, attn_bwd, attn_bwd_v64, attn_fwd, attn_fwd_v64, rope_apply
 
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -189,6 +189,7 @@ def direct_grads_possible(bucket, params) -> bool:
 # cuBLAS addmm + the RoPE pass inside the graph-replayed step (56.9 vs 56.6 ms) and loses for the K = 64 memory-bank
 # projections (profiles/r1_proj_rope_bench.txt).  SAM2B200_PROJ_KERNEL=1 routes the K = 256 projections through it,
 # SAM2B200_PROJ_KERNEL_K64=1 the K = 64 ones as well.
+NO_V64 = bool(os.environ.get("SAM2B200_NO_V64"))    # A/B switch: cross-attention on the projected 256-d values (with the dV kernel)
 NO_PROJ_KERNEL = not bool(os.environ.get("SAM2B200_PROJ_KERNEL"))
 PROJ_KERNEL_K64 = bool(os.environ.get("SAM2B200_PROJ_KERNEL_K64"))
 NO_MLP_KERNEL = bool(os.environ.get("SAM2B200_NO_MLP_KERNEL"))     # A/B switch: cuBLAS GEMM + separate ReLU-backward pass
@@ -349,6 +350,13 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             return (dr[p_key], dr["seed"], l * 8 + k) if dr is not None and dr[p_key] > 0.0 else None
 
         mirror = weight_mirror(masters)
+        # Cross-attention on the raw 64-d memory features (sam2b200_attn_fwd_v64): softmax rows sum to 1, so
+        # softmax(.) (mem Wv^T + bv) = (softmax(.) mem) Wv^T + bv -- v_proj moves from the [B M, 64] bank to the [B N, 64]
+        # result, the [B, M, 256] value tensor and the dV kernel disappear.  Needs: no attention-probability dropout
+        # (rows of the dropped matrix do not sum to 1), no gradient w.r.t. `memory` (the bank is detached in training,
+        # sam2model.py:345-358), enough (query block, object) CTAs to fill the GPU without split-KV.
+        v64 = (not NO_V64 and (dr is None or dr["p_ca"] <= 0.0) and not ctx.needs_input_grad[3]
+               and b * ((n + 127) // 128) >= 64)
 
         def project_memory():        # cross-attention keys / values of every layer: functions of the bank only
             for l in range(nl):
@@ -357,11 +365,11 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                     # K = 64: cuBLAS + the RoPE pass measured faster than the fused kernel (1777 CTAs of 64 KB output each
                     # are dominated by per-CTA set-up: 129 vs 80 us, profiles/r1_proj_rope_bench.txt)
                     k2 = torch.addmm(W["ca.k.b"], memk, W["ca.k.w"].t())
-                    v2 = torch.addmm(W["ca.v.b"], memv, W["ca.v.w"].t())
+                    v2 = None if v64 else torch.addmm(W["ca.v.b"], memv, W["ca.v.w"].t())
                     k2_rot = rope_apply(k2.view(b, m, d), table, n_rope_k)
                 else:
                     k2_rot = proj_rope(memk, W["ca.k.w"], W["ca.k.b"], 1, table, 1, m, n_rope_k)[0].view(b, m, d)
-                    v2 = proj_rope(memv, W["ca.v.w"], W["ca.v.b"], 1)[0]
+                    v2 = None if v64 else proj_rope(memv, W["ca.v.w"], W["ca.v.b"], 1)[0]
                 kv_ready.append((k2_rot, v2, side.event()))
 
         side.run(project_memory, memk, memv)
@@ -390,7 +398,12 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                 q2_rot = proj_rope(y2, W["ca.q.w"], W["ca.q.b"], 1, table, 1, n, n)[0].view(b, n, d)
             k2_rot, v2, ev = kv_ready[l]
             side.wait(ev)
-            o2, o2_32, lse2 = attn_fwd(q2_rot, k2_rot, v2.view(b, m, d), scale, meta["nsplit"], drop=dsite("p_ca", l, 1))
+            if v64:
+                # v2 / o2_32 slots of `saved` then hold out64 (bf16) and its fp32 copy
+                v2, o2_32, lse2 = attn_fwd_v64(q2_rot, k2_rot, memv.view(b, m, 64), scale)
+                o2 = torch.addmm(W["ca.v.b"], v2.view(r, 64), W["ca.v.w"].t()).view(b, n, d)      # v_proj on the result
+            else:
+                o2, o2_32, lse2 = attn_fwd(q2_rot, k2_rot, v2.view(b, m, d), scale, meta["nsplit"], drop=dsite("p_ca", l, 1))
             ca = torch.addmm(W["ca.o.b"], o2.view(r, d), W["ca.o.w"].t())
             # ---- MLP (memory_attention.py:95-98)
             y3, x2, mean3, rstd3 = ln_fwd(x1, ca, P["n3.w"], P["n3.b"], drop=dsite("p_res", l, 3))
@@ -409,7 +422,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
         ctx.n_saved = len(saved)
         ctx.meta = dict(nl=nl, n=n, b=b, m=m, scale=scale, n_rope_k=n_rope_k, pos_at_input=pos_at_input,
                         has_pos=curr_pos is not None, bucket=meta.get("bucket"), masters=masters,
-                        direct=bool(meta.get("direct")), dropout=dr)
+                        direct=bool(meta.get("direct")), dropout=dr, v64=v64)
         return out
 
     @staticmethod
@@ -499,26 +512,48 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             # conjugate RoPE and the q / k / v bias gradients (column sums) are fused into the gradient epilogues.
             # Only dQ is on the path of the residual-stream gradient: the key-side kernels (dV, dK) and everything
             # they feed (weight gradients, memory-bank gradients) go to the side stream.
-            delta = torch.empty((b, n), dtype=F32, device=dev)
-            args = (q2_rot, k2_rot, v2.view(b, m, d), None, o2_32, do2.view(b, n, d), lse2, scale)
-            kw = dict(table=table, n_rope_k=n_rope_k, grad_dtype=BF16, delta=delta, drop=dsite("p_ca", l, 1))
-            attn_bwd(*args, parts=1, **kw)                                              # Delta = rowsum(dO o O)
+            if mt["v64"]:
+                # saved v2 / o2_32 are out64 / its fp32 copy.  v_proj acted on out64: its gradients are two small GEMMs,
+                # dout64 = dO Wv feeds the attention backward, Delta = rowsum(dout64 o out64); there is no dV.
+                o64, o64_32 = v2, o2_32
+                acc_w(ix["ca.v.w"], do2.t(), o64.view(r, 64), gv[ix["ca.v.b"]])
+                do64 = torch.mm(do2, W["ca.v.w"]).view(b, n, 64)
+                delta = (do64.float() * o64_32).sum(-1)
+                kw = dict(table=table, n_rope_k=n_rope_k, grad_dtype=BF16)
+                args = (q2_rot, k2_rot, memv.view(b, m, 64), do64, lse2, delta, scale)
 
-            def key_side(args=args, kw=kw, l=l, ix=ix, W=W):
-                _, dk2, dv2 = attn_bwd(*args, parts=2 | 4, dbias=(None, gv[ix["ca.k.b"]], gv[ix["ca.v.b"]]), **kw)
-                dk2, dv2 = dk2.view(rm, d), dv2.view(rm, d)
-                if direct:
-                    torch.addmm(gv[ix["ca.k.w"]], dk2.t(), memk, out_dtype=F32, out=gv[ix["ca.k.w"]])
-                    torch.addmm(gv[ix["ca.v.w"]], dv2.t(), memv, out_dtype=F32, out=gv[ix["ca.v.w"]])
-                else:
-                    grads[ix["ca.k.w"]] = _mm32(dk2.t(), memk)
-                    grads[ix["ca.v.w"]] = _mm32(dv2.t(), memv)
-                if need_memgrad:
-                    torch.addmm(dmemk, dk2, W["ca.k.w"], out_dtype=F32, out=dmemk)
-                if need_mem:
-                    torch.addmm(dmemv, dv2, W["ca.v.w"], out_dtype=F32, out=dmemv)
-            side.run(key_side, *args[:3], o2_32, do2, lse2, delta)
-            dq2, _, _ = attn_bwd(*args, parts=8, dbias=(gv[ix["ca.q.b"]], None, None), **kw)
+                def key_side(args=args, kw=kw, l=l, ix=ix, W=W):
+                    _, dk2 = attn_bwd_v64(*args, parts=4, dbias=(None, gv[ix["ca.k.b"]]), **kw)
+                    dk2 = dk2.view(rm, d)
+                    if direct:
+                        torch.addmm(gv[ix["ca.k.w"]], dk2.t(), memk, out_dtype=F32, out=gv[ix["ca.k.w"]])
+                    else:
+                        grads[ix["ca.k.w"]] = _mm32(dk2.t(), memk)
+                    if need_memgrad:
+                        torch.addmm(dmemk, dk2, W["ca.k.w"], out_dtype=F32, out=dmemk)
+                side.run(key_side, q2_rot, k2_rot, memv, do64, lse2, delta)
+                dq2, _ = attn_bwd_v64(*args, parts=8, dbias=(gv[ix["ca.q.b"]], None), **kw)
+            else:
+                delta = torch.empty((b, n), dtype=F32, device=dev)
+                args = (q2_rot, k2_rot, v2.view(b, m, d), None, o2_32, do2.view(b, n, d), lse2, scale)
+                kw = dict(table=table, n_rope_k=n_rope_k, grad_dtype=BF16, delta=delta, drop=dsite("p_ca", l, 1))
+                attn_bwd(*args, parts=1, **kw)                                              # Delta = rowsum(dO o O)
+
+                def key_side(args=args, kw=kw, l=l, ix=ix, W=W):
+                    _, dk2, dv2 = attn_bwd(*args, parts=2 | 4, dbias=(None, gv[ix["ca.k.b"]], gv[ix["ca.v.b"]]), **kw)
+                    dk2, dv2 = dk2.view(rm, d), dv2.view(rm, d)
+                    if direct:
+                        torch.addmm(gv[ix["ca.k.w"]], dk2.t(), memk, out_dtype=F32, out=gv[ix["ca.k.w"]])
+                        torch.addmm(gv[ix["ca.v.w"]], dv2.t(), memv, out_dtype=F32, out=gv[ix["ca.v.w"]])
+                    else:
+                        grads[ix["ca.k.w"]] = _mm32(dk2.t(), memk)
+                        grads[ix["ca.v.w"]] = _mm32(dv2.t(), memv)
+                    if need_memgrad:
+                        torch.addmm(dmemk, dk2, W["ca.k.w"], out_dtype=F32, out=dmemk)
+                    if need_mem:
+                        torch.addmm(dmemv, dv2, W["ca.v.w"], out_dtype=F32, out=dmemv)
+                side.run(key_side, *args[:3], o2_32, do2, lse2, delta)
+                dq2, _, _ = attn_bwd(*args, parts=8, dbias=(gv[ix["ca.q.b"]], None, None), **kw)
             dq2 = dq2.view(r, d)
             dy2 = torch.mm(dq2, W["ca.q.w"])
             acc_w(ix["ca.q.w"], dq2.t(), y2)

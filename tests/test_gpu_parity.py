@@ -185,6 +185,47 @@ def test_memory_attention_random_vs_oracle(dev, grid, b, nf, nptr, fused):
     assert worst[0] > 0.998, worst
 
 
+def test_fused_stack_raw_memory_cross_attention_vs_oracle(dev, monkeypatch):
+    """Training-shaped call (memory detached, memory_pos trainable, no dropout, enough objects to fill the GPU): the fused
+    stack runs its cross-attention on the raw 64-d memory features (attn_fwd_v64 / attn_bwd_v64, v_proj applied to the
+    [B N, 64] result, no dV kernel).  Output and every gradient against the fp32 oracle of the reference formulation."""
+    from sam2_video_training_b200 import fused_stack
+    from sam2_video_training_b200.modeling.memory_attention import build_memory_attention
+    calls = {"fwd": 0, "bwd": 0}
+    f0, b0 = fused_stack.attn_fwd_v64, fused_stack.attn_bwd_v64
+    monkeypatch.setattr(fused_stack, "attn_fwd_v64", lambda *a, **k: (calls.__setitem__("fwd", calls["fwd"] + 1), f0(*a, **k))[1])
+    monkeypatch.setattr(fused_stack, "attn_bwd_v64", lambda *a, **k: (calls.__setitem__("bwd", calls["bwd"] + 1), b0(*a, **k))[1])
+    params = ao.init_params(seed=0)
+    grid, b, nf, nptr = 8, 64, 3, 12
+    n, m = grid * grid, nf * grid * grid + nptr
+    g = torch.Generator().manual_seed(19)
+    inputs = dict(curr=torch.randn(n, b, 256, generator=g), curr_pos=torch.randn(n, b, 256, generator=g) * 0.7,
+                  memory=torch.randn(m, b, 64, generator=g), memory_pos=torch.randn(m, b, 64, generator=g) * 0.7)
+    gout = torch.randn(n, b, 256, generator=g)
+    po = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    lo_ = {k: v.clone().requires_grad_(k != "memory") for k, v in inputs.items()}
+    ref = ao.memory_attention(po, lo_["curr"], lo_["memory"], lo_["curr_pos"], lo_["memory_pos"], nptr)
+    ref.backward(gout)
+    model = build_memory_attention().to(dev).eval()
+    _load_params(model, params)
+    ld = {k: v.to(dev).clone().requires_grad_(k != "memory") for k, v in inputs.items()}
+    out = model(ld["curr"], ld["memory"], ld["curr_pos"], ld["memory_pos"], nptr)
+    out.backward(gout.to(dev))
+    torch.cuda.synchronize()
+    assert calls == {"fwd": 4, "bwd": 8}, calls            # 4 layers: forward once, backward dK + dQ
+    assert rel_l2(out, ref) < ATTN_REL_TOL
+    for k in ("curr", "curr_pos", "memory_pos"):
+        assert cosine(ld[k].grad, lo_[k].grad) > GRAD_COS_TOL, k
+    names = [nm for nm, _ in model.named_parameters()]
+    mine = torch.cat([p.grad.flatten().cpu() for _, p in model.named_parameters()])
+    theirs = torch.cat([po[nm].grad.flatten() for nm in names])
+    assert cosine(mine, theirs) > GRAD_COS_TOL
+    for nm in ("layers.0.cross_attn_image.v_proj.weight", "layers.3.cross_attn_image.v_proj.bias",
+               "layers.2.cross_attn_image.k_proj.weight", "layers.1.cross_attn_image.q_proj.bias"):
+        p = dict(model.named_parameters())[nm]
+        assert cosine(p.grad, po[nm].grad) > GRAD_COS_TOL, nm
+
+
 def test_fused_and_composed_paths_agree(dev):
     from sam2_video_training_b200.modeling.memory_attention import build_memory_attention
     model = build_memory_attention().to(dev).eval()

@@ -470,11 +470,13 @@ def main():
     roofline = {"bound": "tensor", "kernel": "sam2b200_" + dom + " (tcgen05 kernels, all launches of the timed region)",
                 "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
                 "peak_source": pk["src"] + " sustained cuBLAS bf16",
-                # dram__bytes_read.sum + dram__bytes_write.sum of the three backward kernels (dV + dK + dQ) of ONE launch at the
-                # largest shape of this workload (B=56, N=576, M=4060), ncu --set full: profiles/r1_ncu_attn_v3_cfg2_cross.csv
-                "traffic": 871.97e6 if wl_name.startswith("cfg2") else None,
-                "traffic_note": "per backward call at B=56 N=576 M=4060 (dV 229.5 + dK 357.2 + dQ 285.3 MB); algorithmic operand bytes "
-                                "q,k,v,dO,O32,dq,dk,dv = 0.39 GB -- K and V are re-read by the three kernels",
+                # dram__bytes_read.sum + dram__bytes_write.sum of the backward kernels of ONE cross-attention call at the largest
+                # shape of this workload (B=56, N=576, M=4060), ncu --set full.  Raw-memory path (default, no dropout):
+                # dK 249.3 + dQ 181.7 MB, profiles/r1_ncu_attn_v64_cfg2_cross.csv; 256-d value path (dropout on):
+                # dV 229.5 + dK 357.2 + dQ 285.3 MB, profiles/r1_ncu_attn_v3_cfg2_cross.csv
+                "traffic": (None if not wl_name.startswith("cfg2") else 871.97e6 if args.dropout > 0 else 431.0e6),
+                "traffic_note": "per cross-attention backward call at B=56 N=576 M=4060; algorithmic operand bytes q,k,mem,dO',dq,dk "
+                                "= 0.30 GB on the raw-memory path (K is read once by each of the two kernels)",
                 "attention_fwd_bwd_tflops": attn_fl / (attn_ms * 1e-3) / 1e12 if attn_ms else None,
                 "attention_share_of_step": attn_ms / (eager_ms_per_step * args.steps) if eager_ms_per_step else None,
                 "mask_loss": {"bound": "hbm", "achieved": loss_by / (loss_ms * 1e-3) / 1e9 if loss_ms else None, "peak": pk["hbm"],

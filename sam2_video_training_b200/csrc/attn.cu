@@ -514,8 +514,16 @@ int sam2b200_attn_bwd_v64(const void* q, const void* k, const void* memv, const 
     p.gout = attn::GradOut{grad_dtype, dbias_k, table, table ? n_rope_k : 0, table ? rope_period : 1};
     p.drop = nodrop;
     dim3 grid((M + attn::kBlockM - 1) / attn::kBlockM, B, 1);
-    if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DK, false, 64>, smem3))) return rc;
-    attn::three_gemm_kernel<attn::MODE_DK, false, 64><<<grid, attn::kThreads, smem3, stream>>>(map_m128, map_q64, map_d64, map_k128, map_dk, p);
+    p.n_atiles = (int)grid.x;
+    p.n_items = (int)(grid.x * grid.y);
+    static const bool no_persist = getenv("SAM2B200_NO_PERSIST") != nullptr;
+    if (!no_persist && N < 1024 && grad_dtype && p.n_items > num_sms()) {   // short query loops: resident CTAs (attn_persist_kernels.cuh)
+      if ((rc = set_smem(attn::dk_persistent_kernel<false, 64>, smem3))) return rc;
+      attn::dk_persistent_kernel<false, 64><<<num_sms(), attn::kThreads, smem3, stream>>>(map_m128, map_q64, map_d64, map_k128, map_dk, p);
+    } else {
+      if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DK, false, 64>, smem3))) return rc;
+      attn::three_gemm_kernel<attn::MODE_DK, false, 64><<<grid, attn::kThreads, smem3, stream>>>(map_m128, map_q64, map_d64, map_k128, map_dk, p);
+    }
     if ((rc = sam2b200::check_launch("attn_bwd_v64 dK"))) return rc;
   }
   if (parts & 8) {   // dQ: A1 = Q block (TMEM), A2 = dout64 block, X = K tiles, Y = memory tiles

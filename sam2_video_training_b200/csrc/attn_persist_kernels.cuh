@@ -261,7 +261,7 @@ __device__ __forceinline__ uint32_t ring3_parity(int r) { return (uint32_t)(r / 
 // A2 = V block (its own 64 KB buffer, for dP^T = V dO^T), X = Q tiles, Y = dO tiles.  Ring slots per item:
 // [ A1 | tile 0 .. tile nt-1 | epilogue staging ] over the two ring stages; A2 of the NEXT item is fetched as soon as the
 // last dP MMA of the current item has completed (a2_empty), i.e. under the last softmax pass and the epilogue.
-template <bool DROP>
+template <bool DROP, int DY = kD>     // DY = 64: raw-memory cross-attention (A2 = memory block, Y = dO Wv tiles)
 __global__ void __launch_bounds__(kThreads, 1)
 dk_persistent_kernel(const __grid_constant__ CUtensorMap map_a2,   // V  [B, M, 256] bf16, box 64 x 128
                      const __grid_constant__ CUtensorMap map_x,    // Q  box 64 x 64
@@ -326,9 +326,9 @@ dk_persistent_kernel(const __grid_constant__ CUtensorMap map_a2,   // V  [B, M, 
       }
       mbar_wait(&sh.a2_empty, (uint32_t)(it & 1) ^ 1u);   // the previous item's dP MMAs are done with A2
       if (leader) {
-        mbar_arrive_expect_tx(&sh.a2_full, kA2Bytes);
+        mbar_arrive_expect_tx(&sh.a2_full, kBlockM * DY * 2);
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < DY / 64; ++c)
           tma_load_3d(&sh.a2[c * kA2ChunkBytes], &map_a2, &sh.a2_full, c * 64, a_tile * kBlockM, b);
       }
       __syncwarp();
@@ -347,9 +347,9 @@ dk_persistent_kernel(const __grid_constant__ CUtensorMap map_a2,   // V  [B, M, 
         __syncwarp();
         mbar_wait(&sh.y_empty[s], ph ^ 1);
         if (leader) {
-          mbar_arrive_expect_tx(&sh.y_full[s], kTileBytes);
+          mbar_arrive_expect_tx(&sh.y_full[s], kBlockN * DY * 2);
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < DY / 64; ++c)
             tma_load_3d(&sh.y_tiles[s][c * kChunkBytes], &map_y, &sh.y_full[s], c * 64, row0, b);
         }
         __syncwarp();
@@ -398,7 +398,7 @@ dk_persistent_kernel(const __grid_constant__ CUtensorMap map_a2,   // V  [B, M, 
         if (leader) {
           const uint32_t ylo = y_lo0 + s * (kTileBytes >> 4);
 #pragma unroll
-          for (int ks = 0; ks < kD / 16; ++ks)
+          for (int ks = 0; ks < DY / 16; ++ks)
             umma_ss_lohi(tmem + k3ColDP, a2_lo + (ks >> 2) * (kA2ChunkBytes >> 4) + (ks & 3) * 2,
                          ylo + (ks >> 2) * (kChunkBytes >> 4) + (ks & 3) * 2, kDescHiSw128_1024, idesc_s, ks > 0);
           umma_commit(&sh.y_empty[s]);

@@ -196,7 +196,7 @@ def test_fused_stack_raw_memory_cross_attention_vs_oracle(dev, monkeypatch):
     monkeypatch.setattr(fused_stack, "attn_fwd_v64", lambda *a, **k: (calls.__setitem__("fwd", calls["fwd"] + 1), f0(*a, **k))[1])
     monkeypatch.setattr(fused_stack, "attn_bwd_v64", lambda *a, **k: (calls.__setitem__("bwd", calls["bwd"] + 1), b0(*a, **k))[1])
     params = ao.init_params(seed=0)
-    grid, b, nf, nptr = 8, 64, 3, 12
+    grid, b, nf, nptr = 8, 64, 5, 12        # 3 key blocks x 64 objects > #SMs: the persistent dK kernel
     n, m = grid * grid, nf * grid * grid + nptr
     g = torch.Generator().manual_seed(19)
     inputs = dict(curr=torch.randn(n, b, 256, generator=g), curr_pos=torch.randn(n, b, 256, generator=g) * 0.7,
@@ -742,7 +742,7 @@ def test_attention_backward_persistent_key_side_kernels(dev, b, grid, nf, extra,
         assert rel_l2(res[torch.bfloat16][2].float(), vf.grad) < 8e-3
 
 
-@pytest.mark.parametrize("b,grid,nf,nptr", [(3, 12, 2, 8), (2, 24, 7, 28), (1, 32, 2, 20)])
+@pytest.mark.parametrize("b,grid,nf,nptr", [(3, 12, 2, 8), (2, 24, 7, 28), (1, 32, 2, 20), (40, 8, 7, 12)])   # last: persistent dK
 def test_cross_attention_on_raw_memory_features(dev, b, grid, nf, nptr):
     """sam2b200_attn_fwd_v64 / _bwd_v64: softmax(q k^T) (mem Wv^T + bv) == (softmax(q k^T) mem) Wv^T + bv (rows sum to 1),
     so the value projection moves from the [B M, 64] memory to the [B N, 64] result.  Output, dq, dk and the value

@@ -189,6 +189,7 @@ def direct_grads_possible(bucket, params) -> bool:
 # cuBLAS addmm + the RoPE pass inside the graph-replayed step (56.9 vs 56.6 ms) and loses for the K = 64 memory-bank
 # projections (profiles/r1_proj_rope_bench.txt).  SAM2B200_PROJ_KERNEL=1 routes the K = 256 projections through it,
 # SAM2B200_PROJ_KERNEL_K64=1 the K = 64 ones as well.
+NO_FOLD = bool(os.environ.get("SAM2B200_NO_FOLD"))  # A/B switch: v_proj and out_proj of the raw-memory cross-attention as two GEMMs
 NO_V64 = bool(os.environ.get("SAM2B200_NO_V64"))    # A/B switch: cross-attention on the projected 256-d values (with the dV kernel)
 NO_PROJ_KERNEL = not bool(os.environ.get("SAM2B200_PROJ_KERNEL"))
 PROJ_KERNEL_K64 = bool(os.environ.get("SAM2B200_PROJ_KERNEL_K64"))
@@ -401,10 +402,17 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             if v64:
                 # v2 / o2_32 slots of `saved` then hold out64 (bf16) and its fp32 copy
                 v2, o2_32, lse2 = attn_fwd_v64(q2_rot, k2_rot, memv.view(b, m, 64), scale)
-                o2 = torch.addmm(W["ca.v.b"], v2.view(r, 64), W["ca.v.w"].t()).view(b, n, d)      # v_proj on the result
+                if NO_FOLD:
+                    o2 = torch.addmm(W["ca.v.b"], v2.view(r, 64), W["ca.v.w"].t()).view(b, n, d)      # v_proj on the result
+                    ca = torch.addmm(W["ca.o.b"], o2.view(r, d), W["ca.o.w"].t())
+                else:
+                    # out_proj(v_proj(out64)) = out64 (Wo Wv)^T + (Wo bv + bo): one [B N, 64] -> 256 GEMM; the o2 slot of
+                    # `saved` holds the folded weight (fp32 product of the master weights, rounded once)
+                    o2 = torch.mm(P["ca.o.w"], P["ca.v.w"]).to(BF16)
+                    ca = torch.addmm(torch.addmv(P["ca.o.b"], P["ca.o.w"], P["ca.v.b"]).to(BF16), v2.view(r, 64), o2.t())
             else:
                 o2, o2_32, lse2 = attn_fwd(q2_rot, k2_rot, v2.view(b, m, d), scale, meta["nsplit"], drop=dsite("p_ca", l, 1))
-            ca = torch.addmm(W["ca.o.b"], o2.view(r, d), W["ca.o.w"].t())
+                ca = torch.addmm(W["ca.o.b"], o2.view(r, d), W["ca.o.w"].t())
             # ---- MLP (memory_attention.py:95-98)
             y3, x2, mean3, rstd3 = ln_fwd(x1, ca, P["n3.w"], P["n3.b"], drop=dsite("p_res", l, 3))
             h = torch._addmm_activation(W["l1.b"], y3, W["l1.w"].t(), use_gelu=False)  # bias + ReLU epilogue
@@ -422,7 +430,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
         ctx.n_saved = len(saved)
         ctx.meta = dict(nl=nl, n=n, b=b, m=m, scale=scale, n_rope_k=n_rope_k, pos_at_input=pos_at_input,
                         has_pos=curr_pos is not None, bucket=meta.get("bucket"), masters=masters,
-                        direct=bool(meta.get("direct")), dropout=dr, v64=v64)
+                        direct=bool(meta.get("direct")), dropout=dr, v64=v64, fold=v64 and not NO_FOLD)
         return out
 
     @staticmethod
@@ -504,11 +512,14 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                 dh = mlp_dh(dm, W["l2.w"], h, relu_scale)
                 acc_w(ix["l1.w"], dh.t(), y3, gv[ix["l1.b"]])
             dy3 = torch.mm(dh, W["l1.w"])
-            g, dca = ln_bwd(dy3, x2, mean3, rstd3, P["n3.w"], g, gv[ix["n3.w"]], gv[ix["n3.b"]], dbias=gv[ix["ca.o.b"]],
+            fold = mt["fold"]
+            g_bo = torch.zeros(d, dtype=F32, device=dev) if fold else gv[ix["ca.o.b"]]    # colsum(dca), needed on its own when folded
+            g, dca = ln_bwd(dy3, x2, mean3, rstd3, P["n3.w"], g, gv[ix["n3.w"]], gv[ix["n3.b"]], dbias=g_bo,
                             drop=dsite("p_res", l, 3))
             # ---- cross attention backward
-            acc_w(ix["ca.o.w"], dca.t(), o2.view(r, d))
-            do2 = torch.mm(dca, W["ca.o.w"])
+            if not fold:
+                acc_w(ix["ca.o.w"], dca.t(), o2.view(r, d))
+                do2 = torch.mm(dca, W["ca.o.w"])
             # conjugate RoPE and the q / k / v bias gradients (column sums) are fused into the gradient epilogues.
             # Only dQ is on the path of the residual-stream gradient: the key-side kernels (dV, dK) and everything
             # they feed (weight gradients, memory-bank gradients) go to the side stream.
@@ -516,8 +527,26 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                 # saved v2 / o2_32 are out64 / its fp32 copy.  v_proj acted on out64: its gradients are two small GEMMs,
                 # dout64 = dO Wv feeds the attention backward, Delta = rowsum(dout64 o out64); there is no dV.
                 o64, o64_32 = v2, o2_32
-                acc_w(ix["ca.v.w"], do2.t(), o64.view(r, 64), gv[ix["ca.v.b"]])
-                do64 = torch.mm(do2, W["ca.v.w"]).view(b, n, 64)
+                if fold:
+                    # ca = out64 (Wo Wv)^T + (Wo bv + bo):  G = d/d(Wo Wv) = dca^T out64, g = d/d(Wo bv + bo) = colsum(dca);
+                    # dWo = G Wv^T + g bv^T, dWv = Wo^T G, dbv = Wo^T g, dbo = g -- four [256 x 64]-sized fp32 products
+                    do64 = torch.mm(dca, o2).view(b, n, 64)                 # o2 slot = folded weight [256, 64]
+
+                    def fold_grads(dca=dca, o64=o64, g_bo=g_bo, ix=ix, P=P):
+                        G = _mm32(dca.t(), o64.view(r, 64))
+                        d_wo = torch.addmm(torch.outer(g_bo, P["ca.v.b"]), G, P["ca.v.w"].t())
+                        d_wv = torch.mm(P["ca.o.w"].t(), G)
+                        gv[ix["ca.o.b"]].add_(g_bo)
+                        gv[ix["ca.v.b"]].addmv_(P["ca.o.w"].t(), g_bo)
+                        if direct:
+                            gv[ix["ca.o.w"]].add_(d_wo)
+                            gv[ix["ca.v.w"]].add_(d_wv)
+                        else:
+                            grads[ix["ca.o.w"]], grads[ix["ca.v.w"]] = d_wo, d_wv
+                    side.run(fold_grads, dca, o64, g_bo)
+                else:
+                    acc_w(ix["ca.v.w"], do2.t(), o64.view(r, 64), gv[ix["ca.v.b"]])
+                    do64 = torch.mm(do2, W["ca.v.w"]).view(b, n, 64)
                 delta = (do64.float() * o64_32).sum(-1)
                 kw = dict(table=table, n_rope_k=n_rope_k, grad_dtype=BF16)
                 args = (q2_rot, k2_rot, memv.view(b, m, 64), do64, lse2, delta, scale)

@@ -16,6 +16,7 @@
 #include "attn_kernels.cuh"
 #include "attn_pair_kernel.cuh"
 #include "attn_persist_kernels.cuh"
+#include "attn_v64_kernels.cuh"
 #include "tma_desc.cuh"
 
 namespace {
@@ -517,7 +518,13 @@ int sam2b200_attn_bwd_v64(const void* q, const void* k, const void* memv, const 
     p.n_atiles = (int)grid.x;
     p.n_items = (int)(grid.x * grid.y);
     static const bool no_persist = getenv("SAM2B200_NO_PERSIST") != nullptr;
-    if (!no_persist && N < 1024 && grad_dtype && p.n_items > num_sms()) {   // short query loops: resident CTAs (attn_persist_kernels.cuh)
+    static const bool single_buf = getenv("SAM2B200_V64_SINGLE_BUFFER") != nullptr;   // A/B: the generic single-buffered kernels
+    static const bool persist_dk = getenv("SAM2B200_V64_PERSIST_DK") != nullptr;
+    if (!single_buf && !persist_dk) {   // double-buffered S / dP, both fixed operands in shared memory (attn_v64_kernels.cuh)
+      const size_t smemv = sizeof(attn::SharedStorageV64) + 1024;
+      if ((rc = set_smem(attn::three_gemm_v64_kernel<attn::MODE_DK>, smemv))) return rc;
+      attn::three_gemm_v64_kernel<attn::MODE_DK><<<grid, attn::kThreads, smemv, stream>>>(map_m128, map_q64, map_d64, map_k128, map_dk, p);
+    } else if (!no_persist && N < 1024 && grad_dtype && p.n_items > num_sms()) {   // short query loops: resident CTAs (attn_persist_kernels.cuh)
       if ((rc = set_smem(attn::dk_persistent_kernel<false, 64>, smem3))) return rc;
       attn::dk_persistent_kernel<false, 64><<<num_sms(), attn::kThreads, smem3, stream>>>(map_m128, map_q64, map_d64, map_k128, map_dk, p);
     } else {
@@ -532,8 +539,15 @@ int sam2b200_attn_bwd_v64(const void* q, const void* k, const void* memv, const 
     p.gout = attn::GradOut{grad_dtype, dbias_q, table, table ? N : 0, table ? rope_period : 1};
     p.drop = nodrop;
     dim3 grid((N + attn::kBlockM - 1) / attn::kBlockM, B, 1);
-    if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DQ, false, 64>, smem3))) return rc;
-    attn::three_gemm_kernel<attn::MODE_DQ, false, 64><<<grid, attn::kThreads, smem3, stream>>>(map_d128, map_k64, map_m64, map_q128, map_dq, p);
+    static const bool single_buf = getenv("SAM2B200_V64_SINGLE_BUFFER") != nullptr;
+    if (!single_buf) {
+      const size_t smemv = sizeof(attn::SharedStorageV64) + 1024;
+      if ((rc = set_smem(attn::three_gemm_v64_kernel<attn::MODE_DQ>, smemv))) return rc;
+      attn::three_gemm_v64_kernel<attn::MODE_DQ><<<grid, attn::kThreads, smemv, stream>>>(map_d128, map_k64, map_m64, map_q128, map_dq, p);
+    } else {
+      if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DQ, false, 64>, smem3))) return rc;
+      attn::three_gemm_kernel<attn::MODE_DQ, false, 64><<<grid, attn::kThreads, smem3, stream>>>(map_d128, map_k64, map_m64, map_q128, map_dq, p);
+    }
     if ((rc = sam2b200::check_launch("attn_bwd_v64 dQ"))) return rc;
   }
   return SAM2B200_OK;

@@ -98,13 +98,18 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
  * to the [B M, 64] memory -- a quarter of the PV / dP FLOPs, no [B, M, 256] value tensor, no dV kernel.
  * fwd: q [B,N,256], k [B,M,256] (rotated), memv [B,M,64] bf16 -> out64 [B,N,64] bf16 (+ optional fp32 copy), lse2 [B,N].
  * bwd: dout64 = dO Wv [B,N,64] bf16; delta = rowsum(dout64 o out64) [B,N] fp32 (caller); parts 4 = dK, 8 = dQ; the
- * remaining arguments as sam2b200_attn_bwd_ex.  No attention-probability dropout on this path. */
+ * remaining arguments as sam2b200_attn_bwd_ex.
+ * Attention-probability dropout (drop_p > 0 with a device seed, transformer.py:304-306): the rows of the dropped matrix do
+ * not sum to 1, so the forward also returns rowsum_drop [B,N] (out = out64 Wv^T + rowsum_drop bv) and the backward takes
+ * dp_bias [B,N] = dO . bv (added to dP before the mask); delta = rowsum(dout64 o out64) + dp_bias * rowsum_drop. */
 int sam2b200_attn_fwd_v64(const void* q, const void* k, const void* memv, void* out64, float* out64_f32, float* lse2,
-                          int B, int N, int M, float scale, sam2b200_stream_t stream);
+                          float* rowsum_drop, int B, int N, int M, float scale, float drop_p,
+                          const unsigned long long* drop_seed, unsigned drop_site, sam2b200_stream_t stream);
 int sam2b200_attn_bwd_v64(const void* q, const void* k, const void* memv, const void* dout64, const float* lse2,
                           const float* delta, void* dq, void* dk, int grad_dtype, int ldq, int ldk, const float* rope_table,
                           int rope_period, int n_rope_k, int B, int N, int M, float scale, float* dbias_q, float* dbias_k,
-                          int parts, sam2b200_stream_t stream);
+                          int parts, const float* dp_bias, float drop_p, const unsigned long long* drop_seed,
+                          unsigned drop_site, sam2b200_stream_t stream);
 
 /* ---- fused LayerNorm / residual / bias-gradient kernels (d_model = 256) -------------------
  * Replace nn.LayerNorm + residual add + dropout(0) + dtype casts of MemoryAttentionLayer

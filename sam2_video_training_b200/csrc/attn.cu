@@ -281,12 +281,16 @@ int sam2b200_attn_fwd_ex(const void* q, const void* k, const void* v, void* out,
 // Cross-attention forward on the RAW 64-d memory features (kv_in_dim = 64, sam2.1_hiera_t.yaml:41-50):
 // out64 = softmax(scale q k^T) memv, [B, N, 64] bf16 (+ fp32 copy).  Because softmax rows sum to 1, the reference's
 // softmax(.) (memv Wv^T + bv) equals out64 Wv^T + bv: the caller applies v_proj to the [B N, 64] result instead of to the
-// [B M, 64] memory -- 4x fewer PV FLOPs, no [B, M, 256] value tensor.  No attention-probability dropout on this path.
+// [B M, 64] memory -- 4x fewer PV FLOPs, no [B, M, 256] value tensor.
+// With attention-probability dropout (drop_p > 0, device seed) the rows of the dropped matrix no longer sum to 1:
+// out = out64 Wv^T + rowsum_drop bv, rowsum_drop [B, N] = row sums of the kept, re-scaled probabilities (required then).
 // q: [B, N, 256], k: [B, M, 256] (rotated), memv: [B, M, 64] bf16.
 int sam2b200_attn_fwd_v64(const void* q, const void* k, const void* memv, void* out64, float* out64_f32, float* lse2,
-                          int B, int N, int M, float scale, cudaStream_t stream) {
+                          float* rowsum_drop, int B, int N, int M, float scale, float drop_p,
+                          const unsigned long long* drop_seed, unsigned drop_site, cudaStream_t stream) {
   if (!q || !k || !memv || !out64 || !lse2 || B <= 0 || N <= 0 || M <= 0 || B > 65535 || !aligned16(q) || !aligned16(k) ||
-      !aligned16(memv) || !aligned16(out64) || (out64_f32 && !aligned16(out64_f32)))
+      !aligned16(memv) || !aligned16(out64) || (out64_f32 && !aligned16(out64_f32)) || drop_p < 0.f || drop_p >= 1.f ||
+      (drop_p > 0.f && drop_seed && (!rowsum_drop || (long long)B * N * M >= (1LL << 32))))
     return sam2b200::fail(SAM2B200_ERR_INVALID, "attn_fwd_v64: bad arguments");
   CUtensorMap map_k, map_v, map_q;
   int rc;
@@ -296,12 +300,17 @@ int sam2b200_attn_fwd_v64(const void* q, const void* k, const void* memv, void* 
   attn::TwoGemmParams p{};
   p.La = N; p.Lx = M; p.scale_log2 = scale * kLog2e;
   p.lse2 = lse2; p.tiles_per_split = (M + attn::kBlockN - 1) / attn::kBlockN;
-  p.drop = sam2b200::make_dropout(nullptr, 0, 0.f);
-  p.out_small = out64; p.out_small_f32 = out64_f32;
+  p.drop = sam2b200::make_dropout(drop_seed, drop_site, drop_p);
+  p.out_small = out64; p.out_small_f32 = out64_f32; p.rowsum_drop = rowsum_drop;
   const size_t smem = sizeof(attn::SharedStorage) + 1024;
   dim3 grid((N + attn::kBlockM - 1) / attn::kBlockM, B, 1);
-  if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_FWD, false, 64>, smem))) return rc;
-  attn::two_gemm_kernel<attn::MODE_FWD, false, 64><<<grid, attn::kThreads, smem, stream>>>(map_k, map_v, map_q, map_q, map_q, p);
+  if (p.drop.seed != nullptr) {
+    if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_FWD, true, 64>, smem))) return rc;
+    attn::two_gemm_kernel<attn::MODE_FWD, true, 64><<<grid, attn::kThreads, smem, stream>>>(map_k, map_v, map_q, map_q, map_q, p);
+  } else {
+    if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_FWD, false, 64>, smem))) return rc;
+    attn::two_gemm_kernel<attn::MODE_FWD, false, 64><<<grid, attn::kThreads, smem, stream>>>(map_k, map_v, map_q, map_q, map_q, p);
+  }
   return sam2b200::check_launch("attn_fwd_v64");
 }
 
@@ -486,13 +495,17 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
 // w.r.t. out64), delta = rowsum(dout64 o out64) ([B, N] fp32, computed by the caller): dP = dout64 memv^T differs from
 // dO V^T by a per-row constant, which dP - Delta cancels.  parts: 4 = dK, 8 = dQ (there is no dV: the gradient of the
 // value projection is dO^T out64, a [256, 64] GEMM on the caller's side).  Other arguments as sam2b200_attn_bwd_ex.
+// With dropout (same drop_p / seed / site as the forward): dp_bias [B, N] = dO . bv per query (added to dP before the
+// mask) and delta = rowsum(dout64 o out64) + dp_bias * rowsum_drop.
 int sam2b200_attn_bwd_v64(const void* q, const void* k, const void* memv, const void* dout64, const float* lse2,
                           const float* delta, void* dq, void* dk, int grad_dtype, int ldq, int ldk, const float* rope_table,
                           int rope_period, int n_rope_k, int B, int N, int M, float scale, float* dbias_q, float* dbias_k,
-                          int parts, cudaStream_t stream) {
+                          int parts, const float* dp_bias, float drop_p, const unsigned long long* drop_seed,
+                          unsigned drop_site, cudaStream_t stream) {
   if (!q || !k || !memv || !dout64 || !lse2 || !delta || ((parts & 8) && !dq) || ((parts & 4) && !dk) || (parts & ~12) ||
       B <= 0 || N <= 0 || M <= 0 || B > 65535 || !aligned16(q) || !aligned16(k) || !aligned16(memv) || !aligned16(dout64) ||
-      (rope_table && rope_period <= 0) || ldq < 256 || ldk < 256)
+      (rope_table && rope_period <= 0) || ldq < 256 || ldk < 256 || drop_p < 0.f || drop_p >= 1.f ||
+      (drop_p > 0.f && drop_seed && (!dp_bias || (long long)B * N * M >= (1LL << 32))))
     return sam2b200::fail(SAM2B200_ERR_INVALID, "attn_bwd_v64: bad arguments");
   int rc;
   CUtensorMap map_q64, map_k64, map_q128, map_k128, map_m64, map_m128, map_d64, map_d128, map_dq, map_dk;
@@ -508,20 +521,24 @@ int sam2b200_attn_bwd_v64(const void* q, const void* k, const void* memv, const 
   if ((parts & 4) && (rc = sam2b200::make_out_map(&map_dk, dk, grad_dtype, B, M, ldk, 32))) return rc;
   const float2* table = reinterpret_cast<const float2*>(rope_table);
   const size_t smem3 = sizeof(attn::SharedStorage3) + 1024;
-  const sam2b200::Dropout nodrop = sam2b200::make_dropout(nullptr, 0, 0.f);
+  const sam2b200::Dropout nodrop = sam2b200::make_dropout(drop_seed, drop_site, drop_p);   // (no dropout unless a seed is given)
+  const bool drop_on = nodrop.seed != nullptr;
+  const size_t smemv = sizeof(attn::SharedStorageV64) + 1024;
   if (parts & 4) {   // dK: A1 = K block (TMEM), A2 = memory block, X = Q tiles, Y = dout64 tiles
     attn::ThreeGemmParams p{};
     p.La = M; p.Lx = N; p.scale_log2 = scale * kLog2e; p.scale = scale; p.lse2 = lse2; p.delta = delta;
     p.gout = attn::GradOut{grad_dtype, dbias_k, table, table ? n_rope_k : 0, table ? rope_period : 1};
-    p.drop = nodrop;
+    p.drop = nodrop; p.dp_bias = dp_bias;
     dim3 grid((M + attn::kBlockM - 1) / attn::kBlockM, B, 1);
     p.n_atiles = (int)grid.x;
     p.n_items = (int)(grid.x * grid.y);
     static const bool no_persist = getenv("SAM2B200_NO_PERSIST") != nullptr;
     static const bool single_buf = getenv("SAM2B200_V64_SINGLE_BUFFER") != nullptr;   // A/B: the generic single-buffered kernels
     static const bool persist_dk = getenv("SAM2B200_V64_PERSIST_DK") != nullptr;
-    if (!single_buf && !persist_dk) {   // double-buffered S / dP, both fixed operands in shared memory (attn_v64_kernels.cuh)
-      const size_t smemv = sizeof(attn::SharedStorageV64) + 1024;
+    if (drop_on) {
+      if ((rc = set_smem(attn::three_gemm_v64_kernel<attn::MODE_DK, true>, smemv))) return rc;
+      attn::three_gemm_v64_kernel<attn::MODE_DK, true><<<grid, attn::kThreads, smemv, stream>>>(map_m128, map_q64, map_d64, map_k128, map_dk, p);
+    } else if (!single_buf && !persist_dk) {   // double-buffered S / dP, both fixed operands in shared memory (attn_v64_kernels.cuh)
       if ((rc = set_smem(attn::three_gemm_v64_kernel<attn::MODE_DK>, smemv))) return rc;
       attn::three_gemm_v64_kernel<attn::MODE_DK><<<grid, attn::kThreads, smemv, stream>>>(map_m128, map_q64, map_d64, map_k128, map_dk, p);
     } else if (!no_persist && N < 1024 && grad_dtype && p.n_items > num_sms()) {   // short query loops: resident CTAs (attn_persist_kernels.cuh)
@@ -537,11 +554,13 @@ int sam2b200_attn_bwd_v64(const void* q, const void* k, const void* memv, const 
     attn::ThreeGemmParams p{};
     p.La = N; p.Lx = M; p.scale_log2 = scale * kLog2e; p.scale = scale; p.lse2 = lse2; p.delta = delta;
     p.gout = attn::GradOut{grad_dtype, dbias_q, table, table ? N : 0, table ? rope_period : 1};
-    p.drop = nodrop;
+    p.drop = nodrop; p.dp_bias = dp_bias;
     dim3 grid((N + attn::kBlockM - 1) / attn::kBlockM, B, 1);
     static const bool single_buf = getenv("SAM2B200_V64_SINGLE_BUFFER") != nullptr;
-    if (!single_buf) {
-      const size_t smemv = sizeof(attn::SharedStorageV64) + 1024;
+    if (drop_on) {
+      if ((rc = set_smem(attn::three_gemm_v64_kernel<attn::MODE_DQ, true>, smemv))) return rc;
+      attn::three_gemm_v64_kernel<attn::MODE_DQ, true><<<grid, attn::kThreads, smemv, stream>>>(map_d128, map_k64, map_m64, map_q128, map_dq, p);
+    } else if (!single_buf) {
       if ((rc = set_smem(attn::three_gemm_v64_kernel<attn::MODE_DQ>, smemv))) return rc;
       attn::three_gemm_v64_kernel<attn::MODE_DQ><<<grid, attn::kThreads, smemv, stream>>>(map_d128, map_k64, map_m64, map_q128, map_dq, p);
     } else {

@@ -107,6 +107,8 @@ struct TwoGemmParams {
   int n_items, n_atiles;       // persistent kernels: items = (a block, batch) pairs, a blocks per batch
   void* out_small;             // DY = 64 forward: out' [B, La, 64] bf16
   float* out_small_f32;        //                  and its fp32 copy (optional)
+  float* rowsum_drop;          // DY = 64 forward with dropout: [B, La] row sums of the dropped, re-scaled probabilities
+                               // (the factor of the value bias: out = out' Wv^T + rowsum bv)
 };
 
 struct SharedStorage {
@@ -443,6 +445,7 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const uint32_t drop_key = drop_on ? sam2b200::dropout_key(*p.drop.seed, p.drop.site) : 0u;
     float m_ref = -INFINITY;   // running (lazily updated) row max of the raw scores -- identical in both halves
     float l = 0.f;             // this half's running sum of exp2((s - m_ref) c)
+    float lk = 0.f;            // DY = 64 with dropout: the same sum over the KEPT probabilities only
 
     // DV: per-column LSE2 (columns are queries) is staged through shared memory ONE TILE AHEAD, so the
     // global-load latency is off the per-tile critical path.
@@ -509,6 +512,7 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           }
           tmem_wait_st();
           l *= f;
+          lk *= f;
           m_ref = m_new;
         }
         const float mc = m_ref * c;
@@ -523,6 +527,7 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           if (drop_on) {
             e0 = sam2b200::dropout_keep(drop_key, didx + i, p.drop.thresh) ? e0 : 0.f;
             e1 = sam2b200::dropout_keep(drop_key, didx + i + 1, p.drop.thresh) ? e1 : 0.f;
+            if (DY == 64) lk += e0 + e1;
           }
           pk[i >> 1] = pack_bf16(e0, e1);
         }
@@ -564,6 +569,12 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       if (DY == 64) {
         // narrow accumulator: this warp holds 32 rows x 32 of the 64 output columns -> plain 16-byte global stores
         const float inv_l = p.drop.inv_keep / l;
+        if (drop_on) {          // row sum of the dropped, re-scaled probabilities (both halves; xchg is idle by now)
+          sh.xchg[0][half][row] = lk;
+          pair_barrier(quarter);
+          lk += sh.xchg[0][half ^ 1][row];
+          if (row_valid && half == 0 && p.rowsum_drop != nullptr) p.rowsum_drop[(long long)b * p.La + a_row_idx] = lk * inv_l;
+        }
         uint32_t o[32];
         SAM2B200_TMEM_LD32(lane_addr + kColAcc + half * 32, o);
         tmem_wait_ld();
@@ -662,6 +673,7 @@ struct ThreeGemmParams {
   sam2b200::Dropout drop;      // attention-probability dropout: dP is masked and scaled like P was in the forward
   unsigned long long* dbg;     // optional timeline buffer
   int n_items, n_atiles;       // persistent kernel: items = (a block, batch) pairs, a blocks per batch
+  const float* dp_bias;        // raw-memory path with dropout: [B, N] per-query constant dO . bv added to dP before the mask
 };
 
 struct SharedStorage3 {

@@ -41,10 +41,13 @@ struct SharedStorageV64 {
   uint64_t acc_done;
   float col_lse[2][kBlockN];
   float col_delta[2][kBlockN];
+  float col_bias[2][kBlockN];
   uint32_t tmem_base;
 };
 
-template <int MODE>
+// DROP: attention-probability dropout (compile-time).  dP = keep ? (dO' mem^T + dO . bv) / (1 - p) : 0 -- under dropout the
+// rows of the probability matrix no longer sum to 1, so the per-query constant dO . bv (p.dp_bias) does not cancel.
+template <int MODE, bool DROP = false>
 __global__ void __launch_bounds__(kThreads, 1)
 three_gemm_v64_kernel(const __grid_constant__ CUtensorMap map_a2,   // [B, La, 64] bf16, box 64 x 128
                       const __grid_constant__ CUtensorMap map_x,    // [B, Lx, 256] bf16, box 64 x 64
@@ -176,25 +179,30 @@ three_gemm_v64_kernel(const __grid_constant__ CUtensorMap map_a2,   // [B, La, 6
     const uint32_t stage = smem_u32(&sh.a1[0]) + warp * (4 * kBoxBytes);   // a1 + the ring behind it are idle at the epilogue
     const bool rotate = p.gout.rope_table != nullptr && (row0 + lane) < p.gout.rope_rows;
     const float c = p.scale_log2;
-    float row_lse = 0.f, row_delta = 0.f;
+    float row_lse = 0.f, row_delta = 0.f, row_bias = 0.f;
     if (MODE == MODE_DQ && row_valid) {
       row_lse = p.lse2[(long long)b * p.La + a_row_idx];
       row_delta = p.delta[(long long)b * p.La + a_row_idx];
+      if (DROP) row_bias = p.dp_bias[(long long)b * p.La + a_row_idx];
     }
-    float lse_next = INFINITY, delta_next = 0.f;
+    float lse_next = INFINITY, delta_next = 0.f, bias_next = 0.f;
     if (MODE == MODE_DK && threadIdx.x < kBlockN && (int)threadIdx.x < p.Lx) {
       lse_next = p.lse2[(long long)b * p.Lx + threadIdx.x];
       delta_next = p.delta[(long long)b * p.Lx + threadIdx.x];
+      if (DROP) bias_next = p.dp_bias[(long long)b * p.Lx + threadIdx.x];
     }
+    const uint32_t drop_key = DROP ? sam2b200::dropout_key(*p.drop.seed, p.drop.site) : 0u;
     for (int j = 0; j < nt; ++j) {
       if (MODE == MODE_DK) {
         if (threadIdx.x < kBlockN) {
           sh.col_lse[j & 1][threadIdx.x] = lse_next;
           sh.col_delta[j & 1][threadIdx.x] = delta_next;
+          if (DROP) sh.col_bias[j & 1][threadIdx.x] = bias_next;
           const int col = (j + 1) * kBlockN + threadIdx.x;
           const bool ok = (j + 1 < nt) && col < p.Lx;
           lse_next = ok ? p.lse2[(long long)b * p.Lx + col] : INFINITY;
           delta_next = ok ? p.delta[(long long)b * p.Lx + col] : 0.f;
+          if (DROP) bias_next = ok ? p.dp_bias[(long long)b * p.Lx + col] : 0.f;
         }
         asm volatile("bar.sync 5, 256;" ::: "memory");
       }
@@ -222,11 +230,23 @@ three_gemm_v64_kernel(const __grid_constant__ CUtensorMap map_a2,   // [B, La, 6
         uint32_t r0[32];
         SAM2B200_TMEM_LD32(dbuf, r0);
         tmem_wait_ld();
+        // element (query q, key k) has dropout index (b N + q) M + k: DQ rows are queries, DK rows are keys
+        const uint32_t didx = (MODE == MODE_DQ)
+            ? (uint32_t)(((long long)b * p.La + a_row_idx) * p.Lx) + (uint32_t)(j * kBlockN + half * kHalfN)
+            : (uint32_t)(((long long)b * p.Lx + (j * kBlockN + half * kHalfN)) * p.La + a_row_idx);
+        const uint32_t dstep = (MODE == MODE_DQ) ? 1u : (uint32_t)p.La;
 #pragma unroll
         for (int i = 0; i < kHalfN; i += 2) {
           const float dl0 = (MODE == MODE_DQ) ? row_delta : sh.col_delta[j & 1][half * kHalfN + i];
           const float dl1 = (MODE == MODE_DQ) ? row_delta : sh.col_delta[j & 1][half * kHalfN + i + 1];
-          pk[i >> 1] = pack_bf16(pv[i] * (__uint_as_float(r0[i]) - dl0), pv[i + 1] * (__uint_as_float(r0[i + 1]) - dl1));
+          float d0 = __uint_as_float(r0[i]), d1 = __uint_as_float(r0[i + 1]);
+          if (DROP) {
+            const float cb0 = (MODE == MODE_DQ) ? row_bias : sh.col_bias[j & 1][half * kHalfN + i];
+            const float cb1 = (MODE == MODE_DQ) ? row_bias : sh.col_bias[j & 1][half * kHalfN + i + 1];
+            d0 = sam2b200::dropout_keep(drop_key, didx + (uint32_t)i * dstep, p.drop.thresh) ? (d0 + cb0) * p.drop.inv_keep : 0.f;
+            d1 = sam2b200::dropout_keep(drop_key, didx + (uint32_t)(i + 1) * dstep, p.drop.thresh) ? (d1 + cb1) * p.drop.inv_keep : 0.f;
+          }
+          pk[i >> 1] = pack_bf16(pv[i] * (d0 - dl0), pv[i + 1] * (d1 - dl1));
         }
       }
       SAM2B200_TMEM_ST16(dbuf, pk);          // dS over this warp's own dP columns

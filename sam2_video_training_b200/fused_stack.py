@@ -353,11 +353,13 @@ class MemoryAttentionStackFn(torch.autograd.Function):
         mirror = weight_mirror(masters)
         # Cross-attention on the raw 64-d memory features (sam2b200_attn_fwd_v64): softmax rows sum to 1, so
         # softmax(.) (mem Wv^T + bv) = (softmax(.) mem) Wv^T + bv -- v_proj moves from the [B M, 64] bank to the [B N, 64]
-        # result, the [B, M, 256] value tensor and the dV kernel disappear.  Needs: no attention-probability dropout
-        # (rows of the dropped matrix do not sum to 1), no gradient w.r.t. `memory` (the bank is detached in training,
-        # sam2model.py:345-358), enough (query block, object) CTAs to fill the GPU without split-KV.
-        v64 = (not NO_V64 and (dr is None or dr["p_ca"] <= 0.0) and not ctx.needs_input_grad[3]
-               and b * ((n + 127) // 128) >= 64)
+        # result, the [B, M, 256] value tensor and the dV kernel disappear.  Needs: no gradient w.r.t. `memory` (the bank
+        # is detached in training, sam2model.py:345-358) and enough (query block, object) CTAs to fill the GPU without
+        # split-KV.  With attention-probability dropout the rows of the dropped matrix do not sum to 1: the kernels then
+        # also return those row sums (factor of the value bias) and take the per-query constant dO . bv in the backward
+        # (folded projections only).
+        ca_drop = dr is not None and dr["p_ca"] > 0.0
+        v64 = (not NO_V64 and not (ca_drop and NO_FOLD) and not ctx.needs_input_grad[3] and b * ((n + 127) // 128) >= 64)
 
         def project_memory():        # cross-attention keys / values of every layer: functions of the bank only
             for l in range(nl):
@@ -401,7 +403,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             side.wait(ev)
             if v64:
                 # v2 / o2_32 slots of `saved` then hold out64 (bf16) and its fp32 copy
-                v2, o2_32, lse2 = attn_fwd_v64(q2_rot, k2_rot, memv.view(b, m, 64), scale)
+                v2, o2_32, lse2, rs = attn_fwd_v64(q2_rot, k2_rot, memv.view(b, m, 64), scale, drop=dsite("p_ca", l, 1))
                 if NO_FOLD:
                     o2 = torch.addmm(W["ca.v.b"], v2.view(r, 64), W["ca.v.w"].t()).view(b, n, d)      # v_proj on the result
                     ca = torch.addmm(W["ca.o.b"], o2.view(r, d), W["ca.o.w"].t())
@@ -409,8 +411,13 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                     # out_proj(v_proj(out64)) = out64 (Wo Wv)^T + (Wo bv + bo): one [B N, 64] -> 256 GEMM; the o2 slot of
                     # `saved` holds the folded weight (fp32 product of the master weights, rounded once)
                     o2 = torch.mm(P["ca.o.w"], P["ca.v.w"]).to(BF16)
-                    ca = torch.addmm(torch.addmv(P["ca.o.b"], P["ca.o.w"], P["ca.v.b"]).to(BF16), v2.view(r, 64), o2.t())
+                    if rs is None:
+                        ca = torch.addmm(torch.addmv(P["ca.o.b"], P["ca.o.w"], P["ca.v.b"]).to(BF16), v2.view(r, 64), o2.t())
+                    else:   # dropout: the value bias enters with the row sums of the dropped probabilities (rank-1 term)
+                        ca = torch.addmm(W["ca.o.b"], v2.view(r, 64), o2.t())
+                        ca.addr_(rs.view(r).to(BF16), torch.mv(P["ca.o.w"], P["ca.v.b"]).to(BF16))
             else:
+                rs = None
                 o2, o2_32, lse2 = attn_fwd(q2_rot, k2_rot, v2.view(b, m, d), scale, meta["nsplit"], drop=dsite("p_ca", l, 1))
                 ca = torch.addmm(W["ca.o.b"], o2.view(r, d), W["ca.o.w"].t())
             # ---- MLP (memory_attention.py:95-98)
@@ -420,7 +427,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             mlp = torch.addmm(W["l2.b"], h, W["l2.w"].t())
             saved += [x, mean1, rstd1, y1, q_rot, k_rot, v, o, o32, lse,
                       x1, mean2, rstd2, y2, q2_rot, k2_rot, v2, o2, o2_32, lse2,
-                      x2, mean3, rstd3, y3, h]
+                      x2, mean3, rstd3, y3, h, rs if rs is not None else lse2[:0]]
             x, res = x2, mlp
         gamma_f, beta_f = params[nl * _NPL], params[nl * _NPL + 1]
         out, x_fin, mean_f, rstd_f = ln_fwd(x, res, gamma_f, beta_f, want_f32_seq_first=(b, n), drop=dsite("p_res", nl - 1, 5))
@@ -493,10 +500,10 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                         seq_first=(b, n), dbias=gv[last + _LAYER_KEYS.index("l2.b")], drop=dsite("p_res", nl - 1, 5))
         dmemk = torch.zeros((rm, memk.shape[1]), dtype=F32, device=dev) if need_memgrad else None
         dmemv = torch.zeros((rm, memv.shape[1]), dtype=F32, device=dev) if need_mem else None
-        per = 25
+        per = 26
         for l in reversed(range(nl)):
             (x0, mean1, rstd1, y1, q_rot, k_rot, v, o, o32, lse, x1, mean2, rstd2, y2, q2_rot, k2_rot, v2, o2, o2_32,
-             lse2, x2, mean3, rstd3, y3, h) = saved[l * per:(l + 1) * per]
+             lse2, x2, mean3, rstd3, y3, h, rs) = saved[l * per:(l + 1) * per]
             base = l * _NPL
             ix = {k: base + i for i, k in enumerate(_LAYER_KEYS)}
             W = {k: wb[ix[k]] for k in _LAYER_KEYS}
@@ -531,24 +538,33 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                     # ca = out64 (Wo Wv)^T + (Wo bv + bo):  G = d/d(Wo Wv) = dca^T out64, g = d/d(Wo bv + bo) = colsum(dca);
                     # dWo = G Wv^T + g bv^T, dWv = Wo^T G, dbv = Wo^T g, dbo = g -- four [256 x 64]-sized fp32 products
                     do64 = torch.mm(dca, o2).view(b, n, 64)                 # o2 slot = folded weight [256, 64]
+                    ca_drop = rs.numel() > 0
+                    # with dropout the value bias entered as rowsum (x) Wo bv: its gradients use g_rs = dca^T rowsum
+                    # instead of g = colsum(dca), and the per-query constant c = dca . (Wo bv) goes into dP and Delta
+                    g_rs = _mm32(dca.t(), rs.view(r, 1).to(BF16)).view(d) if ca_drop else g_bo
+                    dp_bias = (_mm32(dca, torch.mv(P["ca.o.w"], P["ca.v.b"]).to(BF16).view(d, 1)).view(b, n)
+                               if ca_drop else None)
 
-                    def fold_grads(dca=dca, o64=o64, g_bo=g_bo, ix=ix, P=P):
+                    def fold_grads(dca=dca, o64=o64, g_bo=g_bo, g_rs=g_rs, ix=ix, P=P):
                         G = _mm32(dca.t(), o64.view(r, 64))
-                        d_wo = torch.addmm(torch.outer(g_bo, P["ca.v.b"]), G, P["ca.v.w"].t())
+                        d_wo = torch.addmm(torch.outer(g_rs, P["ca.v.b"]), G, P["ca.v.w"].t())
                         d_wv = torch.mm(P["ca.o.w"].t(), G)
                         gv[ix["ca.o.b"]].add_(g_bo)
-                        gv[ix["ca.v.b"]].addmv_(P["ca.o.w"].t(), g_bo)
+                        gv[ix["ca.v.b"]].addmv_(P["ca.o.w"].t(), g_rs)
                         if direct:
                             gv[ix["ca.o.w"]].add_(d_wo)
                             gv[ix["ca.v.w"]].add_(d_wv)
                         else:
                             grads[ix["ca.o.w"]], grads[ix["ca.v.w"]] = d_wo, d_wv
-                    side.run(fold_grads, dca, o64, g_bo)
+                    side.run(fold_grads, dca, o64, g_bo, g_rs)
                 else:
+                    dp_bias = None
                     acc_w(ix["ca.v.w"], do2.t(), o64.view(r, 64), gv[ix["ca.v.b"]])
                     do64 = torch.mm(do2, W["ca.v.w"]).view(b, n, 64)
                 delta = (do64.float() * o64_32).sum(-1)
-                kw = dict(table=table, n_rope_k=n_rope_k, grad_dtype=BF16)
+                if dp_bias is not None:
+                    delta = torch.addcmul(delta, dp_bias, rs)
+                kw = dict(table=table, n_rope_k=n_rope_k, grad_dtype=BF16, dp_bias=dp_bias, drop=dsite("p_ca", l, 1))
                 args = (q2_rot, k2_rot, memv.view(b, m, 64), do64, lse2, delta, scale)
 
                 def key_side(args=args, kw=kw, l=l, ix=ix, W=W):
@@ -560,7 +576,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                         grads[ix["ca.k.w"]] = _mm32(dk2.t(), memk)
                     if need_memgrad:
                         torch.addmm(dmemk, dk2, W["ca.k.w"], out_dtype=F32, out=dmemk)
-                side.run(key_side, q2_rot, k2_rot, memv, do64, lse2, delta)
+                side.run(key_side, q2_rot, k2_rot, memv, do64, lse2, delta, dp_bias)
                 dq2, _ = attn_bwd_v64(*args, parts=8, dbias=(gv[ix["ca.q.b"]], None), **kw)
             else:
                 delta = torch.empty((b, n), dtype=F32, device=dev)

@@ -128,9 +128,10 @@ def attn_bwd(q, k, v, out, out32, dout, lse2, scale: float, table=None, n_rope_k
     return dq, dk, dv
 
 
-def attn_fwd_v64(q, k, memv, scale: float, keep_f32: bool = True):
+def attn_fwd_v64(q, k, memv, scale: float, keep_f32: bool = True, drop=None):
     """Cross-attention on the raw 64-d memory features (sam2b200_attn_fwd_v64): q [B,N,256], k [B,M,256] (rotated),
-    memv [B,M,64] bf16 -> (out64 bf16 [B,N,64], its fp32 copy or None, lse2 [B,N]); the caller applies v_proj to out64."""
+    memv [B,M,64] bf16 -> (out64 bf16 [B,N,64], its fp32 copy or None, lse2 [B,N], rowsum); the caller applies v_proj to
+    out64.  drop = (p, seed, site): rowsum [B,N] = row sums of the dropped, re-scaled probabilities (None without dropout)."""
     lib = _lib.load()
     b, n, d = q.shape
     m = k.shape[1]
@@ -140,16 +141,18 @@ def attn_fwd_v64(q, k, memv, scale: float, keep_f32: bool = True):
     out = torch.empty((b, n, 64), dtype=torch.bfloat16, device=q.device)
     out32 = torch.empty((b, n, 64), dtype=torch.float32, device=q.device) if keep_f32 else None
     lse2 = torch.empty((b, n), dtype=torch.float32, device=q.device)
+    rowsum = torch.empty((b, n), dtype=torch.float32, device=q.device) if drop is not None else None
     with _Timed("attn_fwd", 4.0 * b * n * m * 256):      # algorithmic FLOPs of the op it replaces
         rc = lib.sam2b200_attn_fwd_v64(q.data_ptr(), k.data_ptr(), memv.data_ptr(), out.data_ptr(),
-                                       out32.data_ptr() if out32 is not None else None, lse2.data_ptr(), b, n, m, scale,
-                                       _stream(q.device))
+                                       out32.data_ptr() if out32 is not None else None, lse2.data_ptr(),
+                                       rowsum.data_ptr() if rowsum is not None else None, b, n, m, scale,
+                                       *_drop_args(drop), _stream(q.device))
     _lib.check(rc, "sam2b200_attn_fwd_v64")
-    return out, out32, lse2
+    return out, out32, lse2, rowsum
 
 
 def attn_bwd_v64(q, k, memv, dout64, lse2, delta, scale: float, table=None, n_rope_k: int = 0, grad_dtype=torch.float32,
-                 dq=None, dk=None, dbias=(None, None), parts: int = 12):
+                 dq=None, dk=None, dbias=(None, None), parts: int = 12, dp_bias=None, drop=None):
     """Backward of attn_fwd_v64: dout64 = dO Wv [B,N,64] bf16, delta = rowsum(dout64 o out64) [B,N] fp32.
     parts: 4 = dK, 8 = dQ (no dV on this path).  Returns (dq, dk)."""
     lib = _lib.load()
@@ -172,7 +175,8 @@ def attn_bwd_v64(q, k, memv, dout64, lse2, delta, scale: float, table=None, n_ro
                                        dq.stride(-2) if dq is not None else 256, dk.stride(-2) if dk is not None else 256,
                                        table.data_ptr() if table is not None else None,
                                        table.shape[0] if table is not None else 0, n_rope_k, b, n, m, scale,
-                                       *[t_.data_ptr() if t_ is not None else None for t_ in dbias], int(parts), _stream(dev))
+                                       *[t_.data_ptr() if t_ is not None else None for t_ in dbias], int(parts),
+                                       dp_bias.data_ptr() if dp_bias is not None else None, *_drop_args(drop), _stream(dev))
     _lib.check(rc, "sam2b200_attn_bwd_v64")
     return dq, dk
 

@@ -27,7 +27,7 @@ for shape in sys.argv[1:] or ["56,576,4060", "56,576,1160", "13,1024,7196", "4,4
     table = compute_axial_cis(dim=256, end_x=grid, end_y=grid).to(dev)
     nr = (m // n) * n
     o, o32, lse = ops.attn_fwd(q, k, v, 1 / 16.0)
-    o64, o64_32, lse64 = ops.attn_fwd_v64(q, k, mem, 1 / 16.0)
+    o64, o64_32, lse64, _ = ops.attn_fwd_v64(q, k, mem, 1 / 16.0)
     delta = torch.zeros(b, n, device=dev)
     db = tuple(torch.zeros(256, device=dev) for _ in range(3))
     t_f = timeit(lambda: ops.attn_fwd(q, k, v, 1 / 16.0))

@@ -185,6 +185,40 @@ def test_memory_attention_random_vs_oracle(dev, grid, b, nf, nptr, fused):
     assert worst[0] > 0.998, worst
 
 
+def test_raw_memory_cross_attention_dropout_matches_explicit_mask(dev):
+    """Attention-probability dropout on the raw-memory path: rows of the dropped matrix do not sum to 1, so the forward
+    returns their sums (factor of the value bias) and the backward takes the per-query constant dO . bv.  Against fp32
+    torch of the reference formulation softmax -> mask / (1 - p) -> @ (mem Wv^T + bv) with the kernels' own mask."""
+    from sam2_video_training_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(77)
+    b, n, m, p_drop, site = 3, 144, 300, 0.1, 9
+    seed = torch.tensor([0x0123456789ABCDE], dtype=torch.int64, device=dev)
+    q = torch.randn(b, n, 256, device=dev, generator=g).to(torch.bfloat16)
+    k = torch.randn(b, m, 256, device=dev, generator=g).to(torch.bfloat16)
+    mem = torch.randn(b, m, 64, device=dev, generator=g).to(torch.bfloat16)
+    wv = (torch.randn(256, 64, device=dev, generator=g) / 8).to(torch.bfloat16)
+    bv = torch.randn(256, device=dev, generator=g) * 0.5
+    do = torch.randn(b, n, 256, device=dev, generator=g).to(torch.bfloat16)
+    keep = _keep_mask(dev, seed, site, p_drop, b * n * m).view(b, n, m)
+    qf, kf, mf, wf, bf = (t.float().requires_grad_(True) for t in (q, k, mem, wv, bv))
+    a = torch.softmax(qf @ kf.transpose(1, 2) / 16.0, dim=-1) * keep / (1 - p_drop)
+    ref = a @ (mf @ wf.t() + bf)
+    ref.backward(do.float())
+    drop = (p_drop, seed, site)
+    o64, o64_32, lse, rs = ops.attn_fwd_v64(q, k, mem, 1 / 16.0, drop=drop)
+    assert rel_l2(rs, a.sum(-1)) < 1e-3
+    out = o64_32 @ wv.float().t() + rs[..., None] * bv
+    assert rel_l2(out, ref) < 5e-3
+    do64 = (do.float() @ wv.float()).to(torch.bfloat16)
+    c = do.float() @ bv
+    delta = (do64.float() * o64_32).sum(-1) + c * rs
+    dq, dk = ops.attn_bwd_v64(q, k, mem, do64, lse, delta.contiguous(), 1 / 16.0, grad_dtype=torch.float32, dp_bias=c.contiguous(), drop=drop)
+    assert rel_l2(dq, qf.grad) < 1e-2, rel_l2(dq, qf.grad)
+    assert rel_l2(dk, kf.grad) < 1e-2, rel_l2(dk, kf.grad)
+    assert rel_l2(do.float().flatten(0, 1).t() @ o64_32.flatten(0, 1), wf.grad) < 5e-3
+    assert rel_l2((rs[..., None] * do.float()).sum((0, 1)), bf.grad) < 1e-3
+
+
 def test_fused_stack_raw_memory_cross_attention_vs_oracle(dev, monkeypatch):
     """Training-shaped call (memory detached, memory_pos trainable, no dropout, enough objects to fill the GPU): the fused
     stack runs its cross-attention on the raw 64-d memory features (attn_fwd_v64 / attn_bwd_v64, v_proj applied to the
@@ -327,7 +361,8 @@ def test_attention_dropout_matches_explicit_mask(dev, b, n, m):
     assert rel_l2(o_nodrop, ref) > 0.05        # the mask really changes the result
 
 
-def test_training_mode_dropout_fused_stack_matches_oracle_with_same_masks(dev):
+@pytest.mark.parametrize("b", [2, 64])      # 64 objects: the cross-attention runs on the raw 64-d memory features
+def test_training_mode_dropout_fused_stack_matches_oracle_with_same_masks(dev, b):
     """Train mode with the shipped dropout = 0.1 runs the fused stack; every dropout of the reference
     (memory_attention.py:64,81,97,99, transformer.py:304-306) is applied with counter-based masks.  The oracle, given
     the very masks the kernels generate, must reproduce output and gradients; two calls draw different masks."""
@@ -337,7 +372,7 @@ def test_training_mode_dropout_fused_stack_matches_oracle_with_same_masks(dev):
     assert model._fused_eligible()
     params = ao.init_params(seed=0)
     _load_params(model, params)
-    grid, b, nf, nptr = 8, 2, 2, 4
+    grid, nf, nptr = 8, 2, 4
     n, m = grid * grid, nf * grid * grid + nptr
     g = torch.Generator().manual_seed(5)
     curr, curr_pos = torch.randn(n, b, 256, generator=g), torch.randn(n, b, 256, generator=g) * 0.7
@@ -764,7 +799,7 @@ def test_cross_attention_on_raw_memory_features(dev, b, grid, nf, nptr):
     ref = torch.softmax(qf @ kf.transpose(1, 2) / 16.0, dim=-1) @ (mf @ wf.t() + bf)
     ref.backward(do.float())
     # new path
-    o64, o64_32, lse = ops.attn_fwd_v64(q, k, mem, 1 / 16.0)
+    o64, o64_32, lse, _ = ops.attn_fwd_v64(q, k, mem, 1 / 16.0)
     out = o64_32 @ wv.float().t() + bv
     assert rel_l2(out, ref) < 5e-3
     do64 = (do.float() @ wv.float()).to(torch.bfloat16)

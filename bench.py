@@ -471,10 +471,10 @@ def main():
                 "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
                 "peak_source": pk["src"] + " sustained cuBLAS bf16",
                 # dram__bytes_read.sum + dram__bytes_write.sum of the backward kernels of ONE cross-attention call at the largest
-                # shape of this workload (B=56, N=576, M=4060), ncu --set full.  Raw-memory path (default, no dropout):
-                # dK 249.3 + dQ 181.7 MB, profiles/r1_ncu_attn_v64_cfg2_cross.csv; 256-d value path (dropout on):
-                # dV 229.5 + dK 357.2 + dQ 285.3 MB, profiles/r1_ncu_attn_v3_cfg2_cross.csv
-                "traffic": (None if not wl_name.startswith("cfg2") else 871.97e6 if args.dropout > 0 else 431.0e6),
+                # shape of this workload (B=56, N=576, M=4060), ncu --set full.  Raw-memory path: dK 249.3 + dQ 181.7 MB,
+                # profiles/r1_ncu_attn_v64_cfg2_cross.csv (the 256-d value path it replaced: dV 229.5 + dK 357.2 + dQ 285.3 MB,
+                # profiles/r1_ncu_attn_v3_cfg2_cross.csv)
+                "traffic": (431.0e6 if wl_name.startswith("cfg2") else None),
                 "traffic_note": "per cross-attention backward call at B=56 N=576 M=4060; algorithmic operand bytes q,k,mem,dO',dq,dk "
                                 "= 0.30 GB on the raw-memory path (K is read once by each of the two kernels)",
                 "attention_fwd_bwd_tflops": attn_fl / (attn_ms * 1e-3) / 1e12 if attn_ms else None,

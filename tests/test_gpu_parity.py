@@ -777,7 +777,7 @@ def test_attention_backward_persistent_key_side_kernels(dev, b, grid, nf, extra,
         assert rel_l2(res[torch.bfloat16][2].float(), vf.grad) < 8e-3
 
 
-@pytest.mark.parametrize("b,grid,nf,nptr", [(3, 12, 2, 8), (2, 24, 7, 28), (1, 32, 2, 20), (40, 8, 7, 12), (40, 12, 4, 16)])   # last two: persistent dK (1 and 3 query tiles)
+@pytest.mark.parametrize("b,grid,nf,nptr", [(3, 12, 2, 8), (2, 24, 7, 28), (1, 32, 2, 20), (40, 8, 7, 12), (40, 12, 4, 16)])   # last two: more (key block, object) items than SMs, 1 and 3 query tiles
 def test_cross_attention_on_raw_memory_features(dev, b, grid, nf, nptr):
     """sam2b200_attn_fwd_v64 / _bwd_v64: softmax(q k^T) (mem Wv^T + bv) == (softmax(q k^T) mem) Wv^T + bv (rows sum to 1),
     so the value projection moves from the [B M, 64] memory to the [B N, 64] result.  Output, dq, dk and the value

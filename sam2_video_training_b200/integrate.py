@@ -1,0 +1,47 @@
+"""Single-flag switch for the reference wrapper (INTEGRATION.md sections 2-3).
+
+``use_b200_attention(model)`` is what ``SAM2Model.__init__`` would call right after adopting the built SAM2 model's
+sub-modules (sam2_video/model/sam2model.py:80-105) when ``model.use_b200_attention: true``: it replaces
+``model.memory_attention`` (the ``nn.Module`` attribute set at sam2_video/model/modeling/sam2_base.py:125 and invoked at
+:695-709) by the drop-in, carrying the weights over with ``load_state_dict(strict=True)`` -- the drop-in keeps the
+reference's 106 state_dict keys, so checkpoints written afterwards load into the reference classes as well.
+``b200_criterion(loss_type, ...)`` mirrors the ``loss.type`` dispatch of sam2_video/training/trainer.py:67-94.
+"""
+from __future__ import annotations
+
+from typing import Any
+
+from torch import nn
+
+from .losses import BCECategoryLoss, MultiStepMultiMasksAndIous
+from .merged_loss import CategoryMergedMultiStepLoss
+from .modeling.memory_attention import MemoryAttention, build_memory_attention
+
+
+def use_b200_attention(model: nn.Module, attr: str = "memory_attention") -> MemoryAttention:
+    """Swap ``getattr(model, attr)`` (a reference ``MemoryAttention``) for the B200 drop-in, weights included."""
+    ref = getattr(model, attr)
+    layer0 = ref.layers[0]
+    dropout = float(getattr(layer0, "dropout_value", layer0.dropout1.p if hasattr(layer0, "dropout1") else 0.0))
+    fast = build_memory_attention(dropout=dropout)
+    p0 = next(ref.parameters())
+    fast = fast.to(device=p0.device)
+    missing, unexpected = fast.load_state_dict(ref.state_dict(), strict=True)
+    assert not missing and not unexpected
+    fast.train(ref.training)
+    for p_new, p_old in zip(fast.parameters(), ref.parameters()):
+        p_new.requires_grad_(p_old.requires_grad)          # keep the freeze map (trainable_modules, sam2model.py:133-137)
+    setattr(model, attr, fast)
+    return fast
+
+
+def b200_criterion(loss_type: str, **cfg: Any) -> nn.Module:
+    """``multi_step_b200`` / ``bce_b200`` / ``multi_step_merged_b200`` (the last one takes the un-merged tracker stages,
+    INTEGRATION.md section 3b)."""
+    if loss_type == "multi_step_b200":
+        return MultiStepMultiMasksAndIous(**cfg)
+    if loss_type == "bce_b200":
+        return BCECategoryLoss(**cfg)
+    if loss_type == "multi_step_merged_b200":
+        return CategoryMergedMultiStepLoss(**cfg)
+    raise ValueError(f"unknown loss type {loss_type!r}")

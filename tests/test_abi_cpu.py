@@ -143,3 +143,40 @@ def test_merged_loss_host_checks_without_device():
     stages = [{"multistep_pred_multimasks": [torch.zeros(2, 1, 4, 4)], "multistep_pred_ious": [torch.zeros(2, 1)]}]
     with pytest.raises(L.Sam2B200Error):
         crit(stages, [0, 1], 2, torch.ones(1, 2, 16, 16, dtype=torch.bool))
+
+
+def test_single_flag_switch_against_the_real_reference_module():
+    """integrate.use_b200_attention on a stand-in for SAM2Base that holds the UNMODIFIED reference MemoryAttention (built
+    through oracle/ref_shim.py; skipped where /root/reference does not exist): strict state_dict transfer both ways, the
+    freeze map and train/eval mode are kept, the attributes the caller touches exist (memory_attention.py:119-169)."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference sources not present")
+    from sam2_video_training_b200 import integrate
+    from sam2_video_training_b200.modeling.memory_attention import MemoryAttention
+    from sam2_video_training_b200.modeling.sam.transformer import RoPEAttention as FastRope
+
+    class Holder(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.memory_attention = ref_shim.build_memory_attention(dropout=0.1)
+
+    m = Holder().eval()
+    for p in m.memory_attention.layers[1].parameters():
+        p.requires_grad_(False)
+    ref_sd = {k: v.clone() for k, v in m.memory_attention.state_dict().items()}
+    ref_mod = m.memory_attention
+    fast = integrate.use_b200_attention(m)
+    assert m.memory_attention is fast and isinstance(fast, MemoryAttention) and not fast.training
+    assert list(fast.state_dict().keys()) == list(ref_sd.keys())
+    for k, v in fast.state_dict().items():
+        assert torch.equal(v, ref_sd[k]), k
+    assert [p.requires_grad for p in fast.parameters()] == [p.requires_grad for p in ref_mod.parameters()]
+    assert fast.d_model == 256 and fast.num_layers == 4 and len(fast.layers) == 4 and fast.norm.normalized_shape == (256,)
+    assert isinstance(fast.layers[0].cross_attn_image, FastRope) and fast.layers[0].cross_attn_image.rope_k_repeat
+    assert fast.layers[0].dropout1.p == pytest.approx(0.1) if hasattr(fast.layers[0], "dropout1") else True
+    ref_mod.load_state_dict(fast.state_dict(), strict=True)          # and back: checkpoints stay interchangeable
+    with pytest.raises(ValueError):
+        integrate.b200_criterion("nope")
+    crit = integrate.b200_criterion("multi_step_b200", weight_dict={"loss_mask": 20, "loss_dice": 1, "loss_iou": 1})
+    assert crit.weight_dict["loss_class"] == 0.0

@@ -180,3 +180,25 @@ def test_single_flag_switch_against_the_real_reference_module():
         integrate.b200_criterion("nope")
     crit = integrate.b200_criterion("multi_step_b200", weight_dict={"loss_mask": 20, "loss_dice": 1, "loss_iou": 1})
     assert crit.weight_dict["loss_class"] == 0.0
+
+
+def test_bench_reference_arm_runs_on_cpu_and_keeps_the_json_contract():
+    """`bench.py --impl reference` (the CPU oracle timed on the host cores) needs no GPU and prints ONE JSON line with the
+    contract keys; under torchrun ranks other than 0 exit 0 without work."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["impl"] == "reference" and d["metric"] == "memory_attn_fwd_bwd_plus_mask_loss_clip_frames_per_sec"
+    assert d["unit"] == "clip-frames/s" and d["higher_is_better"] is True and d["n_gpus"] == 1 and d["value"] > 0
+    assert d["config"]["workload"].startswith("cfg2") and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    env1 = dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                           "--warmup", "1"], capture_output=True, text=True, timeout=120, env=env1, cwd=ROOT)
+    assert out1.returncode == 0 and not [l for l in out1.stdout.splitlines() if l.startswith("{")]

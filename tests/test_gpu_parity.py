@@ -246,7 +246,8 @@ def test_fused_stack_raw_memory_cross_attention_vs_oracle(dev, monkeypatch):
     out = model(ld["curr"], ld["memory"], ld["curr_pos"], ld["memory_pos"], nptr)
     out.backward(gout.to(dev))
     torch.cuda.synchronize()
-    assert calls == {"fwd": 4, "bwd": 8}, calls            # 4 layers: forward once, backward dK + dQ
+    if not fused_stack.NO_V64:                             # (SAM2B200_NO_V64=1 is the A/B switch back to the 256-d value path)
+        assert calls == {"fwd": 4, "bwd": 8}, calls        # 4 layers: forward once, backward dK + dQ
     assert rel_l2(out, ref) < ATTN_REL_TOL
     for k in ("curr", "curr_pos", "memory_pos"):
         assert cosine(ld[k].grad, lo_[k].grad) > GRAD_COS_TOL, k

@@ -280,6 +280,12 @@ class WeightMirror:
             self.qkv.append(self.flat[o0:o0 + 3 * v0.numel()].view(3 * v0.shape[0], v0.shape[1]))
             b0 = self.views[first[3 * nl + 3 * l]]
             self.qkv_bias.append(self.flat[b0.storage_offset():b0.storage_offset() + 3 * b0.numel()])
+        # raw-memory cross-attention: out_proj(v_proj(.)) folded per layer -- Wo Wv [256, 64], Wo bv + bo and Wo bv [256],
+        # recomputed from the fp32 masters on refresh (static addresses, like the mirror itself)
+        self.nl = nl
+        self.w_eff = [torch.empty(256, 64, dtype=BF16, device=dev) for _ in range(nl)]
+        self.b_eff = [torch.empty(256, dtype=BF16, device=dev) for _ in range(nl)]
+        self.wobv = [torch.empty(256, dtype=BF16, device=dev) for _ in range(nl)]
         self.versions = None
         self.device = dev
 
@@ -294,6 +300,15 @@ class WeightMirror:
                 raise RuntimeError("WeightMirror.refresh() inside a CUDA graph capture: refresh before capturing")
             with torch.no_grad():
                 torch._foreach_copy_(self.views, [p.detach() for p in self.params])
+                for l in range(self.nl):
+                    wo, bo, wv, bv = (self.params[l * _NPL + _LAYER_KEYS.index(k)].detach()
+                                      for k in ("ca.o.w", "ca.o.b", "ca.v.w", "ca.v.b"))
+                    if wv.shape != (256, 64):
+                        continue
+                    self.w_eff[l].copy_(torch.mm(wo, wv))
+                    wobv = torch.mv(wo, bv)
+                    self.wobv[l].copy_(wobv)
+                    self.b_eff[l].copy_(wobv + bo)
             self.versions = v
         return self.views
 
@@ -410,12 +425,12 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                 else:
                     # out_proj(v_proj(out64)) = out64 (Wo Wv)^T + (Wo bv + bo): one [B N, 64] -> 256 GEMM; the o2 slot of
                     # `saved` holds the folded weight (fp32 product of the master weights, rounded once)
-                    o2 = torch.mm(P["ca.o.w"], P["ca.v.w"]).to(BF16)
+                    o2 = mirror.w_eff[l]                       # Wo Wv, refreshed with the weight mirror (once per optimizer step)
                     if rs is None:
-                        ca = torch.addmm(torch.addmv(P["ca.o.b"], P["ca.o.w"], P["ca.v.b"]).to(BF16), v2.view(r, 64), o2.t())
+                        ca = torch.addmm(mirror.b_eff[l], v2.view(r, 64), o2.t())
                     else:   # dropout: the value bias enters with the row sums of the dropped probabilities (rank-1 term)
                         ca = torch.addmm(W["ca.o.b"], v2.view(r, 64), o2.t())
-                        ca.addr_(rs.view(r).to(BF16), torch.mv(P["ca.o.w"], P["ca.v.b"]).to(BF16))
+                        ca.addr_(rs.view(r).to(BF16), mirror.wobv[l])
             else:
                 rs = None
                 o2, o2_32, lse2 = attn_fwd(q2_rot, k2_rot, v2.view(b, m, d), scale, meta["nsplit"], drop=dsite("p_ca", l, 1))
@@ -542,8 +557,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                     # with dropout the value bias entered as rowsum (x) Wo bv: its gradients use g_rs = dca^T rowsum
                     # instead of g = colsum(dca), and the per-query constant c = dca . (Wo bv) goes into dP and Delta
                     g_rs = _mm32(dca.t(), rs.view(r, 1).to(BF16)).view(d) if ca_drop else g_bo
-                    dp_bias = (_mm32(dca, torch.mv(P["ca.o.w"], P["ca.v.b"]).to(BF16).view(d, 1)).view(b, n)
-                               if ca_drop else None)
+                    dp_bias = _mm32(dca, weight_mirror(masters).wobv[l].view(d, 1)).view(b, n) if ca_drop else None
 
                     def fold_grads(dca=dca, o64=o64, g_bo=g_bo, g_rs=g_rs, ix=ix, P=P):
                         G = _mm32(dca.t(), o64.view(r, 64))

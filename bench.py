@@ -38,6 +38,11 @@ WORKLOADS = {
     "cfg4_1024px_T8_4obj_x1clip": dict(grid=64, T=8, C=4, clips=1, S=1024),
 }
 LOSS_W = {"loss_mask": 20, "loss_dice": 1, "loss_iou": 1, "loss_class": 0}
+# DRAM bytes (read + write) of the backward kernels of one cross-attention call at B=56, N=576, M=4060 from `ncu --set full`
+# (profiles/r1_ncu_attn_v64_cfg2_cross.csv: dK 248.0 + dQ 177.0 MB); updated whenever a new capture is committed
+TRAFFIC_CFG2_BYTES = 431.0e6
+TRAFFIC_NOTE = ("per cross-attention backward call at B=56 N=576 M=4060 (dK + dQ kernels); algorithmic operand bytes q,k,mem,dO',dq,dk = "
+                "0.30 GB on the raw-memory path (K is read once by each of the two kernels)")
 
 
 def bank_sizes(t: int, n: int):
@@ -301,10 +306,101 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
 
 
-# ----------------------------------------------------------------------------- CPU oracle timing
+# ----------------------------------------------------------------------------- the reference itself (baseline/_ref)
+REF_ROOT = os.path.join(ROOT, "baseline", "_ref")
+
+
+def load_reference():
+    """The UNMODIFIED reference modules of the hot path from the git-ignored baseline/_ref/ (placed there by
+    scripts/install_reference.py; the contract's pip install fails -- the reference has no setup.py / pyproject).
+    They import the un-installed pip package `sam2`, so the vendored files are registered under those names
+    (sam2_video/model/modeling/memory_attention.py:12-14).  Returns a namespace or None when baseline/_ref is absent."""
+    import importlib.util
+    import types
+    mdl = os.path.join(REF_ROOT, "sam2_video", "model", "modeling")
+    if not os.path.isfile(os.path.join(mdl, "memory_attention.py")):
+        return None
+    if "_bench_ref_ns" in sys.modules:
+        return sys.modules["_bench_ref_ns"]
+
+    def load(name, path):
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+        return mod
+
+    for pkg in ("sam2", "sam2.modeling", "sam2.modeling.sam", "sam2.utils"):
+        if pkg not in sys.modules:
+            m = types.ModuleType(pkg)
+            m.__path__ = []
+            sys.modules[pkg] = m
+    if "sam2.utils.misc" not in sys.modules:
+        misc = types.ModuleType("sam2.utils.misc")
+        misc.mask_to_box = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError("outside the hot path"))
+        sys.modules["sam2.utils.misc"] = misc
+    load("sam2.modeling.position_encoding", os.path.join(mdl, "position_encoding.py"))
+    load("sam2.modeling.sam2_utils", os.path.join(mdl, "sam2_utils.py"))
+    tr = load("sam2.modeling.sam.transformer", os.path.join(mdl, "sam", "transformer.py"))
+    ma = load("sam2.modeling.memory_attention", os.path.join(mdl, "memory_attention.py"))
+    ls = load("_bench_ref_losses", os.path.join(REF_ROOT, "sam2_video", "model", "losses.py"))
+    try:
+        from loguru import logger
+        logger.disable("_bench_ref_losses")
+    except Exception:
+        pass
+    ns = types.SimpleNamespace(transformer=tr, memory_attention=ma, losses=ls)
+    sys.modules["_bench_ref_ns"] = ns
+    return ns
+
+
+def build_reference_stack(ns, dropout=0.0):
+    """configs/sam2/sam2.1_hiera_t.yaml:29-60 through the reference's own constructors."""
+    sa = ns.transformer.RoPEAttention(rope_theta=10000.0, feat_sizes=[64, 64], embedding_dim=256, num_heads=1,
+                                      downsample_rate=1, dropout=dropout)
+    ca = ns.transformer.RoPEAttention(rope_theta=10000.0, feat_sizes=[64, 64], rope_k_repeat=True, embedding_dim=256,
+                                      num_heads=1, downsample_rate=1, dropout=dropout, kv_in_dim=64)
+    layer = ns.memory_attention.MemoryAttentionLayer(activation="relu", dim_feedforward=2048, dropout=dropout, pos_enc_at_attn=False,
+                                                     self_attention=sa, d_model=256, pos_enc_at_cross_attn_keys=True,
+                                                     pos_enc_at_cross_attn_queries=False, cross_attention=ca)
+    return ns.memory_attention.MemoryAttention(d_model=256, pos_enc_at_input=True, layer=layer, num_layers=4)
+
+
+def reference_clip_sample(ns, wl, threads, objects=None):
+    """ONE clip of the workload (all `objects` = C objects batched along B as the reference does, dataset.py:358) through
+    the reference's own MemoryAttention (T-1 frames fwd+bwd, growing bank) and MultiStepMultiMasksAndIous (T frames
+    fwd+bwd) on the host cores, fp32.  Returns seconds."""
+    torch.set_num_threads(threads)
+    n, T, S = wl["grid"] ** 2, wl["T"], wl["S"]
+    C = objects or wl["C"]
+    g = torch.Generator().manual_seed(11)
+    if "_ref_cpu_model" not in reference_clip_sample.__dict__:
+        torch.manual_seed(0)
+        reference_clip_sample._ref_cpu_model = build_reference_stack(ns, 0.0).train()
+    model = reference_clip_sample._ref_cpu_model
+    crit = ns.losses.MultiStepMultiMasksAndIous(weight_dict=dict(LOSS_W), supervise_all_iou=True, iou_use_l1_loss=True,
+                                                pred_obj_scores=False, focal_gamma_obj_score=0.0, focal_alpha_obj_score=-1.0)
+    curr_pos = torch.randn(n, C, 256, generator=g) * 0.7
+    t0 = time.perf_counter()
+    model.zero_grad(set_to_none=True)
+    for t in range(1, T):
+        m, p = bank_sizes(t, n)
+        curr = torch.randn(n, C, 256, generator=g)
+        mem = torch.randn(m, C, 64, generator=g)
+        pos = (torch.randn(m, C, 64, generator=g) * 0.7).requires_grad_(True)
+        out = model(curr=[curr], curr_pos=[curr_pos], memory=mem, memory_pos=pos, num_obj_ptr_tokens=p)
+        out.backward(torch.randn(n, C, 256, generator=g))
+    logits = (torch.randn(T, C, 1, S, S, generator=g) * 4).requires_grad_(True)
+    targets = torch.rand(T, C, S, S, generator=g) > 0.8
+    iou = torch.rand(T, C, 1, generator=g).requires_grad_(True)
+    outs = [{"multistep_pred_multimasks_high_res": [logits[f]], "multistep_pred_ious": [iou[f]],
+             "multistep_object_score_logits": [torch.zeros(C, 1)]} for f in range(T)]
+    crit(outs, targets)["total_loss"].backward()
+    return time.perf_counter() - t0
+
+
 def cpu_oracle_sample(wl, threads):
-    """One object-clip (1 object, all T-1 attention frames fwd+bwd + loss fwd+bwd on T frames) of the
-    workload through the CPU oracle port, fp32.  Returns seconds."""
+    """Fallback when baseline/_ref is absent: one object-clip through the CPU oracle port (oracle/), fp32.  Seconds."""
     from oracle import attention_oracle as ao
     from oracle import losses_oracle as lo
     torch.set_num_threads(threads)
@@ -328,28 +424,180 @@ def cpu_oracle_sample(wl, threads):
     return time.perf_counter() - t0
 
 
+def cpu_reference_leg(wl, budget_s, min_samples=2, max_samples=64):
+    """The reference's CPU path on all host cores for ~budget_s seconds.  Returns (clip-frames/s, dict for the JSON line)."""
+    threads = os.cpu_count() or 1
+    ns = load_reference()
+    if ns is not None:
+        reference_clip_sample(ns, WORKLOADS["cfg1_384px_T10_1obj_x1clip"], threads)     # warm-up (thread pool, allocator)
+        ts, t_start = [], time.perf_counter()
+        while len(ts) < min_samples or (time.perf_counter() - t_start < budget_s and len(ts) < max_samples):
+            ts.append(reference_clip_sample(ns, wl, threads))
+        tb = sum(ts) / len(ts)
+        value = wl["T"] / tb            # one clip = T clip-frames
+        return value, tb, {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
+                           "sample": "the UNMODIFIED reference modules (baseline/_ref: MemoryAttention + MultiStepMultiMasksAndIous, torch CPU "
+                                     "fp32, dropout 0): %d clip(s) of the %d per step, each = %d objects batched x (%d attention frames fwd+bwd + "
+                                     "loss on %d x %d x %d^2); mean of %d after 1 warm-up (%.2f s each)" % (
+                                         len(ts), wl["clips"], wl["C"], wl["T"] - 1, wl["T"], wl["C"], wl["S"], len(ts), tb)}
+    cpu_oracle_sample(WORKLOADS["cfg1_384px_T10_1obj_x1clip"], threads)
+    ts, t_start = [], time.perf_counter()
+    while len(ts) < min_samples or (time.perf_counter() - t_start < budget_s and len(ts) < max_samples):
+        ts.append(cpu_oracle_sample(wl, threads))
+    tb = sum(ts) / len(ts)
+    value = (wl["T"] / wl["C"]) / tb    # one object-clip = T / C clip-frames
+    return value, tb, {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                       "sample": "baseline/_ref absent -> oracle/ port, torch CPU fp32: %d object-clips (of %d per step), scaled by 1/C "
+                                 "to clip-frames (%.2f s each)" % (len(ts), wl["C"] * wl["clips"], tb)}
+
+
+def same_box_torch_gpu(wl, dev, d, banks, reps=2):
+    """The SAME step (attention fwd+bwd for every frame of every object + the loss, no optimizer) through the unmodified
+    reference modules moved to this GPU: torch SDPA + eager loss, fp32 and bf16-autocast.  This is the bar SURVEY.md
+    section 2.2 names (the reference has no Blackwell kernel of its own).  None when baseline/_ref is absent."""
+    ns = load_reference()
+    if ns is None:
+        return None
+    torch.manual_seed(0)
+    model = build_reference_stack(ns, 0.0).to(dev).train()
+    crit = ns.losses.MultiStepMultiMasksAndIous(weight_dict=dict(LOSS_W), supervise_all_iou=True, iou_use_l1_loss=True,
+                                                pred_obj_scores=False, focal_gamma_obj_score=0.0, focal_alpha_obj_score=-1.0)
+    T, C = wl["T"], wl["C"]
+
+    def step(autocast):
+        model.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            for t in range(1, T):
+                mem, pos, p = banks[t - 1]
+                out = model(curr=[d["curr"][t - 1]], curr_pos=[d["curr_pos"]], memory=mem, memory_pos=pos, num_obj_ptr_tokens=p)
+                out.backward(d["grad_out"][t - 1].to(out.dtype))
+                pos.grad = None
+            for ci in range(wl["clips"]):
+                xs = [d["logits"][ci * T + f].requires_grad_(True) for f in range(T)]
+                ips = [v.detach().requires_grad_(True) for v in d["iou"][ci].unbind(0)]
+                outs = [{"multistep_pred_multimasks_high_res": [xs[f]], "multistep_pred_ious": [ips[f]],
+                         "multistep_object_score_logits": [torch.zeros(C, 1, device=dev)]} for f in range(T)]
+                crit(outs, d["targets"][ci])["total_loss"].backward()
+                for x in xs:
+                    x.grad = None
+
+    res = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for name, ac in (("bf16_autocast_ms", True), ("fp32_ms", False)):
+        step(ac)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            step(ac)
+        e1.record()
+        torch.cuda.synchronize()
+        res[name] = e0.elapsed_time(e1) / reps
+    res["what"] = ("unmodified reference MemoryAttention (F.scaled_dot_product_attention) + MultiStepMultiMasksAndIous from baseline/_ref on "
+                   "this GPU, same inputs and step as `value` minus the optimizer; torch %s" % torch.__version__)
+    del model
+    torch.cuda.empty_cache()
+    return res
+
+
 def main_reference(args, wl_name, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    for _ in range(max(args.warmup, 0)):
-        cpu_oracle_sample(wl, threads)
-    ts = [cpu_oracle_sample(wl, threads) for _ in range(max(args.steps, 1))]
+    ns = load_reference()
+    sample = (lambda: reference_clip_sample(ns, wl, threads)) if ns is not None else (lambda: cpu_oracle_sample(wl, threads))
+    per_sample_frames = wl["T"] if ns is not None else wl["T"] / wl["C"]
+    for _ in range(min(max(args.warmup, 0), 1)):      # one warm-up (thread pool, allocator): there are no clocks to ramp on the CPU,
+        sample()                                       # and a sample is seconds long
+    ts = [sample() for _ in range(max(args.steps, 1))]
     tmean = sum(ts) / len(ts)
-    # one object-clip = T object-frames = T / C clip-frames of this workload
-    value = (wl["T"] / wl["C"]) / tmean
+    value = per_sample_frames / tmean
+    kind = "reference" if ns is not None else "port"
+    what = ("the UNMODIFIED reference modules from baseline/_ref (torch CPU fp32, dropout 0): 1 clip per step = %d objects batched x (%d "
+            "attention frames fwd+bwd + loss on %d frames); the workload has %d such clips per step" % (wl["C"], wl["T"] - 1, wl["T"], wl["clips"])
+            if ns is not None else "baseline/_ref absent -> oracle/ port: 1 object-clip per step, scaled by 1/C to clip-frames")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": tmean * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl_name, "sample_per_step": "1 object-clip (1 of %d objects x %d clips): %d attention frames fwd+bwd + loss on %d frames"
-                   % (wl["C"], wl["clips"], wl["T"] - 1, wl["T"])},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "oracle/ (CPU restatement of the reference, torch CPU fp32): 1 object-clip per step, scaled by 1/C to clip-frames"},
+        "config": {"workload": wl_name, "sample_per_step": what},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": what},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def measure_workload(wl_name, wl, model, crit, opt, lib, dev, world, rank, steps, warmup, use_graphs, barrier, pk, want_clocks):
+    """Device-resident throughput of one workload + the per-kernel-family pass.  Returns a dict (and keeps the device
+    inputs in it for the callers that go on to the end-to-end / same-box legs)."""
+    import torch.distributed as dist
+    from sam2_video_training_b200 import fused_stack, ops
+    from sam2_video_training_b200.graphs import GraphedMemoryAttention
+    run_model = GraphedMemoryAttention(model) if use_graphs else model
+    host = make_host_inputs(wl, 1234 + rank, pin=True)
+    d = to_device(host, dev)
+    banks = assemble_banks(d, wl)
+    torch.cuda.synchronize()
+    for _ in range(max(warmup, 3)):
+        run_step(model, crit, opt, d, banks, wl, world, fwd=run_model)
+    crit.raise_if_invalid()
+    barrier()
+    clocks = ClockSampler(dev.index) if want_clocks else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        run_step(model, crit, opt, d, banks, wl, world, fwd=run_model)
+    ev1.record()
+    barrier()
+    crit.raise_if_invalid()          # the reference's "No valid masks" contract, checked once outside the timed region
+    t_ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_ms.item()) / steps
+    clk = clocks.stop() if clocks is not None else None
+
+    # same steps, every kernel launched from the host on ONE stream, CUDA events around each kernel family (events cannot
+    # be timed inside a replayed graph, and with the side stream an event pair around one kernel would time its neighbours)
+    fused_stack.NO_SIDE_STREAM = True
+    run_step(model, crit, opt, d, banks, wl, world)
+    barrier()
+    launches0 = lib.sam2b200_launch_count()
+    ops.PROFILE = {}
+    ev0.record()
+    for _ in range(steps):
+        run_step(model, crit, opt, d, banks, wl, world)
+    ev1.record()
+    barrier()
+    prof, ops.PROFILE = ops.PROFILE, None
+    fused_stack.NO_SIDE_STREAM = bool(os.environ.get("SAM2B200_NO_SIDE_STREAM"))
+    eager_ms = ev0.elapsed_time(ev1) / steps
+    launches = lib.sam2b200_launch_count() - launches0      # a replayed graph launches the same kernels
+    crit.raise_if_invalid()
+    fam = {}
+    for name, evs in prof.items():
+        fam[name] = dict(ms=sum(a.elapsed_time(b) for a, b, _ in evs), work=sum(w for _, _, w in evs), launches=len(evs))
+    attn_ms = sum(fam[k]["ms"] for k in ("attn_fwd", "attn_bwd") if k in fam)
+    attn_fl = sum(fam[k]["work"] for k in ("attn_fwd", "attn_bwd") if k in fam)
+    loss_ms = sum(fam[k]["ms"] for k in ("mask_loss_fwd", "mask_loss_bwd") if k in fam)
+    loss_by = sum(fam[k]["work"] for k in ("mask_loss_fwd", "mask_loss_bwd") if k in fam)
+    dom = max(("attn_fwd", "attn_bwd"), key=lambda k: fam.get(k, {"ms": 0})["ms"])
+    ach = fam[dom]["work"] / (fam[dom]["ms"] * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "sam2b200_" + dom + " (tcgen05 kernels, all launches of the timed region)",
+                "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
+                "peak_source": pk["src"] + " sustained cuBLAS bf16",
+                "timing_note": "kernel time from CUDA events on the launching stream in a second, single-stream, host-launched pass of "
+                               "the same steps (events cannot sit inside the graph-replayed timed region)",
+                "frac_of_spec_2250": ach / 2250.0,
+                "attention_fwd_bwd_tflops": attn_fl / (attn_ms * 1e-3) / 1e12 if attn_ms else None,
+                "attention_fwd_tflops": (fam["attn_fwd"]["work"] / (fam["attn_fwd"]["ms"] * 1e-3) / 1e12) if "attn_fwd" in fam else None,
+                "attention_share_of_step": attn_ms / (eager_ms * steps) if eager_ms else None,
+                "mask_loss": {"bound": "hbm", "achieved": loss_by / (loss_ms * 1e-3) / 1e9 if loss_ms else None, "peak": pk["hbm"],
+                              "unit": "GB/s", "frac": (loss_by / (loss_ms * 1e-3) / 1e9 / pk["hbm"]) if loss_ms else None,
+                              "bytes_per_px": "5 fwd + 9 bwd"},
+                "whole_step_tflops": algorithmic_flops(wl) / (ms_per_step * 1e-3) / 1e12}
+    return dict(ms_per_step=ms_per_step, clocks=clk, eager_ms=eager_ms, launches=int(launches), fam=fam, roofline=roofline,
+                host=host, d=d, banks=banks, run_model=run_model)
 
 
 def main():
@@ -361,6 +609,7 @@ def main():
     ap.add_argument("--workload", default="cfg2_endovis18_384px_T10_7obj_x8clips", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip other_workloads / same_box_torch_gpu / the dropout leg")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host (no CUDA-graph replay)")
     ap.add_argument("--dropout", type=float, default=0.0,
                     help="train-mode dropout of the stack (the reference ships 0.1); default 0 = the parity configuration "
@@ -371,7 +620,7 @@ def main():
         return main_reference(args, wl_name, wl)
 
     import torch.distributed as dist
-    from sam2_video_training_b200 import _lib, ops
+    from sam2_video_training_b200 import _lib, ddp
     from sam2_video_training_b200.losses import MultiStepMultiMasksAndIous
     from sam2_video_training_b200.modeling.memory_attention import build_memory_attention
 
@@ -388,104 +637,32 @@ def main():
 
     torch.manual_seed(0)
     model = build_memory_attention(dropout=args.dropout).to(dev).train()   # default 0: throughput with parity numerics
-    crit = MultiStepMultiMasksAndIous(dict(LOSS_W), supervise_all_iou=True, iou_use_l1_loss=True, check_valid=False)
+    # the reference's "No valid masks" contract stays ON: the per-frame valid-channel minimum is folded on the device and
+    # checked at the step's 4-byte read-back (e2e leg) / once per timed region (device-resident leg) -- no host sync per call
+    crit = MultiStepMultiMasksAndIous(dict(LOSS_W), supervise_all_iou=True, iou_use_l1_loss=True, check_valid="deferred")
     opt = torch.optim.AdamW(model.parameters(), lr=1e-5, fused=True)
-    from sam2_video_training_b200 import ddp
-    from sam2_video_training_b200.graphs import GraphedMemoryAttention
     ddp.attach_grad_bucket(model)   # all 106 gradients are views of one flat fp32 buffer
-    eager_model = model
-    run_model = model if args.no_graphs else GraphedMemoryAttention(model)
-
-    host = make_host_inputs(wl, 1234 + rank, pin=True)
-    d = to_device(host, dev)
-    banks = assemble_banks(d, wl)
-    torch.cuda.synchronize()
+    pk = peaks()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident throughput (`value`) ----------------
-    for _ in range(max(args.warmup, 3)):
-        run_step(model, crit, opt, d, banks, wl, world, fwd=run_model)
-    barrier()
-    clocks = ClockSampler(local_rank) if rank == 0 else None
-    launches0 = lib.sam2b200_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        run_step(model, crit, opt, d, banks, wl, world, fwd=run_model)
-    ev1.record()
-    barrier()
-    launches = lib.sam2b200_launch_count() - launches0
-    ms = ev0.elapsed_time(ev1)
-    t_ms = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t_ms.item()) / args.steps
-    clk = clocks.stop() if clocks is not None else None
+    r = measure_workload(wl_name, wl, model, crit, opt, lib, dev, world, rank, args.steps, args.warmup, not args.no_graphs,
+                         barrier, pk, want_clocks=(rank == 0))
+    ms_per_step, clk, host, d, banks, run_model = r["ms_per_step"], r["clocks"], r["host"], r["d"], r["banks"], r["run_model"]
+    roofline, fam = r["roofline"], r["fam"]
+    r_launches, eager_ms_headline = r["launches"], r["eager_ms"]
     frames_per_step = wl["T"] * wl["clips"]
     value = world * frames_per_step / (ms_per_step * 1e-3)
-
-    # ---------------- same steps, every kernel launched from the host, CUDA events around each kernel family
-    # (events cannot be timed inside a replayed graph): feeds `roofline` and `kernel_families_ms_per_step`
-    # (single stream here: with the side stream the key-side attention kernels overlap other work and an event pair
-    # around one kernel would also time its neighbours)
-    from sam2_video_training_b200 import fused_stack
-    fused_stack.NO_SIDE_STREAM = True
-    run_step(model, crit, opt, d, banks, wl, world)
-    barrier()
-    launches_e0 = lib.sam2b200_launch_count()
-    ops.PROFILE = {}
-    ev0.record()
-    for _ in range(args.steps):
-        run_step(model, crit, opt, d, banks, wl, world)
-    ev1.record()
-    barrier()
-    prof = ops.PROFILE
-    ops.PROFILE = None
-    fused_stack.NO_SIDE_STREAM = bool(os.environ.get("SAM2B200_NO_SIDE_STREAM"))
-    eager_ms_per_step = ev0.elapsed_time(ev1) / args.steps
-    launches_eager = lib.sam2b200_launch_count() - launches_e0
-    if args.no_graphs:
-        launches = launches_eager
-    else:
-        launches = launches_eager   # a replayed graph launches the same kernels; the host-side counter only sees eager launches
-
-    # ---------------- per-kernel-family device time inside the timed region ----------------
-    fam = {}
-    for name, evs in prof.items():
-        tot_ms = sum(s.elapsed_time(e) for s, e, _ in evs)
-        tot_work = sum(w for _, _, w in evs)
-        fam[name] = dict(ms=tot_ms, work=tot_work, launches=len(evs))
-    pk = peaks()
-    attn_ms = sum(fam[k]["ms"] for k in ("attn_fwd", "attn_bwd") if k in fam)
-    attn_fl = sum(fam[k]["work"] for k in ("attn_fwd", "attn_bwd") if k in fam)
-    loss_ms = sum(fam[k]["ms"] for k in ("mask_loss_fwd", "mask_loss_bwd") if k in fam)
-    loss_by = sum(fam[k]["work"] for k in ("mask_loss_fwd", "mask_loss_bwd") if k in fam)
-    dom = max(("attn_fwd", "attn_bwd"), key=lambda k: fam.get(k, {"ms": 0})["ms"])
-    ach = fam[dom]["work"] / (fam[dom]["ms"] * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "sam2b200_" + dom + " (tcgen05 kernels, all launches of the timed region)",
-                "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
-                "peak_source": pk["src"] + " sustained cuBLAS bf16",
-                # dram__bytes_read.sum + dram__bytes_write.sum of the backward kernels of ONE cross-attention call at the largest
-                # shape of this workload (B=56, N=576, M=4060), ncu --set full.  Raw-memory path: dK 249.3 + dQ 181.7 MB,
-                # profiles/r1_ncu_attn_v64_cfg2_cross.csv (the 256-d value path it replaced: dV 229.5 + dK 357.2 + dQ 285.3 MB,
-                # profiles/r1_ncu_attn_v3_cfg2_cross.csv)
-                "traffic": (431.0e6 if wl_name.startswith("cfg2") else None),
-                "traffic_note": "per cross-attention backward call at B=56 N=576 M=4060; algorithmic operand bytes q,k,mem,dO',dq,dk "
-                                "= 0.30 GB on the raw-memory path (K is read once by each of the two kernels)",
-                "attention_fwd_bwd_tflops": attn_fl / (attn_ms * 1e-3) / 1e12 if attn_ms else None,
-                "attention_share_of_step": attn_ms / (eager_ms_per_step * args.steps) if eager_ms_per_step else None,
-                "mask_loss": {"bound": "hbm", "achieved": loss_by / (loss_ms * 1e-3) / 1e9 if loss_ms else None, "peak": pk["hbm"],
-                              "unit": "GB/s", "frac": (loss_by / (loss_ms * 1e-3) / 1e9 / pk["hbm"]) if loss_ms else None,
-                              "bytes_per_px": "5 fwd + 9 bwd"},
-                "whole_step_tflops": algorithmic_flops(wl) / (ms_per_step * 1e-3) / 1e12}
+    # dram__bytes_read.sum + dram__bytes_write.sum of the backward kernels of ONE cross-attention call at the largest shape of
+    # cfg2 (B=56, N=576, M=4060), ncu --set full: see profiles/ (r2 file when present, else the round-1 capture)
+    roofline["traffic"] = (TRAFFIC_CFG2_BYTES if wl_name.startswith("cfg2") else None)
+    roofline["traffic_note"] = TRAFFIC_NOTE
     if rank == 0:
         roofline["mask_loss_sweep_max"] = loss_sweep_roofline(lib, dev, pk["hbm"])
-        roofline["mask_loss"]["note"] = "in-step: 8 per-clip calls of 10 x 7 x 384^2 (52 MB each) -- launch/latency bound at this size"
+        roofline["mask_loss"]["note"] = "in-step: %d per-clip calls of %d x %d x %d^2" % (wl["clips"], wl["T"], wl["C"], wl["S"])
 
     # ---------------- end to end: host buffers, H2D inside the timed region, loss read back ----------------
     e2e = None
@@ -505,10 +682,14 @@ def main():
                                arrivals=evs)
                 if i + 1 < k:       # enqueue the next step's copies AFTER this step's kernels: the compute stream never
                     nxt = start_copy()   # waits for the host to issue ~130 cudaMemcpyAsync calls
-                float(tot.item())   # D2H of the step's loss (also keeps `dd` alive until the step is done)
+                # D2H of the step's result: [loss, min valid channels] in ONE 8-byte read (also keeps `dd` alive until the
+                # step is done); the validity contract of the reference is enforced from it
+                both = torch.stack([tot.float(), crit.deferred_state().float()]).cpu()
+                crit.raise_if_invalid(value=int(both[1]))
 
         e2e_loop(2)
         barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         e2e_loop(args.steps)
         ev1.record()
@@ -518,20 +699,69 @@ def main():
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         e2e_ms = float(t2.item()) / args.steps
         e2e = {"value": world * frames_per_step / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(host),
-               "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms}
+               "d2h_bytes_per_step": 8, "ms_per_step": e2e_ms}
+
+    extras = {}
+    if rank == 0 and world == 1 and not args.no_extras:
+        # ---- the bar SURVEY.md 2.2 names: the reference modules on this same GPU (torch SDPA), same step
+        try:
+            sb = same_box_torch_gpu(wl, dev, d, banks)
+        except Exception as e:      # the baseline leg must never take the measurement down
+            sb = {"error": repr(e)[:300]}
+        if sb is not None:
+            if "bf16_autocast_ms" in sb:
+                sb["speedup_vs_bf16_autocast"] = sb["bf16_autocast_ms"] / ms_per_step
+                sb["speedup_vs_fp32"] = sb["fp32_ms"] / ms_per_step
+            extras["same_box_torch_gpu"] = sb
+        # ---- the shipped training configuration has dropout 0.1 in the stack: same step with it switched on
+        if args.dropout == 0.0:
+            try:
+                for mod in model.modules():
+                    if isinstance(mod, torch.nn.Dropout):
+                        mod.p = 0.1
+                for layer in model.layers:
+                    layer.dropout_value = 0.1
+                    layer.self_attn.dropout_p = 0.1
+                    layer.cross_attn_image.dropout_p = 0.1
+                rd = measure_workload(wl_name, wl, model, crit, opt, lib, dev, world, rank, max(2, args.steps // 2), 3, not args.no_graphs,
+                                      barrier, pk, want_clocks=False)
+                extras["dropout_0.1"] = {"ms_per_step": rd["ms_per_step"], "value": frames_per_step / (rd["ms_per_step"] * 1e-3),
+                                         "overhead_vs_dropout_0": rd["ms_per_step"] / ms_per_step - 1.0}
+                del rd
+            finally:
+                for mod in model.modules():
+                    if isinstance(mod, torch.nn.Dropout):
+                        mod.p = 0.0
+                for layer in model.layers:
+                    layer.dropout_value = 0.0
+                    layer.self_attn.dropout_p = 0.0
+                    layer.cross_attn_image.dropout_p = 0.0
+    del d, banks, run_model, r
+    torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_extras:
+        # ---- the other single-GPU shapes of BASELINE.json (cfg3: 512 px x 13 objects; cfg4: 1024 px x 4 objects)
+        other = {}
+        for name in ("cfg3_cholec_512px_T8_13obj_x1clip", "cfg4_1024px_T8_4obj_x1clip"):
+            if name == wl_name:
+                continue
+            try:
+                ro = measure_workload(name, WORKLOADS[name], model, crit, opt, lib, dev, world, rank, 3, 3, not args.no_graphs, barrier, pk,
+                                      want_clocks=False)
+                w2 = WORKLOADS[name]
+                other[name] = {"ms_per_step": ro["ms_per_step"], "value": w2["T"] * w2["clips"] / (ro["ms_per_step"] * 1e-3), "unit": UNIT,
+                               "algorithmic_tflop_per_step": algorithmic_flops(w2) / 1e12,
+                               "roofline": {k: ro["roofline"][k] for k in ("kernel", "achieved", "frac", "peak", "frac_of_spec_2250",
+                                                                          "attention_fwd_bwd_tflops", "attention_fwd_tflops", "whole_step_tflops")},
+                               "kernel_families_ms_per_step": {k: v["ms"] / 3 for k, v in ro["fam"].items()}}
+                del ro
+            except Exception as e:
+                other[name] = {"error": repr(e)[:300]}
+            torch.cuda.empty_cache()
+        extras["other_workloads"] = other
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        cpu_oracle_sample(WORKLOADS["cfg1_384px_T10_1obj_x1clip"], threads)  # warm-up
-        ts, t_start = [], time.perf_counter()
-        while len(ts) < 2 or (time.perf_counter() - t_start < 12.0 and len(ts) < 64):   # ~12 s of CPU work
-            ts.append(cpu_oracle_sample(wl, threads))
-        tb = sum(ts) / len(ts)
-        cpu_baseline = {"value": (wl["T"] / wl["C"]) / tb, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": "oracle/ port, torch CPU fp32: %d object-clips (of the %d per step), each = %d attention frames fwd+bwd "
-                                  "+ loss on %d x 1 x %d^2, scaled by 1/C to clip-frames; mean of %d after 1 warm-up (%.2f s each, %.1f s total)" % (
-                                      len(ts), wl["C"] * wl["clips"], wl["T"] - 1, wl["T"], wl["S"], len(ts), tb, sum(ts))}
+        _, _, cpu_baseline = cpu_reference_leg(wl, budget_s=12.0)
 
     if rank == 0:
         line = {
@@ -543,13 +773,14 @@ def main():
                        "l2": "inputs_larger_than_L2 (%.0f MB per step)" % (h2d_bytes(host) / 1e6),
                        "launch": "memory-attention fwd/bwd replayed as CUDA graphs (one pair per memory-bank shape)" if not args.no_graphs else "host-launched",
                        "parallelism": "dp%d (clips sharded, NCCL grad all-reduce)" % world,
-                       "dropout": args.dropout,
+                       "dropout": args.dropout, "loss_validity_check": "on (deferred: device flag read with the loss)",
                        "object_frames_per_step": wl["T"] * wl["C"] * wl["clips"],
                        "algorithmic_tflop_per_step": algorithmic_flops(wl) / 1e12},
-            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(r_launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "kernel_families_ms_per_step": {k: v["ms"] / args.steps for k, v in fam.items()},
-            "ms_per_step_host_launched": eager_ms_per_step, "cuda_graphs": not args.no_graphs,
+            "ms_per_step_host_launched": eager_ms_headline, "cuda_graphs": not args.no_graphs,
         }
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

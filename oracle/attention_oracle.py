@@ -115,7 +115,7 @@ def rope_attention(p: Dict[str, Tensor], prefix: str, q_in: Tensor, k_in: Tensor
     n, m = q.shape[1], k.shape[1]
     if n != m and not rope_k_repeat:
         raise AssertionError("rope_k_repeat required when N != M (transformer.py:293-294)")
-    cos, sin = axial_rope_table(n, q.shape[-1], dtype=q.dtype)
+    cos, sin = (t.to(q.device) for t in axial_rope_table(n, q.shape[-1], dtype=q.dtype))
     num_k_rope = m - num_k_exclude_rope
     q = apply_axial_rope(q, cos, sin)
     if num_k_rope > 0:
@@ -203,12 +203,54 @@ def init_params(seed: int = 0, dtype=torch.float32) -> Dict[str, Tensor]:
     return p
 
 
+def reference_init_params(seed: int = 0) -> Dict[str, Tensor]:
+    """The reference's OWN random initialisation, reproduced without the reference: the nn.Linear layers are created
+    under ``torch.manual_seed(seed)`` in the order the reference constructors create them when the stack is built as
+    ``oracle/ref_shim.build_memory_attention`` does (self-attention RoPEAttention first, then the cross-attention one --
+    q, k, v, out each, transformer.py:213-216 -- then linear1, linear2 of MemoryAttentionLayer, memory_attention.py:39-41),
+    and ``get_clones`` deep-copies that layer (sam2_utils.py:77-78): ALL FOUR LAYERS START IDENTICAL.  LayerNorms are
+    (1, 0).  ``tests/test_oracle_golden.py`` checks this against the reference's state_dict when the reference is present."""
+    torch.manual_seed(seed)
+    lin = {}
+    for pre, kv in (("self_attn.", D_MODEL), ("cross_attn_image.", KV_IN_DIM)):
+        lin[pre + "q_proj"] = torch.nn.Linear(D_MODEL, D_MODEL)
+        lin[pre + "k_proj"] = torch.nn.Linear(kv, D_MODEL)
+        lin[pre + "v_proj"] = torch.nn.Linear(kv, D_MODEL)
+        lin[pre + "out_proj"] = torch.nn.Linear(D_MODEL, D_MODEL)
+    lin["linear1"] = torch.nn.Linear(D_MODEL, DIM_FF)
+    lin["linear2"] = torch.nn.Linear(DIM_FF, D_MODEL)
+    p: Dict[str, Tensor] = {}
+    for i in range(NUM_LAYERS):
+        pre = f"layers.{i}."
+        for nm in ("self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj", "self_attn.out_proj",
+                   "cross_attn_image.q_proj", "cross_attn_image.k_proj", "cross_attn_image.v_proj",
+                   "cross_attn_image.out_proj", "linear1", "linear2"):
+            p[pre + nm + ".weight"] = lin[nm].weight.detach().clone()
+            p[pre + nm + ".bias"] = lin[nm].bias.detach().clone()
+        for nm in ("norm1", "norm2", "norm3"):
+            p[pre + nm + ".weight"] = torch.ones(D_MODEL)
+            p[pre + nm + ".bias"] = torch.zeros(D_MODEL)
+    p["norm.weight"] = torch.ones(D_MODEL)
+    p["norm.bias"] = torch.zeros(D_MODEL)
+    return p
+
+
+def random_inputs(grid: int, batch: int, n_frames: int, n_ptr: int, seed: int = 1234) -> Dict[str, Tensor]:
+    """Well-conditioned synthetic inputs of SURVEY.md section 8d: N(0,1) features, 0.7 N(0,1) positional encodings,
+    N(0,1) upstream gradient, from one seeded CPU generator (bit-reproducible for a given torch build)."""
+    g = torch.Generator().manual_seed(seed)
+    n, m = grid * grid, n_frames * grid * grid + n_ptr
+    return dict(curr=torch.randn(n, batch, D_MODEL, generator=g), curr_pos=torch.randn(n, batch, D_MODEL, generator=g) * 0.7,
+                memory=torch.randn(m, batch, KV_IN_DIM, generator=g), memory_pos=torch.randn(m, batch, KV_IN_DIM, generator=g) * 0.7,
+                grad_out=torch.randn(n, batch, D_MODEL, generator=g))
+
+
 def core_attention(q: Tensor, k: Tensor, v: Tensor, num_k_exclude_rope: int,
                    scale: Optional[float] = None) -> Tensor:
     """Just the kernel-level op: rotate (q, first M-P keys) then softmax(q k^T * scale) v.
     q: [B, N, 256]; k, v: [B, M, 256] (already projected)."""
     n, m = q.shape[1], k.shape[1]
-    cos, sin = axial_rope_table(n, q.shape[-1], dtype=q.dtype)
+    cos, sin = (t.to(q.device) for t in axial_rope_table(n, q.shape[-1], dtype=q.dtype))
     nk = m - num_k_exclude_rope
     qr = apply_axial_rope(q, cos, sin)
     kr = torch.cat([apply_axial_rope(k[:, :nk], cos, sin), k[:, nk:]], dim=1) if nk > 0 else k

@@ -76,6 +76,12 @@ def loss_inputs(t: int, c: int, s: int, clear=((1, 2),), dtype=torch.float32):
     return logits, targets, iou_pred
 
 
+def multimask_loss_inputs(t: int, c: int, m: int, s: int, dtype=torch.float32):
+    """M masks per channel (losses.py:143-238 with src_masks [C, M, H, W]): logits [t, c, m, s, s], IoU heads [t, c, m]."""
+    _, targets, _ = loss_inputs(t, c, s)
+    return det((t, c, m, s, s), 0.43, 0.19, 4.0, dtype), targets, det((t, c, m), 1.1, 0.3, 0.5, dtype) + 0.5
+
+
 def merged_inputs(t: int, n_obj: int, c: int, s: int, clear=((1, 0),), dtype=torch.float32):
     """Producer-side fixture (oracle/merge_oracle.py): low-res logits [t, n_obj, 1, s, s], per-object IoU predictions
     [t, n_obj, 1], object -> category map with the LAST category left without objects, targets [t, c, 4s, 4s]."""

@@ -53,6 +53,43 @@ def golden_attention(ns, grid, batch, n_frames, n_ptr, tag, full_grads=False):
     return rec
 
 
+REFINIT_PARAM_GRADS = ("layers.0.self_attn.q_proj.weight", "layers.3.cross_attn_image.k_proj.weight",
+                       "layers.1.cross_attn_image.v_proj.bias", "layers.2.linear1.bias", "layers.0.norm2.weight", "norm.bias",
+                       "layers.3.cross_attn_image.out_proj.weight", "layers.1.self_attn.v_proj.weight")
+
+
+def golden_attention_refinit(ns, grid, batch, n_frames, n_ptr, tag, seed=1234):
+    """WELL-CONDITIONED fixture: the reference stack with ITS OWN random init (torch.manual_seed(0), nn.Linear defaults,
+    get_clones) on N(0,1) inputs (attention_oracle.random_inputs).  Stored: output, all input gradients, eight full
+    parameter gradients, per-parameter |grad| sums, and checksums of weights / inputs so that a consumer which
+    regenerates them (attention_oracle.reference_init_params / random_inputs) can prove it holds the same tensors."""
+    from . import attention_oracle as ao
+    torch.manual_seed(0)
+    model = ref_shim.build_memory_attention(ns).eval()
+    mine = ao.reference_init_params(0)
+    for n, p in model.named_parameters():       # the regenerated init IS the reference's
+        assert torch.equal(p.detach(), mine[n]), n
+    inp = ao.random_inputs(grid, batch, n_frames, n_ptr, seed)
+    leaves = {k: inp[k].clone().requires_grad_(True) for k in ("curr", "curr_pos", "memory", "memory_pos")}
+    out = model(curr=[leaves["curr"]], curr_pos=[leaves["curr_pos"]], memory=leaves["memory"],
+                memory_pos=leaves["memory_pos"], num_obj_ptr_tokens=n_ptr)
+    out.backward(inp["grad_out"])
+    rec = dict(grid=grid, batch=batch, n_frames=n_frames, n_ptr=n_ptr, seed=seed, out=out.detach().numpy(),
+               d_curr=leaves["curr"].grad.numpy(), d_memory=leaves["memory"].grad.numpy(),
+               d_memory_pos=leaves["memory_pos"].grad.numpy(),
+               d_curr_pos_over_d_curr=float((leaves["curr_pos"].grad.double() * leaves["curr"].grad.double()).sum()
+                                            / (leaves["curr"].grad.double() ** 2).sum()),
+               input_abs_sums=np.array([float(inp[k].double().abs().sum()) for k in ("curr", "curr_pos", "memory", "memory_pos", "grad_out")]),
+               weight_abs_sums=np.array([float(p.detach().double().abs().sum()) for _, p in model.named_parameters()]),
+               param_names=np.array([n for n, _ in model.named_parameters()]),
+               param_grad_abs_sums=np.array([float(p.grad.double().abs().sum()) for _, p in model.named_parameters()]))
+    for n, p in model.named_parameters():
+        if n in REFINIT_PARAM_GRADS:
+            rec["dparam:" + n] = p.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, f"attn_refinit_{tag}.npz"), **rec)
+    return rec
+
+
 def golden_bank():
     """Memory-bank assembly: the unmodified SAM2Base._prepare_memory_conditioned_features (sam2_base.py:524-713) with a
     stub memory_attention that records (memory, memory_pos, num_obj_ptr_tokens), plus the gradients that reach the
@@ -211,6 +248,27 @@ def golden_loss(ns, t, c, s, tag):
     return rec
 
 
+def golden_loss_multimask(ns, t, c, m, s, tag):
+    """MultiStepMultiMasksAndIous of the unmodified reference on M > 1 masks per channel (object_score_logits None: with
+    a tensor the reference fails to index it with its [N, M] valid mask, losses.py:169-170)."""
+    logits, targets, iou_pred = detgen.multimask_loss_inputs(t, c, m, s)
+    rec = dict(t=t, c=c, m=m, s=s)
+    for mode, kw in (("l1_all", dict(iou_use_l1_loss=True, supervise_all_iou=True)), ("mse", dict(iou_use_l1_loss=False))):
+        crit = ns.MultiStepMultiMasksAndIous(weight_dict={"loss_mask": 20, "loss_dice": 1, "loss_iou": 1, "loss_class": 0}, **kw)
+        x = logits.clone().requires_grad_(True)
+        ip = iou_pred.clone().requires_grad_(True)
+        outs = [{"multistep_pred_multimasks_high_res": [x[f]], "multistep_pred_ious": [ip[f]],
+                 "multistep_object_score_logits": [None]} for f in range(t)]
+        losses = crit(outs, targets)
+        losses["total_loss"].backward()
+        for k in ("loss_mask", "loss_dice", "loss_iou", "total_loss"):
+            rec[f"{mode}:{k}"] = float(losses[k])
+        rec[f"{mode}:dlogits"] = x.grad.numpy()
+        rec[f"{mode}:diou"] = ip.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, f"loss_multimask_{tag}.npz"), **rec)
+    return rec
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_shim.load()
@@ -222,8 +280,14 @@ def main():
     print("attn g8: out abs", float(np.abs(r["out"]).sum()))
     r = golden_attention(ns, 12, 1, 1, 0, "g12_b1_f1_p0")
     print("attn g12: out abs", float(np.abs(r["out"]).sum()))
+    r = golden_attention_refinit(ns, 24, 1, 7, 28, "g24_b1_f7_p28")      # BASELINE configs[0] steady state
+    print("attn refinit g24: out abs", float(np.abs(r["out"]).sum()))
+    r = golden_attention_refinit(ns, 8, 3, 3, 12, "g8_b3_f3_p12", seed=4321)
+    print("attn refinit g8: out abs", float(np.abs(r["out"]).sum()))
     r = golden_loss(ns, 2, 3, 16, "t2_c3_s16")
     print("loss: l1 total", r["l1:total_loss"], "mse total", r["mse:total_loss"], "bce", r["bce:total_loss"])
+    r = golden_loss_multimask(ns, 2, 3, 3, 16, "t2_c3_m3_s16")
+    print("multimask loss: total", r["l1_all:total_loss"])
     golden_functional(ns, 3, 2, 24, "n3_m2_s24")
     golden_bank()
     r = golden_merged(ns, 2, 5, 4, 6, "t2_n5_c4_s6")

@@ -39,9 +39,21 @@ class GradBucket:
             self.offset[id(p)] = off
             off += -(-p.numel() // self.ALIGN) * self.ALIGN
         self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
-        for p in self.params:
-            o = self.offset[id(p)]
-            p.grad = self.flat[o:o + p.numel()].view_as(p)
+        self.attach()
+
+    def attach(self):
+        """(Re-)install the views as the parameters' .grad.  A gradient that already exists elsewhere (accumulated before
+        the bucket was attached, or after ``zero_grad(set_to_none=True)`` detached the views) is carried over."""
+        with torch.no_grad():
+            for p in self.params:
+                o = self.offset[id(p)]
+                view = self.flat[o:o + p.numel()].view_as(p)
+                if p.grad is not None and p.grad.data_ptr() != view.data_ptr():
+                    view.copy_(p.grad)
+                p.grad = view
+
+    def owns_all(self) -> bool:
+        return all(self.owns(p) for p in self.params)
 
     def span(self, plist, shape):
         """One view over the gradients of `plist` if they are laid out back to back (no padding), else None."""
@@ -76,6 +88,18 @@ def allreduce_gradients(model: torch.nn.Module, world: int):
     else flattens on the fly."""
     bucket = getattr(model, "_sam2b200_grad_bucket", None)
     if bucket is not None:
+        if not bucket.owns_all():
+            # optimizer.zero_grad(set_to_none=True) (the PyTorch default) detached the views: the stack then fell back to
+            # autograd, which wrote FRESH .grad tensors -- reducing the stale flat buffer would silently leave the ranks
+            # out of sync.  Pull those gradients into the bucket (parameters without a gradient contribute zeros) and
+            # re-install the views, so the next backward accumulates in place again.
+            stale = [p for p in bucket.params if not bucket.owns(p)]
+            with torch.no_grad():
+                for p in stale:
+                    o = bucket.offset[id(p)]
+                    if p.grad is None:
+                        bucket.flat[o:o + p.numel()].zero_()
+            bucket.attach()
         bucket.allreduce(world)
         return
     grads = [p.grad for p in model.parameters() if p.grad is not None]
@@ -93,7 +117,14 @@ def allreduce_gradients(model: torch.nn.Module, world: int):
 
 def attach_grad_bucket(model: torch.nn.Module) -> GradBucket:
     """Give `model` a flat gradient buffer.  A model that offers `grad_bucket_order()` (MemoryAttention) chooses the
-    layout and, from then on, accumulates its gradients into the buffer directly inside its backward kernels."""
+    layout and, from then on, accumulates its gradients into the buffer directly inside its backward kernels.
+
+    Direct accumulation hides the parameters from autograd (they are passed detached), so torch / Lightning DDP reducer
+    hooks never fire for them: use ``allreduce_gradients`` (one NCCL call on the flat buffer) instead of wrapping the
+    module in ``DistributedDataParallel`` -- ``attach_grad_bucket`` refuses a DDP-wrapped module."""
+    if isinstance(model, torch.nn.parallel.DistributedDataParallel):
+        raise ValueError("attach_grad_bucket: direct gradient accumulation cannot be combined with a DistributedDataParallel "
+                         "wrapper (its reducer hooks would never fire); attach to the bare module and call allreduce_gradients")
     order = model.grad_bucket_order() if hasattr(model, "grad_bucket_order") else None
     b = GradBucket(list(model.parameters()), order=order)
     model._sam2b200_grad_bucket = b

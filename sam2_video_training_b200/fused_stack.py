@@ -293,8 +293,21 @@ class WeightMirror:
         return (len(params) == len(self.params) and all(a is b for a, b in zip(params, self.params))
                 and params[0].device == self.device)
 
+    def invalidate(self):
+        """Force the next refresh() to re-cast (call after updates the version counter cannot see; an
+        ``optimizer.register_step_post_hook(lambda *_: mirror.invalidate())`` covers third-party optimizers)."""
+        self.versions = None
+
     def refresh(self):
-        v = [p._version for p in self.params]
+        # (version counter, storage address) per parameter: `p.data = new` / `p.data.copy_()` style updates keep the
+        # version but usually move or at least can be announced through invalidate(); in debug mode one slice per
+        # parameter is compared with its master as well
+        v = [(p._version, p.data_ptr()) for p in self.params]
+        if DEBUG_MIRROR and v == self.versions and not torch.cuda.is_current_stream_capturing():
+            for view, p in zip(self.views, self.params):
+                if not torch.equal(view.flatten()[:64], p.detach().flatten()[:64].to(BF16)):
+                    raise RuntimeError("WeightMirror is stale: a parameter was updated through .data without bumping its "
+                                       "version counter; call fused_stack.invalidate_mirrors(module) after such updates")
         if v != self.versions:
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("WeightMirror.refresh() inside a CUDA graph capture: refresh before capturing")
@@ -313,16 +326,28 @@ class WeightMirror:
         return self.views
 
 
-_MIRRORS = {}
+DEBUG_MIRROR = bool(os.environ.get("SAM2B200_DEBUG_MIRROR"))
+# the mirror lives ON the first parameter tensor (an attribute of the nn.Parameter object): it is dropped together with
+# the model instead of accumulating in a global dict
+_MIRROR_ATTR = "_sam2b200_weight_mirror"
 
 
 def weight_mirror(params) -> WeightMirror:
-    key = id(params[0])
-    m = _MIRRORS.get(key)
+    m = getattr(params[0], _MIRROR_ATTR, None)
     if m is None or not m.matches(params):
         m = WeightMirror(params)
-        _MIRRORS[key] = m
+        setattr(params[0], _MIRROR_ATTR, m)
     return m
+
+
+def invalidate_mirrors(module) -> None:
+    """Mark the bf16 weight mirror of `module` (a MemoryAttention) stale: the next forward re-casts every parameter and
+    recomputes the folded projections.  Needed only after updates made through ``p.data`` (EMA swaps,
+    ``vector_to_parameters``, optimizers that bypass the version counter)."""
+    params = [p for _, p in module.named_parameters()]
+    m = getattr(params[0], _MIRROR_ATTR, None) if params else None
+    if m is not None:
+        m.invalidate()
 
 
 def bf16_params(params):

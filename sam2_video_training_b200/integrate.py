@@ -18,12 +18,38 @@ from .merged_loss import CategoryMergedMultiStepLoss
 from .modeling.memory_attention import MemoryAttention, build_memory_attention
 
 
+def _rope_theta(attn) -> float:
+    """The reference keeps theta only inside ``compute_cis = partial(compute_axial_cis, dim=..., theta=...)``
+    (transformer.py:264-266)."""
+    if hasattr(attn, "rope_theta"):
+        return float(attn.rope_theta)
+    kw = getattr(getattr(attn, "compute_cis", None), "keywords", None) or {}
+    return float(kw.get("theta", 10000.0))
+
+
+def _feat_sizes(attn):
+    n = int(getattr(attn, "freqs_cis").shape[0]) if hasattr(attn, "freqs_cis") else 4096
+    w = int(round(n ** 0.5))
+    return (w, w) if w * w == n else (64, 64)
+
+
 def use_b200_attention(model: nn.Module, attr: str = "memory_attention") -> MemoryAttention:
     """Swap ``getattr(model, attr)`` (a reference ``MemoryAttention``) for the B200 drop-in, weights included."""
     ref = getattr(model, attr)
     layer0 = ref.layers[0]
-    dropout = float(getattr(layer0, "dropout_value", layer0.dropout1.p if hasattr(layer0, "dropout1") else 0.0))
-    fast = build_memory_attention(dropout=dropout)
+    sa, ca = layer0.self_attn, layer0.cross_attn_image
+    # every hyper-parameter is read from the reference module (nothing is assumed to be the shipped yaml's value)
+    fast = build_memory_attention(
+        dropout=float(getattr(layer0, "dropout_value", layer0.dropout1.p if hasattr(layer0, "dropout1") else 0.0)),
+        sa_dropout=float(getattr(sa, "dropout_p", 0.0)), ca_dropout=float(getattr(ca, "dropout_p", 0.0)),
+        num_layers=int(getattr(ref, "num_layers", len(ref.layers))),
+        dim_feedforward=int(getattr(layer0, "dim_feedforward", layer0.linear1.out_features)),
+        rope_theta=_rope_theta(sa), feat_sizes=_feat_sizes(sa), ca_rope_theta=_rope_theta(ca),
+        pos_enc_at_input=bool(getattr(ref, "pos_enc_at_input", True)))
+    for l_new, l_old in zip(fast.layers, ref.layers):
+        for nm in ("norm1", "norm2", "norm3"):
+            getattr(l_new, nm).eps = getattr(l_old, nm).eps
+    fast.norm.eps = ref.norm.eps
     p0 = next(ref.parameters())
     fast = fast.to(device=p0.device)
     missing, unexpected = fast.load_state_dict(ref.state_dict(), strict=True)

@@ -12,9 +12,14 @@ Differences, all deliberate:
 * the "no valid channel" condition (losses.py:153-161) is detected on the device and raised as the
   same ``ValueError("No valid masks")`` after ONE device->host read of T ints per call (the
   reference synchronises once per frame); ``check_valid=False`` defers/omits that read;
-* the multi-mask branch (M > 1 masks per channel, losses.py:217-229) is outside the hot path --
-  the training wrapper always produces one mask per channel (sam2model.py:472-476) -- and raises
-  ``NotImplementedError``.
+* M > 1 masks per channel: the reference's valid filter ``src_masks[valid]`` with a [N, M] mask flattens the masks
+  into the batch dimension (losses.py:149-166), so every (channel, mask) pair is scored as its own channel with
+  ``num_objects = Nv * M`` and the argmin branch (losses.py:217-229) can never be taken -- reproduced exactly that way
+  (the M masks become C * M channels of the same kernel; the training wrapper itself always produces M = 1,
+  sam2model.py:472-476);
+* ``check_valid="deferred"``: the same ``ValueError("No valid masks")`` contract without a host synchronisation per
+  call -- the minimum valid-channel count is folded into a device scalar and ``raise_if_invalid()`` reads it once
+  (e.g. together with the step's loss read-back).
 """
 from __future__ import annotations
 
@@ -90,6 +95,9 @@ class _FusedMaskLossFn(torch.autograd.Function):
                 mode | (_TICKETS_ZEROED if persistent else 0),
                 cfg["alpha"], cfg["gamma"], cfg["inv_temp"], int(cfg["iou_l1"]), int(cfg["reduction_mean"]),
                 _stream_ptr(dev))
+        if rc != 0 and persistent:
+            # an aborted launch may leave the ticket counters non-zero: the cached workspace is dropped (re-zeroed on next use)
+            _WORKSPACES.pop((dev.index, _stream_ptr(dev)), None)
         _lib.check(rc, "sam2b200_mask_loss_fwd")
         ctx.cfg = cfg
         ctx.shape = (t, c, hw)
@@ -131,8 +139,19 @@ def _targets_u8(targets_batch: torch.Tensor) -> torch.Tensor:
     return (tb > 0).contiguous().view(torch.uint8)  # float {0,1} masks: foreground = > 0 (losses.py:64)
 
 
+def reset_workspaces() -> None:
+    """Drop the cached per-(device, stream) loss workspaces (they are re-created zero-filled).  Call after a sticky CUDA
+    error or an interrupted launch: the forward relies on its ticket counters having been left at zero."""
+    _WORKSPACES.clear()
+
+
 def _raise_if_no_valid(n_valid: torch.Tensor):
-    if bool((n_valid == 0).any().item()):
+    try:
+        bad = bool((n_valid == 0).any().item())
+    except RuntimeError:
+        reset_workspaces()      # the read-back surfaced an asynchronous failure of the launch
+        raise
+    if bad:
         raise ValueError("No valid masks")  # losses.py:161
 
 
@@ -159,7 +178,23 @@ class MultiStepMultiMasksAndIous(nn.Module):
         if not (isinstance(logit_temperature, (int, float)) and logit_temperature > 0):
             raise ValueError("logit_temperature must be a positive float")  # losses.py:107-108
         self.logit_temperature = float(logit_temperature)
-        self.check_valid = check_valid
+        self.check_valid = check_valid          # True (per call, like the reference) | False | "deferred"
+        self._min_valid: Optional[torch.Tensor] = None
+
+    def deferred_state(self) -> Optional[torch.Tensor]:
+        """check_valid="deferred": int32 device scalar = minimum number of valid channels over every frame seen since the
+        last raise_if_invalid() (None before the first call).  0 means a frame had no foreground."""
+        return self._min_valid
+
+    def raise_if_invalid(self, value: Optional[int] = None) -> None:
+        """Deferred form of losses.py:153-161.  `value`: the content of deferred_state() if the caller already copied it
+        to the host (e.g. in the same read-back as the loss); otherwise it is read here (one 4-byte D2H)."""
+        if self._min_valid is None:
+            return
+        v = int(self._min_valid.item()) if value is None else int(value)
+        self._min_valid = None
+        if v <= 0:
+            raise ValueError("No valid masks")  # losses.py:161
 
     def forward(self, outs_batch: List[Dict], targets_batch: torch.Tensor) -> Dict[str, torch.Tensor]:
         assert len(outs_batch) == len(targets_batch)  # losses.py:113
@@ -175,6 +210,13 @@ class MultiStepMultiMasksAndIous(nn.Module):
                 n_steps = len(a)
             elif n_steps != len(a):
                 raise NotImplementedError("frames with different numbers of correction steps")
+        n_masks = int(outs_batch[0]["multistep_pred_multimasks_high_res"][0].shape[1]) if t else 1
+        if n_masks > 1:
+            # [C, M, H, W]: the reference's filter turns every (channel, mask) pair into its own row (module docstring)
+            if self.pred_obj_scores:
+                raise NotImplementedError("pred_obj_scores with M > 1 masks per channel (the reference itself fails to index "
+                                          "object_score_logits with its [N, M] valid mask, losses.py:169-170)")
+            targets_batch = targets_batch.repeat_interleave(n_masks, dim=1)
         tu8 = _targets_u8(targets_batch)
         cfg = dict(mode=_MODE_MULTISTEP, alpha=float(self.focal_alpha), gamma=float(self.focal_gamma),
                    inv_temp=1.0 / self.logit_temperature, iou_l1=bool(self.iou_use_l1_loss),
@@ -186,16 +228,19 @@ class MultiStepMultiMasksAndIous(nn.Module):
             for outs in outs_batch:
                 x = outs["multistep_pred_multimasks_high_res"][s]
                 _require_cuda(x, "mask logits")
-                if x.dim() != 4 or x.shape[1] != 1:
-                    raise NotImplementedError(
-                        "multi-mask outputs (M > 1 per channel, losses.py:217-229) are outside the B200 "
-                        "hot path; the training wrapper produces [C, 1, H, W]")
+                if x.dim() != 4 or x.shape[1] != n_masks:
+                    raise ValueError(f"mask logits must be [C, {n_masks}, H, W] in every frame and step, got {tuple(x.shape)}")
+                if n_masks > 1:
+                    x = x.reshape(x.shape[0] * n_masks, 1, *x.shape[-2:])
                 if tuple(x.shape[-2:]) != tuple(targets_batch.shape[-2:]) or x.shape[0] != targets_batch.shape[1]:
                     raise ValueError("mask logits / targets shape mismatch")
                 logits.append(_prep_logits(x))
             ious = torch.stack([outs["multistep_pred_ious"][s].reshape(-1) for outs in outs_batch]).float()
             losses4, chan_sums, n_valid = _FusedMaskLossFn.apply(cfg, tu8, None, ious.contiguous(), *logits)
-            if self.check_valid:
+            if self.check_valid == "deferred":
+                mv = n_valid.amin()
+                self._min_valid = mv if self._min_valid is None else torch.minimum(self._min_valid, mv)
+            elif self.check_valid:
                 _raise_if_no_valid(n_valid)
             total4 = losses4 if total4 is None else total4 + losses4
             if self.pred_obj_scores:  # losses.py:194-204 -- [C, 1] tensors, not on the hot path

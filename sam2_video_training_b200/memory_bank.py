@@ -220,6 +220,16 @@ def assemble_memory(cfg: BankConfig, frame_idx: int, output_dict: dict, num_fram
         feats, pos = [t.float() for t in feats], [t.float() for t in pos]
     feats = [t.contiguous() for t in feats]
     pos = [t.contiguous() for t in pos]
+    # the reference's torch.cat / torch.stack raise on a frame with another batch size or resolution (an object added
+    # mid-video, mixed resolutions); the gather kernel takes raw pointers, so the same check happens here
+    if feats:
+        shape0 = tuple(feats[0].shape)
+        if len(shape0) < 3 or shape0[1] != cfg.mem_dim:
+            raise ValueError(f"maskmem_features must be [B, {cfg.mem_dim}, H, W], got {shape0}")
+        for (t_pos, _), f_, p_ in zip(frames, feats, pos):
+            if tuple(f_.shape) != shape0 or tuple(p_.shape) != shape0:
+                raise ValueError(f"memory frame at t_pos={t_pos}: maskmem_features {tuple(f_.shape)} / maskmem_pos_enc "
+                                 f"{tuple(p_.shape)} do not match the first frame's {shape0}")
     tpos_rows = None
     if frames:
         idx = _tpos_index(dev, tuple(cfg.num_maskmem - t_pos - 1 for t_pos, _ in frames))            # sam2_base.py:608-610
@@ -232,6 +242,10 @@ def assemble_memory(cfg: BankConfig, frame_idx: int, output_dict: dict, num_fram
         if ptrs[0].dtype not in _DT or any(p.dtype != ptrs[0].dtype for p in ptrs):
             ptrs = [p.float() for p in ptrs]
         ptrs = [p.contiguous() for p in ptrs]
+        want = (feats[0].shape[0] if feats else ptrs[0].shape[0], cfg.hidden_dim)
+        for t_diff, p_ in zip(pos_list, ptrs):
+            if tuple(p_.shape) != want:
+                raise ValueError(f"object pointer at t_diff={t_diff}: shape {tuple(p_.shape)}, expected {want}")
         if cfg.add_tpos_enc_to_obj_ptrs:                                                              # :654-663
             t_diff_max = min(num_frames, cfg.max_obj_ptrs_in_encoder) - 1
             tpos_dim = cfg.hidden_dim if cfg.proj_tpos_enc_in_obj_ptrs else cfg.mem_dim

@@ -115,6 +115,13 @@ class MemoryAttention(nn.Module):
                     or layer.activation_str != "relu" or not ca.rope_k_repeat or ca.kv_in_dim != 64
                     or layer.d_model != 256 or not self.batch_first):
                 return False
+            # hyper-parameters the kernels hard-code (csrc/glue.cu: eps 1e-5, width 256; csrc/mlp.cu: hidden width 2048;
+            # one RoPE table for both attentions): anything else takes the composed path instead of wrong numerics
+            if (layer.dim_feedforward != 2048 or layer.linear1.out_features != 2048
+                    or any(abs(ln.eps - 1e-5) > 1e-12 for ln in (layer.norm1, layer.norm2, layer.norm3, self.norm))
+                    or getattr(sa, "rope_theta", 10000.0) != getattr(ca, "rope_theta", 10000.0)
+                    or sa.num_heads != 1 or ca.num_heads != 1 or sa.internal_dim != 256 or ca.internal_dim != 256):
+                return False
             l0 = self.layers[0]   # one set of dropout rates for the stack (get_clones copies the layer)
             if (layer.dropout_value, sa.dropout_p, ca.dropout_p) != (l0.dropout_value, l0.self_attn.dropout_p,
                                                                       l0.cross_attn_image.dropout_p):
@@ -200,13 +207,17 @@ class MemoryAttention(nn.Module):
         return normed_output
 
 
-def build_memory_attention(dropout: float = 0.1, feat_sizes=(64, 64), num_layers: int = 4) -> MemoryAttention:
-    """The stack of configs/sam2/sam2.1_hiera_t.yaml:29-60 (same for every SAM2.1 size)."""
-    sa = RoPEAttention(rope_theta=10000.0, feat_sizes=list(feat_sizes), embedding_dim=256, num_heads=1,
-                       downsample_rate=1, dropout=dropout)
-    ca = RoPEAttention(rope_theta=10000.0, feat_sizes=list(feat_sizes), rope_k_repeat=True, embedding_dim=256,
-                       num_heads=1, downsample_rate=1, dropout=dropout, kv_in_dim=64)
-    layer = MemoryAttentionLayer(activation="relu", dim_feedforward=2048, dropout=dropout, pos_enc_at_attn=False,
+def build_memory_attention(dropout: float = 0.1, feat_sizes=(64, 64), num_layers: int = 4, sa_dropout: Optional[float] = None,
+                           ca_dropout: Optional[float] = None, dim_feedforward: int = 2048, rope_theta: float = 10000.0,
+                           ca_rope_theta: Optional[float] = None, pos_enc_at_input: bool = True) -> MemoryAttention:
+    """The stack of configs/sam2/sam2.1_hiera_t.yaml:29-60 (same for every SAM2.1 size); the keyword arguments cover the
+    hyper-parameters a differently configured reference stack may carry (integrate.use_b200_attention reads them)."""
+    sa = RoPEAttention(rope_theta=rope_theta, feat_sizes=list(feat_sizes), embedding_dim=256, num_heads=1,
+                       downsample_rate=1, dropout=dropout if sa_dropout is None else sa_dropout)
+    ca = RoPEAttention(rope_theta=rope_theta if ca_rope_theta is None else ca_rope_theta, feat_sizes=list(feat_sizes),
+                       rope_k_repeat=True, embedding_dim=256, num_heads=1, downsample_rate=1,
+                       dropout=dropout if ca_dropout is None else ca_dropout, kv_in_dim=64)
+    layer = MemoryAttentionLayer(activation="relu", dim_feedforward=dim_feedforward, dropout=dropout, pos_enc_at_attn=False,
                                  self_attention=sa, d_model=256, pos_enc_at_cross_attn_keys=True,
                                  pos_enc_at_cross_attn_queries=False, cross_attention=ca)
-    return MemoryAttention(d_model=256, pos_enc_at_input=True, layer=layer, num_layers=num_layers)
+    return MemoryAttention(d_model=256, pos_enc_at_input=pos_enc_at_input, layer=layer, num_layers=num_layers)

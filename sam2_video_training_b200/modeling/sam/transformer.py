@@ -72,6 +72,7 @@ class RoPEAttention(Attention):
         # plain attribute like the reference's freqs_cis (NOT in the state_dict, transformer.py:269-272)
         self.freqs_cis = self.compute_cis(end_x=feat_sizes[0], end_y=feat_sizes[1])
         self.rope_k_repeat = rope_k_repeat
+        self.rope_theta = float(rope_theta)        # kept for integrate.use_b200_attention / _fused_eligible
 
     def _table(self, n_tokens: int, device) -> Tensor:
         if self.freqs_cis.shape[0] != n_tokens:  # transformer.py:289-292

@@ -142,10 +142,48 @@ def test_memory_attention_vs_reference_golden(dev, golden_dir, tag, fused):
     assert rel_l2(out, torch.from_numpy(g["out"])) < ATTN_REL_TOL
     for k in ("curr", "curr_pos", "memory", "memory_pos"):
         assert cosine(leaves[k].grad, torch.from_numpy(g["d_" + k])) > 0.995, k
+    # parameter gradients: asserted at the north-star 0.999 on the WELL-CONDITIONED reference fixtures below
+    # (test_memory_attention_vs_reference_refinit_golden); on these analytic ones only finiteness
+    for _, p in model.named_parameters():
+        assert torch.isfinite(p.grad).all()
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("tag", ["g24_b1_f7_p28", "g8_b3_f3_p12"])
+def test_memory_attention_vs_reference_refinit_golden(dev, golden_dir, tag, fused):
+    """North-star tolerances against the UNMODIFIED REFERENCE itself (not the oracle): the reference stack with its own
+    random init (torch.manual_seed(0)) on N(0,1) inputs, BASELINE.json configs[0] steady-state shape (24x24 tokens, 7
+    memory frames + 28 pointer tokens) and a ragged 8x8 / 3-object case -- oracle/make_golden.py::
+    golden_attention_refinit.  Weights and inputs are regenerated and proven identical by checksum."""
+    from sam2_video_training_b200.modeling.memory_attention import build_memory_attention
+    g = np.load(os.path.join(golden_dir, f"attn_refinit_{tag}.npz"))
+    grid, batch, nf, nptr, seed = (int(g[k]) for k in ("grid", "batch", "n_frames", "n_ptr", "seed"))
+    params = ao.reference_init_params(0)
+    for n, s_ in zip([str(n) for n in g["param_names"]], g["weight_abs_sums"]):
+        assert abs(float(params[n].double().abs().sum()) - s_) <= 1e-9 * max(s_, 1.0), n
+    inp = ao.random_inputs(grid, batch, nf, nptr, seed)
+    for k, s_ in zip(("curr", "curr_pos", "memory", "memory_pos", "grad_out"), g["input_abs_sums"]):
+        assert abs(float(inp[k].double().abs().sum()) - s_) <= 1e-9 * s_, k
+    model = build_memory_attention().to(dev).eval()
+    model.use_fused_stack = fused
+    _load_params(model, params)
+    leaves = {k: inp[k].to(dev).requires_grad_(True) for k in ("curr", "curr_pos", "memory", "memory_pos")}
+    out = model(curr=[leaves["curr"]], curr_pos=[leaves["curr_pos"]], memory=leaves["memory"],
+                memory_pos=leaves["memory_pos"], num_obj_ptr_tokens=nptr)
+    out.backward(inp["grad_out"].to(dev))
+    torch.cuda.synchronize()
+    assert rel_l2(out, torch.from_numpy(g["out"])) < ATTN_REL_TOL
+    for k in ("curr", "memory", "memory_pos"):
+        assert cosine(leaves[k].grad, torch.from_numpy(g["d_" + k])) > GRAD_COS_TOL, (k, cosine(leaves[k].grad, torch.from_numpy(g["d_" + k])))
+    assert cosine(leaves["curr_pos"].grad, torch.from_numpy(0.1 * g["d_curr"])) > GRAD_COS_TOL
+    named = dict(model.named_parameters())
     for key in g.files:
         if key.startswith("dparam:"):
-            pg = dict(model.named_parameters())[key[7:]].grad
-            assert cosine(pg, torch.from_numpy(g[key])) > 0.75, key   # ill-conditioned, see docstring
+            c = cosine(named[key[7:]].grad, torch.from_numpy(g[key]))
+            assert c > GRAD_COS_TOL, (key, c)
+    for n, s_ in zip([str(n) for n in g["param_names"]], g["param_grad_abs_sums"]):
+        mine = float(named[n].grad.double().abs().sum())
+        assert abs(mine - s_) <= 5e-2 * max(abs(s_), 1e-3), (n, mine, s_)
 
 
 @pytest.mark.parametrize("fused", [True, False])
@@ -649,6 +687,53 @@ def test_multistep_loss_vs_oracle_real_shapes(dev, t, c, s):
     assert rel_l2(x.grad, x64.grad) < 1e-4
     assert cosine(x.grad, x64.grad) > 0.99999
     assert rel_l2(ip.grad, i64.grad) < 1e-5
+
+
+def test_multistep_loss_multimask_vs_reference_golden(dev, golden_dir):
+    """M = 3 masks per channel: the reference's valid filter flattens (channel, mask) pairs into rows (losses.py:149-166),
+    reproduced on the same fused kernels; against the unmodified reference (tests/golden/loss_multimask_*.npz)."""
+    from sam2_video_training_b200.losses import MultiStepMultiMasksAndIous
+    g = np.load(os.path.join(golden_dir, "loss_multimask_t2_c3_m3_s16.npz"))
+    t, c, m, s = (int(g[k]) for k in ("t", "c", "m", "s"))
+    logits, targets, iou_pred = detgen.multimask_loss_inputs(t, c, m, s)
+    for mode, kw in (("l1_all", dict(iou_use_l1_loss=True, supervise_all_iou=True)), ("mse", dict(iou_use_l1_loss=False))):
+        crit = MultiStepMultiMasksAndIous(dict(W_FOCAL), **kw)
+        xs = [logits[f].to(dev).requires_grad_(True) for f in range(t)]
+        ips = [iou_pred[f].to(dev).requires_grad_(True) for f in range(t)]
+        outs = [{"multistep_pred_multimasks_high_res": [xs[f]], "multistep_pred_ious": [ips[f]],
+                 "multistep_object_score_logits": [None]} for f in range(t)]
+        got = crit(outs, targets.to(dev))
+        got["total_loss"].backward()
+        for k in ("loss_mask", "loss_dice", "loss_iou", "total_loss"):
+            want = float(g[f"{mode}:{k}"])
+            assert abs(float(got[k]) - want) <= 1e-5 * max(abs(want), 1.0), (mode, k, float(got[k]), want)
+        assert rel_l2(torch.stack([x.grad for x in xs]), torch.from_numpy(g[f"{mode}:dlogits"])) < 1e-5
+        assert rel_l2(torch.stack([x.grad for x in ips]), torch.from_numpy(g[f"{mode}:diou"])) < 1e-5
+
+
+def test_loss_deferred_validity_check(dev):
+    """check_valid="deferred": no host synchronisation per call; the "No valid masks" contract (losses.py:153-161) is
+    enforced by raise_if_invalid(), which reads one device scalar -- or takes the value the caller already read."""
+    from sam2_video_training_b200.losses import MultiStepMultiMasksAndIous
+    crit = MultiStepMultiMasksAndIous(dict(W_FOCAL), check_valid="deferred")
+    x = torch.randn(2, 3, 1, 32, 32, device=dev)
+    tg = torch.rand(2, 3, 32, 32, device=dev) > 0.5
+    mk = lambda: [{"multistep_pred_multimasks_high_res": [x[f]], "multistep_pred_ious": [torch.rand(3, 1, device=dev)],
+                   "multistep_object_score_logits": [None]} for f in range(2)]
+    crit(mk(), tg)
+    assert int(crit.deferred_state().item()) == 3
+    crit.raise_if_invalid()                      # fine, and resets
+    assert crit.deferred_state() is None
+    crit(mk(), tg)
+    bad = tg.clone()
+    bad[1] = False                               # frame 1 has no foreground at all
+    crit(mk(), bad)                              # does not raise here ...
+    crit(mk(), tg)
+    with pytest.raises(ValueError, match="No valid masks"):
+        crit.raise_if_invalid()                  # ... but here, whatever came after
+    crit(mk(), bad)
+    with pytest.raises(ValueError, match="No valid masks"):
+        crit.raise_if_invalid(value=int(crit.deferred_state().item()))
 
 
 def test_loss_no_valid_masks_raises(dev):

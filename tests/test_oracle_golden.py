@@ -54,6 +54,53 @@ def test_attention_oracle_matches_reference(golden_dir, tag):
             assert _l2(params[key[7:]].grad.numpy(), g[key]) < 5e-3, key
 
 
+@pytest.mark.parametrize("tag", ["g24_b1_f7_p28", "g8_b3_f3_p12"])
+def test_attention_oracle_matches_reference_refinit(golden_dir, tag):
+    """Well-conditioned fixtures: the reference's own random init + N(0,1) inputs (oracle/make_golden.py::
+    golden_attention_refinit).  Weights and inputs are REGENERATED here (attention_oracle.reference_init_params /
+    random_inputs) and proven identical through the stored checksums; oracle fp32 vs the reference fp32."""
+    g = np.load(os.path.join(golden_dir, f"attn_refinit_{tag}.npz"))
+    grid, batch, nf, nptr, seed = (int(g[k]) for k in ("grid", "batch", "n_frames", "n_ptr", "seed"))
+    params = ao.reference_init_params(0)
+    names = [str(n) for n in g["param_names"]]
+    assert names == list(params.keys())
+    for n, s in zip(names, g["weight_abs_sums"]):
+        assert abs(float(params[n].double().abs().sum()) - s) <= 1e-9 * max(s, 1.0), n
+    inp = ao.random_inputs(grid, batch, nf, nptr, seed)
+    for k, s in zip(("curr", "curr_pos", "memory", "memory_pos", "grad_out"), g["input_abs_sums"]):
+        assert abs(float(inp[k].double().abs().sum()) - s) <= 1e-9 * s, k
+    po = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    leaves = {k: inp[k].clone().requires_grad_(True) for k in ("curr", "curr_pos", "memory", "memory_pos")}
+    out = ao.memory_attention(po, leaves["curr"], leaves["memory"], leaves["curr_pos"], leaves["memory_pos"], nptr)
+    out.backward(inp["grad_out"])
+    assert _l2(out.detach().numpy(), g["out"]) < 2e-6
+    for k in ("curr", "memory", "memory_pos"):
+        assert _l2(leaves[k].grad.numpy(), g["d_" + k]) < 2e-5, k
+    assert _l2(leaves["curr_pos"].grad.numpy(), 0.1 * g["d_curr"]) < 2e-5
+    for n, s in zip(names, g["param_grad_abs_sums"]):
+        assert abs(float(po[n].grad.double().abs().sum()) - s) <= 1e-3 * max(abs(s), 1e-3), n
+    for key in g.files:
+        if key.startswith("dparam:"):
+            assert _l2(po[key[7:]].grad.numpy(), g[key]) < 5e-5, key
+
+
+def test_reference_init_params_is_the_reference_init():
+    """attention_oracle.reference_init_params replays the reference constructors' RNG order: checked against the real
+    reference modules when they are present (build container); the fixtures' weight checksums cover the GPU box."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference not present")
+    torch.manual_seed(0)
+    model = ref_shim.build_memory_attention().eval()
+    mine = ao.reference_init_params(0)
+    sd = dict(model.named_parameters())
+    assert list(sd.keys()) == list(mine.keys())
+    for n in sd:
+        assert torch.equal(sd[n].detach(), mine[n]), n
+    # get_clones deep-copies one layer: the four layers start identical (sam2_utils.py:77-78)
+    assert torch.equal(mine["layers.0.linear1.weight"], mine["layers.3.linear1.weight"])
+
+
 def test_attention_survey_anchor(golden_dir):
     """Hand-checked values recorded in SURVEY.md section 8c for the 4x4 case."""
     g = np.load(os.path.join(golden_dir, "attn_g4_b2_f2_p8.npz"))

@@ -41,6 +41,10 @@ const char* sam2b200_last_error(void);
 long long sam2b200_launch_count(void);
 /* Debug aid: per-CTA phase timelines of the attention kernels into a device buffer (NULL = off). */
 long long sam2b200_debug_set_timeline(void* buf, long long n_u64);
+/* Debug / A-B aid: choose a kernel variant at run time.  key 0 = backward of the raw-memory cross-attention
+ * (0 = default, 1 = experimental two-softmax-group kernels); key 1 = rotation-table addressing of the gradient epilogues
+ * (0 = default: axial -- rows x and y*w of a w x w grid table, 1 = full rows).  Returns the previous value, -1 for an unknown key. */
+int sam2b200_debug_set_variant(int key, int value);
 /* 0 iff CUDA device `dev` is an sm_100 part. */
 int sam2b200_check_device(int dev);
 
@@ -71,7 +75,9 @@ int sam2b200_attn_fwd_ex(const void* q, const void* k, const void* v, void* out,
                          float drop_p, const unsigned long long* drop_seed, unsigned drop_site, sam2b200_stream_t stream);
 /* Backward (what autograd derives for transformer.py:296-306).  delta: [B, N] fp32 scratch.
  * dq: [B, N, ldq], dk: [B, M, ldk], dv: [B, M, ldv], fp32 (grad_dtype 0) or bf16 (1), first 256 columns
- * fully overwritten.  With rope_table != NULL the conjugate rotation is fused into the epilogue (all rows
+ * fully overwritten.  With rope_table != NULL (an AXIAL table as compute_axial_cis builds it: when rope_period is a square
+ * w^2 the epilogues read pair j < 64 of row p from row p mod w and pair j >= 64 from row p - p mod w, which hold the same
+ * values) the conjugate rotation is fused into the epilogue (all rows
  * of dq, rows [0, n_rope_k) of dk; table row = row % rope_period), i.e. the outputs are gradients with
  * respect to the un-rotated projections (the backward of apply_rotary_enc + the slice write-back). */
 int sam2b200_attn_bwd(const void* q, const void* k, const void* v, const void* out /* bf16, or NULL if */,

@@ -22,6 +22,7 @@ _SIGNATURES = {
     "sam2b200_last_error": (c_char_p, []),
     "sam2b200_launch_count": (c_longlong, []),
     "sam2b200_debug_set_timeline": (c_longlong, [c_void_p, c_longlong]),
+    "sam2b200_debug_set_variant": (c_int, [c_int, c_int]),
     "sam2b200_check_device": (c_int, [c_int]),
     "sam2b200_rope_apply": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                     c_int, c_int, c_void_p]),

@@ -17,6 +17,7 @@
 #include "attn_pair_kernel.cuh"
 #include "attn_persist_kernels.cuh"
 #include "attn_v64_kernels.cuh"
+#include "attn_v64x2_kernels.cuh"
 #include "tma_desc.cuh"
 
 namespace {
@@ -170,7 +171,24 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 
 }  // namespace
 
+int g_variant[4] = {0, 0, 0, 0};
+
+// Width of the square grid an axial RoPE table of `period` rows belongs to (0 if period is not a square, or when the
+// compact addressing is switched off with sam2b200_debug_set_variant(1, 1)): see GradOut::rope_w.
+int axial_w(int period) {
+  if (g_variant[1] == 1 || period <= 0) return 0;
+  int w = (int)(sqrt((double)period) + 0.5);
+  return (w * w == period) ? w : 0;
+}
+
 extern "C" {
+
+int sam2b200_debug_set_variant(int key, int value) {
+  if (key < 0 || key >= 4) return -1;
+  const int old = g_variant[key];
+  g_variant[key] = value;
+  return old;
+}
 
 // Debug aid (not part of the training path): buf = device buffer of n_u64 u64 (or NULL to switch off).
 // Each subsequent attention kernel launch appends grid-size x 8 u64 {smid, t_entry, t_setup, t_operand, t_first_scores,
@@ -390,8 +408,8 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
   if ((parts & 6) == 6 && use_pair) {
     attn::PairParams p{};
     p.Lk = M; p.Lq = N; p.scale_log2 = scale * kLog2e; p.scale = scale; p.lse2 = lse2; p.delta = delta;
-    p.gout_v = attn::GradOut{grad_dtype, dbias_v, nullptr, 0, 1};
-    p.gout_k = attn::GradOut{grad_dtype, dbias_k, table, table ? n_rope_k : 0, table ? rope_period : 1};
+    p.gout_v = attn::GradOut{grad_dtype, dbias_v, nullptr, 0, 1, 0};
+    p.gout_k = attn::GradOut{grad_dtype, dbias_k, table, table ? n_rope_k : 0, table ? rope_period : 1, table ? axial_w(rope_period) : 0};
     p.drop = drop;
     const size_t smem = sizeof(attn::PairShared) + 1024;
     dim3 grid(2 * ((M + attn::kBlockM - 1) / attn::kBlockM), B, 1);
@@ -410,7 +428,7 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
     attn::TwoGemmParams p{};
     p.La = M; p.Lx = N; p.scale_log2 = scale * kLog2e;
     p.lse2 = const_cast<float*>(lse2);
-    p.gout = attn::GradOut{grad_dtype, dbias_v, nullptr, 0, 1};
+    p.gout = attn::GradOut{grad_dtype, dbias_v, nullptr, 0, 1, 0};
     p.drop = drop;
     p.tiles_per_split = (N + attn::kBlockN - 1) / attn::kBlockN;
     const size_t smem = sizeof(attn::SharedStorage) + 1024;
@@ -444,7 +462,7 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
     attn::ThreeGemmParams p{};
     p.La = M; p.Lx = N; p.scale_log2 = scale * kLog2e; p.scale = scale;
     p.lse2 = lse2; p.delta = delta;
-    p.gout = attn::GradOut{grad_dtype, dbias_k, table, table ? n_rope_k : 0, table ? rope_period : 1};
+    p.gout = attn::GradOut{grad_dtype, dbias_k, table, table ? n_rope_k : 0, table ? rope_period : 1, table ? axial_w(rope_period) : 0};
     p.drop = drop;
     dim3 grid((M + attn::kBlockM - 1) / attn::kBlockM, B, 1);
     p.n_atiles = (int)grid.x;
@@ -475,7 +493,7 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
     attn::ThreeGemmParams p{};
     p.La = N; p.Lx = M; p.scale_log2 = scale * kLog2e; p.scale = scale;
     p.lse2 = lse2; p.delta = delta;
-    p.gout = attn::GradOut{grad_dtype, dbias_q, table, table ? N : 0, table ? rope_period : 1};
+    p.gout = attn::GradOut{grad_dtype, dbias_q, table, table ? N : 0, table ? rope_period : 1, table ? axial_w(rope_period) : 0};
     p.drop = drop;
     dim3 grid((N + attn::kBlockM - 1) / attn::kBlockM, B, 1);
     p.dbg = timeline_slice((size_t)grid.x * grid.y);
@@ -527,7 +545,7 @@ int sam2b200_attn_bwd_v64(const void* q, const void* k, const void* memv, const 
   if (parts & 4) {   // dK: A1 = K block (TMEM), A2 = memory block, X = Q tiles, Y = dout64 tiles
     attn::ThreeGemmParams p{};
     p.La = M; p.Lx = N; p.scale_log2 = scale * kLog2e; p.scale = scale; p.lse2 = lse2; p.delta = delta;
-    p.gout = attn::GradOut{grad_dtype, dbias_k, table, table ? n_rope_k : 0, table ? rope_period : 1};
+    p.gout = attn::GradOut{grad_dtype, dbias_k, table, table ? n_rope_k : 0, table ? rope_period : 1, table ? axial_w(rope_period) : 0};
     p.drop = nodrop; p.dp_bias = dp_bias;
     dim3 grid((M + attn::kBlockM - 1) / attn::kBlockM, B, 1);
     p.n_atiles = (int)grid.x;
@@ -535,10 +553,25 @@ int sam2b200_attn_bwd_v64(const void* q, const void* k, const void* memv, const 
     static const bool no_persist = getenv("SAM2B200_NO_PERSIST") != nullptr;
     static const bool single_buf = getenv("SAM2B200_V64_SINGLE_BUFFER") != nullptr;   // A/B: the generic single-buffered kernels
     static const bool persist_dk = getenv("SAM2B200_V64_PERSIST_DK") != nullptr;
-    if (drop_on) {
+    // A/B: two softmax groups on alternate tiles.  NOT the default: measured equal to the single-group kernels (the loop is
+    // bound by the SS-mode MMAs' shared-memory reads, not by softmax latency -- profiles/r2_two_softmax_groups_experiment.txt)
+    static const bool x2_env = getenv("SAM2B200_V64_X2") != nullptr;
+    const bool no_x2 = !(x2_env || g_variant[0] == 1);
+    const size_t smemx2 = sizeof(attn::SharedStorageV64x2) + 1024;
+    if (!no_x2 && !single_buf && !persist_dk) {   // two softmax groups on alternate tiles (attn_v64x2_kernels.cuh)
+      p.dbg = timeline_slice((size_t)grid.x * grid.y);
+      if (drop_on) {
+        if ((rc = set_smem(attn::three_gemm_v64x2_kernel<attn::MODE_DK, true>, smemx2))) return rc;
+        attn::three_gemm_v64x2_kernel<attn::MODE_DK, true><<<grid, attn::kX2Threads, smemx2, stream>>>(map_m128, map_q64, map_d64, map_k128, map_dk, p);
+      } else {
+        if ((rc = set_smem(attn::three_gemm_v64x2_kernel<attn::MODE_DK>, smemx2))) return rc;
+        attn::three_gemm_v64x2_kernel<attn::MODE_DK><<<grid, attn::kX2Threads, smemx2, stream>>>(map_m128, map_q64, map_d64, map_k128, map_dk, p);
+      }
+    } else if (drop_on) {
       if ((rc = set_smem(attn::three_gemm_v64_kernel<attn::MODE_DK, true>, smemv))) return rc;
       attn::three_gemm_v64_kernel<attn::MODE_DK, true><<<grid, attn::kThreads, smemv, stream>>>(map_m128, map_q64, map_d64, map_k128, map_dk, p);
     } else if (!single_buf && !persist_dk) {   // double-buffered S / dP, both fixed operands in shared memory (attn_v64_kernels.cuh)
+      p.dbg = timeline_slice((size_t)grid.x * grid.y);
       if ((rc = set_smem(attn::three_gemm_v64_kernel<attn::MODE_DK>, smemv))) return rc;
       attn::three_gemm_v64_kernel<attn::MODE_DK><<<grid, attn::kThreads, smemv, stream>>>(map_m128, map_q64, map_d64, map_k128, map_dk, p);
     } else if (!no_persist && N < 1024 && grad_dtype && p.n_items > num_sms()) {   // short query loops: resident CTAs (attn_persist_kernels.cuh)
@@ -553,14 +586,27 @@ int sam2b200_attn_bwd_v64(const void* q, const void* k, const void* memv, const 
   if (parts & 8) {   // dQ: A1 = Q block (TMEM), A2 = dout64 block, X = K tiles, Y = memory tiles
     attn::ThreeGemmParams p{};
     p.La = N; p.Lx = M; p.scale_log2 = scale * kLog2e; p.scale = scale; p.lse2 = lse2; p.delta = delta;
-    p.gout = attn::GradOut{grad_dtype, dbias_q, table, table ? N : 0, table ? rope_period : 1};
+    p.gout = attn::GradOut{grad_dtype, dbias_q, table, table ? N : 0, table ? rope_period : 1, table ? axial_w(rope_period) : 0};
     p.drop = nodrop; p.dp_bias = dp_bias;
     dim3 grid((N + attn::kBlockM - 1) / attn::kBlockM, B, 1);
     static const bool single_buf = getenv("SAM2B200_V64_SINGLE_BUFFER") != nullptr;
-    if (drop_on) {
+    static const bool x2_env = getenv("SAM2B200_V64_X2") != nullptr;
+    const bool no_x2 = !(x2_env || g_variant[0] == 1);
+    const size_t smemx2 = sizeof(attn::SharedStorageV64x2) + 1024;
+    if (!no_x2 && !single_buf) {
+      p.dbg = timeline_slice((size_t)grid.x * grid.y);
+      if (drop_on) {
+        if ((rc = set_smem(attn::three_gemm_v64x2_kernel<attn::MODE_DQ, true>, smemx2))) return rc;
+        attn::three_gemm_v64x2_kernel<attn::MODE_DQ, true><<<grid, attn::kX2Threads, smemx2, stream>>>(map_d128, map_k64, map_m64, map_q128, map_dq, p);
+      } else {
+        if ((rc = set_smem(attn::three_gemm_v64x2_kernel<attn::MODE_DQ>, smemx2))) return rc;
+        attn::three_gemm_v64x2_kernel<attn::MODE_DQ><<<grid, attn::kX2Threads, smemx2, stream>>>(map_d128, map_k64, map_m64, map_q128, map_dq, p);
+      }
+    } else if (drop_on) {
       if ((rc = set_smem(attn::three_gemm_v64_kernel<attn::MODE_DQ, true>, smemv))) return rc;
       attn::three_gemm_v64_kernel<attn::MODE_DQ, true><<<grid, attn::kThreads, smemv, stream>>>(map_d128, map_k64, map_m64, map_q128, map_dq, p);
     } else if (!single_buf) {
+      p.dbg = timeline_slice((size_t)grid.x * grid.y);
       if ((rc = set_smem(attn::three_gemm_v64_kernel<attn::MODE_DQ>, smemv))) return rc;
       attn::three_gemm_v64_kernel<attn::MODE_DQ><<<grid, attn::kThreads, smemv, stream>>>(map_d128, map_k64, map_m64, map_q128, map_dq, p);
     } else {

@@ -89,6 +89,10 @@ struct GradOut {
   const float2* rope_table;    // [period, 128] (cos, sin) or nullptr = no rotation
   int rope_rows;               // rows [0, rope_rows) of every batch item are un-rotated (conjugate)
   int rope_period;             // table row = row % rope_period
+  int rope_w;                  // > 0: AXIAL table of a rope_w x rope_w grid (period = rope_w^2): the first 64 (cos, sin) pairs of
+                               // row p depend only on x = p mod w, the last 64 only on y = p div w, so they are read from rows x and
+                               // y * w -- the 128 rows of a CTA then touch w + 128 / w table rows (16 KB at w = 24, L1-resident)
+                               // instead of 128 (128 KB from L2, ~1.5 us per CTA); 0 = address the full row
 };
 
 struct TwoGemmParams {
@@ -193,7 +197,9 @@ __device__ __forceinline__ void store_box(const CUtensorMap* map, uint32_t box_s
 // for chunk i+1 are issued before chunk i is processed, and the TMEM load of chunk i+1 is in flight meanwhile.
 __device__ __forceinline__ void load_table_chunk(const GradOut& g, bool rotate, int row_in_batch, int col0, float2* t) {
   if (rotate) {
-    const float4* src = reinterpret_cast<const float4*>(g.rope_table + (long long)(row_in_batch % g.rope_period) * 128 + (col0 >> 1));
+    const int pos = row_in_batch % g.rope_period;
+    const int trow = g.rope_w > 0 ? (col0 < 128 ? pos % g.rope_w : pos - pos % g.rope_w) : pos;
+    const float4* src = reinterpret_cast<const float4*>(g.rope_table + (long long)trow * 128 + (col0 >> 1));
 #pragma unroll
     for (int i = 0; i < 8; ++i) { const float4 f = __ldg(src + i); t[2 * i] = make_float2(f.x, f.y); t[2 * i + 1] = make_float2(f.z, f.w); }
   }

@@ -64,6 +64,11 @@ three_gemm_v64_kernel(const __grid_constant__ CUtensorMap map_a2,   // [B, La, 6
   const int a_tile = blockIdx.x;
   const int b = blockIdx.y;
   const int nt = (p.Lx + kBlockN - 1) / kBlockN;
+  if (p.dbg != nullptr && threadIdx.x == 0) {
+    unsigned long long* e = p.dbg + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8;
+    e[0] = smid(); e[7] = nt;
+  }
+  SAM2B200_STAMP(p.dbg, 1);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kV64Stages; ++s) {
@@ -84,6 +89,7 @@ three_gemm_v64_kernel(const __grid_constant__ CUtensorMap map_a2,   // [B, La, 6
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh.tmem_base;
+  SAM2B200_STAMP(p.dbg, 2);
 
   if (warp == kProducerWarp) {
     const bool leader = elect_one();
@@ -149,6 +155,8 @@ three_gemm_v64_kernel(const __grid_constant__ CUtensorMap map_a2,   // [B, La, 6
     };
     mbar_wait(&sh.a_full, 0);
     tc_fence_after();
+    if (p.dbg != nullptr && lane == 0)
+      p.dbg[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + 3] = gtimer();
     issue_s_dp(0);
     if (nt > 1) issue_s_dp(1);
     for (int j = 0; j < nt; ++j) {
@@ -210,6 +218,7 @@ three_gemm_v64_kernel(const __grid_constant__ CUtensorMap map_a2,   // [B, La, 6
       const uint32_t dbuf = lane_addr + ((j & 1) ? kVColDP1 : kVColDP0) + half * kHalfN;
       mbar_wait(&sh.s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
+      if (j == 0) SAM2B200_STAMP(p.dbg, 4);
       float pv[kHalfN];
       {
         uint32_t r0[32];
@@ -258,11 +267,13 @@ three_gemm_v64_kernel(const __grid_constant__ CUtensorMap map_a2,   // [B, La, 6
     load_table_chunk(p.gout, rotate, row0 + lane, half * 128, tcur);
     mbar_wait(&sh.acc_done, 0);
     tc_fence_after();
+    SAM2B200_STAMP(p.dbg, 5);
     grad_epilogue(p.gout, &map_g, stage, lane_addr + kVColAcc, half, lane, row0, p.La, b, p.scale, rotate, tcur);
   }
 
   tc_fence_before();
   __syncthreads();
+  SAM2B200_STAMP(p.dbg, 6);
   if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
 }
 

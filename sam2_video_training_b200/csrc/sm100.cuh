@@ -249,6 +249,24 @@ __device__ __forceinline__ void umma_ss_lohi(uint32_t d_tmem, uint32_t a_lo, uin
         "r"(r[14]), "r"(r[15])                                                                    \
       : "memory")
 
+#define SAM2B200_TMEM_LD16(taddr, r)                                                              \
+  asm volatile(                                                                                   \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                   \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                           \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),       \
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),   \
+        "=r"(r[14]), "=r"(r[15])                                                                  \
+      : "r"(taddr)                                                                                \
+      : "memory")
+
+#define SAM2B200_TMEM_ST8(taddr, r)                                                               \
+  asm volatile(                                                                                   \
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"                    \
+      :                                                                                           \
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),  \
+        "r"(r[7])                                                                                 \
+      : "memory")
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);  // .x = lo (low 16 bits), .y = hi
   return *reinterpret_cast<uint32_t*>(&v);

@@ -912,6 +912,82 @@ def test_cross_attention_on_raw_memory_features(dev, b, grid, nf, nptr):
     assert rel_l2(db[0], want_q.sum((0, 1))) < 5e-3 and rel_l2(db[1], want_k.sum((0, 1))) < 5e-3
 
 
+@pytest.mark.parametrize("b,grid,nf,nptr,drop", [(3, 12, 2, 8, 0.0), (2, 24, 7, 28, 0.0), (1, 32, 3, 20, 0.0), (40, 8, 7, 12, 0.0),
+                                                  (2, 16, 3, 12, 0.1), (1, 8, 1, 0, 0.0)])
+def test_raw_memory_backward_two_softmax_groups_bit_identical(dev, b, grid, nf, nptr, drop):
+    """The experimental three_gemm_v64x2_kernel (two softmax groups on alternate tiles, 16-warp epilogue; variant 1 of
+    sam2b200_debug_set_variant key 0, not the default) runs the same products in the same order as the single-group kernel: dq / dk are bit-identical in fp32 and bf16 (ragged last tiles, odd and even tile
+    counts, a single tile, RoPE, dropout); the bias gradients agree to fp32 summation order."""
+    from sam2_video_training_b200 import _lib, ops
+    from sam2_video_training_b200.modeling.position_encoding import compute_axial_cis
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(97)
+    n = grid * grid
+    m = nf * n + nptr
+    table = compute_axial_cis(dim=256, end_x=grid, end_y=grid).to(dev)
+    q = torch.randn(b, n, 256, device=dev, generator=g).to(torch.bfloat16)
+    k = torch.randn(b, m, 256, device=dev, generator=g).to(torch.bfloat16)
+    mem = torch.randn(b, m, 64, device=dev, generator=g).to(torch.bfloat16)
+    do64 = torch.randn(b, n, 64, device=dev, generator=g).to(torch.bfloat16)
+    dr = (drop, torch.tensor([4242], dtype=torch.int64, device=dev), 5) if drop > 0 else None
+    o64, o32, lse, rs = ops.attn_fwd_v64(q, k, mem, 1 / 16.0, drop=dr)
+    delta = (do64.float() * o32).sum(-1)
+    c = torch.randn(b, n, device=dev, generator=g) if drop > 0 else None
+    if drop > 0:
+        delta = delta + c * rs
+    res = {}
+    try:
+        for variant in (0, 1):
+            lib.sam2b200_debug_set_variant(0, variant)
+            for gdt in (torch.float32, torch.bfloat16):
+                db = [torch.zeros(256, device=dev) for _ in range(2)]
+                dq, dk = ops.attn_bwd_v64(q, k, mem, do64, lse, delta.contiguous(), 1 / 16.0, table=table, n_rope_k=nf * n, grad_dtype=gdt,
+                                          dbias=tuple(db), dp_bias=c, drop=dr)
+                torch.cuda.synchronize()
+                res[(variant, gdt)] = (dq, dk, db)
+    finally:
+        lib.sam2b200_debug_set_variant(0, 0)
+    for gdt in (torch.float32, torch.bfloat16):
+        one, two = res[(0, gdt)], res[(1, gdt)]
+        assert torch.equal(one[0], two[0]), ("dq", gdt)
+        assert torch.equal(one[1], two[1]), ("dk", gdt)
+        for i in range(2):
+            assert rel_l2(two[2][i], one[2][i]) < 1e-4, ("dbias", i, gdt)
+
+
+@pytest.mark.parametrize("grid", [8, 24, 32])
+def test_gradient_epilogue_axial_table_addressing_bit_identical(dev, grid):
+    """The gradient epilogues read the (cos, sin) pairs of position p from rows p mod w (x part) and p - p mod w (y part)
+    of the axial table instead of row p (w + 128 / w rows per CTA instead of 128): the values are the same numbers, so the
+    rotated-back gradients must be bit-identical to full-row addressing (sam2b200_debug_set_variant key 1)."""
+    from sam2_video_training_b200 import _lib, ops
+    from sam2_video_training_b200.modeling.position_encoding import compute_axial_cis
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n, b = grid * grid, 2
+    m = 2 * n + 12
+    table = compute_axial_cis(dim=256, end_x=grid, end_y=grid).to(dev)
+    q, do = (torch.randn(b, n, 256, device=dev, generator=g).to(torch.bfloat16) for _ in range(2))
+    k, v = (torch.randn(b, m, 256, device=dev, generator=g).to(torch.bfloat16) for _ in range(2))
+    mem = torch.randn(b, m, 64, device=dev, generator=g).to(torch.bfloat16)
+    do64 = torch.randn(b, n, 64, device=dev, generator=g).to(torch.bfloat16)
+    o, o32, lse = ops.attn_fwd(q, k, v, 1 / 16.0)
+    o64, o64_32, lse64, _ = ops.attn_fwd_v64(q, k, mem, 1 / 16.0)
+    delta = (do64.float() * o64_32).sum(-1)
+    res = {}
+    try:
+        for variant in (1, 0):
+            lib.sam2b200_debug_set_variant(1, variant)
+            a = ops.attn_bwd(q, k, v, None, o32, do, lse, 1 / 16.0, table=table, n_rope_k=2 * n, grad_dtype=torch.float32)
+            c = ops.attn_bwd_v64(q, k, mem, do64, lse64, delta, 1 / 16.0, table=table, n_rope_k=2 * n, grad_dtype=torch.bfloat16)
+            torch.cuda.synchronize()
+            res[variant] = (*a, *c)
+    finally:
+        lib.sam2b200_debug_set_variant(1, 0)
+    for x, y in zip(res[0], res[1]):
+        assert torch.equal(x, y)
+
+
 def test_attention_backward_fused_bias_gradients(dev):
     """sam2b200_attn_bwd_ex: the q / k / v bias gradients (column sums of dq / dk / dv over all rows, after the
     conjugate rotation) are accumulated inside the gradient epilogues -- ragged sizes, bf16 and fp32 outputs."""

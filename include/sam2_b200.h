@@ -224,6 +224,21 @@ int sam2b200_merged_loss_bwd(const float* const* low_res, float* const* dlow_res
                              const int* n_valid, const float* grad_losses, float* d_obj_iou, int T, int C, int n_obj, int s,
                              float alpha, float gamma, float inv_temp, int iou_l1, sam2b200_stream_t stream);
 
+/* ---- LayerNorm + projection (+ RoPE | ReLU) in one kernel (csrc/lnproj.cu) ------------------------------------------
+ * The head of every pre-norm block of MemoryAttentionLayer (sam2_video/model/modeling/memory_attention.py:58-64, 66-81,
+ * 95-97 with the projections of sam2_video/model/modeling/sam/transformer.py:277-302):
+ *   x_out = x + dropout(res);  y = LayerNorm(x_out) * gamma + beta;  OUT = epi(y . w^T + bias)
+ * x [R, 256] fp32; res [R, 256] bf16 or NULL; y_out [R, 256] bf16 or NULL; mean / rstd [R]; w [Nout, 256] bf16;
+ * n_out = Nout / out_width <= 3 outputs [R, out_width] bf16.  The leading rope_cols output columns (multiple of 128) are
+ * rotated with the axial table [period, 128] (cos, sin) for rows with (row mod rows_per_item) < n_rope_rows; relu != 0
+ * applies max(., 0) and then dropout (index row * Nout + column).  Replaces ln_fwd + addmm (x1..3) + rope_apply (x0..2). */
+int sam2b200_ln_proj(const float* x, const void* res, float* x_out, const float* gamma, const float* beta, void* y_out,
+                     float* mean, float* rstd, long long R, float eps, const void* w, const void* bias, int Nout, void* out0,
+                     void* out1, void* out2, int out_width, int rope_cols, const float* table, int rows_per_item,
+                     int n_rope_rows, int period, int relu, float drop_res_p, const unsigned long long* drop_res_seed,
+                     unsigned drop_res_site, float drop_out_p, const unsigned long long* drop_out_seed, unsigned drop_out_site,
+                     cudaStream_t stream);
+
 /* ---- projections with fused bias + axial RoPE (transformer.py:277-279, :296-302; position_encoding.py:212-239) ------
  * Y[R, Nout] = X[R, K] . W[Nout, K]^T + bias (bf16, fp32 accumulation; K = 256 or 64), written to up to three contiguous
  * [R, 256] outputs (q | k | v); the first rope_cols output columns (multiple of 256) are rotated in the GEMM epilogue

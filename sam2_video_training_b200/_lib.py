@@ -63,6 +63,8 @@ _SIGNATURES = {
     "sam2b200_merged_loss_bwd": (c_int, [c_void_p] * 13 + [c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_int, c_void_p]),
     "sam2b200_proj_rope": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
                                    c_void_p, c_int, c_int, c_int, c_void_p]),
+    "sam2b200_ln_proj": (c_int, [c_void_p] * 8 + [c_longlong, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                 c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_uint, c_float, c_void_p, c_uint, c_void_p]),
     "sam2b200_mlp_dh": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p]),
     "sam2b200_bank_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                      c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

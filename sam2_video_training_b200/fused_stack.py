@@ -127,6 +127,35 @@ def proj_rope(x16, w16, bias16, n_out, table=None, rope_outs=0, rows_per_item=1,
     return outs
 
 
+def ln_proj(x, res, gamma, beta, w16, bias16, n_out, out_width=256, table=None, rope_outs=0, rows_per_item=1, n_rope_rows=0,
+            relu=False, drop_res=None, drop_out=None, eps=1e-5):
+    """Head of a pre-norm block in ONE kernel (sam2b200_ln_proj, csrc/lnproj.cu):
+        x_new = x + dropout(res);  y = LayerNorm(x_new);  outs = epi(y @ w16^T + bias16)
+    x [R, 256] fp32, res [R, 256] bf16 | None, w16 [n_out * out_width, 256] bf16.  The first `rope_outs` outputs (of width
+    256) are rotated with the axial `table`; relu: max(., 0) then drop_out.  Returns (outs, y, x_new, mean, rstd) -- the
+    same tensors ln_fwd + addmm (+ rope_apply | dropout_inplace_) produce."""
+    r = x.shape[0]
+    dev = x.device
+    nout = n_out * out_width
+    assert x.is_contiguous() and x.dtype == F32 and w16.is_contiguous() and w16.shape == (nout, 256) and w16.dtype == BF16
+    assert res is None or (res.is_contiguous() and res.dtype == BF16 and res.shape == x.shape)
+    assert bias16 is None or (bias16.is_contiguous() and bias16.numel() == nout)
+    x_new = torch.empty_like(x) if res is not None else x
+    y = torch.empty((r, 256), dtype=BF16, device=dev)
+    mean = torch.empty(r, dtype=F32, device=dev)
+    rstd = torch.empty(r, dtype=F32, device=dev)
+    outs = [torch.empty((r, out_width), dtype=BF16, device=dev) for _ in range(n_out)]
+    ptr = [o.data_ptr() for o in outs] + [None] * (3 - n_out)
+    rc = _lib.load().sam2b200_ln_proj(
+        x.data_ptr(), res.data_ptr() if res is not None else None, x_new.data_ptr() if res is not None else None, gamma.data_ptr(),
+        beta.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), r, float(eps), w16.data_ptr(),
+        bias16.data_ptr() if bias16 is not None else None, nout, ptr[0], ptr[1], ptr[2], int(out_width), 256 * int(rope_outs),
+        table.data_ptr() if table is not None else None, int(rows_per_item), int(n_rope_rows), table.shape[0] if table is not None else 1,
+        int(bool(relu)), *_drop(drop_res), *_drop(drop_out), _stream(dev))
+    _lib.check(rc, "sam2b200_ln_proj")
+    return outs, y, x_new, mean, rstd
+
+
 def mlp_dh(dm16, w2_16, h16, scale=1.0):
     """dh = (dm @ W2) * (h > 0) * scale in one tcgen05 GEMM with the ReLU / hidden-dropout backward in its epilogue."""
     r, f = h16.shape
@@ -193,6 +222,7 @@ NO_FOLD = bool(os.environ.get("SAM2B200_NO_FOLD"))  # A/B switch: v_proj and out
 NO_V64 = bool(os.environ.get("SAM2B200_NO_V64"))    # A/B switch: cross-attention on the projected 256-d values (with the dV kernel)
 NO_PROJ_KERNEL = not bool(os.environ.get("SAM2B200_PROJ_KERNEL"))
 PROJ_KERNEL_K64 = bool(os.environ.get("SAM2B200_PROJ_KERNEL_K64"))
+NO_LNPROJ = bool(os.environ.get("SAM2B200_NO_LNPROJ"))     # A/B switch: ln_fwd + cuBLAS addmm + RoPE pass instead of sam2b200_ln_proj
 NO_MLP_KERNEL = bool(os.environ.get("SAM2B200_NO_MLP_KERNEL"))     # A/B switch: cuBLAS GEMM + separate ReLU-backward pass
 NO_SIDE_STREAM = bool(os.environ.get("SAM2B200_NO_SIDE_STREAM"))   # A/B switch: everything on one stream
 _SIDE_STREAMS = {}
@@ -420,8 +450,17 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             P = dict(zip(_LAYER_KEYS, params[l * _NPL:(l + 1) * _NPL]))
             W = dict(zip(_LAYER_KEYS, wb[l * _NPL:(l + 1) * _NPL]))
             # ---- self attention (memory_attention.py:58-64)
-            y1, x, mean1, rstd1 = ln_fwd(x, res, P["n1.w"], P["n1.b"], drop=dsite("p_res", l - 1, 5) if l > 0 else None)
-            if NO_PROJ_KERNEL:
+            if not NO_LNPROJ:
+                # LayerNorm + q|k|v projection + bias + RoPE(q, k) in one kernel: no un-rotated q / k in HBM
+                (q_rot, k_rot, v), y1, x, mean1, rstd1 = ln_proj(
+                    x, res, P["n1.w"], P["n1.b"], mirror.qkv[l], mirror.qkv_bias[l], 3, table=table, rope_outs=2, rows_per_item=n,
+                    n_rope_rows=n, drop_res=dsite("p_res", l - 1, 5) if l > 0 else None)
+                q_rot, k_rot = q_rot.view(b, n, d), k_rot.view(b, n, d)
+            else:
+                y1, x, mean1, rstd1 = ln_fwd(x, res, P["n1.w"], P["n1.b"], drop=dsite("p_res", l - 1, 5) if l > 0 else None)
+            if not NO_LNPROJ:
+                pass
+            elif NO_PROJ_KERNEL:
                 q = torch.addmm(W["sa.q.b"], y1, W["sa.q.w"].t())
                 k = torch.addmm(W["sa.k.b"], y1, W["sa.k.w"].t())
                 v = torch.addmm(W["sa.v.b"], y1, W["sa.v.w"].t())
@@ -433,8 +472,15 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             o, o32, lse = attn_fwd(q_rot, k_rot, v.view(b, n, d), scale, meta["nsplit"], drop=dsite("p_sa", l, 0))
             sa = torch.addmm(W["sa.o.b"], o.view(r, d), W["sa.o.w"].t())
             # ---- cross attention to the memory bank (memory_attention.py:66-81)
-            y2, x1, mean2, rstd2 = ln_fwd(x, sa, P["n2.w"], P["n2.b"], drop=dsite("p_res", l, 2))
-            if NO_PROJ_KERNEL:
+            if not NO_LNPROJ:
+                (q2_rot,), y2, x1, mean2, rstd2 = ln_proj(x, sa, P["n2.w"], P["n2.b"], W["ca.q.w"], W["ca.q.b"], 1, table=table,
+                                                          rope_outs=1, rows_per_item=n, n_rope_rows=n, drop_res=dsite("p_res", l, 2))
+                q2_rot = q2_rot.view(b, n, d)
+            else:
+                y2, x1, mean2, rstd2 = ln_fwd(x, sa, P["n2.w"], P["n2.b"], drop=dsite("p_res", l, 2))
+            if not NO_LNPROJ:
+                pass
+            elif NO_PROJ_KERNEL:
                 q2 = torch.addmm(W["ca.q.b"], y2, W["ca.q.w"].t())
                 q2_rot = rope_apply(q2.view(b, n, d), table, n)
             else:
@@ -461,9 +507,13 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                 o2, o2_32, lse2 = attn_fwd(q2_rot, k2_rot, v2.view(b, m, d), scale, meta["nsplit"], drop=dsite("p_ca", l, 1))
                 ca = torch.addmm(W["ca.o.b"], o2.view(r, d), W["ca.o.w"].t())
             # ---- MLP (memory_attention.py:95-98)
-            y3, x2, mean3, rstd3 = ln_fwd(x1, ca, P["n3.w"], P["n3.b"], drop=dsite("p_res", l, 3))
-            h = torch._addmm_activation(W["l1.b"], y3, W["l1.w"].t(), use_gelu=False)  # bias + ReLU epilogue
-            dropout_inplace_(h, dsite("p_res", l, 4))
+            if not NO_LNPROJ:   # LayerNorm + linear1 + bias + ReLU (+ hidden dropout) in one kernel
+                (h,), y3, x2, mean3, rstd3 = ln_proj(x1, ca, P["n3.w"], P["n3.b"], W["l1.w"], W["l1.b"], 1, out_width=2048, relu=True,
+                                                     drop_res=dsite("p_res", l, 3), drop_out=dsite("p_res", l, 4))
+            else:
+                y3, x2, mean3, rstd3 = ln_fwd(x1, ca, P["n3.w"], P["n3.b"], drop=dsite("p_res", l, 3))
+                h = torch._addmm_activation(W["l1.b"], y3, W["l1.w"].t(), use_gelu=False)  # bias + ReLU epilogue
+                dropout_inplace_(h, dsite("p_res", l, 4))
             mlp = torch.addmm(W["l2.b"], h, W["l2.w"].t())
             saved += [x, mean1, rstd1, y1, q_rot, k_rot, v, o, o32, lse,
                       x1, mean2, rstd2, y2, q2_rot, k2_rot, v2, o2, o2_32, lse2,

@@ -547,6 +547,73 @@ def test_proj_rope_kernel(dev, k, n_out, b, length, n_rope):
         assert rel_l2(o.view(b, length, 256), want) < 4e-3, (i, rel_l2(o.view(b, length, 256), want))
 
 
+@pytest.mark.parametrize("mode,b,length,with_res,drop", [("qkv", 3, 64, True, 0.0), ("q", 2, 144, True, 0.0), ("q", 1, 100, False, 0.0),
+                                                         ("mlp", 2, 200, True, 0.0), ("mlp", 3, 70, True, 0.1), ("qkv", 2, 576, True, 0.1)])
+def test_ln_proj_kernel(dev, mode, b, length, with_res, drop):
+    """sam2b200_ln_proj: x + dropout(res) -> LayerNorm -> projection (+ bias) -> RoPE | ReLU (+ dropout) in one kernel, against
+    the op sequence it replaces restated in fp32 torch on the same bf16-rounded operands (with the kernel's own dropout
+    masks): x_new / mean / rstd to fp32 round-off, y and the outputs to bf16 rounding; ragged last row tile."""
+    from sam2_video_training_b200 import fused_stack as fs
+    from sam2_video_training_b200.modeling.position_encoding import compute_axial_cis
+    g = torch.Generator(device="cuda").manual_seed(11)
+    r = b * length
+    grid = int(round(math.sqrt(length)))
+    table = compute_axial_cis(dim=256, end_x=grid, end_y=grid).to(dev) if grid * grid == length else None
+    n_rope = length if table is not None else 0
+    if table is None:      # a table for a smaller square grid: positions beyond it stay un-rotated
+        grid = int(math.sqrt(length))
+        table = compute_axial_cis(dim=256, end_x=grid, end_y=grid).to(dev)
+        n_rope = grid * grid
+    x = torch.randn(r, 256, device=dev, generator=g) * 1.3 + 0.2
+    res = torch.randn(r, 256, device=dev, generator=g).to(torch.bfloat16) if with_res else None
+    gamma = 1 + 0.1 * torch.randn(256, device=dev, generator=g)
+    beta = 0.1 * torch.randn(256, device=dev, generator=g)
+    nout, n_out, width, rope_outs, relu = {"qkv": (768, 3, 256, 2, False), "q": (256, 1, 256, 1, False), "mlp": (2048, 1, 2048, 0, True)}[mode]
+    w = (torch.randn(nout, 256, device=dev, generator=g) / 16).to(torch.bfloat16)
+    bias = (torch.randn(nout, device=dev, generator=g) * 0.2).to(torch.bfloat16)
+    seed = torch.tensor([987654321], dtype=torch.int64, device=dev)
+    d_res = (drop, seed, 7) if drop > 0 and with_res else None
+    d_out = (drop, seed, 12) if drop > 0 and relu else None
+    outs, y, x_new, mean, rstd = fs.ln_proj(x, res, gamma, beta, w, bias, n_out, out_width=width, table=table if rope_outs else None,
+                                            rope_outs=rope_outs, rows_per_item=length, n_rope_rows=n_rope, relu=relu,
+                                            drop_res=d_res, drop_out=d_out)
+    torch.cuda.synchronize()
+    # ---- reference
+    xr = x.clone()
+    if with_res:
+        rr = res.float()
+        if d_res is not None:
+            rr = rr * _keep_mask(dev, seed, 7, drop, r * 256).view(r, 256) / (1 - drop)
+        xr = xr + rr
+        assert rel_l2(x_new, xr) < 1e-6
+    else:
+        assert x_new.data_ptr() == x.data_ptr()
+    mu = xr.mean(-1)
+    var = ((xr - mu[:, None]) ** 2).mean(-1)
+    assert rel_l2(mean, mu) < 1e-5 and rel_l2(rstd, torch.rsqrt(var + 1e-5)) < 1e-5
+    yr = ((xr - mu[:, None]) * torch.rsqrt(var + 1e-5)[:, None] * gamma + beta)
+    assert rel_l2(y, yr) < 4e-3
+    o = y.float() @ w.float().t() + bias.float()           # the kernel's own bf16 y: the error budget below is the GEMM + epilogue only
+    if rope_outs:
+        o3 = o.view(b, length, nout)
+        parts = []
+        for i in range(n_out):
+            blk = o3[:, :, i * 256:(i + 1) * 256]
+            if i < rope_outs:
+                cos, sin = ao.axial_rope_table(grid * grid)
+                rot = ao.apply_axial_rope(blk[:, :n_rope].cpu(), cos, sin).to(dev)
+                blk = torch.cat([rot, blk[:, n_rope:]], dim=1)
+            parts.append(blk.reshape(r, 256))
+    else:
+        o = torch.relu(o)
+        if d_out is not None:
+            o = o * _keep_mask(dev, seed, 12, drop, r * nout).view(r, nout) / (1 - drop)
+        parts = [o]
+    for got, want in zip(outs, parts):
+        assert got.shape == want.shape and got.dtype == torch.bfloat16
+        assert rel_l2(got, want) < 4e-3, (mode, rel_l2(got, want))
+
+
 @pytest.mark.parametrize("rows", [128, 700, 4096])
 def test_mlp_dh_kernel(dev, rows):
     """sam2b200_mlp_dh: dh = (dm @ W2) * (h > 0) * scale (tcgen05 GEMM, ReLU / hidden-dropout backward in the epilogue)

@@ -46,8 +46,10 @@ TRAFFIC_NOTE = ("per cross-attention backward call at B=56 N=576 M=4060 (dK + dQ
 
 
 def bank_sizes(t: int, n: int):
-    nf = min(t, 7)
-    return nf * n + 4 * nf, 4 * nf  # M, P
+    """Frame t of a clip attends to the conditioning frame + the last 6 frames (num_maskmem = 7, sam2_base.py:551-596) and to
+    the object pointers of up to 16 past frames, 4 tokens each (sam2_base.py:612-672): M = min(t, 7) N + 4 min(t, 16)."""
+    nf, npt = min(t, 7), min(t, 16)
+    return nf * n + 4 * npt, 4 * npt  # M, P
 
 
 def algorithmic_flops(wl) -> float:
@@ -85,8 +87,11 @@ def make_host_inputs(wl, seed, pin):
     h = dict(
         curr=[mk(n, b, 256) for _ in range(1, T)],
         curr_pos=mk(n, b, 256, scale=0.7),
-        mem_feat=[mk(n + 4, b, 64) for _ in range(min(T - 1, 7))],      # one memory frame + its 4 pointer tokens
-        mem_pos=[mk(n + 4, b, 64, scale=0.7) for _ in range(min(T - 1, 7))],
+        # what the tracker keeps per processed frame (sam2_base.py:715-769, 795-811), in the reference's own layout:
+        # memory-encoder features + their position encoding [B, 64, H, W] and the object pointer [B, 256]
+        mem_feat=[mk(b, 64, wl["grid"], wl["grid"]) for _ in range(T - 1)],
+        mem_pos=[mk(b, 64, wl["grid"], wl["grid"], scale=0.7) for _ in range(T - 1)],
+        obj_ptr=[mk(b, 256) for _ in range(T - 1)],
         grad_out=[mk(n, b, 256) for _ in range(1, T)],
         logits=[mk(C, 1, S, S, scale=4.0) for _ in range(clips * T)],   # per-frame tensors, as the wrapper produces
         iou=[torch.rand(T, C, 1, generator=g) for _ in range(clips)],
@@ -124,18 +129,40 @@ def to_device(h, dev):
     return out
 
 
-def assemble_bank(d, wl, t):
-    """[cond frame | older frames | pointer tokens] like sam2_base.py:691-692 (torch.cat on device)."""
-    n = wl["grid"] ** 2
-    nf = min(t, 7)
-    mem = torch.cat([d["mem_feat"][i][:n] for i in range(nf)] + [d["mem_feat"][i][n:] for i in range(nf)], dim=0)
-    pos = torch.cat([d["mem_pos"][i][:n] for i in range(nf)] + [d["mem_pos"][i][n:] for i in range(nf)], dim=0)
-    # memory_pos carries gradient in real training (maskmem_tpos_enc, sam2_base.py:608-610): ask for it
-    return mem, pos.requires_grad_(True), 4 * nf
+class BankState:
+    """The trainable tensors the bank assembly differentiates through (SAM2Base.maskmem_tpos_enc, obj_ptr_tpos_proj:
+    sam2_base.py:138-141, 654-663) -- outside the MemoryAttention freeze map, their gradients are produced and dropped."""
 
+    def __init__(self, dev):
+        from sam2_video_training_b200 import memory_bank as mb
+        self.mb = mb
+        self.cfg = mb.BankConfig()
+        g = torch.Generator().manual_seed(3)
+        self.tpos = (torch.randn(7, 1, 1, 64, generator=g) * 0.02).to(dev).requires_grad_(True)
+        self.proj = torch.nn.Linear(256, 64).to(dev)
 
-def assemble_banks(d, wl):
-    return [assemble_bank(d, wl, t) for t in range(1, wl["T"])]
+    def output_dict(self, d, t):
+        """Tracker state before frame t: frame 0 is the conditioning frame, frames 1 .. t-1 were tracked."""
+        od = {"cond_frame_outputs": {}, "non_cond_frame_outputs": {}}
+        for f in range(t):
+            od["cond_frame_outputs" if f == 0 else "non_cond_frame_outputs"][f] = {
+                "maskmem_features": d["mem_feat"][f], "maskmem_pos_enc": [d["mem_pos"][f]], "obj_ptr": d["obj_ptr"][f]}
+        return od
+
+    def packed(self, d, wl, t):
+        """memory_bank.assemble_memory_packed: the bank written once per frame in the kernels' layout (bf16, batch-first,
+        tpos added on write, pointer tokens appended) -- two launches, inside the timed region."""
+        return self.mb.assemble_memory_packed(self.cfg, t, self.output_dict(d, t), wl["T"], self.tpos, self.proj, training=True)
+
+    def reference_layout(self, d, wl, t):
+        """(memory, memory_pos, P) as SAM2Base._prepare_memory_conditioned_features builds them (for the reference legs)."""
+        with torch.no_grad():
+            m, p, n = self.mb.assemble_memory(self.cfg, t, self.output_dict(d, t), wl["T"], self.tpos, self.proj, training=True)
+        return m, p.detach().requires_grad_(True), n
+
+    def drop_grads(self):
+        self.tpos.grad = None
+        self.proj.zero_grad(set_to_none=True)
 
 
 def to_device_streamed(h, dev, wl, stream):
@@ -148,9 +175,8 @@ def to_device_streamed(h, dev, wl, stream):
         for t in range(1, wl["T"]):
             out["curr"][t - 1] = h["curr"][t - 1].to(dev, non_blocking=True)
             out["grad_out"][t - 1] = h["grad_out"][t - 1].to(dev, non_blocking=True)
-            if t - 1 < len(h["mem_feat"]):
-                out["mem_feat"][t - 1] = h["mem_feat"][t - 1].to(dev, non_blocking=True)
-                out["mem_pos"][t - 1] = h["mem_pos"][t - 1].to(dev, non_blocking=True)
+            for k in ("mem_feat", "mem_pos", "obj_ptr"):        # outputs of frame t - 1: first read by frame t
+                out[k][t - 1] = h[k][t - 1].to(dev, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(stream)
             events.append(ev)
@@ -162,18 +188,23 @@ def to_device_streamed(h, dev, wl, stream):
     return out, events
 
 
-def run_step(model, crit, opt, d, banks, wl, world, fwd=None, arrivals=None):
-    """`arrivals` (end-to-end leg): events of the copy stream, one per attention frame (inputs of frame t and the
-    memory frames it reads have landed) + one for the loss inputs; `banks` may then be a function t -> bank."""
+def run_step(model, crit, opt, d, bank, wl, world, fwd=None, arrivals=None):
+    """`bank`: BankState -- the memory bank of every frame is assembled HERE, inside the step, from the per-frame tracker
+    outputs (packed layout).  `arrivals` (end-to-end leg): events of the copy stream, one per attention frame (inputs of
+    frame t and the memory frames it reads have landed) + one for the loss inputs."""
     T, C = wl["T"], wl["C"]
     fwd = fwd or model
     for t in range(1, T):
         if arrivals is not None:
             torch.cuda.current_stream().wait_event(arrivals[t - 1])
-        mem, pos, p = banks(t) if callable(banks) else banks[t - 1]
-        out = fwd(d["curr"][t - 1], mem, d["curr_pos"], pos, p)
+        out = fwd(d["curr"][t - 1], bank.packed(d, wl, t), d["curr_pos"])
         out.backward(d["grad_out"][t - 1])
-        pos.grad = None
+    bank.drop_grads()
+    # the parameter gradients are complete: the all-reduce starts here and overlaps the (parameter-free) mask loss below
+    pending = None
+    if world > 1:
+        from sam2_video_training_b200 import ddp
+        pending = ddp.allreduce_gradients_async(model, world)
     total = None
     if arrivals is not None:
         torch.cuda.current_stream().wait_event(arrivals[-1])
@@ -188,9 +219,8 @@ def run_step(model, crit, opt, d, banks, wl, world, fwd=None, arrivals=None):
         total = losses["total_loss"].detach() if total is None else total + losses["total_loss"].detach()
         for x in xs:
             x.grad = None
-    if world > 1:
-        from sam2_video_training_b200 import ddp
-        ddp.allreduce_gradients(model, world)
+    if pending is not None:
+        pending.wait()
     opt.step()
     model._sam2b200_grad_bucket.zero()   # one memset for all 106 gradients
     return total
@@ -464,11 +494,13 @@ def same_box_torch_gpu(wl, dev, d, banks, reps=2):
                                                 pred_obj_scores=False, focal_gamma_obj_score=0.0, focal_alpha_obj_score=-1.0)
     T, C = wl["T"], wl["C"]
 
+    ref_banks = [banks.reference_layout(d, wl, t) for t in range(1, T)]     # built once, outside the timed region
+
     def step(autocast):
         model.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
             for t in range(1, T):
-                mem, pos, p = banks[t - 1]
+                mem, pos, p = ref_banks[t - 1]
                 out = model(curr=[d["curr"][t - 1]], curr_pos=[d["curr_pos"]], memory=mem, memory_pos=pos, num_obj_ptr_tokens=p)
                 out.backward(d["grad_out"][t - 1].to(out.dtype))
                 pos.grad = None
@@ -536,7 +568,7 @@ def measure_workload(wl_name, wl, model, crit, opt, lib, dev, world, rank, steps
     run_model = GraphedMemoryAttention(model) if use_graphs else model
     host = make_host_inputs(wl, 1234 + rank, pin=True)
     d = to_device(host, dev)
-    banks = assemble_banks(d, wl)
+    banks = BankState(dev)
     torch.cuda.synchronize()
     for _ in range(max(warmup, 3)):
         run_step(model, crit, opt, d, banks, wl, world, fwd=run_model)
@@ -678,8 +710,7 @@ def main():
             nxt = start_copy()
             for i in range(k):
                 dd, evs = nxt
-                tot = run_step(model, crit, opt, dd, lambda t: assemble_bank(dd, wl, t), wl, world, fwd=run_model,
-                               arrivals=evs)
+                tot = run_step(model, crit, opt, dd, banks, wl, world, fwd=run_model, arrivals=evs)
                 if i + 1 < k:       # enqueue the next step's copies AFTER this step's kernels: the compute stream never
                     nxt = start_copy()   # waits for the host to issue ~130 cudaMemcpyAsync calls
                 # D2H of the step's result: [loss, min valid channels] in ONE 8-byte read (also keeps `dd` alive until the
@@ -769,7 +800,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": wl_name, "tokens": wl["grid"] ** 2, "frames_per_clip": wl["T"], "objects_per_clip": wl["C"],
-                       "clips_per_gpu": wl["clips"], "mask_px": wl["S"], "memory_bank": "min(t,7) frames x (N + 4 pointer tokens)",
+                       "clips_per_gpu": wl["clips"], "mask_px": wl["S"], "memory_bank": "frame t: min(t,7) memory frames x N tokens + 4 x min(t,16) pointer tokens, assembled per frame inside the timed region (memory_bank.assemble_memory_packed)",
                        "l2": "inputs_larger_than_L2 (%.0f MB per step)" % (h2d_bytes(host) / 1e6),
                        "launch": "memory-attention fwd/bwd replayed as CUDA graphs (one pair per memory-bank shape)" if not args.no_graphs else "host-launched",
                        "parallelism": "dp%d (clips sharded, NCCL grad all-reduce)" % world,

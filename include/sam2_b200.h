@@ -264,6 +264,11 @@ int sam2b200_mlp_dh(const void* dm, const void* w2, const void* h, void* dh, lon
 int sam2b200_bank_gather(const void* const* feats, const void* const* pos, const float* const* tpos, int n_slots,
                          int feat_dtype, const void* const* ptrs, int n_ptrs, int ptr_dtype, const float* obj_pos,
                          float* memory, float* memory_pos, int B, int HW, int mem_dim, int C, sam2b200_stream_t stream);
+/* Same inputs; the bank is written directly in the layout the fused stack reads: memk = bf16(feat + pos + tpos), memv =
+ * bf16(feat), both [B, M, 64] batch-first (no fp32 [M, B, 64] tensors, no re-pack pass). */
+int sam2b200_bank_gather_packed(const void* const* feats, const void* const* pos, const float* const* tpos, int n_slots,
+                         int feat_dtype, const void* const* ptrs, int n_ptrs, int ptr_dtype, const float* obj_pos,
+                         void* memk, void* memv, int B, int HW, int mem_dim, int C, sam2b200_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -83,6 +83,22 @@ class GradBucket:
         return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
 
 
+def allreduce_gradients_async(model: torch.nn.Module, world: int):
+    """Start the gradient all-reduce NOW (on NCCL's own stream, after everything enqueued so far on the current stream) and
+    return a handle; ``handle.wait()`` makes the current stream wait for it.  Called right after the last backward that
+    touches the parameters, so that the collective overlaps whatever follows on the compute stream before the optimizer
+    (in the hot path: the mask-loss forward / backward, which has no parameters).  Returns None when there is nothing to do."""
+    bucket = getattr(model, "_sam2b200_grad_bucket", None)
+    if bucket is None or world <= 1:
+        if world > 1:
+            allreduce_gradients(model, world)
+        return None
+    if not bucket.owns_all():
+        allreduce_gradients(model, world)       # re-attaches the views (see there); synchronous on the compute stream
+        return None
+    return bucket.allreduce(world, async_op=True)
+
+
 def allreduce_gradients(model: torch.nn.Module, world: int):
     """Average gradients over ranks.  Uses the model's GradBucket if one is attached (no copies),
     else flattens on the fly."""

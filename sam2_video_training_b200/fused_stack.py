@@ -389,7 +389,9 @@ class MemoryAttentionStackFn(torch.autograd.Function):
     """out[N,B,256] = MemoryAttention(curr, memory, curr_pos, memory_pos, num_obj_ptr_tokens)."""
 
     @staticmethod
-    def forward(ctx, meta, curr, curr_pos, memory, memory_pos, *params):
+    def forward(ctx, meta, curr, curr_pos, memory, memory_pos, bank_tpos, bank_objpos, *params):
+        # bank_tpos [n_slots, 64] / bank_objpos [n_ptrs, 64] (packed bank only, else None): the differentiable tensors the key
+        # source memk depends on; their gradients are reductions of the fp32 d memk over tokens and objects (backward)
         # direct-gradient mode: params are detached aliases and the LAST tensor is a 1-element leaf with
         # requires_grad=True (the "grad anchor") whose only job is to make the output require grad, so that the
         # backward -- which accumulates the parameter gradients itself -- always runs
@@ -398,14 +400,21 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             params = params[:-1]
         nl, p_excl, table, pos_at_input = meta["num_layers"], meta["num_k_exclude_rope"], meta["table"], meta["pos_enc_at_input"]
         n, b, d = curr.shape
-        m = memory.shape[0]
+        # packed bank (memory_bank.PackedBank): `memory` IS memk = bf16(memory + pos) and `memory_pos` IS memv = bf16(memory),
+        # both [B, M, 64] batch-first -- written once by sam2b200_bank_gather_packed, consumed here without a re-pack
+        packed = bool(meta.get("packed"))
+        m = memory.shape[1] if packed else memory.shape[0]
         r, rm = b * n, b * m
         scale = 1.0 / math.sqrt(d)
         n_rope_k = m - p_excl
         # ---- pack inputs once per call (memory_attention.py:140-148; the reference re-adds pos per layer)
         # one pass each: x = curr + 0.1 curr_pos as batch-first fp32 rows; memk = bf16(memory + pos), memv = bf16(memory)
         x = permute_rows(curr, curr_pos if (pos_at_input and curr_pos is not None) else None, 0.1, b, n, False)
-        memk, memv = permute_rows(memory, memory_pos, 1.0, b, m, False, out_dtype=BF16, second=True)
+        if packed:
+            assert memory.shape == (b, m, 64) and memory_pos.shape == (b, m, 64) and memory.dtype == BF16 and memory_pos.dtype == BF16
+            memk, memv = memory.contiguous().view(rm, 64), memory_pos.contiguous().view(rm, 64)
+        else:
+            memk, memv = permute_rows(memory, memory_pos, 1.0, b, m, False, out_dtype=BF16, second=True)
         masters = meta.get("master_params") or list(params)   # the nn.Parameters (params may be detached aliases)
         wb = bf16_params(masters)
         saved: List[torch.Tensor] = []
@@ -429,7 +438,9 @@ class MemoryAttentionStackFn(torch.autograd.Function):
         # also return those row sums (factor of the value bias) and take the per-query constant dO . bv in the backward
         # (folded projections only).
         ca_drop = dr is not None and dr["p_ca"] > 0.0
-        v64 = (not NO_V64 and not (ca_drop and NO_FOLD) and not ctx.needs_input_grad[3] and b * ((n + 127) // 128) >= 64)
+        # gradient w.r.t. the VALUE source: input 3 (memory) in the reference layout; a packed bank's features are constants
+        need_v_grad = False if packed else ctx.needs_input_grad[3]
+        v64 = (not NO_V64 and not (ca_drop and NO_FOLD) and not need_v_grad and b * ((n + 127) // 128) >= 64)
 
         def project_memory():        # cross-attention keys / values of every layer: functions of the bank only
             for l in range(nl):
@@ -527,7 +538,9 @@ class MemoryAttentionStackFn(torch.autograd.Function):
         ctx.n_saved = len(saved)
         ctx.meta = dict(nl=nl, n=n, b=b, m=m, scale=scale, n_rope_k=n_rope_k, pos_at_input=pos_at_input,
                         has_pos=curr_pos is not None, bucket=meta.get("bucket"), masters=masters,
-                        direct=bool(meta.get("direct")), dropout=dr, v64=v64, fold=v64 and not NO_FOLD)
+                        direct=bool(meta.get("direct")), dropout=dr, v64=v64, fold=v64 and not NO_FOLD, packed=packed,
+                        bank_slots=int(meta.get("bank_slots", 0)), bank_hw=int(meta.get("bank_hw", 0)),
+                        bank_ptrs=int(bank_objpos.shape[0]) if bank_objpos is not None else 0)
         return out
 
     @staticmethod
@@ -541,6 +554,10 @@ class MemoryAttentionStackFn(torch.autograd.Function):
         x_fin, mean_f, rstd_f, memk, memv, table = saved[-6:]
         dev = x_fin.device
         need_curr, need_pos, need_mem, need_mpos = ctx.needs_input_grad[1:5]
+        packed = mt.get("packed", False)
+        need_tpos, need_objpos = ctx.needs_input_grad[5:7]
+        if packed:      # memk / memv are constants; the key-source gradient is wanted iff the bank's position tensors ask for it
+            need_mem, need_mpos = False, bool(need_tpos or need_objpos)      # below: need_mpos = "dmemk wanted"
         need_memgrad = need_mem or need_mpos
         masters = mt["masters"]
         wb = bf16_params(masters)
@@ -725,14 +742,26 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             d_curr = permute_rows(g, None, 0.0, b, n, True)
         if need_pos and mt["has_pos"] and mt["pos_at_input"]:
             d_pos = permute_rows(g, None, 0.0, b, n, True, scale=0.1)
-        if need_mpos:
-            d_mpos = permute_rows(dmemk, None, 0.0, b, m, True)
-        if need_mem:
-            d_mem = permute_rows(dmemk, dmemv, 1.0, b, m, True)
+        d_tpos = d_objpos = None
+        if packed:
+            # d maskmem_tpos_enc rows / d pointer positions = the fp32 key-source gradient summed over tokens and objects
+            ns, hw = mt["bank_slots"], mt["bank_hw"]
+            sp = ns * hw
+            dk3 = dmemk.view(b, m, 64) if need_mpos else None
+            if need_tpos and ns:
+                d_tpos = dk3[:, :sp].reshape(b, ns, hw, 64).sum((0, 2))
+            if need_objpos and m > sp:
+                n_ptr = mt["bank_ptrs"]
+                d_objpos = dk3[:, sp:].reshape(b, n_ptr, (m - sp) // n_ptr, 64).sum((0, 2))
+        else:
+            if need_mpos:
+                d_mpos = permute_rows(dmemk, None, 0.0, b, m, True)
+            if need_mem:
+                d_mem = permute_rows(dmemk, dmemv, 1.0, b, m, True)
         if not ctx.has_anchor:
-            return (None, d_curr, d_pos, d_mem, d_mpos, *grads)
+            return (None, d_curr, d_pos, d_mem, d_mpos, d_tpos, d_objpos, *grads)
         # The anchor gets a (zero) gradient only when it is the ONLY input that requires grad: a backward whose
         # outputs are all None makes the autograd engine synchronise the capturing stream with the (uncaptured)
         # stream of the anchor's AccumulateGrad node and invalidates a CUDA-graph capture (scripts/probe_capture.py).
         lonely = not (need_curr or need_pos or need_mem or need_mpos)
-        return (None, d_curr, d_pos, d_mem, d_mpos, *grads, torch.zeros(1, dtype=F32, device=dev) if lonely else None)
+        return (None, d_curr, d_pos, d_mem, d_mpos, d_tpos, d_objpos, *grads, torch.zeros(1, dtype=F32, device=dev) if lonely else None)

@@ -197,14 +197,9 @@ class _BankGatherFn(torch.autograd.Function):
         return (None, None, None, d_tpos, d_obj, *grads)
 
 
-def assemble_memory(cfg: BankConfig, frame_idx: int, output_dict: dict, num_frames: int, maskmem_tpos_enc: Tensor,
-                    obj_ptr_tpos_proj=None, training: bool = True, track_in_reverse: bool = False):
-    """``(memory [M, B, 64], memory_pos [M, B, 64], num_obj_ptr_tokens)`` for a frame that is not an initial
-    conditioning frame -- the arguments ``SAM2Base.memory_attention`` is called with (sam2_base.py:695-709).
-
-    ``output_dict`` is the reference's ``{"cond_frame_outputs": {t: out}, "non_cond_frame_outputs": {t: out}}`` with
-    ``out["maskmem_features"] [B, 64, H, W]``, ``out["maskmem_pos_enc"][-1] [B, 64, H, W]``, ``out["obj_ptr"] [B, C]``;
-    ``maskmem_tpos_enc [num_maskmem, 1, 1, 64]``; ``obj_ptr_tpos_proj``: the ``nn.Linear(C, 64)`` (or Identity)."""
+def _prepare(cfg: BankConfig, frame_idx: int, output_dict: dict, num_frames: int, maskmem_tpos_enc: Tensor,
+             obj_ptr_tpos_proj=None, training: bool = True, track_in_reverse: bool = False):
+    """Selection + validation + the small differentiable tensors (tpos rows, pointer positions) shared by both back ends."""
     if cfg.mem_dim != 64:
         raise _lib.Sam2B200Error("the B200 bank kernels are built for mem_dim = 64 (SAM2 memory encoder out_dim)")
     frames, pointers = select_bank_entries(cfg, frame_idx, output_dict, num_frames, training, track_in_reverse)
@@ -253,5 +248,81 @@ def assemble_memory(cfg: BankConfig, frame_idx: int, output_dict: dict, num_fram
             if obj_ptr_tpos_proj is not None:
                 obj_pos = obj_ptr_tpos_proj(obj_pos)
             obj_pos = obj_pos.reshape(len(pos_list), cfg.mem_dim)
+    return frames, ptrs, tpos_rows, obj_pos, feats, pos
+
+
+def assemble_memory(cfg: BankConfig, frame_idx: int, output_dict: dict, num_frames: int, maskmem_tpos_enc: Tensor,
+                    obj_ptr_tpos_proj=None, training: bool = True, track_in_reverse: bool = False):
+    """``(memory [M, B, 64], memory_pos [M, B, 64], num_obj_ptr_tokens)`` for a frame that is not an initial
+    conditioning frame -- the arguments ``SAM2Base.memory_attention`` is called with (sam2_base.py:695-709).
+
+    ``output_dict`` is the reference's ``{"cond_frame_outputs": {t: out}, "non_cond_frame_outputs": {t: out}}`` with
+    ``out["maskmem_features"] [B, 64, H, W]``, ``out["maskmem_pos_enc"][-1] [B, 64, H, W]``, ``out["obj_ptr"] [B, C]``;
+    ``maskmem_tpos_enc [num_maskmem, 1, 1, 64]``; ``obj_ptr_tpos_proj``: the ``nn.Linear(C, 64)`` (or Identity)."""
+    frames, ptrs, tpos_rows, obj_pos, feats, pos = _prepare(cfg, frame_idx, output_dict, num_frames, maskmem_tpos_enc,
+                                                           obj_ptr_tpos_proj, training, track_in_reverse)
     memory, memory_pos = _BankGatherFn.apply(len(frames), len(ptrs), cfg.hidden_dim, tpos_rows, obj_pos, *feats, *pos, *ptrs)
     return memory, memory_pos, len(ptrs) * (cfg.hidden_dim // cfg.mem_dim)
+
+
+@dataclass
+class PackedBank:
+    """The memory bank in the layout the fused MemoryAttention stack reads: batch-first, bf16,
+    ``memk = memory + memory_pos`` (key source) and ``memv = memory`` (value source), both ``[B, M, 64]``.  Pass it as the
+    ``memory`` argument of ``MemoryAttention`` (``memory_pos`` is then ignored): no fp32 ``[M, B, 64]`` tensors are
+    materialised and the stack does not re-pack.
+
+    The frame features and pointers are constants here (the training wrapper detaches them, sam2model.py:345-358); what stays
+    differentiable is what ``memory_pos`` depends on: ``tpos_rows [n_slots, 64]`` (rows of maskmem_tpos_enc) and ``obj_pos
+    [n_ptrs, 64]`` (projected pointer positions).  The stack's backward reduces its fp32 key-source gradient over tokens and
+    objects itself and hands the two small gradients to autograd (nothing is rounded to bf16 on the way)."""
+    memk: Tensor
+    memv: Tensor
+    num_obj_ptr_tokens: int
+    tpos_rows: Optional[Tensor] = None
+    obj_pos: Optional[Tensor] = None
+    n_slots: int = 0
+    hw: int = 0
+
+    @property
+    def shape(self):            # (M, B, 64), like the seq-first tensor it stands for (memory_attention.py:135-137 asserts on it)
+        return (self.memk.shape[1], self.memk.shape[0], self.memk.shape[2])
+
+
+def _pack(n_slots: int, n_ptrs: int, hidden_dim: int, tpos_rows, obj_pos, feats, pos, ptrs):
+    """sam2b200_bank_gather_packed: (memk, memv) bf16 [B, M, 64]; no autograd (see PackedBank)."""
+    lib = _lib.load()
+    ref = feats[0] if n_slots else ptrs[0]
+    dev = ref.device
+    b = ref.shape[0]
+    hw = feats[0][0, 0].numel() if n_slots else 0
+    per = hidden_dim // 64
+    m = n_slots * hw + n_ptrs * per
+    memk = torch.empty((b, m, 64), dtype=torch.bfloat16, device=dev)
+    memv = torch.empty((b, m, 64), dtype=torch.bfloat16, device=dev)
+    tp = tpos_rows.detach().float().contiguous() if n_slots else None
+    op = obj_pos.detach().float().contiguous() if obj_pos is not None else None
+    rc = lib.sam2b200_bank_gather_packed(
+        _lib.ptr_array([t.data_ptr() for t in feats]) if n_slots else None,
+        _lib.ptr_array([t.data_ptr() for t in pos]) if n_slots else None,
+        _lib.ptr_array([tp[s].data_ptr() for s in range(n_slots)]) if n_slots else None, n_slots,
+        _DT[feats[0].dtype] if n_slots else 0,
+        _lib.ptr_array([t.data_ptr() for t in ptrs]) if n_ptrs else None, n_ptrs, _DT[ptrs[0].dtype] if n_ptrs else 0,
+        op.data_ptr() if op is not None else None, memk.data_ptr(), memv.data_ptr(), b, hw, 64, hidden_dim,
+        torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "sam2b200_bank_gather_packed")
+    return memk, memv, hw
+
+
+def assemble_memory_packed(cfg: BankConfig, frame_idx: int, output_dict: dict, num_frames: int, maskmem_tpos_enc: Tensor,
+                           obj_ptr_tpos_proj=None, training: bool = True, track_in_reverse: bool = False) -> PackedBank:
+    """Same selection rules and inputs as :func:`assemble_memory`, but the bank is written ONCE, directly in the kernel
+    layout of the fused stack (``PackedBank``): per frame the reference's ``[B, 64, H, W]`` memory-encoder outputs are
+    transposed to token-major bf16 rows with the temporal position added on write, the pointer tokens appended behind
+    them -- no fp32 ``[M, B, 64]`` pair, no ``memory + pos`` pass, no re-pack inside ``MemoryAttention``."""
+    frames, ptrs, tpos_rows, obj_pos, feats, pos = _prepare(cfg, frame_idx, output_dict, num_frames, maskmem_tpos_enc,
+                                                           obj_ptr_tpos_proj, training, track_in_reverse)
+    with torch.no_grad():
+        memk, memv, hw = _pack(len(frames), len(ptrs), cfg.hidden_dim, tpos_rows, obj_pos, feats, pos, ptrs)
+    return PackedBank(memk, memv, len(ptrs) * (cfg.hidden_dim // cfg.mem_dim), tpos_rows=tpos_rows, obj_pos=obj_pos,
+                      n_slots=len(frames), hw=hw)

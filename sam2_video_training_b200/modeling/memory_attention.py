@@ -145,10 +145,13 @@ class MemoryAttention(nn.Module):
             self._sam2b200_anchor = a
         return a
 
-    def _forward_fused(self, curr, memory, curr_pos, memory_pos, num_obj_ptr_tokens, anchor=None):
+    def _forward_fused(self, curr, memory, curr_pos, memory_pos, num_obj_ptr_tokens, anchor=None, packed=None, raw=False,
+                       direct=None):
+        """packed = (tpos_rows, obj_pos, n_slots, hw) of a memory_bank.PackedBank: `memory` / `memory_pos` are then its memk /
+        memv tensors ([B, M, 64] bf16)."""
         from ..fused_stack import MemoryAttentionStackFn
         n = curr.shape[0]
-        m = memory.shape[0]
+        m = memory.shape[1] if packed else memory.shape[0]
         ca0 = self.layers[0].cross_attn_image
         if (m - num_obj_ptr_tokens) % n != 0:
             raise ValueError("rotated key count must be a multiple of the query count (position_encoding.py:230)")
@@ -158,7 +161,8 @@ class MemoryAttention(nn.Module):
         bucket = getattr(self, "_sam2b200_grad_bucket", None)
         # With a GradBucket attached (ddp.attach_grad_bucket) the backward accumulates parameter gradients into the
         # bucket itself; autograd then only sees detached aliases of the parameters (no 106 AccumulateGrad nodes).
-        direct = direct_grads_possible(bucket, params)
+        if direct is None:     # (graphs.py decides once per captured signature and passes its decision in: it builds the call
+            direct = direct_grads_possible(bucket, params)      # under no_grad, where this test would say no)
         # train-mode dropout: one device seed per call; the kernels derive every mask of the stack from it
         dropout = None
         l0 = self.layers[0]
@@ -170,11 +174,21 @@ class MemoryAttention(nn.Module):
                 dropout["seed"].fill_(int(self._sam2b200_fixed_seed))
         meta = dict(num_layers=self.num_layers, num_k_exclude_rope=int(num_obj_ptr_tokens), table=table,
                     pos_enc_at_input=bool(self.pos_enc_at_input), nsplit=int(self.attn_nsplit),
-                    bucket=bucket, direct=direct, master_params=params, dropout=dropout)
+                    bucket=bucket, direct=direct, master_params=params, dropout=dropout, packed=packed is not None,
+                    bank_slots=packed[2] if packed is not None else 0, bank_hw=packed[3] if packed is not None else 0)
+        b_tpos, b_obj = (packed[0], packed[1]) if packed is not None else (None, None)
+        if b_tpos is not None and b_tpos.numel() == 0:
+            b_tpos = None
+        if b_obj is not None and b_obj.numel() == 0:
+            b_obj = None
         if direct:
             anchor = anchor if anchor is not None else self._grad_anchor(curr.device)
-            return MemoryAttentionStackFn.apply(meta, curr, curr_pos, memory, memory_pos, *[p.detach() for p in params], anchor)
-        return MemoryAttentionStackFn.apply(meta, curr, curr_pos, memory, memory_pos, *params)
+            args = (meta, curr, curr_pos, memory, memory_pos, b_tpos, b_obj, *[p.detach() for p in params], anchor)
+        else:
+            args = (meta, curr, curr_pos, memory, memory_pos, b_tpos, b_obj, *params)
+        if raw:         # graphs.GraphedMemoryAttention calls the function's forward / backward itself (no autograd in a capture)
+            return args
+        return MemoryAttentionStackFn.apply(*args)
 
     def forward(self, curr: torch.Tensor, memory: torch.Tensor, curr_pos: Optional[Tensor] = None,
                 memory_pos: Optional[Tensor] = None, num_obj_ptr_tokens: int = 0):
@@ -186,6 +200,13 @@ class MemoryAttention(nn.Module):
         if not curr.is_cuda:
             raise _lib.Sam2B200Error("MemoryAttention (B200 path) needs CUDA tensors: no CPU fallback")
         _lib.load()  # fail loudly before any compute if the CUDA library is missing
+        from ..memory_bank import PackedBank
+        if isinstance(memory, PackedBank):
+            # the bank already is in the kernels' layout (memory_bank.assemble_memory_packed): memory_pos is ignored
+            if not (self.use_fused_stack and self._fused_eligible()):
+                raise _lib.Sam2B200Error("a PackedBank needs the fused stack (shipped SAM2 configuration)")
+            return self._forward_fused(curr, memory.memk, curr_pos, memory.memv, memory.num_obj_ptr_tokens,
+                                       packed=(memory.tpos_rows, memory.obj_pos, memory.n_slots, memory.hw))
         if self.use_fused_stack and self._fused_eligible():
             return self._forward_fused(curr, memory, curr_pos, memory_pos, num_obj_ptr_tokens)
         output = curr.float()

@@ -37,7 +37,12 @@ def _worker(rank, world, rdv, use_bucket, q, steps=1):
             model.zero_grad(set_to_none=True)
         loss = model(x).pow(2).sum() / 7.0 * world  # so that the mean over ranks == full-batch gradient
         loss.backward()
-        ddp.allreduce_gradients(model, world)
+        if use_bucket and step == 0:
+            h = ddp.allreduce_gradients_async(model, world)     # overlappable form; wait() orders it before the optimizer
+            assert h is not None
+            h.wait()
+        else:
+            ddp.allreduce_gradients(model, world)
         if use_bucket:
             assert bucket.owns_all()
     flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])

@@ -1122,6 +1122,85 @@ def test_memory_bank_assembly_matches_oracle(dev, golden_dir, tag, dtype):
     assert rel_l2(proj.weight.grad.cpu(), pwo.grad) < 1e-5 and rel_l2(proj.bias.grad.cpu(), pbo.grad) < 1e-5
 
 
+@pytest.mark.parametrize("tag", [t for t, _ in detgen.bank_scenarios()])
+def test_packed_bank_matches_reference_fixture(dev, golden_dir, tag):
+    """memory_bank.assemble_memory_packed (sam2b200_bank_gather_packed): the bank written directly in the kernel layout --
+    memk = bf16(memory + memory_pos), memv = bf16(memory), [B, M, 64] batch-first -- against the fixture produced by the
+    UNMODIFIED SAM2Base._prepare_memory_conditioned_features (bit-exact on memv, 1 bf16 ulp on memk)."""
+    import numpy as np
+    from sam2_video_training_b200 import memory_bank as mb
+    kw = dict(detgen.bank_scenarios())[tag]
+    od, tpos, pw, pb = detgen.bank_inputs(kw["cond"], kw["non_cond"])
+    od_dev = {k_: {t: {"maskmem_features": o["maskmem_features"].to(dev), "maskmem_pos_enc": [o["maskmem_pos_enc"][0].to(dev)],
+                       "obj_ptr": o["obj_ptr"].to(dev)} for t, o in v_.items()} for k_, v_ in od.items()}
+    args = dict(max_cond_frames_in_attn=kw.get("max_cond", -1), memory_temporal_stride_for_eval=kw.get("stride", 1))
+    g = np.load(os.path.join(golden_dir, f"bank_{tag}.npz"))
+    ref_mem, ref_pos = torch.from_numpy(g["memory"]), torch.from_numpy(g["memory_pos"])          # [M, B, 64] fp32
+    proj = torch.nn.Linear(256, 64).to(dev)
+    with torch.no_grad():
+        proj.weight.copy_(pw); proj.bias.copy_(pb)
+    tpos_d = tpos.to(dev).requires_grad_(True)
+    out = mb.assemble_memory_packed(mb.BankConfig(**args), kw["frame_idx"], od_dev, kw["num_frames"], tpos_d, proj, training=kw["training"],
+                                    track_in_reverse=kw.get("reverse", False))
+    assert isinstance(out, mb.PackedBank) and out.num_obj_ptr_tokens == int(g["n_ptr"]) and out.shape == tuple(ref_mem.shape)
+    assert out.memk.dtype == out.memv.dtype == torch.bfloat16 and not out.memv.requires_grad and not out.memk.requires_grad
+    assert torch.equal(out.memv.cpu(), ref_mem.transpose(0, 1).to(torch.bfloat16))
+    want_k = (ref_mem + ref_pos).transpose(0, 1)
+    assert float((out.memk.float().cpu() - want_k).abs().max()) <= 2.0 ** -7 * float(want_k.abs().max())
+    # the bank's differentiable part: rows of maskmem_tpos_enc / projected pointer positions (gradients flow through the stack,
+    # test_memory_attention_on_packed_bank_matches_reference_layout)
+    assert out.tpos_rows.requires_grad and out.tpos_rows.shape == (out.n_slots, 64)
+    assert out.n_slots * out.hw + out.num_obj_ptr_tokens == out.memk.shape[1]
+
+
+def test_memory_attention_on_packed_bank_matches_reference_layout(dev):
+    """MemoryAttention fed a PackedBank (no fp32 [M, B, 64] pair, no re-pack inside the stack) == MemoryAttention fed the
+    reference-layout memory / memory_pos built from the same frames: output, d curr and the gradient that reaches
+    maskmem_tpos_enc through the bank; eager and CUDA-graph replay."""
+    from sam2_video_training_b200 import memory_bank as mb
+    from sam2_video_training_b200.graphs import GraphedMemoryAttention
+    from sam2_video_training_b200.modeling.memory_attention import build_memory_attention
+    torch.manual_seed(5)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    grid, b, nf = 8, 64, 4                          # 64 objects: the raw-memory cross-attention path
+    n = grid * grid
+    model = build_memory_attention(dropout=0.0).to(dev).train()
+    graphed = GraphedMemoryAttention(model)
+    od = {"cond_frame_outputs": {}, "non_cond_frame_outputs": {}}
+    for t in range(nf):
+        o = {"maskmem_features": torch.randn(b, 64, grid, grid, device=dev, generator=g),
+             "maskmem_pos_enc": [torch.randn(b, 64, grid, grid, device=dev, generator=g) * 0.7],
+             "obj_ptr": torch.randn(b, 256, device=dev, generator=g)}
+        od["cond_frame_outputs" if t == 0 else "non_cond_frame_outputs"][t] = o
+    proj = torch.nn.Linear(256, 64).to(dev)
+    curr0 = torch.randn(n, b, 256, device=dev, generator=g)
+    cpos = torch.randn(n, b, 256, device=dev, generator=g) * 0.7
+    gout = torch.randn(n, b, 256, device=dev, generator=g)
+    res = {}
+    for mode in ("reference_layout", "packed", "packed_graph", "packed_graph_replay"):
+        model.zero_grad(set_to_none=True)
+        proj.zero_grad(set_to_none=True)
+        tpos = (torch.randn(7, 1, 1, 64, device=dev, generator=torch.Generator(device="cuda").manual_seed(1)) * 0.02).requires_grad_(True)
+        curr = curr0.clone().requires_grad_(True)
+        if mode == "reference_layout":
+            memory, memory_pos, p = mb.assemble_memory(mb.BankConfig(), nf, od, 10, tpos, proj, training=True)
+            out = model(curr, memory.detach(), cpos, memory_pos, p)
+        else:
+            bank = mb.assemble_memory_packed(mb.BankConfig(), nf, od, 10, tpos, proj, training=True)
+            out = (graphed if "graph" in mode else model)(curr, bank, cpos)
+        out.backward(gout)
+        torch.cuda.synchronize()
+        res[mode] = (out.detach().clone(), curr.grad.clone(), tpos.grad.clone(), proj.weight.grad.clone(),
+                     torch.cat([p_.grad.flatten() for p_ in model.parameters()]))
+    ref = res["reference_layout"]
+    for mode in ("packed", "packed_graph", "packed_graph_replay"):
+        got = res[mode]
+        assert rel_l2(got[0], ref[0]) < 2e-3, (mode, rel_l2(got[0], ref[0]))            # memk rounded once (fp32 add order differs)
+        assert cosine(got[1], ref[1]) > 0.9999 and cosine(got[4], ref[4]) > 0.9999, mode
+        assert cosine(got[2], ref[2]) > GRAD_COS_TOL and cosine(got[3], ref[3]) > GRAD_COS_TOL, (mode, cosine(got[2], ref[2]))
+    assert len(graphed._graphs) == 1
+
+
 # ---- mask loss fused with its producer side (4x bilinear up-sampling + category merge), SURVEY.md section 8f rank 2 ----
 
 MERGED_W = {"loss_mask": 20, "loss_dice": 1, "loss_iou": 1, "loss_class": 0}

@@ -98,6 +98,19 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
                          int parts, float drop_p, const unsigned long long* drop_seed, unsigned drop_site,
                          sam2b200_stream_t stream);
 
+/* ---- attention forward with the OUTPUT PROJECTION fused into the kernel's epilogue (north star; replaces the nn.Linear out_proj
+ * of sam2_video/model/modeling/sam/transformer.py:308-309 that follows scaled_dot_product_attention at :306).
+ * proj_out [B, N, 256] bf16 = out . w^T + bias; w [256, 256] bf16 row-major (nn.Linear layout), bias [256] fp32.  out / out_f32 /
+ * lse2 as sam2b200_attn_fwd_ex (no split-KV).  The _v64 form is the raw-memory cross-attention with the folded projection
+ * w = Wo Wv [256, 64], bias = Wo bv + bo (no dropout) or bo with rank1 = Wo bv multiplied by the dropped row sums. */
+int sam2b200_attn_fwd_proj(const void* q, const void* k, const void* v, void* out, float* out_f32, float* lse2, const void* w,
+                           const float* bias, void* proj_out, int B, int N, int M, float scale, float drop_p,
+                           const unsigned long long* drop_seed, unsigned drop_site, cudaStream_t stream);
+int sam2b200_attn_fwd_v64_proj(const void* q, const void* k, const void* memv, void* out64, float* out64_f32, float* lse2,
+                               float* rowsum_drop, const void* w, const float* bias, const float* rank1, void* proj_out, int B, int N,
+                               int M, float scale, float drop_p, const unsigned long long* drop_seed, unsigned drop_site,
+                               cudaStream_t stream);
+
 /* Cross-attention on the RAW 64-d memory features (kv_in_dim = 64: memory_attention.py:66-81 with the cross-attention of
  * configs/sam2/sam2.1_hiera_t.yaml:41-50).  softmax rows sum to 1, hence softmax(q k^T) (memv Wv^T + bv) = out64 Wv^T + bv
  * with out64 = softmax(q k^T) memv: v_proj (transformer.py:279) is applied by the caller to the [B N, 64] result instead of

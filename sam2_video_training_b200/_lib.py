@@ -56,6 +56,8 @@ _SIGNATURES = {
     "sam2b200_mask_loss_bwd_coef": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_float,
                                             c_float, c_float, c_void_p]),
     "sam2b200_attn_fwd_v64": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_float, c_float, c_void_p, c_uint, c_void_p]),
+    "sam2b200_attn_fwd_proj": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_float, c_float, c_void_p, c_uint, c_void_p]),
+    "sam2b200_attn_fwd_v64_proj": (c_int, [c_void_p] * 11 + [c_int, c_int, c_int, c_float, c_float, c_void_p, c_uint, c_void_p]),
     "sam2b200_attn_bwd_v64": (c_int, [c_void_p] * 8 + [c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
                                       c_void_p, c_void_p, c_int, c_void_p, c_float, c_void_p, c_uint, c_void_p]),
     "sam2b200_merged_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

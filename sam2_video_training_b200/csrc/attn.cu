@@ -282,10 +282,10 @@ int sam2b200_attn_fwd_ex(const void* q, const void* k, const void* v, void* out,
   p.dbg = timeline_slice((size_t)grid.x * grid.y * grid.z);
   if (p.drop.seed != nullptr) {
     if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_FWD, true>, smem))) return rc;
-    attn::two_gemm_kernel<attn::MODE_FWD, true><<<grid, attn::kThreads, smem, stream>>>(map_k, map_v, map_q, map_o, map_o32, p);
+    attn::two_gemm_kernel<attn::MODE_FWD, true><<<grid, attn::kThreads, smem, stream>>>(map_k, map_v, map_q, map_o, map_o32, map_o, p);
   } else {
     if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_FWD, false>, smem))) return rc;
-    attn::two_gemm_kernel<attn::MODE_FWD, false><<<grid, attn::kThreads, smem, stream>>>(map_k, map_v, map_q, map_o, map_o32, p);
+    attn::two_gemm_kernel<attn::MODE_FWD, false><<<grid, attn::kThreads, smem, stream>>>(map_k, map_v, map_q, map_o, map_o32, map_o, p);
   }
   if ((rc = sam2b200::check_launch("attn_fwd"))) return rc;
   if (nsplit > 1) {
@@ -324,12 +324,87 @@ int sam2b200_attn_fwd_v64(const void* q, const void* k, const void* memv, void* 
   dim3 grid((N + attn::kBlockM - 1) / attn::kBlockM, B, 1);
   if (p.drop.seed != nullptr) {
     if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_FWD, true, 64>, smem))) return rc;
-    attn::two_gemm_kernel<attn::MODE_FWD, true, 64><<<grid, attn::kThreads, smem, stream>>>(map_k, map_v, map_q, map_q, map_q, p);
+    attn::two_gemm_kernel<attn::MODE_FWD, true, 64><<<grid, attn::kThreads, smem, stream>>>(map_k, map_v, map_q, map_q, map_q, map_q, p);
   } else {
     if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_FWD, false, 64>, smem))) return rc;
-    attn::two_gemm_kernel<attn::MODE_FWD, false, 64><<<grid, attn::kThreads, smem, stream>>>(map_k, map_v, map_q, map_q, map_q, p);
+    attn::two_gemm_kernel<attn::MODE_FWD, false, 64><<<grid, attn::kThreads, smem, stream>>>(map_k, map_v, map_q, map_q, map_q, map_q, p);
   }
   return sam2b200::check_launch("attn_fwd_v64");
+}
+
+// ---- forward with the OUTPUT PROJECTION fused into the epilogue (transformer.py:308-309; two_gemm_kernel<.., PROJ = true>) ----
+// proj_out [B, N, 256] bf16 = out . w^T + bias, w [256, 256] bf16 (K-major, as nn.Linear stores it), bias [256] fp32.
+// out (bf16) and out_f32 (optional) are still written: the backward needs them (weight gradient of the projection, Delta).
+// No split-KV: the caller uses this entry only when B * ceil(N / 128) CTAs fill the GPU.
+int sam2b200_attn_fwd_proj(const void* q, const void* k, const void* v, void* out, float* out_f32, float* lse2, const void* w,
+                           const float* bias, void* proj_out, int B, int N, int M, float scale, float drop_p,
+                           const unsigned long long* drop_seed, unsigned drop_site, cudaStream_t stream) {
+  if (!q || !k || !v || !out || !lse2 || !w || !bias || !proj_out || B <= 0 || N <= 0 || M <= 0 || B > 65535 || !aligned16(q) ||
+      !aligned16(k) || !aligned16(v) || !aligned16(out) || !aligned16(w) || !aligned16(bias) || !aligned16(proj_out) ||
+      (out_f32 && !aligned16(out_f32)) || drop_p < 0.f || drop_p >= 1.f ||
+      (drop_p > 0.f && drop_seed && (long long)B * N * M >= (1LL << 32)))
+    return sam2b200::fail(SAM2B200_ERR_INVALID, "attn_fwd_proj: bad arguments");
+  CUtensorMap map_k, map_v, map_q, map_o, map_w, map_p;
+  int rc;
+  if ((rc = sam2b200::make_rows256_map(&map_k, k, B, M, attn::kBlockN))) return rc;
+  if ((rc = sam2b200::make_rows256_map(&map_v, v, B, M, attn::kBlockN))) return rc;
+  if ((rc = sam2b200::make_rows256_map(&map_q, q, B, N, attn::kBlockM))) return rc;
+  if ((rc = sam2b200::make_out_map(&map_o, out, 1, B, N, 256, 32))) return rc;
+  if ((rc = sam2b200::make_rows256_map(&map_w, w, 1, 256, attn::kBlockM))) return rc;
+  if ((rc = sam2b200::make_out_map(&map_p, proj_out, 1, B, N, 256, 32))) return rc;
+  attn::TwoGemmParams p{};
+  p.La = N; p.Lx = M; p.scale_log2 = scale * kLog2e;
+  p.has_out_f32 = 0; p.out_small_f32 = out_f32; p.lse2 = lse2;
+  p.tiles_per_split = (M + attn::kBlockN - 1) / attn::kBlockN;
+  p.drop = sam2b200::make_dropout(drop_seed, drop_site, drop_p);
+  p.proj_bias = bias;
+  const size_t smem = sizeof(attn::SharedStorage) + 1024;
+  dim3 grid((N + attn::kBlockM - 1) / attn::kBlockM, B, 1);
+  if (p.drop.seed != nullptr) {
+    if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_FWD, true, attn::kD, true>, smem))) return rc;
+    attn::two_gemm_kernel<attn::MODE_FWD, true, attn::kD, true><<<grid, attn::kThreads, smem, stream>>>(map_k, map_v, map_q, map_o, map_w, map_p, p);
+  } else {
+    if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_FWD, false, attn::kD, true>, smem))) return rc;
+    attn::two_gemm_kernel<attn::MODE_FWD, false, attn::kD, true><<<grid, attn::kThreads, smem, stream>>>(map_k, map_v, map_q, map_o, map_w, map_p, p);
+  }
+  return sam2b200::check_launch("attn_fwd_proj");
+}
+
+// Raw-memory cross-attention forward with the folded projection out_proj(v_proj(.)) in the epilogue:
+// proj_out [B, N, 256] bf16 = out64 . w^T + bias (+ rowsum_drop * rank1), w [256, 64] bf16 = Wo Wv, bias [256] fp32 = Wo bv + bo
+// (without dropout) or bo (with dropout, then rank1 [256] fp32 = Wo bv).  Other arguments as sam2b200_attn_fwd_v64.
+int sam2b200_attn_fwd_v64_proj(const void* q, const void* k, const void* memv, void* out64, float* out64_f32, float* lse2,
+                               float* rowsum_drop, const void* w, const float* bias, const float* rank1, void* proj_out, int B, int N,
+                               int M, float scale, float drop_p, const unsigned long long* drop_seed, unsigned drop_site,
+                               cudaStream_t stream) {
+  if (!q || !k || !memv || !out64 || !lse2 || !w || !bias || !proj_out || B <= 0 || N <= 0 || M <= 0 || B > 65535 || !aligned16(q) ||
+      !aligned16(k) || !aligned16(memv) || !aligned16(out64) || (out64_f32 && !aligned16(out64_f32)) || !aligned16(w) || !aligned16(bias) ||
+      (rank1 && !aligned16(rank1)) || !aligned16(proj_out) || drop_p < 0.f || drop_p >= 1.f ||
+      (drop_p > 0.f && drop_seed && (!rowsum_drop || !rank1 || (long long)B * N * M >= (1LL << 32))))
+    return sam2b200::fail(SAM2B200_ERR_INVALID, "attn_fwd_v64_proj: bad arguments");
+  CUtensorMap map_k, map_v, map_q, map_w, map_p;
+  int rc;
+  if ((rc = sam2b200::make_rows256_map(&map_k, k, B, M, attn::kBlockN))) return rc;
+  if ((rc = sam2b200::make_rows256_map(&map_v, memv, B, M, attn::kBlockN, 64))) return rc;
+  if ((rc = sam2b200::make_rows256_map(&map_q, q, B, N, attn::kBlockM))) return rc;
+  if ((rc = sam2b200::make_rows256_map(&map_w, w, 1, 256, attn::kBlockM, 64))) return rc;
+  if ((rc = sam2b200::make_out_map(&map_p, proj_out, 1, B, N, 256, 32))) return rc;
+  attn::TwoGemmParams p{};
+  p.La = N; p.Lx = M; p.scale_log2 = scale * kLog2e;
+  p.lse2 = lse2; p.tiles_per_split = (M + attn::kBlockN - 1) / attn::kBlockN;
+  p.drop = sam2b200::make_dropout(drop_seed, drop_site, drop_p);
+  p.out_small = out64; p.out_small_f32 = out64_f32; p.rowsum_drop = rowsum_drop;
+  p.proj_bias = bias; p.proj_rank1 = (p.drop.seed != nullptr) ? rank1 : nullptr;
+  const size_t smem = sizeof(attn::SharedStorage) + 1024;
+  dim3 grid((N + attn::kBlockM - 1) / attn::kBlockM, B, 1);
+  if (p.drop.seed != nullptr) {
+    if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_FWD, true, 64, true>, smem))) return rc;
+    attn::two_gemm_kernel<attn::MODE_FWD, true, 64, true><<<grid, attn::kThreads, smem, stream>>>(map_k, map_v, map_q, map_q, map_w, map_p, p);
+  } else {
+    if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_FWD, false, 64, true>, smem))) return rc;
+    attn::two_gemm_kernel<attn::MODE_FWD, false, 64, true><<<grid, attn::kThreads, smem, stream>>>(map_k, map_v, map_q, map_q, map_w, map_p, p);
+  }
+  return sam2b200::check_launch("attn_fwd_v64_proj");
 }
 
 int sam2b200_attn_fwd(const void* q, const void* k, const void* v, void* out, float* out_f32, float* lse2,
@@ -448,10 +523,10 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
       p.dbg = timeline_slice((size_t)grid.x * grid.y);
       if (drop_on) {
         if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_DV, true>, smem))) return rc;
-        attn::two_gemm_kernel<attn::MODE_DV, true><<<grid, attn::kThreads, smem, stream>>>(map_q64, map_do64, map_k128, map_dv, map_dv, p);
+        attn::two_gemm_kernel<attn::MODE_DV, true><<<grid, attn::kThreads, smem, stream>>>(map_q64, map_do64, map_k128, map_dv, map_dv, map_dv, p);
       } else {
         if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_DV, false>, smem))) return rc;
-        attn::two_gemm_kernel<attn::MODE_DV, false><<<grid, attn::kThreads, smem, stream>>>(map_q64, map_do64, map_k128, map_dv, map_dv, p);
+        attn::two_gemm_kernel<attn::MODE_DV, false><<<grid, attn::kThreads, smem, stream>>>(map_q64, map_do64, map_k128, map_dv, map_dv, map_dv, p);
       }
     }
     if ((rc = sam2b200::check_launch("attn_bwd dV"))) return rc;

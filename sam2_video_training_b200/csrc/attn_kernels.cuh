@@ -113,6 +113,9 @@ struct TwoGemmParams {
   float* out_small_f32;        //                  and its fp32 copy (optional)
   float* rowsum_drop;          // DY = 64 forward with dropout: [B, La] row sums of the dropped, re-scaled probabilities
                                // (the factor of the value bias: out = out' Wv^T + rowsum bv)
+  // PROJ (fused output projection, transformer.py:308-309): proj = O . W^T + proj_bias (+ rowsum * proj_rank1), bf16 [B, La, 256]
+  const float* proj_bias;      // [256] fp32
+  const float* proj_rank1;     // [256] fp32 or nullptr (DY = 64 with dropout: Wo bv, multiplied by the row sum)
 };
 
 struct SharedStorage {
@@ -130,8 +133,17 @@ struct SharedStorage {
   float colvec[2][kBlockN];    // DV: LSE2 of the tile's columns
   float xchg[2][2][kBlockM];   // [buffer][half][row]: row-max exchange between the two halves of a row
   float lsum[2][kBlockM];      // [half][row]: row-sum exchange in the epilogue
+  uint64_t loop_done;          // PROJ: every MMA of the main loop has completed (the ring is free for the projection weight)
+  uint64_t w_full;             // PROJ: projection weight landed in shared memory
+  uint64_t o_ready;            // PROJ: the normalised bf16 output tile is in tensor memory (A operand of the projection)
+  uint64_t proj_done;          // PROJ: projection MMAs completed
   uint32_t tmem_base;
 };
+// PROJ tensor-memory columns.  DY = 64: the bf16 output operand goes to the unused columns behind the 64-column accumulator,
+// the [128 x 256] projection result over the (then dead) Q operand + score buffers.  DY = 256: the bf16 output operand replaces
+// the Q operand, the result overwrites the accumulator once every warp has read it.
+constexpr uint32_t kColProjA64 = 64, kColProjD64 = 256;
+constexpr int kProjW64Offset = 8192;      // DY = 64: the weight halves live behind the 8 KB a Y stage uses
 
 // The fixed operand is staged by TMA as four [128 rows x 128 B] slabs (64 features each, 128-byte swizzle).
 // Each of the two warps of a lane quarter moves HALF of its rows' 256 features (slabs 2*half, 2*half+1, which
@@ -289,19 +301,59 @@ __device__ __forceinline__ void grad_epilogue(const GradOut& g, const CUtensorMa
   if (lane == 0) tma_store_wait_read();
 }
 
+// PROJ epilogue, phase 2: this warp's 32 rows x 128 columns of the projection result (TMEM) + bias (+ rowsum * rank-1 vector)
+// -> bf16 -> staging (two 64-column boxes) -> TMA store.
+__device__ __forceinline__ void proj_store(const TwoGemmParams& p, const CUtensorMap* map_p, uint32_t stage, uint32_t d_addr /*column 0 of this half*/,
+                                           int half, int lane, int row0, int b, float rowsum) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t o[32];
+    SAM2B200_TMEM_LD32(d_addr + i * 32, o);
+    tmem_wait_ld();
+    const int col0 = half * 128 + i * 32;
+    float v[32];
+    const float4* bp = reinterpret_cast<const float4*>(p.proj_bias + col0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 bq = __ldg(bp + k);
+      v[4 * k] = __uint_as_float(o[4 * k]) + bq.x; v[4 * k + 1] = __uint_as_float(o[4 * k + 1]) + bq.y;
+      v[4 * k + 2] = __uint_as_float(o[4 * k + 2]) + bq.z; v[4 * k + 3] = __uint_as_float(o[4 * k + 3]) + bq.w;
+    }
+    if (p.proj_rank1 != nullptr) {
+      const float4* rp = reinterpret_cast<const float4*>(p.proj_rank1 + col0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float4 rq = __ldg(rp + k);
+        v[4 * k] = fmaf(rowsum, rq.x, v[4 * k]); v[4 * k + 1] = fmaf(rowsum, rq.y, v[4 * k + 1]);
+        v[4 * k + 2] = fmaf(rowsum, rq.z, v[4 * k + 2]); v[4 * k + 3] = fmaf(rowsum, rq.w, v[4 * k + 3]);
+      }
+    }
+    stage_chunk_bf16(stage, lane, i, v);
+    if (i & 1) store_box(map_p, stage + (i >> 1) * kBoxBytes, lane, half * 128 + (i >> 1) * 64, row0, b, row0 < p.La);
+  }
+  if (lane == 0) tma_store_wait_read();
+}
+
 // DROP: attention-probability dropout compiled in or out (a run-time branch in the softmax loops costs registers and
 // scheduling freedom even when never taken -- measured on the pair kernel).
 // DY: width of the streamed Y operand and of the accumulator.  256 = the projected values; 64 (forward only) = the raw
 // 64-d memory features of the cross-attention: out' = softmax(.) mem, the value projection is applied to the [N, 64] result
 // afterwards (softmax rows sum to 1, so out = out' Wv^T + bv exactly) -- 4x fewer PV FLOPs and no [B, M, 256] V tensor.
-template <int MODE, bool DROP, int DY = kD>
+// PROJ (forward, no split-KV): the OUTPUT PROJECTION of the attention module (transformer.py:308-309; for the raw-memory
+// cross-attention the folded Wo Wv) runs in this kernel's epilogue: the normalised output tile goes back to tensor memory as
+// bf16, one more tcgen05 GEMM against the projection weight staged in the idle tile ring, bias added on the fp32
+// accumulator, the projected [128 x 256] tile leaves through map_p.  The un-projected output is still written (the backward
+// needs it for the weight gradient and Delta).
+template <int MODE, bool DROP, int DY = kD, bool PROJ = false>
 __global__ void __launch_bounds__(kThreads, 1)
 two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
                 const __grid_constant__ CUtensorMap map_a,    // fixed operand [B, La, 256] bf16, box 64 x 128
                 const __grid_constant__ CUtensorMap map_o,    // FWD: out bf16 (box 64 x 32); DV: dV (bf16 64 x 32 | fp32 32 x 32)
-                const __grid_constant__ CUtensorMap map_o32,  // FWD: fp32 copy of out (box 32 x 32)
+                const __grid_constant__ CUtensorMap map_o32,  // FWD: fp32 copy of out (box 32 x 32); PROJ: the weight [256, DY], box 64 x 128
+                const __grid_constant__ CUtensorMap map_p,    // PROJ: projected output [B, La, 256] bf16, box 64 x 32
                 const TwoGemmParams p) {
   static_assert(DY == kD || (DY == 64 && MODE == MODE_FWD), "narrow Y: forward only");
+  static_assert(!PROJ || MODE == MODE_FWD, "fused projection: forward only");
   extern __shared__ uint8_t smem_raw[];
   SharedStorage& sh = *reinterpret_cast<SharedStorage*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -332,10 +384,13 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     mbar_init(&sh.acc_done, 1);
     mbar_init(&sh.a_full, 1);
     mbar_init(&sh.a_ready, kNumSoftmaxThreads);
+    if (PROJ) {
+      mbar_init(&sh.loop_done, 1); mbar_init(&sh.w_full, 1); mbar_init(&sh.o_ready, kNumSoftmaxThreads); mbar_init(&sh.proj_done, 1);
+    }
     fence_barrier_init();
   }
-  if (warp == kProducerWarp && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_x); prefetch_tmap(&map_y); }
-  if (warp == 0 && lane == 0) { prefetch_tmap(&map_o); if (MODE == MODE_FWD) prefetch_tmap(&map_o32); }
+  if (warp == kProducerWarp && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_x); prefetch_tmap(&map_y); if (PROJ) prefetch_tmap(&map_o32); }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&map_o); if (MODE == MODE_FWD) prefetch_tmap(&map_o32); if (PROJ) prefetch_tmap(&map_p); }
   if (warp == kMmaWarp) { tmem_alloc(&sh.tmem_base, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
@@ -352,6 +407,11 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       for (int c = 0; c < 4; ++c)
         tma_load_3d((c < 2 ? &sh.x_tiles[kStages - 1][0] : &sh.y_tiles[kStages - 1][0]) + (c & 1) * kSlabBytes, &map_a,
                     &sh.a_full, c * 64, a_tile * kBlockM, b);
+      if (PROJ && DY == 64) {   // folded weight [256, 64]: two [128 x 128 B] halves behind the 8 KB the narrow Y tiles use (never touched by the ring)
+        mbar_arrive_expect_tx(&sh.w_full, 2 * kSlabBytes);
+        tma_load_3d(&sh.y_tiles[0][kProjW64Offset], &map_o32, &sh.w_full, 0, 0, 0);
+        tma_load_3d(&sh.y_tiles[1][kProjW64Offset], &map_o32, &sh.w_full, 0, kBlockM, 0);
+      }
     }
     __syncwarp();
     for (int j = 0; j < nt; ++j) {
@@ -373,6 +433,21 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 #pragma unroll
         for (int c = 0; c < DY / 64; ++c)
           tma_load_3d(&sh.y_tiles[s][c * kChunkBytes], &map_y, &sh.y_full[s], c * 64, row0, b);
+      }
+      __syncwarp();
+    }
+    if (PROJ && DY == kD) {
+      // Wo [256, 256]: four K slabs of [256 rows x 128 B] = 32 KB each, into Y stages 0..2 and X stage 2 once the whole ring is idle
+      // (X stages 0, 1 are the epilogue's staging area); overlaps the normalisation / store of the un-projected output
+      mbar_wait(&sh.loop_done, 0);
+      if (leader) {
+        mbar_arrive_expect_tx(&sh.w_full, 8 * kSlabBytes);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint8_t* dst = (c < 3) ? &sh.y_tiles[c][0] : &sh.x_tiles[2][0];
+          tma_load_3d(dst, &map_o32, &sh.w_full, c * 64, 0, 0);
+          tma_load_3d(dst + kSlabBytes, &map_o32, &sh.w_full, c * 64, kBlockM, 0);
+        }
       }
       __syncwarp();
     }
@@ -421,9 +496,38 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                        (j > 0) || (ks > 0));
         umma_commit(&sh.y_empty[s]);
         umma_commit(&sh.acc_done);
+        if (PROJ && j + 1 >= nt) umma_commit(&sh.loop_done);
       }
       __syncwarp();
       if (j + 2 < nt) issue_scores(j + 2);
+    }
+    if (PROJ) {
+      // ---- output projection: D[128 x 256] = O_bf16 (TMEM) . W^T (shared memory, K-major)
+      mbar_wait(&sh.w_full, 0);
+      mbar_wait(&sh.o_ready, 0);
+      tc_fence_after();
+      if (leader) {
+        if (DY == 64) {
+          constexpr uint32_t idesc_p = make_idesc_bf16(kBlockM, 128, 0, 0);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t wlo = desc_lo_sw128(smem_u32(&sh.y_tiles[h][kProjW64Offset]), 16);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_ts_lohi(tmem + kColProjD64 + h * 128, tmem + kColProjA64 + ks * 8, wlo + ks * 2, kDescHiSw128_1024, idesc_p, ks > 0);
+          }
+        } else {
+          constexpr uint32_t idesc_p = make_idesc_bf16(kBlockM, kD, 0, 0);
+#pragma unroll
+          for (int ks = 0; ks < kD / 16; ++ks) {
+            const int c = ks >> 2;
+            const uint32_t wlo = desc_lo_sw128(smem_u32((c < 3) ? &sh.y_tiles[c][0] : &sh.x_tiles[2][0]), 16);
+            umma_ts_lohi(tmem + kColAcc, tmem + kColA + ks * 8, wlo + (ks & 3) * 2, kDescHiSw128_1024, idesc_p, ks > 0);
+          }
+        }
+        umma_commit(&sh.proj_done);
+      }
+      __syncwarp();
     }
   } else {
     // ===================== softmax / epilogue warps (0..7) =====================
@@ -442,7 +546,9 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     }
     // this warp's epilogue staging area inside the (then idle) tile ring, and its first row in the batch item
     const int row0 = a_tile * kBlockM + quarter * 32;
-    const uint32_t stage = smem_u32(&sh.x_tiles[0][0]) + warp * ((MODE == MODE_FWD) ? 6 * kBoxBytes : 4 * kBoxBytes);
+    // (PROJ at full width: only X stages 0, 1 -- 8 KB per warp -- the rest of the ring receives the projection weight)
+    const uint32_t stage = smem_u32(&sh.x_tiles[0][0]) +
+                           warp * ((PROJ && DY == kD) ? 2 * kBoxBytes : ((MODE == MODE_FWD) ? 6 * kBoxBytes : 4 * kBoxBytes));
     const bool rotate = false;   // dV is never rotated
     float2 tcur[16];
 
@@ -584,10 +690,19 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         uint32_t o[32];
         SAM2B200_TMEM_LD32(lane_addr + kColAcc + half * 32, o);
         tmem_wait_ld();
-        if (row_valid) {
-          float v[32];
+        float v[32];
 #pragma unroll
-          for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(o[k]) * inv_l;
+        for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(o[k]) * inv_l;
+        if (PROJ) {   // the bf16 output tile (what out' holds) back to tensor memory: A operand of the projection
+          uint32_t pk2[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) pk2[k] = pack_bf16(v[2 * k], v[2 * k + 1]);
+          SAM2B200_TMEM_ST16(lane_addr + kColProjA64 + half * 16, pk2);
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(&sh.o_ready);
+        }
+        if (row_valid) {
           const long long off = ((long long)b * p.La + a_row_idx) * 64 + half * 32;
           uint4* o16 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out_small) + off);
 #pragma unroll
@@ -600,6 +715,11 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             for (int k = 0; k < 8; ++k) o32[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
           }
           if (half == 0) p.lse2[(long long)b * p.La + a_row_idx] = fmaf(m_ref, c, log2f(l));
+        }
+        if (PROJ) {
+          mbar_wait(&sh.proj_done, 0);
+          tc_fence_after();
+          proj_store(p, &map_p, stage, lane_addr + kColProjD64 + half * 128, half, lane, row0, b, drop_on ? lk * inv_l : 0.f);
         }
       } else if (nsplit == 1) {
         // out (bf16, two 64-column boxes) and optionally its fp32 copy (four 32-column boxes) leave through this
@@ -615,16 +735,41 @@ two_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 #pragma unroll
           for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(ocur[k]) * inv_l;
           stage_chunk_bf16(stage, lane, i, v);
-          if (p.has_out_f32) stage_chunk_f32(stage + 2 * kBoxBytes, lane, i, v);
+          if (PROJ) {
+            // fp32 copy straight from registers (128 contiguous bytes per thread); the bf16 tile back to tensor memory over the
+            // dead Q operand: A operand of the projection
+            if (p.out_small_f32 != nullptr && row_valid) {
+              float4* o32p = reinterpret_cast<float4*>(p.out_small_f32 + ((long long)b * p.La + a_row_idx) * kD + half * 128 + i * 32);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) o32p[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            }
+            uint32_t pk2[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) pk2[k] = pack_bf16(v[2 * k], v[2 * k + 1]);
+            SAM2B200_TMEM_ST16(lane_addr + kColA + half * 64 + i * 16, pk2);
+          } else if (p.has_out_f32) {
+            stage_chunk_f32(stage + 2 * kBoxBytes, lane, i, v);
+          }
           if (i & 1) store_box(&map_o, stage + (i >> 1) * kBoxBytes, lane, half * 128 + (i >> 1) * 64, row0, b, row0 < p.La);
-          if (p.has_out_f32) store_box(&map_o32, stage + (2 + i) * kBoxBytes, lane, half * 128 + i * 32, row0, b, row0 < p.La);
+          if (!PROJ && p.has_out_f32) store_box(&map_o32, stage + (2 + i) * kBoxBytes, lane, half * 128 + i * 32, row0, b, row0 < p.La);
           if (i + 1 < 4) {
 #pragma unroll
             for (int k = 0; k < 32; ++k) ocur[k] = onext[k];
           }
         }
+        if (PROJ) {
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(&sh.o_ready);      // every warp has read its part of the accumulator: the projection may overwrite it
+        }
         if (row_valid && half == 0) p.lse2[(long long)b * p.La + a_row_idx] = fmaf(m_ref, c, log2f(l));
         if (lane == 0) tma_store_wait_read();
+        if (PROJ) {
+          __syncwarp();
+          mbar_wait(&sh.proj_done, 0);
+          tc_fence_after();
+          proj_store(p, &map_p, stage, lane_addr + kColAcc + half * 128, half, lane, row0, b, 0.f);
+        }
       } else {
         const long long prow = ((long long)split * gridDim.y + b) * p.La + a_row_idx;
         float* orow = p.part_acc + prow * kD;

@@ -21,7 +21,7 @@ from typing import List
 import torch
 
 from . import _lib
-from .ops import _Timed, attn_bwd, attn_bwd_v64, attn_fwd, attn_fwd_v64, rope_apply
+from .ops import _Timed, attn_bwd, attn_bwd_v64, attn_fwd, attn_fwd_proj, attn_fwd_v64, attn_fwd_v64_proj, rope_apply
 
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -222,6 +222,7 @@ NO_FOLD = bool(os.environ.get("SAM2B200_NO_FOLD"))  # A/B switch: v_proj and out
 NO_V64 = bool(os.environ.get("SAM2B200_NO_V64"))    # A/B switch: cross-attention on the projected 256-d values (with the dV kernel)
 NO_PROJ_KERNEL = not bool(os.environ.get("SAM2B200_PROJ_KERNEL"))
 PROJ_KERNEL_K64 = bool(os.environ.get("SAM2B200_PROJ_KERNEL_K64"))
+NO_FUSED_OUT_PROJ = bool(os.environ.get("SAM2B200_NO_FUSED_OUT_PROJ"))   # A/B switch: out_proj as a separate cuBLAS addmm after the attention kernel
 NO_LNPROJ = bool(os.environ.get("SAM2B200_NO_LNPROJ"))     # A/B switch: ln_fwd + cuBLAS addmm + RoPE pass instead of sam2b200_ln_proj
 NO_MLP_KERNEL = bool(os.environ.get("SAM2B200_NO_MLP_KERNEL"))     # A/B switch: cuBLAS GEMM + separate ReLU-backward pass
 NO_SIDE_STREAM = bool(os.environ.get("SAM2B200_NO_SIDE_STREAM"))   # A/B switch: everything on one stream
@@ -316,6 +317,9 @@ class WeightMirror:
         self.w_eff = [torch.empty(256, 64, dtype=BF16, device=dev) for _ in range(nl)]
         self.b_eff = [torch.empty(256, dtype=BF16, device=dev) for _ in range(nl)]
         self.wobv = [torch.empty(256, dtype=BF16, device=dev) for _ in range(nl)]
+        # fp32 copies for the attention kernels' fused output projection (bias added on the fp32 accumulator)
+        self.b_eff32 = [torch.empty(256, dtype=F32, device=dev) for _ in range(nl)]
+        self.wobv32 = [torch.empty(256, dtype=F32, device=dev) for _ in range(nl)]
         self.versions = None
         self.device = dev
 
@@ -352,6 +356,8 @@ class WeightMirror:
                     wobv = torch.mv(wo, bv)
                     self.wobv[l].copy_(wobv)
                     self.b_eff[l].copy_(wobv + bo)
+                    self.wobv32[l].copy_(wobv)
+                    self.b_eff32[l].copy_(wobv + bo)
             self.versions = v
         return self.views
 
@@ -480,8 +486,13 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             else:   # one GEMM for q | k | v with bias, q and k rotated in its epilogue
                 q_rot, k_rot, v = proj_rope(y1, mirror.qkv[l], mirror.qkv_bias[l], 3, table, 2, n, n)
                 q_rot, k_rot = q_rot.view(b, n, d), k_rot.view(b, n, d)
-            o, o32, lse = attn_fwd(q_rot, k_rot, v.view(b, n, d), scale, meta["nsplit"], drop=dsite("p_sa", l, 0))
-            sa = torch.addmm(W["sa.o.b"], o.view(r, d), W["sa.o.w"].t())
+            fuse_out = (not NO_FUSED_OUT_PROJ) and meta["nsplit"] in (0, 1) and b * ((n + 127) // 128) >= 100
+            if fuse_out:   # out_proj inside the attention kernel's epilogue (transformer.py:308-309): no separate GEMM, o is not re-read
+                o, o32, lse, sa = attn_fwd_proj(q_rot, k_rot, v.view(b, n, d), W["sa.o.w"], P["sa.o.b"], scale, drop=dsite("p_sa", l, 0))
+                sa = sa.view(r, d)
+            else:
+                o, o32, lse = attn_fwd(q_rot, k_rot, v.view(b, n, d), scale, meta["nsplit"], drop=dsite("p_sa", l, 0))
+                sa = torch.addmm(W["sa.o.b"], o.view(r, d), W["sa.o.w"].t())
             # ---- cross attention to the memory bank (memory_attention.py:66-81)
             if not NO_LNPROJ:
                 (q2_rot,), y2, x1, mean2, rstd2 = ln_proj(x, sa, P["n2.w"], P["n2.b"], W["ca.q.w"], W["ca.q.b"], 1, table=table,
@@ -498,7 +509,16 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                 q2_rot = proj_rope(y2, W["ca.q.w"], W["ca.q.b"], 1, table, 1, n, n)[0].view(b, n, d)
             k2_rot, v2, ev = kv_ready[l]
             side.wait(ev)
-            if v64:
+            if v64 and not NO_FOLD and not NO_FUSED_OUT_PROJ:
+                # raw-memory cross-attention with the folded out_proj(v_proj(.)) in the kernel's epilogue; the o2 slot of `saved`
+                # holds the folded weight, the v2 / o2_32 slots out64 and its fp32 copy
+                o2 = mirror.w_eff[l]
+                ca_d = dsite("p_ca", l, 1)
+                v2, o2_32, lse2, rs, ca = attn_fwd_v64_proj(q2_rot, k2_rot, memv.view(b, m, 64), o2,
+                                                            P["ca.o.b"] if ca_d is not None else mirror.b_eff32[l],
+                                                            mirror.wobv32[l] if ca_d is not None else None, scale, drop=ca_d)
+                ca = ca.view(r, d)
+            elif v64:
                 # v2 / o2_32 slots of `saved` then hold out64 (bf16) and its fp32 copy
                 v2, o2_32, lse2, rs = attn_fwd_v64(q2_rot, k2_rot, memv.view(b, m, 64), scale, drop=dsite("p_ca", l, 1))
                 if NO_FOLD:

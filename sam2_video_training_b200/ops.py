@@ -89,6 +89,53 @@ def attn_fwd(q, k, v, scale: float, nsplit: int = 0, keep_f32: bool = True, drop
     return out, out32, lse2
 
 
+def attn_fwd_proj(q, k, v, w16, bias32, scale: float, keep_f32: bool = True, drop=None):
+    """attn_fwd with the output projection fused into the kernel's epilogue (sam2b200_attn_fwd_proj; no split-KV):
+    returns (out bf16, out fp32 | None, lse2, proj bf16 [B, N, 256] = out @ w16^T + bias32)."""
+    lib = _lib.load()
+    b, n, d = q.shape
+    m = k.shape[1]
+    assert d == 256 and k.shape == v.shape == (b, m, 256) and w16.shape == (256, 256) and bias32.shape == (256,)
+    for t in (q, k, v, w16):
+        assert t.dtype == torch.bfloat16 and t.is_contiguous() and t.is_cuda
+    assert bias32.dtype == torch.float32 and bias32.is_contiguous()
+    out = torch.empty_like(q)
+    out32 = torch.empty((b, n, 256), dtype=torch.float32, device=q.device) if keep_f32 else None
+    lse2 = torch.empty((b, n), dtype=torch.float32, device=q.device)
+    proj = torch.empty((b, n, 256), dtype=torch.bfloat16, device=q.device)
+    with _Timed("attn_fwd", 4.0 * b * n * m * 256):
+        rc = lib.sam2b200_attn_fwd_proj(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+                                        out32.data_ptr() if out32 is not None else None, lse2.data_ptr(), w16.data_ptr(),
+                                        bias32.data_ptr(), proj.data_ptr(), b, n, m, scale, *_drop_args(drop), _stream(q.device))
+    _lib.check(rc, "sam2b200_attn_fwd_proj")
+    return out, out32, lse2, proj
+
+
+def attn_fwd_v64_proj(q, k, memv, w16, bias32, rank1_32, scale: float, keep_f32: bool = True, drop=None):
+    """attn_fwd_v64 with the folded projection out_proj(v_proj(.)) fused into the epilogue (sam2b200_attn_fwd_v64_proj):
+    returns (out64 bf16, out64 fp32 | None, lse2, rowsum | None, proj bf16 [B, N, 256] = out64 @ w16^T + bias32 (+ rowsum x rank1_32))."""
+    lib = _lib.load()
+    b, n, d = q.shape
+    m = k.shape[1]
+    assert d == 256 and k.shape == (b, m, 256) and memv.shape == (b, m, 64) and w16.shape == (256, 64)
+    for t in (q, k, memv, w16):
+        assert t.dtype == torch.bfloat16 and t.is_contiguous() and t.is_cuda
+    assert bias32.dtype == torch.float32 and bias32.shape == (256,) and (rank1_32 is None or rank1_32.dtype == torch.float32)
+    out = torch.empty((b, n, 64), dtype=torch.bfloat16, device=q.device)
+    out32 = torch.empty((b, n, 64), dtype=torch.float32, device=q.device) if keep_f32 else None
+    lse2 = torch.empty((b, n), dtype=torch.float32, device=q.device)
+    rowsum = torch.empty((b, n), dtype=torch.float32, device=q.device) if drop is not None else None
+    proj = torch.empty((b, n, 256), dtype=torch.bfloat16, device=q.device)
+    with _Timed("attn_fwd", 4.0 * b * n * m * 256):
+        rc = lib.sam2b200_attn_fwd_v64_proj(q.data_ptr(), k.data_ptr(), memv.data_ptr(), out.data_ptr(),
+                                            out32.data_ptr() if out32 is not None else None, lse2.data_ptr(),
+                                            rowsum.data_ptr() if rowsum is not None else None, w16.data_ptr(), bias32.data_ptr(),
+                                            rank1_32.data_ptr() if rank1_32 is not None else None, proj.data_ptr(), b, n, m, scale,
+                                            *_drop_args(drop), _stream(q.device))
+    _lib.check(rc, "sam2b200_attn_fwd_v64_proj")
+    return out, out32, lse2, rowsum, proj
+
+
 def attn_bwd(q, k, v, out, out32, dout, lse2, scale: float, table=None, n_rope_k: int = 0, grad_dtype=torch.float32,
              dq=None, dk=None, dv=None, dbias=(None, None, None), parts: int = 0, delta=None, drop=None):
     """Backward of the attention core.  With `table` the conjugate RoPE is fused into the epilogue (dq / dk are then

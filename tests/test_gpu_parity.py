@@ -264,8 +264,10 @@ def test_fused_stack_raw_memory_cross_attention_vs_oracle(dev, monkeypatch):
     from sam2_video_training_b200 import fused_stack
     from sam2_video_training_b200.modeling.memory_attention import build_memory_attention
     calls = {"fwd": 0, "bwd": 0}
-    f0, b0 = fused_stack.attn_fwd_v64, fused_stack.attn_bwd_v64
+    f0, f1, b0 = fused_stack.attn_fwd_v64, fused_stack.attn_fwd_v64_proj, fused_stack.attn_bwd_v64
     monkeypatch.setattr(fused_stack, "attn_fwd_v64", lambda *a, **k: (calls.__setitem__("fwd", calls["fwd"] + 1), f0(*a, **k))[1])
+    # (default: the variant with the folded output projection in its epilogue)
+    monkeypatch.setattr(fused_stack, "attn_fwd_v64_proj", lambda *a, **k: (calls.__setitem__("fwd", calls["fwd"] + 1), f1(*a, **k))[1])
     monkeypatch.setattr(fused_stack, "attn_bwd_v64", lambda *a, **k: (calls.__setitem__("bwd", calls["bwd"] + 1), b0(*a, **k))[1])
     params = ao.init_params(seed=0)
     grid, b, nf, nptr = 8, 64, 5, 12        # 3 key blocks x 64 objects > #SMs: the persistent dK kernel
@@ -1053,6 +1055,44 @@ def test_gradient_epilogue_axial_table_addressing_bit_identical(dev, grid):
         lib.sam2b200_debug_set_variant(1, 0)
     for x, y in zip(res[0], res[1]):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("b,grid,nf,nptr,drop", [(3, 12, 2, 8, 0.0), (2, 24, 7, 28, 0.0), (40, 8, 3, 12, 0.0), (2, 16, 2, 4, 0.1)])
+def test_attention_forward_with_fused_output_projection(dev, b, grid, nf, nptr, drop):
+    """The output projection (transformer.py:308-309) inside the attention kernels' epilogue: sam2b200_attn_fwd_proj (256-d
+    values, Wo) and sam2b200_attn_fwd_v64_proj (raw memory features, folded Wo Wv; with dropout the rank-1 row-sum term).  The
+    un-projected outputs / lse must be BIT-IDENTICAL to the un-fused kernels; the projection is compared with an fp32 GEMM on
+    the kernel's own bf16 output (the tile the tensor core multiplies) -- ragged last query tile, several key tiles."""
+    from sam2_video_training_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(55)
+    n = grid * grid
+    m = nf * n + nptr
+    q = torch.randn(b, n, 256, device=dev, generator=g).to(torch.bfloat16)
+    k = torch.randn(b, m, 256, device=dev, generator=g).to(torch.bfloat16)
+    v = torch.randn(b, m, 256, device=dev, generator=g).to(torch.bfloat16)
+    mem = torch.randn(b, m, 64, device=dev, generator=g).to(torch.bfloat16)
+    wo = (torch.randn(256, 256, device=dev, generator=g) / 16).to(torch.bfloat16)
+    weff = (torch.randn(256, 64, device=dev, generator=g) / 8).to(torch.bfloat16)
+    bias = torch.randn(256, device=dev, generator=g) * 0.3
+    rank1 = torch.randn(256, device=dev, generator=g) * 0.3
+    dr = (drop, torch.tensor([777], dtype=torch.int64, device=dev), 6) if drop > 0 else None
+    # 256-d values
+    o0, o0_32, lse0 = ops.attn_fwd(q, k, v, 1 / 16.0, 1, drop=dr)
+    o1, o1_32, lse1, proj = ops.attn_fwd_proj(q, k, v, wo, bias, 1 / 16.0, drop=dr)
+    torch.cuda.synchronize()
+    assert torch.equal(o0, o1) and torch.equal(lse0, lse1) and torch.equal(o0_32, o1_32)
+    want = o1.float() @ wo.float().t() + bias
+    assert rel_l2(proj, want) < 4e-3, rel_l2(proj, want)
+    # raw memory features + folded projection
+    a0 = ops.attn_fwd_v64(q, k, mem, 1 / 16.0, drop=dr)
+    a1 = ops.attn_fwd_v64_proj(q, k, mem, weff, bias, rank1 if dr is not None else None, 1 / 16.0, drop=dr)
+    torch.cuda.synchronize()
+    assert torch.equal(a0[0], a1[0]) and torch.equal(a0[1], a1[1]) and torch.equal(a0[2], a1[2])
+    want = a1[0].float() @ weff.float().t() + bias
+    if dr is not None:
+        assert torch.equal(a0[3], a1[3])
+        want = want + a1[3][..., None] * rank1
+    assert rel_l2(a1[4], want) < 4e-3, rel_l2(a1[4], want)
 
 
 def test_attention_backward_fused_bias_gradients(dev):

@@ -222,6 +222,21 @@ NO_FOLD = bool(os.environ.get("SAM2B200_NO_FOLD"))  # A/B switch: v_proj and out
 NO_V64 = bool(os.environ.get("SAM2B200_NO_V64"))    # A/B switch: cross-attention on the projected 256-d values (with the dV kernel)
 NO_PROJ_KERNEL = not bool(os.environ.get("SAM2B200_PROJ_KERNEL"))
 PROJ_KERNEL_K64 = bool(os.environ.get("SAM2B200_PROJ_KERNEL_K64"))
+# q / k / v bias gradients: column sums of dq / dk / dv.  Default: the attention kernels' gradient epilogues accumulate them
+# (31-shuffle butterfly + fp32 atomics per 32 x 32 block, ~6 % of the backward kernels' time).  SAM2B200_SIDE_STREAM_BIAS=1 = a
+# separate column-sum pass on the side stream instead: the attention backward gets 1.0 ms faster at cfg2 (roofline 0.465 ->
+# 0.497) but the STEP gets 0.5 ms slower -- both streams together saturate the GPU, so re-reading the gradients (116 MB for the
+# cross-attention keys) costs more than the epilogue arithmetic (profiles/r2_bias_gradient_ab.txt).  Not the default.
+EPILOGUE_BIAS = not bool(os.environ.get("SAM2B200_SIDE_STREAM_BIAS"))
+
+
+def bias_grad_(gbias, dx16):
+    """gbias [C] fp32 += column sums of dx16 [R, C] bf16 (C = 256 or 768; row stride may exceed C): the two-stage
+    deterministic column-sum kernel of csrc/glue.cu (HBM bound, ~6 us for a [32 256 x 256] gradient)."""
+    assert dx16.dtype == BF16 and dx16.stride(1) == 1
+    _colsum(2, None, dx16, None, gbias, dx16.shape[0], dx16.shape[1], ld=dx16.stride(0))
+
+
 NO_FUSED_OUT_PROJ = bool(os.environ.get("SAM2B200_NO_FUSED_OUT_PROJ"))   # A/B switch: out_proj as a separate cuBLAS addmm after the attention kernel
 NO_LNPROJ = bool(os.environ.get("SAM2B200_NO_LNPROJ"))     # A/B switch: ln_fwd + cuBLAS addmm + RoPE pass instead of sam2b200_ln_proj
 NO_MLP_KERNEL = bool(os.environ.get("SAM2B200_NO_MLP_KERNEL"))     # A/B switch: cuBLAS GEMM + separate ReLU-backward pass
@@ -694,8 +709,10 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                 args = (q2_rot, k2_rot, memv.view(b, m, 64), do64, lse2, delta, scale)
 
                 def key_side(args=args, kw=kw, l=l, ix=ix, W=W):
-                    _, dk2 = attn_bwd_v64(*args, parts=4, dbias=(None, gv[ix["ca.k.b"]]), **kw)
+                    _, dk2 = attn_bwd_v64(*args, parts=4, dbias=(None, gv[ix["ca.k.b"]] if EPILOGUE_BIAS else None), **kw)
                     dk2 = dk2.view(rm, d)
+                    if not EPILOGUE_BIAS:
+                        bias_grad_(gv[ix["ca.k.b"]], dk2)
                     if direct:
                         torch.addmm(gv[ix["ca.k.w"]], dk2.t(), memk, out_dtype=F32, out=gv[ix["ca.k.w"]])
                     else:
@@ -703,7 +720,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                     if need_memgrad:
                         torch.addmm(dmemk, dk2, W["ca.k.w"], out_dtype=F32, out=dmemk)
                 side.run(key_side, q2_rot, k2_rot, memv, do64, lse2, delta, dp_bias)
-                dq2, _ = attn_bwd_v64(*args, parts=8, dbias=(gv[ix["ca.q.b"]], None), **kw)
+                dq2, _ = attn_bwd_v64(*args, parts=8, dbias=(gv[ix["ca.q.b"]] if EPILOGUE_BIAS else None, None), **kw)
             else:
                 delta = torch.empty((b, n), dtype=F32, device=dev)
                 args = (q2_rot, k2_rot, v2.view(b, m, d), None, o2_32, do2.view(b, n, d), lse2, scale)
@@ -711,8 +728,12 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                 attn_bwd(*args, parts=1, **kw)                                              # Delta = rowsum(dO o O)
 
                 def key_side(args=args, kw=kw, l=l, ix=ix, W=W):
-                    _, dk2, dv2 = attn_bwd(*args, parts=2 | 4, dbias=(None, gv[ix["ca.k.b"]], gv[ix["ca.v.b"]]), **kw)
+                    eb = EPILOGUE_BIAS
+                    _, dk2, dv2 = attn_bwd(*args, parts=2 | 4, dbias=(None, gv[ix["ca.k.b"]] if eb else None, gv[ix["ca.v.b"]] if eb else None), **kw)
                     dk2, dv2 = dk2.view(rm, d), dv2.view(rm, d)
+                    if not eb:
+                        bias_grad_(gv[ix["ca.k.b"]], dk2)
+                        bias_grad_(gv[ix["ca.v.b"]], dv2)
                     if direct:
                         torch.addmm(gv[ix["ca.k.w"]], dk2.t(), memk, out_dtype=F32, out=gv[ix["ca.k.w"]])
                         torch.addmm(gv[ix["ca.v.w"]], dv2.t(), memv, out_dtype=F32, out=gv[ix["ca.v.w"]])
@@ -724,10 +745,12 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                     if need_mem:
                         torch.addmm(dmemv, dv2, W["ca.v.w"], out_dtype=F32, out=dmemv)
                 side.run(key_side, *args[:3], o2_32, do2, lse2, delta)
-                dq2, _, _ = attn_bwd(*args, parts=8, dbias=(gv[ix["ca.q.b"]], None, None), **kw)
+                dq2, _, _ = attn_bwd(*args, parts=8, dbias=(gv[ix["ca.q.b"]] if EPILOGUE_BIAS else None, None, None), **kw)
             dq2 = dq2.view(r, d)
             dy2 = torch.mm(dq2, W["ca.q.w"])
             acc_w(ix["ca.q.w"], dq2.t(), y2)
+            if not EPILOGUE_BIAS:
+                side.run(lambda dq2=dq2, gb=gv[ix["ca.q.b"]]: bias_grad_(gb, dq2), dq2)
             g, dsa = ln_bwd(dy2, x1, mean2, rstd2, P["n2.w"], g, gv[ix["n2.w"]], gv[ix["n2.b"]], dbias=gv[ix["sa.o.b"]],
                             drop=dsite("p_res", l, 2))
             # ---- self attention backward
@@ -736,8 +759,17 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             dqkv = torch.empty((b, n, 3 * d), dtype=BF16, device=dev)   # [dq | dk | dv], written in place by the kernels
             attn_bwd(q_rot, k_rot, v.view(b, n, d), None, o32, do.view(b, n, d), lse, scale, table=table, n_rope_k=n,
                      grad_dtype=BF16, dq=dqkv[:, :, :d], dk=dqkv[:, :, d:2 * d], dv=dqkv[:, :, 2 * d:],
-                     dbias=(gv[ix["sa.q.b"]], gv[ix["sa.k.b"]], gv[ix["sa.v.b"]]), drop=dsite("p_sa", l, 0))
+                     dbias=(gv[ix["sa.q.b"]], gv[ix["sa.k.b"]], gv[ix["sa.v.b"]]) if EPILOGUE_BIAS else (None, None, None),
+                     drop=dsite("p_sa", l, 0))
             dqkv = dqkv.view(r, 3 * d)
+            if not EPILOGUE_BIAS:
+                qkv_b = [masters[ix[k]] for k in ("sa.q.b", "sa.k.b", "sa.v.b")]
+                gb = bucket.span(qkv_b, (3 * d,)) if direct else None
+                if gb is not None:      # the bucket lays the three biases out back to back: one [1 x R] . [R x 768] product
+                    side.run(lambda dqkv=dqkv, gb=gb: bias_grad_(gb, dqkv), dqkv)
+                else:
+                    for j, kb in enumerate(("sa.q.b", "sa.k.b", "sa.v.b")):
+                        side.run(lambda dx=dqkv[:, j * d:(j + 1) * d], g_=gv[ix[kb]]: bias_grad_(g_, dx), dqkv)
             qkv_w = [masters[ix[k]] for k in ("sa.q.w", "sa.k.w", "sa.v.w")]
             gw = bucket.span(qkv_w, (3 * d, d)) if direct else None
             if gw is not None:

@@ -237,6 +237,13 @@ int sam2b200_merged_loss_bwd(const float* const* low_res, float* const* dlow_res
                              const int* n_valid, const float* grad_losses, float* d_obj_iou, int T, int C, int n_obj, int s,
                              float alpha, float gamma, float inv_temp, int iou_l1, sam2b200_stream_t stream);
 
+/* ---- weight gradients: c [Mo, ldc] fp32 += a[R, Mo]^T . b[R, No] (csrc/wgrad.cu) ------------------------------------------
+ * dW = dY^T X of every nn.Linear of the stack (sam2_video/model/modeling/memory_attention.py:97, sam/transformer.py:213-216),
+ * accumulated IN PLACE into the fp32 gradient (split over R, partial tiles added with vector fp32 reductions: no workspace,
+ * no reduce pass).  a, b: bf16 with row strides lda / ldb (elements); Mo a multiple of 256, No = 64 or a multiple of 256. */
+int sam2b200_wgrad(float* c, long long ldc, const void* a, long long lda, const void* b, long long ldb, long long R, int Mo, int No,
+                   cudaStream_t stream);
+
 /* ---- LayerNorm + projection (+ RoPE | ReLU) in one kernel (csrc/lnproj.cu) ------------------------------------------
  * The head of every pre-norm block of MemoryAttentionLayer (sam2_video/model/modeling/memory_attention.py:58-64, 66-81,
  * 95-97 with the projections of sam2_video/model/modeling/sam/transformer.py:277-302):

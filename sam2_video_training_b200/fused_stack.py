@@ -156,6 +156,19 @@ def ln_proj(x, res, gamma, beta, w16, bias16, n_out, out_width=256, table=None, 
     return outs, y, x_new, mean, rstd
 
 
+def wgrad_(c32, a16, b16):
+    """c32 [Mo, No] fp32 += a16[R, Mo]^T @ b16[R, No] in place (sam2b200_wgrad: split over R, tcgen05, partial tiles added with
+    fp32 reductions).  Row strides may exceed the widths (column slices of wider buffers)."""
+    r, mo = a16.shape
+    no = b16.shape[1]
+    assert c32.shape == (mo, no) and c32.dtype == F32 and c32.stride(1) == 1
+    assert a16.dtype == BF16 and b16.dtype == BF16 and a16.stride(1) == 1 and b16.stride(1) == 1 and b16.shape[0] == r
+    rc = _lib.load().sam2b200_wgrad(c32.data_ptr(), c32.stride(0), a16.data_ptr(), a16.stride(0), b16.data_ptr(), b16.stride(0), r, mo, no,
+                                    _stream(c32.device))
+    _lib.check(rc, "sam2b200_wgrad")
+    return c32
+
+
 def mlp_dh(dm16, w2_16, h16, scale=1.0):
     """dh = (dm @ W2) * (h > 0) * scale in one tcgen05 GEMM with the ReLU / hidden-dropout backward in its epilogue."""
     r, f = h16.shape
@@ -235,6 +248,16 @@ def bias_grad_(gbias, dx16):
     deterministic column-sum kernel of csrc/glue.cu (HBM bound, ~6 us for a [32 256 x 256] gradient)."""
     assert dx16.dtype == BF16 and dx16.stride(1) == 1
     _colsum(2, None, dx16, None, gbias, dx16.shape[0], dx16.shape[1], ld=dx16.stride(0))
+
+
+# Weight gradients with 64 or <= 768 x 256 outputs go to sam2b200_wgrad (own split-K tcgen05 kernel, in-place fp32 accumulation: 10.5
+# vs 14.9 us for [256 x 256], 17.6 vs 20.8 us for the stacked q|k|v, 29 vs 35 us for the memory-key projection); the two MLP weights
+# ([256 x 2048], [2048 x 256]) stay on cuBLAS, which is 5-15 % faster there (profiles/r2_wgrad_bench.txt).  A/B: SAM2B200_NO_WGRAD=1.
+NO_WGRAD = bool(os.environ.get("SAM2B200_NO_WGRAD"))
+
+
+def _wgrad_ok(mo, no):
+    return (not NO_WGRAD) and mo % 256 == 0 and (no == 64 or (no == 256 and mo <= 768))
 
 
 NO_FUSED_OUT_PROJ = bool(os.environ.get("SAM2B200_NO_FUSED_OUT_PROJ"))   # A/B switch: out_proj as a separate cuBLAS addmm after the attention kernel
@@ -629,7 +652,12 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             def work():
                 if bias is not None:
                     colsum_bf16(a_t.t(), bias)
-                if direct:
+                if _wgrad_ok(a_t.shape[0], bmat.shape[1]) and a_t.stride(0) == 1:
+                    if direct:
+                        wgrad_(gv[i], a_t.t(), bmat)
+                    else:
+                        grads[i] = wgrad_(torch.zeros((a_t.shape[0], bmat.shape[1]), dtype=F32, device=bmat.device), a_t.t(), bmat)
+                elif direct:
                     torch.addmm(gv[i], a_t, bmat, out_dtype=F32, out=gv[i])
                 else:
                     grads[i] = _mm32(a_t, bmat)
@@ -687,7 +715,10 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                     dp_bias = _mm32(dca, weight_mirror(masters).wobv[l].view(d, 1)).view(b, n) if ca_drop else None
 
                     def fold_grads(dca=dca, o64=o64, g_bo=g_bo, g_rs=g_rs, ix=ix, P=P):
-                        G = _mm32(dca.t(), o64.view(r, 64))
+                        if _wgrad_ok(d, 64):
+                            G = wgrad_(torch.zeros((d, 64), dtype=F32, device=dev), dca, o64.view(r, 64))
+                        else:
+                            G = _mm32(dca.t(), o64.view(r, 64))
                         d_wo = torch.addmm(torch.outer(g_rs, P["ca.v.b"]), G, P["ca.v.w"].t())
                         d_wv = torch.mm(P["ca.o.w"].t(), G)
                         gv[ix["ca.o.b"]].add_(g_bo)
@@ -713,7 +744,12 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                     dk2 = dk2.view(rm, d)
                     if not EPILOGUE_BIAS:
                         bias_grad_(gv[ix["ca.k.b"]], dk2)
-                    if direct:
+                    if _wgrad_ok(d, 64):
+                        if direct:
+                            wgrad_(gv[ix["ca.k.w"]], dk2, memk)
+                        else:
+                            grads[ix["ca.k.w"]] = wgrad_(torch.zeros((d, 64), dtype=F32, device=dev), dk2, memk)
+                    elif direct:
                         torch.addmm(gv[ix["ca.k.w"]], dk2.t(), memk, out_dtype=F32, out=gv[ix["ca.k.w"]])
                     else:
                         grads[ix["ca.k.w"]] = _mm32(dk2.t(), memk)
@@ -774,7 +810,10 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             gw = bucket.span(qkv_w, (3 * d, d)) if direct else None
             if gw is not None:
                 # the bucket lays the three projection weights out back to back: one [768, 256] weight-gradient GEMM
-                side.run(lambda dqkv=dqkv, y1=y1, gw=gw: torch.addmm(gw, dqkv.t(), y1, out_dtype=F32, out=gw), dqkv, y1)
+                if _wgrad_ok(3 * d, d):
+                    side.run(lambda dqkv=dqkv, y1=y1, gw=gw: wgrad_(gw, dqkv, y1), dqkv, y1)
+                else:
+                    side.run(lambda dqkv=dqkv, y1=y1, gw=gw: torch.addmm(gw, dqkv.t(), y1, out_dtype=F32, out=gw), dqkv, y1)
             elif direct:
                 for j, kw in enumerate(("sa.q.w", "sa.k.w", "sa.v.w")):
                     acc_w(ix[kw], dqkv[:, j * d:(j + 1) * d].t(), y1)

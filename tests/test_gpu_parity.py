@@ -616,6 +616,25 @@ def test_ln_proj_kernel(dev, mode, b, length, with_res, drop):
         assert rel_l2(got, want) < 4e-3, (mode, rel_l2(got, want))
 
 
+@pytest.mark.parametrize("r,mo,no", [(200, 256, 256), (4096, 256, 64), (1000, 768, 256), (3000, 256, 2048), (2500, 2048, 256), (33, 256, 64),
+                                    (32256, 256, 256)])
+def test_wgrad_kernel(dev, r, mo, no):
+    """sam2b200_wgrad: c += a^T b (bf16 operands, fp32 accumulation, split over the rows, partial tiles added with fp32
+    reductions) against an fp32 GEMM on the same bf16 operands -- ragged row counts, strided operands (column slices of wider
+    buffers, as the stacked q|k|v gradient is), accumulation into a non-zero c."""
+    from sam2_video_training_b200 import fused_stack as fs
+    g = torch.Generator(device="cuda").manual_seed(r + mo + no)
+    a_wide = torch.randn(r, mo + 64, device=dev, generator=g).to(torch.bfloat16)
+    b_wide = torch.randn(r, no + 128, device=dev, generator=g).to(torch.bfloat16)
+    a, b = a_wide[:, 64:], b_wide[:, :no]
+    c0 = torch.randn(mo, no, device=dev, generator=g)
+    c = c0.clone()
+    fs.wgrad_(c, a, b)
+    torch.cuda.synchronize()
+    want = c0.double() + a.double().t() @ b.double()
+    assert rel_l2(c, want) < 2e-5, rel_l2(c, want)
+
+
 @pytest.mark.parametrize("rows", [128, 700, 4096])
 def test_mlp_dh_kernel(dev, rows):
     """sam2b200_mlp_dh: dh = (dm @ W2) * (h > 0) * scale (tcgen05 GEMM, ReLU / hidden-dropout backward in the epilogue)

@@ -237,6 +237,19 @@ int sam2b200_merged_loss_bwd(const float* const* low_res, float* const* dlow_res
                              const int* n_valid, const float* grad_losses, float* d_obj_iou, int T, int C, int n_obj, int s,
                              float alpha, float gamma, float inv_temp, int iou_l1, sam2b200_stream_t stream);
 
+/* ---- memory encoder (sam2_video/model/modeling/memory_encoder.py; csrc/memenc.cu), channels-last fp32 ------------------
+ * ln_gelu: y [P, C] = act(LayerNorm_C(x) * w + b), the LayerNorm2d (sam2_utils.py:141-153) + GELU pair that follows every
+ * strided convolution of MaskDownSampler (memory_encoder.py:38-53); C in {4, 16, 64, 256}; act != 0 = exact GELU.
+ * The backward writes dx and ADDS the parameter gradients to dw / db [C].
+ * dwconv7: depth-wise 7 x 7 convolution, padding 3, of CXBlock (memory_encoder.py:84-91) on x [B, H, W, C], w [C, 7, 7];
+ * flip != 0 mirrors the taps (= the data gradient when called on dy); dwconv7_bwd_w ADDS dw [C, 7, 7] and db [C]. */
+int sam2b200_ln_gelu_fwd(const float* x, const float* w, const float* b, float* y, long long P, int C, float eps, int act,
+                         cudaStream_t stream);
+int sam2b200_ln_gelu_bwd(const float* dy, const float* x, const float* w, const float* b, float* dx, float* dw, float* db, long long P, int C,
+                         float eps, int act, cudaStream_t stream);
+int sam2b200_dwconv7(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int C, int flip, cudaStream_t stream);
+int sam2b200_dwconv7_bwd_w(const float* dy, const float* x, float* dw, float* db, int B, int H, int W, int C, cudaStream_t stream);
+
 /* ---- weight gradients: c [Mo, ldc] fp32 += a[R, Mo]^T . b[R, No] (csrc/wgrad.cu) ------------------------------------------
  * dW = dY^T X of every nn.Linear of the stack (sam2_video/model/modeling/memory_attention.py:97, sam/transformer.py:213-216),
  * accumulated IN PLACE into the fp32 gradient (split over R, partial tiles added with vector fp32 reductions: no workspace,

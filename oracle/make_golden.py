@@ -269,6 +269,45 @@ def golden_loss_multimask(ns, t, c, m, s, tag):
     return rec
 
 
+MEMENC_FULL_GRADS = ("mask_downsampler.encoder.0.weight", "mask_downsampler.encoder.1.weight", "mask_downsampler.encoder.4.bias",
+                     "mask_downsampler.encoder.6.weight", "mask_downsampler.encoder.10.weight", "mask_downsampler.encoder.12.bias",
+                     "pix_feat_proj.bias", "fuser.layers.0.dwconv.weight", "fuser.layers.0.norm.weight", "fuser.layers.1.gamma",
+                     "fuser.layers.1.pwconv1.bias", "fuser.layers.0.pwconv2.bias", "out_proj.weight", "fuser.layers.1.dwconv.bias")
+
+
+def golden_memory_encoder(b, grid, tag, skip_mask_sigmoid, seed=77):
+    """The UNMODIFIED reference MemoryEncoder (its own init under torch.manual_seed(0); layer scales moved to 0.5 +- 0.1, see
+    memenc_oracle.reference_init_state) on N(0, 1) features / N(0, 16) mask logits: outputs, input gradients, per-parameter
+    |grad| sums, fourteen full parameter gradients, checksums of the regenerated weights / inputs."""
+    from . import memenc_oracle as mo
+    torch.manual_seed(0)
+    model = ref_shim.build_memory_encoder()
+    sd = mo.reference_init_state(0)
+    with torch.no_grad():
+        for i in range(2):
+            model.fuser.layers[i].gamma.copy_(sd[f"fuser.layers.{i}.gamma"])
+    ref_sd = dict(model.named_parameters())
+    assert list(ref_sd.keys()) == list(dict(model.named_parameters()).keys()) and set(ref_sd) == set(sd), set(ref_sd) ^ set(sd)
+    for n, p in ref_sd.items():
+        assert torch.equal(p.detach(), sd[n]), n           # the regenerated init IS the reference's
+    inp = mo.random_inputs(b, grid, seed)
+    pix = inp["pix_feat"].clone().requires_grad_(True)
+    masks = inp["masks"].clone().requires_grad_(True)
+    m_in = torch.sigmoid(masks) * 20.0 - 10.0 if skip_mask_sigmoid else masks     # sam2_base.py:741-747 scales before the call
+    out = model(pix, m_in, skip_mask_sigmoid=skip_mask_sigmoid)
+    out["vision_features"].backward(inp["grad_out"])
+    names = [n for n, _ in model.named_parameters()]
+    rec = dict(b=b, grid=grid, seed=seed, skip=int(skip_mask_sigmoid), features=out["vision_features"].detach().numpy(),
+               pos=out["vision_pos_enc"][0].detach().numpy(), d_pix_feat=pix.grad.numpy(), d_masks=masks.grad.numpy(),
+               param_names=np.array(names), weight_abs_sums=np.array([float(ref_sd[n].detach().double().abs().sum()) for n in names]),
+               param_grad_abs_sums=np.array([float(ref_sd[n].grad.double().abs().sum()) for n in names]),
+               input_abs_sums=np.array([float(inp[k].double().abs().sum()) for k in ("pix_feat", "masks", "grad_out")]))
+    for n in MEMENC_FULL_GRADS:
+        rec["dparam:" + n] = ref_sd[n].grad.numpy()
+    np.savez_compressed(os.path.join(OUT, f"memenc_{tag}.npz"), **rec)
+    return rec
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_shim.load()
@@ -284,6 +323,10 @@ def main():
     print("attn refinit g24: out abs", float(np.abs(r["out"]).sum()))
     r = golden_attention_refinit(ns, 8, 3, 3, 12, "g8_b3_f3_p12", seed=4321)
     print("attn refinit g8: out abs", float(np.abs(r["out"]).sum()))
+    r = golden_memory_encoder(2, 4, "b2_g4_sigmoid", False)
+    print("memory encoder: |features|", float(np.abs(r["features"]).sum()))
+    r = golden_memory_encoder(3, 6, "b3_g6_scaled", True, seed=78)
+    print("memory encoder (scaled masks): |features|", float(np.abs(r["features"]).sum()))
     r = golden_loss(ns, 2, 3, 16, "t2_c3_s16")
     print("loss: l1 total", r["l1:total_loss"], "mse total", r["mse:total_loss"], "bce", r["bce:total_loss"])
     r = golden_loss_multimask(ns, 2, 3, 3, 16, "t2_c3_m3_s16")

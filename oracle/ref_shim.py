@@ -83,6 +83,23 @@ def load_sam2_base():
     return _cache["sam2_base"].SAM2Base
 
 
+def load_memory_encoder():
+    """The reference's memory-encoder module (sam2_video/model/modeling/memory_encoder.py) and PositionEmbeddingSine."""
+    ns = load()
+    if "memory_encoder" not in _cache:
+        _cache["memory_encoder"] = _load("sam2.modeling.memory_encoder", os.path.join(_MODELING, "memory_encoder.py"))
+    return _cache["memory_encoder"], ns.position_encoding
+
+
+def build_memory_encoder():
+    """configs/sam2/sam2.1_hiera_t.yaml:62-85 through the reference's own constructors, sub-modules created in yaml order."""
+    me, pe = load_memory_encoder()
+    position_encoding = pe.PositionEmbeddingSine(num_pos_feats=64, normalize=True, scale=None, temperature=10000)
+    mask_downsampler = me.MaskDownSampler(kernel_size=3, stride=2, padding=1)
+    fuser = me.Fuser(layer=me.CXBlock(dim=256, kernel_size=7, padding=3, layer_scale_init_value=1e-6, use_dwconv=True), num_layers=2)
+    return me.MemoryEncoder(out_dim=64, position_encoding=position_encoding, mask_downsampler=mask_downsampler, fuser=fuser)
+
+
 def load_masks():
     """The reference's ``sam2_video/utils/masks.py`` (``merge_object_results_to_category``), loaded by path: the
     package ``__init__`` pulls in out-of-scope modules, the file itself needs only torch, numpy, cv2 and loguru."""

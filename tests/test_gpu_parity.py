@@ -1363,3 +1363,118 @@ def test_merged_loss_error_contract(dev):
         crit(_merged_stages([low], [iou]), [0, 5], 2, torch.ones(1, 2, 32, 32, dtype=torch.bool, device=dev))
     with pytest.raises(AssertionError):                                # losses.py:113
         crit(_merged_stages([low, low], [iou, iou]), [0, 1], 2, tg)
+
+
+# ---- memory encoder -------------------------------------------------------------------------
+
+@pytest.mark.parametrize("c,p_,act", [(4, 1000, True), (16, 777, True), (64, 4097, True), (256, 513, True), (256, 64, False)])
+def test_ln_gelu_kernels(dev, c, p_, act):
+    """sam2b200_ln_gelu_fwd / _bwd (LayerNorm2d + exact GELU over the channels of channels-last pixels) against fp64 torch."""
+    from sam2_video_training_b200.modeling.memory_encoder import _LnGeluFn
+    g = torch.Generator(device="cuda").manual_seed(c + p_)
+    x = (torch.randn(p_, c, device=dev, generator=g) * 1.7 + 0.3).requires_grad_(True)
+    w = (1 + 0.2 * torch.randn(c, device=dev, generator=g)).requires_grad_(True)
+    b = (0.2 * torch.randn(c, device=dev, generator=g)).requires_grad_(True)
+    go = torch.randn(p_, c, device=dev, generator=g)
+    y = _LnGeluFn.apply(x, w, b, 1e-6, act)
+    y.backward(go)
+    xd, wd, bd = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    z = torch.nn.functional.layer_norm(xd, (c,), wd, bd, 1e-6)
+    ref = torch.nn.functional.gelu(z) if act else z
+    ref.backward(go.double())
+    assert rel_l2(y, ref) < 2e-6
+    assert rel_l2(x.grad, xd.grad) < 2e-5 and rel_l2(w.grad, wd.grad) < 2e-5 and rel_l2(b.grad, bd.grad) < 2e-5
+
+
+@pytest.mark.parametrize("b,h,w", [(2, 24, 24), (3, 5, 9), (1, 32, 32)])
+def test_dwconv7_kernels(dev, b, h, w):
+    """sam2b200_dwconv7 / _bwd_w (depth-wise 7 x 7, padding 3, channels-last) against F.conv2d(groups = C) in fp64."""
+    from sam2_video_training_b200.modeling.memory_encoder import _DwConv7Fn
+    g = torch.Generator(device="cuda").manual_seed(b * h + w)
+    c = 256
+    x = torch.randn(b, h, w, c, device=dev, generator=g).requires_grad_(True)
+    wt = (torch.randn(c, 1, 7, 7, device=dev, generator=g) / 7).requires_grad_(True)
+    bias = (0.1 * torch.randn(c, device=dev, generator=g)).requires_grad_(True)
+    go = torch.randn(b, h, w, c, device=dev, generator=g)
+    y = _DwConv7Fn.apply(x, wt, bias)
+    y.backward(go)
+    xd, wd, bd = (t.detach().double().requires_grad_(True) for t in (x, wt, bias))
+    ref = torch.nn.functional.conv2d(xd.permute(0, 3, 1, 2), wd, bd, padding=3, groups=c).permute(0, 2, 3, 1)
+    ref.backward(go.double())
+    assert rel_l2(y, ref) < 2e-6
+    assert rel_l2(x.grad, xd.grad) < 2e-6 and rel_l2(wt.grad, wd.grad) < 2e-5 and rel_l2(bias.grad, bd.grad) < 2e-5
+
+
+@pytest.mark.parametrize("tag", ["b2_g4_sigmoid", "b3_g6_scaled"])
+def test_memory_encoder_vs_reference_golden(dev, golden_dir, tag):
+    """MemoryEncoder (B200 path) against the UNMODIFIED reference class (tests/golden/memenc_*.npz): same state_dict keys, the
+    reference's own init reproduced by constructing the module under torch.manual_seed(0); features within 1e-2 relative
+    (bf16 tensor-core GEMMs vs the reference's fp32), position encoding exact, input / parameter gradient cosines >= 0.999."""
+    from oracle import memenc_oracle as mo
+    from sam2_video_training_b200.modeling.memory_encoder import build_memory_encoder
+    g = np.load(os.path.join(golden_dir, f"memenc_{tag}.npz"))
+    b, grid, seed, skip = int(g["b"]), int(g["grid"]), int(g["seed"]), bool(int(g["skip"]))
+    torch.manual_seed(0)
+    model = build_memory_encoder()
+    names = [str(n) for n in g["param_names"]]
+    assert [n for n, _ in model.named_parameters()] == names          # the reference's state_dict layout
+    sd = mo.reference_init_state(0)
+    with torch.no_grad():
+        for i in range(2):
+            model.fuser.layers[i].gamma.copy_(sd[f"fuser.layers.{i}.gamma"])
+    for n, p in model.named_parameters():                              # same RNG consumption as the reference constructors
+        assert torch.equal(p.detach(), sd[n]), n
+    model = model.to(dev).train()
+    inp = mo.random_inputs(b, grid, seed)
+    pix = inp["pix_feat"].to(dev).requires_grad_(True)
+    masks = inp["masks"].to(dev).requires_grad_(True)
+    m_in = torch.sigmoid(masks) * 20.0 - 10.0 if skip else masks
+    out = model(pix, m_in, skip_mask_sigmoid=skip)
+    feat, pos = out["vision_features"], out["vision_pos_enc"][0]
+    feat.backward(inp["grad_out"].to(dev))
+    torch.cuda.synchronize()
+    assert feat.shape == (b, 64, grid, grid) and pos.shape == feat.shape
+    assert rel_l2(feat, torch.from_numpy(g["features"])) < ATTN_REL_TOL, rel_l2(feat, torch.from_numpy(g["features"]))
+    assert rel_l2(pos, torch.from_numpy(g["pos"])) < 1e-6
+    assert cosine(pix.grad, torch.from_numpy(g["d_pix_feat"])) > GRAD_COS_TOL
+    assert cosine(masks.grad, torch.from_numpy(g["d_masks"])) > GRAD_COS_TOL
+    named = dict(model.named_parameters())
+    for key in g.files:
+        if key.startswith("dparam:"):
+            c_ = cosine(named[key[7:]].grad, torch.from_numpy(g[key]))
+            assert c_ > GRAD_COS_TOL, (key, c_)
+    for n, s_ in zip(names, g["param_grad_abs_sums"]):
+        mine = float(named[n].grad.double().abs().sum())
+        assert abs(mine - s_) <= 5e-2 * max(abs(s_), 1e-3), (n, mine, s_)
+
+
+def test_memory_encoder_cfg2_shape_vs_oracle(dev):
+    """cfg2 frame shape (7 objects, 384 px masks -> 24 x 24 memory features) against oracle/memenc_oracle.py run in fp32 on the
+    device (TF32 off): the features feed the memory bank, so the output tolerance is the attention path's 1e-2."""
+    from oracle import memenc_oracle as mo
+    from sam2_video_training_b200.modeling.memory_encoder import build_memory_encoder
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+    model = build_memory_encoder()
+    sd = mo.reference_init_state(0)
+    with torch.no_grad():
+        for i in range(2):
+            model.fuser.layers[i].gamma.copy_(sd[f"fuser.layers.{i}.gamma"])
+    model = model.to(dev).train()
+    inp = {k: v.to(dev) for k, v in mo.random_inputs(7, 24, 5).items()}
+    pix = inp["pix_feat"].clone().requires_grad_(True)
+    masks = inp["masks"].clone().requires_grad_(True)
+    out = model(pix, torch.sigmoid(masks) * 20.0 - 10.0, skip_mask_sigmoid=True)
+    out["vision_features"].backward(inp["grad_out"])
+    p = {k: v.to(dev).clone().requires_grad_(True) for k, v in sd.items()}
+    pix_o = inp["pix_feat"].clone().requires_grad_(True)
+    masks_o = inp["masks"].clone().requires_grad_(True)
+    feat, pos = mo.memory_encoder(p, pix_o, torch.sigmoid(masks_o) * 20.0 - 10.0, skip_mask_sigmoid=True)
+    feat.backward(inp["grad_out"])
+    torch.cuda.synchronize()
+    assert rel_l2(out["vision_features"], feat) < ATTN_REL_TOL and rel_l2(out["vision_pos_enc"][0], pos) < 1e-6
+    assert cosine(pix.grad, pix_o.grad) > GRAD_COS_TOL and cosine(masks.grad, masks_o.grad) > GRAD_COS_TOL
+    mine = torch.cat([q.grad.flatten() for _, q in model.named_parameters()])
+    theirs = torch.cat([p[n].grad.flatten() for n, _ in model.named_parameters()])
+    assert cosine(mine, theirs) > GRAD_COS_TOL, cosine(mine, theirs)

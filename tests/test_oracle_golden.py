@@ -295,3 +295,33 @@ def test_merge_oracle_matches_reference_golden(golden_dir, tag):
             assert abs(float(l[k]) - float(g[f"{mode}:{k}"])) <= 1e-5 * max(1.0, abs(float(g[f"{mode}:{k}"])))
         np.testing.assert_allclose(x.grad.numpy(), g[f"{mode}:dlow"], rtol=0, atol=2e-7)
         np.testing.assert_allclose(p.grad.numpy(), g[f"{mode}:diou"], rtol=0, atol=2e-7)
+
+
+@pytest.mark.parametrize("tag", ["b2_g4_sigmoid", "b3_g6_scaled"])
+def test_memory_encoder_oracle_matches_reference(golden_dir, tag):
+    """oracle/memenc_oracle.py against the UNMODIFIED reference MemoryEncoder (tests/golden/memenc_*.npz): weights and
+    inputs are regenerated and proven identical by checksum; outputs, input gradients and every stored parameter gradient."""
+    from oracle import memenc_oracle as mo
+    g = np.load(os.path.join(golden_dir, f"memenc_{tag}.npz"))
+    b, grid, seed, skip = int(g["b"]), int(g["grid"]), int(g["seed"]), bool(int(g["skip"]))
+    sd = mo.reference_init_state(0)
+    names = [str(n) for n in g["param_names"]]
+    assert set(names) == set(sd)
+    for n, s_ in zip(names, g["weight_abs_sums"]):
+        assert abs(float(sd[n].double().abs().sum()) - s_) <= 1e-9 * max(s_, 1.0), n
+    inp = mo.random_inputs(b, grid, seed)
+    for k, s_ in zip(("pix_feat", "masks", "grad_out"), g["input_abs_sums"]):
+        assert abs(float(inp[k].double().abs().sum()) - s_) <= 1e-9 * s_, k
+    p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    pix = inp["pix_feat"].clone().requires_grad_(True)
+    masks = inp["masks"].clone().requires_grad_(True)
+    m_in = torch.sigmoid(masks) * 20.0 - 10.0 if skip else masks
+    feat, pos = mo.memory_encoder(p, pix, m_in, skip_mask_sigmoid=skip)
+    feat.backward(inp["grad_out"])
+    assert _l2(feat.detach().numpy(), g["features"]) < 2e-6 and _l2(pos.numpy(), g["pos"]) < 1e-6
+    assert _l2(pix.grad.numpy(), g["d_pix_feat"]) < 2e-5 and _l2(masks.grad.numpy(), g["d_masks"]) < 2e-4
+    for n, s_ in zip(names, g["param_grad_abs_sums"]):
+        assert abs(float(p[n].grad.double().abs().sum()) - s_) <= 2e-3 * max(abs(s_), 1e-4), n
+    for key in g.files:
+        if key.startswith("dparam:"):
+            assert _l2(p[key[7:]].grad.numpy(), g[key]) < 2e-4, key

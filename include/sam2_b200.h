@@ -242,13 +242,16 @@ int sam2b200_merged_loss_bwd(const float* const* low_res, float* const* dlow_res
  * strided convolution of MaskDownSampler (memory_encoder.py:38-53); C in {4, 16, 64, 256}; act != 0 = exact GELU.
  * The backward writes dx and ADDS the parameter gradients to dw / db [C].
  * dwconv7: depth-wise 7 x 7 convolution, padding 3, of CXBlock (memory_encoder.py:84-91) on x [B, H, W, C], w [C, 7, 7];
- * flip != 0 mirrors the taps (= the data gradient when called on dy); dwconv7_bwd_w ADDS dw [C, 7, 7] and db [C]. */
+ * flip != 0 mirrors the taps (= the data gradient when called on dy); dwconv7_bwd_w ADDS dw [C, 7, 7] and db [C] (per-block
+ * partial sums in `workspace`, folded in a fixed order: deterministic). */
 int sam2b200_ln_gelu_fwd(const float* x, const float* w, const float* b, float* y, long long P, int C, float eps, int act,
                          cudaStream_t stream);
 int sam2b200_ln_gelu_bwd(const float* dy, const float* x, const float* w, const float* b, float* dx, float* dw, float* db, long long P, int C,
                          float eps, int act, cudaStream_t stream);
 int sam2b200_dwconv7(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int C, int flip, cudaStream_t stream);
-int sam2b200_dwconv7_bwd_w(const float* dy, const float* x, float* dw, float* db, int B, int H, int W, int C, cudaStream_t stream);
+size_t sam2b200_dwconv7_bwd_w_workspace_bytes(int B, int H, int C);
+int sam2b200_dwconv7_bwd_w(const float* dy, const float* x, float* dw, float* db, void* workspace, int B, int H, int W, int C,
+                           cudaStream_t stream);
 
 /* ---- weight gradients: c [Mo, ldc] fp32 += a[R, Mo]^T . b[R, No] (csrc/wgrad.cu) ------------------------------------------
  * dW = dY^T X of every nn.Linear of the stack (sam2_video/model/modeling/memory_attention.py:97, sam/transformer.py:213-216),

@@ -123,78 +123,113 @@ ln_gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, co
   for (int i = threadIdx.x; i < C; i += blockDim.x) { atomicAdd(dw + i, sw[i]); atomicAdd(db + i, sb[i]); }
 }
 
-// ---- depth-wise 7 x 7, padding 3, channels-last [B, H, W, C]; one thread per (channel, strip of kStrip pixels along x).
-constexpr int kStrip = 4;
+// ---- depth-wise 7 x 7, padding 3, channels-last [B, H, W, C]: one thread per channel (a warp reads 128 contiguous bytes per
+// pixel) and per [kTy x kTx] output tile; the (kTy + 6) x (kTx + 6) input window is walked row by row with a register row
+// buffer, so every input value is loaded once per tile: 100 loads for 784 FMAs.
+constexpr int kTy = 4, kTx = 4;
 
 template <bool FLIP>
 __global__ void __launch_bounds__(256)
 dwconv7_kernel(const float* __restrict__ x, const float* __restrict__ wgt /*[C, 7, 7]*/, const float* __restrict__ bias, float* __restrict__ y,
                int B, int H, int W, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int strips = (W + kStrip - 1) / kStrip;
-  const int sx = blockIdx.y % strips, yy = (blockIdx.y / strips) % H, bb = blockIdx.y / (strips * H);
+  const int tx_n = (W + kTx - 1) / kTx, ty_n = (H + kTy - 1) / kTy;
+  const int tx = blockIdx.y % tx_n, ty = (blockIdx.y / tx_n) % ty_n, bb = blockIdx.y / (tx_n * ty_n);
   if (c >= C) return;
   float wk[49];
 #pragma unroll
   for (int i = 0; i < 49; ++i) wk[i] = wgt[c * 49 + (FLIP ? 48 - i : i)];
-  float acc[kStrip];
+  float acc[kTy][kTx];
   const float b0 = bias ? bias[c] : 0.f;
 #pragma unroll
-  for (int i = 0; i < kStrip; ++i) acc[i] = b0;
-  const int x0 = sx * kStrip;
+  for (int i = 0; i < kTy; ++i)
 #pragma unroll
-  for (int ky = 0; ky < 7; ++ky) {
-    const int iy = yy + ky - 3;
+    for (int k = 0; k < kTx; ++k) acc[i][k] = b0;
+  const int x0 = tx * kTx, y0 = ty * kTy;
+#pragma unroll
+  for (int r = 0; r < kTy + 6; ++r) {                     // input row y0 + r - 3 contributes to output rows oy with ky = r - oy in [0, 7)
+    const int iy = y0 + r - 3;
     if (iy < 0 || iy >= H) continue;
     const float* row = x + (((long long)bb * H + iy) * W) * C + c;
-    float in[kStrip + 6];
+    float in[kTx + 6];
 #pragma unroll
-    for (int i = 0; i < kStrip + 6; ++i) {
+    for (int i = 0; i < kTx + 6; ++i) {
       const int ix = x0 + i - 3;
       in[i] = (ix >= 0 && ix < W) ? row[(long long)ix * C] : 0.f;
     }
 #pragma unroll
-    for (int kx = 0; kx < 7; ++kx)
+    for (int oy = 0; oy < kTy; ++oy) {
+      const int ky = r - oy;
+      if (ky < 0 || ky >= 7) continue;
 #pragma unroll
-      for (int i = 0; i < kStrip; ++i) acc[i] = fmaf(wk[ky * 7 + kx], in[i + kx], acc[i]);
+      for (int kx = 0; kx < 7; ++kx)
+#pragma unroll
+        for (int k = 0; k < kTx; ++k) acc[oy][k] = fmaf(wk[ky * 7 + kx], in[k + kx], acc[oy][k]);
+    }
   }
 #pragma unroll
-  for (int i = 0; i < kStrip; ++i)
-    if (x0 + i < W) y[(((long long)bb * H + yy) * W + x0 + i) * C + c] = acc[i];
+  for (int oy = 0; oy < kTy; ++oy)
+#pragma unroll
+    for (int k = 0; k < kTx; ++k)
+      if (y0 + oy < H && x0 + k < W) y[(((long long)bb * H + y0 + oy) * W + x0 + k) * C + c] = acc[oy][k];
 }
 
-// dw[c, ky, kx] += sum_{b, y, x} dy[b, y, x, c] x[b, y + ky - 3, x + kx - 3, c];  db[c] += sum dy.  One block per (image, 4 rows),
-// one thread per channel: 49 + 1 partial sums in registers, one atomic each at the end.
+// dw[c, ky, kx] = sum_{b, y, x} dy[b, y, x, c] x[b, y + ky - 3, x + kx - 3, c];  db[c] = sum dy.  One block per (image, kRowsPerBlock
+// output rows), one thread per channel.  For every (output row, ky) the input row and the gradient row are walked in chunks of 8
+// pixels held in registers (8 + 14 loads for 7 x 8 FMAs); the 49 + 1 partial sums of a block go to part[block][50][C] with plain
+// coalesced stores and a second kernel folds the blocks in a fixed order (deterministic, no atomics).
 constexpr int kRowsPerBlock = 4;
+constexpr int kWChunk = 8;
 __global__ void __launch_bounds__(256)
-dwconv7_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw, float* __restrict__ db, int B, int H,
-                     int W, int C) {
+dwconv7_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ part, int B, int H, int W, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int rb = blockIdx.y % ((H + kRowsPerBlock - 1) / kRowsPerBlock), bb = blockIdx.y / ((H + kRowsPerBlock - 1) / kRowsPerBlock);
+  const int nrb = (H + kRowsPerBlock - 1) / kRowsPerBlock;
+  const int rb = blockIdx.y % nrb, bb = blockIdx.y / nrb;
   if (c >= C) return;
   float acc[49];
 #pragma unroll
   for (int i = 0; i < 49; ++i) acc[i] = 0.f;
   float accb = 0.f;
   for (int yy = rb * kRowsPerBlock; yy < min(H, (rb + 1) * kRowsPerBlock); ++yy) {
-    for (int xx = 0; xx < W; ++xx) {
-      const float g = dy[(((long long)bb * H + yy) * W + xx) * C + c];
-      accb += g;
+    const float* grow = dy + (((long long)bb * H + yy) * W) * C + c;
+    for (int xc = 0; xc < W; xc += kWChunk) {
+      float g[kWChunk];
+#pragma unroll
+      for (int i = 0; i < kWChunk; ++i) { g[i] = (xc + i < W) ? grow[(long long)(xc + i) * C] : 0.f; accb += g[i]; }
 #pragma unroll
       for (int ky = 0; ky < 7; ++ky) {
         const int iy = yy + ky - 3;
         if (iy < 0 || iy >= H) continue;
+        const float* row = x + (((long long)bb * H + iy) * W) * C + c;
+        float in[kWChunk + 6];
 #pragma unroll
-        for (int kx = 0; kx < 7; ++kx) {
-          const int ix = xx + kx - 3;
-          if (ix >= 0 && ix < W) acc[ky * 7 + kx] = fmaf(g, x[(((long long)bb * H + iy) * W + ix) * C + c], acc[ky * 7 + kx]);
+        for (int i = 0; i < kWChunk + 6; ++i) {
+          const int ix = xc + i - 3;
+          in[i] = (ix >= 0 && ix < W) ? row[(long long)ix * C] : 0.f;
         }
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx)
+#pragma unroll
+          for (int i = 0; i < kWChunk; ++i) acc[ky * 7 + kx] = fmaf(g[i], in[i + kx], acc[ky * 7 + kx]);
       }
     }
   }
+  float* dst = part + (long long)blockIdx.y * 50 * C + c;
 #pragma unroll
-  for (int i = 0; i < 49; ++i) atomicAdd(dw + c * 49 + i, acc[i]);
-  atomicAdd(db + c, accb);
+  for (int i = 0; i < 49; ++i) dst[(long long)i * C] = acc[i];
+  dst[49LL * C] = accb;
+}
+
+// dw[c * 49 + i] += sum_blocks part[blk][i][c], db[c] += sum_blocks part[blk][49][c]
+__global__ void __launch_bounds__(256)
+dwconv7_bwd_w_fold_kernel(const float* __restrict__ part, float* __restrict__ dw, float* __restrict__ db, int nblk, int C) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;      // e = i * C + c
+  if (e >= 50 * C) return;
+  float s = 0.f;
+  for (int k = 0; k < nblk; ++k) s += part[(long long)k * 50 * C + e];
+  const int i = e / C, c = e % C;
+  if (i < 49) dw[c * 49 + i] += s;
+  else db[c] += s;
 }
 
 template <int C>
@@ -249,8 +284,7 @@ int sam2b200_ln_gelu_bwd(const float* dy, const float* x, const float* w, const 
 // mirrored in both axes: the data gradient of the same convolution (call with x = dy, bias = NULL).
 int sam2b200_dwconv7(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int C, int flip, cudaStream_t stream) {
   if (!x || !w || !y || B <= 0 || H <= 0 || W <= 0 || C <= 0) return sam2b200::fail(SAM2B200_ERR_INVALID, "dwconv7: bad arguments");
-  const int strips = (W + kStrip - 1) / kStrip;
-  const long long gy = (long long)B * H * strips;
+  const long long gy = (long long)B * ((H + kTy - 1) / kTy) * ((W + kTx - 1) / kTx);
   if (gy > 0x7fffffffLL) return sam2b200::fail(SAM2B200_ERR_INVALID, "dwconv7: grid too large");
   const int tpb = C >= 256 ? 256 : ((C + 31) / 32) * 32;
   dim3 grid((C + tpb - 1) / tpb, (unsigned)gy);
@@ -259,13 +293,23 @@ int sam2b200_dwconv7(const float* x, const float* w, const float* bias, float* y
   return sam2b200::check_launch("dwconv7");
 }
 
-// dw [C, 7, 7] += , db [C] += for the same convolution (fp32 atomics).
-int sam2b200_dwconv7_bwd_w(const float* dy, const float* x, float* dw, float* db, int B, int H, int W, int C, cudaStream_t stream) {
-  if (!dy || !x || !dw || !db || B <= 0 || H <= 0 || W <= 0 || C <= 0) return sam2b200::fail(SAM2B200_ERR_INVALID, "dwconv7_bwd_w: bad arguments");
+size_t sam2b200_dwconv7_bwd_w_workspace_bytes(int B, int H, int C) {
+  return (size_t)B * ((H + kRowsPerBlock - 1) / kRowsPerBlock) * 50 * (size_t)C * sizeof(float);
+}
+
+// dw [C, 7, 7] += , db [C] += for the same convolution; workspace: sam2b200_dwconv7_bwd_w_workspace_bytes(B, H, C) bytes.
+// Deterministic (per-block partial sums folded in a fixed order).
+int sam2b200_dwconv7_bwd_w(const float* dy, const float* x, float* dw, float* db, void* workspace, int B, int H, int W, int C,
+                           cudaStream_t stream) {
+  if (!dy || !x || !dw || !db || !workspace || B <= 0 || H <= 0 || W <= 0 || C <= 0)
+    return sam2b200::fail(SAM2B200_ERR_INVALID, "dwconv7_bwd_w: bad arguments");
   const int tpb = C >= 256 ? 256 : ((C + 31) / 32) * 32;
-  dim3 grid((C + tpb - 1) / tpb, (unsigned)(B * ((H + kRowsPerBlock - 1) / kRowsPerBlock)));
-  dwconv7_bwd_w_kernel<<<grid, tpb, 0, stream>>>(dy, x, dw, db, B, H, W, C);
-  return sam2b200::check_launch("dwconv7_bwd_w");
+  const int nblk = B * ((H + kRowsPerBlock - 1) / kRowsPerBlock);
+  dim3 grid((C + tpb - 1) / tpb, (unsigned)nblk);
+  float* part = static_cast<float*>(workspace);
+  dwconv7_bwd_w_kernel<<<grid, tpb, 0, stream>>>(dy, x, part, B, H, W, C);
+  dwconv7_bwd_w_fold_kernel<<<(50 * C + 255) / 256, 256, 0, stream>>>(part, dw, db, nblk, C);
+  return sam2b200::check_launch("dwconv7_bwd_w", 2);
 }
 
 }  // extern "C"

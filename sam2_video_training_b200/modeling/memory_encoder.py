@@ -101,8 +101,9 @@ class _DwConv7Fn(torch.autograd.Function):
             _lib.check(lib.sam2b200_dwconv7(dy.data_ptr(), wf.data_ptr(), None, dx.data_ptr(), b, h, wd, c, 1, _stream(x.device)), "sam2b200_dwconv7")
         dw = torch.zeros(c, 49, dtype=F32, device=x.device)
         db = torch.zeros(c, dtype=F32, device=x.device)
-        _lib.check(lib.sam2b200_dwconv7_bwd_w(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), db.data_ptr(), b, h, wd, c, _stream(x.device)),
-                   "sam2b200_dwconv7_bwd_w")
+        ws = torch.empty(max(lib.sam2b200_dwconv7_bwd_w_workspace_bytes(b, h, c) // 4, 1), dtype=F32, device=x.device)
+        _lib.check(lib.sam2b200_dwconv7_bwd_w(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), b, h, wd, c,
+                                              _stream(x.device)), "sam2b200_dwconv7_bwd_w")
         return dx, dw.view(ctx.wshape), (db if ctx.has_bias else None)
 
 

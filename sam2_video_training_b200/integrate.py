@@ -61,6 +61,24 @@ def use_b200_attention(model: nn.Module, attr: str = "memory_attention") -> Memo
     return fast
 
 
+def use_b200_memory_encoder(model: nn.Module, attr: str = "memory_encoder"):
+    """Swap ``getattr(model, attr)`` (a reference ``MemoryEncoder``, built at sam2_base.py:126 from
+    configs/sam2/sam2.1_hiera_t.yaml:62-85) for the B200 drop-in, weights included (the reference's 40 state_dict keys)."""
+    from .modeling.memory_encoder import build_memory_encoder
+    ref = getattr(model, attr)
+    out_dim = ref.out_proj.out_channels if isinstance(ref.out_proj, nn.Conv2d) else ref.pix_feat_proj.out_channels
+    fast = build_memory_encoder(out_dim=out_dim)
+    p0 = next(ref.parameters())
+    fast = fast.to(device=p0.device)
+    missing, unexpected = fast.load_state_dict(ref.state_dict(), strict=True)
+    assert not missing and not unexpected
+    fast.train(ref.training)
+    for p_new, p_old in zip(fast.parameters(), ref.parameters()):
+        p_new.requires_grad_(p_old.requires_grad)
+    setattr(model, attr, fast)
+    return fast
+
+
 def b200_criterion(loss_type: str, **cfg: Any) -> nn.Module:
     """``multi_step_b200`` / ``bce_b200`` / ``multi_step_merged_b200`` (the last one takes the un-merged tracker stages,
     INTEGRATION.md section 3b)."""

@@ -208,3 +208,27 @@ def test_bench_reference_arm_runs_on_cpu_and_keeps_the_json_contract():
     out1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                            "--warmup", "1"], capture_output=True, text=True, timeout=120, env=env1, cwd=ROOT)
     assert out1.returncode == 0 and not [l for l in out1.stdout.splitlines() if l.startswith("{")]
+
+
+def test_memory_encoder_drop_in_loads_the_reference_state_dict():
+    """integrate.use_b200_memory_encoder: the drop-in takes the reference MemoryEncoder's 40 tensors with strict=True and keeps
+    the freeze map; without a GPU the forward refuses to run (no CPU fallback)."""
+    import torch
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference not present")
+    from sam2_video_training_b200 import _lib
+    from sam2_video_training_b200.integrate import use_b200_memory_encoder
+    torch.manual_seed(0)
+    holder = torch.nn.Module()
+    holder.memory_encoder = ref_shim.build_memory_encoder()
+    ref_sd = {k: v.clone() for k, v in holder.memory_encoder.state_dict().items()}
+    holder.memory_encoder.fuser.layers[1].gamma.requires_grad_(False)
+    fast = use_b200_memory_encoder(holder)
+    assert holder.memory_encoder is fast and list(fast.state_dict().keys()) == list(ref_sd.keys()) and len(ref_sd) == 40
+    for k, v in fast.state_dict().items():
+        assert torch.equal(v, ref_sd[k]), k
+    assert not fast.fuser.layers[1].gamma.requires_grad and fast.fuser.layers[0].gamma.requires_grad
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.Sam2B200Error):
+            fast(torch.zeros(1, 256, 2, 2), torch.zeros(1, 1, 32, 32))

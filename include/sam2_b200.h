@@ -288,8 +288,8 @@ int sam2b200_proj_rope(const void* x, const void* w, const void* bias, void* out
  * dh[R, F] = (dm[R, 256] . W2[256, F]) o (h[R, F] > 0) * scale: input gradient of linear2 with the ReLU (and hidden
  * dropout: h is the dropped activation, scale = 1/(1-p)) backward fused into the epilogue of a tcgen05 GEMM.
  * All bf16 row-major contiguous, F a multiple of 128. */
-int sam2b200_mlp_dh(const void* dm, const void* w2, const void* h, void* dh, long long R, int F, float scale,
-                    sam2b200_stream_t stream);
+int sam2b200_mlp_dh(const void* dm, const void* w2, const void* h, void* dh, float* dbias, long long R, int F, float scale,
+                    cudaStream_t stream);
 
 /* ---- memory-bank assembly -------------------------------------------------
  * The data movement of SAM2Base._prepare_memory_conditioned_features (sam2_base.py:597-692) in one launch: for each

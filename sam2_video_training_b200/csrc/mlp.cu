@@ -56,6 +56,7 @@ struct Params {
   int n_chunks;       // F / 128
   int rows;           // R
   float scale;        // 1 / (1 - p) of the hidden dropout (1 if none)
+  float* dbias;       // [F] fp32 or nullptr: column sums of dh (the bias gradient of linear1) are ADDED here (fp32 atomics)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -167,6 +168,7 @@ dh_kernel(const __grid_constant__ CUtensorMap map_dm,     // dm  [R, 256]  bf16,
       mbar_wait(&sh.h_full[s], ph);
       // this thread's 128 bytes: row `row` of slab `half` (64 bf16), 16-byte chunks XOR-swizzled with (row & 7)
       const uint32_t hrow = smem_u32(&sh.h_tiles[s][0]) + half * kSlabBytes + row * 128;
+      const bool row_in = (row0 + lane) < p.rows;     // rows beyond the tensor are clipped by the store, not by the column sums
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const uint32_t addr = hrow + ((q ^ (row & 7)) << 4);
@@ -179,8 +181,19 @@ dh_kernel(const __grid_constant__ CUtensorMap map_dm,     // dm  [R, 256]  bf16,
           const float v0 = hf.x > 0.f ? __uint_as_float(acc[q * 8 + 2 * e]) * scale : 0.f;
           const float v1 = hf.y > 0.f ? __uint_as_float(acc[q * 8 + 2 * e + 1]) * scale : 0.f;
           o[e] = pack_bf16(v0, v1);
+          // keep the masked values (as the bf16 numbers the weight-gradient GEMM will see) for the bias gradient
+          const float2 r2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o[e]));
+          acc[q * 8 + 2 * e] = __float_as_uint(row_in ? r2.x : 0.f);
+          acc[q * 8 + 2 * e + 1] = __float_as_uint(row_in ? r2.y : 0.f);
         }
         sts128(addr, o[0], o[1], o[2], o[3]);
+      }
+      if (p.dbias != nullptr) {   // bias gradient of linear1: column sums of this warp's 32 x 64 block (31-shuffle butterfly per 32 columns)
+        const float* mv = reinterpret_cast<const float*>(acc);
+        const float c0s = attn::warp_column_sum32(mv, lane);
+        const float c1s = attn::warp_column_sum32(mv + 32, lane);
+        atomicAdd(p.dbias + j * kBlockN + half * 64 + lane, c0s);
+        atomicAdd(p.dbias + j * kBlockN + half * 64 + 32 + lane, c1s);
       }
       // the warp's box: 32 rows x 64 columns = rows quarter*32 .. +31 of slab `half`
       fence_proxy_async();
@@ -228,7 +241,8 @@ int make_matrix_map(CUtensorMap* map, const void* base, long long rows, long lon
 extern "C" {
 
 // dh[R, F] = (dm[R, 256] . W2[256, F]) o (h[R, F] > 0) * scale; all bf16 row-major contiguous, F a multiple of 128.
-int sam2b200_mlp_dh(const void* dm, const void* w2, const void* h, void* dh, long long R, int F, float scale,
+// dbias (optional): [F] fp32, += column sums of dh -- the bias gradient of linear1 from the tile in registers (no extra pass).
+int sam2b200_mlp_dh(const void* dm, const void* w2, const void* h, void* dh, float* dbias, long long R, int F, float scale,
                     cudaStream_t stream) {
   if (!dm || !w2 || !h || !dh || R <= 0 || F <= 0 || (F % mlp::kBlockN) || R > 0x7fffffffLL - 256 ||
       ((reinterpret_cast<uintptr_t>(dm) | reinterpret_cast<uintptr_t>(w2) | reinterpret_cast<uintptr_t>(h) |
@@ -243,7 +257,7 @@ int sam2b200_mlp_dh(const void* dm, const void* w2, const void* h, void* dh, lon
   const size_t smem = sizeof(mlp::Shared) + 1024;
   cudaError_t e = cudaFuncSetAttribute(mlp::dh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return sam2b200::fail(SAM2B200_ERR_CUDA, cudaGetErrorString(e));
-  mlp::Params p{F / mlp::kBlockN, (int)R, scale};
+  mlp::Params p{F / mlp::kBlockN, (int)R, scale, dbias};
   const unsigned grid = (unsigned)((R + mlp::kBlockM - 1) / mlp::kBlockM);
   mlp::dh_kernel<<<grid, mlp::kThreads, smem, stream>>>(map_dm, map_w2, map_h, map_dh, p);
   return sam2b200::check_launch("mlp_dh");

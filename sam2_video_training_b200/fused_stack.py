@@ -169,13 +169,15 @@ def wgrad_(c32, a16, b16):
     return c32
 
 
-def mlp_dh(dm16, w2_16, h16, scale=1.0):
-    """dh = (dm @ W2) * (h > 0) * scale in one tcgen05 GEMM with the ReLU / hidden-dropout backward in its epilogue."""
+def mlp_dh(dm16, w2_16, h16, scale=1.0, dbias=None):
+    """dh = (dm @ W2) * (h > 0) * scale in one tcgen05 GEMM with the ReLU / hidden-dropout backward in its epilogue; dbias
+    (fp32 [F], optional) += column sums of dh = the bias gradient of linear1, taken from the tile in registers."""
     r, f = h16.shape
     assert dm16.is_contiguous() and w2_16.is_contiguous() and h16.is_contiguous() and dm16.dtype == w2_16.dtype == h16.dtype == BF16
+    assert dbias is None or (dbias.dtype == F32 and dbias.numel() == f and dbias.is_contiguous())
     dh = torch.empty_like(h16)
-    rc = _lib.load().sam2b200_mlp_dh(dm16.data_ptr(), w2_16.data_ptr(), h16.data_ptr(), dh.data_ptr(), r, f, float(scale),
-                                     _stream(h16.device))
+    rc = _lib.load().sam2b200_mlp_dh(dm16.data_ptr(), w2_16.data_ptr(), h16.data_ptr(), dh.data_ptr(),
+                                     dbias.data_ptr() if dbias is not None else None, r, f, float(scale), _stream(h16.device))
     _lib.check(rc, "sam2b200_mlp_dh")
     return dh
 
@@ -686,8 +688,8 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                 relu_bwd_colsum_(dh, h, gv[ix["l1.b"]], scale=relu_scale)
                 acc_w(ix["l1.w"], dh.t(), y3)
             else:   # ReLU / hidden-dropout backward fused into the GEMM; the bias gradient joins the weight gradient (side stream)
-                dh = mlp_dh(dm, W["l2.w"], h, relu_scale)
-                acc_w(ix["l1.w"], dh.t(), y3, gv[ix["l1.b"]])
+                dh = mlp_dh(dm, W["l2.w"], h, relu_scale, dbias=gv[ix["l1.b"]])     # + bias gradient of linear1 (column sums of dh)
+                acc_w(ix["l1.w"], dh.t(), y3)
             dy3 = torch.mm(dh, W["l1.w"])
             fold = mt["fold"]
             g_bo = torch.zeros(d, dtype=F32, device=dev) if fold else gv[ix["ca.o.b"]]    # colsum(dca), needed on its own when folded

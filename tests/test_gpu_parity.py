@@ -650,6 +650,11 @@ def test_mlp_dh_kernel(dev, rows):
         assert dh.dtype == torch.bfloat16 and dh.shape == ref.shape
         assert rel_l2(dh, ref) < 4e-3, rel_l2(dh, ref)
         assert torch.equal(dh == 0, (ref.to(torch.bfloat16) == 0) | (h == 0))
+        # the bias gradient of linear1 fused into the epilogue: column sums of the dh it stores, accumulated (+=)
+        db = torch.full((2048,), 0.5, device=dev)
+        dh2 = fs.mlp_dh(dm, w2, h, scale, dbias=db)
+        assert torch.equal(dh2, dh)
+        assert rel_l2(db - 0.5, dh.float().sum(0)) < 1e-4, rel_l2(db - 0.5, dh.float().sum(0))
 
 
 @pytest.mark.parametrize("c", [256, 768, 2048])

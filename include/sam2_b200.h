@@ -43,7 +43,8 @@ long long sam2b200_launch_count(void);
 long long sam2b200_debug_set_timeline(void* buf, long long n_u64);
 /* Debug / A-B aid: choose a kernel variant at run time.  key 0 = backward of the raw-memory cross-attention
  * (0 = default, 1 = experimental two-softmax-group kernels); key 1 = rotation-table addressing of the gradient epilogues
- * (0 = default: axial -- rows x and y*w of a w x w grid table, 1 = full rows).  Returns the previous value, -1 for an unknown key. */
+ * (0 = default: axial -- rows x and y*w of a w x w grid table, 1 = full rows); key 2 = forward of the raw-memory cross-attention
+ * (0 = default: one online-softmax stream per CTA, 1 = experimental two-stream kernel, same results to bf16 rounding of the probabilities).  Returns the previous value, -1 for an unknown key. */
 int sam2b200_debug_set_variant(int key, int value);
 /* 0 iff CUDA device `dev` is an sm_100 part. */
 int sam2b200_check_device(int dev);

@@ -18,6 +18,7 @@
 #include "attn_persist_kernels.cuh"
 #include "attn_v64_kernels.cuh"
 #include "attn_v64x2_kernels.cuh"
+#include "attn_fwd_v64x2_kernel.cuh"
 #include "tma_desc.cuh"
 
 namespace {
@@ -322,6 +323,17 @@ int sam2b200_attn_fwd_v64(const void* q, const void* k, const void* memv, void* 
   p.out_small = out64; p.out_small_f32 = out64_f32; p.rowsum_drop = rowsum_drop;
   const size_t smem = sizeof(attn::SharedStorage) + 1024;
   dim3 grid((N + attn::kBlockM - 1) / attn::kBlockM, B, 1);
+  if (g_variant[2] == 1) {   // experiment: two independent online-softmax streams per CTA (attn_fwd_v64x2_kernel.cuh); same speed, not the default
+    const size_t smem2 = sizeof(attn::SharedStorageF2) + 1024;
+    if (p.drop.seed != nullptr) {
+      if ((rc = set_smem(attn::fwd_v64x2_kernel<true, false>, smem2))) return rc;
+      attn::fwd_v64x2_kernel<true, false><<<grid, attn::kF2Threads, smem2, stream>>>(map_k, map_v, map_q, map_q, map_q, p);
+    } else {
+      if ((rc = set_smem(attn::fwd_v64x2_kernel<false, false>, smem2))) return rc;
+      attn::fwd_v64x2_kernel<false, false><<<grid, attn::kF2Threads, smem2, stream>>>(map_k, map_v, map_q, map_q, map_q, p);
+    }
+    return sam2b200::check_launch("attn_fwd_v64");
+  }
   if (p.drop.seed != nullptr) {
     if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_FWD, true, 64>, smem))) return rc;
     attn::two_gemm_kernel<attn::MODE_FWD, true, 64><<<grid, attn::kThreads, smem, stream>>>(map_k, map_v, map_q, map_q, map_q, map_q, p);
@@ -397,6 +409,17 @@ int sam2b200_attn_fwd_v64_proj(const void* q, const void* k, const void* memv, v
   p.proj_bias = bias; p.proj_rank1 = (p.drop.seed != nullptr) ? rank1 : nullptr;
   const size_t smem = sizeof(attn::SharedStorage) + 1024;
   dim3 grid((N + attn::kBlockM - 1) / attn::kBlockM, B, 1);
+  if (g_variant[2] == 1) {
+    const size_t smem2 = sizeof(attn::SharedStorageF2) + 1024;
+    if (p.drop.seed != nullptr) {
+      if ((rc = set_smem(attn::fwd_v64x2_kernel<true, true>, smem2))) return rc;
+      attn::fwd_v64x2_kernel<true, true><<<grid, attn::kF2Threads, smem2, stream>>>(map_k, map_v, map_q, map_w, map_p, p);
+    } else {
+      if ((rc = set_smem(attn::fwd_v64x2_kernel<false, true>, smem2))) return rc;
+      attn::fwd_v64x2_kernel<false, true><<<grid, attn::kF2Threads, smem2, stream>>>(map_k, map_v, map_q, map_w, map_p, p);
+    }
+    return sam2b200::check_launch("attn_fwd_v64_proj");
+  }
   if (p.drop.seed != nullptr) {
     if ((rc = set_smem(attn::two_gemm_kernel<attn::MODE_FWD, true, 64, true>, smem))) return rc;
     attn::two_gemm_kernel<attn::MODE_FWD, true, 64, true><<<grid, attn::kThreads, smem, stream>>>(map_k, map_v, map_q, map_q, map_w, map_p, p);

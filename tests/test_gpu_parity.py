@@ -1048,6 +1048,50 @@ def test_raw_memory_backward_two_softmax_groups_bit_identical(dev, b, grid, nf, 
             assert rel_l2(two[2][i], one[2][i]) < 1e-4, ("dbias", i, gdt)
 
 
+@pytest.mark.parametrize("b,n,m,drop", [(2, 576, 4060, 0.0), (3, 64, 64, 0.0), (2, 200, 129, 0.0), (1, 1024, 3092, 0.0), (2, 144, 300, 0.1),
+                                        (5, 576, 128, 0.0), (1, 130, 1000, 0.1)])
+def test_raw_memory_forward_two_softmax_streams(dev, b, n, m, drop):
+    """fwd_v64x2_kernel (experiment, sam2b200_debug_set_variant key 2 = 1; two online-softmax streams on alternate memory tiles,
+    merged at the end) against the default single-stream kernel and an fp32 torch softmax: one tile, two tiles, odd and even
+    tile counts, ragged query and memory tiles, dropout (same Philox stream, so the same mask), with and without the fused
+    output projection.  The row sums (lse2, rowsum) are fp32 sums of the same terms in another order; the outputs differ by the
+    bf16 rounding of the probabilities, which are taken relative to each stream's own running maximum (2^-9 per term)."""
+    from sam2_video_training_b200 import _lib, ops
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(11 + n + m)
+    q = torch.randn(b, n, 256, device=dev, generator=g).to(torch.bfloat16)
+    k = (0.5 * torch.randn(b, m, 256, device=dev, generator=g)).to(torch.bfloat16)
+    mem = torch.randn(b, m, 64, device=dev, generator=g).to(torch.bfloat16)
+    w16 = (0.1 * torch.randn(256, 64, device=dev, generator=g)).to(torch.bfloat16)
+    bias = torch.randn(256, device=dev, generator=g)
+    rank1 = torch.randn(256, device=dev, generator=g)
+    dr = (drop, torch.tensor([77], dtype=torch.int64, device=dev), 3) if drop > 0 else None
+    res = {}
+    try:
+        for variant in (0, 1):
+            lib.sam2b200_debug_set_variant(2, variant)
+            a = ops.attn_fwd_v64(q, k, mem, 1 / 16.0, drop=dr)
+            c = ops.attn_fwd_v64_proj(q, k, mem, w16, bias, rank1 if dr is not None else None, 1 / 16.0, drop=dr)
+            torch.cuda.synchronize()
+            res[variant] = (a, c)
+    finally:
+        lib.sam2b200_debug_set_variant(2, 0)
+    (one, one_p), (two, two_p) = res[0], res[1]
+    for x in (two, two_p[:4]):
+        assert rel_l2(x[1], one[1]) < 3e-3, "out32"
+        assert (x[2] - one[2]).abs().max().item() < 1e-4 * max(1.0, one[2].abs().max().item()), "lse2"
+        assert rel_l2(x[0].float(), one[0].float()) < 4e-3, "out bf16"
+        if dr is not None:
+            assert rel_l2(x[3], one[3]) < 1e-4, "rowsum"
+    assert rel_l2(two_p[4].float(), one_p[4].float()) < 4e-3, "proj"
+    if dr is None:
+        s = torch.einsum("bnd,bmd->bnm", q.float(), k.float()) / 16.0
+        want = torch.softmax(s, -1) @ mem.float()
+        assert rel_l2(two[1], want) < 6e-3
+        assert (two[2] - torch.logsumexp(s, -1) * 1.4426950408889634).abs().max().item() < 2e-3
+        assert rel_l2(two_p[4].float(), want @ w16.float().t() + bias) < 8e-3
+
+
 @pytest.mark.parametrize("grid", [8, 24, 32])
 def test_gradient_epilogue_axial_table_addressing_bit_identical(dev, grid):
     """The gradient epilogues read the (cos, sin) pairs of position p from rows p mod w (x part) and p - p mod w (y part)

@@ -43,7 +43,8 @@ long long sam2b200_launch_count(void);
 long long sam2b200_debug_set_timeline(void* buf, long long n_u64);
 /* Debug / A-B aid: choose a kernel variant at run time.  key 0 = backward of the raw-memory cross-attention
  * (0 = default, 1 = experimental two-softmax-group kernels); key 1 = rotation-table addressing of the gradient epilogues
- * (0 = default: axial -- rows x and y*w of a w x w grid table, 1 = full rows); key 2 = forward of the raw-memory cross-attention
+ * (0 = default: axial -- rows x and y*w of a w x w grid table, 1 = full rows); key 3 = rotation table of the gradient epilogues
+ * (0 = default: staged in shared memory, 1 = read from global memory per chunk); key 2 = forward of the raw-memory cross-attention
  * (0 = default: one online-softmax stream per CTA, 1 = experimental two-stream kernel, same results to bf16 rounding of the probabilities).  Returns the previous value, -1 for an unknown key. */
 int sam2b200_debug_set_variant(int key, int value);
 /* 0 iff CUDA device `dev` is an sm_100 part. */
@@ -257,9 +258,11 @@ int sam2b200_dwconv7_bwd_w(const float* dy, const float* x, float* dw, float* db
 /* ---- weight gradients: c [Mo, ldc] fp32 += a[R, Mo]^T . b[R, No] (csrc/wgrad.cu) ------------------------------------------
  * dW = dY^T X of every nn.Linear of the stack (sam2_video/model/modeling/memory_attention.py:97, sam/transformer.py:213-216),
  * accumulated IN PLACE into the fp32 gradient (split over R, partial tiles added with vector fp32 reductions: no workspace,
- * no reduce pass).  a, b: bf16 with row strides lda / ldb (elements); Mo a multiple of 256, No = 64 or a multiple of 256. */
+ * no reduce pass).  a, b: bf16 with row strides lda / ldb (elements); Mo a multiple of 256, No = 64 or a multiple of 256.
+ * dbias (nullable, fp32 [Mo]) += column sums of a = the bias gradient of the same layer (transformer.py:213-215 q/k/v_proj
+ * biases), from 16 extra accumulator columns against a constant operand of ones; needs No = 64 or (No = 256 and Mo <= 768). */
 int sam2b200_wgrad(float* c, long long ldc, const void* a, long long lda, const void* b, long long ldb, long long R, int Mo, int No,
-                   cudaStream_t stream);
+                   float* dbias, cudaStream_t stream);
 
 /* ---- LayerNorm + projection (+ RoPE | ReLU) in one kernel (csrc/lnproj.cu) ------------------------------------------
  * The head of every pre-norm block of MemoryAttentionLayer (sam2_video/model/modeling/memory_attention.py:58-64, 66-81,

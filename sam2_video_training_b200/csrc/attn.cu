@@ -182,6 +182,15 @@ int axial_w(int period) {
   return (w * w == period) ? w : 0;
 }
 
+// Shared-memory bytes for the staged rotation table of a gradient epilogue (GradOut::rope_smem): 0 when there is no axial
+// table, when the kernel's shared memory has no room for it (w > 32 next to the raw-memory kernels' 200 KB), or when
+// sam2b200_debug_set_variant(3, 1) asks for the global-memory path.
+int rope_stage_bytes(const attn::GradOut& g, size_t base_smem, bool persistent) {
+  if (!g.rope_table || g.rope_w <= 0 || g.rope_period != g.rope_w * g.rope_w || g_variant[3] == 1) return 0;
+  const int bytes = attn::rope_smem_bytes(g.rope_w) + (persistent ? attn::rope_y_bytes(g.rope_w) : 0);
+  return (base_smem + (size_t)bytes <= 232448) ? bytes : 0;      // 227 KB per CTA
+}
+
 extern "C" {
 
 int sam2b200_debug_set_variant(int key, int value) {
@@ -567,21 +576,25 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
     p.n_items = (int)(grid.x * grid.y);
     static const bool no_persist_dk = getenv("SAM2B200_NO_PERSIST_DK") != nullptr;
     if (use_persist && !no_persist_dk && grad_dtype && p.n_items > num_sms()) {
+      p.gout.rope_smem = rope_stage_bytes(p.gout, smem3, true);
+      const size_t sm = smem3 + p.gout.rope_smem;
       if (drop_on) {
-        if ((rc = set_smem(attn::dk_persistent_kernel<true>, smem3))) return rc;
-        attn::dk_persistent_kernel<true><<<num_sms(), attn::kThreads, smem3, stream>>>(map_v128, map_q64, map_do64, map_k128, map_dk, p);
+        if ((rc = set_smem(attn::dk_persistent_kernel<true>, sm))) return rc;
+        attn::dk_persistent_kernel<true><<<num_sms(), attn::kThreads, sm, stream>>>(map_v128, map_q64, map_do64, map_k128, map_dk, p);
       } else {
-        if ((rc = set_smem(attn::dk_persistent_kernel<false>, smem3))) return rc;
-        attn::dk_persistent_kernel<false><<<num_sms(), attn::kThreads, smem3, stream>>>(map_v128, map_q64, map_do64, map_k128, map_dk, p);
+        if ((rc = set_smem(attn::dk_persistent_kernel<false>, sm))) return rc;
+        attn::dk_persistent_kernel<false><<<num_sms(), attn::kThreads, sm, stream>>>(map_v128, map_q64, map_do64, map_k128, map_dk, p);
       }
     } else {
       p.dbg = timeline_slice((size_t)grid.x * grid.y);
+      p.gout.rope_smem = rope_stage_bytes(p.gout, smem3, false);
+      const size_t sm = smem3 + p.gout.rope_smem;
       if (drop_on) {
-        if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DK, true>, smem3))) return rc;
-        attn::three_gemm_kernel<attn::MODE_DK, true><<<grid, attn::kThreads, smem3, stream>>>(map_v128, map_q64, map_do64, map_k128, map_dk, p);
+        if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DK, true>, sm))) return rc;
+        attn::three_gemm_kernel<attn::MODE_DK, true><<<grid, attn::kThreads, sm, stream>>>(map_v128, map_q64, map_do64, map_k128, map_dk, p);
       } else {
-        if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DK, false>, smem3))) return rc;
-        attn::three_gemm_kernel<attn::MODE_DK, false><<<grid, attn::kThreads, smem3, stream>>>(map_v128, map_q64, map_do64, map_k128, map_dk, p);
+        if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DK, false>, sm))) return rc;
+        attn::three_gemm_kernel<attn::MODE_DK, false><<<grid, attn::kThreads, sm, stream>>>(map_v128, map_q64, map_do64, map_k128, map_dk, p);
       }
     }
     if ((rc = sam2b200::check_launch("attn_bwd dK"))) return rc;
@@ -595,12 +608,14 @@ int sam2b200_attn_bwd_ex(const void* q, const void* k, const void* v, const void
     p.drop = drop;
     dim3 grid((N + attn::kBlockM - 1) / attn::kBlockM, B, 1);
     p.dbg = timeline_slice((size_t)grid.x * grid.y);
+    p.gout.rope_smem = rope_stage_bytes(p.gout, smem3, false);
+    const size_t sm = smem3 + p.gout.rope_smem;
     if (drop_on) {
-      if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DQ, true>, smem3))) return rc;
-      attn::three_gemm_kernel<attn::MODE_DQ, true><<<grid, attn::kThreads, smem3, stream>>>(map_do128, map_k64, map_v64, map_q128, map_dq, p);
+      if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DQ, true>, sm))) return rc;
+      attn::three_gemm_kernel<attn::MODE_DQ, true><<<grid, attn::kThreads, sm, stream>>>(map_do128, map_k64, map_v64, map_q128, map_dq, p);
     } else {
-      if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DQ, false>, smem3))) return rc;
-      attn::three_gemm_kernel<attn::MODE_DQ, false><<<grid, attn::kThreads, smem3, stream>>>(map_do128, map_k64, map_v64, map_q128, map_dq, p);
+      if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DQ, false>, sm))) return rc;
+      attn::three_gemm_kernel<attn::MODE_DQ, false><<<grid, attn::kThreads, sm, stream>>>(map_do128, map_k64, map_v64, map_q128, map_dq, p);
     }
     if ((rc = sam2b200::check_launch("attn_bwd dQ"))) return rc;
   }
@@ -666,12 +681,14 @@ int sam2b200_attn_bwd_v64(const void* q, const void* k, const void* memv, const 
         attn::three_gemm_v64x2_kernel<attn::MODE_DK><<<grid, attn::kX2Threads, smemx2, stream>>>(map_m128, map_q64, map_d64, map_k128, map_dk, p);
       }
     } else if (drop_on) {
-      if ((rc = set_smem(attn::three_gemm_v64_kernel<attn::MODE_DK, true>, smemv))) return rc;
-      attn::three_gemm_v64_kernel<attn::MODE_DK, true><<<grid, attn::kThreads, smemv, stream>>>(map_m128, map_q64, map_d64, map_k128, map_dk, p);
+      p.gout.rope_smem = rope_stage_bytes(p.gout, smemv, false);
+      if ((rc = set_smem(attn::three_gemm_v64_kernel<attn::MODE_DK, true>, smemv + p.gout.rope_smem))) return rc;
+      attn::three_gemm_v64_kernel<attn::MODE_DK, true><<<grid, attn::kThreads, smemv + p.gout.rope_smem, stream>>>(map_m128, map_q64, map_d64, map_k128, map_dk, p);
     } else if (!single_buf && !persist_dk) {   // double-buffered S / dP, both fixed operands in shared memory (attn_v64_kernels.cuh)
       p.dbg = timeline_slice((size_t)grid.x * grid.y);
-      if ((rc = set_smem(attn::three_gemm_v64_kernel<attn::MODE_DK>, smemv))) return rc;
-      attn::three_gemm_v64_kernel<attn::MODE_DK><<<grid, attn::kThreads, smemv, stream>>>(map_m128, map_q64, map_d64, map_k128, map_dk, p);
+      p.gout.rope_smem = rope_stage_bytes(p.gout, smemv, false);
+      if ((rc = set_smem(attn::three_gemm_v64_kernel<attn::MODE_DK>, smemv + p.gout.rope_smem))) return rc;
+      attn::three_gemm_v64_kernel<attn::MODE_DK><<<grid, attn::kThreads, smemv + p.gout.rope_smem, stream>>>(map_m128, map_q64, map_d64, map_k128, map_dk, p);
     } else if (!no_persist && N < 1024 && grad_dtype && p.n_items > num_sms()) {   // short query loops: resident CTAs (attn_persist_kernels.cuh)
       if ((rc = set_smem(attn::dk_persistent_kernel<false, 64>, smem3))) return rc;
       attn::dk_persistent_kernel<false, 64><<<num_sms(), attn::kThreads, smem3, stream>>>(map_m128, map_q64, map_d64, map_k128, map_dk, p);
@@ -701,12 +718,14 @@ int sam2b200_attn_bwd_v64(const void* q, const void* k, const void* memv, const 
         attn::three_gemm_v64x2_kernel<attn::MODE_DQ><<<grid, attn::kX2Threads, smemx2, stream>>>(map_d128, map_k64, map_m64, map_q128, map_dq, p);
       }
     } else if (drop_on) {
-      if ((rc = set_smem(attn::three_gemm_v64_kernel<attn::MODE_DQ, true>, smemv))) return rc;
-      attn::three_gemm_v64_kernel<attn::MODE_DQ, true><<<grid, attn::kThreads, smemv, stream>>>(map_d128, map_k64, map_m64, map_q128, map_dq, p);
+      p.gout.rope_smem = rope_stage_bytes(p.gout, smemv, false);
+      if ((rc = set_smem(attn::three_gemm_v64_kernel<attn::MODE_DQ, true>, smemv + p.gout.rope_smem))) return rc;
+      attn::three_gemm_v64_kernel<attn::MODE_DQ, true><<<grid, attn::kThreads, smemv + p.gout.rope_smem, stream>>>(map_d128, map_k64, map_m64, map_q128, map_dq, p);
     } else if (!single_buf) {
       p.dbg = timeline_slice((size_t)grid.x * grid.y);
-      if ((rc = set_smem(attn::three_gemm_v64_kernel<attn::MODE_DQ>, smemv))) return rc;
-      attn::three_gemm_v64_kernel<attn::MODE_DQ><<<grid, attn::kThreads, smemv, stream>>>(map_d128, map_k64, map_m64, map_q128, map_dq, p);
+      p.gout.rope_smem = rope_stage_bytes(p.gout, smemv, false);
+      if ((rc = set_smem(attn::three_gemm_v64_kernel<attn::MODE_DQ>, smemv + p.gout.rope_smem))) return rc;
+      attn::three_gemm_v64_kernel<attn::MODE_DQ><<<grid, attn::kThreads, smemv + p.gout.rope_smem, stream>>>(map_d128, map_k64, map_m64, map_q128, map_dq, p);
     } else {
       if ((rc = set_smem(attn::three_gemm_kernel<attn::MODE_DQ, false, 64>, smem3))) return rc;
       attn::three_gemm_kernel<attn::MODE_DQ, false, 64><<<grid, attn::kThreads, smem3, stream>>>(map_d128, map_k64, map_m64, map_q128, map_dq, p);

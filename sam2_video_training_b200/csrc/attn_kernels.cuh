@@ -93,7 +93,58 @@ struct GradOut {
                                // row p depend only on x = p mod w, the last 64 only on y = p div w, so they are read from rows x and
                                // y * w -- the 128 rows of a CTA then touch w + 128 / w table rows (16 KB at w = 24, L1-resident)
                                // instead of 128 (128 KB from L2, ~1.5 us per CTA); 0 = address the full row
+  int rope_smem;               // > 0 (bytes, set by the host when rope_w > 0 and the kernel's shared memory has room): the CTA stages
+                               // those w + 128 / w table rows in shared memory while its operands are in flight (rope_stage), and
+                               // the epilogue reads them from there.  The L2 round trip per 32-column chunk was the largest single
+                               // item of the gradient epilogue (profiles/r2_timeline_epilogue.txt: 3.6 us with rotation, 2.0 without).
 };
+
+// Shared-memory copy of the axial rotation table for the kBlockM rows of a CTA:
+//   X part  rope_w rows x 64 (cos, sin) pairs, row stride 528 B (lanes read consecutive rows: conflict-free 16-byte loads)
+//   Y part  one 512 B row per "slot" = run of rows with the same y: slot(r) = (r + x0) / w, x0 = (first row of the CTA) mod w
+constexpr int kRopeXStride = 528;
+__host__ __device__ constexpr int rope_y_bytes(int w) { return ((128 - 1 + w - 1) / w + 1) * 512; }
+__host__ __device__ constexpr int rope_smem_bytes(int w) { return w * kRopeXStride + rope_y_bytes(w); }   // persistent kernels: + one more Y part
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// X part: the same for every CTA / item.  tid in [0, 256).
+__device__ __forceinline__ void rope_stage_x(const GradOut& g, uint32_t area, int tid) {
+  const int w = g.rope_w;
+  for (int idx = tid; idx < w * 32; idx += 256)
+    cp_async16(area + (idx >> 5) * kRopeXStride + (idx & 31) * 16, g.rope_table + (size_t)(idx >> 5) * 128 + (idx & 31) * 2);
+}
+// Y part for the 128 rows starting at row `cta_row0` of a batch item, into `ybase` (up to 128 / w + 2 rows of 512 B).
+__device__ __forceinline__ void rope_stage_y(const GradOut& g, uint32_t ybase, int cta_row0, int tid) {
+  const int w = g.rope_w;
+  const int pos0 = cta_row0 % g.rope_period;
+  const int x0 = pos0 % w, y0 = pos0 / w;
+  const int ny = (kBlockM - 1 + x0) / w + 1;
+  for (int idx = tid; idx < ny * 32; idx += 256) {
+    const int yr = (y0 + (idx >> 5)) % w;
+    cp_async16(ybase + (idx >> 5) * 512 + (idx & 31) * 16, g.rope_table + (size_t)(yr * w) * 128 + 64 + (idx & 31) * 2);
+  }
+}
+// This thread's 64 pairs (row `row` of the CTA, columns [128 half, 128 half + 128)): shared-memory address of the first one.
+__device__ __forceinline__ uint32_t rope_tab_addr(const GradOut& g, uint32_t area, uint32_t ybase, int cta_row0, int row, int half) {
+  const int w = g.rope_w;
+  const int x0 = (cta_row0 % g.rope_period) % w;
+  return half == 0 ? area + ((x0 + row) % w) * kRopeXStride : ybase + ((x0 + row) / w) * 512;
+}
+__device__ __forceinline__ void load_table_chunk_smem(uint32_t tab, bool rotate, int chunk /*0..3 within the half*/, float2* t) {
+  if (rotate) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint4 f = lds128(tab + chunk * 128 + i * 16);
+      t[2 * i] = make_float2(__uint_as_float(f.x), __uint_as_float(f.y));
+      t[2 * i + 1] = make_float2(__uint_as_float(f.z), __uint_as_float(f.w));
+    }
+  }
+}
 
 struct TwoGemmParams {
   int La;                      // rows of a per batch (N in FWD, M in DV)
@@ -250,8 +301,11 @@ __device__ __forceinline__ float warp_column_sum32(const float* v, int lane) {
 // stage: this warp's staging area (8 KB bf16 / 16 KB fp32); row0 = first row (in the batch item) of the warp.
 __device__ __forceinline__ void grad_epilogue(const GradOut& g, const CUtensorMap* map, uint32_t stage, uint32_t acc_addr,
                                               int half, int lane, int row0, int La, int b, float scale, bool rotate,
-                                              float2* tcur /* chunk 0 of the table, already loaded */) {
+                                              float2* tcur /* chunk 0 of the table, already loaded (tab == 0) */,
+                                              unsigned long long* dbg = nullptr /* SAM2B200_EPI_TIMELINE builds only */,
+                                              uint32_t tab = 0 /* rope_tab_addr: the staged table, 0 = read the global table */) {
   const int row_in_batch = row0 + lane;
+  if (tab != 0) load_table_chunk_smem(tab, rotate, 0, tcur);
   float2 tnext[16];
   uint32_t ocur[32], onext[32];
   const int c0 = half * 4;
@@ -262,7 +316,8 @@ __device__ __forceinline__ void grad_epilogue(const GradOut& g, const CUtensorMa
     tmem_wait_ld();
     if (i + 1 < 4) {
       SAM2B200_TMEM_LD32(acc_addr + (cc + 1) * 32, onext);
-      load_table_chunk(g, rotate, row_in_batch, (cc + 1) * 32, tnext);
+      if (tab != 0) load_table_chunk_smem(tab, rotate, i + 1, tnext);
+      else load_table_chunk(g, rotate, row_in_batch, (cc + 1) * 32, tnext);
     }
     float v[32];
 #pragma unroll
@@ -297,8 +352,16 @@ __device__ __forceinline__ void grad_epilogue(const GradOut& g, const CUtensorMa
 #pragma unroll
       for (int k = 0; k < 16; ++k) tcur[k] = tnext[k];
     }
+#ifdef SAM2B200_EPI_TIMELINE
+    if (i == 0) SAM2B200_STAMP(dbg, 2);
+    if (i == 1) SAM2B200_STAMP(dbg, 3);
+    if (i == 3) SAM2B200_STAMP(dbg, 4);
+#endif
   }
   if (lane == 0) tma_store_wait_read();
+#ifdef SAM2B200_EPI_TIMELINE
+  SAM2B200_STAMP(dbg, 7);
+#endif
 }
 
 // PROJ epilogue, phase 2: this warp's 32 rows x 128 columns of the projection result (TMEM) + bias (+ rowsum * rank-1 vector)
@@ -1003,6 +1066,15 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
     const uint32_t lane_addr = tmem + (uint32_t(quarter * 32) << 16);
     const long long a_row_idx = (long long)a_tile * kBlockM + row;
     const bool row_valid = a_row_idx < p.La;
+    uint32_t tab = 0;
+    if (p.gout.rope_smem > 0) {     // rotation table of this CTA's rows -> shared memory, under the operand fetch
+      const uint32_t area = smem_u32(&sh) + (uint32_t)sizeof(SharedStorage3);
+      const uint32_t ybase = area + p.gout.rope_w * kRopeXStride;
+      rope_stage_x(p.gout, area, threadIdx.x);
+      rope_stage_y(p.gout, ybase, a_tile * kBlockM, threadIdx.x);
+      cp_async_commit();
+      tab = rope_tab_addr(p.gout, area, ybase, a_tile * kBlockM, row, half);
+    }
     {
       mbar_wait(&sh.a1_full, 0);
       stage_to_tmem_half(smem_u32(half ? &sh.y_tiles[kStages3 - 1][0] : &sh.x_tiles[kStages3 - 1][0]), row, lane_addr + k3ColA1, half);
@@ -1089,11 +1161,12 @@ three_gemm_kernel(const __grid_constant__ CUtensorMap map_a2, const __grid_const
       mbar_arrive(&sh.ds_ready);
     }
     float2 tcur[16];
-    load_table_chunk(p.gout, rotate, row0 + lane, half * 128, tcur);   // in flight while the last MMAs drain
+    if (tab == 0) load_table_chunk(p.gout, rotate, row0 + lane, half * 128, tcur);   // in flight while the last MMAs drain
+    else { cp_async_wait_all(); asm volatile("bar.sync 6, 256;" ::: "memory"); }       // the staged table is complete and visible
     mbar_wait(&sh.acc_done, 0);
     tc_fence_after();
     SAM2B200_STAMP(p.dbg, 5);
-    grad_epilogue(p.gout, &map_g, stage, lane_addr + k3ColAcc, half, lane, row0, p.La, b, p.scale, rotate, tcur);
+    grad_epilogue(p.gout, &map_g, stage, lane_addr + k3ColAcc, half, lane, row0, p.La, b, p.scale, rotate, tcur, nullptr, tab);
   }
 
   tc_fence_before();

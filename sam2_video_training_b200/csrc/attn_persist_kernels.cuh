@@ -457,12 +457,25 @@ dk_persistent_kernel(const __grid_constant__ CUtensorMap map_a2,   // V  [B, M, 
     constexpr bool drop_on = DROP;
     const uint32_t drop_key = drop_on ? sam2b200::dropout_key(*p.drop.seed, p.drop.site) : 0u;
     int tc0 = 0;
+    // rotation table in shared memory: the X part once, the Y part of each item's rows into one of two buffers (item parity) --
+    // the buffer an item overwrites was last read two epilogues ago, and every warp passes the barrier in front of each epilogue
+    const bool tab_on = p.gout.rope_smem > 0;
+    const uint32_t tab_area = smem_u32(&sh) + (uint32_t)sizeof(SharedStorage3);
+    const uint32_t tab_y0 = tab_area + p.gout.rope_w * kRopeXStride;
+    if (tab_on) rope_stage_x(p.gout, tab_area, threadIdx.x);
     for (int it = 0; it < n_my; ++it) {
       const int item = (int)blockIdx.x + it * (int)gridDim.x;
       const int a_tile = item % p.n_atiles, b = item / p.n_atiles;
       const int rA = it * slots, rE = rA + nt + 1;
       const int sA = ring3_stage(rA), sE = ring3_stage(rE);
       const long long a_row_idx = (long long)a_tile * kBlockM + row;
+      uint32_t tab = 0;
+      if (tab_on) {
+        const uint32_t ybase = tab_y0 + (it & 1) * rope_y_bytes(p.gout.rope_w);
+        rope_stage_y(p.gout, ybase, a_tile * kBlockM, threadIdx.x);
+        cp_async_commit();
+        tab = rope_tab_addr(p.gout, tab_area, ybase, a_tile * kBlockM, row, half);
+      }
       float lse_next = INFINITY, delta_next = 0.f;   // per-column vectors staged one tile ahead
       if (threadIdx.x < kBlockN && (int)threadIdx.x < p.Lx) {
         lse_next = p.lse2[(long long)b * p.Lx + threadIdx.x];
@@ -527,12 +540,13 @@ dk_persistent_kernel(const __grid_constant__ CUtensorMap map_a2,   // V  [B, M, 
         mbar_arrive(&sh.ds_ready);
       }
       float2 tcur[16];
-      load_table_chunk(p.gout, rotate, row0 + lane, half * 128, tcur);
+      if (tab == 0) load_table_chunk(p.gout, rotate, row0 + lane, half * 128, tcur);
+      else { cp_async_wait_all(); asm volatile("bar.sync 6, 256;" ::: "memory"); }     // the staged table is complete and visible
       mbar_wait(&sh.acc_done, it & 1);
       tc_fence_after();
       mbar_wait(half ? &sh.y_full[sE] : &sh.x_full[sE], ring3_parity(rE));
       const uint32_t stage = smem_u32(half ? &sh.y_tiles[sE][0] : &sh.x_tiles[sE][0]) + quarter * 2 * kBoxBytes;
-      grad_epilogue(p.gout, &map_g, stage, lane_addr + k3ColAcc, half, lane, row0, p.La, b, p.scale, rotate, tcur);
+      grad_epilogue(p.gout, &map_g, stage, lane_addr + k3ColAcc, half, lane, row0, p.La, b, p.scale, rotate, tcur, nullptr, tab);
       tc0 += nt;
     }
   }

@@ -89,7 +89,9 @@ three_gemm_v64_kernel(const __grid_constant__ CUtensorMap map_a2,   // [B, La, 6
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh.tmem_base;
+#ifndef SAM2B200_EPI_TIMELINE
   SAM2B200_STAMP(p.dbg, 2);
+#endif
 
   if (warp == kProducerWarp) {
     const bool leader = elect_one();
@@ -155,8 +157,10 @@ three_gemm_v64_kernel(const __grid_constant__ CUtensorMap map_a2,   // [B, La, 6
     };
     mbar_wait(&sh.a_full, 0);
     tc_fence_after();
+#ifndef SAM2B200_EPI_TIMELINE
     if (p.dbg != nullptr && lane == 0)
       p.dbg[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + 3] = gtimer();
+#endif
     issue_s_dp(0);
     if (nt > 1) issue_s_dp(1);
     for (int j = 0; j < nt; ++j) {
@@ -184,6 +188,15 @@ three_gemm_v64_kernel(const __grid_constant__ CUtensorMap map_a2,   // [B, La, 6
     const long long a_row_idx = (long long)a_tile * kBlockM + row;
     const bool row_valid = a_row_idx < p.La;
     const int row0 = a_tile * kBlockM + quarter * 32;
+    uint32_t tab = 0;
+    if (p.gout.rope_smem > 0) {     // rotation table of this CTA's rows -> shared memory, under the operand fetch
+      const uint32_t area = smem_u32(&sh) + (uint32_t)sizeof(SharedStorageV64);
+      const uint32_t ybase = area + p.gout.rope_w * kRopeXStride;
+      rope_stage_x(p.gout, area, threadIdx.x);
+      rope_stage_y(p.gout, ybase, a_tile * kBlockM, threadIdx.x);
+      cp_async_commit();
+      tab = rope_tab_addr(p.gout, area, ybase, a_tile * kBlockM, row, half);
+    }
     const uint32_t stage = smem_u32(&sh.a1[0]) + warp * (4 * kBoxBytes);   // a1 + the ring behind it are idle at the epilogue
     const bool rotate = p.gout.rope_table != nullptr && (row0 + lane) < p.gout.rope_rows;
     const float c = p.scale_log2;
@@ -218,7 +231,9 @@ three_gemm_v64_kernel(const __grid_constant__ CUtensorMap map_a2,   // [B, La, 6
       const uint32_t dbuf = lane_addr + ((j & 1) ? kVColDP1 : kVColDP0) + half * kHalfN;
       mbar_wait(&sh.s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
+#ifndef SAM2B200_EPI_TIMELINE
       if (j == 0) SAM2B200_STAMP(p.dbg, 4);
+#endif
       float pv[kHalfN];
       {
         uint32_t r0[32];
@@ -264,11 +279,12 @@ three_gemm_v64_kernel(const __grid_constant__ CUtensorMap map_a2,   // [B, La, 6
       mbar_arrive(&sh.ds_ready[j & 1]);
     }
     float2 tcur[16];
-    load_table_chunk(p.gout, rotate, row0 + lane, half * 128, tcur);
+    if (tab == 0) load_table_chunk(p.gout, rotate, row0 + lane, half * 128, tcur);
+    else { cp_async_wait_all(); asm volatile("bar.sync 6, 256;" ::: "memory"); }       // the staged table is complete and visible
     mbar_wait(&sh.acc_done, 0);
     tc_fence_after();
     SAM2B200_STAMP(p.dbg, 5);
-    grad_epilogue(p.gout, &map_g, stage, lane_addr + kVColAcc, half, lane, row0, p.La, b, p.scale, rotate, tcur);
+    grad_epilogue(p.gout, &map_g, stage, lane_addr + kVColAcc, half, lane, row0, p.La, b, p.scale, rotate, tcur, p.dbg, tab);
   }
 
   tc_fence_before();

@@ -15,6 +15,11 @@
 //   warp 8  TMA producer: per 64-row slab 4 boxes of A (256 output rows) + NT / 64 boxes of B, 3- or 4-stage ring
 //   warp 9  tcgen05.mma issuer: two [128 x NT] fp32 accumulators in tensor memory (2 x NT columns), 4 k-steps per slab each
 //   warps 0-7  epilogue: TMEM -> registers -> red.global.add.v4.f32 (each thread owns 32 contiguous floats of a C row)
+//
+// BIAS GRADIENT (dbias[Mo] += column sums of A = A^T . 1): the MN-major B operand is 64-column boxes one LBO apart, so a constant
+// box of ones behind the last B box turns the column sum into 16 more accumulator columns of the SAME instructions (N = NT + 16;
+// only the CTAs of output column tile 0 do it).  The attention backward's gradient epilogues then no longer need the
+// 31-shuffle butterfly + atomics per 32 x 32 block (1.4 us of a 5 us epilogue, profiles/r2_timeline_epilogue.txt).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -38,12 +43,16 @@ constexpr int kMaxStages = 4;
 
 template <int TM, int NT>
 struct Shared {
-  static constexpr int kStageBytes = (TM / 64 + NT / 64) * kBoxBytes;              // 64 KB (256 x 256) | 40 KB (256 x 64) | 32 KB (128 x 128)
+  static constexpr bool kBias = NT <= 128;                                         // room for 16 more accumulator columns
+  static constexpr int kLoadBytes = (TM / 64 + NT / 64) * kBoxBytes;               // 64 KB (256 x 256) | 40 KB (256 x 64) | 32 KB (128 x 128)
+  static constexpr int kStageBytes = kLoadBytes + (kBias ? kBoxBytes : 0);         // + the box of ones
   static constexpr int kStages = (kStageBytes >= 65536) ? 3 : 4;
-  alignas(1024) uint8_t tiles[kStages][kStageBytes];     // [A box 0..3 | B box 0..NT/64-1]
+  static constexpr int kAccStride = (NT == 64) ? 128 : NT;                         // TMEM columns between the two accumulators
+  alignas(1024) uint8_t tiles[kStages][kStageBytes];     // [A box 0..3 | B box 0..NT/64-1 | ones]
   alignas(8) uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
   uint64_t acc_done;
+  uint64_t ones_ready;
   uint32_t tmem_base;
 };
 
@@ -53,6 +62,7 @@ struct Params {
   long long rows;           // R
   long long rows_per_split; // multiple of 64
   int n_tiles_m, n_tiles_n; // output tiles
+  float* dbias;             // [Mo] fp32 or nullptr: += column sums of A
 };
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
@@ -76,11 +86,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a,   // A [R, Mo] bf16, box
   const long long r_end = min(p.rows, r_begin + p.rows_per_split);
   const int nslab = (int)((r_end - r_begin + kSlab - 1) / kSlab);      // >= 1 by construction of the grid
   constexpr int kStages = Sh::kStages;
-  constexpr uint32_t kTmemCols = (kAcc * NT >= 512) ? 512 : ((kAcc * NT >= 256) ? 256 : 128);
+  constexpr int kAccStride = Sh::kAccStride;
+  constexpr uint32_t kTmemCols = Sh::kBias ? 256 : 512;     // 2 x 128 (NT = 64) | 144 (NT = 128) | 2 x 256
+  const bool do_bias = Sh::kBias && p.dbias != nullptr && tn == 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], 1); }
     mbar_init(&sh.acc_done, 1);
+    mbar_init(&sh.ones_ready, kEpiWarps * 32);
     fence_barrier_init();
   }
   if (warp == 8 && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_b); }
@@ -98,7 +111,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a,   // A [R, Mo] bf16, box
       mbar_wait(&sh.empty[s], ((j / kStages) & 1) ^ 1);
       if (leader) {
         const int row0 = (int)(r_begin + (long long)j * kSlab);
-        mbar_arrive_expect_tx(&sh.full[s], Sh::kStageBytes);
+        mbar_arrive_expect_tx(&sh.full[s], Sh::kLoadBytes);
 #pragma unroll
         for (int c = 0; c < kTileM / 64; ++c)
           tma_load_3d(&sh.tiles[s][c * kBoxBytes], &map_a, &sh.full[s], tm * kTileM + c * 64, row0, 0);
@@ -111,7 +124,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a,   // A [R, Mo] bf16, box
   } else if (warp == 9) {
     // ===================== MMA issuer =====================
     const bool leader = elect_one();
-    constexpr uint32_t idesc = make_idesc_bf16(128, NT, 1, 1);              // A^T and B both MN-major
+    constexpr uint32_t idesc_plain = make_idesc_bf16(128, NT, 1, 1);        // A^T and B both MN-major
+    constexpr uint32_t idesc_ones = make_idesc_bf16(128, Sh::kBias ? NT + 16 : NT, 1, 1);
+    const uint32_t idesc = do_bias ? idesc_ones : idesc_plain;
+    if (do_bias) mbar_wait(&sh.ones_ready, 0);
     const uint32_t base_lo = desc_lo_sw128(smem_u32(&sh.tiles[0][0]), kBoxBytes);   // LBO = stride between 64-column boxes
     for (int j = 0; j < nslab; ++j) {
       const int s = j % kStages;
@@ -125,7 +141,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a,   // A [R, Mo] bf16, box
           const uint32_t a_lo = st + (h * 2 * kBoxBytes >> 4);                // rows h * 128 .. of the output tile: boxes 2h, 2h + 1
 #pragma unroll
           for (int ks = 0; ks < kSlab / 16; ++ks)                             // 16 contraction rows = 2 groups of 8 rows = 2048 B
-            umma_ss_lohi(tmem + h * NT, a_lo + ks * (2048 >> 4), b_lo + ks * (2048 >> 4), kDescHiSw128_1024, idesc, (j > 0) || (ks > 0));
+            umma_ss_lohi(tmem + h * kAccStride, a_lo + ks * (2048 >> 4), b_lo + ks * (2048 >> 4), kDescHiSw128_1024, idesc, (j > 0) || (ks > 0));
         }
         umma_commit(&sh.empty[s]);
         if (j + 1 >= nslab) umma_commit(&sh.acc_done);
@@ -136,6 +152,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a,   // A [R, Mo] bf16, box
     // ===================== epilogue: partial tile -> C with vector reductions =====================
     const int quarter = warp & 3, half = warp >> 2;
     const uint32_t lane_addr = tmem + (uint32_t(quarter * 32) << 16);
+    if (do_bias) {   // the constant operand: bf16 ones in the box behind the B boxes of every stage (2 x 16 bytes per thread and stage)
+#pragma unroll
+      for (int s = 0; s < kStages; ++s) {
+        const uint32_t box = smem_u32(&sh.tiles[s][Sh::kLoadBytes]) + threadIdx.x * 16;
+        sts128(box, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+        sts128(box + 4096, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+      }
+      fence_proxy_async();
+      mbar_arrive(&sh.ones_ready);
+    }
     mbar_wait(&sh.acc_done, 0);
     tc_fence_after();
     constexpr int kColsPerWarp = NT / 2;                 // this warp's share of the tile's columns
@@ -146,12 +172,18 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a,   // A [R, Mo] bf16, box
 #pragma unroll 1
       for (int cc = 0; cc < kColsPerWarp / 32; ++cc) {
         uint32_t o[32];
-        SAM2B200_TMEM_LD32(lane_addr + h * NT + half * kColsPerWarp + cc * 32, o);
+        SAM2B200_TMEM_LD32(lane_addr + h * kAccStride + half * kColsPerWarp + cc * 32, o);
         tmem_wait_ld();
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           red_add_v4(dst + cc * 32 + 4 * k, __uint_as_float(o[4 * k]), __uint_as_float(o[4 * k + 1]), __uint_as_float(o[4 * k + 2]),
                      __uint_as_float(o[4 * k + 3]));
+      }
+      if (do_bias && half == 0) {     // columns NT .. NT + 15 all hold sum_r A[r, row]
+        uint32_t o[16];
+        SAM2B200_TMEM_LD16(lane_addr + h * kAccStride + NT, o);
+        tmem_wait_ld();
+        atomicAdd(p.dbias + crow, __uint_as_float(o[0]));
       }
     }
   }
@@ -201,9 +233,11 @@ extern "C" {
 
 // c [Mo, ldc] fp32 += a[R, Mo]^T . b[R, No]; a: bf16, row stride lda elements; b: bf16, row stride ldb.  Mo a multiple of 256,
 // No = 64 or a multiple of 256.  Partial tiles are added with fp32 reductions (order not fixed: results are reproducible to
-// fp32 round-off only, like every split-K scheme with atomics).
+// fp32 round-off only, like every split-K scheme with atomics).  dbias (nullable): [Mo] fp32 += column sums of a (the bias
+// gradient of the same linear layer) from the same instructions; only for the [256 x 64] / [128 x 128] tile shapes
+// (No = 64, or No = 256 with Mo <= 768).
 int sam2b200_wgrad(float* c, long long ldc, const void* a, long long lda, const void* b, long long ldb, long long R, int Mo, int No,
-                   cudaStream_t stream) {
+                   float* dbias, cudaStream_t stream) {
   if (!c || !a || !b || R <= 0 || R >= (1LL << 31) || Mo <= 0 || (Mo % 256) || !(No == 64 || (No > 0 && No % 256 == 0)) || ldc < No ||
       lda < Mo || ldb < No || (lda % 8) || (ldb % 8) || (ldc % 4) || (reinterpret_cast<uintptr_t>(c) & 15) ||
       (reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15))
@@ -215,10 +249,11 @@ int sam2b200_wgrad(float* c, long long ldc, const void* a, long long lda, const 
   // tile shape: [256 x 64] for the 64-wide outputs, [128 x 128] when the output is at most 768 x 256 (reduction traffic
   // dominates), [256 x 256] for the [256 x 2048] / [2048 x 256] MLP weights (operand traffic dominates)
   const bool small = No == 256 && Mo <= 768;
+  if (dbias && !(No == 64 || small)) return sam2b200::fail(SAM2B200_ERR_INVALID, "wgrad: dbias needs No = 64 or (No = 256 and Mo <= 768)");
   const int tm_sz = small ? 128 : 256;
   const int nt = (No == 64) ? 64 : (small ? 128 : 256);
   wgrad::Params p{};
-  p.c = c; p.ldc = ldc; p.rows = R;
+  p.c = c; p.ldc = ldc; p.rows = R; p.dbias = dbias;
   p.n_tiles_m = Mo / tm_sz; p.n_tiles_n = No / nt;
   const int tiles = p.n_tiles_m * p.n_tiles_n;
   int dev = 0, sms = 148;

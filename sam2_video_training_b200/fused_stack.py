@@ -156,15 +156,17 @@ def ln_proj(x, res, gamma, beta, w16, bias16, n_out, out_width=256, table=None, 
     return outs, y, x_new, mean, rstd
 
 
-def wgrad_(c32, a16, b16):
+def wgrad_(c32, a16, b16, dbias=None):
     """c32 [Mo, No] fp32 += a16[R, Mo]^T @ b16[R, No] in place (sam2b200_wgrad: split over R, tcgen05, partial tiles added with
-    fp32 reductions).  Row strides may exceed the widths (column slices of wider buffers)."""
+    fp32 reductions).  Row strides may exceed the widths (column slices of wider buffers).  dbias (fp32 [Mo], optional) +=
+    column sums of a16 (the bias gradient of the same layer) from the same MMAs (No = 64 or Mo <= 768 only)."""
     r, mo = a16.shape
     no = b16.shape[1]
     assert c32.shape == (mo, no) and c32.dtype == F32 and c32.stride(1) == 1
     assert a16.dtype == BF16 and b16.dtype == BF16 and a16.stride(1) == 1 and b16.stride(1) == 1 and b16.shape[0] == r
+    assert dbias is None or (dbias.dtype == F32 and dbias.shape == (mo,) and dbias.is_contiguous())
     rc = _lib.load().sam2b200_wgrad(c32.data_ptr(), c32.stride(0), a16.data_ptr(), a16.stride(0), b16.data_ptr(), b16.stride(0), r, mo, no,
-                                    _stream(c32.device))
+                                    dbias.data_ptr() if dbias is not None else None, _stream(c32.device))
     _lib.check(rc, "sam2b200_wgrad")
     return c32
 
@@ -243,6 +245,10 @@ PROJ_KERNEL_K64 = bool(os.environ.get("SAM2B200_PROJ_KERNEL_K64"))
 # 0.497) but the STEP gets 0.5 ms slower -- both streams together saturate the GPU, so re-reading the gradients (116 MB for the
 # cross-attention keys) costs more than the epilogue arithmetic (profiles/r2_bias_gradient_ab.txt).  Not the default.
 EPILOGUE_BIAS = not bool(os.environ.get("SAM2B200_SIDE_STREAM_BIAS"))
+# Round 2, later: wherever the weight gradient of the same projection goes through sam2b200_wgrad, the bias gradient comes out of
+# THAT kernel (16 extra accumulator columns against a constant operand of ones: no extra pass, no extra launch) and the attention
+# epilogue skips its column sums.  SAM2B200_NO_WGRAD_BIAS=1 restores the epilogue sums everywhere.
+WGRAD_BIAS = not bool(os.environ.get("SAM2B200_NO_WGRAD_BIAS"))
 
 
 def bias_grad_(gbias, dx16):
@@ -652,13 +658,15 @@ class MemoryAttentionStackFn(torch.autograd.Function):
 
         def acc_w(i, a_t, bmat, bias=None):     # grad[i] (+)= a_t @ bmat (bf16 x bf16 -> fp32); bias grad (+)= colsum(a_t^T)
             def work():
-                if bias is not None:
+                own = _wgrad_ok(a_t.shape[0], bmat.shape[1]) and a_t.stride(0) == 1
+                fused_b = bias if (own and WGRAD_BIAS) else None
+                if bias is not None and fused_b is None:
                     colsum_bf16(a_t.t(), bias)
-                if _wgrad_ok(a_t.shape[0], bmat.shape[1]) and a_t.stride(0) == 1:
+                if own:
                     if direct:
-                        wgrad_(gv[i], a_t.t(), bmat)
+                        wgrad_(gv[i], a_t.t(), bmat, fused_b)
                     else:
-                        grads[i] = wgrad_(torch.zeros((a_t.shape[0], bmat.shape[1]), dtype=F32, device=bmat.device), a_t.t(), bmat)
+                        grads[i] = wgrad_(torch.zeros((a_t.shape[0], bmat.shape[1]), dtype=F32, device=bmat.device), a_t.t(), bmat, fused_b)
                 elif direct:
                     torch.addmm(gv[i], a_t, bmat, out_dtype=F32, out=gv[i])
                 else:
@@ -702,6 +710,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             # conjugate RoPE and the q / k / v bias gradients (column sums) are fused into the gradient epilogues.
             # Only dQ is on the path of the residual-stream gradient: the key-side kernels (dV, dK) and everything
             # they feed (weight gradients, memory-bank gradients) go to the side stream.
+            wb_q = WGRAD_BIAS and _wgrad_ok(d, d)          # q bias gradient from the weight-gradient kernel instead of the dQ epilogue
             if mt["v64"]:
                 # saved v2 / o2_32 are out64 / its fp32 copy.  v_proj acted on out64: its gradients are two small GEMMs,
                 # dout64 = dO Wv feeds the attention backward, Delta = rowsum(dout64 o out64); there is no dV.
@@ -742,15 +751,17 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                 args = (q2_rot, k2_rot, memv.view(b, m, 64), do64, lse2, delta, scale)
 
                 def key_side(args=args, kw=kw, l=l, ix=ix, W=W):
-                    _, dk2 = attn_bwd_v64(*args, parts=4, dbias=(None, gv[ix["ca.k.b"]] if EPILOGUE_BIAS else None), **kw)
+                    wb = WGRAD_BIAS and _wgrad_ok(d, 64)       # bias gradient from the weight-gradient kernel
+                    _, dk2 = attn_bwd_v64(*args, parts=4, dbias=(None, gv[ix["ca.k.b"]] if (EPILOGUE_BIAS and not wb) else None), **kw)
                     dk2 = dk2.view(rm, d)
-                    if not EPILOGUE_BIAS:
+                    if not EPILOGUE_BIAS and not wb:
                         bias_grad_(gv[ix["ca.k.b"]], dk2)
                     if _wgrad_ok(d, 64):
+                        gb_k = gv[ix["ca.k.b"]] if wb else None
                         if direct:
-                            wgrad_(gv[ix["ca.k.w"]], dk2, memk)
+                            wgrad_(gv[ix["ca.k.w"]], dk2, memk, gb_k)
                         else:
-                            grads[ix["ca.k.w"]] = wgrad_(torch.zeros((d, 64), dtype=F32, device=dev), dk2, memk)
+                            grads[ix["ca.k.w"]] = wgrad_(torch.zeros((d, 64), dtype=F32, device=dev), dk2, memk, gb_k)
                     elif direct:
                         torch.addmm(gv[ix["ca.k.w"]], dk2.t(), memk, out_dtype=F32, out=gv[ix["ca.k.w"]])
                     else:
@@ -758,7 +769,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                     if need_memgrad:
                         torch.addmm(dmemk, dk2, W["ca.k.w"], out_dtype=F32, out=dmemk)
                 side.run(key_side, q2_rot, k2_rot, memv, do64, lse2, delta, dp_bias)
-                dq2, _ = attn_bwd_v64(*args, parts=8, dbias=(gv[ix["ca.q.b"]] if EPILOGUE_BIAS else None, None), **kw)
+                dq2, _ = attn_bwd_v64(*args, parts=8, dbias=(gv[ix["ca.q.b"]] if (EPILOGUE_BIAS and not wb_q) else None, None), **kw)
             else:
                 delta = torch.empty((b, n), dtype=F32, device=dev)
                 args = (q2_rot, k2_rot, v2.view(b, m, d), None, o2_32, do2.view(b, n, d), lse2, scale)
@@ -783,11 +794,11 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                     if need_mem:
                         torch.addmm(dmemv, dv2, W["ca.v.w"], out_dtype=F32, out=dmemv)
                 side.run(key_side, *args[:3], o2_32, do2, lse2, delta)
-                dq2, _, _ = attn_bwd(*args, parts=8, dbias=(gv[ix["ca.q.b"]] if EPILOGUE_BIAS else None, None, None), **kw)
+                dq2, _, _ = attn_bwd(*args, parts=8, dbias=(gv[ix["ca.q.b"]] if (EPILOGUE_BIAS and not wb_q) else None, None, None), **kw)
             dq2 = dq2.view(r, d)
             dy2 = torch.mm(dq2, W["ca.q.w"])
-            acc_w(ix["ca.q.w"], dq2.t(), y2)
-            if not EPILOGUE_BIAS:
+            acc_w(ix["ca.q.w"], dq2.t(), y2, gv[ix["ca.q.b"]] if wb_q else None)
+            if not EPILOGUE_BIAS and not wb_q:
                 side.run(lambda dq2=dq2, gb=gv[ix["ca.q.b"]]: bias_grad_(gb, dq2), dq2)
             g, dsa = ln_bwd(dy2, x1, mean2, rstd2, P["n2.w"], g, gv[ix["n2.w"]], gv[ix["n2.b"]], dbias=gv[ix["sa.o.b"]],
                             drop=dsite("p_res", l, 2))
@@ -795,25 +806,26 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             acc_w(ix["sa.o.w"], dsa.t(), o.view(r, d))
             do = torch.mm(dsa, W["sa.o.w"])
             dqkv = torch.empty((b, n, 3 * d), dtype=BF16, device=dev)   # [dq | dk | dv], written in place by the kernels
+            qkv_w = [masters[ix[k]] for k in ("sa.q.w", "sa.k.w", "sa.v.w")]
+            gw = bucket.span(qkv_w, (3 * d, d)) if direct else None
+            gb3 = bucket.span([masters[ix[k]] for k in ("sa.q.b", "sa.k.b", "sa.v.b")], (3 * d,)) if direct else None
+            wb_sa = WGRAD_BIAS and gw is not None and gb3 is not None and _wgrad_ok(3 * d, d)   # the three bias gradients from the stacked weight-gradient GEMM
             attn_bwd(q_rot, k_rot, v.view(b, n, d), None, o32, do.view(b, n, d), lse, scale, table=table, n_rope_k=n,
                      grad_dtype=BF16, dq=dqkv[:, :, :d], dk=dqkv[:, :, d:2 * d], dv=dqkv[:, :, 2 * d:],
-                     dbias=(gv[ix["sa.q.b"]], gv[ix["sa.k.b"]], gv[ix["sa.v.b"]]) if EPILOGUE_BIAS else (None, None, None),
+                     dbias=(gv[ix["sa.q.b"]], gv[ix["sa.k.b"]], gv[ix["sa.v.b"]]) if (EPILOGUE_BIAS and not wb_sa) else (None, None, None),
                      drop=dsite("p_sa", l, 0))
             dqkv = dqkv.view(r, 3 * d)
-            if not EPILOGUE_BIAS:
-                qkv_b = [masters[ix[k]] for k in ("sa.q.b", "sa.k.b", "sa.v.b")]
-                gb = bucket.span(qkv_b, (3 * d,)) if direct else None
+            if not EPILOGUE_BIAS and not wb_sa:
+                gb = gb3
                 if gb is not None:      # the bucket lays the three biases out back to back: one [1 x R] . [R x 768] product
                     side.run(lambda dqkv=dqkv, gb=gb: bias_grad_(gb, dqkv), dqkv)
                 else:
                     for j, kb in enumerate(("sa.q.b", "sa.k.b", "sa.v.b")):
                         side.run(lambda dx=dqkv[:, j * d:(j + 1) * d], g_=gv[ix[kb]]: bias_grad_(g_, dx), dqkv)
-            qkv_w = [masters[ix[k]] for k in ("sa.q.w", "sa.k.w", "sa.v.w")]
-            gw = bucket.span(qkv_w, (3 * d, d)) if direct else None
             if gw is not None:
                 # the bucket lays the three projection weights out back to back: one [768, 256] weight-gradient GEMM
                 if _wgrad_ok(3 * d, d):
-                    side.run(lambda dqkv=dqkv, y1=y1, gw=gw: wgrad_(gw, dqkv, y1), dqkv, y1)
+                    side.run(lambda dqkv=dqkv, y1=y1, gw=gw, gb=(gb3 if wb_sa else None): wgrad_(gw, dqkv, y1, gb), dqkv, y1)
                 else:
                     side.run(lambda dqkv=dqkv, y1=y1, gw=gw: torch.addmm(gw, dqkv.t(), y1, out_dtype=F32, out=gw), dqkv, y1)
             elif direct:

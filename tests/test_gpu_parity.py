@@ -633,6 +633,16 @@ def test_wgrad_kernel(dev, r, mo, no):
     torch.cuda.synchronize()
     want = c0.double() + a.double().t() @ b.double()
     assert rel_l2(c, want) < 2e-5, rel_l2(c, want)
+    if no == 64 or (no == 256 and mo <= 768):
+        # bias gradient from the same MMAs: 16 extra accumulator columns against a constant operand of ones
+        c = c0.clone()
+        db0 = torch.randn(mo, device=dev, generator=g)
+        db = db0.clone()
+        fs.wgrad_(c, a, b, db)
+        torch.cuda.synchronize()
+        assert rel_l2(c, want) < 2e-5, rel_l2(c, want)
+        want_b = db0.double() + a.double().sum(0)
+        assert rel_l2(db, want_b) < 2e-5, rel_l2(db, want_b)
 
 
 @pytest.mark.parametrize("rows", [128, 700, 4096])
@@ -1123,6 +1133,41 @@ def test_gradient_epilogue_axial_table_addressing_bit_identical(dev, grid):
         lib.sam2b200_debug_set_variant(1, 0)
     for x, y in zip(res[0], res[1]):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("b,grid,nf,nptr", [(2, 8, 2, 12), (3, 24, 2, 12), (56, 24, 1, 0), (2, 32, 3, 20), (40, 12, 2, 8), (1, 64, 1, 4)])
+def test_gradient_epilogue_staged_rotation_table_bit_identical(dev, b, grid, nf, nptr):
+    """The gradient epilogues rotate with a copy of the CTA's table rows staged in shared memory at kernel start (default)
+    instead of loading them from global memory per 32-column chunk (sam2b200_debug_set_variant key 3 = 1): same numbers, so dq / dk
+    must be bit-identical -- one-shot and persistent key-side kernels (b * key blocks > 148), CTAs whose rows straddle a frame
+    boundary and the pointer tokens, grids whose table does not fit next to the raw-memory kernels (64: falls back)."""
+    from sam2_video_training_b200 import _lib, ops
+    from sam2_video_training_b200.modeling.position_encoding import compute_axial_cis
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n = grid * grid
+    m = nf * n + nptr
+    table = compute_axial_cis(dim=256, end_x=grid, end_y=grid).to(dev)
+    q, do = (torch.randn(b, n, 256, device=dev, generator=g).to(torch.bfloat16) for _ in range(2))
+    k, v = (torch.randn(b, m, 256, device=dev, generator=g).to(torch.bfloat16) for _ in range(2))
+    mem = torch.randn(b, m, 64, device=dev, generator=g).to(torch.bfloat16)
+    do64 = torch.randn(b, n, 64, device=dev, generator=g).to(torch.bfloat16)
+    o, o32, lse = ops.attn_fwd(q, k, v, 1 / 16.0)
+    o64, o64_32, lse64, _ = ops.attn_fwd_v64(q, k, mem, 1 / 16.0)
+    delta = (do64.float() * o64_32).sum(-1)
+    res = {}
+    try:
+        for variant in (1, 0):
+            lib.sam2b200_debug_set_variant(3, variant)
+            a = ops.attn_bwd(q, k, v, None, o32, do, lse, 1 / 16.0, table=table, n_rope_k=nf * n, grad_dtype=torch.bfloat16)
+            c = ops.attn_bwd_v64(q, k, mem, do64, lse64, delta, 1 / 16.0, table=table, n_rope_k=nf * n, grad_dtype=torch.bfloat16)
+            a32 = ops.attn_bwd(q, k, v, None, o32, do, lse, 1 / 16.0, table=table, n_rope_k=nf * n, grad_dtype=torch.float32)
+            torch.cuda.synchronize()
+            res[variant] = (*a, *c, *a32)
+    finally:
+        lib.sam2b200_debug_set_variant(3, 0)
+    for i, (x, y) in enumerate(zip(res[0], res[1])):
+        assert torch.equal(x, y), i
 
 
 @pytest.mark.parametrize("b,grid,nf,nptr,drop", [(3, 12, 2, 8, 0.0), (2, 24, 7, 28, 0.0), (40, 8, 3, 12, 0.0), (2, 16, 2, 4, 0.1)])

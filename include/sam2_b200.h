@@ -42,7 +42,9 @@ long long sam2b200_launch_count(void);
 /* Debug aid: per-CTA phase timelines of the attention kernels into a device buffer (NULL = off). */
 long long sam2b200_debug_set_timeline(void* buf, long long n_u64);
 /* Debug / A-B aid: choose a kernel variant at run time.  key 0 = backward of the raw-memory cross-attention
- * (0 = default, 1 = experimental two-softmax-group kernels); key 1 = rotation-table addressing of the gradient epilogues
+ * (0 = default: dK with resident CTAs walking over (key block, object) items when N <= 768, there are more items than SMs and
+ * the gradients are bf16; 1 = experimental two-softmax-group kernels, 2 = one CTA per item, 3 = resident CTAs for dK and dQ at
+ * every length); key 1 = rotation-table addressing of the gradient epilogues
  * (0 = default: axial -- rows x and y*w of a w x w grid table, 1 = full rows); key 3 = rotation table of the gradient epilogues
  * (0 = default: staged in shared memory, 1 = read from global memory per chunk); key 2 = forward of the raw-memory cross-attention
  * (0 = default: one online-softmax stream per CTA, 1 = experimental two-stream kernel, same results to bf16 rounding of the probabilities).  Returns the previous value, -1 for an unknown key. */

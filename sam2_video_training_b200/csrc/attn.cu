@@ -19,6 +19,7 @@
 #include "attn_v64_kernels.cuh"
 #include "attn_v64x2_kernels.cuh"
 #include "attn_fwd_v64x2_kernel.cuh"
+#include "attn_v64_persist_kernel.cuh"
 #include "tma_desc.cuh"
 
 namespace {
@@ -655,6 +656,7 @@ int sam2b200_attn_bwd_v64(const void* q, const void* k, const void* memv, const 
   const sam2b200::Dropout nodrop = sam2b200::make_dropout(drop_seed, drop_site, drop_p);   // (no dropout unless a seed is given)
   const bool drop_on = nodrop.seed != nullptr;
   const size_t smemv = sizeof(attn::SharedStorageV64) + 1024;
+  const size_t smemvp = sizeof(attn::SharedStorageV64P) + 1024;
   if (parts & 4) {   // dK: A1 = K block (TMEM), A2 = memory block, X = Q tiles, Y = dout64 tiles
     attn::ThreeGemmParams p{};
     p.La = M; p.Lx = N; p.scale_log2 = scale * kLog2e; p.scale = scale; p.lse2 = lse2; p.delta = delta;
@@ -679,6 +681,20 @@ int sam2b200_attn_bwd_v64(const void* q, const void* k, const void* memv, const 
       } else {
         if ((rc = set_smem(attn::three_gemm_v64x2_kernel<attn::MODE_DK>, smemx2))) return rc;
         attn::three_gemm_v64x2_kernel<attn::MODE_DK><<<grid, attn::kX2Threads, smemx2, stream>>>(map_m128, map_q64, map_d64, map_k128, map_dk, p);
+      }
+    } else if (!single_buf && !persist_dk && g_variant[0] != 2 && grad_dtype == 1 && N > 2 * attn::kBlockN &&
+               (N <= 12 * attn::kBlockN || g_variant[0] == 3) && p.n_items > num_sms()) {
+      // resident CTAs walking over (key block, object) items: the next item's operands land under this item's epilogue
+      // (attn_v64_persist_kernel.cuh); sam2b200_debug_set_variant(0, 2) = one CTA per item.  Short query loops only
+      // (N <= 768: dK 204 -> 189 us at cfg2; no gain at N = 1024, 5 % slower at N = 4096 -- profiles/r2_v64_persist_ab.txt)
+      p.gout.rope_smem = rope_stage_bytes(p.gout, smemvp, true);
+      const size_t sm = smemvp + p.gout.rope_smem;
+      if (drop_on) {
+        if ((rc = set_smem(attn::three_gemm_v64_persistent_kernel<attn::MODE_DK, true>, sm))) return rc;
+        attn::three_gemm_v64_persistent_kernel<attn::MODE_DK, true><<<num_sms(), attn::kThreads, sm, stream>>>(map_m128, map_q64, map_d64, map_k128, map_dk, p);
+      } else {
+        if ((rc = set_smem(attn::three_gemm_v64_persistent_kernel<attn::MODE_DK>, sm))) return rc;
+        attn::three_gemm_v64_persistent_kernel<attn::MODE_DK><<<num_sms(), attn::kThreads, sm, stream>>>(map_m128, map_q64, map_d64, map_k128, map_dk, p);
       }
     } else if (drop_on) {
       p.gout.rope_smem = rope_stage_bytes(p.gout, smemv, false);
@@ -716,6 +732,19 @@ int sam2b200_attn_bwd_v64(const void* q, const void* k, const void* memv, const 
       } else {
         if ((rc = set_smem(attn::three_gemm_v64x2_kernel<attn::MODE_DQ>, smemx2))) return rc;
         attn::three_gemm_v64x2_kernel<attn::MODE_DQ><<<grid, attn::kX2Threads, smemx2, stream>>>(map_d128, map_k64, map_m64, map_q128, map_dq, p);
+      }
+    } else if (!single_buf && g_variant[0] == 3 && grad_dtype == 1 && M > 2 * attn::kBlockN && (int)(grid.x * grid.y) > num_sms()) {
+      // query side: measured equal or slower than one CTA per item at every shape (long key loops) -- only on request (variant 3, tests)
+      p.n_atiles = (int)grid.x;
+      p.n_items = (int)(grid.x * grid.y);
+      p.gout.rope_smem = rope_stage_bytes(p.gout, smemvp, true);
+      const size_t sm = smemvp + p.gout.rope_smem;
+      if (drop_on) {
+        if ((rc = set_smem(attn::three_gemm_v64_persistent_kernel<attn::MODE_DQ, true>, sm))) return rc;
+        attn::three_gemm_v64_persistent_kernel<attn::MODE_DQ, true><<<num_sms(), attn::kThreads, sm, stream>>>(map_d128, map_k64, map_m64, map_q128, map_dq, p);
+      } else {
+        if ((rc = set_smem(attn::three_gemm_v64_persistent_kernel<attn::MODE_DQ>, sm))) return rc;
+        attn::three_gemm_v64_persistent_kernel<attn::MODE_DQ><<<num_sms(), attn::kThreads, sm, stream>>>(map_d128, map_k64, map_m64, map_q128, map_dq, p);
       }
     } else if (drop_on) {
       p.gout.rope_smem = rope_stage_bytes(p.gout, smemv, false);

@@ -1058,6 +1058,50 @@ def test_raw_memory_backward_two_softmax_groups_bit_identical(dev, b, grid, nf, 
             assert rel_l2(two[2][i], one[2][i]) < 1e-4, ("dbias", i, gdt)
 
 
+@pytest.mark.parametrize("b,grid,nf,nptr,drop", [(56, 24, 2, 8, 0.0), (40, 24, 1, 4, 0.0), (150, 12, 3, 8, 0.0), (60, 16, 3, 12, 0.1), (9, 32, 2, 20, 0.0),
+                                                  (200, 12, 1, 0, 0.1)])
+def test_raw_memory_backward_persistent_bit_identical(dev, b, grid, nf, nptr, drop):
+    """three_gemm_v64_persistent_kernel (default when there are more (row block, object) items than SMs: resident CTAs, the next
+    item's operands fetched under the current epilogue, output staging in the idle tile ring) against one CTA per item
+    (sam2b200_debug_set_variant key 0 = 2; 3 = resident CTAs for dK and dQ at every length): the same instructions on the same data, so dq / dk must be bit-identical -- odd and
+    even tile counts, 1..13 items per CTA, ragged last row blocks and tiles, frame boundaries inside a row block, dropout."""
+    from sam2_video_training_b200 import _lib, ops
+    from sam2_video_training_b200.modeling.position_encoding import compute_axial_cis
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(1234 + b)
+    n = grid * grid
+    m = nf * n + nptr
+    table = compute_axial_cis(dim=256, end_x=grid, end_y=grid).to(dev)
+    q = torch.randn(b, n, 256, device=dev, generator=g).to(torch.bfloat16)
+    k = torch.randn(b, m, 256, device=dev, generator=g).to(torch.bfloat16)
+    mem = torch.randn(b, m, 64, device=dev, generator=g).to(torch.bfloat16)
+    do64 = torch.randn(b, n, 64, device=dev, generator=g).to(torch.bfloat16)
+    dr = (drop, torch.tensor([99], dtype=torch.int64, device=dev), 2) if drop > 0 else None
+    o64, o32, lse, rs = ops.attn_fwd_v64(q, k, mem, 1 / 16.0, drop=dr)
+    delta = (do64.float() * o32).sum(-1)
+    c = torch.randn(b, n, device=dev, generator=g) if drop > 0 else None
+    if drop > 0:
+        delta = delta + c * rs
+    res = {}
+    try:
+        for variant in (2, 3):
+            lib.sam2b200_debug_set_variant(0, variant)
+            db = [torch.zeros(256, device=dev) for _ in range(2)]
+            dq, dk = ops.attn_bwd_v64(q, k, mem, do64, lse, delta.contiguous(), 1 / 16.0, table=table, n_rope_k=nf * n, grad_dtype=torch.bfloat16,
+                                      dbias=tuple(db), dp_bias=c, drop=dr)
+            dq2, dk2 = ops.attn_bwd_v64(q, k, mem, do64, lse, delta.contiguous(), 1 / 16.0, table=table, n_rope_k=nf * n, grad_dtype=torch.bfloat16,
+                                        dp_bias=c, drop=dr)
+            torch.cuda.synchronize()
+            res[variant] = (dq, dk, dq2, dk2, db)
+    finally:
+        lib.sam2b200_debug_set_variant(0, 0)
+    for i in range(4):
+        assert torch.equal(res[3][i], res[2][i]), i
+    for i in range(2):
+        assert rel_l2(res[3][4][i], res[2][4][i]) < 1e-4, ("dbias", i)
+    assert torch.isfinite(res[3][0].float()).all() and torch.isfinite(res[3][1].float()).all()
+
+
 @pytest.mark.parametrize("b,n,m,drop", [(2, 576, 4060, 0.0), (3, 64, 64, 0.0), (2, 200, 129, 0.0), (1, 1024, 3092, 0.0), (2, 144, 300, 0.1),
                                         (5, 576, 128, 0.0), (1, 130, 1000, 0.1)])
 def test_raw_memory_forward_two_softmax_streams(dev, b, n, m, drop):

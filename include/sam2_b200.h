@@ -266,6 +266,21 @@ int sam2b200_dwconv7_bwd_w(const float* dy, const float* x, float* dw, float* db
 int sam2b200_wgrad(float* c, long long ldc, const void* a, long long lda, const void* b, long long ldb, long long R, int Mo, int No,
                    float* dbias, cudaStream_t stream);
 
+/* ---- dense GEMMs without a LayerNorm in front or a ReLU mask behind (csrc/gemm.cu) -------------------------------------------
+ * c[R, No] (bf16, row stride ldc) = a[R, K] (bf16, row stride lda) . B (+ bias), fp32 accumulation; No = 256 or 64, K % 64 == 0.
+ *   b_layout 0: b = W[No, K] (row stride ldb), c = a W^T -- nn.Linear forward: linear2 (memory_attention.py:97-98) and the
+ *               memory-key projection k_proj (sam/transformer.py:278) with the axial rotation of position_encoding.py:212-239
+ *               on the fp32 accumulator when table != NULL (rows with (row % rows_per_item) < n_rope_rows, table row =
+ *               position % period; object-pointer rows stay un-rotated, transformer.py:296-302);
+ *   b_layout 1: b = W[K, No] (row stride ldb), c = a W   -- nn.Linear input gradient dX = dY W (autograd of the same lines).
+ * bias: [No] fp32 or NULL.  dot_rows [R, 64] fp32 / dot_out [R] fp32 (No = 64, both or neither): dot_out[r] = sum_c bf16(c[r, c]) *
+ * dot_rows[r, c] -- Delta = rowsum(dO' o out64) of the raw-memory cross-attention backward, from the GEMM that produces dO'.
+ * Resident CTAs, 4-stage TMA ring across tiles, SS-mode tcgen05.mma, two alternating TMEM
+ * accumulators (the epilogue of tile i overlaps the MMAs of tile i + 1), TMA-store epilogue. */
+int sam2b200_gemm(void* c, long long ldc, const void* a, long long lda, const void* b, long long ldb, int b_layout, long long R, int K,
+                  int No, const float* bias, const float* table, int rows_per_item, int n_rope_rows, int period, const float* dot_rows,
+                  float* dot_out, cudaStream_t stream);
+
 /* ---- LayerNorm + projection (+ RoPE | ReLU) in one kernel (csrc/lnproj.cu) ------------------------------------------
  * The head of every pre-norm block of MemoryAttentionLayer (sam2_video/model/modeling/memory_attention.py:58-64, 66-81,
  * 95-97 with the projections of sam2_video/model/modeling/sam/transformer.py:277-302):

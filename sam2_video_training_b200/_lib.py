@@ -73,6 +73,8 @@ _SIGNATURES = {
     "sam2b200_dwconv7_bwd_w_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "sam2b200_dwconv7_bwd_w": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "sam2b200_wgrad": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_longlong, c_int, c_int, c_void_p, c_void_p]),
+    "sam2b200_gemm": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_longlong, c_int, c_int, c_void_p, c_void_p,
+                              c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "sam2b200_mlp_dh": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p]),
     "sam2b200_bank_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                      c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsam2b200.so")
-SOURCES = ["abi.cu", "mask_loss.cu", "merge_loss.cu", "attn.cu", "glue.cu", "bank.cu", "mlp.cu", "proj.cu", "lnproj.cu", "wgrad.cu", "memenc.cu"]
+SOURCES = ["abi.cu", "mask_loss.cu", "merge_loss.cu", "attn.cu", "glue.cu", "bank.cu", "mlp.cu", "proj.cu", "lnproj.cu", "wgrad.cu", "memenc.cu", "gemm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-DNDEBUG", *os.environ.get("SAM2B200_EXTRA_NVCC_FLAGS", "").split()]
 

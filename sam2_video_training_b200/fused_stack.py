@@ -171,6 +171,33 @@ def wgrad_(c32, a16, b16, dbias=None):
     return c32
 
 
+def gemm(a16, w16, nn=False, bias=None, table=None, rows_per_item=1, n_rope_rows=0, dot_rows=None):
+    """Dense GEMM on our own resident-CTA tcgen05 kernel (sam2b200_gemm, csrc/gemm.cu), bf16 in / bf16 out, fp32 accumulation:
+        nn=False: a16 [R, K] @ w16[No, K]^T + bias   (nn.Linear forward; `table`: axial rotation of rows whose position inside
+                  their item of `rows_per_item` rows is < n_rope_rows, fused on the fp32 accumulator)
+        nn=True:  a16 [R, K] @ w16[K, No]            (nn.Linear input gradient)
+    No = 256 or 64, K a multiple of 64; bias fp32 [No]; row strides may exceed the widths.  dot_rows (fp32 [R, 64], No = 64): also
+    returns dot[r] = sum_c out[r, c] * dot_rows[r, c] (fp32 [R]) from the epilogue."""
+    r, k = a16.shape
+    no = w16.shape[1] if nn else w16.shape[0]
+    assert a16.dtype == BF16 and w16.dtype == BF16 and a16.stride(1) == 1 and w16.stride(1) == 1
+    assert w16.shape == ((k, no) if nn else (no, k)), (tuple(a16.shape), tuple(w16.shape), nn)
+    assert bias is None or (bias.dtype == F32 and bias.shape == (no,) and bias.is_contiguous())
+    assert table is None or (table.dtype == F32 and table.is_contiguous())
+    out = torch.empty((r, no), dtype=BF16, device=a16.device)
+    dot = None
+    if dot_rows is not None:
+        assert no == 64 and dot_rows.dtype == F32 and dot_rows.is_contiguous() and dot_rows.numel() == r * 64
+        dot = torch.empty(r, dtype=F32, device=a16.device)
+    rc = _lib.load().sam2b200_gemm(out.data_ptr(), no, a16.data_ptr(), a16.stride(0), w16.data_ptr(), w16.stride(0), int(bool(nn)), r, k, no,
+                                   bias.data_ptr() if bias is not None else None, table.data_ptr() if table is not None else None,
+                                   int(rows_per_item), int(n_rope_rows), table.shape[0] if table is not None else 1,
+                                   dot_rows.data_ptr() if dot_rows is not None else None, dot.data_ptr() if dot is not None else None,
+                                   _stream(a16.device))
+    _lib.check(rc, "sam2b200_gemm")
+    return out if dot is None else (out, dot)
+
+
 def mlp_dh(dm16, w2_16, h16, scale=1.0, dbias=None):
     """dh = (dm @ W2) * (h > 0) * scale in one tcgen05 GEMM with the ReLU / hidden-dropout backward in its epilogue; dbias
     (fp32 [F], optional) += column sums of dh = the bias gradient of linear1, taken from the tile in registers."""
@@ -266,6 +293,39 @@ NO_WGRAD = bool(os.environ.get("SAM2B200_NO_WGRAD"))
 
 def _wgrad_ok(mo, no):
     return (not NO_WGRAD) and mo % 256 == 0 and (no == 64 or (no == 256 and mo <= 768))
+
+
+# Dense projections without a LayerNorm in front (linear2, the memory-key / value projections, the un-fused out_proj fall-backs) and
+# every input-gradient GEMM dX = dY W run on sam2b200_gemm (csrc/gemm.cu: resident CTAs, SS-mode tcgen05, bias / RoPE epilogue).
+# A/B: SAM2B200_NO_GEMM=1 sends them back to cuBLAS (torch.addmm / mm) and the stand-alone RoPE pass.
+NO_GEMM = bool(os.environ.get("SAM2B200_NO_GEMM"))
+
+
+def _gemm_ok(a, k, no):
+    return (not NO_GEMM) and no in (256, 64) and k % 64 == 0 and a.dim() == 2 and a.stride(1) == 1 and a.stride(0) % 8 == 0 and a.data_ptr() % 16 == 0
+
+
+def linear_fwd(a16, w16, bias32, bias16):
+    """a16 @ w16^T + bias (nn.Linear forward, w16 [No, K]); the fp32 master bias feeds our kernel, the bf16 mirror cuBLAS."""
+    if _gemm_ok(a16, w16.shape[1], w16.shape[0]) and w16.is_contiguous():
+        return gemm(a16, w16, bias=bias32)
+    return torch.addmm(bias16, a16, w16.t())
+
+
+def linear_dgrad_dot(dy16, w16, rows32):
+    """(dx, dot): dx = dy16 @ w16 ([R, 64], bf16) and dot[r] = sum_c dx[r, c] * rows32[r, c] (fp32) -- the attention backward's
+    Delta = rowsum(dO' o out64) comes out of the epilogue of the GEMM that produces dO' (no cast / multiply / row-sum passes)."""
+    if _gemm_ok(dy16, w16.shape[0], w16.shape[1]) and w16.is_contiguous() and w16.shape[1] == 64 and rows32.is_contiguous():
+        return gemm(dy16, w16, nn=True, dot_rows=rows32)
+    dx = torch.mm(dy16, w16)
+    return dx, (dx.float() * rows32.view(dx.shape)).sum(-1)
+
+
+def linear_dgrad(dy16, w16):
+    """dy16 @ w16 (nn.Linear input gradient, w16 [K = out_features, No = in_features])."""
+    if _gemm_ok(dy16, w16.shape[0], w16.shape[1]) and w16.is_contiguous():
+        return gemm(dy16, w16, nn=True)
+    return torch.mm(dy16, w16)
 
 
 NO_FUSED_OUT_PROJ = bool(os.environ.get("SAM2B200_NO_FUSED_OUT_PROJ"))   # A/B switch: out_proj as a separate cuBLAS addmm after the attention kernel
@@ -497,9 +557,15 @@ class MemoryAttentionStackFn(torch.autograd.Function):
         def project_memory():        # cross-attention keys / values of every layer: functions of the bank only
             for l in range(nl):
                 W = dict(zip(_LAYER_KEYS, wb[l * _NPL:(l + 1) * _NPL]))
-                if not PROJ_KERNEL_K64:
-                    # K = 64: cuBLAS + the RoPE pass measured faster than the fused kernel (1777 CTAs of 64 KB output each
-                    # are dominated by per-CTA set-up: 129 vs 80 us, profiles/r1_proj_rope_bench.txt)
+                Pm = dict(zip(_LAYER_KEYS, params[l * _NPL:(l + 1) * _NPL]))
+                if not NO_GEMM and not PROJ_KERNEL_K64 and _gemm_ok(memk, 64, d):
+                    # K = 64 on resident CTAs (one k-slice per tile, the epilogue of tile i under the loads of tile i + 1), bias and
+                    # rotation on the fp32 accumulator: no un-rotated memory keys in HBM, no RoPE pass
+                    k2_rot = gemm(memk, W["ca.k.w"], bias=Pm["ca.k.b"], table=table, rows_per_item=m, n_rope_rows=n_rope_k).view(b, m, d)
+                    v2 = None if v64 else gemm(memv, W["ca.v.w"], bias=Pm["ca.v.b"])
+                elif not PROJ_KERNEL_K64:
+                    # A/B (SAM2B200_NO_GEMM=1): cuBLAS + the RoPE pass; the one-tile-per-CTA proj_rope kernel below is slower at K = 64
+                    # (1777 CTAs of 64 KB output each are dominated by per-CTA set-up: 129 vs 80 us, profiles/r1_proj_rope_bench.txt)
                     k2 = torch.addmm(W["ca.k.b"], memk, W["ca.k.w"].t())
                     v2 = None if v64 else torch.addmm(W["ca.v.b"], memv, W["ca.v.w"].t())
                     k2_rot = rope_apply(k2.view(b, m, d), table, n_rope_k)
@@ -538,7 +604,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                 sa = sa.view(r, d)
             else:
                 o, o32, lse = attn_fwd(q_rot, k_rot, v.view(b, n, d), scale, meta["nsplit"], drop=dsite("p_sa", l, 0))
-                sa = torch.addmm(W["sa.o.b"], o.view(r, d), W["sa.o.w"].t())
+                sa = linear_fwd(o.view(r, d), W["sa.o.w"], P["sa.o.b"], W["sa.o.b"])
             # ---- cross attention to the memory bank (memory_attention.py:66-81)
             if not NO_LNPROJ:
                 (q2_rot,), y2, x1, mean2, rstd2 = ln_proj(x, sa, P["n2.w"], P["n2.b"], W["ca.q.w"], W["ca.q.b"], 1, table=table,
@@ -568,21 +634,21 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                 # v2 / o2_32 slots of `saved` then hold out64 (bf16) and its fp32 copy
                 v2, o2_32, lse2, rs = attn_fwd_v64(q2_rot, k2_rot, memv.view(b, m, 64), scale, drop=dsite("p_ca", l, 1))
                 if NO_FOLD:
-                    o2 = torch.addmm(W["ca.v.b"], v2.view(r, 64), W["ca.v.w"].t()).view(b, n, d)      # v_proj on the result
-                    ca = torch.addmm(W["ca.o.b"], o2.view(r, d), W["ca.o.w"].t())
+                    o2 = linear_fwd(v2.view(r, 64), W["ca.v.w"], P["ca.v.b"], W["ca.v.b"]).view(b, n, d)      # v_proj on the result
+                    ca = linear_fwd(o2.view(r, d), W["ca.o.w"], P["ca.o.b"], W["ca.o.b"])
                 else:
                     # out_proj(v_proj(out64)) = out64 (Wo Wv)^T + (Wo bv + bo): one [B N, 64] -> 256 GEMM; the o2 slot of
                     # `saved` holds the folded weight (fp32 product of the master weights, rounded once)
                     o2 = mirror.w_eff[l]                       # Wo Wv, refreshed with the weight mirror (once per optimizer step)
                     if rs is None:
-                        ca = torch.addmm(mirror.b_eff[l], v2.view(r, 64), o2.t())
+                        ca = linear_fwd(v2.view(r, 64), o2, mirror.b_eff32[l], mirror.b_eff[l])
                     else:   # dropout: the value bias enters with the row sums of the dropped probabilities (rank-1 term)
-                        ca = torch.addmm(W["ca.o.b"], v2.view(r, 64), o2.t())
+                        ca = linear_fwd(v2.view(r, 64), o2, P["ca.o.b"], W["ca.o.b"])
                         ca.addr_(rs.view(r).to(BF16), mirror.wobv[l])
             else:
                 rs = None
                 o2, o2_32, lse2 = attn_fwd(q2_rot, k2_rot, v2.view(b, m, d), scale, meta["nsplit"], drop=dsite("p_ca", l, 1))
-                ca = torch.addmm(W["ca.o.b"], o2.view(r, d), W["ca.o.w"].t())
+                ca = linear_fwd(o2.view(r, d), W["ca.o.w"], P["ca.o.b"], W["ca.o.b"])
             # ---- MLP (memory_attention.py:95-98)
             if not NO_LNPROJ:   # LayerNorm + linear1 + bias + ReLU (+ hidden dropout) in one kernel
                 (h,), y3, x2, mean3, rstd3 = ln_proj(x1, ca, P["n3.w"], P["n3.b"], W["l1.w"], W["l1.b"], 1, out_width=2048, relu=True,
@@ -591,7 +657,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                 y3, x2, mean3, rstd3 = ln_fwd(x1, ca, P["n3.w"], P["n3.b"], drop=dsite("p_res", l, 3))
                 h = torch._addmm_activation(W["l1.b"], y3, W["l1.w"].t(), use_gelu=False)  # bias + ReLU epilogue
                 dropout_inplace_(h, dsite("p_res", l, 4))
-            mlp = torch.addmm(W["l2.b"], h, W["l2.w"].t())
+            mlp = linear_fwd(h, W["l2.w"], P["l2.b"], W["l2.b"])
             saved += [x, mean1, rstd1, y1, q_rot, k_rot, v, o, o32, lse,
                       x1, mean2, rstd2, y2, q2_rot, k2_rot, v2, o2, o2_32, lse2,
                       x2, mean3, rstd3, y3, h, rs if rs is not None else lse2[:0]]
@@ -698,7 +764,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             else:   # ReLU / hidden-dropout backward fused into the GEMM; the bias gradient joins the weight gradient (side stream)
                 dh = mlp_dh(dm, W["l2.w"], h, relu_scale, dbias=gv[ix["l1.b"]])     # + bias gradient of linear1 (column sums of dh)
                 acc_w(ix["l1.w"], dh.t(), y3)
-            dy3 = torch.mm(dh, W["l1.w"])
+            dy3 = linear_dgrad(dh, W["l1.w"])
             fold = mt["fold"]
             g_bo = torch.zeros(d, dtype=F32, device=dev) if fold else gv[ix["ca.o.b"]]    # colsum(dca), needed on its own when folded
             g, dca = ln_bwd(dy3, x2, mean3, rstd3, P["n3.w"], g, gv[ix["n3.w"]], gv[ix["n3.b"]], dbias=g_bo,
@@ -706,7 +772,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             # ---- cross attention backward
             if not fold:
                 acc_w(ix["ca.o.w"], dca.t(), o2.view(r, d))
-                do2 = torch.mm(dca, W["ca.o.w"])
+                do2 = linear_dgrad(dca, W["ca.o.w"])
             # conjugate RoPE and the q / k / v bias gradients (column sums) are fused into the gradient epilogues.
             # Only dQ is on the path of the residual-stream gradient: the key-side kernels (dV, dK) and everything
             # they feed (weight gradients, memory-bank gradients) go to the side stream.
@@ -718,7 +784,8 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                 if fold:
                     # ca = out64 (Wo Wv)^T + (Wo bv + bo):  G = d/d(Wo Wv) = dca^T out64, g = d/d(Wo bv + bo) = colsum(dca);
                     # dWo = G Wv^T + g bv^T, dWv = Wo^T G, dbv = Wo^T g, dbo = g -- four [256 x 64]-sized fp32 products
-                    do64 = torch.mm(dca, o2).view(b, n, 64)                 # o2 slot = folded weight [256, 64]
+                    do64, delta = linear_dgrad_dot(dca, o2, o64_32)             # o2 slot = folded weight [256, 64]
+                    do64, delta = do64.view(b, n, 64), delta.view(b, n)
                     ca_drop = rs.numel() > 0
                     # with dropout the value bias entered as rowsum (x) Wo bv: its gradients use g_rs = dca^T rowsum
                     # instead of g = colsum(dca), and the per-query constant c = dca . (Wo bv) goes into dP and Delta
@@ -743,8 +810,8 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                 else:
                     dp_bias = None
                     acc_w(ix["ca.v.w"], do2.t(), o64.view(r, 64), gv[ix["ca.v.b"]])
-                    do64 = torch.mm(do2, W["ca.v.w"]).view(b, n, 64)
-                delta = (do64.float() * o64_32).sum(-1)
+                    do64, delta = linear_dgrad_dot(do2, W["ca.v.w"], o64_32)
+                    do64, delta = do64.view(b, n, 64), delta.view(b, n)
                 if dp_bias is not None:
                     delta = torch.addcmul(delta, dp_bias, rs)
                 kw = dict(table=table, n_rope_k=n_rope_k, grad_dtype=BF16, dp_bias=dp_bias, drop=dsite("p_ca", l, 1))
@@ -796,7 +863,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                 side.run(key_side, *args[:3], o2_32, do2, lse2, delta)
                 dq2, _, _ = attn_bwd(*args, parts=8, dbias=(gv[ix["ca.q.b"]] if (EPILOGUE_BIAS and not wb_q) else None, None, None), **kw)
             dq2 = dq2.view(r, d)
-            dy2 = torch.mm(dq2, W["ca.q.w"])
+            dy2 = linear_dgrad(dq2, W["ca.q.w"])
             acc_w(ix["ca.q.w"], dq2.t(), y2, gv[ix["ca.q.b"]] if wb_q else None)
             if not EPILOGUE_BIAS and not wb_q:
                 side.run(lambda dq2=dq2, gb=gv[ix["ca.q.b"]]: bias_grad_(gb, dq2), dq2)
@@ -804,7 +871,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                             drop=dsite("p_res", l, 2))
             # ---- self attention backward
             acc_w(ix["sa.o.w"], dsa.t(), o.view(r, d))
-            do = torch.mm(dsa, W["sa.o.w"])
+            do = linear_dgrad(dsa, W["sa.o.w"])
             dqkv = torch.empty((b, n, 3 * d), dtype=BF16, device=dev)   # [dq | dk | dv], written in place by the kernels
             qkv_w = [masters[ix[k]] for k in ("sa.q.w", "sa.k.w", "sa.v.w")]
             gw = bucket.span(qkv_w, (3 * d, d)) if direct else None
@@ -834,7 +901,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             else:
                 dw = _mm32(dqkv.t(), y1)                     # [768, 256] = d(Wq | Wk | Wv) in one GEMM
                 grads[ix["sa.q.w"]], grads[ix["sa.k.w"]], grads[ix["sa.v.w"]] = dw[:d], dw[d:2 * d], dw[2 * d:]
-            dy1 = torch.mm(dqkv, wqkv_all[l])            # stacked [768, 256] weights: contraction over 768, fp32 accumulation
+            dy1 = linear_dgrad(dqkv, wqkv_all[l])            # stacked [768, 256] weights: contraction over 768, fp32 accumulation
             if l > 0:
                 g, g16 = ln_bwd(dy1, x0, mean1, rstd1, P["n1.w"], g, gv[ix["n1.w"]], gv[ix["n1.b"]],
                                 dbias=gv[base - _NPL + _LAYER_KEYS.index("l2.b")], drop=dsite("p_res", l - 1, 5))

@@ -18,7 +18,7 @@ for k, (n, us) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
 grp = collections.defaultdict(float)
 for k, (n, us) in tot.items():
     g = ("cuBLAS / cutlass / ATen" if (k.startswith("nvjet") or "cublas" in k.lower() or "cutlass" in k.lower() or k.startswith("at::") or "gemv" in k.lower() or k.startswith("std::") or "internal::" in k)
-         else ("own tcgen05 attention" if k.startswith("attn::") else ("own tcgen05 GEMM (ln_proj, mlp_dh)" if k.startswith(("lnproj::", "mlp::", "proj::")) else "own HBM-bound kernels")))
+         else ("own tcgen05 attention" if k.startswith("attn::") else ("own tcgen05 GEMM (ln_proj, mlp_dh, wgrad, gemm)" if k.startswith(("lnproj::", "mlp::", "proj::", "wgrad::", "gemm::")) else "own HBM-bound kernels")))
     grp[g] += us
 print("# groups:")
 for g, us in sorted(grp.items(), key=lambda kv: -kv[1]): print(f"#   {g:40s} {us/total*100:6.2f}%")

@@ -355,8 +355,20 @@ def test_grad_bucket_direct_accumulation_and_graph_replay(dev):
             assert rel_l2(a, c) < 1e-6, "graph replay / mirror changed the forward"
         for a, c in zip(pos_grads, ref_pos_grads):
             assert rel_l2(a, c) < 1e-5
+        ref_grads = {name: pr.grad for name, pr in ref_model.named_parameters()}
         for (name, pr), pm in zip(ref_model.named_parameters(), model.parameters()):
             assert pm.grad.data_ptr() >= bucket.flat.data_ptr(), name          # still a view of the bucket
+            # the self-attention q / k / v bias gradients of the direct path are column sums of the bf16 dq | dk | dv (extra
+            # accumulator columns of the stacked weight-gradient GEMM); the autograd path sums the fp32 accumulators in the
+            # attention epilogues -- the two differ by the bf16 rounding of the summands, everything else is the same arithmetic
+            if "self_attn" in name and name.endswith("_proj.bias") and "out_proj" not in name:
+                # (the k bias gradient is identically 0 in exact arithmetic -- rows of dS sum to 0 -- so it is pure rounding noise:
+                # measure all three against the layer's largest q / k / v bias gradient)
+                scale = max(float(ref_grads[name.replace(nm, alt)].norm()) for nm in ("q_proj", "k_proj", "v_proj") if nm in name
+                            for alt in ("q_proj", "k_proj", "v_proj"))
+                err = float((pm.grad - pr.grad).norm()) / scale
+                assert err < 5e-3, (step, name, err)
+                continue
             assert rel_l2(pm.grad, pr.grad) < 2e-5, (step, name, rel_l2(pm.grad, pr.grad))
         with torch.no_grad():        # same in-place update on both models
             for pr, pm in zip(ref_model.parameters(), model.parameters()):
@@ -643,6 +655,57 @@ def test_wgrad_kernel(dev, r, mo, no):
         assert rel_l2(c, want) < 2e-5, rel_l2(c, want)
         want_b = db0.double() + a.double().sum(0)
         assert rel_l2(db, want_b) < 2e-5, rel_l2(db, want_b)
+
+
+@pytest.mark.parametrize("r,k,no,nn", [(200, 256, 256, True), (32256, 256, 256, True), (1000, 768, 256, True), (3000, 2048, 256, True),
+                                       (2500, 2048, 256, False), (40000, 256, 64, True), (33, 64, 256, False), (700, 256, 64, False),
+                                       (19000, 64, 256, False)])
+def test_gemm_kernel(dev, r, k, no, nn):
+    """sam2b200_gemm (resident-CTA SS-mode tcgen05 GEMM, both weight layouts, fp32 bias) against an fp64 GEMM on the same bf16
+    operands: ragged row counts (TMA clipping), more tiles than SMs (accumulator / ring phases across tiles), strided operands,
+    canary rows behind the output."""
+    from sam2_video_training_b200 import fused_stack as fs
+    g = torch.Generator(device="cuda").manual_seed(r + k + no)
+    a_wide = torch.randn(r, k + 64, device=dev, generator=g).to(torch.bfloat16)
+    a = a_wide[:, 64:]
+    w = (torch.randn((k, no) if nn else (no, k), device=dev, generator=g) / k ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(no, device=dev, generator=g) if not nn else None
+    out = fs.gemm(a, w, nn=nn, bias=bias)
+    torch.cuda.synchronize()
+    want = a.double() @ (w.double() if nn else w.double().t())
+    if bias is not None:
+        want = want + bias.double()
+    assert out.shape == (r, no) and out.dtype == torch.bfloat16
+    assert rel_l2(out, want) < 3e-3, rel_l2(out, want)
+    assert (out.double() - want).abs().max() < 0.05 * want.abs().max()
+    if nn and no == 64:      # row dot products with an fp32 companion from the epilogue (Delta of the raw-memory attention backward)
+        rows32 = torch.randn(r, 64, device=dev, generator=g)
+        out2, dot = fs.gemm(a, w, nn=True, dot_rows=rows32)
+        torch.cuda.synchronize()
+        assert torch.equal(out2, out)
+        want_dot = (out.double() * rows32.double()).sum(-1)
+        assert rel_l2(dot, want_dot) < 1e-5, rel_l2(dot, want_dot)
+
+
+@pytest.mark.parametrize("b,length,n_rope,grid", [(2, 136, 128, 8), (3, 100, 0, 8), (5, 4060 // 5, 576, 24)])
+def test_gemm_kernel_memory_key_projection_with_rope(dev, b, length, n_rope, grid):
+    """sam2b200_gemm as the memory-key projection (transformer.py:278, K = 64) with bias and the axial rotation on the fp32
+    accumulator; object-pointer rows (position >= n_rope) stay un-rotated (transformer.py:296-302); keys tile the table."""
+    from sam2_video_training_b200 import fused_stack as fs
+    from sam2_video_training_b200.modeling.position_encoding import compute_axial_cis
+    g = torch.Generator(device="cuda").manual_seed(length)
+    period = grid * grid
+    table = compute_axial_cis(dim=256, end_x=grid, end_y=grid).to(dev)
+    x = torch.randn(b * length, 64, device=dev, generator=g).to(torch.bfloat16)
+    w = (torch.randn(256, 64, device=dev, generator=g) / 8).to(torch.bfloat16)
+    bias = torch.randn(256, device=dev, generator=g) * 0.1
+    out = fs.gemm(x, w, bias=bias, table=table if n_rope else None, rows_per_item=length, n_rope_rows=n_rope)
+    ref = (x.float() @ w.float().t() + bias).view(b, length, 256).cpu()
+    cos, sin = ao.axial_rope_table(period)
+    if n_rope:
+        rot = ao.apply_axial_rope(ref[:, :n_rope], cos, sin)
+        ref = torch.cat([rot, ref[:, n_rope:]], dim=1)
+    assert rel_l2(out.view(b, length, 256), ref) < 4e-3, rel_l2(out.view(b, length, 256), ref)
 
 
 @pytest.mark.parametrize("rows", [128, 700, 4096])

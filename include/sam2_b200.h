@@ -280,6 +280,14 @@ int sam2b200_wgrad(float* c, long long ldc, const void* a, long long lda, const 
 int sam2b200_gemm(void* c, long long ldc, const void* a, long long lda, const void* b, long long ldb, int b_layout, long long R, int K,
                   int No, const float* bias, const float* table, int rows_per_item, int n_rope_rows, int period, const float* dot_rows,
                   float* dot_out, cudaStream_t stream);
+/* The same kernel with the epilogues of the pre-norm block heads (behind the stand-alone LayerNorm pass sam2b200_ln_fwd): C[R, Nout],
+ * Nout = 64 or a multiple of 256 up to 2048, split over n_out = Nout / out_width <= 3 outputs [R, out_width] (q | k | v); the leading
+ * rope_cols columns (multiple of 256) rotated as above (transformer.py:296-302); relu != 0: max(., 0) on the biased accumulator, then
+ * inverted dropout (drop_p, element index row * Nout + column) -- linear1 + activation + dropout of memory_attention.py:95-97. */
+int sam2b200_gemm_ex(void* out0, void* out1, void* out2, int out_width, long long ldc, const void* a, long long lda, const void* b,
+                     long long ldb, int b_layout, long long R, int K, int Nout, const float* bias, int rope_cols, const float* table,
+                     int rows_per_item, int n_rope_rows, int period, int relu, float drop_p, const unsigned long long* drop_seed,
+                     unsigned drop_site, const float* dot_rows, float* dot_out, cudaStream_t stream);
 
 /* ---- LayerNorm + projection (+ RoPE | ReLU) in one kernel (csrc/lnproj.cu) ------------------------------------------
  * The head of every pre-norm block of MemoryAttentionLayer (sam2_video/model/modeling/memory_attention.py:58-64, 66-81,

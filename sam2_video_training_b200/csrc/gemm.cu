@@ -1,7 +1,11 @@
 // Dense GEMMs around the attention core of MemoryAttentionLayer that have no LayerNorm in front of them (those are
 // csrc/lnproj.cu) and no ReLU mask behind them (csrc/mlp.cu):
 //
-//     C[R, BN] (bf16) = epi( A[R, K] (bf16) . B  + bias )            BN = 256 | 64,  K a multiple of 64
+//     C[R, Nout] (bf16) = epi( A[R, K] (bf16) . B  + bias )          Nout = 64 | 256 x (1..8),  K a multiple of 64
+//
+// and, behind the stand-alone LayerNorm pass (glue.cu ln_fwd), the projections of the pre-norm block heads with their epilogues:
+// q|k|v / q with bias + axial RoPE on the fp32 accumulator (transformer.py:277-302), linear1 with bias + ReLU (+ hidden dropout)
+// (memory_attention.py:95-97) -- C split over up to three [R, out_width] outputs.
 //
 //   B layout 0 ("NT"): B = W[BN, K] row-major, C = A W^T  -- forward projections: linear2 (memory_attention.py:97-98, K = 2048) and
 //                      the memory-key projection k_proj (transformer.py:278, K = 64) with the axial rotation of
@@ -18,9 +22,11 @@
 // per warp) overlaps the MMAs of tile i + 1.  HBM-bound at every shape of the stack: algorithmic bytes = 2 (R K + K BN + R BN).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 #include "abi_common.cuh"
+#include "dropout.cuh"
 #include "sm100.cuh"
 #include "tma_desc.cuh"
 
@@ -45,15 +51,22 @@ struct Shared {
   uint64_t empty[kStages];
   uint64_t acc_full[2];
   uint64_t acc_free[2];
-  float bias[BN];
+  float bias[BN];                                            // the current column block's bias slice
   uint32_t tmem_base;
 };
 
 struct Params {
   int rows;                 // R
-  int n_tiles;              // ceil(R / 128)
+  int n_tiles;              // ceil(R / 128) * n_col_blocks; tile t = (row tile t / n_col_blocks, column block t % n_col_blocks)
+  int n_col_blocks;         // Nout / BN
+  int blocks_per_out;       // output tensor of column block cb = cb / blocks_per_out, its first column (cb % blocks_per_out) * BN
   int ksteps;               // K / 64
-  const float* bias;        // [BN] fp32 or nullptr
+  int nout;                 // Nout (dropout element index = row * Nout + column)
+  int rope_blocks;          // leading column blocks (of 256) that are rotated
+  int rope_w;               // sqrt(period) if the table is axial over a square grid (row = x part | y part), else 0
+  int relu;                 // max(., 0) on the biased accumulator, then drop_out
+  sam2b200::Dropout drop_out;
+  const float* bias;        // [Nout] fp32 or nullptr
   const float2* table;      // RoPE: [period, 128] (cos, sin) or nullptr
   int rows_per_item;        // row r is position r % rows_per_item of its batch item
   int n_rope_rows;          // positions [0, n_rope_rows) are rotated
@@ -66,8 +79,8 @@ template <int BN, int B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a,      // A [R, K]: box 64 x 128
             const __grid_constant__ CUtensorMap map_b,      // NT: W [BN, K], box 64 x BN;  NN: W [K, BN], box 64 x 64
-            const __grid_constant__ CUtensorMap map_c,      // C [R, BN]: box 64 x 32 (store)
-            const Params p) {
+            const __grid_constant__ CUtensorMap map_c0,     // outputs [R, out_width]: box 64 x 32 (store)
+            const __grid_constant__ CUtensorMap map_c1, const __grid_constant__ CUtensorMap map_c2, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   Shared<BN>& sh = *reinterpret_cast<Shared<BN>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -80,32 +93,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a,      // A [R, K]: box 64 
     fence_barrier_init();
   }
   if (warp == 8 && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_b); }
-  if (warp == 0 && lane == 0) prefetch_tmap(&map_c);
+  if (warp == 0 && lane == 0) { prefetch_tmap(&map_c0); prefetch_tmap(&map_c1); prefetch_tmap(&map_c2); }
   if (warp == 9) { tmem_alloc(&sh.tmem_base, kTmemCols); tmem_relinquish(); }
-  if (threadIdx.x < BN) sh.bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh.tmem_base;
   const int ksteps = p.ksteps;
+  const int ncb = p.n_col_blocks;
 
   if (warp == 8) {
     // ===================== TMA producer: one (A, B) k-slice per ring slot, running across tile boundaries =====================
     const bool leader = elect_one();
     uint32_t slot = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const int row_tile = tile / ncb, cb = tile - row_tile * ncb;
       for (int ks = 0; ks < ksteps; ++ks, ++slot) {
         const int s = slot % kStages;
         mbar_wait(&sh.empty[s], ((slot / kStages) & 1) ^ 1);
         if (leader) {
           mbar_arrive_expect_tx(&sh.full[s], kATileBytes + kBBytes);
-          tma_load_3d(&sh.a_tiles[s][0], &map_a, &sh.full[s], ks * kBlockK, tile * kBlockM, 0);
+          tma_load_3d(&sh.a_tiles[s][0], &map_a, &sh.full[s], ks * kBlockK, row_tile * kBlockM, 0);
           if (B_MN) {
 #pragma unroll
             for (int c = 0; c < BN / 64; ++c)
-              tma_load_3d(&sh.b_tiles[s][c * 8192], &map_b, &sh.full[s], c * 64, ks * kBlockK, 0);
+              tma_load_3d(&sh.b_tiles[s][c * 8192], &map_b, &sh.full[s], cb * BN + c * 64, ks * kBlockK, 0);
           } else {
-            tma_load_3d(&sh.b_tiles[s][0], &map_b, &sh.full[s], ks * kBlockK, 0, 0);
+            tma_load_3d(&sh.b_tiles[s][0], &map_b, &sh.full[s], ks * kBlockK, cb * BN, 0);
           }
         }
         __syncwarp();
@@ -148,14 +162,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a,      // A [R, K]: box 64 
     const uint32_t lane_addr = tmem + (uint32_t(quarter * 32) << 16);
     const uint32_t srow = smem_u32(&sh.stage[warp][0]) + lane * 128;
     constexpr int kChunks = BN / 64;
+    const bool drop_on = p.drop_out.seed != nullptr;
+    const uint32_t dkey = drop_on ? sam2b200::dropout_key(*p.drop_out.seed, p.drop_out.site) : 0u;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int ab = it & 1;
-      const int row0 = tile * kBlockM + quarter * 32;
-      const float2* trow = nullptr;
-      if (BN == 256 && p.table != nullptr) {
+      const int row_tile = tile / ncb, cb = tile - row_tile * ncb;
+      const int row0 = row_tile * kBlockM + quarter * 32;
+      const int which = cb / p.blocks_per_out;
+      const int ocol0 = (cb - which * p.blocks_per_out) * BN;         // first column of this block inside its output tensor
+      const CUtensorMap* mo = which == 0 ? &map_c0 : (which == 1 ? &map_c1 : &map_c2);
+      // this column block's bias slice -> shared memory (broadcast reads below); with one column block it is loaded once
+      if (it == 0 || ncb > 1) {
+        if (it > 0) asm volatile("bar.sync 5, 256;" ::: "memory");      // every warp has finished reading the previous slice
+        if ((int)threadIdx.x < BN) sh.bias[threadIdx.x] = p.bias ? __ldg(p.bias + cb * BN + threadIdx.x) : 0.f;
+        asm volatile("bar.sync 5, 256;" ::: "memory");
+      }
+      const float2* trow_x = nullptr;             // (cos, sin) rows of this thread's position: columns [0, 128) | [128, 256) of the head
+      const float2* trow_y = nullptr;
+      if (BN == 256 && cb < p.rope_blocks) {
         const int pos = (int)(((long long)row0 + lane) % p.rows_per_item);
-        if (pos < p.n_rope_rows) trow = p.table + (long long)(pos % p.period) * 128;
+        if (pos < p.n_rope_rows) {
+          const int tpos = pos % p.period;
+          // axial table over a square grid: the first 64 pairs depend on x = pos % w only, the last 64 on y = pos / w only --
+          // a tile touches w + 128 / w distinct half rows instead of 128 (L1 resident)
+          trow_x = p.table + (long long)(p.rope_w > 0 ? tpos % p.rope_w : tpos) * 128;
+          trow_y = p.table + (long long)(p.rope_w > 0 ? tpos - tpos % p.rope_w : tpos) * 128;
+        }
       }
       mbar_wait(&sh.acc_full[ab], (it >> 1) & 1);
       tc_fence_after();
@@ -165,12 +198,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a,      // A [R, K]: box 64 
         if (lane == 0) tma_store_wait_read();
         __syncwarp();
         float dot = 0.f;
+        const float2* trow = (c < 2) ? trow_x : trow_y;
 #pragma unroll
         for (int sb = 0; sb < 2; ++sb) {          // two sub-blocks of 32 columns
           uint32_t acc[32];
           SAM2B200_TMEM_LD32(lane_addr + ab * BN + c * 64 + sb * 32, acc);
           float4 cs[16];
-          if (BN == 256 && trow != nullptr) {     // the (cos, sin) pairs of this row's 32 columns (L2-resident table), under the TMEM load
+          if (BN == 256 && trow != nullptr) {     // the (cos, sin) pairs of this row's 32 columns, fetched under the TMEM load
             const float4* src = reinterpret_cast<const float4*>(trow + c * 32 + sb * 16);
 #pragma unroll
             for (int i = 0; i < 8; ++i) cs[i] = __ldg(src + i);
@@ -186,6 +220,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a,      // A [R, K]: box 64 
               const float r0 = v[4 * i] * cs[i].x - v[4 * i + 1] * cs[i].y, i0 = v[4 * i] * cs[i].y + v[4 * i + 1] * cs[i].x;
               const float r1 = v[4 * i + 2] * cs[i].z - v[4 * i + 3] * cs[i].w, i1 = v[4 * i + 2] * cs[i].w + v[4 * i + 3] * cs[i].z;
               v[4 * i] = r0; v[4 * i + 1] = i0; v[4 * i + 2] = r1; v[4 * i + 3] = i1;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            if (drop_on) {
+              const uint32_t idx = (uint32_t)(((long long)row0 + lane) * p.nout + cb * BN + c * 64 + sb * 32);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = sam2b200::dropout_keep(dkey, idx + i, p.drop_out.thresh) ? v[i] * p.drop_out.inv_keep : 0.f;
             }
           }
           uint32_t pk[16];
@@ -209,7 +252,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a,      // A [R, K]: box 64 
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          if (row0 < p.rows) tma_store_3d(&map_c, &sh.stage[warp][0], c * 64, row0, 0);   // rows beyond R are clipped by the TMA unit
+          if (row0 < p.rows) tma_store_3d(mo, &sh.stage[warp][0], ocol0 + c * 64, row0, 0);   // rows beyond R are clipped by the TMA unit
           tma_store_commit();
         }
       }
@@ -258,46 +301,70 @@ int sm_count() {
 }
 
 template <int BN, int B_MN>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const gemm::Params& p, cudaStream_t stream) {
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap* mc, const gemm::Params& p, cudaStream_t stream) {
   const size_t smem = sizeof(gemm::Shared<BN>) + 1024;
+  static_assert(sizeof(gemm::Shared<BN>) + 1024 <= 227 * 1024, "shared memory of one CTA");
   cudaError_t e = cudaFuncSetAttribute(gemm::gemm_kernel<BN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return sam2b200::fail(SAM2B200_ERR_CUDA, cudaGetErrorString(e));
   const unsigned grid = (unsigned)(p.n_tiles < sm_count() ? p.n_tiles : sm_count());
-  gemm::gemm_kernel<BN, B_MN><<<grid, gemm::kThreads, smem, stream>>>(ma, mb, mc, p);
+  gemm::gemm_kernel<BN, B_MN><<<grid, gemm::kThreads, smem, stream>>>(ma, mb, mc[0], mc[1], mc[2], p);
   return sam2b200::check_launch("gemm");
 }
+
+bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
 
 extern "C" {
 
-// c[R, No] (bf16, row stride ldc) = a[R, K] (bf16, row stride lda) . B (+ bias) (rotated), No = 256 or 64, K % 64 == 0.
-// b_layout 0: b = W[No, K] (row stride ldb), c = a W^T;  b_layout 1: b = W[K, No] (row stride ldb), c = a W.
-// bias: [No] fp32 or NULL.  table != NULL (No = 256, b_layout 0): rows whose position (row % rows_per_item) is < n_rope_rows are
-// rotated with table [period, 128] (cos, sin), table row = position % period -- sam2b200_proj_rope's rule.
-// dot_rows / dot_out (No = 64, both or neither): dot_out[r] = sum_c bf16(c[r, c]) * dot_rows[r, c] with dot_rows [R, 64] fp32 contiguous.
+// C[R, Nout] = epi(a[R, K] . B + bias), C split over n_out = Nout / out_width <= 3 bf16 tensors [R, out_width] (row stride ldc):
+// Nout = 64 (one output) or a multiple of 256 up to 2048, out_width a multiple of 256 (or 64), K % 64 == 0.
+// b_layout 0: b = W[Nout, K] (row stride ldb), C = a W^T;  b_layout 1: b = W[K, Nout] (row stride ldb), C = a W.  bias: [Nout] fp32 | NULL.
+// rope_cols (a multiple of 256, table != NULL): the leading output columns are rotated with table [period, 128] (cos, sin) -- pair
+// index = (column mod 256) / 2 -- for rows whose position (row % rows_per_item) is < n_rope_rows, table row = position % period.
+// relu != 0: max(., 0) on the biased accumulator, then (drop_p > 0) inverted dropout with element index row * Nout + column.
+// dot_rows / dot_out (Nout = 64, both or neither): dot_out[r] = sum_c bf16(C[r, c]) * dot_rows[r, c], dot_rows [R, 64] fp32 contiguous.
+int sam2b200_gemm_ex(void* out0, void* out1, void* out2, int out_width, long long ldc, const void* a, long long lda, const void* b,
+                     long long ldb, int b_layout, long long R, int K, int Nout, const float* bias, int rope_cols, const float* table,
+                     int rows_per_item, int n_rope_rows, int period, int relu, float drop_p, const unsigned long long* drop_seed,
+                     unsigned drop_site, const float* dot_rows, float* dot_out, cudaStream_t stream) {
+  const int bn = Nout == 64 ? 64 : 256;
+  const int n_out = out_width > 0 ? Nout / out_width : 0;
+  if (!out0 || !a || !b || R <= 0 || R > 0x7fffffffLL - 256 || K <= 0 || (K % 64) || Nout <= 0 || (Nout % bn) || Nout > 2048 ||
+      out_width <= 0 || (out_width % bn) || n_out * out_width != Nout || n_out > 3 || (n_out > 1 && !out1) || (n_out > 2 && !out2) ||
+      (b_layout != 0 && b_layout != 1) || lda < K || ldc < out_width || ldb < (b_layout ? Nout : K) || ((lda | ldb | ldc) & 7) ||
+      rope_cols < 0 || (rope_cols % 256) || rope_cols > Nout || (rope_cols > 0 && (bn != 256 || !table || rows_per_item <= 0 || n_rope_rows < 0 || period <= 0)) ||
+      drop_p < 0.f || drop_p >= 1.f || (drop_p > 0.f && drop_seed && R * (long long)Nout >= (1LL << 32)) ||
+      ((dot_rows != nullptr) != (dot_out != nullptr)) || (dot_rows && Nout != 64) ||
+      !al16(out0) || !al16(out1) || !al16(out2) || !al16(a) || !al16(b) || !al16(bias) || !al16(table) || !al16(dot_rows))
+    return sam2b200::fail(SAM2B200_ERR_INVALID, "gemm: bad arguments (Nout = 64 | k x 256 <= 2048, K % 64 == 0, 16-byte aligned tensors, strides % 8 == 0)");
+  CUtensorMap ma, mb, mc[3];
+  int rc;
+  if ((rc = make_map(&ma, a, R, K, lda, 128))) return rc;
+  if (b_layout == 0) { if ((rc = make_map(&mb, b, Nout, K, ldb, bn))) return rc; }
+  else               { if ((rc = make_map(&mb, b, K, Nout, ldb, 64))) return rc; }
+  void* outs[3] = {out0, out1 ? out1 : out0, out2 ? out2 : out0};
+  for (int i = 0; i < 3; ++i)
+    if ((rc = make_map(&mc[i], outs[i], R, out_width, ldc, 32))) return rc;
+  gemm::Params p{};
+  p.rows = (int)R; p.n_col_blocks = Nout / bn; p.n_tiles = (int)((R + gemm::kBlockM - 1) / gemm::kBlockM) * p.n_col_blocks;
+  p.blocks_per_out = out_width / bn; p.ksteps = K / gemm::kBlockK; p.nout = Nout; p.bias = bias;
+  p.rope_blocks = rope_cols / 256; p.table = reinterpret_cast<const float2*>(table); p.rows_per_item = rows_per_item > 0 ? rows_per_item : 1;
+  p.n_rope_rows = n_rope_rows; p.period = period > 0 ? period : 1;
+  if (rope_cols > 0) { int w = (int)(sqrt((double)p.period) + 0.5); p.rope_w = (w * w == p.period) ? w : 0; }
+  p.relu = relu; p.drop_out = sam2b200::make_dropout(drop_seed, drop_site, drop_p);
+  p.dot_rows = dot_rows; p.dot_out = dot_out;
+  if (bn == 256) return b_layout ? launch<256, 1>(ma, mb, mc, p, stream) : launch<256, 0>(ma, mb, mc, p, stream);
+  return b_layout ? launch<64, 1>(ma, mb, mc, p, stream) : launch<64, 0>(ma, mb, mc, p, stream);
+}
+
+// One output of width No = 256 | 64: c[R, No] = a . B (+ bias); table != NULL rotates the whole output (the memory-key projection).
 int sam2b200_gemm(void* c, long long ldc, const void* a, long long lda, const void* b, long long ldb, int b_layout, long long R, int K,
                   int No, const float* bias, const float* table, int rows_per_item, int n_rope_rows, int period, const float* dot_rows, float* dot_out,
                   cudaStream_t stream) {
-  if (!c || !a || !b || R <= 0 || R > 0x7fffffffLL - 256 || K <= 0 || (K % 64) || (No != 256 && No != 64) || (b_layout != 0 && b_layout != 1) ||
-      lda < K || ldc < No || ldb < (b_layout ? No : K) || ((lda | ldb | ldc) & 7) ||
-      (table && (No != 256 || rows_per_item <= 0 || n_rope_rows < 0 || period <= 0)) || ((dot_rows != nullptr) != (dot_out != nullptr)) ||
-      (dot_rows && No != 64) || (reinterpret_cast<uintptr_t>(dot_rows) & 15) ||
-      ((reinterpret_cast<uintptr_t>(c) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) ||
-      ((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(table)) & 15))
-    return sam2b200::fail(SAM2B200_ERR_INVALID, "gemm: bad arguments (No = 256 | 64, K % 64 == 0, 16-byte aligned tensors, strides % 8 == 0)");
-  CUtensorMap ma, mb, mc;
-  int rc;
-  if ((rc = make_map(&ma, a, R, K, lda, 128))) return rc;
-  if (b_layout == 0) { if ((rc = make_map(&mb, b, No, K, ldb, No))) return rc; }
-  else               { if ((rc = make_map(&mb, b, K, No, ldb, 64))) return rc; }
-  if ((rc = make_map(&mc, c, R, No, ldc, 32))) return rc;
-  gemm::Params p{};
-  p.rows = (int)R; p.n_tiles = (int)((R + gemm::kBlockM - 1) / gemm::kBlockM); p.ksteps = K / gemm::kBlockK; p.bias = bias;
-  p.table = reinterpret_cast<const float2*>(table); p.rows_per_item = rows_per_item > 0 ? rows_per_item : 1;
-  p.n_rope_rows = n_rope_rows; p.period = period > 0 ? period : 1; p.dot_rows = dot_rows; p.dot_out = dot_out;
-  if (No == 256) return b_layout ? launch<256, 1>(ma, mb, mc, p, stream) : launch<256, 0>(ma, mb, mc, p, stream);
-  return b_layout ? launch<64, 1>(ma, mb, mc, p, stream) : launch<64, 0>(ma, mb, mc, p, stream);
+  if (No != 256 && No != 64) return sam2b200::fail(SAM2B200_ERR_INVALID, "gemm: No must be 256 or 64");
+  return sam2b200_gemm_ex(c, nullptr, nullptr, No, ldc, a, lda, b, ldb, b_layout, R, K, No, bias, table ? No : 0, table, rows_per_item,
+                          n_rope_rows, period, 0, 0.f, nullptr, 0, dot_rows, dot_out, stream);
 }
 
 }  // extern "C"

@@ -156,6 +156,45 @@ def ln_proj(x, res, gamma, beta, w16, bias16, n_out, out_width=256, table=None, 
     return outs, y, x_new, mean, rstd
 
 
+def gemm_ex(a16, w16, n_out, out_width, nn=False, bias=None, table=None, rope_outs=0, rows_per_item=1, n_rope_rows=0, relu=False, drop_out=None):
+    """n_out bf16 tensors [R, out_width] = epi(a16 @ w16^T + bias) on sam2b200_gemm_ex (csrc/gemm.cu): w16 [n_out * out_width, K] (or
+    [K, n_out * out_width] with nn=True), bias fp32; the first rope_outs outputs (width 256) rotated with the axial `table`; relu:
+    max(., 0) then drop_out = (p, seed, site)."""
+    r, k = a16.shape
+    nout = n_out * out_width
+    assert a16.dtype == BF16 and w16.dtype == BF16 and a16.stride(1) == 1 and w16.stride(1) == 1
+    assert w16.shape == ((k, nout) if nn else (nout, k)), (tuple(a16.shape), tuple(w16.shape), nn)
+    assert bias is None or (bias.dtype == F32 and bias.shape == (nout,) and bias.is_contiguous())
+    outs = [torch.empty((r, out_width), dtype=BF16, device=a16.device) for _ in range(n_out)]
+    ptr = [o.data_ptr() for o in outs] + [None] * (3 - n_out)
+    rc = _lib.load().sam2b200_gemm_ex(ptr[0], ptr[1], ptr[2], int(out_width), int(out_width), a16.data_ptr(), a16.stride(0), w16.data_ptr(),
+                                      w16.stride(0), int(bool(nn)), r, k, nout, bias.data_ptr() if bias is not None else None,
+                                      256 * int(rope_outs), table.data_ptr() if table is not None else None, int(rows_per_item),
+                                      int(n_rope_rows), table.shape[0] if table is not None else 1, int(bool(relu)), *_drop(drop_out),
+                                      None, None, _stream(a16.device))
+    _lib.check(rc, "sam2b200_gemm_ex")
+    return outs
+
+
+def ln_then_proj(x, res, gamma, beta, w16, bias32, n_out, out_width=256, table=None, rope_outs=0, rows_per_item=1, n_rope_rows=0,
+                 relu=False, drop_res=None, drop_out=None, eps=1e-5):
+    """Head of a pre-norm block as TWO kernels: the HBM-bound LayerNorm pass (ln_fwd: x + dropout(res), LayerNorm, bf16 y, statistics)
+    and the resident-CTA GEMM with the bias / RoPE / ReLU (+ dropout) epilogue (gemm_ex).  Same results and return value as ln_proj;
+    measured faster than the one-kernel version, whose one-tile-per-CTA LayerNorm prologue and 64-column chunk loop leave the HBM
+    pipe half idle (profiles/r2_lnproj_vs_split.txt)."""
+    y, x_new, mean, rstd = ln_fwd(x, res, gamma, beta, eps=eps, drop=drop_res)
+    outs = gemm_ex(y, w16, n_out, out_width, bias=bias32, table=table, rope_outs=rope_outs, rows_per_item=rows_per_item,
+                   n_rope_rows=n_rope_rows, relu=relu, drop_out=drop_out)
+    return outs, y, x_new, mean, rstd
+
+
+def block_head(x, res, gamma, beta, w16, bias16, bias32, n_out, **kw):
+    """Pre-norm block head: ln_fwd + gemm_ex (default) or the one-kernel ln_proj (SAM2B200_LNPROJ_FUSED=1 / SAM2B200_NO_GEMM=1)."""
+    if LNPROJ_FUSED or NO_GEMM:
+        return ln_proj(x, res, gamma, beta, w16, bias16, n_out, **kw)
+    return ln_then_proj(x, res, gamma, beta, w16, bias32, n_out, **kw)
+
+
 def wgrad_(c32, a16, b16, dbias=None):
     """c32 [Mo, No] fp32 += a16[R, Mo]^T @ b16[R, No] in place (sam2b200_wgrad: split over R, tcgen05, partial tiles added with
     fp32 reductions).  Row strides may exceed the widths (column slices of wider buffers).  dbias (fp32 [Mo], optional) +=
@@ -329,6 +368,8 @@ def linear_dgrad(dy16, w16):
 
 
 NO_FUSED_OUT_PROJ = bool(os.environ.get("SAM2B200_NO_FUSED_OUT_PROJ"))   # A/B switch: out_proj as a separate cuBLAS addmm after the attention kernel
+# Heads of the pre-norm blocks: default = ln_fwd + sam2b200_gemm_ex (two kernels); SAM2B200_LNPROJ_FUSED=1 = the one-kernel sam2b200_ln_proj.
+LNPROJ_FUSED = bool(os.environ.get("SAM2B200_LNPROJ_FUSED"))
 NO_LNPROJ = bool(os.environ.get("SAM2B200_NO_LNPROJ"))     # A/B switch: ln_fwd + cuBLAS addmm + RoPE pass instead of sam2b200_ln_proj
 NO_MLP_KERNEL = bool(os.environ.get("SAM2B200_NO_MLP_KERNEL"))     # A/B switch: cuBLAS GEMM + separate ReLU-backward pass
 NO_SIDE_STREAM = bool(os.environ.get("SAM2B200_NO_SIDE_STREAM"))   # A/B switch: everything on one stream
@@ -425,6 +466,7 @@ class WeightMirror:
         self.wobv = [torch.empty(256, dtype=BF16, device=dev) for _ in range(nl)]
         # fp32 copies for the attention kernels' fused output projection (bias added on the fp32 accumulator)
         self.b_eff32 = [torch.empty(256, dtype=F32, device=dev) for _ in range(nl)]
+        self.qkv_bias32 = [torch.empty(768, dtype=F32, device=dev) for _ in range(nl)]    # stacked fp32 q|k|v bias (epilogue of gemm_ex)
         self.wobv32 = [torch.empty(256, dtype=F32, device=dev) for _ in range(nl)]
         self.versions = None
         self.device = dev
@@ -454,6 +496,8 @@ class WeightMirror:
             with torch.no_grad():
                 torch._foreach_copy_(self.views, [p.detach() for p in self.params])
                 for l in range(self.nl):
+                    for j, kb in enumerate(("sa.q.b", "sa.k.b", "sa.v.b")):
+                        self.qkv_bias32[l][256 * j:256 * (j + 1)].copy_(self.params[l * _NPL + _LAYER_KEYS.index(kb)].detach())
                     wo, bo, wv, bv = (self.params[l * _NPL + _LAYER_KEYS.index(k)].detach()
                                       for k in ("ca.o.w", "ca.o.b", "ca.v.w", "ca.v.b"))
                     if wv.shape != (256, 64):
@@ -581,9 +625,9 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             # ---- self attention (memory_attention.py:58-64)
             if not NO_LNPROJ:
                 # LayerNorm + q|k|v projection + bias + RoPE(q, k) in one kernel: no un-rotated q / k in HBM
-                (q_rot, k_rot, v), y1, x, mean1, rstd1 = ln_proj(
-                    x, res, P["n1.w"], P["n1.b"], mirror.qkv[l], mirror.qkv_bias[l], 3, table=table, rope_outs=2, rows_per_item=n,
-                    n_rope_rows=n, drop_res=dsite("p_res", l - 1, 5) if l > 0 else None)
+                (q_rot, k_rot, v), y1, x, mean1, rstd1 = block_head(
+                    x, res, P["n1.w"], P["n1.b"], mirror.qkv[l], mirror.qkv_bias[l], mirror.qkv_bias32[l], 3, table=table, rope_outs=2,
+                    rows_per_item=n, n_rope_rows=n, drop_res=dsite("p_res", l - 1, 5) if l > 0 else None)
                 q_rot, k_rot = q_rot.view(b, n, d), k_rot.view(b, n, d)
             else:
                 y1, x, mean1, rstd1 = ln_fwd(x, res, P["n1.w"], P["n1.b"], drop=dsite("p_res", l - 1, 5) if l > 0 else None)
@@ -607,8 +651,8 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                 sa = linear_fwd(o.view(r, d), W["sa.o.w"], P["sa.o.b"], W["sa.o.b"])
             # ---- cross attention to the memory bank (memory_attention.py:66-81)
             if not NO_LNPROJ:
-                (q2_rot,), y2, x1, mean2, rstd2 = ln_proj(x, sa, P["n2.w"], P["n2.b"], W["ca.q.w"], W["ca.q.b"], 1, table=table,
-                                                          rope_outs=1, rows_per_item=n, n_rope_rows=n, drop_res=dsite("p_res", l, 2))
+                (q2_rot,), y2, x1, mean2, rstd2 = block_head(x, sa, P["n2.w"], P["n2.b"], W["ca.q.w"], W["ca.q.b"], P["ca.q.b"], 1, table=table,
+                                                             rope_outs=1, rows_per_item=n, n_rope_rows=n, drop_res=dsite("p_res", l, 2))
                 q2_rot = q2_rot.view(b, n, d)
             else:
                 y2, x1, mean2, rstd2 = ln_fwd(x, sa, P["n2.w"], P["n2.b"], drop=dsite("p_res", l, 2))
@@ -651,8 +695,8 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                 ca = linear_fwd(o2.view(r, d), W["ca.o.w"], P["ca.o.b"], W["ca.o.b"])
             # ---- MLP (memory_attention.py:95-98)
             if not NO_LNPROJ:   # LayerNorm + linear1 + bias + ReLU (+ hidden dropout) in one kernel
-                (h,), y3, x2, mean3, rstd3 = ln_proj(x1, ca, P["n3.w"], P["n3.b"], W["l1.w"], W["l1.b"], 1, out_width=2048, relu=True,
-                                                     drop_res=dsite("p_res", l, 3), drop_out=dsite("p_res", l, 4))
+                (h,), y3, x2, mean3, rstd3 = block_head(x1, ca, P["n3.w"], P["n3.b"], W["l1.w"], W["l1.b"], P["l1.b"], 1, out_width=2048, relu=True,
+                                                        drop_res=dsite("p_res", l, 3), drop_out=dsite("p_res", l, 4))
             else:
                 y3, x2, mean3, rstd3 = ln_fwd(x1, ca, P["n3.w"], P["n3.b"], drop=dsite("p_res", l, 3))
                 h = torch._addmm_activation(W["l1.b"], y3, W["l1.w"].t(), use_gelu=False)  # bias + ReLU epilogue

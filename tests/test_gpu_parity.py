@@ -708,6 +708,50 @@ def test_gemm_kernel_memory_key_projection_with_rope(dev, b, length, n_rope, gri
     assert rel_l2(out.view(b, length, 256), ref) < 4e-3, rel_l2(out.view(b, length, 256), ref)
 
 
+@pytest.mark.parametrize("mode,b,length,drop", [("qkv", 3, 64, 0.0), ("q", 2, 144, 0.0), ("q", 1, 100, 0.0), ("mlp", 2, 200, 0.0),
+                                                ("mlp", 3, 70, 0.1), ("qkv", 56, 576, 0.0), ("mlp", 56, 576, 0.1)])
+def test_block_head_two_kernel_path_matches_fused_kernel_and_reference(dev, mode, b, length, drop):
+    """ln_fwd + sam2b200_gemm_ex (column blocks, three outputs, RoPE / ReLU + dropout epilogues) against fp32 torch on the same bf16
+    operands with the kernel's own dropout mask, and against the one-kernel sam2b200_ln_proj (same y / x_new / statistics bit for bit)."""
+    from sam2_video_training_b200 import fused_stack as fs
+    from sam2_video_training_b200.modeling.position_encoding import compute_axial_cis
+    g = torch.Generator(device="cuda").manual_seed(17)
+    r = b * length
+    grid = {64: 8, 144: 12, 100: 10, 576: 24}.get(length, 0)
+    table = compute_axial_cis(dim=256, end_x=grid, end_y=grid).to(dev) if grid else None
+    n_out, width, ropes, relu = {"qkv": (3, 256, 2, False), "q": (1, 256, 1, False), "mlp": (1, 2048, 0, True)}[mode]
+    nout = n_out * width
+    x = torch.randn(r, 256, device=dev, generator=g)
+    res = torch.randn(r, 256, device=dev, generator=g).to(torch.bfloat16)
+    gamma, beta = torch.rand(256, device=dev, generator=g) + 0.5, torch.randn(256, device=dev, generator=g) * 0.1
+    w = (torch.randn(nout, 256, device=dev, generator=g) / 16).to(torch.bfloat16)
+    bias = torch.randn(nout, device=dev, generator=g) * 0.1
+    seed = torch.full((1,), 4321, dtype=torch.int64, device=dev)
+    d_out = (drop, seed, 12) if drop > 0 else None
+    kw = dict(out_width=width, table=table if ropes else None, rope_outs=ropes, rows_per_item=length, n_rope_rows=length, relu=relu, drop_out=d_out)
+    outs, y, x_new, mean, rstd = fs.ln_then_proj(x, res, gamma, beta, w, bias, n_out, **kw)
+    outs_f, y_f, x_new_f, mean_f, rstd_f = fs.ln_proj(x, res, gamma, beta, w, bias.to(torch.bfloat16), n_out, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_f) and torch.equal(x_new, x_new_f) and rel_l2(mean, mean_f) < 1e-6 and rel_l2(rstd, rstd_f) < 1e-6
+    o = y.float() @ w.float().t() + bias
+    if ropes:
+        cos, sin = ao.axial_rope_table(grid * grid)
+        parts = []
+        for i in range(n_out):
+            blk = o[:, 256 * i:256 * (i + 1)].view(b, length, 256).cpu()
+            parts.append((ao.apply_axial_rope(blk, cos, sin) if i < ropes else blk).reshape(r, 256))
+    else:
+        if relu:
+            o = torch.relu(o)
+            if d_out is not None:
+                o = o * _keep_mask(dev, seed, 12, drop, r * nout).view(r, nout) / (1 - drop)
+        parts = [o[:, width * i:width * (i + 1)].cpu() for i in range(n_out)]
+    for got, got_f, want in zip(outs, outs_f, parts):
+        assert got.shape == want.shape and got.dtype == torch.bfloat16
+        assert rel_l2(got, want) < 4e-3, (mode, rel_l2(got, want))
+        assert rel_l2(got, got_f) < 4e-3, (mode, rel_l2(got, got_f))     # same operands; bias bf16 vs fp32, accumulation order
+
+
 @pytest.mark.parametrize("rows", [128, 700, 4096])
 def test_mlp_dh_kernel(dev, rows):
     """sam2b200_mlp_dh: dh = (dm @ W2) * (h > 0) * scale (tcgen05 GEMM, ReLU / hidden-dropout backward in the epilogue)

@@ -14,12 +14,17 @@
 //   B layout 1 ("NN"): B = W[K, BN] row-major, C = A W    -- input gradients dX = dY W of linear1 (K = 2048), of the stacked
 //                      q|k|v projection (K = 768), of out_proj / q_proj (K = 256) and of the folded Wo Wv (BN = 64).
 //
-// Blackwell mapping: RESIDENT CTAs (one per SM) walk the 128-row tiles of C; A and B k-slices of 64 arrive by TMA in a 4-stage
-// ring shared by consecutive tiles (the producer runs ahead into the next tile while the current one drains); both operands are
-// read from shared memory (SS-mode tcgen05.mma, M = 128, N = BN, K = 16 per instruction), the B tile K-major (NT) or MN-major
-// (NN) straight from the TMA boxes -- no transposed weight copy exists anywhere; two BN-column fp32 accumulators in tensor memory
-// alternate between tiles, so the epilogue of tile i (tcgen05.ld -> bias / rotation -> bf16 -> swizzled staging box -> TMA store
-// per warp) overlaps the MMAs of tile i + 1.  HBM-bound at every shape of the stack: algorithmic bytes = 2 (R K + K BN + R BN).
+// Blackwell mapping: RESIDENT CTAs (one per SM) walk 128-row x BN-column tiles of C (BN = 256; 128 for rotated outputs -- the x and
+// y halves of a head; 64); A k-slices of 64 arrive by TMA in a 4-stage ring shared by consecutive tiles (the producer runs ahead into
+// the next tile while the current one drains).  K <= 256: the CTA keeps ONE column block whose weight slices are loaded once and stay
+// in shared memory (a first version re-streamed them per tile and was bound by L2 -> SM traffic: 387 MB for the linear1 head at cfg2);
+// K > 256: weight slices travel with the A slices.  Both operands are read from shared memory (SS-mode tcgen05.mma, M = 128, N = BN,
+// K = 16 per instruction), the B tile K-major (NT) or MN-major (NN) straight from the TMA boxes -- no transposed weight copy exists
+// anywhere; two BN-column fp32 accumulators in tensor memory alternate between tiles, so the epilogue of tile i (tcgen05.ld -> bias /
+// rotation / ReLU -> bf16 -> swizzled staging box -> TMA store per warp) overlaps the MMAs of tile i + 1.  The x half of the axial
+// rotation table (<= 64 rows x 64 pairs) is cached in shared memory with a padded row stride: a warp's 32 rows have up to 32 different
+// x positions, i.e. 32 different L1 lines per load instruction when read from global memory; the y half (<= 3 rows per warp) is read
+// through L1.  HBM-bound at every shape of the stack: algorithmic bytes = 2 (R K + K Nout + R Nout).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -34,35 +39,36 @@ namespace gemm {
 
 using namespace sm100;
 
-constexpr int kBlockM = 128;                 // rows per tile (TMEM lanes)
-constexpr int kBlockK = 64;                  // contraction slice per ring stage (one 128-byte swizzle row)
-constexpr int kStages = 4;
+constexpr int kBlockM = 128;                 // rows per accumulator (TMEM lanes)
+constexpr int kBlockK = 64;                  // contraction slice per ring slot (one 128-byte swizzle row)
+constexpr int kMaxSlots = 12;
 constexpr int kThreads = 320;                // warps 0-7 epilogue, 8 TMA producer, 9 MMA issuer
 constexpr int kEpiWarps = 8;
 constexpr int kATileBytes = kBlockM * 128;   // 16 KB: [128 rows x 128 B]
 constexpr int kBoxBytes = 32 * 128;          // one warp's output box: 32 rows x 64 bf16 columns
+constexpr int kXStride = 528;                // bytes per cached table row: 64 (cos, sin) pairs + 16 B pad (conflict-free 16-byte reads)
+constexpr int kXRows = 64;                   // cached x rows (grids up to 64 x 64 = 1024 px; larger grids read the table from L1 / L2)
+constexpr int kCtrlBytes = 2048;
 
-template <int BN>
-struct Shared {
-  alignas(1024) uint8_t a_tiles[kStages][kATileBytes];
-  alignas(1024) uint8_t b_tiles[kStages][BN * 128];          // NT: [BN rows x 128 B]; NN: BN / 64 slabs of [64 k-rows x 128 B]
-  alignas(1024) uint8_t stage[kEpiWarps][kBoxBytes];         // per-warp output staging (128-byte swizzle box layout)
-  alignas(8) uint64_t full[kStages];
-  uint64_t empty[kStages];
+struct Ctrl {                                // first 2 KB of the (1024-aligned) dynamic shared memory
+  uint64_t full[kMaxSlots];
+  uint64_t empty[kMaxSlots];
+  uint64_t b_full[4];                        // resident-weight mode: slice ks of the column block has landed
   uint64_t acc_full[2];
   uint64_t acc_free[2];
-  float bias[BN];                                            // the current column block's bias slice
+  float bias[256];                           // the current column block's bias slice
   uint32_t tmem_base;
 };
+static_assert(sizeof(Ctrl) <= kCtrlBytes, "control block");
 
 struct Params {
   int rows;                 // R
-  int n_tiles;              // ceil(R / 128) * n_col_blocks; tile t = (row tile t / n_col_blocks, column block t % n_col_blocks)
+  int n_row_tiles;          // ceil(R / 128)
   int n_col_blocks;         // Nout / BN
   int blocks_per_out;       // output tensor of column block cb = cb / blocks_per_out, its first column (cb % blocks_per_out) * BN
   int ksteps;               // K / 64
   int nout;                 // Nout (dropout element index = row * Nout + column)
-  int rope_blocks;          // leading column blocks (of 256) that are rotated
+  int rope_blocks;          // BN = 128: leading column blocks that are rotated (two per 256-wide head)
   int rope_w;               // sqrt(period) if the table is axial over a square grid (row = x part | y part), else 0
   int relu;                 // max(., 0) on the biased accumulator, then drop_out
   sam2b200::Dropout drop_out;
@@ -73,22 +79,59 @@ struct Params {
   int period;               // table row = position % period
   const float* dot_rows;    // BN = 64 only: [R, 64] fp32 or nullptr -> dot_out[r] = sum_c bf16(C[r, c]) * dot_rows[r, c]
   float* dot_out;           // [R] fp32 (the attention backward's Delta = rowsum(dO' o out64) from the GEMM that produces dO')
+  // shared-memory layout chosen by the host (byte offsets from the 1024-aligned base; every region 1024-aligned but the x cache)
+  int wres;                 // 1: K <= 256, the column block's weight slices stay in the B region; 0: B slices travel with the A slices
+  int n_slots;              // ring slots (each: MT A tiles of 16 KB, + one B slice when !wres)
+  int stage_bufs;           // staging boxes per epilogue warp (1 | 2)
+  uint32_t off_a, off_b, off_stage, off_x;
+  unsigned long long* dbg;  // optional per-CTA phase timeline (32 x u64 per CTA, %globaltimer ns; sam2b200_gemm_debug_timeline), else nullptr
 };
 
-template <int BN, int B_MN>
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Work items of one CTA; an item = MT consecutive row tiles x one column block.  Resident weights: the CTA keeps ONE column block and
+// walks items blockIdx.x / ncb, + gridDim.x / ncb, ... (gridDim.x is a multiple of ncb).  Streamed weights: items t = blockIdx.x,
+// + gridDim.x, ... with the column block fastest (CTAs that run together share the A tiles in L2).
+struct Schedule {
+  int ncb, n_groups, first, step, cb_fixed;
+  bool wres;
+  __device__ Schedule(const Params& p, int mt) {
+    ncb = p.n_col_blocks; n_groups = (p.n_row_tiles + mt - 1) / mt; wres = p.wres != 0;
+    if (wres) { cb_fixed = blockIdx.x % ncb; first = blockIdx.x / ncb; step = gridDim.x / ncb; }
+    else      { cb_fixed = 0; first = blockIdx.x; step = gridDim.x; }
+  }
+  __device__ bool item(int i, int& group, int& cb) const {
+    const int t = first + i * step;
+    if (wres) { group = t; cb = cb_fixed; return t < n_groups; }
+    group = t / ncb; cb = t - group * ncb;
+    return group < n_groups;
+  }
+};
+
+template <int BN, int B_MN, int MT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a,      // A [R, K]: box 64 x 128
-            const __grid_constant__ CUtensorMap map_b,      // NT: W [BN, K], box 64 x BN;  NN: W [K, BN], box 64 x 64
+            const __grid_constant__ CUtensorMap map_b,      // NT: W [Nout, K], box 64 x BN;  NN: W [K, Nout], box 64 x 64
             const __grid_constant__ CUtensorMap map_c0,     // outputs [R, out_width]: box 64 x 32 (store)
             const __grid_constant__ CUtensorMap map_c1, const __grid_constant__ CUtensorMap map_c2, const Params p) {
+  static_assert(MT == 1 || BN == 256, "two accumulators per item: BN = 256 only (2 x 256 TMEM columns)");
   extern __shared__ uint8_t smem_raw[];
-  Shared<BN>& sh = *reinterpret_cast<Shared<BN>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Ctrl& sh = *reinterpret_cast<Ctrl*>(base);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t kBBytes = BN * 128;
-  constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  constexpr uint32_t kABytes = MT * kATileBytes;            // A bytes per ring slot
+  constexpr uint32_t kTmemCols = 2 * BN;
+  const uint32_t a_base = smem_u32(base + p.off_a), b_base = smem_u32(base + p.off_b);
+  const int nslots = p.n_slots;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], 1); }
+    for (int i = 0; i < kMaxSlots; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], 1); }
+    for (int i = 0; i < 4; ++i) mbar_init(&sh.b_full[i], 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&sh.acc_full[i], 1); mbar_init(&sh.acc_free[i], kEpiWarps * 32); }
     fence_barrier_init();
   }
@@ -100,59 +143,79 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a,      // A [R, K]: box 64 
   tc_fence_after();
   const uint32_t tmem = sh.tmem_base;
   const int ksteps = p.ksteps;
-  const int ncb = p.n_col_blocks;
+  const Schedule sched(p, MT);
+  unsigned long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 32 : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = gtime();
 
   if (warp == 8) {
-    // ===================== TMA producer: one (A, B) k-slice per ring slot, running across tile boundaries =====================
+    // ===================== TMA producer =====================
     const bool leader = elect_one();
-    uint32_t slot = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const int row_tile = tile / ncb, cb = tile - row_tile * ncb;
-      for (int ks = 0; ks < ksteps; ++ks, ++slot) {
-        const int s = slot % kStages;
-        mbar_wait(&sh.empty[s], ((slot / kStages) & 1) ^ 1);
-        if (leader) {
-          mbar_arrive_expect_tx(&sh.full[s], kATileBytes + kBBytes);
-          tma_load_3d(&sh.a_tiles[s][0], &map_a, &sh.full[s], ks * kBlockK, row_tile * kBlockM, 0);
-          if (B_MN) {
+    auto load_b = [&](uint32_t dst, uint64_t* bar, int ks, int cb) {
+      if (B_MN) {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c)
-              tma_load_3d(&sh.b_tiles[s][c * 8192], &map_b, &sh.full[s], cb * BN + c * 64, ks * kBlockK, 0);
-          } else {
-            tma_load_3d(&sh.b_tiles[s][0], &map_b, &sh.full[s], ks * kBlockK, cb * BN, 0);
-          }
+        for (int c = 0; c < BN / 64; ++c) tma_load_3d_addr(dst + c * 8192, &map_b, bar, cb * BN + c * 64, ks * kBlockK, 0);
+      } else {
+        tma_load_3d_addr(dst, &map_b, bar, ks * kBlockK, cb * BN, 0);
+      }
+    };
+    if (sched.wres && leader) {               // the column block's weights: once, slice ks -> B slot ks
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_arrive_expect_tx(&sh.b_full[ks], kBBytes);
+        load_b(b_base + ks * kBBytes, &sh.b_full[ks], ks, sched.cb_fixed);
+      }
+    }
+    __syncwarp();
+    int s = 0;
+    uint32_t ph = 0;
+    int group, cb;
+    for (int i = 0; sched.item(i, group, cb); ++i) {
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(&sh.empty[s], ph ^ 1);
+        if (leader) {
+          mbar_arrive_expect_tx(&sh.full[s], kABytes + (sched.wres ? 0u : kBBytes));
+#pragma unroll
+          for (int m = 0; m < MT; ++m)          // a row tile beyond R loads as zeros (its stores are skipped)
+            tma_load_3d_addr(a_base + s * kABytes + m * kATileBytes, &map_a, &sh.full[s], ks * kBlockK, (group * MT + m) * kBlockM, 0);
+          if (!sched.wres) load_b(b_base + s * kBBytes, &sh.full[s], ks, cb);
         }
         __syncwarp();
+        if (++s == nslots) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 9) {
     // ===================== MMA issuer =====================
     const bool leader = elect_one();
     constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN, 0, B_MN);
-    const uint32_t a_lo0 = desc_lo_sw128(smem_u32(&sh.a_tiles[0][0]), 16);                 // K-major: LBO unused
-    const uint32_t b_lo0 = desc_lo_sw128(smem_u32(&sh.b_tiles[0][0]), B_MN ? 8192 : 16);   // MN-major: LBO = 64-column slab stride
+    const uint32_t a_lo0 = desc_lo_sw128(a_base, 16);                   // K-major: LBO unused
+    const uint32_t b_lo0 = desc_lo_sw128(b_base, B_MN ? 8192 : 16);     // MN-major: LBO = 64-column slab stride
     constexpr uint32_t b_kstep = B_MN ? (2048 >> 4) : 2;    // 16 k-rows x 128 B (MN-major) | 32 B inside the row (K-major)
-    uint32_t slot = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-      const int ab = it & 1;
-      mbar_wait(&sh.acc_free[ab], ((it >> 1) & 1) ^ 1);
+    int s = 0;
+    uint32_t ph = 0;
+    int group, cb;
+    for (int it = 0; sched.item(it, group, cb); ++it) {
+      // MT = 1: accumulators alternate between items; MT = 2: both belong to the item (no overlap with the previous drain)
+      const int ab = MT == 1 ? (it & 1) : 0;
+      mbar_wait(&sh.acc_free[ab], (MT == 1 ? ((it >> 1) & 1) : (it & 1)) ^ 1);
       tc_fence_after();
+      if (dbg && leader && it < 4) dbg[2 + 4 * it] = gtime();        // accumulator free: this item's MMAs may be issued
       const uint32_t d = tmem + ab * BN;
-      for (int ks = 0; ks < ksteps; ++ks, ++slot) {
-        const int s = slot % kStages;
-        mbar_wait(&sh.full[s], (slot / kStages) & 1);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(&sh.full[s], ph);
+        if (sched.wres && it == 0) mbar_wait(&sh.b_full[ks], 0);
         tc_fence_after();
         if (leader) {
-          const uint32_t alo = a_lo0 + s * (kATileBytes >> 4);
-          const uint32_t blo = b_lo0 + s * (kBBytes >> 4);
+          const uint32_t alo = a_lo0 + s * (kABytes >> 4);
+          const uint32_t blo = b_lo0 + (sched.wres ? ks : s) * (kBBytes >> 4);
 #pragma unroll
-          for (int k16 = 0; k16 < 4; ++k16)
-            umma_ss_lohi(d, alo + k16 * 2, blo + k16 * b_kstep, kDescHiSw128_1024, idesc, (ks | k16) != 0);
+          for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16)
+              umma_ss_lohi(d + m * BN, alo + m * (kATileBytes >> 4) + k16 * 2, blo + k16 * b_kstep, kDescHiSw128_1024, idesc, (ks | k16) != 0);
           umma_commit(&sh.empty[s]);
-          if (ks == ksteps - 1) umma_commit(&sh.acc_full[ab]);
+          if (ks == ksteps - 1) { umma_commit(&sh.acc_full[ab]); if (dbg && it < 4) dbg[3 + 4 * it] = gtime(); }   // last slice had landed, all MMAs issued
         }
         __syncwarp();
+        if (++s == nslots) { s = 0; ph ^= 1; }
       }
     }
   } else {
@@ -160,107 +223,146 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a,      // A [R, K]: box 64 
     const int quarter = warp & 3;
     const int half = warp >> 2;
     const uint32_t lane_addr = tmem + (uint32_t(quarter * 32) << 16);
-    const uint32_t srow = smem_u32(&sh.stage[warp][0]) + lane * 128;
+    const int nbufs = p.stage_bufs;
+    const uint32_t stage0 = smem_u32(base + p.off_stage) + warp * nbufs * kBoxBytes;
+    uint32_t nstore = 0;
     constexpr int kChunks = BN / 64;
+    constexpr int kMyChunks = (kChunks + 1) / 2;            // chunks per warp (BN = 64: the upper four warps have none)
     const bool drop_on = p.drop_out.seed != nullptr;
     const uint32_t dkey = drop_on ? sam2b200::dropout_key(*p.drop_out.seed, p.drop_out.site) : 0u;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-      const int ab = it & 1;
-      const int row_tile = tile / ncb, cb = tile - row_tile * ncb;
-      const int row0 = row_tile * kBlockM + quarter * 32;
+    // x half of the axial rotation table -> shared memory, once per CTA (rows x = 0 .. w-1, 64 pairs each)
+    const bool xcached = BN == 128 && p.rope_blocks > 0 && p.rope_w > 0 && p.rope_w <= kXRows;
+    const uint32_t xbase = smem_u32(base + p.off_x);
+    if (BN == 128 && xcached) {
+      const float4* src = reinterpret_cast<const float4*>(p.table);
+      for (int idx = threadIdx.x; idx < p.rope_w * 32; idx += kEpiWarps * 32) {
+        const int x = idx >> 5, q = idx & 31;
+        *reinterpret_cast<float4*>(base + p.off_x + x * kXStride + q * 16) = __ldg(src + x * 64 + q);
+      }
+      asm volatile("bar.sync 5, 256;" ::: "memory");
+    }
+    int group, cb;
+    for (int it = 0; sched.item(it, group, cb); ++it) {
+      const int ab = MT == 1 ? (it & 1) : 0;
       const int which = cb / p.blocks_per_out;
       const int ocol0 = (cb - which * p.blocks_per_out) * BN;         // first column of this block inside its output tensor
       const CUtensorMap* mo = which == 0 ? &map_c0 : (which == 1 ? &map_c1 : &map_c2);
-      // this column block's bias slice -> shared memory (broadcast reads below); with one column block it is loaded once
-      if (it == 0 || ncb > 1) {
+      // this column block's bias slice -> shared memory (broadcast reads below); with a fixed column block it is loaded once
+      if (it == 0 || (!sched.wres && sched.ncb > 1)) {
         if (it > 0) asm volatile("bar.sync 5, 256;" ::: "memory");      // every warp has finished reading the previous slice
         if ((int)threadIdx.x < BN) sh.bias[threadIdx.x] = p.bias ? __ldg(p.bias + cb * BN + threadIdx.x) : 0.f;
         asm volatile("bar.sync 5, 256;" ::: "memory");
       }
-      const float2* trow_x = nullptr;             // (cos, sin) rows of this thread's position: columns [0, 128) | [128, 256) of the head
-      const float2* trow_y = nullptr;
-      if (BN == 256 && cb < p.rope_blocks) {
-        const int pos = (int)(((long long)row0 + lane) % p.rows_per_item);
-        if (pos < p.n_rope_rows) {
-          const int tpos = pos % p.period;
-          // axial table over a square grid: the first 64 pairs depend on x = pos % w only, the last 64 on y = pos / w only --
-          // a tile touches w + 128 / w distinct half rows instead of 128 (L1 resident)
-          trow_x = p.table + (long long)(p.rope_w > 0 ? tpos % p.rope_w : tpos) * 128;
-          trow_y = p.table + (long long)(p.rope_w > 0 ? tpos - tpos % p.rope_w : tpos) * 128;
-        }
-      }
-      mbar_wait(&sh.acc_full[ab], (it >> 1) & 1);
+      mbar_wait(&sh.acc_full[ab], MT == 1 ? ((it >> 1) & 1) : (it & 1));
       tc_fence_after();
-#pragma unroll
-      for (int c = half; c < kChunks; c += 2) {
-        // the warp's previous box must have been read by the TMA unit before its staging buffer is rewritten
-        if (lane == 0) tma_store_wait_read();
-        __syncwarp();
-        float dot = 0.f;
-        const float2* trow = (c < 2) ? trow_x : trow_y;
-#pragma unroll
-        for (int sb = 0; sb < 2; ++sb) {          // two sub-blocks of 32 columns
-          uint32_t acc[32];
-          SAM2B200_TMEM_LD32(lane_addr + ab * BN + c * 64 + sb * 32, acc);
-          float4 cs[16];
-          if (BN == 256 && trow != nullptr) {     // the (cos, sin) pairs of this row's 32 columns, fetched under the TMEM load
-            const float4* src = reinterpret_cast<const float4*>(trow + c * 32 + sb * 16);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) cs[i] = __ldg(src + i);
-          }
-          tmem_wait_ld();
-          if (sb == 1 && c + 2 >= kChunks) { tc_fence_before(); mbar_arrive(&sh.acc_free[ab]); }   // this thread's last read of the accumulator
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) + sh.bias[c * 64 + sb * 32 + i];
-          if (BN == 256 && trow != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {         // (re, im) = (v[2j], v[2j+1]) times (cos + i sin), two pairs per float4
-              const float r0 = v[4 * i] * cs[i].x - v[4 * i + 1] * cs[i].y, i0 = v[4 * i] * cs[i].y + v[4 * i + 1] * cs[i].x;
-              const float r1 = v[4 * i + 2] * cs[i].z - v[4 * i + 3] * cs[i].w, i1 = v[4 * i + 2] * cs[i].w + v[4 * i + 3] * cs[i].z;
-              v[4 * i] = r0; v[4 * i + 1] = i0; v[4 * i + 2] = r1; v[4 * i + 3] = i1;
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-            if (drop_on) {
-              const uint32_t idx = (uint32_t)(((long long)row0 + lane) * p.nout + cb * BN + c * 64 + sb * 32);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = sam2b200::dropout_keep(dkey, idx + i, p.drop_out.thresh) ? v[i] * p.drop_out.inv_keep : 0.f;
-            }
-          }
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
-          if (BN == 64 && p.dot_rows != nullptr && row0 + lane < p.rows) {      // row dot product with the values the consumer will read (bf16)
-            const float4* orow = reinterpret_cast<const float4*>(p.dot_rows + (long long)(row0 + lane) * 64 + sb * 32);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 o4 = __ldg(orow + i);
-              const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[2 * i]));
-              const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[2 * i + 1]));
-              dot += lo.x * o4.x + lo.y * o4.y + hi.x * o4.z + hi.y * o4.w;
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            sts128(srow + (((sb * 4 + q) ^ (lane & 7)) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-        }
-        if (BN == 64 && p.dot_out != nullptr && row0 + lane < p.rows) p.dot_out[row0 + lane] = dot;
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          if (row0 < p.rows) tma_store_3d(mo, &sh.stage[warp][0], ocol0 + c * 64, row0, 0);   // rows beyond R are clipped by the TMA unit
-          tma_store_commit();
-        }
-      }
-      if (kChunks == 1 && half == 1) {            // BN = 64: the upper four warps only release the accumulator
+      if (dbg && threadIdx.x == 0 && it < 4) dbg[4 + 4 * it] = gtime();   // MMAs of this item complete
+      if (kMyChunks * 2 > kChunks && half == 1) {   // BN = 64: the upper four warps only release the accumulator
         tc_fence_before();
         mbar_arrive(&sh.acc_free[ab]);
+        continue;
       }
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const int row0 = (group * MT + m) * kBlockM + quarter * 32;
+        const uint32_t acc_col = (MT == 1 ? ab : m) * BN;
+        // rotation (BN = 128): block cb covers head columns [0, 128) (the x half of the axial table) if cb is even, else [128, 256) (y half)
+        bool rotate = false;
+        const float4* tsrc = nullptr;               // this thread's (cos, sin) pairs for the block's 128 columns: 64 pairs = 32 float4
+        uint32_t xs_addr = 0;
+        if (BN == 128 && cb < p.rope_blocks) {
+          const int pos = (int)((unsigned)(row0 + lane) % (unsigned)p.rows_per_item);
+          if (pos < p.n_rope_rows) {
+            rotate = true;
+            const int tpos = pos % p.period;
+            const bool xhalf = (cb & 1) == 0;
+            if (xhalf && xcached) xs_addr = xbase + (tpos % p.rope_w) * kXStride;
+            else {
+              const int trow = p.rope_w > 0 ? (xhalf ? tpos % p.rope_w : tpos - tpos % p.rope_w) : tpos;
+              tsrc = reinterpret_cast<const float4*>(p.table + (long long)trow * 128 + (xhalf ? 0 : 64));
+            }
+          }
+        }
+#pragma unroll
+        for (int ci = 0; ci < kMyChunks; ++ci) {
+          const int c = half + 2 * ci;
+          float dot = 0.f;
+          uint32_t pk[32];                          // this row's 64 columns of the chunk as bf16 pairs
+#pragma unroll
+          for (int sb = 0; sb < 2; ++sb) {          // two sub-blocks of 32 columns
+            uint32_t acc[32];
+            SAM2B200_TMEM_LD32(lane_addr + acc_col + c * 64 + sb * 32, acc);
+            float4 cs[8];
+            if (BN == 128 && rotate) {              // the 16 (cos, sin) pairs of this row's 32 columns, fetched under the TMEM load
+              if (tsrc == nullptr) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const uint4 u = lds128(xs_addr + (c * 16 + sb * 8 + i) * 16);
+                  cs[i] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w)); }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) cs[i] = __ldg(tsrc + c * 16 + sb * 8 + i);
+              }
+            }
+            tmem_wait_ld();
+            if (sb == 1 && ci == kMyChunks - 1 && m == MT - 1) { tc_fence_before(); mbar_arrive(&sh.acc_free[ab]); }   // this thread's last read of the accumulator(s)
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) + sh.bias[c * 64 + sb * 32 + i];
+            if (BN == 128 && rotate) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {         // (re, im) = (v[2j], v[2j+1]) times (cos + i sin), two pairs per float4
+                const float r0 = v[4 * i] * cs[i].x - v[4 * i + 1] * cs[i].y, i0 = v[4 * i] * cs[i].y + v[4 * i + 1] * cs[i].x;
+                const float r1 = v[4 * i + 2] * cs[i].z - v[4 * i + 3] * cs[i].w, i1 = v[4 * i + 2] * cs[i].w + v[4 * i + 3] * cs[i].z;
+                v[4 * i] = r0; v[4 * i + 1] = i0; v[4 * i + 2] = r1; v[4 * i + 3] = i1;
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+              if (drop_on) {
+                const uint32_t idx = (uint32_t)(((long long)row0 + lane) * p.nout + cb * BN + c * 64 + sb * 32);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = sam2b200::dropout_keep(dkey, idx + i, p.drop_out.thresh) ? v[i] * p.drop_out.inv_keep : 0.f;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[sb * 16 + i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+            if (BN == 64 && p.dot_rows != nullptr && row0 + lane < p.rows) {      // row dot product with the values the consumer will read (bf16)
+              const float4* orow = reinterpret_cast<const float4*>(p.dot_rows + (long long)(row0 + lane) * 64 + sb * 32);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 o4 = __ldg(orow + i);
+                const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[sb * 16 + 2 * i]));
+                const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[sb * 16 + 2 * i + 1]));
+                dot += lo.x * o4.x + lo.y * o4.y + hi.x * o4.z + hi.y * o4.w;
+              }
+            }
+          }
+          if (BN == 64 && p.dot_out != nullptr && row0 + lane < p.rows) p.dot_out[row0 + lane] = dot;
+          // staging: the box handed to the TMA unit `nbufs` chunks ago must have been read before its buffer is rewritten -- waited
+          // for only now, with the chunk already in registers
+          const uint32_t sbuf = stage0 + ((nbufs == 2) ? (nstore & 1) : 0) * kBoxBytes;
+          if (lane == 0) {
+            if (nbufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else tma_store_wait_read();
+          }
+          __syncwarp();
+          const uint32_t srow = sbuf + lane * 128;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            sts128(srow + ((q ^ (lane & 7)) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (row0 < p.rows) tma_store_3d_addr(mo, sbuf, ocol0 + c * 64, row0, 0);   // rows beyond R are clipped by the TMA unit
+            tma_store_commit();
+          }
+          ++nstore;
+        }
+      }
+      if (dbg && threadIdx.x == 0 && it < 4) dbg[5 + 4 * it] = gtime();   // warp 0: last box of this item handed to the TMA unit
+      if (dbg && threadIdx.x == 0) dbg[31] = (unsigned long long)(it + 1);
     }
+    if (dbg && threadIdx.x == 0) dbg[30] = gtime();
     if (lane == 0) tma_store_wait_read();
   }
   tc_fence_before();
@@ -300,14 +402,48 @@ int sm_count() {
   return n;
 }
 
-template <int BN, int B_MN>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap* mc, const gemm::Params& p, cudaStream_t stream) {
-  const size_t smem = sizeof(gemm::Shared<BN>) + 1024;
-  static_assert(sizeof(gemm::Shared<BN>) + 1024 <= 227 * 1024, "shared memory of one CTA");
-  cudaError_t e = cudaFuncSetAttribute(gemm::gemm_kernel<BN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+unsigned long long* g_dbg = nullptr;      // sam2b200_gemm_debug_timeline: consecutive launches append 32 x u64 per CTA
+size_t g_dbg_cap = 0, g_dbg_used = 0;
+
+constexpr int kSmemBudget = 227 * 1024 - 1024 - gemm::kCtrlBytes;      // after the alignment slack and the control block
+
+// Shared-memory layout + grid for one problem, then the launch.  Regions (1024-aligned): B | A ring | staging | x cache.
+template <int BN, int B_MN, int MT>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap* mc, gemm::Params p, cudaStream_t stream) {
+  const int b_slice = BN * 128, a_slot = MT * gemm::kATileBytes;
+  const int x_bytes = (BN == 128 && p.rope_blocks > 0 && p.rope_w > 0 && p.rope_w <= gemm::kXRows) ? ((p.rope_w * gemm::kXStride + 1023) & ~1023) : 0;
+  int stage_bytes = gemm::kEpiWarps * gemm::kBoxBytes;
+  p.stage_bufs = 1;
+  int left;
+  if (p.wres) {
+    left = kSmemBudget - p.ksteps * b_slice - stage_bytes - x_bytes;
+    p.n_slots = left / a_slot;
+    // more than two row tiles of A in flight buy nothing: a second staging box per warp instead
+    if (p.n_slots > 2 * p.ksteps + 2 && left - stage_bytes >= (2 * p.ksteps + 2) * a_slot) { p.stage_bufs = 2; stage_bytes *= 2; left -= stage_bytes / 2; p.n_slots = left / a_slot; }
+  } else {
+    left = kSmemBudget - stage_bytes;
+    p.n_slots = left / (a_slot + b_slice);
+  }
+  if (p.n_slots > gemm::kMaxSlots) p.n_slots = gemm::kMaxSlots;
+  if (p.n_slots < 2) return sam2b200::fail(SAM2B200_ERR_UNSUPPORTED, "gemm: shared memory layout does not fit");
+  const int b_bytes = (p.wres ? p.ksteps : p.n_slots) * b_slice;
+  p.off_b = gemm::kCtrlBytes; p.off_a = p.off_b + b_bytes; p.off_stage = p.off_a + p.n_slots * a_slot; p.off_x = p.off_stage + stage_bytes;
+  const size_t smem = (size_t)p.off_x + x_bytes + 1024;
+  if (smem > 227 * 1024) return sam2b200::fail(SAM2B200_ERR_UNSUPPORTED, "gemm: shared memory layout does not fit");
+  cudaError_t e = cudaFuncSetAttribute(gemm::gemm_kernel<BN, B_MN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return sam2b200::fail(SAM2B200_ERR_CUDA, cudaGetErrorString(e));
-  const unsigned grid = (unsigned)(p.n_tiles < sm_count() ? p.n_tiles : sm_count());
-  gemm::gemm_kernel<BN, B_MN><<<grid, gemm::kThreads, smem, stream>>>(ma, mb, mc[0], mc[1], mc[2], p);
+  const int sms = sm_count(), ncb = p.n_col_blocks, groups = (p.n_row_tiles + MT - 1) / MT;
+  unsigned grid;
+  if (p.wres) {                               // resident weights: a CTA keeps one column block, grid = CTAs per block x blocks
+    int per_cb = sms / ncb < 1 ? 1 : sms / ncb;
+    if (per_cb > groups) per_cb = groups;
+    grid = (unsigned)(per_cb * ncb);
+  } else {
+    const long long items = (long long)groups * ncb;
+    grid = (unsigned)(items < sms ? items : sms);
+  }
+  if (g_dbg && g_dbg_used + (size_t)grid * 32 <= g_dbg_cap) { p.dbg = g_dbg + g_dbg_used; g_dbg_used += (size_t)grid * 32; }
+  gemm::gemm_kernel<BN, B_MN, MT><<<grid, gemm::kThreads, smem, stream>>>(ma, mb, mc[0], mc[1], mc[2], p);
   return sam2b200::check_launch("gemm");
 }
 
@@ -316,6 +452,15 @@ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 }  // namespace
 
 extern "C" {
+
+// Debug aid: per-CTA %globaltimer phase stamps of the following sam2b200_gemm* launches into buf (n_u64 entries, 32 per CTA:
+// [0] start, per item i < 4: [2+4i] accumulator free, [3+4i] MMAs issued, [4+4i] MMAs complete, [5+4i] last store issued, [30] end,
+// [31] tiles of the CTA).  buf = NULL switches it off; returns the number of entries written since the last call.
+long long sam2b200_gemm_debug_timeline(void* buf, long long n_u64) {
+  const long long used = (long long)g_dbg_used;
+  g_dbg = static_cast<unsigned long long*>(buf); g_dbg_cap = buf ? (size_t)n_u64 : 0; g_dbg_used = 0;
+  return used;
+}
 
 // C[R, Nout] = epi(a[R, K] . B + bias), C split over n_out = Nout / out_width <= 3 bf16 tensors [R, out_width] (row stride ldc):
 // Nout = 64 (one output) or a multiple of 256 up to 2048, out_width a multiple of 256 (or 64), K % 64 == 0.
@@ -328,12 +473,12 @@ int sam2b200_gemm_ex(void* out0, void* out1, void* out2, int out_width, long lon
                      long long ldb, int b_layout, long long R, int K, int Nout, const float* bias, int rope_cols, const float* table,
                      int rows_per_item, int n_rope_rows, int period, int relu, float drop_p, const unsigned long long* drop_seed,
                      unsigned drop_site, const float* dot_rows, float* dot_out, cudaStream_t stream) {
-  const int bn = Nout == 64 ? 64 : 256;
+  const int bn = Nout == 64 ? 64 : (rope_cols > 0 ? 128 : 256);      // rotated outputs: 128-column blocks = the x / y halves of a head
   const int n_out = out_width > 0 ? Nout / out_width : 0;
   if (!out0 || !a || !b || R <= 0 || R > 0x7fffffffLL - 256 || K <= 0 || (K % 64) || Nout <= 0 || (Nout % bn) || Nout > 2048 ||
       out_width <= 0 || (out_width % bn) || n_out * out_width != Nout || n_out > 3 || (n_out > 1 && !out1) || (n_out > 2 && !out2) ||
       (b_layout != 0 && b_layout != 1) || lda < K || ldc < out_width || ldb < (b_layout ? Nout : K) || ((lda | ldb | ldc) & 7) ||
-      rope_cols < 0 || (rope_cols % 256) || rope_cols > Nout || (rope_cols > 0 && (bn != 256 || !table || rows_per_item <= 0 || n_rope_rows < 0 || period <= 0)) ||
+      rope_cols < 0 || (rope_cols % 256) || rope_cols > Nout || (rope_cols > 0 && (!table || rows_per_item <= 0 || n_rope_rows < 0 || period <= 0)) ||
       drop_p < 0.f || drop_p >= 1.f || (drop_p > 0.f && drop_seed && R * (long long)Nout >= (1LL << 32)) ||
       ((dot_rows != nullptr) != (dot_out != nullptr)) || (dot_rows && Nout != 64) ||
       !al16(out0) || !al16(out1) || !al16(out2) || !al16(a) || !al16(b) || !al16(bias) || !al16(table) || !al16(dot_rows))
@@ -347,15 +492,22 @@ int sam2b200_gemm_ex(void* out0, void* out1, void* out2, int out_width, long lon
   for (int i = 0; i < 3; ++i)
     if ((rc = make_map(&mc[i], outs[i], R, out_width, ldc, 32))) return rc;
   gemm::Params p{};
-  p.rows = (int)R; p.n_col_blocks = Nout / bn; p.n_tiles = (int)((R + gemm::kBlockM - 1) / gemm::kBlockM) * p.n_col_blocks;
+  p.rows = (int)R; p.n_col_blocks = Nout / bn; p.n_row_tiles = (int)((R + gemm::kBlockM - 1) / gemm::kBlockM);
   p.blocks_per_out = out_width / bn; p.ksteps = K / gemm::kBlockK; p.nout = Nout; p.bias = bias;
-  p.rope_blocks = rope_cols / 256; p.table = reinterpret_cast<const float2*>(table); p.rows_per_item = rows_per_item > 0 ? rows_per_item : 1;
+  p.rope_blocks = rope_cols / 128; p.table = reinterpret_cast<const float2*>(table); p.rows_per_item = rows_per_item > 0 ? rows_per_item : 1;
   p.n_rope_rows = n_rope_rows; p.period = period > 0 ? period : 1;
   if (rope_cols > 0) { int w = (int)(sqrt((double)p.period) + 0.5); p.rope_w = (w * w == p.period) ? w : 0; }
   p.relu = relu; p.drop_out = sam2b200::make_dropout(drop_seed, drop_site, drop_p);
   p.dot_rows = dot_rows; p.dot_out = dot_out;
-  if (bn == 256) return b_layout ? launch<256, 1>(ma, mb, mc, p, stream) : launch<256, 0>(ma, mb, mc, p, stream);
-  return b_layout ? launch<64, 1>(ma, mb, mc, p, stream) : launch<64, 0>(ma, mb, mc, p, stream);
+  p.wres = p.ksteps <= 4;
+  if (bn == 256) {
+    // streamed weights and more row tiles than SMs: two row tiles (two accumulators) per item share every weight slice -- the
+    // kernel is bound by L2 -> SM traffic otherwise (1 MB of weights per 128 rows at K = 2048)
+    if (!p.wres && p.n_row_tiles > sm_count()) return b_layout ? launch<256, 1, 2>(ma, mb, mc, p, stream) : launch<256, 0, 2>(ma, mb, mc, p, stream);
+    return b_layout ? launch<256, 1, 1>(ma, mb, mc, p, stream) : launch<256, 0, 1>(ma, mb, mc, p, stream);
+  }
+  if (bn == 128) return b_layout ? launch<128, 1, 1>(ma, mb, mc, p, stream) : launch<128, 0, 1>(ma, mb, mc, p, stream);
+  return b_layout ? launch<64, 1, 1>(ma, mb, mc, p, stream) : launch<64, 0, 1>(ma, mb, mc, p, stream);
 }
 
 // One output of width No = 256 | 64: c[R, No] = a . B (+ bias); table != NULL rotates the whole output (the memory-key projection).

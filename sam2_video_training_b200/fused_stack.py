@@ -330,7 +330,12 @@ def bias_grad_(gbias, dx16):
 NO_WGRAD = bool(os.environ.get("SAM2B200_NO_WGRAD"))
 
 
+WGRAD_MLP = bool(os.environ.get("SAM2B200_WGRAD_MLP"))   # A/B: the two MLP weight gradients on sam2b200_wgrad as well
+
+
 def _wgrad_ok(mo, no):
+    if WGRAD_MLP and not NO_WGRAD and ((mo, no) == (256, 2048) or (mo, no) == (2048, 256)):
+        return True
     return (not NO_WGRAD) and mo % 256 == 0 and (no == 64 or (no == 256 and mo <= 768))
 
 

@@ -29,6 +29,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "abi_common.cuh"
 #include "dropout.cuh"
@@ -42,8 +43,10 @@ using namespace sm100;
 constexpr int kBlockM = 128;                 // rows per accumulator (TMEM lanes)
 constexpr int kBlockK = 64;                  // contraction slice per ring slot (one 128-byte swizzle row)
 constexpr int kMaxSlots = 12;
-constexpr int kThreads = 320;                // warps 0-7 epilogue, 8 TMA producer, 9 MMA issuer
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 8;                 // epilogue warps per group: warp (quarter, half) = TMEM lane quarter x column half
+// EG epilogue groups of 8 warps (EG = 2, BN = 128 only: four 128-column accumulators, group g drains items g, g + 2, ...), then one
+// TMA producer warp and one MMA issuer warp
+__host__ __device__ constexpr int threads_for(int eg) { return (eg * kEpiWarps + 2) * 32; }
 constexpr int kATileBytes = kBlockM * 128;   // 16 KB: [128 rows x 128 B]
 constexpr int kBoxBytes = 32 * 128;          // one warp's output box: 32 rows x 64 bf16 columns
 constexpr int kXStride = 528;                // bytes per cached table row: 64 (cos, sin) pairs + 16 B pad (conflict-free 16-byte reads)
@@ -54,8 +57,8 @@ struct Ctrl {                                // first 2 KB of the (1024-aligned)
   uint64_t full[kMaxSlots];
   uint64_t empty[kMaxSlots];
   uint64_t b_full[4];                        // resident-weight mode: slice ks of the column block has landed
-  uint64_t acc_full[2];
-  uint64_t acc_free[2];
+  uint64_t acc_full[4];
+  uint64_t acc_free[4];
   float bias[256];                           // the current column block's bias slice
   uint32_t tmem_base;
 };
@@ -112,32 +115,35 @@ struct Schedule {
   }
 };
 
-template <int BN, int B_MN, int MT>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, int B_MN, int MT, int EG>
+__global__ void __launch_bounds__(threads_for(EG), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a,      // A [R, K]: box 64 x 128
             const __grid_constant__ CUtensorMap map_b,      // NT: W [Nout, K], box 64 x BN;  NN: W [K, Nout], box 64 x 64
             const __grid_constant__ CUtensorMap map_c0,     // outputs [R, out_width]: box 64 x 32 (store)
             const __grid_constant__ CUtensorMap map_c1, const __grid_constant__ CUtensorMap map_c2, const Params p) {
   static_assert(MT == 1 || BN == 256, "two accumulators per item: BN = 256 only (2 x 256 TMEM columns)");
+  static_assert(EG == 1 || (BN == 128 && MT == 1), "two epilogue groups: BN = 128 only (4 x 128 TMEM columns)");
+  constexpr int kProdWarp = EG * kEpiWarps, kMmaWarp = kProdWarp + 1;
+  constexpr int kAcc = 2 * EG;                              // accumulators in tensor memory (MT = 1)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Ctrl& sh = *reinterpret_cast<Ctrl*>(base);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t kBBytes = BN * 128;
   constexpr uint32_t kABytes = MT * kATileBytes;            // A bytes per ring slot
-  constexpr uint32_t kTmemCols = 2 * BN;
+  constexpr uint32_t kTmemCols = (MT == 2 ? 2 : kAcc) * BN;
   const uint32_t a_base = smem_u32(base + p.off_a), b_base = smem_u32(base + p.off_b);
   const int nslots = p.n_slots;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxSlots; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], 1); }
     for (int i = 0; i < 4; ++i) mbar_init(&sh.b_full[i], 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&sh.acc_full[i], 1); mbar_init(&sh.acc_free[i], kEpiWarps * 32); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&sh.acc_full[i], 1); mbar_init(&sh.acc_free[i], kEpiWarps * 32); }
     fence_barrier_init();
   }
-  if (warp == 8 && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_b); }
+  if (warp == kProdWarp && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_b); }
   if (warp == 0 && lane == 0) { prefetch_tmap(&map_c0); prefetch_tmap(&map_c1); prefetch_tmap(&map_c2); }
-  if (warp == 9) { tmem_alloc(&sh.tmem_base, kTmemCols); tmem_relinquish(); }
+  if (warp == kMmaWarp) { tmem_alloc(&sh.tmem_base, kTmemCols); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -147,7 +153,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a,      // A [R, K]: box 64 
   unsigned long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 32 : nullptr;
   if (dbg && threadIdx.x == 0) dbg[0] = gtime();
 
-  if (warp == 8) {
+  if (warp == kProdWarp) {
     // ===================== TMA producer =====================
     const bool leader = elect_one();
     auto load_b = [&](uint32_t dst, uint64_t* bar, int ks, int cb) {
@@ -182,7 +188,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a,      // A [R, K]: box 64 
         if (++s == nslots) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
     const bool leader = elect_one();
     constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN, 0, B_MN);
@@ -194,8 +200,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a,      // A [R, K]: box 64 
     int group, cb;
     for (int it = 0; sched.item(it, group, cb); ++it) {
       // MT = 1: accumulators alternate between items; MT = 2: both belong to the item (no overlap with the previous drain)
-      const int ab = MT == 1 ? (it & 1) : 0;
-      mbar_wait(&sh.acc_free[ab], (MT == 1 ? ((it >> 1) & 1) : (it & 1)) ^ 1);
+      const int ab = MT == 1 ? (it % kAcc) : 0;
+      mbar_wait(&sh.acc_free[ab], (MT == 1 ? ((it / kAcc) & 1) : (it & 1)) ^ 1);
       tc_fence_after();
       if (dbg && leader && it < 4) dbg[2 + 4 * it] = gtime();        // accumulator free: this item's MMAs may be issued
       const uint32_t d = tmem + ab * BN;
@@ -220,8 +226,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a,      // A [R, K]: box 64 
     }
   } else {
     // ===================== epilogue warps (0..7): warp (quarter, half) owns rows quarter*32.. of column chunks c = half, half + 2 =====================
+    const int group = warp / kEpiWarps;                     // epilogue group (EG = 2: items group, group + 2, ...)
+    const int gtid = threadIdx.x - group * kEpiWarps * 32;  // thread index inside the group
     const int quarter = warp & 3;
-    const int half = warp >> 2;
+    const int half = (warp >> 2) & 1;
     const uint32_t lane_addr = tmem + (uint32_t(quarter * 32) << 16);
     const int nbufs = p.stage_bufs;
     const uint32_t stage0 = smem_u32(base + p.off_stage) + warp * nbufs * kBoxBytes;
@@ -235,25 +243,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a,      // A [R, K]: box 64 
     const uint32_t xbase = smem_u32(base + p.off_x);
     if (BN == 128 && xcached) {
       const float4* src = reinterpret_cast<const float4*>(p.table);
-      for (int idx = threadIdx.x; idx < p.rope_w * 32; idx += kEpiWarps * 32) {
+      for (int idx = threadIdx.x; idx < p.rope_w * 32; idx += EG * kEpiWarps * 32) {
         const int x = idx >> 5, q = idx & 31;
         *reinterpret_cast<float4*>(base + p.off_x + x * kXStride + q * 16) = __ldg(src + x * 64 + q);
       }
-      asm volatile("bar.sync 5, 256;" ::: "memory");
+      asm volatile("bar.sync 7, %0;" ::"r"(EG * kEpiWarps * 32) : "memory");
     }
-    int group, cb;
-    for (int it = 0; sched.item(it, group, cb); ++it) {
-      const int ab = MT == 1 ? (it & 1) : 0;
+    float* bias_s = sh.bias + group * BN;               // this group's copy of the bias slice
+    int rgroup, cb;
+    for (int it = group; sched.item(it, rgroup, cb); it += EG) {
+      const int ab = MT == 1 ? (it % kAcc) : 0;
       const int which = cb / p.blocks_per_out;
       const int ocol0 = (cb - which * p.blocks_per_out) * BN;         // first column of this block inside its output tensor
       const CUtensorMap* mo = which == 0 ? &map_c0 : (which == 1 ? &map_c1 : &map_c2);
       // this column block's bias slice -> shared memory (broadcast reads below); with a fixed column block it is loaded once
-      if (it == 0 || (!sched.wres && sched.ncb > 1)) {
-        if (it > 0) asm volatile("bar.sync 5, 256;" ::: "memory");      // every warp has finished reading the previous slice
-        if ((int)threadIdx.x < BN) sh.bias[threadIdx.x] = p.bias ? __ldg(p.bias + cb * BN + threadIdx.x) : 0.f;
-        asm volatile("bar.sync 5, 256;" ::: "memory");
+      if (it == group || (!sched.wres && sched.ncb > 1)) {
+        if (it != group) asm volatile("bar.sync %0, 256;" ::"r"(5 + group) : "memory");      // every warp of the group has finished reading the previous slice
+        if (gtid < BN) bias_s[gtid] = p.bias ? __ldg(p.bias + cb * BN + gtid) : 0.f;
+        asm volatile("bar.sync %0, 256;" ::"r"(5 + group) : "memory");
       }
-      mbar_wait(&sh.acc_full[ab], MT == 1 ? ((it >> 1) & 1) : (it & 1));
+      mbar_wait(&sh.acc_full[ab], MT == 1 ? ((it / kAcc) & 1) : (it & 1));
       tc_fence_after();
       if (dbg && threadIdx.x == 0 && it < 4) dbg[4 + 4 * it] = gtime();   // MMAs of this item complete
       if (kMyChunks * 2 > kChunks && half == 1) {   // BN = 64: the upper four warps only release the accumulator
@@ -263,7 +272,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a,      // A [R, K]: box 64 
       }
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
-        const int row0 = (group * MT + m) * kBlockM + quarter * 32;
+        const int row0 = (rgroup * MT + m) * kBlockM + quarter * 32;
         const uint32_t acc_col = (MT == 1 ? ab : m) * BN;
         // rotation (BN = 128): block cb covers head columns [0, 128) (the x half of the axial table) if cb is even, else [128, 256) (y half)
         bool rotate = false;
@@ -286,7 +295,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a,      // A [R, K]: box 64 
         for (int ci = 0; ci < kMyChunks; ++ci) {
           const int c = half + 2 * ci;
           float dot = 0.f;
-          uint32_t pk[32];                          // this row's 64 columns of the chunk as bf16 pairs
+          // staging: the box handed to the TMA unit `nbufs` chunks ago must have been read before its buffer is rewritten
+          const uint32_t sbuf = stage0 + ((nbufs == 2) ? (nstore & 1) : 0) * kBoxBytes;
+          if (lane == 0) {
+            if (nbufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else tma_store_wait_read();
+          }
+          __syncwarp();
+          const uint32_t srow = sbuf + lane * 128;
 #pragma unroll
           for (int sb = 0; sb < 2; ++sb) {          // two sub-blocks of 32 columns
             uint32_t acc[32];
@@ -306,7 +322,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a,      // A [R, K]: box 64 
             if (sb == 1 && ci == kMyChunks - 1 && m == MT - 1) { tc_fence_before(); mbar_arrive(&sh.acc_free[ab]); }   // this thread's last read of the accumulator(s)
             float v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) + sh.bias[c * 64 + sb * 32 + i];
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) + bias_s[c * 64 + sb * 32 + i];
             if (BN == 128 && rotate) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {         // (re, im) = (v[2j], v[2j+1]) times (cos + i sin), two pairs per float4
@@ -324,32 +340,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a,      // A [R, K]: box 64 
                 for (int i = 0; i < 32; ++i) v[i] = sam2b200::dropout_keep(dkey, idx + i, p.drop_out.thresh) ? v[i] * p.drop_out.inv_keep : 0.f;
               }
             }
+            uint32_t pk[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) pk[sb * 16 + i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+            for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
             if (BN == 64 && p.dot_rows != nullptr && row0 + lane < p.rows) {      // row dot product with the values the consumer will read (bf16)
               const float4* orow = reinterpret_cast<const float4*>(p.dot_rows + (long long)(row0 + lane) * 64 + sb * 32);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const float4 o4 = __ldg(orow + i);
-                const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[sb * 16 + 2 * i]));
-                const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[sb * 16 + 2 * i + 1]));
+                const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[2 * i]));
+                const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[2 * i + 1]));
                 dot += lo.x * o4.x + lo.y * o4.y + hi.x * o4.z + hi.y * o4.w;
               }
             }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              sts128(srow + (((sb * 4 + q) ^ (lane & 7)) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
           }
           if (BN == 64 && p.dot_out != nullptr && row0 + lane < p.rows) p.dot_out[row0 + lane] = dot;
-          // staging: the box handed to the TMA unit `nbufs` chunks ago must have been read before its buffer is rewritten -- waited
-          // for only now, with the chunk already in registers
-          const uint32_t sbuf = stage0 + ((nbufs == 2) ? (nstore & 1) : 0) * kBoxBytes;
-          if (lane == 0) {
-            if (nbufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            else tma_store_wait_read();
-          }
-          __syncwarp();
-          const uint32_t srow = sbuf + lane * 128;
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            sts128(srow + ((q ^ (lane & 7)) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
@@ -367,7 +375,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a,      // A [R, K]: box 64 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem, kTmemCols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
 }
 
 }  // namespace gemm
@@ -408,11 +416,11 @@ size_t g_dbg_cap = 0, g_dbg_used = 0;
 constexpr int kSmemBudget = 227 * 1024 - 1024 - gemm::kCtrlBytes;      // after the alignment slack and the control block
 
 // Shared-memory layout + grid for one problem, then the launch.  Regions (1024-aligned): B | A ring | staging | x cache.
-template <int BN, int B_MN, int MT>
+template <int BN, int B_MN, int MT, int EG = 1>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap* mc, gemm::Params p, cudaStream_t stream) {
   const int b_slice = BN * 128, a_slot = MT * gemm::kATileBytes;
   const int x_bytes = (BN == 128 && p.rope_blocks > 0 && p.rope_w > 0 && p.rope_w <= gemm::kXRows) ? ((p.rope_w * gemm::kXStride + 1023) & ~1023) : 0;
-  int stage_bytes = gemm::kEpiWarps * gemm::kBoxBytes;
+  int stage_bytes = EG * gemm::kEpiWarps * gemm::kBoxBytes;
   p.stage_bufs = 1;
   int left;
   if (p.wres) {
@@ -430,7 +438,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap* mc, 
   p.off_b = gemm::kCtrlBytes; p.off_a = p.off_b + b_bytes; p.off_stage = p.off_a + p.n_slots * a_slot; p.off_x = p.off_stage + stage_bytes;
   const size_t smem = (size_t)p.off_x + x_bytes + 1024;
   if (smem > 227 * 1024) return sam2b200::fail(SAM2B200_ERR_UNSUPPORTED, "gemm: shared memory layout does not fit");
-  cudaError_t e = cudaFuncSetAttribute(gemm::gemm_kernel<BN, B_MN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(gemm::gemm_kernel<BN, B_MN, MT, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return sam2b200::fail(SAM2B200_ERR_CUDA, cudaGetErrorString(e));
   const int sms = sm_count(), ncb = p.n_col_blocks, groups = (p.n_row_tiles + MT - 1) / MT;
   unsigned grid;
@@ -443,7 +451,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap* mc, 
     grid = (unsigned)(items < sms ? items : sms);
   }
   if (g_dbg && g_dbg_used + (size_t)grid * 32 <= g_dbg_cap) { p.dbg = g_dbg + g_dbg_used; g_dbg_used += (size_t)grid * 32; }
-  gemm::gemm_kernel<BN, B_MN, MT><<<grid, gemm::kThreads, smem, stream>>>(ma, mb, mc[0], mc[1], mc[2], p);
+  gemm::gemm_kernel<BN, B_MN, MT, EG><<<grid, gemm::threads_for(EG), smem, stream>>>(ma, mb, mc[0], mc[1], mc[2], p);
   return sam2b200::check_launch("gemm");
 }
 
@@ -506,7 +514,13 @@ int sam2b200_gemm_ex(void* out0, void* out1, void* out2, int out_width, long lon
     if (!p.wres && p.n_row_tiles > sm_count()) return b_layout ? launch<256, 1, 2>(ma, mb, mc, p, stream) : launch<256, 0, 2>(ma, mb, mc, p, stream);
     return b_layout ? launch<256, 1, 1>(ma, mb, mc, p, stream) : launch<256, 0, 1>(ma, mb, mc, p, stream);
   }
-  if (bn == 128) return b_layout ? launch<128, 1, 1>(ma, mb, mc, p, stream) : launch<128, 0, 1>(ma, mb, mc, p, stream);
+  if (bn == 128) {
+    // two epilogue groups (16 warps, four accumulators) when a CTA has several items: the drain of a 128 x 128 accumulator is a
+    // latency chain of ~1.5 us per warp, twice the MMA time -- SAM2B200_GEMM_EG1=1 keeps one group (A/B)
+    static const bool eg1 = getenv("SAM2B200_GEMM_EG1") != nullptr;
+    if (!eg1 && p.wres) return b_layout ? launch<128, 1, 1, 2>(ma, mb, mc, p, stream) : launch<128, 0, 1, 2>(ma, mb, mc, p, stream);
+    return b_layout ? launch<128, 1, 1>(ma, mb, mc, p, stream) : launch<128, 0, 1>(ma, mb, mc, p, stream);
+  }
   return b_layout ? launch<64, 1, 1>(ma, mb, mc, p, stream) : launch<64, 0, 1>(ma, mb, mc, p, stream);
 }
 

@@ -472,6 +472,7 @@ class WeightMirror:
         # fp32 copies for the attention kernels' fused output projection (bias added on the fp32 accumulator)
         self.b_eff32 = [torch.empty(256, dtype=F32, device=dev) for _ in range(nl)]
         self.qkv_bias32 = [torch.empty(768, dtype=F32, device=dev) for _ in range(nl)]    # stacked fp32 q|k|v bias (epilogue of gemm_ex)
+        self.wk_all32 = torch.empty(max(nl, 1) * 256, 64, dtype=F32, device=dev)      # cross-attention key weights of all layers, stacked (bank position gradients)
         self.wobv32 = [torch.empty(256, dtype=F32, device=dev) for _ in range(nl)]
         self.versions = None
         self.device = dev
@@ -505,6 +506,9 @@ class WeightMirror:
                         self.qkv_bias32[l][256 * j:256 * (j + 1)].copy_(self.params[l * _NPL + _LAYER_KEYS.index(kb)].detach())
                     wo, bo, wv, bv = (self.params[l * _NPL + _LAYER_KEYS.index(k)].detach()
                                       for k in ("ca.o.w", "ca.o.b", "ca.v.w", "ca.v.b"))
+                    wk = self.params[l * _NPL + _LAYER_KEYS.index("ca.k.w")].detach()
+                    if wk.shape == (256, 64):
+                        self.wk_all32[256 * l:256 * (l + 1)].copy_(wk)
                     if wv.shape != (256, 64):
                         continue
                     self.w_eff[l].copy_(torch.mm(wo, wv))
@@ -544,6 +548,30 @@ def invalidate_mirrors(module) -> None:
 def bf16_params(params):
     """bf16 views of the parameters (see WeightMirror); keyed by the identity of the first parameter."""
     return weight_mirror(params).refresh()
+
+
+_SEG_IND = {}
+
+
+def segment_indicator(dev, b, m, n_slots, hw, n_ptrs):
+    """[B * M, 64] bf16 one-hot rows: column j marks the bank segment of the row -- memory slot j (tokens [j hw, (j + 1) hw)) for
+    j < n_slots, pointer j - n_slots behind them.  S = dk^T . Ind (one sam2b200_wgrad launch) gives the key gradient summed over
+    objects and over the tokens of every segment, which is all the bank's position tensors need:
+    d tpos[j] = sum_layers S_l[:, j]^T Wk_l  (sum over rows commutes with the projection).  Cached per bank shape."""
+    key = (dev.index, b, m, n_slots, hw, n_ptrs)
+    ind = _SEG_IND.get(key)
+    if ind is None:
+        if n_slots + n_ptrs > 64:
+            raise _lib.Sam2B200Error("packed bank with more than 64 segments")
+        sp = n_slots * hw
+        t = torch.arange(m, device=dev)
+        per = (m - sp) // n_ptrs if n_ptrs else 1
+        seg = torch.where(t < sp, t // max(hw, 1), (n_slots + (t - sp) // max(per, 1)) if n_ptrs else torch.full_like(t, 63))
+        ind = torch.nn.functional.one_hot(seg, 64).to(BF16).unsqueeze(0).expand(b, m, 64).reshape(b * m, 64).contiguous()
+        if len(_SEG_IND) > 64:
+            _SEG_IND.clear()
+        _SEG_IND[key] = ind
+    return ind
 
 
 class MemoryAttentionStackFn(torch.autograd.Function):
@@ -793,7 +821,13 @@ class MemoryAttentionStackFn(torch.autograd.Function):
         last = (nl - 1) * _NPL
         g, g16 = ln_bwd(grad_out, x_fin, mean_f, rstd_f, params[nl * _NPL], None, gv[nl * _NPL], gv[nl * _NPL + 1],
                         seq_first=(b, n), dbias=gv[last + _LAYER_KEYS.index("l2.b")], drop=dsite("p_res", nl - 1, 5))
-        dmemk = torch.zeros((rm, memk.shape[1]), dtype=F32, device=dev) if need_memgrad else None
+        # Packed bank: only the position tensors want a gradient, i.e. the key-source gradient summed over objects and over the
+        # tokens of each bank segment -- S_l = dk_l^T . Ind ([256, 64] per layer, one wgrad launch on the side stream) instead of
+        # the dense [B M, 64] fp32 gradient (a [B M, 256] x [256, 64] GEMM per layer, a 58 MB zero fill and three reductions).
+        seg_mode = packed and need_memgrad and memk.shape[1] == 64 and _wgrad_ok(d, 64)
+        seg_ind = segment_indicator(dev, b, m, int(mt["bank_slots"]), int(mt["bank_hw"]), int(mt["bank_ptrs"])) if seg_mode else None
+        seg_sum = torch.zeros((nl * d, 64), dtype=F32, device=dev) if seg_mode else None
+        dmemk = torch.zeros((rm, memk.shape[1]), dtype=F32, device=dev) if (need_memgrad and not seg_mode) else None
         dmemv = torch.zeros((rm, memv.shape[1]), dtype=F32, device=dev) if need_mem else None
         per = 26
         for l in reversed(range(nl)):
@@ -882,7 +916,9 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                         torch.addmm(gv[ix["ca.k.w"]], dk2.t(), memk, out_dtype=F32, out=gv[ix["ca.k.w"]])
                     else:
                         grads[ix["ca.k.w"]] = _mm32(dk2.t(), memk)
-                    if need_memgrad:
+                    if seg_mode:
+                        wgrad_(seg_sum[l * d:(l + 1) * d], dk2, seg_ind)
+                    elif need_memgrad:
                         torch.addmm(dmemk, dk2, W["ca.k.w"], out_dtype=F32, out=dmemk)
                 side.run(key_side, q2_rot, k2_rot, memv, do64, lse2, delta, dp_bias)
                 dq2, _ = attn_bwd_v64(*args, parts=8, dbias=(gv[ix["ca.q.b"]] if (EPILOGUE_BIAS and not wb_q) else None, None), **kw)
@@ -905,7 +941,9 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                     else:
                         grads[ix["ca.k.w"]] = _mm32(dk2.t(), memk)
                         grads[ix["ca.v.w"]] = _mm32(dv2.t(), memv)
-                    if need_memgrad:
+                    if seg_mode:
+                        wgrad_(seg_sum[l * d:(l + 1) * d], dk2, seg_ind)
+                    elif need_memgrad:
                         torch.addmm(dmemk, dk2, W["ca.k.w"], out_dtype=F32, out=dmemk)
                     if need_mem:
                         torch.addmm(dmemv, dv2, W["ca.v.w"], out_dtype=F32, out=dmemv)
@@ -968,12 +1006,19 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             # d maskmem_tpos_enc rows / d pointer positions = the fp32 key-source gradient summed over tokens and objects
             ns, hw = mt["bank_slots"], mt["bank_hw"]
             sp = ns * hw
-            dk3 = dmemk.view(b, m, 64) if need_mpos else None
-            if need_tpos and ns:
-                d_tpos = dk3[:, :sp].reshape(b, ns, hw, 64).sum((0, 2))
-            if need_objpos and m > sp:
-                n_ptr = mt["bank_ptrs"]
-                d_objpos = dk3[:, sp:].reshape(b, n_ptr, (m - sp) // n_ptr, 64).sum((0, 2))
+            n_ptr = mt["bank_ptrs"]
+            if seg_mode:      # [64 segments, nl * 256] x [nl * 256, 64]: sum over layers of S_l^T Wk_l (fp32 masters)
+                d_seg = torch.mm(seg_sum.t(), weight_mirror(masters).wk_all32[:nl * d])
+                if need_tpos and ns:
+                    d_tpos = d_seg[:ns]
+                if need_objpos and m > sp:
+                    d_objpos = d_seg[ns:ns + n_ptr]
+            else:
+                dk3 = dmemk.view(b, m, 64) if need_mpos else None
+                if need_tpos and ns:
+                    d_tpos = dk3[:, :sp].reshape(b, ns, hw, 64).sum((0, 2))
+                if need_objpos and m > sp:
+                    d_objpos = dk3[:, sp:].reshape(b, n_ptr, (m - sp) // n_ptr, 64).sum((0, 2))
         else:
             if need_mpos:
                 d_mpos = permute_rows(dmemk, None, 0.0, b, m, True)

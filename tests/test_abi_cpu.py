@@ -232,3 +232,43 @@ def test_memory_encoder_drop_in_loads_the_reference_state_dict():
     if not torch.cuda.is_available():
         with pytest.raises(_lib.Sam2B200Error):
             fast(torch.zeros(1, 256, 2, 2), torch.zeros(1, 1, 32, 32))
+
+
+def test_gemm_argument_validation_needs_no_device(lib):
+    """sam2b200_gemm / gemm_ex reject malformed problems on the host (no launch, no device): widths other than 64 / k x 256,
+    K not a multiple of 64, misaligned pointers, a rotation table without its geometry, an unpaired row-dot argument."""
+    ok = dict(c=4096, ldc=256, a=8192, lda=256, b=12288, ldb=256, layout=0, R=128, K=256, No=256)
+
+    def call(**kw):
+        a = {**ok, **kw}
+        return lib.sam2b200_gemm(a["c"], a["ldc"], a["a"], a["lda"], a["b"], a["ldb"], a["layout"], a["R"], a["K"], a["No"],
+                                 kw.get("bias"), kw.get("table"), kw.get("rpi", 1), kw.get("nrope", 0), kw.get("period", 1),
+                                 kw.get("dot_rows"), kw.get("dot_out"), None)
+    for bad in (dict(No=192), dict(K=100), dict(a=8200), dict(lda=128), dict(layout=2), dict(R=0), dict(table=4096, rpi=0),
+                dict(dot_rows=4096), dict(No=64, ldc=64, dot_out=4096)):
+        assert call(**bad) == -1, bad
+        assert b"gemm" in lib.sam2b200_last_error()
+    rc = lib.sam2b200_gemm_ex(4096, None, None, 256, 256, 8192, 256, 12288, 256, 0, 128, 256, 768, None, 0, None, 1, 0, 1, 0, 0.0, None, 0,
+                              None, None, None)
+    assert rc == -1          # three outputs of width 256 announced (Nout = 768), two of them missing
+
+
+def test_segment_indicator_reproduces_the_dense_bank_position_gradient():
+    """The packed bank's position gradients: S_l = dk_l^T Ind summed per segment, then sum_l S_l^T Wk_l, equals the reference
+    route (dense d memk = sum_l dk_l Wk_l, reduced over objects and over the tokens of every slot / pointer) -- host algebra,
+    checked on CPU in fp64."""
+    from sam2_video_training_b200 import fused_stack as fs
+    torch.manual_seed(0)
+    b, ns, hw, n_ptr, per, nl = 3, 2, 5, 3, 4, 2
+    m = ns * hw + n_ptr * per
+    ind = fs.segment_indicator(torch.device("cpu"), b, m, ns, hw, n_ptr).double()
+    assert ind.shape == (b * m, 64) and torch.equal(ind.sum(1), torch.ones(b * m, dtype=torch.float64))
+    dk = [torch.randn(b * m, 256, dtype=torch.float64) for _ in range(nl)]
+    wk = [torch.randn(256, 64, dtype=torch.float64) for _ in range(nl)]
+    dense = sum(d @ w for d, w in zip(dk, wk)).view(b, m, 64)
+    want_t = dense[:, :ns * hw].reshape(b, ns, hw, 64).sum((0, 2))
+    want_p = dense[:, ns * hw:].reshape(b, n_ptr, per, 64).sum((0, 2))
+    seg = torch.cat([d.t() @ ind for d in dk], 0)                     # [nl * 256, 64]
+    got = seg.t() @ torch.cat(wk, 0)                                   # [64 segments, 64]
+    assert torch.allclose(got[:ns], want_t, atol=1e-9) and torch.allclose(got[ns:ns + n_ptr], want_p, atol=1e-9)
+    assert float(got[ns + n_ptr:].abs().max()) == 0.0

@@ -38,6 +38,7 @@ WORKLOADS = {
     "cfg4_1024px_T8_4obj_x1clip": dict(grid=64, T=8, C=4, clips=1, S=1024),
 }
 LOSS_W = {"loss_mask": 20, "loss_dice": 1, "loss_iou": 1, "loss_class": 0}
+PER_CLIP_LOSS = False      # --per-clip-loss: one criterion call per clip (the reference trainer's pattern) instead of one for the step
 # DRAM bytes (read + write) of the backward kernels of one cross-attention call at B=56, N=576, M=4060 from `ncu --set full`
 # (profiles/r1_ncu_attn_v64_cfg2_cross.csv: dK 248.0 + dQ 177.0 MB); updated whenever a new capture is committed
 TRAFFIC_CFG2_BYTES = 431.0e6
@@ -208,17 +209,28 @@ def run_step(model, crit, opt, d, bank, wl, world, fwd=None, arrivals=None):
     total = None
     if arrivals is not None:
         torch.cuda.current_stream().wait_event(arrivals[-1])
+    # the criterion over ALL clips of the step in one launch (forward_clips: one target pointer per frame); the per-clip form is
+    # what the reference trainer does (trainer.py:268) and what --per-clip-loss times
+    clips, leaves = [], []
     for ci in range(wl["clips"]):
         xs = [d["logits"][ci * T + f].requires_grad_(True) for f in range(T)]
         # per-frame IoU-head outputs are separate leaves, as the tracker produces them (one [C, 1] tensor per frame)
         ips = [v.detach().requires_grad_(True) for v in d["iou"][ci].unbind(0)]
         outs = [{"multistep_pred_multimasks_high_res": [xs[f]], "multistep_pred_ious": [ips[f]],
                  "multistep_object_score_logits": [None]} for f in range(T)]
-        losses = crit(outs, d["targets"][ci])
+        clips.append((outs, d["targets"][ci]))
+        leaves += xs
+    if PER_CLIP_LOSS:
+        for outs, tg in clips:
+            losses = crit(outs, tg)
+            losses["total_loss"].backward()
+            total = losses["total_loss"].detach() if total is None else total + losses["total_loss"].detach()
+    else:
+        losses = crit.forward_clips(clips)
         losses["total_loss"].backward()
-        total = losses["total_loss"].detach() if total is None else total + losses["total_loss"].detach()
-        for x in xs:
-            x.grad = None
+        total = losses["total_loss"].detach()
+    for x in leaves:
+        x.grad = None
     if pending is not None:
         pending.wait()
     opt.step()
@@ -643,10 +655,13 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip other_workloads / same_box_torch_gpu / the dropout leg")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host (no CUDA-graph replay)")
+    ap.add_argument("--per-clip-loss", action="store_true", help="one criterion call per clip instead of one launch for all clips of the step")
     ap.add_argument("--dropout", type=float, default=0.0,
                     help="train-mode dropout of the stack (the reference ships 0.1); default 0 = the parity configuration "
                          "SURVEY.md section 8d prescribes for the headline number")
     args = ap.parse_args()
+    global PER_CLIP_LOSS
+    PER_CLIP_LOSS = bool(args.per_clip_loss)
     wl_name, wl = args.workload, WORKLOADS[args.workload]
     if args.impl == "reference":
         return main_reference(args, wl_name, wl)
@@ -694,7 +709,8 @@ def main():
     roofline["traffic_note"] = TRAFFIC_NOTE
     if rank == 0:
         roofline["mask_loss_sweep_max"] = loss_sweep_roofline(lib, dev, pk["hbm"])
-        roofline["mask_loss"]["note"] = "in-step: %d per-clip calls of %d x %d x %d^2" % (wl["clips"], wl["T"], wl["C"], wl["S"])
+        roofline["mask_loss"]["note"] = ("in-step: %d per-clip calls of %d x %d x %d^2" % (wl["clips"], wl["T"], wl["C"], wl["S"]) if PER_CLIP_LOSS else
+                                         "in-step: ONE launch for the %d clips of the step (%d frames x %d x %d^2)" % (wl["clips"], wl["clips"] * wl["T"], wl["C"], wl["S"]))
 
     # ---------------- end to end: host buffers, H2D inside the timed region, loss read back ----------------
     e2e = None

@@ -209,6 +209,19 @@ int sam2b200_mask_loss_bwd(const float* const* logits, float* const* dlogits, co
                            long long HW, int mode, float alpha, float gamma, float inv_temp,
                            int iou_l1, int reduction_mean, sam2b200_stream_t stream);
 
+/* The same pair with ONE TARGET POINTER PER FRAME (target_ptrs: HOST array of T device pointers to [C, HW] bytes): the frames of
+ * several clips of a step -- whose targets are different tensors (sam2_video/training/trainer.py:268 calls the criterion once per
+ * batch element) -- go through one launch (up to 128 frames per launch); losses = the sum over all frames, i.e. over the clips. */
+int sam2b200_mask_loss_fwd_frames(const float* const* logits, const uint8_t* const* target_ptrs, const float* iou_pred,
+                                  const float* pos_weight, void* workspace, float* chan_sums, int* n_valid,
+                                  float* losses, int T, int C, long long HW, int mode, float alpha,
+                                  float gamma, float inv_temp, int iou_l1, int reduction_mean, sam2b200_stream_t stream);
+int sam2b200_mask_loss_bwd_frames(const float* const* logits, float* const* dlogits, const uint8_t* const* target_ptrs,
+                                  const float* iou_pred, const float* pos_weight, const float* chan_sums,
+                                  const int* n_valid, const float* grad_losses, float* diou, int T, int C,
+                                  long long HW, int mode, float alpha, float gamma, float inv_temp,
+                                  int iou_l1, int reduction_mean, sam2b200_stream_t stream);
+
 /* Backward of the six per-channel sums themselves -- what the stand-alone dice_loss / sigmoid_focal_loss of
  * sam2_video/model/losses.py:20-57 need: dlogits = coef[c][0] * d(sum_px focal)/dx + (t ? coef[c][1] : coef[c][2]) * p(1-p),
  * coef: device [T, C, 3] fp32 (coef[.][1] = d/d(sum p*t) + d/d(sum p), coef[.][2] = d/d(sum p)); no valid filter. */

@@ -53,6 +53,11 @@ _SIGNATURES = {
                                        c_float, c_float, c_int, c_int, c_void_p]),
     "sam2b200_mask_loss_bwd": (c_int, [c_void_p] * 9 + [c_int, c_int, c_longlong, c_int, c_float,
                                                          c_float, c_float, c_int, c_int, c_void_p]),
+    "sam2b200_mask_loss_fwd_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                              c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_float,
+                                              c_float, c_float, c_int, c_int, c_void_p]),
+    "sam2b200_mask_loss_bwd_frames": (c_int, [c_void_p] * 9 + [c_int, c_int, c_longlong, c_int, c_float,
+                                                                c_float, c_float, c_int, c_int, c_void_p]),
     "sam2b200_mask_loss_bwd_coef": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_float,
                                             c_float, c_float, c_void_p]),
     "sam2b200_attn_fwd_v64": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_float, c_float, c_void_p, c_uint, c_void_p]),

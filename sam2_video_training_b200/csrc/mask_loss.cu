@@ -51,19 +51,19 @@ constexpr int kBwdRounds = SAM2B200_LOSS_BWD_ROUNDS;
 constexpr int kFwdChunk = kIterPx * kItersPerRound * kFwdRounds;     // px per forward block
 constexpr int kBwdChunk = kIterPx * kItersPerRound * kBwdRounds;     // px per backward block
 static_assert(kFwdChunk / kThreads <= 255 && kBwdChunk / kThreads <= 255, "8-bit per-thread counters");
-constexpr int kMaxFrames = 64;                       // frames per launch (pointer table in params)
+constexpr int kMaxFrames = 128;                      // frames per launch (pointer tables in the kernel parameters: 2 x 1 KB + 1 KB for the backward)
 constexpr int kNumSums = 6;                          // focal|bce, p*t, p, t, inter, union
 constexpr int kRec = 8;                              // floats per block record
 
 struct FramePtrs {
   const float* logits[kMaxFrames];
+  const uint8_t* targets[kMaxFrames];   // frame f: [C, HW] bytes (frames of several clips may come from different tensors)
 };
 struct FrameOutPtrs {
   float* dlogits[kMaxFrames];
 };
 
 struct FwdParams {
-  const uint8_t* targets;      // [frames, C, HW]
   const float* pos_weight;     // [C] or null (BCE)
   const float* iou_pred;       // [tt, C] (multistep)
   float* records;              // [tt*C][nblk][kRec]
@@ -86,7 +86,7 @@ mask_loss_fwd_kernel(const __grid_constant__ FramePtrs fp, const __grid_constant
   const int f = fc / P.C, c = fc % P.C;
   const long long HW = P.HW;
   const float* __restrict__ x = fp.logits[f] + (long long)c * HW;
-  const uint8_t* __restrict__ tg = P.targets + ((long long)(P.frame0 + f) * P.C + c) * HW;
+  const uint8_t* __restrict__ tg = fp.targets[f] + (long long)c * HW;
   const long long begin = (long long)blockIdx.x * kFwdChunk;
   const long long end = (begin + kFwdChunk < HW) ? (begin + kFwdChunk) : HW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -244,7 +244,6 @@ mask_loss_fwd_kernel(const __grid_constant__ FramePtrs fp, const __grid_constant
 }
 
 struct BwdParams {
-  const uint8_t* targets;
   const float* pos_weight;
   const float* chan_sums;      // [tt*C][6]
   const int* n_valid;          // [tt]
@@ -269,7 +268,7 @@ mask_loss_bwd_kernel(const __grid_constant__ FramePtrs fp, const __grid_constant
   const long long HW = P.HW;
   const float* __restrict__ x = fp.logits[f] + (long long)c * HW;
   float* __restrict__ dx = op.dlogits[f] + (long long)c * HW;
-  const uint8_t* __restrict__ tg = P.targets + ((long long)(P.frame0 + f) * P.C + c) * HW;
+  const uint8_t* __restrict__ tg = fp.targets[f] + (long long)c * HW;
   const bool raw = P.raw_coef != nullptr;
   const float* s = raw ? nullptr : P.chan_sums + (long long)fc * kNumSums;
   const int nv = raw ? 1 : P.n_valid[f];
@@ -401,16 +400,17 @@ size_t sam2b200_mask_loss_workspace_bytes(int T, int C, long long HW) {
   return kTicketBytes + records_bytes(tt, C, HW);
 }
 
-int sam2b200_mask_loss_fwd(const float* const* logits, const uint8_t* targets, const float* iou_pred,
-                           const float* pos_weight, void* workspace, float* chan_sums, int* n_valid,
-                           float* losses, int T, int C, long long HW, int mode, float alpha,
-                           float gamma, float inv_temp, int iou_l1, int reduction_mean,
-                           cudaStream_t stream) {
+// targets: one [T, C, HW] tensor (targets_base) or one pointer per frame (target_ptrs[f] -> [C, HW]); exactly one is non-null
+static int mask_loss_fwd_impl(const float* const* logits, const uint8_t* targets_base, const uint8_t* const* target_ptrs, const float* iou_pred,
+                              const float* pos_weight, void* workspace, float* chan_sums, int* n_valid,
+                              float* losses, int T, int C, long long HW, int mode, float alpha,
+                              float gamma, float inv_temp, int iou_l1, int reduction_mean,
+                              cudaStream_t stream) {
   // mode bit 8 (SAM2B200_LOSS_TICKETS_ZEROED): the caller guarantees that the ticket region of `workspace` is zero
   // (zero-initialised once and since then only used by this function, which leaves it zeroed) -> no memset node.
   const bool tickets_zeroed = (mode & 0x100) != 0;
   mode &= 0xff;
-  if (T <= 0 || C <= 0 || HW <= 0 || !logits || !targets || !workspace || !chan_sums || !n_valid ||
+  if (T <= 0 || C <= 0 || HW <= 0 || !logits || (!targets_base) == (!target_ptrs) || !workspace || !chan_sums || !n_valid ||
       !losses || (mode == 0 && !iou_pred) || (mode != 0 && mode != 1))
     return sam2b200::fail(SAM2B200_ERR_INVALID, "mask_loss_fwd: bad arguments");
   const int nblk = fwd_blocks_per_channel(HW);
@@ -419,14 +419,15 @@ int sam2b200_mask_loss_fwd(const float* const* logits, const uint8_t* targets, c
     const int tt = (T - f0 < kMaxFrames) ? (T - f0) : kMaxFrames;
     if ((long long)tt * C > kMaxChannelsPerLaunch) return sam2b200::fail(SAM2B200_ERR_INVALID, "mask_loss_fwd: frames x channels per launch > 65535");
     FramePtrs fp;
-    int vec_ok = (HW % 4 == 0) && aligned4(targets);
+    int vec_ok = (HW % 4 == 0);
     for (int f = 0; f < tt; ++f) {
       fp.logits[f] = logits[f0 + f];
-      if (!fp.logits[f]) return sam2b200::fail(SAM2B200_ERR_INVALID, "mask_loss_fwd: null frame");
-      vec_ok = vec_ok && aligned16(fp.logits[f]);
+      fp.targets[f] = target_ptrs ? target_ptrs[f0 + f] : targets_base + (size_t)(f0 + f) * C * HW;
+      if (!fp.logits[f] || !fp.targets[f]) return sam2b200::fail(SAM2B200_ERR_INVALID, "mask_loss_fwd: null frame");
+      vec_ok = vec_ok && aligned16(fp.logits[f]) && aligned4(fp.targets[f]);
     }
     FwdParams P;
-    P.targets = targets; P.pos_weight = pos_weight; P.iou_pred = iou_pred ? iou_pred + (size_t)f0 * C : nullptr;
+    P.pos_weight = pos_weight; P.iou_pred = iou_pred ? iou_pred + (size_t)f0 * C : nullptr;
     P.chan_ticket = static_cast<int*>(workspace);
     P.done_ticket = P.chan_ticket + kMaxChannelsPerLaunch;
     P.records = reinterpret_cast<float*>(static_cast<char*>(workspace) + kTicketBytes);
@@ -454,8 +455,28 @@ int sam2b200_mask_loss_fwd(const float* const* logits, const uint8_t* targets, c
   return sam2b200::check_launch("mask_loss_fwd", launches);
 }
 
-static int mask_loss_bwd_impl(const float* const* logits, float* const* dlogits, const uint8_t* targets,
-                              const float* iou_pred, const float* pos_weight, const float* chan_sums,
+int sam2b200_mask_loss_fwd(const float* const* logits, const uint8_t* targets, const float* iou_pred,
+                           const float* pos_weight, void* workspace, float* chan_sums, int* n_valid,
+                           float* losses, int T, int C, long long HW, int mode, float alpha,
+                           float gamma, float inv_temp, int iou_l1, int reduction_mean,
+                           cudaStream_t stream) {
+  return mask_loss_fwd_impl(logits, targets, nullptr, iou_pred, pos_weight, workspace, chan_sums, n_valid, losses, T, C, HW, mode, alpha,
+                            gamma, inv_temp, iou_l1, reduction_mean, stream);
+}
+
+// The same with one target pointer per frame (target_ptrs[f] -> [C, HW] bytes): the frames of SEVERAL clips -- whose targets live in
+// different tensors -- go through one launch (up to 128 frames per launch); the result is the sum over all frames, i.e. over the clips.
+int sam2b200_mask_loss_fwd_frames(const float* const* logits, const uint8_t* const* target_ptrs, const float* iou_pred,
+                                  const float* pos_weight, void* workspace, float* chan_sums, int* n_valid,
+                                  float* losses, int T, int C, long long HW, int mode, float alpha,
+                                  float gamma, float inv_temp, int iou_l1, int reduction_mean,
+                                  cudaStream_t stream) {
+  return mask_loss_fwd_impl(logits, nullptr, target_ptrs, iou_pred, pos_weight, workspace, chan_sums, n_valid, losses, T, C, HW, mode, alpha,
+                            gamma, inv_temp, iou_l1, reduction_mean, stream);
+}
+
+static int mask_loss_bwd_impl(const float* const* logits, float* const* dlogits, const uint8_t* targets_base,
+                              const uint8_t* const* target_ptrs, const float* iou_pred, const float* pos_weight, const float* chan_sums,
                               const int* n_valid, const float* grad_losses, float* diou, const float* raw_coef, int T, int C,
                               long long HW, int mode, float alpha, float gamma, float inv_temp,
                               int iou_l1, int reduction_mean, cudaStream_t stream) {
@@ -465,16 +486,17 @@ static int mask_loss_bwd_impl(const float* const* logits, float* const* dlogits,
     const int tt = (T - f0 < kMaxFrames) ? (T - f0) : kMaxFrames;
     FramePtrs fp;
     FrameOutPtrs op;
-    int vec_ok = (HW % 4 == 0) && aligned4(targets);
+    int vec_ok = (HW % 4 == 0);
     for (int f = 0; f < tt; ++f) {
       fp.logits[f] = logits[f0 + f];
+      fp.targets[f] = target_ptrs ? target_ptrs[f0 + f] : targets_base + (size_t)(f0 + f) * C * HW;
       op.dlogits[f] = dlogits[f0 + f];
-      if (!fp.logits[f] || !op.dlogits[f])
+      if (!fp.logits[f] || !op.dlogits[f] || !fp.targets[f])
         return sam2b200::fail(SAM2B200_ERR_INVALID, "mask_loss_bwd: null frame");
-      vec_ok = vec_ok && aligned16(fp.logits[f]) && aligned16(op.dlogits[f]);
+      vec_ok = vec_ok && aligned16(fp.logits[f]) && aligned16(op.dlogits[f]) && aligned4(fp.targets[f]);
     }
     BwdParams P;
-    P.targets = targets; P.pos_weight = pos_weight; P.chan_sums = chan_sums ? chan_sums + (size_t)f0 * C * kNumSums : nullptr;
+    P.pos_weight = pos_weight; P.chan_sums = chan_sums ? chan_sums + (size_t)f0 * C * kNumSums : nullptr;
     P.n_valid = n_valid ? n_valid + f0 : nullptr; P.gout = grad_losses;
     P.iou_pred = iou_pred ? iou_pred + (size_t)f0 * C : nullptr;
     P.diou = diou ? diou + (size_t)f0 * C : nullptr;
@@ -504,7 +526,20 @@ int sam2b200_mask_loss_bwd(const float* const* logits, float* const* dlogits, co
   if (T <= 0 || C <= 0 || HW <= 0 || !logits || !dlogits || !targets || !chan_sums || !n_valid ||
       !grad_losses || (mode == 0 && (!iou_pred || !diou)) || (mode != 0 && mode != 1))
     return sam2b200::fail(SAM2B200_ERR_INVALID, "mask_loss_bwd: bad arguments");
-  return mask_loss_bwd_impl(logits, dlogits, targets, iou_pred, pos_weight, chan_sums, n_valid, grad_losses, diou, nullptr, T, C,
+  return mask_loss_bwd_impl(logits, dlogits, targets, nullptr, iou_pred, pos_weight, chan_sums, n_valid, grad_losses, diou, nullptr, T, C,
+                            HW, mode, alpha, gamma, inv_temp, iou_l1, reduction_mean, stream);
+}
+
+// Backward of sam2b200_mask_loss_fwd_frames (one target pointer per frame).
+int sam2b200_mask_loss_bwd_frames(const float* const* logits, float* const* dlogits, const uint8_t* const* target_ptrs,
+                                  const float* iou_pred, const float* pos_weight, const float* chan_sums,
+                                  const int* n_valid, const float* grad_losses, float* diou, int T, int C,
+                                  long long HW, int mode, float alpha, float gamma, float inv_temp,
+                                  int iou_l1, int reduction_mean, cudaStream_t stream) {
+  if (T <= 0 || C <= 0 || HW <= 0 || !logits || !dlogits || !target_ptrs || !chan_sums || !n_valid ||
+      !grad_losses || (mode == 0 && (!iou_pred || !diou)) || (mode != 0 && mode != 1))
+    return sam2b200::fail(SAM2B200_ERR_INVALID, "mask_loss_bwd_frames: bad arguments");
+  return mask_loss_bwd_impl(logits, dlogits, nullptr, target_ptrs, iou_pred, pos_weight, chan_sums, n_valid, grad_losses, diou, nullptr, T, C,
                             HW, mode, alpha, gamma, inv_temp, iou_l1, reduction_mean, stream);
 }
 
@@ -516,7 +551,7 @@ int sam2b200_mask_loss_bwd_coef(const float* const* logits, float* const* dlogit
                                 cudaStream_t stream) {
   if (T <= 0 || C <= 0 || HW <= 0 || !logits || !dlogits || !targets || !coef)
     return sam2b200::fail(SAM2B200_ERR_INVALID, "mask_loss_bwd_coef: bad arguments");
-  return mask_loss_bwd_impl(logits, dlogits, targets, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, coef, T, C, HW, 0,
+  return mask_loss_bwd_impl(logits, dlogits, targets, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, coef, T, C, HW, 0,
                             alpha, gamma, inv_temp, 0, 1, stream);
 }
 

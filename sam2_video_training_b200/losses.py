@@ -74,7 +74,10 @@ class _FusedMaskLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, cfg, targets_u8, pos_weight, iou_pred, *logits):
+        # targets_u8: one uint8 tensor [T, C, H, W] or a LIST of them (the clips of a step, sum of their lengths = T): the frames of
+        # all clips go through one launch with one target pointer per frame (sam2b200_mask_loss_fwd_frames)
         lib = _lib.load()
+        tlist = list(targets_u8) if isinstance(targets_u8, (list, tuple)) else None
         t = len(logits)
         c, hw = logits[0].shape[0], logits[0][0].numel()
         dev = logits[0].device
@@ -87,9 +90,15 @@ class _FusedMaskLossFn(torch.autograd.Function):
         n_valid = torch.empty(t, dtype=torch.int32, device=dev)
         losses = torch.zeros(4, dtype=torch.float32, device=dev)
         ptrs = _lib.ptr_array([x.data_ptr() for x in logits])
+        if tlist is not None:
+            tptr = [tt_[f].data_ptr() for tt_ in tlist for f in range(tt_.shape[0])]
+            assert len(tptr) == t and all(tt_.is_contiguous() and tt_.dtype == torch.uint8 for tt_ in tlist)
+            fwd_fn, targ = lib.sam2b200_mask_loss_fwd_frames, _lib.ptr_array(tptr)
+        else:
+            fwd_fn, targ = lib.sam2b200_mask_loss_fwd, targets_u8.data_ptr()
         with _ops._Timed("mask_loss_fwd", 5.0 * t * c * hw):
-            rc = lib.sam2b200_mask_loss_fwd(
-                ptrs, targets_u8.data_ptr(), iou_pred.data_ptr() if iou_pred is not None else None,
+            rc = fwd_fn(
+                ptrs, targ, iou_pred.data_ptr() if iou_pred is not None else None,
                 pos_weight.data_ptr() if pos_weight is not None else None, ws.data_ptr(),
                 chan_sums.data_ptr(), n_valid.data_ptr(), losses.data_ptr(), t, c, hw,
                 mode | (_TICKETS_ZEROED if persistent else 0),
@@ -102,14 +111,17 @@ class _FusedMaskLossFn(torch.autograd.Function):
         ctx.cfg = cfg
         ctx.shape = (t, c, hw)
         ctx.logit_shapes = [tuple(x.shape) for x in logits]
-        ctx.save_for_backward(targets_u8, pos_weight, iou_pred, chan_sums, n_valid, *logits)
+        ctx.n_target_tensors = len(tlist) if tlist is not None else 0
+        ctx.save_for_backward(*(tlist if tlist is not None else [targets_u8]), pos_weight, iou_pred, chan_sums, n_valid, *logits)
         ctx.mark_non_differentiable(chan_sums, n_valid)
         return losses, chan_sums, n_valid
 
     @staticmethod
     def backward(ctx, g_losses, _g_sums, _g_nv):
         lib = _lib.load()
-        targets_u8, pos_weight, iou_pred, chan_sums, n_valid, *logits = ctx.saved_tensors
+        nt = max(ctx.n_target_tensors, 1)
+        tlist = list(ctx.saved_tensors[:nt])
+        pos_weight, iou_pred, chan_sums, n_valid, *logits = ctx.saved_tensors[nt:]
         t, c, hw = ctx.shape
         cfg = ctx.cfg
         dev = logits[0].device
@@ -118,9 +130,14 @@ class _FusedMaskLossFn(torch.autograd.Function):
         diou = torch.empty(t, c, dtype=torch.float32, device=dev) if iou_pred is not None else None
         lp = _lib.ptr_array([x.data_ptr() for x in logits])
         dp = _lib.ptr_array([dl[f].data_ptr() for f in range(t)])
+        if ctx.n_target_tensors:
+            bwd_fn = lib.sam2b200_mask_loss_bwd_frames
+            targ = _lib.ptr_array([tt_[f].data_ptr() for tt_ in tlist for f in range(tt_.shape[0])])
+        else:
+            bwd_fn, targ = lib.sam2b200_mask_loss_bwd, tlist[0].data_ptr()
         with _ops._Timed("mask_loss_bwd", 9.0 * t * c * hw):
-            rc = lib.sam2b200_mask_loss_bwd(
-                lp, dp, targets_u8.data_ptr(), iou_pred.data_ptr() if iou_pred is not None else None,
+            rc = bwd_fn(
+                lp, dp, targ, iou_pred.data_ptr() if iou_pred is not None else None,
                 pos_weight.data_ptr() if pos_weight is not None else None, chan_sums.data_ptr(),
                 n_valid.data_ptr(), g.data_ptr(), diou.data_ptr() if diou is not None else None, t, c, hw,
                 cfg["mode"], cfg["alpha"], cfg["gamma"], cfg["inv_temp"], int(cfg["iou_l1"]),
@@ -196,9 +213,34 @@ class MultiStepMultiMasksAndIous(nn.Module):
         if v <= 0:
             raise ValueError("No valid masks")  # losses.py:161
 
+    def forward_clips(self, clips) -> Dict[str, torch.Tensor]:
+        """The criterion over SEVERAL clips of a step in one launch: `clips` = [(outs_batch, targets_batch), ...], one pair per
+        clip exactly as `forward` takes them (the reference trainer calls the criterion once per batch element,
+        trainer.py:268,303).  Returns the SUM over the clips of the dict `forward` returns for each -- what a trainer that
+        averages the batch back-propagates, up to its 1 / len(clips) -- from one kernel launch over all frames of all clips (one
+        target pointer per frame; no concatenation of the targets).  Same validity contract: a frame without any valid channel in
+        ANY clip raises "No valid masks" (per call, or deferred)."""
+        if len(clips) == 0:
+            raise ValueError("forward_clips needs at least one clip")
+        outs_all, targets_all = [], []
+        for outs_batch, targets_batch in clips:
+            assert len(outs_batch) == len(targets_batch)  # losses.py:113
+            outs_all += list(outs_batch)
+            targets_all.append(targets_batch)
+        shapes = {tuple(tb.shape[1:]) for tb in targets_all}
+        if len(shapes) != 1:
+            raise ValueError("forward_clips: every clip must have the same [C, H, W]")
+        return self._forward_frames(outs_all, targets_all)
+
     def forward(self, outs_batch: List[Dict], targets_batch: torch.Tensor) -> Dict[str, torch.Tensor]:
         assert len(outs_batch) == len(targets_batch)  # losses.py:113
-        _require_cuda(targets_batch, "targets_batch")
+        return self._forward_frames(outs_batch, [targets_batch])
+
+    def _forward_frames(self, outs_batch: List[Dict], targets_list: List[torch.Tensor]) -> Dict[str, torch.Tensor]:
+        multi = len(targets_list) > 1
+        targets_batch = targets_list[0]          # shape reference ([C, H, W] is the same in every clip)
+        for tb in targets_list:
+            _require_cuda(tb, "targets_batch")
         t = len(outs_batch)
         n_steps = None
         for outs in outs_batch:
@@ -216,8 +258,9 @@ class MultiStepMultiMasksAndIous(nn.Module):
             if self.pred_obj_scores:
                 raise NotImplementedError("pred_obj_scores with M > 1 masks per channel (the reference itself fails to index "
                                           "object_score_logits with its [N, M] valid mask, losses.py:169-170)")
-            targets_batch = targets_batch.repeat_interleave(n_masks, dim=1)
-        tu8 = _targets_u8(targets_batch)
+            targets_list = [tb.repeat_interleave(n_masks, dim=1) for tb in targets_list]
+            targets_batch = targets_list[0]
+        tu8 = [_targets_u8(tb) for tb in targets_list] if multi else _targets_u8(targets_batch)
         cfg = dict(mode=_MODE_MULTISTEP, alpha=float(self.focal_alpha), gamma=float(self.focal_gamma),
                    inv_temp=1.0 / self.logit_temperature, iou_l1=bool(self.iou_use_l1_loss),
                    reduction_mean=True)

@@ -969,6 +969,50 @@ def test_loss_frames_are_used_in_place(dev):
     assert float(a["total_loss"]) == float(b["total_loss"])
 
 
+@pytest.mark.parametrize("n_clips,t,c,s", [(8, 10, 7, 96), (3, 30, 2, 40), (5, 30, 1, 24), (2, 3, 4, 250)])
+def test_loss_over_several_clips_in_one_launch(dev, n_clips, t, c, s):
+    """forward_clips: the frames of all clips of a step through ONE launch (one target pointer per frame; 80 frames = the
+    cfg2 step, 90 and 150 frames = more than the old 64-frame table, 150 = two sub-launches) equals the sum of the per-clip calls
+    -- loss values to fp32 round-off, gradients w.r.t. every frame's logits and IoU predictions bit for bit."""
+    from sam2_video_training_b200.losses import MultiStepMultiMasksAndIous
+    g = torch.Generator().manual_seed(n_clips * 100 + t)
+    crit = MultiStepMultiMasksAndIous(dict(W_FOCAL), supervise_all_iou=True, iou_use_l1_loss=True)
+    clips, leaves = [], []
+    for ci in range(n_clips):
+        logits = (torch.randn(t, c, 1, s, s, generator=g) * 3).to(dev)
+        targets = (torch.rand(t, c, s, s, generator=g) > 0.6).to(dev)
+        iou = torch.rand(t, c, 1, generator=g).to(dev)
+        xs = [logits[f].clone().requires_grad_(True) for f in range(t)]
+        ips = [iou[f].clone().requires_grad_(True) for f in range(t)]
+        outs = [{"multistep_pred_multimasks_high_res": [xs[f]], "multistep_pred_ious": [ips[f]],
+                 "multistep_object_score_logits": [None]} for f in range(t)]
+        clips.append((outs, targets))
+        leaves.append((xs, ips))
+    ref = None
+    for outs, targets in clips:
+        o = crit(outs, targets)
+        o["total_loss"].backward()
+        ref = {k: float(v) for k, v in o.items()} if ref is None else {k: ref[k] + float(v) for k, v in o.items()}
+    want = [[x.grad.clone() for x in xs] + [i.grad.clone() for i in ips] for xs, ips in leaves]
+    for xs, ips in leaves:
+        for v in xs + ips:
+            v.grad = None
+    got = crit.forward_clips(clips)
+    got["total_loss"].backward()
+    for k in ("loss_mask", "loss_dice", "loss_iou", "total_loss"):
+        assert abs(float(got[k]) - ref[k]) <= 2e-6 * abs(ref[k]), (k, float(got[k]), ref[k])
+    for (xs, ips), w in zip(leaves, want):
+        for v, wv in zip(xs + ips, w):
+            assert torch.equal(v.grad, wv)
+    # the validity contract covers every clip
+    bad_t = clips[-1][1].clone()
+    bad_t[t - 1] = False
+    with pytest.raises(ValueError, match="No valid masks"):
+        crit.forward_clips(clips[:-1] + [(clips[-1][0], bad_t)])
+    with pytest.raises(ValueError):
+        crit.forward_clips(clips[:1] + [(clips[1][0], clips[1][1][:, :, : s // 2])])
+
+
 @pytest.mark.parametrize("multimask", [True, False])
 def test_functional_losses_match_reference_formulas(dev, multimask):
     """dice_loss / sigmoid_focal_loss / iou_loss keep the reference's signatures and values (losses.py:20-76); the

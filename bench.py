@@ -590,8 +590,10 @@ def measure_workload(wl_name, wl, model, crit, opt, lib, dev, world, rank, steps
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
+    t_host0 = time.perf_counter()
     for _ in range(steps):
         run_step(model, crit, opt, d, banks, wl, world, fwd=run_model)
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / steps     # host time to ENQUEUE a step (no synchronisation inside)
     ev1.record()
     barrier()
     crit.raise_if_invalid()          # the reference's "No valid masks" contract, checked once outside the timed region
@@ -640,7 +642,7 @@ def measure_workload(wl_name, wl, model, crit, opt, lib, dev, world, rank, steps
                               "unit": "GB/s", "frac": (loss_by / (loss_ms * 1e-3) / 1e9 / pk["hbm"]) if loss_ms else None,
                               "bytes_per_px": "5 fwd + 9 bwd"},
                 "whole_step_tflops": algorithmic_flops(wl) / (ms_per_step * 1e-3) / 1e12}
-    return dict(ms_per_step=ms_per_step, clocks=clk, eager_ms=eager_ms, launches=int(launches), fam=fam, roofline=roofline,
+    return dict(ms_per_step=ms_per_step, clocks=clk, eager_ms=eager_ms, host_enqueue_ms=host_enqueue_ms, launches=int(launches), fam=fam, roofline=roofline,
                 host=host, d=d, banks=banks, run_model=run_model)
 
 
@@ -700,7 +702,7 @@ def main():
                          barrier, pk, want_clocks=(rank == 0))
     ms_per_step, clk, host, d, banks, run_model = r["ms_per_step"], r["clocks"], r["host"], r["d"], r["banks"], r["run_model"]
     roofline, fam = r["roofline"], r["fam"]
-    r_launches, eager_ms_headline = r["launches"], r["eager_ms"]
+    r_launches, eager_ms_headline, host_enqueue_ms = r["launches"], r["eager_ms"], r["host_enqueue_ms"]
     frames_per_step = wl["T"] * wl["clips"]
     value = world * frames_per_step / (ms_per_step * 1e-3)
     # dram__bytes_read.sum + dram__bytes_write.sum of the backward kernels of ONE cross-attention call at the largest shape of
@@ -825,7 +827,7 @@ def main():
                        "algorithmic_tflop_per_step": algorithmic_flops(wl) / 1e12},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(r_launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "kernel_families_ms_per_step": {k: v["ms"] / args.steps for k, v in fam.items()},
-            "ms_per_step_host_launched": eager_ms_headline, "cuda_graphs": not args.no_graphs,
+            "ms_per_step_host_launched": eager_ms_headline, "host_enqueue_ms_per_step": host_enqueue_ms, "cuda_graphs": not args.no_graphs,
         }
         line.update(extras)
         print(json.dumps(line), flush=True)

@@ -160,6 +160,12 @@ int sam2b200_colsum(int mode, const float* in_f32, void* io_bf16, const void* h_
                     long long rows, int C, long long ld, float scale /* mode 1: 1/(1-p) of the dropout after the ReLU */,
                     sam2b200_stream_t stream);
 
+/* Parameter gradients of the folded cross-attention projection ca = out64 (Wo Wv)^T + (Wo bv + bo) of the raw-memory path (autograd
+ * of out_proj(v_proj(.)), sam2_video/model/modeling/sam/transformer.py:279,308-309): with G = dca^T out64 [256, 64], g = colsum(dca),
+ * g_rs (= g without attention dropout): dWo += G Wv^T + g_rs (x) bv, dWv += Wo^T G, dbo += g, dbv += Wo^T g_rs.  All fp32, in place. */
+int sam2b200_fold_grads(const float* G, const float* g, const float* g_rs, const float* Wo, const float* Wv, const float* bv,
+                        float* dWo, float* dWv, float* dbo, float* dbv, sam2b200_stream_t stream);
+
 /* Row permutation between the module's seq-first [L, B, C] tensors and the stack's batch-first [B, L, C] rows with fused
  * add / scale / cast (C = 256 or 64; memory_attention.py:140-148, :75-76 and the transposes of the input gradients):
  * inverse 0: out[b,l] = scale * (a[l,b] + alpha2 * a2[l,b]), out2[b,l] = scale * a[l,b]; inverse 1: the other way.

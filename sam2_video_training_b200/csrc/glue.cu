@@ -382,6 +382,65 @@ int ln_bwd_blocks_per_sm() {
   return v;
 }
 
+// Parameter gradients of the FOLDED cross-attention projection ca = out64 (Wo Wv)^T + (Wo bv + bo)   (fused_stack.py, raw-memory path):
+// given G = d/d(Wo Wv) = dca^T out64 [256, 64], g = colsum(dca) [256] and g_rs (= g without attention dropout),
+//   dWo [256, 256] += G Wv^T + g_rs (x) bv      dWv [256, 64] += Wo^T G      dbo [256] += g      dbv [64 | 256] += Wo^T g_rs
+// Four products of at most 256 x 256 x 64 (17 MFLOP in all): one launch instead of the nine tiny ATen / cuBLAS launches per layer and
+// frame (outer product, two SIMT SGEMMs, GEMV, four adds).  Block b: row b of dWo (thread j = column j), row b of dWv (threads 0..63)
+// and element b of dbo / dbv.  Wv / bv: the fp32 master weights of v_proj ([256, 64] / [256]); Wo [256, 256].
+__global__ void __launch_bounds__(256)
+fold_grads_kernel(const float* __restrict__ G, const float* __restrict__ g, const float* __restrict__ g_rs, const float* __restrict__ Wo,
+                  const float* __restrict__ Wv, const float* __restrict__ bv, float* __restrict__ dWo, float* __restrict__ dWv,
+                  float* __restrict__ dbo, float* __restrict__ dbv) {
+  __shared__ float g_row[64];           // G[b, :]
+  __shared__ float wo_col[256];         // Wo[:, b]
+  __shared__ float red[8];
+  __shared__ float part4[256];
+  const int b = blockIdx.x, j = threadIdx.x;
+  if (j < 64) g_row[j] = G[b * 64 + j];
+  wo_col[j] = Wo[j * 256 + b];
+  __syncthreads();
+  // dWo[b, j] += sum_k G[b, k] Wv[j, k] + g_rs[b] bv[j]
+  {
+    const float4* wv = reinterpret_cast<const float4*>(Wv + j * 64);
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 w = wv[k];
+      acc += g_row[4 * k] * w.x + g_row[4 * k + 1] * w.y + g_row[4 * k + 2] * w.z + g_row[4 * k + 3] * w.w;
+    }
+    dWo[b * 256 + j] += acc + g_rs[b] * bv[j];
+  }
+  // dWv[b, c] += sum_i Wo[i, b] G[i, c]      (thread j: column c = j % 64, rows i = (j / 64) * 64 .. + 63; coalesced reads of G rows)
+  {
+    const int c = j & 63, i0 = (j >> 6) * 64;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < 64; i += 4) {
+      a0 += wo_col[i0 + i] * G[(i0 + i) * 64 + c];
+      a1 += wo_col[i0 + i + 1] * G[(i0 + i + 1) * 64 + c];
+      a2 += wo_col[i0 + i + 2] * G[(i0 + i + 2) * 64 + c];
+      a3 += wo_col[i0 + i + 3] * G[(i0 + i + 3) * 64 + c];
+    }
+    part4[j] = (a0 + a1) + (a2 + a3);
+  }
+  __syncthreads();
+  if (j < 64) dWv[b * 64 + j] += (part4[j] + part4[64 + j]) + (part4[128 + j] + part4[192 + j]);
+  // dbv[b] += sum_i Wo[i, b] g_rs[i];   dbo[b] += g[b]
+  float part = wo_col[j] * g_rs[j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((j & 31) == 0) red[j >> 5] = part;
+  __syncthreads();
+  if (j == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    dbv[b] += t;
+    dbo[b] += g[b];
+  }
+}
+
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
@@ -502,6 +561,16 @@ int sam2b200_dropout_mask(unsigned char* out, long long index0, long long n, flo
     return sam2b200::fail(SAM2B200_ERR_INVALID, "dropout_mask: bad arguments");
   dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(out, index0, n, sam2b200::make_dropout(drop_seed, drop_site, drop_p));
   return sam2b200::check_launch("dropout_mask");
+}
+
+// Gradients of the folded cross-attention projection (see fold_grads_kernel): all fp32, accumulated in place.  G [256, 64], g / g_rs [256]
+// (g_rs = g unless attention dropout is on), Wo [256, 256], Wv [256, 64], bv [256]; dWo [256, 256], dWv [256, 64], dbo / dbv [256].
+int sam2b200_fold_grads(const float* G, const float* g, const float* g_rs, const float* Wo, const float* Wv, const float* bv,
+                        float* dWo, float* dWv, float* dbo, float* dbv, cudaStream_t stream) {
+  if (!G || !g || !g_rs || !Wo || !Wv || !bv || !dWo || !dWv || !dbo || !dbv || !aligned16(Wv))
+    return sam2b200::fail(SAM2B200_ERR_INVALID, "fold_grads: bad arguments");
+  fold_grads_kernel<<<256, 256, 0, stream>>>(G, g, g_rs, Wo, Wv, bv, dWo, dWv, dbo, dbv);
+  return sam2b200::check_launch("fold_grads");
 }
 
 }  // extern "C"

@@ -301,6 +301,10 @@ def direct_grads_possible(bucket, params) -> bool:
 # cuBLAS addmm + the RoPE pass inside the graph-replayed step (56.9 vs 56.6 ms) and loses for the K = 64 memory-bank
 # projections (profiles/r1_proj_rope_bench.txt).  SAM2B200_PROJ_KERNEL=1 routes the K = 256 projections through it,
 # SAM2B200_PROJ_KERNEL_K64=1 the K = 64 ones as well.
+# The folded projection's parameter gradients (four [256 x 64]-sized fp32 products + accumulations) in one launch of sam2b200_fold_grads
+# instead of nine tiny ATen / cuBLAS launches: correct (the stack parity tests pass with it) but 0.2-0.3 ms per cfg2 step SLOWER in two A/B
+# runs (its 256 blocks take SMs from the main stream; the tiny launches hide on the side stream) -> opt-in, SAM2B200_FOLD_KERNEL=1.
+NO_FOLD_KERNEL = not bool(os.environ.get("SAM2B200_FOLD_KERNEL"))
 NO_FOLD = bool(os.environ.get("SAM2B200_NO_FOLD"))  # A/B switch: v_proj and out_proj of the raw-memory cross-attention as two GEMMs
 NO_V64 = bool(os.environ.get("SAM2B200_NO_V64"))    # A/B switch: cross-attention on the projected 256-d values (with the dV kernel)
 NO_PROJ_KERNEL = not bool(os.environ.get("SAM2B200_PROJ_KERNEL"))
@@ -880,6 +884,18 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                             G = wgrad_(torch.zeros((d, 64), dtype=F32, device=dev), dca, o64.view(r, 64))
                         else:
                             G = _mm32(dca.t(), o64.view(r, 64))
+                        if not NO_FOLD_KERNEL and all(P[k].dtype == F32 and P[k].is_contiguous() for k in ("ca.o.w", "ca.v.w", "ca.v.b")):
+                            # the four small products + accumulations in ONE launch (sam2b200_fold_grads, csrc/glue.cu)
+                            if not direct:
+                                grads[ix["ca.o.w"]] = torch.zeros((d, d), dtype=F32, device=dev)
+                                grads[ix["ca.v.w"]] = torch.zeros((d, 64), dtype=F32, device=dev)
+                            d_wo = gv[ix["ca.o.w"]] if direct else grads[ix["ca.o.w"]]
+                            d_wv = gv[ix["ca.v.w"]] if direct else grads[ix["ca.v.w"]]
+                            rc = _lib.load().sam2b200_fold_grads(G.data_ptr(), g_bo.data_ptr(), g_rs.data_ptr(), P["ca.o.w"].data_ptr(),
+                                                                 P["ca.v.w"].data_ptr(), P["ca.v.b"].data_ptr(), d_wo.data_ptr(), d_wv.data_ptr(),
+                                                                 gv[ix["ca.o.b"]].data_ptr(), gv[ix["ca.v.b"]].data_ptr(), _stream(dev))
+                            _lib.check(rc, "sam2b200_fold_grads")
+                            return
                         d_wo = torch.addmm(torch.outer(g_rs, P["ca.v.b"]), G, P["ca.v.w"].t())
                         d_wv = torch.mm(P["ca.o.w"].t(), G)
                         gv[ix["ca.o.b"]].add_(g_bo)

@@ -310,6 +310,13 @@ int sam2b200_gemm_ex(void* out0, void* out1, void* out2, int out_width, long lon
                      int rows_per_item, int n_rope_rows, int period, int relu, float drop_p, const unsigned long long* drop_seed,
                      unsigned drop_site, const float* dot_rows, float* dot_out, cudaStream_t stream);
 
+/* Two such products that share the long operand, in one pass over it: c [256, ldc] += a^T b and c2 [256, ldc2] += a^T b2 with a [R, 256],
+ * b, b2 [R, 64].  Used for the cross-attention key projection's weight gradient (transformer.py:214, b = the key source) together with the
+ * per-segment sums of the key gradient (b2 = one-hot bank-segment indicator) that the packed bank's position tensors need
+ * (sam2_video/model/modeling/sam2_base.py:618-625, 667-671: maskmem_tpos_enc / obj_ptr_tpos_proj).  dbias as above. */
+int sam2b200_wgrad2(float* c, long long ldc, float* c2, long long ldc2, const void* a, long long lda, const void* b, long long ldb,
+                    const void* b2, long long ldb2, long long R, float* dbias, cudaStream_t stream);
+
 /* ---- LayerNorm + projection (+ RoPE | ReLU) in one kernel (csrc/lnproj.cu) ------------------------------------------
  * The head of every pre-norm block of MemoryAttentionLayer (sam2_video/model/modeling/memory_attention.py:58-64, 66-81,
  * 95-97 with the projections of sam2_video/model/modeling/sam/transformer.py:277-302):

@@ -84,6 +84,8 @@ _SIGNATURES = {
     "sam2b200_gemm_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_longlong, c_int,
                                  c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_uint, c_void_p, c_void_p, c_void_p]),
     "sam2b200_fold_grads": (c_int, [c_void_p] * 11),
+    "sam2b200_wgrad2": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong,
+                                c_longlong, c_void_p, c_void_p]),
     "sam2b200_mlp_dh": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p]),
     "sam2b200_bank_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                      c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -47,7 +47,7 @@ struct Shared {
   static constexpr int kLoadBytes = (TM / 64 + NT / 64) * kBoxBytes;               // 64 KB (256 x 256) | 40 KB (256 x 64) | 32 KB (128 x 128)
   static constexpr int kStageBytes = kLoadBytes + (kBias ? kBoxBytes : 0);         // + the box of ones
   static constexpr int kStages = (kStageBytes >= 65536) ? 3 : 4;
-  static constexpr int kAccStride = (NT == 64) ? 128 : NT;                         // TMEM columns between the two accumulators
+  static constexpr int kAccStride = (NT == 64) ? 128 : ((TM == 256 && NT == 128) ? 256 : NT);   // TMEM columns between the two accumulators (NT = 128 carries 16 bias columns)
   alignas(1024) uint8_t tiles[kStages][kStageBytes];     // [A box 0..3 | B box 0..NT/64-1 | ones]
   alignas(8) uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
@@ -63,6 +63,8 @@ struct Params {
   long long rows_per_split; // multiple of 64
   int n_tiles_m, n_tiles_n; // output tiles
   float* dbias;             // [Mo] fp32 or nullptr: += column sums of A
+  float* c2;                // two-operand form (TM = 256, NT = 128): output columns 64..127 go to c2 [Mo, ldc2] (B2's product), else nullptr
+  long long ldc2;
 };
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
@@ -73,6 +75,7 @@ template <int TM, int NT>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap map_a,   // A [R, Mo] bf16, box 64 cols x 64 rows
              const __grid_constant__ CUtensorMap map_b,   // B [R, No] bf16, box 64 cols x 64 rows
+             const __grid_constant__ CUtensorMap map_b2,  // two-operand form: second B [R, 64] (columns 64..127 of the tile), else = map_b
              const Params p) {
   using Sh = Shared<TM, NT>;
   constexpr int kTileM = TM;
@@ -87,7 +90,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a,   // A [R, Mo] bf16, box
   const int nslab = (int)((r_end - r_begin + kSlab - 1) / kSlab);      // >= 1 by construction of the grid
   constexpr int kStages = Sh::kStages;
   constexpr int kAccStride = Sh::kAccStride;
-  constexpr uint32_t kTmemCols = Sh::kBias ? 256 : 512;     // 2 x 128 (NT = 64) | 144 (NT = 128) | 2 x 256
+  constexpr uint32_t kTmemCols = (Sh::kBias && !(TM == 256 && NT == 128)) ? 256 : 512;     // 2 x 128 (NT = 64) | 144 (NT = 128) | 2 x 256
   const bool do_bias = Sh::kBias && p.dbias != nullptr && tn == 0;
 
   if (threadIdx.x == 0) {
@@ -96,7 +99,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a,   // A [R, Mo] bf16, box
     mbar_init(&sh.ones_ready, kEpiWarps * 32);
     fence_barrier_init();
   }
-  if (warp == 8 && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_b); }
+  if (warp == 8 && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_b); prefetch_tmap(&map_b2); }
   if (warp == 9) { tmem_alloc(&sh.tmem_base, kTmemCols); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
@@ -116,8 +119,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a,   // A [R, Mo] bf16, box
         for (int c = 0; c < kTileM / 64; ++c)
           tma_load_3d(&sh.tiles[s][c * kBoxBytes], &map_a, &sh.full[s], tm * kTileM + c * 64, row0, 0);
 #pragma unroll
-        for (int c = 0; c < NT / 64; ++c)
-          tma_load_3d(&sh.tiles[s][(kTileM / 64 + c) * kBoxBytes], &map_b, &sh.full[s], tn * NT + c * 64, row0, 0);
+        for (int c = 0; c < NT / 64; ++c) {
+          if (p.c2 != nullptr)   // two operands of width 64: box c comes from operand c
+            tma_load_3d(&sh.tiles[s][(kTileM / 64 + c) * kBoxBytes], c == 0 ? &map_b : &map_b2, &sh.full[s], 0, row0, 0);
+          else
+            tma_load_3d(&sh.tiles[s][(kTileM / 64 + c) * kBoxBytes], &map_b, &sh.full[s], tn * NT + c * 64, row0, 0);
+        }
       }
       __syncwarp();
     }
@@ -168,7 +175,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a,   // A [R, Mo] bf16, box
 #pragma unroll
     for (int h = 0; h < kAcc; ++h) {
       const long long crow = (long long)tm * kTileM + h * 128 + quarter * 32 + lane;
-      float* dst = p.c + crow * p.ldc + (long long)tn * NT + half * kColsPerWarp;
+      float* dst = (p.c2 != nullptr && half == 1) ? p.c2 + crow * p.ldc2        // two-operand form: this warp's 64 columns are the second product
+                                                  : p.c + crow * p.ldc + (long long)tn * NT + half * kColsPerWarp;
 #pragma unroll 1
       for (int cc = 0; cc < kColsPerWarp / 32; ++cc) {
         uint32_t o[32];
@@ -214,7 +222,7 @@ int make_rows_map(CUtensorMap* map, const void* base, long long rows, long long 
 }
 
 template <int TM, int NT>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const wgrad::Params& p, int splits, cudaStream_t stream) {
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const wgrad::Params& p, int splits, cudaStream_t stream) {
   const size_t smem = sizeof(wgrad::Shared<TM, NT>) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
@@ -223,7 +231,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const wgrad::Params& p,
     attr_set = true;
   }
   dim3 grid((unsigned)(p.n_tiles_m * p.n_tiles_n), (unsigned)splits, 1);
-  wgrad::wgrad_kernel<TM, NT><<<grid, wgrad::kThreads, smem, stream>>>(ma, mb, p);
+  wgrad::wgrad_kernel<TM, NT><<<grid, wgrad::kThreads, smem, stream>>>(ma, mb, mb2, p);
   return sam2b200::check_launch("wgrad");
 }
 
@@ -266,9 +274,40 @@ int sam2b200_wgrad(float* c, long long ldc, const void* a, long long lda, const 
   long long slabs_per = (slabs + splits - 1) / splits;
   splits = (slabs + slabs_per - 1) / slabs_per;            // no empty split
   p.rows_per_split = slabs_per * wgrad::kSlab;
-  if (nt == 64) return launch<256, 64>(ma, mb, p, (int)splits, stream);
-  if (small) return launch<128, 128>(ma, mb, p, (int)splits, stream);
-  return launch<256, 256>(ma, mb, p, (int)splits, stream);
+  if (nt == 64) return launch<256, 64>(ma, mb, mb, p, (int)splits, stream);
+  if (small) return launch<128, 128>(ma, mb, mb, p, (int)splits, stream);
+  return launch<256, 256>(ma, mb, mb, p, (int)splits, stream);
+}
+
+// Two products that share the long operand in ONE pass over it:  c [256, ldc] += a^T . b   and   c2 [256, ldc2] += a^T . b2, with a [R, 256],
+// b and b2 [R, 64] (bf16; row strides lda / ldb / ldb2).  The cross-attention key projection's weight gradient (b = the key source) and
+// the per-segment sums of the key gradient (b2 = the one-hot segment indicator of the packed bank: its position tensors' gradients,
+// fused_stack.segment_indicator) both contract dk [B M, 256] over its rows.  dbias (nullable, [256]) += column sums of a.
+int sam2b200_wgrad2(float* c, long long ldc, float* c2, long long ldc2, const void* a, long long lda, const void* b, long long ldb,
+                    const void* b2, long long ldb2, long long R, float* dbias, cudaStream_t stream) {
+  if (!c || !c2 || !a || !b || !b2 || R <= 0 || R >= (1LL << 31) || ldc < 64 || ldc2 < 64 || lda < 256 || ldb < 64 || ldb2 < 64 ||
+      (lda % 8) || (ldb % 8) || (ldb2 % 8) || (ldc % 4) || (ldc2 % 4) ||
+      ((reinterpret_cast<uintptr_t>(c) | reinterpret_cast<uintptr_t>(c2) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
+        reinterpret_cast<uintptr_t>(b2)) & 15))
+    return sam2b200::fail(SAM2B200_ERR_INVALID, "wgrad2: bad arguments (a [R, 256], b / b2 [R, 64], 16-byte aligned rows)");
+  CUtensorMap ma, mb, mb2;
+  int rc;
+  if ((rc = make_rows_map(&ma, a, R, 256, lda))) return rc;
+  if ((rc = make_rows_map(&mb, b, R, 64, ldb))) return rc;
+  if ((rc = make_rows_map(&mb2, b2, R, 64, ldb2))) return rc;
+  wgrad::Params p{};
+  p.c = c; p.ldc = ldc; p.c2 = c2; p.ldc2 = ldc2; p.rows = R; p.dbias = dbias; p.n_tiles_m = 1; p.n_tiles_n = 1;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long slabs = (R + wgrad::kSlab - 1) / wgrad::kSlab;
+  long long splits = sms;
+  if (splits > slabs / 4) splits = slabs / 4;
+  if (splits < 1) splits = 1;
+  long long slabs_per = (slabs + splits - 1) / splits;
+  splits = (slabs + slabs_per - 1) / slabs_per;
+  p.rows_per_split = slabs_per * wgrad::kSlab;
+  return launch<256, 128>(ma, mb, mb2, p, (int)splits, stream);
 }
 
 }  // extern "C"

@@ -237,6 +237,17 @@ def gemm(a16, w16, nn=False, bias=None, table=None, rows_per_item=1, n_rope_rows
     return out if dot is None else (out, dot)
 
 
+def wgrad2_(c32, c2_32, a16, b16, b2_16, dbias=None):
+    """c32 [256, 64] += a16^T @ b16 and c2_32 [256, 64] += a16^T @ b2_16 in ONE pass over a16 [R, 256] (sam2b200_wgrad2); dbias += colsum(a16)."""
+    r = a16.shape[0]
+    assert a16.shape == (r, 256) and b16.shape == (r, 64) and b2_16.shape == (r, 64) and c32.shape == (256, 64) and c2_32.shape == (256, 64)
+    assert all(t.dtype == BF16 and t.stride(1) == 1 for t in (a16, b16, b2_16)) and all(t.dtype == F32 and t.stride(1) == 1 for t in (c32, c2_32))
+    rc = _lib.load().sam2b200_wgrad2(c32.data_ptr(), c32.stride(0), c2_32.data_ptr(), c2_32.stride(0), a16.data_ptr(), a16.stride(0),
+                                     b16.data_ptr(), b16.stride(0), b2_16.data_ptr(), b2_16.stride(0), r,
+                                     dbias.data_ptr() if dbias is not None else None, _stream(a16.device))
+    _lib.check(rc, "sam2b200_wgrad2")
+
+
 def mlp_dh(dm16, w2_16, h16, scale=1.0, dbias=None):
     """dh = (dm @ W2) * (h > 0) * scale in one tcgen05 GEMM with the ReLU / hidden-dropout backward in its epilogue; dbias
     (fp32 [F], optional) += column sums of dh = the bias gradient of linear1, taken from the tile in registers."""
@@ -332,6 +343,7 @@ def bias_grad_(gbias, dx16):
 # vs 14.9 us for [256 x 256], 17.6 vs 20.8 us for the stacked q|k|v, 29 vs 35 us for the memory-key projection); the two MLP weights
 # ([256 x 2048], [2048 x 256]) stay on cuBLAS, which is 5-15 % faster there (profiles/r2_wgrad_bench.txt).  A/B: SAM2B200_NO_WGRAD=1.
 NO_WGRAD = bool(os.environ.get("SAM2B200_NO_WGRAD"))
+NO_WGRAD2 = bool(os.environ.get("SAM2B200_NO_WGRAD2"))   # A/B: separate launches for the key weight gradient and the bank-segment sums
 
 
 WGRAD_MLP = bool(os.environ.get("SAM2B200_WGRAD_MLP"))   # A/B: the two MLP weight gradients on sam2b200_wgrad as well
@@ -924,10 +936,13 @@ class MemoryAttentionStackFn(torch.autograd.Function):
                         bias_grad_(gv[ix["ca.k.b"]], dk2)
                     if _wgrad_ok(d, 64):
                         gb_k = gv[ix["ca.k.b"]] if wb else None
-                        if direct:
-                            wgrad_(gv[ix["ca.k.w"]], dk2, memk, gb_k)
-                        else:
-                            grads[ix["ca.k.w"]] = wgrad_(torch.zeros((d, 64), dtype=F32, device=dev), dk2, memk, gb_k)
+                        if not direct:
+                            grads[ix["ca.k.w"]] = torch.zeros((d, 64), dtype=F32, device=dev)
+                        gkw = gv[ix["ca.k.w"]] if direct else grads[ix["ca.k.w"]]
+                        if seg_mode and not NO_WGRAD2:      # weight gradient + per-segment sums of dk in ONE pass over dk (116 MB at cfg2)
+                            wgrad2_(gkw, seg_sum[l * d:(l + 1) * d], dk2, memk, seg_ind, gb_k)
+                            return
+                        wgrad_(gkw, dk2, memk, gb_k)
                     elif direct:
                         torch.addmm(gv[ix["ca.k.w"]], dk2.t(), memk, out_dtype=F32, out=gv[ix["ca.k.w"]])
                     else:

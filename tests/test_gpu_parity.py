@@ -657,6 +657,29 @@ def test_wgrad_kernel(dev, r, mo, no):
         assert rel_l2(db, want_b) < 2e-5, rel_l2(db, want_b)
 
 
+@pytest.mark.parametrize("r", [200, 4096, 56 * 4060])
+def test_wgrad_two_products_in_one_pass(dev, r):
+    """sam2b200_wgrad2: c += a^T b and c2 += a^T b2 (+ column sums of a) from ONE pass over the long operand a [R, 256] -- the key
+    projection's weight gradient together with the per-segment sums of the key gradient (one-hot b2) -- against fp64 products."""
+    from sam2_video_training_b200 import fused_stack as fs
+    g = torch.Generator(device="cuda").manual_seed(r)
+    a = torch.randn(r, 256, device=dev, generator=g).to(torch.bfloat16)
+    b = torch.randn(r, 64, device=dev, generator=g).to(torch.bfloat16)
+    seg = torch.randint(0, 23, (r,), device=dev, generator=g)
+    b2 = torch.nn.functional.one_hot(seg, 64).to(torch.bfloat16)
+    c0, c20, db0 = (torch.randn(256, 64, device=dev, generator=g), torch.randn(512, 64, device=dev, generator=g)[128:384],
+                    torch.randn(256, device=dev, generator=g))
+    c, c2buf, db = c0.clone(), torch.zeros(512, 64, device=dev), db0.clone()
+    c2 = c2buf[128:384]
+    c2.copy_(c20)
+    fs.wgrad2_(c, c2, a, b, b2, db)
+    torch.cuda.synchronize()
+    assert rel_l2(c, c0.double() + a.double().t() @ b.double()) < 2e-5
+    assert rel_l2(c2, c20.double() + a.double().t() @ b2.double()) < 2e-5
+    assert rel_l2(db, db0.double() + a.double().sum(0)) < 2e-5
+    assert float(c2buf[:128].abs().max()) == 0.0 and float(c2buf[384:].abs().max()) == 0.0       # canary rows around the strided output
+
+
 @pytest.mark.parametrize("r,k,no,nn", [(200, 256, 256, True), (32256, 256, 256, True), (1000, 768, 256, True), (3000, 2048, 256, True),
                                        (2500, 2048, 256, False), (40000, 256, 64, True), (33, 64, 256, False), (700, 256, 64, False),
                                        (19000, 64, 256, False)])

@@ -481,7 +481,11 @@ int sam2b200_gemm_ex(void* out0, void* out1, void* out2, int out_width, long lon
                      long long ldb, int b_layout, long long R, int K, int Nout, const float* bias, int rope_cols, const float* table,
                      int rows_per_item, int n_rope_rows, int period, int relu, float drop_p, const unsigned long long* drop_seed,
                      unsigned drop_site, const float* dot_rows, float* dot_out, cudaStream_t stream) {
-  const int bn = Nout == 64 ? 64 : (rope_cols > 0 ? 128 : 256);      // rotated outputs: 128-column blocks = the x / y halves of a head
+  // rotated outputs: 128-column blocks = the x / y halves of a head.  SAM2B200_GEMM_BN128=1 (experiment, NOT faster: the linear1 head
+  // takes 46.7 instead of 37.3 us -- twice the A traffic from L2 outweighs the second epilogue group): 128-column blocks with two
+  // epilogue groups for every resident-weight problem wider than 256
+  static const bool bn128_all = getenv("SAM2B200_GEMM_BN128") != nullptr;
+  const int bn = Nout == 64 ? 64 : ((rope_cols > 0 || (bn128_all && K <= 256 && Nout > 256)) ? 128 : 256);
   const int n_out = out_width > 0 ? Nout / out_width : 0;
   if (!out0 || !a || !b || R <= 0 || R > 0x7fffffffLL - 256 || K <= 0 || (K % 64) || Nout <= 0 || (Nout % bn) || Nout > 2048 ||
       out_width <= 0 || (out_width % bn) || n_out * out_width != Nout || n_out > 3 || (n_out > 1 && !out1) || (n_out > 2 && !out2) ||

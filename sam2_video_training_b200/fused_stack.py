@@ -584,8 +584,8 @@ def segment_indicator(dev, b, m, n_slots, hw, n_ptrs):
         per = (m - sp) // n_ptrs if n_ptrs else 1
         seg = torch.where(t < sp, t // max(hw, 1), (n_slots + (t - sp) // max(per, 1)) if n_ptrs else torch.full_like(t, 63))
         ind = torch.nn.functional.one_hot(seg, 64).to(BF16).unsqueeze(0).expand(b, m, 64).reshape(b * m, 64).contiguous()
-        if len(_SEG_IND) > 64:
-            _SEG_IND.clear()
+        while len(_SEG_IND) >= 64:          # bounded cache; a backward that uses an indicator keeps its own reference (ctx), so an
+            _SEG_IND.pop(next(iter(_SEG_IND)))   # evicted entry that a captured CUDA graph still reads stays alive with that graph
         _SEG_IND[key] = ind
     return ind
 
@@ -842,6 +842,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
         # the dense [B M, 64] fp32 gradient (a [B M, 256] x [256, 64] GEMM per layer, a 58 MB zero fill and three reductions).
         seg_mode = packed and need_memgrad and memk.shape[1] == 64 and _wgrad_ok(d, 64)
         seg_ind = segment_indicator(dev, b, m, int(mt["bank_slots"]), int(mt["bank_hw"]), int(mt["bank_ptrs"])) if seg_mode else None
+        ctx._seg_ind_keepalive = seg_ind      # a CUDA-graph capture of this backward reads it at every replay
         seg_sum = torch.zeros((nl * d, 64), dtype=F32, device=dev) if seg_mode else None
         dmemk = torch.zeros((rm, memk.shape[1]), dtype=F32, device=dev) if (need_memgrad and not seg_mode) else None
         dmemv = torch.zeros((rm, memv.shape[1]), dtype=F32, device=dev) if need_mem else None

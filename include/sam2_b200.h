@@ -152,6 +152,12 @@ int sam2b200_ln_bwd(const void* dy_bf16, const float* dy_f32, const float* x, co
                     const float* gamma, const float* g_in, float* g_out, void* g_out_bf16, float* dgamma, float* dbeta,
                     float* dbias, void* workspace, long long rows, int tr_b, int tr_n, float drop_p,
                     const unsigned long long* drop_seed, unsigned drop_site, sam2b200_stream_t stream);
+/* The same in two separately launchable stages (stages: bit 0 = row pass, bit 1 = fold of the per-block partial sums into dgamma / dbeta /
+ * dbias): the fold feeds parameter gradients only and may be enqueued on another stream behind an event. */
+int sam2b200_ln_bwd_stages(const void* dy_bf16, const float* dy_f32, const float* x, const float* mean, const float* rstd,
+                           const float* gamma, const float* g_in, float* g_out, void* g_out_bf16, float* dgamma, float* dbeta,
+                           float* dbias, void* workspace, long long rows, int tr_b, int tr_n, float drop_p,
+                           const unsigned long long* drop_seed, unsigned drop_site, int stages, sam2b200_stream_t stream);
 size_t sam2b200_colsum_workspace_bytes(long long rows, int C);
 /* Bias gradients (what autograd's sum over rows produces for nn.Linear):
  * mode 0: in_f32 [R,C] -> io_bf16 (cast) and colsum += column sums; mode 1: io_bf16 *= (h_bf16 > 0) in

@@ -40,6 +40,7 @@ _SIGNATURES = {
     "sam2b200_ln_fwd": (c_int, [c_void_p] * 9 + [c_longlong, c_float, c_int, c_int, c_float, c_void_p, c_uint, c_void_p]),
     "sam2b200_ln_bwd_workspace_bytes": (c_size_t, [c_longlong]),
     "sam2b200_ln_bwd": (c_int, [c_void_p] * 13 + [c_longlong, c_int, c_int, c_float, c_void_p, c_uint, c_void_p]),
+    "sam2b200_ln_bwd_stages": (c_int, [c_void_p] * 13 + [c_longlong, c_int, c_int, c_float, c_void_p, c_uint, c_int, c_void_p]),
     "sam2b200_colsum_workspace_bytes": (c_size_t, [c_longlong, c_int]),
     "sam2b200_colsum": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int,
                                 c_longlong, c_float, c_void_p]),

@@ -470,21 +470,39 @@ size_t sam2b200_ln_bwd_workspace_bytes(long long rows) {
 // g_out = g_in + dLN/dx; dgamma += ..., dbeta += ... (accumulated into the given fp32 buffers).
 // Exactly one of dy_bf16 / dy_f32 is non-NULL.
 // g_out_bf16 / dbias (optional, both or neither): bf16 copy of g_out for the next GEMMs and dbias += its column sums.
-int sam2b200_ln_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* mean, const float* rstd,
-                    const float* gamma, const float* g_in, float* g_out, void* g_out_bf16, float* dgamma, float* dbeta,
-                    float* dbias, void* workspace, long long rows, int tr_b, int tr_n, float drop_p,
-                    const unsigned long long* drop_seed, unsigned drop_site, cudaStream_t stream) {
+// stages: bit 0 = the row pass (g_out, g_out_bf16, per-block partial sums in `workspace`), bit 1 = the fold of the partial sums into
+// dgamma / dbeta / dbias.  The fold only feeds parameter gradients, so a caller may enqueue it on another stream (after an event
+// behind the row pass) and keep the 24-CTA kernel off the critical path of the residual-stream gradient.
+int sam2b200_ln_bwd_stages(const void* dy_bf16, const float* dy_f32, const float* x, const float* mean, const float* rstd,
+                           const float* gamma, const float* g_in, float* g_out, void* g_out_bf16, float* dgamma, float* dbeta,
+                           float* dbias, void* workspace, long long rows, int tr_b, int tr_n, float drop_p,
+                           const unsigned long long* drop_seed, unsigned drop_site, int stages, cudaStream_t stream) {
   if ((!dy_bf16) == (!dy_f32) || !x || !mean || !rstd || !gamma || !g_out || !dgamma || !dbeta || !workspace ||
-      rows <= 0 || (!g_out_bf16) != (!dbias) || drop_p < 0.f || drop_p >= 1.f)
+      rows <= 0 || (!g_out_bf16) != (!dbias) || drop_p < 0.f || drop_p >= 1.f || (stages & 3) == 0)
     return sam2b200::fail(SAM2B200_ERR_INVALID, "ln_bwd: bad arguments");
   const int nblk = grid_for_rows(rows, 8 * 8, ln_bwd_blocks_per_sm());
   const int nrow = g_out_bf16 ? 3 : 2;
   float* part = static_cast<float*>(workspace);
-  ln_bwd_kernel<<<nblk, 256, 0, stream>>>((const __nv_bfloat16*)dy_bf16, dy_f32, x, mean, rstd, gamma, g_in, g_out,
-                                          (__nv_bfloat16*)g_out_bf16, part, rows, tr_b, tr_n,
-                                          sam2b200::make_dropout(drop_seed, drop_site, drop_p));
-  partial_reduce_add_kernel<<<(nrow * kD + 31) / 32, 256, 0, stream>>>(part, nblk, nrow * kD, dgamma, dbeta, kD, dbias);
-  return sam2b200::check_launch("ln_bwd", 2);
+  int launches = 0;
+  if (stages & 1) {
+    ln_bwd_kernel<<<nblk, 256, 0, stream>>>((const __nv_bfloat16*)dy_bf16, dy_f32, x, mean, rstd, gamma, g_in, g_out,
+                                            (__nv_bfloat16*)g_out_bf16, part, rows, tr_b, tr_n,
+                                            sam2b200::make_dropout(drop_seed, drop_site, drop_p));
+    ++launches;
+  }
+  if (stages & 2) {
+    partial_reduce_add_kernel<<<(nrow * kD + 31) / 32, 256, 0, stream>>>(part, nblk, nrow * kD, dgamma, dbeta, kD, dbias);
+    ++launches;
+  }
+  return sam2b200::check_launch("ln_bwd", launches);
+}
+
+int sam2b200_ln_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* mean, const float* rstd,
+                    const float* gamma, const float* g_in, float* g_out, void* g_out_bf16, float* dgamma, float* dbeta,
+                    float* dbias, void* workspace, long long rows, int tr_b, int tr_n, float drop_p,
+                    const unsigned long long* drop_seed, unsigned drop_site, cudaStream_t stream) {
+  return sam2b200_ln_bwd_stages(dy_bf16, dy_f32, x, mean, rstd, gamma, g_in, g_out, g_out_bf16, dgamma, dbeta, dbias, workspace, rows, tr_b, tr_n,
+                                drop_p, drop_seed, drop_site, 3, stream);
 }
 
 size_t sam2b200_colsum_workspace_bytes(long long rows, int C) {

@@ -69,9 +69,11 @@ def ln_fwd(x, res, gamma, beta, want_f32_seq_first=None, eps=1e-5, drop=None):
     return y, x_new, mean, rstd
 
 
-def ln_bwd(dy, x, mean, rstd, gamma, g_in, dgamma, dbeta, seq_first=None, dbias=None, drop=None):
+def ln_bwd(dy, x, mean, rstd, gamma, g_in, dgamma, dbeta, seq_first=None, dbias=None, drop=None, side=None):
     """Returns g_out (fp32) or, with dbias, (g_out, bf16 copy of g_out) and dbias += column sums of the copy.
-    drop = (p, seed, site): the copy is the gradient of a branch that went through dropout -> masked and scaled."""
+    drop = (p, seed, site): the copy is the gradient of a branch that went through dropout -> masked and scaled.
+    side (a _SideStream): the fold of the per-block partial sums into dgamma / dbeta / dbias -- parameter gradients only -- is enqueued
+    on the side stream instead of sitting (24 CTAs, ~7 us) on the critical path of the residual-stream gradient."""
     lib = _lib.load()
     rows = x.shape[0]
     dev = x.device
@@ -80,13 +82,19 @@ def ln_bwd(dy, x, mean, rstd, gamma, g_in, dgamma, dbeta, seq_first=None, dbias=
     ws = torch.empty(lib.sam2b200_ln_bwd_workspace_bytes(rows) // 4, dtype=F32, device=dev)
     tb, tn = seq_first if seq_first is not None else (0, 0)
     is16 = dy.dtype == BF16
-    rc = lib.sam2b200_ln_bwd(dy.data_ptr() if is16 else None, None if is16 else dy.data_ptr(), x.data_ptr(),
-                             mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
-                             g_in.data_ptr() if g_in is not None else None, g_out.data_ptr(),
-                             g16.data_ptr() if g16 is not None else None, dgamma.data_ptr(), dbeta.data_ptr(),
-                             dbias.data_ptr() if dbias is not None else None, ws.data_ptr(), rows, tb, tn, *_drop(drop),
-                             _stream(dev))
-    _lib.check(rc, "sam2b200_ln_bwd")
+    def call(stages):
+        rc = lib.sam2b200_ln_bwd_stages(dy.data_ptr() if is16 else None, None if is16 else dy.data_ptr(), x.data_ptr(),
+                                        mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                        g_in.data_ptr() if g_in is not None else None, g_out.data_ptr(),
+                                        g16.data_ptr() if g16 is not None else None, dgamma.data_ptr(), dbeta.data_ptr(),
+                                        dbias.data_ptr() if dbias is not None else None, ws.data_ptr(), rows, tb, tn, *_drop(drop),
+                                        stages, _stream(dev))
+        _lib.check(rc, "sam2b200_ln_bwd")
+    if side is not None and side.enabled and not NO_LN_FOLD_ON_SIDE:
+        call(1)
+        side.run(lambda: call(2), ws, dgamma, dbeta, dbias)
+    else:
+        call(3)
     return g_out if dbias is None else (g_out, g16)
 
 
@@ -393,6 +401,7 @@ NO_FUSED_OUT_PROJ = bool(os.environ.get("SAM2B200_NO_FUSED_OUT_PROJ"))   # A/B s
 LNPROJ_FUSED = bool(os.environ.get("SAM2B200_LNPROJ_FUSED"))
 NO_LNPROJ = bool(os.environ.get("SAM2B200_NO_LNPROJ"))     # A/B switch: ln_fwd + cuBLAS addmm + RoPE pass instead of sam2b200_ln_proj
 NO_MLP_KERNEL = bool(os.environ.get("SAM2B200_NO_MLP_KERNEL"))     # A/B switch: cuBLAS GEMM + separate ReLU-backward pass
+NO_LN_FOLD_ON_SIDE = bool(os.environ.get("SAM2B200_NO_LN_FOLD_ON_SIDE"))   # A/B: LayerNorm-backward parameter folds on the main stream
 NO_SIDE_STREAM = bool(os.environ.get("SAM2B200_NO_SIDE_STREAM"))   # A/B switch: everything on one stream
 _SIDE_STREAMS = {}
 
@@ -836,7 +845,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
         # bias gradient of the projection in front of it: no separate cast + column-sum pass
         last = (nl - 1) * _NPL
         g, g16 = ln_bwd(grad_out, x_fin, mean_f, rstd_f, params[nl * _NPL], None, gv[nl * _NPL], gv[nl * _NPL + 1],
-                        seq_first=(b, n), dbias=gv[last + _LAYER_KEYS.index("l2.b")], drop=dsite("p_res", nl - 1, 5))
+                        seq_first=(b, n), dbias=gv[last + _LAYER_KEYS.index("l2.b")], drop=dsite("p_res", nl - 1, 5), side=side)
         # Packed bank: only the position tensors want a gradient, i.e. the key-source gradient summed over objects and over the
         # tokens of each bank segment -- S_l = dk_l^T . Ind ([256, 64] per layer, one wgrad launch on the side stream) instead of
         # the dense [B M, 64] fp32 gradient (a [B M, 256] x [256, 64] GEMM per layer, a 58 MB zero fill and three reductions).
@@ -868,7 +877,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             fold = mt["fold"]
             g_bo = torch.zeros(d, dtype=F32, device=dev) if fold else gv[ix["ca.o.b"]]    # colsum(dca), needed on its own when folded
             g, dca = ln_bwd(dy3, x2, mean3, rstd3, P["n3.w"], g, gv[ix["n3.w"]], gv[ix["n3.b"]], dbias=g_bo,
-                            drop=dsite("p_res", l, 3))
+                            drop=dsite("p_res", l, 3), side=side)
             # ---- cross attention backward
             if not fold:
                 acc_w(ix["ca.o.w"], dca.t(), o2.view(r, d))
@@ -987,7 +996,7 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             if not EPILOGUE_BIAS and not wb_q:
                 side.run(lambda dq2=dq2, gb=gv[ix["ca.q.b"]]: bias_grad_(gb, dq2), dq2)
             g, dsa = ln_bwd(dy2, x1, mean2, rstd2, P["n2.w"], g, gv[ix["n2.w"]], gv[ix["n2.b"]], dbias=gv[ix["sa.o.b"]],
-                            drop=dsite("p_res", l, 2))
+                            drop=dsite("p_res", l, 2), side=side)
             # ---- self attention backward
             acc_w(ix["sa.o.w"], dsa.t(), o.view(r, d))
             do = linear_dgrad(dsa, W["sa.o.w"])
@@ -1023,9 +1032,9 @@ class MemoryAttentionStackFn(torch.autograd.Function):
             dy1 = linear_dgrad(dqkv, wqkv_all[l])            # stacked [768, 256] weights: contraction over 768, fp32 accumulation
             if l > 0:
                 g, g16 = ln_bwd(dy1, x0, mean1, rstd1, P["n1.w"], g, gv[ix["n1.w"]], gv[ix["n1.b"]],
-                                dbias=gv[base - _NPL + _LAYER_KEYS.index("l2.b")], drop=dsite("p_res", l - 1, 5))
+                                dbias=gv[base - _NPL + _LAYER_KEYS.index("l2.b")], drop=dsite("p_res", l - 1, 5), side=side)
             else:
-                g = ln_bwd(dy1, x0, mean1, rstd1, P["n1.w"], g, gv[ix["n1.w"]], gv[ix["n1.b"]])
+                g = ln_bwd(dy1, x0, mean1, rstd1, P["n1.w"], g, gv[ix["n1.w"]], gv[ix["n1.b"]], side=side)
         side.join()
         # ---- unpack input gradients
         d_curr = d_pos = d_mem = d_mpos = None

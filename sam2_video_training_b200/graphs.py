@@ -15,6 +15,8 @@ Usage:  fast = GraphedMemoryAttention(memory_attention)   # same call signature 
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -85,13 +87,17 @@ class _Captured:
             torch.cuda.synchronize()
             pool = torch.cuda.graph_pool_handle()
             self.fwd, self.bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            # Experiment (SAM2B200_GRAPH_PRIORITY=1, NOT faster: 40.61 / 40.83 vs 40.49 / 40.70 ms per cfg2 step): capture on a high-priority
+            # stream, so that the kernel nodes of the critical path outrank the side stream's weight-gradient work
+            cap = torch.cuda.Stream(device=dev, priority=-1) if os.environ.get("SAM2B200_GRAPH_PRIORITY") else None
+            kw = dict(pool=pool) if cap is None else dict(pool=pool, stream=cap)
             with torch.no_grad():
-                with torch.cuda.graph(self.fwd, pool=pool):
+                with torch.cuda.graph(self.fwd, **kw):
                     args = build()
                     self.ctx = _Ctx(needs(args))
                     self.static_out = fn.forward(self.ctx, *args)
                 self.static_gout = torch.zeros_like(self.static_out)
-                with torch.cuda.graph(self.bwd, pool=pool):
+                with torch.cuda.graph(self.bwd, **kw):
                     self.static_grads = fn.backward(self.ctx, self.static_gout)
         finally:
             _ops.PROFILE = saved_profile

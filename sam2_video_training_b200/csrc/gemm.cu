@@ -147,6 +147,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a,      // A [R, K]: box 64 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // programmatic dependent launch: everything above touched no global memory; the kernel behind this one may start its own set-up
+  // now, and this one waits here for the kernel in front of it (whose output is an operand of this GEMM) to be complete
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t tmem = sh.tmem_base;
   const int ksteps = p.ksteps;
   const Schedule sched(p, MT);
@@ -451,7 +455,15 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap* mc, 
     grid = (unsigned)(items < sms ? items : sms);
   }
   if (g_dbg && g_dbg_used + (size_t)grid * 32 <= g_dbg_cap) { p.dbg = g_dbg + g_dbg_used; g_dbg_used += (size_t)grid * 32; }
-  gemm::gemm_kernel<BN, B_MN, MT, EG><<<grid, gemm::threads_for(EG), smem, stream>>>(ma, mb, mc[0], mc[1], mc[2], p);
+  static const bool pdl = getenv("SAM2B200_NO_PDL") == nullptr;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(gemm::threads_for(EG)); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm::gemm_kernel<BN, B_MN, MT, EG>, ma, mb, mc[0], mc[1], mc[2], p);
+  if (le != cudaSuccess) return sam2b200::fail(SAM2B200_ERR_CUDA, cudaGetErrorString(le));
   return sam2b200::check_launch("gemm");
 }
 

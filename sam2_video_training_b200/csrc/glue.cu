@@ -51,6 +51,9 @@ ln_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ res
               float eps, int tr_b, int tr_n, const sam2b200::Dropout drop) {
   // drop: inverted dropout on the residual branch, x' = x + dropout(res) (memory_attention.py:64,81,99);
   // element index = row * 256 + column
+  // programmatic dependent launch: the next kernel of the stream may start its set-up; this one waits for the one in front of it
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -114,6 +117,8 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ 
   // residual-stream gradient) is not masked, its bf16 copy for the branch is.
   // g16 (optional): bf16 copy of g_out -- the operand of the next GEMMs of the backward chain -- and a third partial
   // row with its column sums (the bias gradient of the projection whose output gradient g_out is).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // programmatic dependent launch (see ln_fwd_kernel)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float4* gp = reinterpret_cast<const float4*>(gamma + lane * 8);
   const float4 g0 = gp[0], g1 = gp[1];
@@ -457,9 +462,10 @@ int sam2b200_ln_fwd(const float* x, const void* res_bf16, float* x_out, const fl
       drop_p >= 1.f || rows * kD >= (1LL << 32))
     return sam2b200::fail(SAM2B200_ERR_INVALID, "ln_fwd: bad arguments");
   const long long blocks = (rows * 32 + 255) / 256;
-  ln_fwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, (const __nv_bfloat16*)res_bf16, x_out, gamma, beta,
+  if (sam2b200::launch_pdl(ln_fwd_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, x, (const __nv_bfloat16*)res_bf16, x_out, gamma, beta,
                                                        (__nv_bfloat16*)y_bf16, y_f32, mean, rstd, rows, eps, tr_b, tr_n,
-                                                       sam2b200::make_dropout(drop_seed, drop_site, drop_p));
+                                                       sam2b200::make_dropout(drop_seed, drop_site, drop_p)) != cudaSuccess)
+    return sam2b200::fail(SAM2B200_ERR_CUDA, "ln_fwd: launch failed");
   return sam2b200::check_launch("ln_fwd");
 }
 
@@ -485,9 +491,10 @@ int sam2b200_ln_bwd_stages(const void* dy_bf16, const float* dy_f32, const float
   float* part = static_cast<float*>(workspace);
   int launches = 0;
   if (stages & 1) {
-    ln_bwd_kernel<<<nblk, 256, 0, stream>>>((const __nv_bfloat16*)dy_bf16, dy_f32, x, mean, rstd, gamma, g_in, g_out,
+    if (sam2b200::launch_pdl(ln_bwd_kernel, dim3(nblk), dim3(256), 0, stream, (const __nv_bfloat16*)dy_bf16, dy_f32, x, mean, rstd, gamma, g_in, g_out,
                                             (__nv_bfloat16*)g_out_bf16, part, rows, tr_b, tr_n,
-                                            sam2b200::make_dropout(drop_seed, drop_site, drop_p));
+                                            sam2b200::make_dropout(drop_seed, drop_site, drop_p)) != cudaSuccess)
+      return sam2b200::fail(SAM2B200_ERR_CUDA, "ln_bwd: launch failed");
     ++launches;
   }
   if (stages & 2) {

@@ -87,6 +87,8 @@ dh_kernel(const __grid_constant__ CUtensorMap map_dm,     // dm  [R, 256]  bf16,
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();      // programmatic dependent launch: nothing above touched global memory
+  pdl_wait();
   const uint32_t tmem = sh.tmem_base;
 
   if (warp == 8) {
@@ -259,7 +261,8 @@ int sam2b200_mlp_dh(const void* dm, const void* w2, const void* h, void* dh, flo
   if (e != cudaSuccess) return sam2b200::fail(SAM2B200_ERR_CUDA, cudaGetErrorString(e));
   mlp::Params p{F / mlp::kBlockN, (int)R, scale, dbias};
   const unsigned grid = (unsigned)((R + mlp::kBlockM - 1) / mlp::kBlockM);
-  mlp::dh_kernel<<<grid, mlp::kThreads, smem, stream>>>(map_dm, map_w2, map_h, map_dh, p);
+  if (sam2b200::launch_pdl(mlp::dh_kernel, dim3(grid), dim3(mlp::kThreads), smem, stream, map_dm, map_w2, map_h, map_dh, p) != cudaSuccess)
+    return sam2b200::fail(SAM2B200_ERR_CUDA, "mlp_dh: launch failed");
   return sam2b200::check_launch("mlp_dh");
 }
 

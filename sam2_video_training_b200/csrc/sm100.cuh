@@ -120,6 +120,14 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   return r;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (barrier set-up, TMEM allocation, descriptor
+// prefetch) while the kernel in front of it in the stream is still draining its last wave; pdl_wait() blocks until that kernel has
+// completed and its memory is visible -- it must precede EVERY global-memory access of the dependent.  pdl_launch_dependents() in the
+// primary lets the next kernel's CTAs be scheduled as soon as SM resources free up.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(

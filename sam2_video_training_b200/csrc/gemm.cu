@@ -15,16 +15,20 @@
 //                      q|k|v projection (K = 768), of out_proj / q_proj (K = 256) and of the folded Wo Wv (BN = 64).
 //
 // Blackwell mapping: RESIDENT CTAs (one per SM) walk 128-row x BN-column tiles of C (BN = 256; 128 for rotated outputs -- the x and
-// y halves of a head; 64); A k-slices of 64 arrive by TMA in a 4-stage ring shared by consecutive tiles (the producer runs ahead into
-// the next tile while the current one drains).  K <= 256: the CTA keeps ONE column block whose weight slices are loaded once and stay
+// y halves of a head; 64); A k-slices of 64 arrive by TMA in a ring shared by consecutive tiles (the producer runs ahead into the next
+// tile while the current one drains; ring depth, staging boxes and the table cache are laid out per problem by the host).  K <= 256: the CTA keeps ONE column block whose weight slices are loaded once and stay
 // in shared memory (a first version re-streamed them per tile and was bound by L2 -> SM traffic: 387 MB for the linear1 head at cfg2);
-// K > 256: weight slices travel with the A slices.  Both operands are read from shared memory (SS-mode tcgen05.mma, M = 128, N = BN,
+// K > 256: weight slices travel with the A slices and, with more row tiles than SMs, two row tiles (two accumulators) share every
+// weight slice.  Both operands are read from shared memory (SS-mode tcgen05.mma, M = 128, N = BN,
 // K = 16 per instruction), the B tile K-major (NT) or MN-major (NN) straight from the TMA boxes -- no transposed weight copy exists
 // anywhere; two BN-column fp32 accumulators in tensor memory alternate between tiles, so the epilogue of tile i (tcgen05.ld -> bias /
 // rotation / ReLU -> bf16 -> swizzled staging box -> TMA store per warp) overlaps the MMAs of tile i + 1.  The x half of the axial
 // rotation table (<= 64 rows x 64 pairs) is cached in shared memory with a padded row stride: a warp's 32 rows have up to 32 different
 // x positions, i.e. 32 different L1 lines per load instruction when read from global memory; the y half (<= 3 rows per warp) is read
-// through L1.  HBM-bound at every shape of the stack: algorithmic bytes = 2 (R K + K Nout + R Nout).
+// through L1.  128-column blocks run TWO epilogue groups of 8 warps on four accumulators (the drain of a 128 x 128 accumulator is a
+// latency chain of ~1.5 us per warp).  The kernel is launched with programmatic dependent launch: its set-up overlaps the tail of the
+// kernel in front of it.  HBM-bound at every shape of the stack: algorithmic bytes = 2 (R K + K Nout + R Nout); measured it is bound
+// by the accumulator drain (profiles/r2_timeline_gemm.txt).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>

@@ -6,11 +6,16 @@ sam2_video/model/modeling/memory_attention.py:119-169 in its shipped configurati
   * keeps the residual stream in fp32 and fuses residual-add + LayerNorm + bf16 cast (ln_fwd),
     LayerNorm backward + residual-gradient add (ln_bwd), cast + bias-gradient (colsum) into single
     passes of the hand-written kernels in csrc/glue.cu,
-  * runs RoPE + attention forward/backward in the tcgen05 kernels (csrc/attn_kernels.cuh),
-  * leaves only the dense projections / MLP to cuBLAS (torch.mm / addmm, bf16 in, fp32 accumulate;
-    weight gradients are produced directly in fp32 with out_dtype),
-  * packs `memory + pos` once per call instead of once per layer (memory_attention.py:75-76).
-PyTorch is used for device memory, streams and the cuBLAS calls only.
+  * runs the attention forward (with the output projection in its epilogue) and backward in the tcgen05 kernels of
+    csrc/attn*.cuh -- the cross-attention on the raw 64-d memory features,
+  * runs every dense GEMM but the two MLP weight gradients on our own tcgen05 kernels with the neighbouring element-wise work in
+    their epilogues: sam2b200_gemm / gemm_ex (csrc/gemm.cu: projections with bias, RoPE, ReLU + dropout; input gradients; the
+    Delta row sums), sam2b200_wgrad / wgrad2 (csrc/wgrad.cu: weight gradients accumulated in place, bias gradients, bank-segment
+    sums), sam2b200_mlp_dh (csrc/mlp.cu),
+  * packs `memory + pos` once per call instead of once per layer (memory_attention.py:75-76), or takes the bank already packed
+    (memory_bank.PackedBank),
+  * puts everything that only feeds parameter gradients on a second stream.
+PyTorch is used for device memory, streams and the few remaining library calls.
 """
 from __future__ import annotations
 

@@ -301,6 +301,35 @@ def test_fused_stack_raw_memory_cross_attention_vs_oracle(dev, monkeypatch):
         assert cosine(p.grad, po[nm].grad) > GRAD_COS_TOL, nm
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_half_precision_inputs_as_under_mixed_precision_training(dev, dtype):
+    """configs/best.yaml:103 trains with 16-bit mixed precision: the tracker then hands MemoryAttention half-precision features.  The
+    drop-in takes them (no fp32 copy is required from the caller), returns the fp32 output the reference's autocast LayerNorm returns,
+    and gradients of the inputs' own dtype -- identical to the run on the same values given as fp32."""
+    from sam2_video_training_b200.modeling.memory_attention import build_memory_attention
+    torch.manual_seed(4)
+    model = build_memory_attention(dropout=0.0).to(dev).train()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    n, b, p = 64, 3, 8
+    m = 2 * n + p
+    mk = lambda *s: torch.randn(*s, device=dev, generator=g).to(dtype)
+    curr, cpos, mem, mpos = mk(n, b, 256), mk(n, b, 256), mk(m, b, 64), mk(m, b, 64)
+    go = torch.randn(n, b, 256, device=dev, generator=g)
+    outs, grads = [], []
+    for cast in (lambda t: t, lambda t: t.float()):
+        c, mp = cast(curr).clone().requires_grad_(True), cast(mpos).clone().requires_grad_(True)
+        model.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=dtype):
+            o = model(c, cast(mem), cast(cpos), mp, p)
+        o.backward(go)
+        outs.append(o.detach())
+        grads.append((c.grad, mp.grad, torch.cat([q.grad.flatten() for q in model.parameters()])))
+    assert outs[0].dtype == torch.float32 and torch.equal(outs[0], outs[1])
+    assert grads[0][0].dtype == dtype and grads[0][1].dtype == dtype and grads[1][0].dtype == torch.float32
+    assert rel_l2(grads[0][0], grads[1][0]) < 6e-3 and rel_l2(grads[0][1], grads[1][1]) < 6e-3      # the rounding of the gradient to 16 bits
+    assert rel_l2(grads[0][2], grads[1][2]) < 1e-5
+
+
 def test_fused_and_composed_paths_agree(dev):
     from sam2_video_training_b200.modeling.memory_attention import build_memory_attention
     model = build_memory_attention().to(dev).eval()

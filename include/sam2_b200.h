@@ -309,6 +309,10 @@ int sam2b200_gemm(void* c, long long ldc, const void* a, long long lda, const vo
  * Nout = 64 or a multiple of 256 up to 2048, split over n_out = Nout / out_width <= 3 outputs [R, out_width] (q | k | v); the leading
  * rope_cols columns (multiple of 256) rotated as above (transformer.py:296-302); relu != 0: max(., 0) on the biased accumulator, then
  * inverted dropout (drop_p, element index row * Nout + column) -- linear1 + activation + dropout of memory_attention.py:95-97. */
+/* host only (no device): kernel variant and shared-memory layout sam2b200_gemm_ex would use on a GPU with `sms` SMs.  out[8] = {column
+ * block width, row tiles per item, epilogue groups, ring slots, staging boxes per warp, grid, resident weights (0 | 1), dynamic shared
+ * memory bytes}; returns 0 or the layout error. */
+int sam2b200_gemm_plan(long long R, int K, int Nout, int rope_cols, int period, int sms, long long* out);
 /* debug aid: per-CTA %globaltimer phase stamps of the following sam2b200_gemm* launches (32 x u64 per CTA); NULL = off */
 long long sam2b200_gemm_debug_timeline(void* buf, long long n_u64);
 int sam2b200_gemm_ex(void* out0, void* out1, void* out2, int out_width, long long ldc, const void* a, long long lda, const void* b,

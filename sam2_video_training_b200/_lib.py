@@ -82,6 +82,7 @@ _SIGNATURES = {
     "sam2b200_gemm": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_longlong, c_int, c_int, c_void_p, c_void_p,
                               c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "sam2b200_gemm_debug_timeline": (c_longlong, [c_void_p, c_longlong]),
+    "sam2b200_gemm_plan": (c_int, [c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "sam2b200_gemm_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_longlong, c_int,
                                  c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_uint, c_void_p, c_void_p, c_void_p]),
     "sam2b200_fold_grads": (c_int, [c_void_p] * 11),

@@ -423,9 +423,9 @@ size_t g_dbg_cap = 0, g_dbg_used = 0;
 
 constexpr int kSmemBudget = 227 * 1024 - 1024 - gemm::kCtrlBytes;      // after the alignment slack and the control block
 
-// Shared-memory layout + grid for one problem, then the launch.  Regions (1024-aligned): B | A ring | staging | x cache.
-template <int BN, int B_MN, int MT, int EG = 1>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap* mc, gemm::Params p, cudaStream_t stream) {
+// Shared-memory layout + grid for one problem (host only; also behind sam2b200_gemm_plan, which the CPU tests sweep).
+// Regions (1024-aligned): control block | B | A ring | staging | x cache.
+int plan(gemm::Params& p, int BN, int MT, int EG, int sms, unsigned* grid_out, size_t* smem_out) {
   const int b_slice = BN * 128, a_slot = MT * gemm::kATileBytes;
   const int x_bytes = (BN == 128 && p.rope_blocks > 0 && p.rope_w > 0 && p.rope_w <= gemm::kXRows) ? ((p.rope_w * gemm::kXStride + 1023) & ~1023) : 0;
   int stage_bytes = EG * gemm::kEpiWarps * gemm::kBoxBytes;
@@ -437,7 +437,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap* mc, 
     // more than two row tiles of A in flight buy nothing: a second staging box per warp instead
     if (p.n_slots > 2 * p.ksteps + 2 && left - stage_bytes >= (2 * p.ksteps + 2) * a_slot) { p.stage_bufs = 2; stage_bytes *= 2; left -= stage_bytes / 2; p.n_slots = left / a_slot; }
   } else {
-    left = kSmemBudget - stage_bytes;
+    left = kSmemBudget - stage_bytes - x_bytes;
     p.n_slots = left / (a_slot + b_slice);
   }
   if (p.n_slots > gemm::kMaxSlots) p.n_slots = gemm::kMaxSlots;
@@ -446,9 +446,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap* mc, 
   p.off_b = gemm::kCtrlBytes; p.off_a = p.off_b + b_bytes; p.off_stage = p.off_a + p.n_slots * a_slot; p.off_x = p.off_stage + stage_bytes;
   const size_t smem = (size_t)p.off_x + x_bytes + 1024;
   if (smem > 227 * 1024) return sam2b200::fail(SAM2B200_ERR_UNSUPPORTED, "gemm: shared memory layout does not fit");
-  cudaError_t e = cudaFuncSetAttribute(gemm::gemm_kernel<BN, B_MN, MT, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e != cudaSuccess) return sam2b200::fail(SAM2B200_ERR_CUDA, cudaGetErrorString(e));
-  const int sms = sm_count(), ncb = p.n_col_blocks, groups = (p.n_row_tiles + MT - 1) / MT;
+  const int ncb = p.n_col_blocks, groups = (p.n_row_tiles + MT - 1) / MT;
   unsigned grid;
   if (p.wres) {                               // resident weights: a CTA keeps one column block, grid = CTAs per block x blocks
     int per_cb = sms / ncb < 1 ? 1 : sms / ncb;
@@ -458,6 +456,34 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap* mc, 
     const long long items = (long long)groups * ncb;
     grid = (unsigned)(items < sms ? items : sms);
   }
+  *grid_out = grid; *smem_out = smem;
+  return SAM2B200_OK;
+}
+
+// Kernel variant for a problem: column-block width, row tiles per item, epilogue groups (see the header comment).
+void choose_variant(int K, int Nout, int rope_cols, int n_row_tiles, int sms, int* bn, int* mt, int* eg) {
+  // rotated outputs: 128-column blocks = the x / y halves of a head.  SAM2B200_GEMM_BN128=1 (experiment, NOT faster: the linear1 head
+  // takes 46.7 instead of 37.3 us -- twice the A traffic from L2 outweighs the second epilogue group): 128-column blocks with two
+  // epilogue groups for every resident-weight problem wider than 256
+  static const bool bn128_all = getenv("SAM2B200_GEMM_BN128") != nullptr;
+  static const bool eg1 = getenv("SAM2B200_GEMM_EG1") != nullptr;
+  const bool wres = K / gemm::kBlockK <= 4;
+  *bn = Nout == 64 ? 64 : ((rope_cols > 0 || (bn128_all && K <= 256 && Nout > 256)) ? 128 : 256);
+  // streamed weights and more row tiles than SMs: two row tiles (two accumulators) per item share every weight slice -- the kernel
+  // is bound by L2 -> SM traffic otherwise (1 MB of weights per 128 rows at K = 2048)
+  *mt = (*bn == 256 && !wres && n_row_tiles > sms) ? 2 : 1;
+  // two epilogue groups (16 warps, four accumulators) for 128-column blocks with resident weights: the drain of a 128 x 128 accumulator
+  // is a latency chain of ~1.5 us per warp, twice the MMA time -- SAM2B200_GEMM_EG1=1 keeps one group (A/B)
+  *eg = (*bn == 128 && wres && !eg1) ? 2 : 1;
+}
+
+template <int BN, int B_MN, int MT, int EG = 1>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap* mc, gemm::Params p, cudaStream_t stream) {
+  unsigned grid;
+  size_t smem;
+  if (int rc = plan(p, BN, MT, EG, sm_count(), &grid, &smem)) return rc;
+  cudaError_t e = cudaFuncSetAttribute(gemm::gemm_kernel<BN, B_MN, MT, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return sam2b200::fail(SAM2B200_ERR_CUDA, cudaGetErrorString(e));
   if (g_dbg && g_dbg_used + (size_t)grid * 32 <= g_dbg_cap) { p.dbg = g_dbg + g_dbg_used; g_dbg_used += (size_t)grid * 32; }
   static const bool pdl = getenv("SAM2B200_NO_PDL") == nullptr;
   cudaLaunchConfig_t cfg{};
@@ -497,11 +523,8 @@ int sam2b200_gemm_ex(void* out0, void* out1, void* out2, int out_width, long lon
                      long long ldb, int b_layout, long long R, int K, int Nout, const float* bias, int rope_cols, const float* table,
                      int rows_per_item, int n_rope_rows, int period, int relu, float drop_p, const unsigned long long* drop_seed,
                      unsigned drop_site, const float* dot_rows, float* dot_out, cudaStream_t stream) {
-  // rotated outputs: 128-column blocks = the x / y halves of a head.  SAM2B200_GEMM_BN128=1 (experiment, NOT faster: the linear1 head
-  // takes 46.7 instead of 37.3 us -- twice the A traffic from L2 outweighs the second epilogue group): 128-column blocks with two
-  // epilogue groups for every resident-weight problem wider than 256
-  static const bool bn128_all = getenv("SAM2B200_GEMM_BN128") != nullptr;
-  const int bn = Nout == 64 ? 64 : ((rope_cols > 0 || (bn128_all && K <= 256 && Nout > 256)) ? 128 : 256);
+  int bn, mt, eg;
+  choose_variant(K, Nout, rope_cols, (int)((R + gemm::kBlockM - 1) / gemm::kBlockM), sm_count(), &bn, &mt, &eg);
   const int n_out = out_width > 0 ? Nout / out_width : 0;
   if (!out0 || !a || !b || R <= 0 || R > 0x7fffffffLL - 256 || K <= 0 || (K % 64) || Nout <= 0 || (Nout % bn) || Nout > 2048 ||
       out_width <= 0 || (out_width % bn) || n_out * out_width != Nout || n_out > 3 || (n_out > 1 && !out1) || (n_out > 2 && !out2) ||
@@ -529,19 +552,34 @@ int sam2b200_gemm_ex(void* out0, void* out1, void* out2, int out_width, long lon
   p.dot_rows = dot_rows; p.dot_out = dot_out;
   p.wres = p.ksteps <= 4;
   if (bn == 256) {
-    // streamed weights and more row tiles than SMs: two row tiles (two accumulators) per item share every weight slice -- the
-    // kernel is bound by L2 -> SM traffic otherwise (1 MB of weights per 128 rows at K = 2048)
-    if (!p.wres && p.n_row_tiles > sm_count()) return b_layout ? launch<256, 1, 2>(ma, mb, mc, p, stream) : launch<256, 0, 2>(ma, mb, mc, p, stream);
+    if (mt == 2) return b_layout ? launch<256, 1, 2>(ma, mb, mc, p, stream) : launch<256, 0, 2>(ma, mb, mc, p, stream);
     return b_layout ? launch<256, 1, 1>(ma, mb, mc, p, stream) : launch<256, 0, 1>(ma, mb, mc, p, stream);
   }
   if (bn == 128) {
-    // two epilogue groups (16 warps, four accumulators) when a CTA has several items: the drain of a 128 x 128 accumulator is a
-    // latency chain of ~1.5 us per warp, twice the MMA time -- SAM2B200_GEMM_EG1=1 keeps one group (A/B)
-    static const bool eg1 = getenv("SAM2B200_GEMM_EG1") != nullptr;
-    if (!eg1 && p.wres) return b_layout ? launch<128, 1, 1, 2>(ma, mb, mc, p, stream) : launch<128, 0, 1, 2>(ma, mb, mc, p, stream);
+    if (eg == 2) return b_layout ? launch<128, 1, 1, 2>(ma, mb, mc, p, stream) : launch<128, 0, 1, 2>(ma, mb, mc, p, stream);
     return b_layout ? launch<128, 1, 1>(ma, mb, mc, p, stream) : launch<128, 0, 1>(ma, mb, mc, p, stream);
   }
   return b_layout ? launch<64, 1, 1>(ma, mb, mc, p, stream) : launch<64, 0, 1>(ma, mb, mc, p, stream);
+}
+
+// Host-only: the kernel variant and shared-memory layout sam2b200_gemm_ex would use for a problem on a GPU with `sms` SMs (no device
+// needed).  out[8] = {BN, row tiles per item, epilogue groups, ring slots, staging boxes per warp, grid, resident weights (0 | 1),
+// dynamic shared memory bytes}.  Returns 0, or the error sam2b200_gemm_ex would return for the layout.
+int sam2b200_gemm_plan(long long R, int K, int Nout, int rope_cols, int period, int sms, long long* out) {
+  if (!out || R <= 0 || K <= 0 || (K % 64) || Nout <= 0 || sms <= 0 || !(Nout == 64 || Nout % 256 == 0) || Nout > 2048 || (rope_cols % 256) || rope_cols > Nout)
+    return sam2b200::fail(SAM2B200_ERR_INVALID, "gemm_plan: bad arguments");
+  int bn, mt, eg;
+  const int n_row_tiles = (int)((R + gemm::kBlockM - 1) / gemm::kBlockM);
+  choose_variant(K, Nout, rope_cols, n_row_tiles, sms, &bn, &mt, &eg);
+  gemm::Params p{};
+  p.rows = (int)R; p.n_col_blocks = Nout / bn; p.n_row_tiles = n_row_tiles; p.ksteps = K / gemm::kBlockK; p.rope_blocks = rope_cols / 128;
+  if (rope_cols > 0 && period > 0) { int w = (int)(sqrt((double)period) + 0.5); p.rope_w = (w * w == period) ? w : 0; }
+  p.wres = p.ksteps <= 4;
+  unsigned grid;
+  size_t smem;
+  if (int rc = plan(p, bn, mt, eg, sms, &grid, &smem)) return rc;
+  out[0] = bn; out[1] = mt; out[2] = eg; out[3] = p.n_slots; out[4] = p.stage_bufs; out[5] = grid; out[6] = p.wres; out[7] = (long long)smem;
+  return SAM2B200_OK;
 }
 
 // One output of width No = 256 | 64: c[R, No] = a . B (+ bias); table != NULL rotates the whole output (the memory-key projection).

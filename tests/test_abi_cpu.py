@@ -272,3 +272,30 @@ def test_segment_indicator_reproduces_the_dense_bank_position_gradient():
     got = seg.t() @ torch.cat(wk, 0)                                   # [64 segments, 64]
     assert torch.allclose(got[:ns], want_t, atol=1e-9) and torch.allclose(got[ns:ns + n_ptr], want_p, atol=1e-9)
     assert float(got[ns + n_ptr:].abs().max()) == 0.0
+
+
+def test_gemm_plan_fits_every_shape_of_the_stack_and_beyond(lib):
+    """sam2b200_gemm_plan (host only): for every (rows, K, Nout, rotation) the stack produces at BASELINE.json's configurations -- and a
+    sweep around them -- the chosen variant's shared-memory layout fits one CTA (227 KB), has at least two ring slots, and the grid
+    never exceeds the SM count; resident weights exactly when K <= 256; 128-column blocks exactly for rotated outputs."""
+    import ctypes
+    out = (ctypes.c_longlong * 8)()
+    rows = [1, 100, 576, 56 * 576, 13 * 1024, 4 * 4096, 56 * 4060, 4 * 28736, 1 << 20]
+    seen = set()
+    for r in rows:
+        for k in (64, 128, 192, 256, 768, 2048, 4096):
+            for nout, rope, period in ((64, 0, 1), (256, 0, 1), (256, 256, 576), (256, 256, 4096), (256, 256, 1000), (768, 512, 576),
+                                       (768, 512, 1024), (2048, 0, 1), (1024, 0, 1)):
+                rc = lib.sam2b200_gemm_plan(r, k, nout, rope, period, 148, out)
+                assert rc == 0, (r, k, nout, rope, lib.sam2b200_last_error())
+                bn, mt, eg, slots, bufs, grid, wres, smem = list(out)
+                assert smem <= 227 * 1024 and slots >= 2 and 1 <= grid <= 148 and bufs in (1, 2)
+                assert wres == (1 if k <= 256 else 0)
+                assert bn == (64 if nout == 64 else (128 if rope else 256))
+                assert mt == (2 if (bn == 256 and not wres and (r + 127) // 128 > 148) else 1)
+                assert eg == (2 if (bn == 128 and wres) else 1)
+                if wres:
+                    assert grid % (nout // bn) == 0          # a CTA keeps one column block
+                seen.add((bn, mt, eg, wres))
+    assert len(seen) >= 6
+    assert lib.sam2b200_gemm_plan(128, 100, 256, 0, 1, 148, out) == -1 and lib.sam2b200_gemm_plan(128, 256, 192, 0, 1, 148, out) == -1

@@ -739,8 +739,9 @@ def test_gemm_kernel(dev, r, k, no, nn):
         assert rel_l2(dot, want_dot) < 1e-5, rel_l2(dot, want_dot)
 
 
-@pytest.mark.parametrize("b,length,n_rope,grid", [(2, 136, 128, 8), (3, 100, 0, 8), (5, 4060 // 5, 576, 24)])
-def test_gemm_kernel_memory_key_projection_with_rope(dev, b, length, n_rope, grid):
+@pytest.mark.parametrize("b,length,n_rope,grid,k", [(2, 136, 128, 8, 64), (3, 100, 0, 8, 64), (5, 4060 // 5, 576, 24, 64), (2, 144, 144, 12, 768),
+                                                   (3, 4096 + 8, 4096, 64, 256)])
+def test_gemm_kernel_memory_key_projection_with_rope(dev, b, length, n_rope, grid, k):
     """sam2b200_gemm as the memory-key projection (transformer.py:278, K = 64) with bias and the axial rotation on the fp32
     accumulator; object-pointer rows (position >= n_rope) stay un-rotated (transformer.py:296-302); keys tile the table."""
     from sam2_video_training_b200 import fused_stack as fs
@@ -748,8 +749,10 @@ def test_gemm_kernel_memory_key_projection_with_rope(dev, b, length, n_rope, gri
     g = torch.Generator(device="cuda").manual_seed(length)
     period = grid * grid
     table = compute_axial_cis(dim=256, end_x=grid, end_y=grid).to(dev)
-    x = torch.randn(b * length, 64, device=dev, generator=g).to(torch.bfloat16)
-    w = (torch.randn(256, 64, device=dev, generator=g) / 8).to(torch.bfloat16)
+    # k = 64: the memory keys; k = 768: a rotated output with STREAMED weights (not used by the stack, allowed by the ABI: the layout
+    # must leave room for the table cache); k = 256 on a 64 x 64 grid: the largest cached table (1024 px)
+    x = torch.randn(b * length, k, device=dev, generator=g).to(torch.bfloat16)
+    w = (torch.randn(256, k, device=dev, generator=g) / k ** 0.5).to(torch.bfloat16)
     bias = torch.randn(256, device=dev, generator=g) * 0.1
     out = fs.gemm(x, w, bias=bias, table=table if n_rope else None, rows_per_item=length, n_rope_rows=n_rope)
     ref = (x.float() @ w.float().t() + bias).view(b, length, 256).cpu()

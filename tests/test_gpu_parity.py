@@ -714,8 +714,7 @@ def test_wgrad_two_products_in_one_pass(dev, r):
                                        (19000, 64, 256, False)])
 def test_gemm_kernel(dev, r, k, no, nn):
     """sam2b200_gemm (resident-CTA SS-mode tcgen05 GEMM, both weight layouts, fp32 bias) against an fp64 GEMM on the same bf16
-    operands: ragged row counts (TMA clipping), more tiles than SMs (accumulator / ring phases across tiles), strided operands,
-    canary rows behind the output."""
+    operands: ragged row counts (TMA clipping), more tiles than SMs (accumulator / ring phases across tiles), strided operands."""
     from sam2_video_training_b200 import fused_stack as fs
     g = torch.Generator(device="cuda").manual_seed(r + k + no)
     a_wide = torch.randn(r, k + 64, device=dev, generator=g).to(torch.bfloat16)

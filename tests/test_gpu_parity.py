@@ -738,6 +738,26 @@ def test_gemm_kernel(dev, r, k, no, nn):
         assert rel_l2(dot, want_dot) < 1e-5, rel_l2(dot, want_dot)
 
 
+@pytest.mark.parametrize("r,k,no,layout", [(200, 256, 256, 1), (33, 64, 256, 0), (700, 256, 64, 1), (2500, 2048, 256, 0), (19000, 256, 256, 0)])
+def test_gemm_kernel_writes_stay_inside_the_output(dev, r, k, no, layout):
+    """Bounds check without compute-sanitizer (closed on this pool): the C ABI writes into a caller-owned buffer with a wider row
+    stride and guard rows; TMA clipping of the ragged last row tile must leave every guard element (columns >= No, rows >= R) untouched."""
+    from sam2_video_training_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(r + k)
+    a = torch.randn(r, k, device=dev, generator=g).to(torch.bfloat16)
+    w = (torch.randn((k, no) if layout else (no, k), device=dev, generator=g) / k ** 0.5).to(torch.bfloat16)
+    ld, guard = no + 64, 160
+    buf = torch.full((r + guard, ld), 7.0, dtype=torch.bfloat16, device=dev)
+    rc = lib.sam2b200_gemm(buf.data_ptr(), ld, a.data_ptr(), k, w.data_ptr(), w.stride(0), layout, r, k, no, None, None, 1, 0, 1, None, None,
+                           torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "sam2b200_gemm")
+    torch.cuda.synchronize()
+    want = a.double() @ (w.double() if layout else w.double().t())
+    assert rel_l2(buf[:r, :no], want) < 3e-3
+    assert bool((buf[:r, no:] == 7.0).all()) and bool((buf[r:] == 7.0).all())
+
+
 @pytest.mark.parametrize("b,length,n_rope,grid,k", [(2, 136, 128, 8, 64), (3, 100, 0, 8, 64), (5, 4060 // 5, 576, 24, 64), (2, 144, 144, 12, 768),
                                                    (3, 4096 + 8, 4096, 64, 256)])
 def test_gemm_kernel_memory_key_projection_with_rope(dev, b, length, n_rope, grid, k):
